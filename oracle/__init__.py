@@ -1,0 +1,213 @@
+"""ctypes front-end of the CPU oracle (oracle/dbeel_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package (dbeel_b200/) never imports this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+BLOOM_FP = 0.01  # lsm_tree.rs:48 BLOOM_MAX_ALLOWED_ERROR
+DEFAULT_BLOOM_MIN_SIZE = 1_048_576  # mod.rs:19
+DEFAULT_TREE_CAPACITY = 8192  # mod.rs:18
+
+
+class _Run(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("data_len", C.c_uint64),
+                ("index", C.c_void_p), ("index_len", C.c_uint64)]
+
+
+class _Out(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("data_cap", C.c_uint64), ("data_len", C.c_uint64),
+                ("index", C.c_void_p), ("index_cap", C.c_uint64), ("index_len", C.c_uint64),
+                ("bloom", C.c_void_p), ("bloom_cap", C.c_uint64), ("bloom_len", C.c_uint64),
+                ("items_written", C.c_uint64)]
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "dbeel_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        L.orc_compact.restype = C.c_int
+        L.orc_compact.argtypes = [C.POINTER(_Run), C.c_uint32, C.c_int, C.c_uint64, C.c_double,
+                                  C.c_char_p, C.c_int, C.POINTER(_Out)]
+        L.orc_siphash13.restype = C.c_uint64
+        L.orc_siphash13.argtypes = [C.c_uint64, C.c_uint64, C.c_char_p, C.c_uint64]
+        L.orc_bloom_bitmap_bytes.restype = C.c_uint64
+        L.orc_bloom_bitmap_bytes.argtypes = [C.c_uint64, C.c_double]
+        L.orc_bloom_k_num.restype = C.c_uint32
+        L.orc_bloom_k_num.argtypes = [C.c_uint64, C.c_uint64]
+        L.orc_bloom_file_size.restype = C.c_uint64
+        L.orc_bloom_file_size.argtypes = [C.c_uint64, C.c_double]
+        L.orc_bloom_check.restype = C.c_int
+        L.orc_bloom_check.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p, C.c_uint64]
+        L.orc_rb_new.restype = C.c_void_p
+        L.orc_rb_new.argtypes = [C.c_uint32]
+        L.orc_rb_free.argtypes = [C.c_void_p]
+        L.orc_rb_len.restype = C.c_uint32
+        L.orc_rb_len.argtypes = [C.c_void_p]
+        L.orc_rb_clear.argtypes = [C.c_void_p]
+        L.orc_rb_set.restype = C.c_int
+        L.orc_rb_set.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_char_p]
+        L.orc_rb_shape.restype = C.c_uint32
+        L.orc_rb_shape.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.orc_rb_flush.restype = C.c_int
+        L.orc_rb_flush.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Out)]
+        L.orc_memtable_flush.restype = C.c_int
+        L.orc_memtable_flush.argtypes = [C.POINTER(_Run), C.c_uint64, C.c_uint32, C.c_int,
+                                         C.POINTER(_Out), C.POINTER(C.c_uint64)]
+        _lib = L
+    return _lib
+
+
+def _u8(a) -> np.ndarray:
+    if isinstance(a, np.ndarray):
+        assert a.dtype == np.uint8 and a.flags.c_contiguous
+        return a
+    return np.frombuffer(bytes(a), dtype=np.uint8)
+
+
+def _mk_runs(runs: Sequence[Tuple[object, object]]):
+    keep = [(_u8(d), _u8(i)) for d, i in runs]
+    arr = (_Run * max(1, len(keep)))()
+    for j, (d, i) in enumerate(keep):
+        arr[j] = _Run(d.ctypes.data, d.size, i.ctypes.data, i.size)
+    return arr, keep
+
+
+def _mk_out(data_cap: int, index_cap: int, bloom_cap: int):
+    d = np.empty(max(1, data_cap), dtype=np.uint8)
+    i = np.empty(max(1, index_cap), dtype=np.uint8)
+    b = np.empty(max(1, bloom_cap), dtype=np.uint8)
+    o = _Out(d.ctypes.data, data_cap, 0, i.ctypes.data, index_cap, 0, b.ctypes.data, bloom_cap, 0, 0)
+    return o, (d, i, b)
+
+
+class OracleError(RuntimeError):
+    pass
+
+
+def compact(runs: Sequence[Tuple[object, object]], keep_tombstones: bool,
+            bloom_min_size: int = DEFAULT_BLOOM_MIN_SIZE, seed: bytes = bytes(32),
+            emulate_page_cache: bool = False, fp: float = BLOOM_FP):
+    """LSMTree::compact merge core.  Returns (data, index, bloom|None, items_written) as
+    numpy uint8 arrays (views trimmed to the written length)."""
+    assert len(seed) == 32
+    arr, keep = _mk_runs(runs)
+    data_cap = sum(d.size for d, _ in keep)
+    index_cap = sum(i.size for _, i in keep)
+    items = sum(i.size // 16 for _, i in keep)
+    bloom_cap = lib().orc_bloom_file_size(items, fp) if items and data_cap > bloom_min_size else 0
+    out, (d, i, b) = _mk_out(data_cap, index_cap, bloom_cap)
+    rc = lib().orc_compact(arr, len(keep), int(keep_tombstones), bloom_min_size, fp, seed,
+                           int(emulate_page_cache), C.byref(out))
+    if rc:
+        raise OracleError(f"orc_compact rc={rc}")
+    bloom = b[:out.bloom_len] if out.bloom_len else None
+    return d[:out.data_len], i[:out.index_len], bloom, int(out.items_written)
+
+
+def memtable_flushes(batch: Tuple[object, object], capacity: int = DEFAULT_TREE_CAPACITY,
+                     emulate_page_cache: bool = False):
+    """Replay an arrival-ordered batch through the red-black-tree memtable, flushing every
+    time it fills (and once more for the remainder).  Returns a list of (data, index, n)."""
+    arr, keep = _mk_runs([batch])
+    d0, i0 = keep[0]
+    n = i0.size // 16
+    pos = 0
+    outs = []
+    while pos < n:
+        out, (d, i, _) = _mk_out(d0.size, i0.size, 0)
+        consumed = C.c_uint64(0)
+        rc = lib().orc_memtable_flush(arr, pos, capacity, int(emulate_page_cache), C.byref(out),
+                                      C.byref(consumed))
+        if rc:
+            raise OracleError(f"orc_memtable_flush rc={rc}")
+        outs.append((d[:out.data_len].copy(), i[:out.index_len].copy(), int(out.items_written)))
+        pos += consumed.value
+    return outs
+
+
+def siphash13(k0: int, k1: int, msg: bytes) -> int:
+    return lib().orc_siphash13(k0, k1, msg, len(msg))
+
+
+def bloom_bitmap_bytes(items: int, fp: float = BLOOM_FP) -> int:
+    return lib().orc_bloom_bitmap_bytes(items, fp)
+
+
+def bloom_k_num(bits: int, items: int) -> int:
+    return lib().orc_bloom_k_num(bits, items)
+
+
+def bloom_file_size(items: int, fp: float = BLOOM_FP) -> int:
+    return lib().orc_bloom_file_size(items, fp)
+
+
+def bloom_check(bloom_file, key: bytes) -> bool:
+    b = _u8(bloom_file)
+    r = lib().orc_bloom_check(b.ctypes.data, b.size, key, len(key))
+    if r < 0:
+        raise OracleError("malformed bloom file")
+    return bool(r)
+
+
+class RbTree:
+    """rbtree_arena::RedBlackTree<Vec<u8>, EntryValue> restatement (shape-observable)."""
+
+    def __init__(self, capacity: int):
+        self._t = lib().orc_rb_new(capacity)
+        self._keep = []
+
+    def __del__(self):
+        if getattr(self, "_t", None):
+            lib().orc_rb_free(self._t)
+            self._t = None
+
+    def __len__(self):
+        return lib().orc_rb_len(self._t)
+
+    def clear(self):
+        lib().orc_rb_clear(self._t)
+        self._keep.clear()
+
+    def set(self, key: bytes, value: bytes, ts: int = 0) -> Optional[bool]:
+        """True if an existing key was replaced, False if inserted; raises when full."""
+        k = C.create_string_buffer(key, len(key))
+        v = C.create_string_buffer(value, len(value))
+        self._keep += [k, v]
+        r = lib().orc_rb_set(self._t, k, len(key), v, len(value), int(ts).to_bytes(16, "little", signed=True))
+        if r < 0:
+            raise OracleError("ReachedCapacity")
+        return bool(r)
+
+    def shape(self):
+        buf = np.zeros(4096, dtype=np.uint8)
+        n = lib().orc_rb_shape(self._t, buf.ctypes.data, buf.size)
+        return [(int(buf[j]), int(buf[j + 1])) for j in range(0, n, 2)]
+
+    def flush(self, cap_bytes: int = 1 << 20):
+        out, (d, i, _) = _mk_out(cap_bytes, cap_bytes, 0)
+        rc = lib().orc_rb_flush(self._t, 0, C.byref(out))
+        if rc:
+            raise OracleError(f"orc_rb_flush rc={rc}")
+        return d[:out.data_len].copy(), i[:out.index_len].copy(), int(out.items_written)

@@ -1,0 +1,269 @@
+"""Pins the CPU oracle (oracle/dbeel_oracle.c) against everything the reference's own tests
+hold for the hot path plus hand-derived byte goldens and an independent model.
+
+Reference tests restated here (paths under /root/reference):
+  * src/storage_engine/lsm_tree.rs:1328-1451  get_after_compaction
+  * src/storage_engine/lsm_tree.rs:1282-1326  set_and_get_sstable (flush of 32 LE-u16 keys)
+  * src/storage_engine/lsm_tree.rs:1489-1556  entry_writer_cache_equals_disk (sizes returned)
+  * rbtree_arena/src/lib.rs:655-719           insert_int / insert_str / rotations+colouring
+The reference has no byte-level golden files; byte goldens below are derived by hand from the
+format rules (mod.rs:45-73, utils/bincode.rs:8-16, entry_writer.rs:76-86).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from dbeel_b200 import sstable
+
+from helpers import BASE_TS, assert_run_equal, model_compact, model_flush, nasty_keys, random_runs
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def u16key(n: int) -> bytes:
+    return int(n).to_bytes(2, "little")
+
+
+# ----------------------------------------------------------------------------- format goldens
+
+def test_entry_bytes_hand_derived():
+    T = 0x0102030405060708090A0B0C0D0E0F10
+    rec = sstable.encode_entry(b"\x01\x00", b"\x01\x00", T)
+    exp = bytes.fromhex("0200000000000000" "0100" "0200000000000000" "0100") + T.to_bytes(16, "little")
+    assert rec == exp and len(rec) == 36
+    d, i = sstable.build_run([(b"\x01\x00", b"\x01\x00", T), (b"\x02\x00", b"", -1)])
+    # record 0: offset 0, key_size 8+2, full_size 36 ; record 1 (tombstone): offset 36, 10, 34
+    assert bytes(i) == bytes.fromhex("0000000000000000" "0a000000" "24000000"
+                                     "2400000000000000" "0a000000" "22000000")
+    assert bytes(d[36:]) == bytes.fromhex("0200000000000000" "0200" "0000000000000000") + b"\xff" * 16
+
+
+def test_oracle_identity_on_single_run():
+    """One run, unique keys, no tombstones: compaction re-serializes every entry unchanged,
+    so output bytes == input bytes (entry_writer.rs:81-92 recomputes identical offsets)."""
+    run = sstable.build_run([(u16key(n), u16key(n) * 3, BASE_TS + n) for n in range(50)])
+    d, i, b, n = oracle.compact([run], keep_tombstones=False)
+    assert n == 50 and b is None
+    assert_run_equal((d, i), run)
+
+
+# ----------------------------------------------------------------------------- reference tests
+
+def _get_after_compaction_runs():
+    """lsm_tree.rs:1400-1432: 94 u16-LE keys (value == key) at capacity 32 -> two automatic
+    flushes, then deletes of [1,0] and [4,0], then a manual flush."""
+    writes = [(u16key(n), u16key(n), BASE_TS + n) for n in range(32 * 3 - 2)]
+    writes += [(u16key(1), b"", BASE_TS + 1000), (u16key(4), b"", BASE_TS + 1001)]
+    batch = sstable.build_run(writes)
+    return oracle.memtable_flushes(batch, capacity=32)
+
+
+def test_get_after_compaction():
+    flushed = _get_after_compaction_runs()
+    assert [n for _, _, n in flushed] == [32, 32, 32]  # (0,32),(2,32),(4,32)  :1425-1432
+    runs = [(d, i) for d, i, _ in flushed]
+    d, i, bloom, n = oracle.compact(runs, keep_tombstones=False)  # compact(&[0,2,4], 5, false)
+    assert n == 32 * 3 - 4 and bloom is None  # (5, 92)  :1381-1384
+    got = {k: v for k, v, _ in sstable.parse_run(d, i)}
+    assert got[u16key(0)] == u16key(0) and got[u16key(2)] == u16key(2) and got[u16key(10)] == u16key(10)
+    assert u16key(1) not in got and u16key(4) not in got  # :1389-1390
+    rng_iter = [v for k, v, _ in sstable.parse_run(d, i) if u16key(1) <= k < u16key(5)]
+    assert rng_iter == [u16key(2), u16key(3)]  # :1391-1397
+    # with keep_tombstones the two deletes survive as empty values (94 distinct keys)
+    d2, i2, _, n2 = oracle.compact(runs, keep_tombstones=True)
+    assert n2 == 94
+    got2 = {k: v for k, v, _ in sstable.parse_run(d2, i2)}
+    assert got2[u16key(1)] == b"" and got2[u16key(4)] == b""
+
+
+def test_set_and_get_sstable_flush():
+    writes = [(u16key(n), u16key(n), BASE_TS + n) for n in range(32)]
+    flushed = oracle.memtable_flushes(sstable.build_run(writes), capacity=32)
+    assert len(flushed) == 1 and flushed[0][2] == 32
+    ents = sstable.parse_run(flushed[0][0], flushed[0][1])
+    # Vec<u8> order of LE u16 keys: [0,0] < [1,0] < ... (all second bytes are 0 below 256)
+    assert [k for k, _, _ in ents] == [u16key(n) for n in range(32)]
+    assert all(k == v for k, v, _ in ents)
+
+
+def test_entry_writer_sizes():
+    """entry_writer_cache_equals_disk: write() returns (data_size, index_size) and the files
+    hold exactly the sum of them."""
+    ents = [(bytes([n]) * (n % 7 + 1), bytes([n]) * (n * 13 % 200), BASE_TS) for n in range(1, 120)]
+    ents.sort()
+    d, i = sstable.build_run(ents)
+    od, oi, _, n = oracle.compact([(d, i)], keep_tombstones=True, emulate_page_cache=True)
+    assert n == len(ents)
+    assert od.size == sum(32 + len(k) + len(v) for k, v, _ in ents) and oi.size == 16 * len(ents)
+    assert_run_equal((od, oi), (d, i))
+
+
+# ----------------------------------------------------------------------------- rbtree_arena
+
+def test_rbtree_insert_replace_capacity():
+    t = oracle.RbTree(2)  # insert_int, lib.rs:655-671
+    assert t.set(b"\x01", b"\x02") is False and len(t) == 1
+    assert t.set(b"\x02", b"\x04") is False and len(t) == 2
+    assert t.set(b"\x02", b"\x06") is True and len(t) == 2
+    with pytest.raises(oracle.OracleError):
+        t.set(b"\xf4", b"x")
+    d, i, n = t.flush()
+    assert sstable.parse_run(d, i) == [(b"\x01", b"\x02", 0), (b"\x02", b"\x06", 0)] and n == 2
+
+
+def test_rbtree_rotations_and_colouring():
+    """lib.rs:690-719: after inserting 8,18,5,15,17,25,40,80 the tree is
+    17(B)[ 8(R)[5(B),15(B)], 25(R)[18(B), 40(B)[-, 80(R)]] ]."""
+    t = oracle.RbTree(8)
+    for k in [8, 18, 5, 15, 17, 25, 40, 80]:
+        assert t.set(bytes([k]), b"\x00") is False
+    R, B, NIL = 0, 1, (255, 255)
+    assert t.shape() == [(17, B), (8, R), (5, B), NIL, NIL, (15, B), NIL, NIL,
+                         (25, R), (18, B), NIL, NIL, (40, B), NIL, (80, R), NIL, NIL]
+
+
+def test_memtable_flush_matches_model():
+    rng = np.random.default_rng(11)
+    pool = nasty_keys(rng, 300)
+    writes = []
+    for s in range(2000):
+        k = pool[int(rng.integers(len(pool)))]
+        v = b"" if rng.random() < 0.1 else bytes(rng.integers(0, 256, int(rng.integers(1, 30)), dtype=np.uint8))
+        writes.append((k, v, BASE_TS + s))
+    batch = sstable.build_run(writes)
+    got = oracle.memtable_flushes(batch, capacity=64)
+    exp = model_flush(batch, 64)
+    assert len(got) == len(exp) and len(got) > 3
+    for (d, i, n), e in zip(got, exp):
+        assert_run_equal((d, i), e)
+        assert n == len(e[1]) // 16
+
+
+# ----------------------------------------------------------------------------- merge semantics
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("keep", [False, True])
+def test_compact_matches_model(seed, keep):
+    rng = np.random.default_rng(seed)
+    pool = nasty_keys(rng, 400)
+    k = int(rng.integers(1, 9))
+    runs = random_runs(rng, k, [int(rng.integers(0, 300)) for _ in range(k)], pool)
+    d, i, bloom, n = oracle.compact(runs, keep_tombstones=keep)
+    exp, exp_n = model_compact(runs, keep)
+    assert n == exp_n and bloom is None
+    assert_run_equal((d, i), exp, f"seed {seed}")
+
+
+def test_tie_breaks_timestamp_then_run_position():
+    """mod.rs:75-81 + lsm_tree.rs:58-65: key, then i128 timestamp (signed!), then position."""
+    k = b"same"
+    runs = [sstable.build_run([(k, b"r0", 5)]), sstable.build_run([(k, b"r1", 5)]),
+            sstable.build_run([(k, b"r2", -7)])]
+    d, i, _, n = oracle.compact(runs, False)
+    assert n == 1 and sstable.parse_run(d, i) == [(k, b"r1", 5)]  # equal ts: later run wins
+    big = 1 << 100
+    runs = [sstable.build_run([(k, b"old-but-huge-ts", big)]), sstable.build_run([(k, b"neg", -big)])]
+    d, i, _, _ = oracle.compact(runs, False)
+    assert sstable.parse_run(d, i) == []  # 2**100 nanos is outside time's year 9999: undecodable
+
+
+def test_winning_tombstone_hides_older_value():
+    runs = [sstable.build_run([(b"a", b"v", 1), (b"b", b"v", 1)]),
+            sstable.build_run([(b"a", b"", 2)])]
+    d, i, _, n = oracle.compact(runs, False)
+    assert sstable.parse_run(d, i) == [(b"b", b"v", 1)] and n == 1
+    d, i, _, n = oracle.compact(runs, True)
+    assert sstable.parse_run(d, i) == [(b"a", b"", 2), (b"b", b"v", 1)] and n == 2
+
+
+def test_short_or_corrupt_run_ends_silently():
+    """lsm_tree.rs:1014,1063,1158-1170: any read/decode error just ends that run."""
+    a = sstable.build_run([(bytes([n]), b"A", 1) for n in range(10)])
+    b = sstable.build_run([(bytes([n]), b"B", 2) for n in range(5, 15)])
+    # truncate b's data in the middle of its 4th record: records 0..2 survive
+    cut = int.from_bytes(bytes(b[1][16 * 3:16 * 3 + 8]), "little") + 5
+    d, i, _, n = oracle.compact([a, (b[0][:cut], b[1])], False)
+    exp, en = model_compact([a, sstable.build_run([(bytes([n]), b"B", 2) for n in range(5, 8)])], False)
+    assert n == en
+    assert_run_equal((d, i), exp)
+    # a ragged index tail (not a multiple of 16) is ignored
+    d2, i2, _, n2 = oracle.compact([a, (b[0], np.concatenate([b[1], np.zeros(7, np.uint8)]))], False)
+    exp2, en2 = model_compact([a, b], False)
+    assert n2 == en2
+    assert_run_equal((d2, i2), exp2)
+    # a record whose full_size disagrees with its content is undecodable -> run ends there
+    bad_idx = b[1].copy()
+    bad_idx[16 * 2 + 12] += 1
+    d3, i3, _, n3 = oracle.compact([a, (b[0], bad_idx)], False)
+    exp3, en3 = model_compact([a, sstable.build_run([(bytes([n]), b"B", 2) for n in range(5, 7)])], False)
+    assert n3 == en3
+    assert_run_equal((d3, i3), exp3)
+
+
+def test_empty_inputs():
+    e = (np.zeros(0, np.uint8), np.zeros(0, np.uint8))
+    d, i, b, n = oracle.compact([], False)
+    assert n == 0 and d.size == 0 and i.size == 0 and b is None
+    d, i, b, n = oracle.compact([e, e], False)
+    assert n == 0 and d.size == 0
+    a = sstable.build_run([(b"", b"empty key is a key", 1), (b"\x00", b"x", 1)])
+    d, i, b, n = oracle.compact([e, a, e], False)
+    assert n == 2
+    assert_run_equal((d, i), a)
+
+
+# ----------------------------------------------------------------------------- bloom
+
+def test_siphash13_against_cpython():
+    """SipHash-1-3 core pinned on an independent implementation (CPython's hash(bytes));
+    vectors + generator script: tests/golden/gen_siphash13_cpython.py."""
+    vec = json.load(open(os.path.join(GOLDEN, "siphash13_cpython.json")))["vectors"]
+    assert len(vec) >= 64
+    for x in vec:
+        h = oracle.siphash13(x["k0"], x["k1"], bytes.fromhex(x["msg"]))
+        s = h - (1 << 64) if h >= 1 << 63 else h
+        assert (-2 if s == -1 else s) == x["hash_signed"]
+
+
+def test_bloom_sizing_matches_survey_a4():
+    """bloomfilter 1.0.12 compute_bitmap_size / optimal_k_num at the benchmark shapes."""
+    for n, nbytes, bits, k, words, fsize in [(8_000_000, 9_585_059, 76_680_472, 7, 2_396_265, 9_585_232),
+                                             (4_000_000, 4_792_530, 38_340_240, 7, 1_198_133, 4_792_704),
+                                             (65_536, 78_521, 628_168, 7, 19_631, 78_696)]:
+        assert oracle.bloom_bitmap_bytes(n) == nbytes
+        assert oracle.bloom_k_num(nbytes * 8, n) == k
+        assert nbytes * 8 == bits and (bits + 31) // 32 == words
+        assert oracle.bloom_file_size(n) == fsize
+
+
+def test_bloom_file_layout_and_membership():
+    rng = np.random.default_rng(5)
+    ents = [(b"\xb0k%015d" % n, bytes(rng.integers(0, 256, 90, dtype=np.uint8)), BASE_TS + n) for n in range(0, 6000, 2)]
+    run_a = sstable.build_run(ents[:2000])
+    run_b = sstable.build_run(ents[1000:])
+    seed = bytes(range(32))
+    d, i, bloom, n = oracle.compact([run_a, run_b], False, bloom_min_size=100_000, seed=seed)
+    assert bloom is not None and n == 3000
+    items = 2000 + 2000  # sized for the INPUT entry count (lsm_tree.rs:978-980,1028-1031)
+    nbytes = oracle.bloom_bitmap_bytes(items)
+    n_words = (nbytes * 8 + 31) // 32
+    assert bloom.size == 8 + 4 * n_words + 8 + 8 + 4 + 144
+    assert int.from_bytes(bytes(bloom[:8]), "little") == n_words
+    t = bytes(bloom[8 + 4 * n_words:])
+    assert int.from_bytes(t[0:8], "little") == nbytes * 8 and int.from_bytes(t[8:16], "little") == nbytes * 8
+    assert int.from_bytes(t[16:20], "little") == 7
+    k0 = int.from_bytes(seed[0:8], "little")
+    assert int.from_bytes(t[20:28], "little") == k0
+    assert int.from_bytes(t[20 + 24:20 + 32], "little") == k0 ^ 0x736F6D6570736575  # v0 of a fresh hasher
+    assert int.from_bytes(t[20 + 32:20 + 40], "little") == k0 ^ 0x6C7967656E657261  # then v2 (field order)
+    for k, _, _ in ents:
+        assert oracle.bloom_check(bloom, k)
+    fp = sum(oracle.bloom_check(bloom, b"\xb0k%015d" % n) for n in range(1, 6000, 2)) / 3000
+    assert fp < 0.02  # sized for 4000 at 1%, holds 3000
+    # strict '>' threshold (lsm_tree.rs:1027)
+    total = run_a[0].size + run_b[0].size
+    assert oracle.compact([run_a, run_b], False, bloom_min_size=total, seed=seed)[2] is None
+    assert oracle.compact([run_a, run_b], False, bloom_min_size=total - 1, seed=seed)[2] is not None
