@@ -1,0 +1,240 @@
+"""ctypes binding of include/dbeel_compact.h -- the same C ABI a Rust `extern "C"` block
+would bind.  There is no CPU fallback: if libdbeel_compact.so is missing or
+no sm_100 device is present, this module raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdbeel_compact.so")
+
+DBEEL_OK = 0
+ERR_NAMES = {1: "INVALID_ARG", 2: "CAPACITY", 3: "ITEM_TOO_LARGE", 4: "CUDA", 5: "NOMEM", 6: "TOO_MANY_RUNS",
+             7: "TOO_MANY_ENTRIES", 8: "UNSORTED_RUN", 9: "NO_DEVICE", 10: "BUSY"}
+ERR_UNSORTED_RUN = 8
+ERR_CAPACITY = 2
+ERR_INVALID_ARG = 1
+ERR_NO_DEVICE = 9
+FLAG_VERIFY_SORTED = 0x1
+DEFAULT_BLOOM_MIN_SIZE = 1_048_576
+DEFAULT_BLOOM_FP = 0.01
+
+EXPORTS = ["dbeel_abi_version", "dbeel_engine_create", "dbeel_engine_destroy", "dbeel_compact_bound",
+           "dbeel_compact", "dbeel_compact_device", "dbeel_flush", "dbeel_flush_device",
+           "dbeel_bloom_bitmap_bytes", "dbeel_bloom_k_num", "dbeel_bloom_file_size", "dbeel_host_alloc",
+           "dbeel_host_free", "dbeel_last_stats", "dbeel_last_error", "dbeel_strerror"]
+
+
+class Run(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("data_len", C.c_uint64), ("index", C.c_void_p), ("index_len", C.c_uint64)]
+
+
+class Out(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("data_cap", C.c_uint64), ("data_len", C.c_uint64),
+                ("index", C.c_void_p), ("index_cap", C.c_uint64), ("index_len", C.c_uint64),
+                ("bloom", C.c_void_p), ("bloom_cap", C.c_uint64), ("bloom_len", C.c_uint64),
+                ("items_written", C.c_uint64)]
+
+
+class Opts(C.Structure):
+    _fields_ = [("keep_tombstones", C.c_int32), ("flags", C.c_uint32), ("bloom_min_size", C.c_uint64),
+                ("bloom_fp", C.c_double), ("bloom_seed", C.c_char_p)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("input_bytes", C.c_uint64), ("output_bytes", C.c_uint64), ("entries_in", C.c_uint64),
+                ("entries_valid", C.c_uint64), ("entries_out", C.c_uint64), ("runs_truncated", C.c_uint32),
+                ("key_prefix_len", C.c_uint32), ("merge_passes", C.c_uint32), ("kernel_launches", C.c_uint32),
+                ("ms_total", C.c_float), ("ms_extract", C.c_float), ("ms_merge", C.c_float),
+                ("ms_resolve", C.c_float), ("ms_gather", C.c_float), ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),
+                ("gather_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class DbeelError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"dbeel error {code} ({ERR_NAMES.get(code, '?')}): {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """The loaded library.  Fails loudly when it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -m dbeel_b200._build` (needs nvcc). "
+                               "There is no CPU fallback for the compaction path.")
+        L = C.CDLL(LIB_PATH)
+        L.dbeel_abi_version.restype = C.c_int
+        L.dbeel_engine_create.restype = C.c_int
+        L.dbeel_engine_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.dbeel_engine_destroy.restype = None
+        L.dbeel_engine_destroy.argtypes = [C.c_void_p]
+        L.dbeel_compact_bound.restype = C.c_int
+        L.dbeel_compact_bound.argtypes = [C.POINTER(Run), C.c_uint32, C.POINTER(Opts)] + [C.POINTER(C.c_uint64)] * 3
+        for name in ("dbeel_compact", "dbeel_compact_device"):
+            f = getattr(L, name)
+            f.restype = C.c_int
+            f.argtypes = [C.c_void_p, C.POINTER(Run), C.c_uint32, C.POINTER(Opts), C.POINTER(Out)]
+        for name in ("dbeel_flush", "dbeel_flush_device"):
+            f = getattr(L, name)
+            f.restype = C.c_int
+            f.argtypes = [C.c_void_p, C.POINTER(Run), C.POINTER(Out)]
+        L.dbeel_bloom_bitmap_bytes.restype = C.c_uint64
+        L.dbeel_bloom_bitmap_bytes.argtypes = [C.c_uint64, C.c_double]
+        L.dbeel_bloom_k_num.restype = C.c_uint32
+        L.dbeel_bloom_k_num.argtypes = [C.c_uint64, C.c_uint64]
+        L.dbeel_bloom_file_size.restype = C.c_uint64
+        L.dbeel_bloom_file_size.argtypes = [C.c_uint64, C.c_double]
+        L.dbeel_host_alloc.restype = C.c_void_p
+        L.dbeel_host_alloc.argtypes = [C.c_uint64]
+        L.dbeel_host_free.restype = None
+        L.dbeel_host_free.argtypes = [C.c_void_p]
+        L.dbeel_last_stats.restype = C.c_int
+        L.dbeel_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.dbeel_last_error.restype = C.c_char_p
+        L.dbeel_last_error.argtypes = [C.c_void_p]
+        L.dbeel_strerror.restype = C.c_char_p
+        L.dbeel_strerror.argtypes = [C.c_int]
+        _lib = L
+    return _lib
+
+
+def _u8(a) -> np.ndarray:
+    if isinstance(a, np.ndarray):
+        if a.dtype != np.uint8 or not a.flags.c_contiguous:
+            a = np.ascontiguousarray(a, dtype=np.uint8)
+        return a
+    return np.frombuffer(bytes(a), dtype=np.uint8)
+
+
+def make_opts(keep_tombstones: bool = False, bloom_min_size: int = DEFAULT_BLOOM_MIN_SIZE,
+              bloom_fp: float = DEFAULT_BLOOM_FP, seed: Optional[bytes] = None, flags: int = 0) -> Opts:
+    if seed is not None and len(seed) != 32:
+        raise ValueError("bloom seed must be 32 bytes")
+    return Opts(int(keep_tombstones), flags, bloom_min_size, bloom_fp, seed)
+
+
+def compact_bound(runs: Sequence[Tuple[int, int]], opts: Opts) -> Tuple[int, int, int]:
+    """runs: (data_len, index_len) pairs -> (data_cap, index_cap, bloom_cap)."""
+    arr = (Run * max(1, len(runs)))()
+    for j, (dl, il) in enumerate(runs):
+        arr[j] = Run(None, dl, None, il)
+    d, i, b = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    rc = lib().dbeel_compact_bound(arr, len(runs), C.byref(opts), C.byref(d), C.byref(i), C.byref(b))
+    if rc:
+        raise DbeelError(rc, "dbeel_compact_bound")
+    return d.value, i.value, b.value
+
+
+class PinnedBuffer:
+    """dbeel_host_alloc'ed memory exposed as a numpy uint8 array."""
+
+    def __init__(self, nbytes: int):
+        self.nbytes = int(nbytes)
+        self.ptr = lib().dbeel_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise MemoryError(f"dbeel_host_alloc({nbytes})")
+        self.array = np.ctypeslib.as_array(C.cast(self.ptr, C.POINTER(C.c_uint8)), shape=(max(1, self.nbytes),))[:self.nbytes]
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().dbeel_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One compaction engine bound to one GPU (dbeel_engine_create)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        rc = lib().dbeel_engine_create(device, C.byref(self._h))
+        if rc:
+            raise DbeelError(rc, f"dbeel_engine_create({device}): {lib().dbeel_strerror(rc).decode()}")
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().dbeel_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc:
+            raise DbeelError(rc, f"{what}: {lib().dbeel_last_error(self._h).decode()}")
+
+    def stats(self) -> dict:
+        s = Stats()
+        lib().dbeel_last_stats(self._h, C.byref(s))
+        return s.as_dict()
+
+    # ---- host buffers (numpy) -------------------------------------------------------
+    def compact(self, runs: Sequence[Tuple[object, object]], keep_tombstones: bool = False,
+                bloom_min_size: int = DEFAULT_BLOOM_MIN_SIZE, seed: Optional[bytes] = None,
+                bloom_fp: float = DEFAULT_BLOOM_FP, flags: int = 0, out_buffers=None):
+        """dbeel_compact: returns (data, index, bloom|None, items_written) as numpy uint8 arrays."""
+        keep = [(_u8(d), _u8(i)) for d, i in runs]
+        arr = (Run * max(1, len(keep)))()
+        for j, (d, i) in enumerate(keep):
+            arr[j] = Run(d.ctypes.data, d.size, i.ctypes.data, i.size)
+        opts = make_opts(keep_tombstones, bloom_min_size, bloom_fp, seed, flags)
+        dc, ic, bc = compact_bound([(d.size, i.size) for d, i in keep], opts)
+        if out_buffers is None:
+            od, oi, ob = (np.empty(max(1, dc), np.uint8), np.empty(max(1, ic), np.uint8), np.empty(max(1, bc), np.uint8))
+        else:
+            od, oi, ob = out_buffers
+        out = Out(od.ctypes.data, dc, 0, oi.ctypes.data, ic, 0, ob.ctypes.data if bc else None, bc, 0, 0)
+        self._check(lib().dbeel_compact(self._h, arr, len(keep), C.byref(opts), C.byref(out)), "dbeel_compact")
+        bloom = ob[:out.bloom_len] if out.bloom_len else None
+        return od[:out.data_len], oi[:out.index_len], bloom, int(out.items_written)
+
+    def flush(self, batch: Tuple[object, object]):
+        """dbeel_flush: returns (data, index, items_written)."""
+        d, i = _u8(batch[0]), _u8(batch[1])
+        run = Run(d.ctypes.data, d.size, i.ctypes.data, i.size)
+        od, oi = np.empty(max(1, d.size), np.uint8), np.empty(max(1, i.size), np.uint8)
+        out = Out(od.ctypes.data, d.size, 0, oi.ctypes.data, i.size // 16 * 16, 0, None, 0, 0, 0)
+        self._check(lib().dbeel_flush(self._h, C.byref(run), C.byref(out)), "dbeel_flush")
+        return od[:out.data_len], oi[:out.index_len], int(out.items_written)
+
+    # ---- device buffers (raw pointers; torch tensors own the memory) -------------------
+    def compact_device(self, runs: Sequence[Tuple[int, int, int, int]], out_ptrs: Tuple[int, int, int, int, int, int],
+                       opts: Opts) -> Tuple[int, int, int, int]:
+        """runs: (data_ptr, data_len, index_ptr, index_len); out_ptrs: (data_ptr, data_cap,
+        index_ptr, index_cap, bloom_ptr, bloom_cap).  Returns (data_len, index_len, bloom_len, items)."""
+        arr = (Run * max(1, len(runs)))()
+        for j, (dp, dl, ip, il) in enumerate(runs):
+            arr[j] = Run(dp, dl, ip, il)
+        dp, dc, ip, ic, bp, bc = out_ptrs
+        out = Out(dp, dc, 0, ip, ic, 0, bp if bc else None, bc, 0, 0)
+        self._check(lib().dbeel_compact_device(self._h, arr, len(runs), C.byref(opts), C.byref(out)),
+                    "dbeel_compact_device")
+        return int(out.data_len), int(out.index_len), int(out.bloom_len), int(out.items_written)
+
+    def flush_device(self, batch: Tuple[int, int, int, int], out_ptrs: Tuple[int, int, int, int]):
+        run = Run(*batch)
+        dp, dc, ip, ic = out_ptrs
+        out = Out(dp, dc, 0, ip, ic, 0, None, 0, 0, 0)
+        self._check(lib().dbeel_flush_device(self._h, C.byref(run), C.byref(out)), "dbeel_flush_device")
+        return int(out.data_len), int(out.index_len), int(out.items_written)

@@ -1,0 +1,559 @@
+// dbeel_compact.cu -- engine + C ABI (include/dbeel_compact.h) over the kernels in kernels.cuh.
+//
+// One engine = one GPU + one stream + a grow-only device workspace.  A compaction job is a
+// fixed sequence of kernel launches with no host round trip in between; the only host sync
+// is the final read-back of the 300-byte control block (output lengths, flags).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/dbeel_compact.h"
+#include "kernels.cuh"
+
+using namespace dbeel;
+
+namespace {
+
+constexpr uint64_t kAlign = 256;
+inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+enum { EV_START = 0, EV_EXTRACT, EV_MERGE, EV_RESOLVE, EV_GATHER, EV_H2D0, EV_H2D1, EV_D2H0, EV_D2H1, EV_COUNT };
+
+} // namespace
+
+struct dbeel_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[EV_COUNT] = {};
+    // device workspace (grow-only)
+    uint8_t *ws = nullptr;
+    uint64_t ws_cap = 0;
+    // device staging for the host entry points (grow-only)
+    uint8_t *stage_in = nullptr, *stage_out = nullptr;
+    uint64_t stage_in_cap = 0, stage_out_cap = 0;
+    // pinned host block: job header going down, control block coming back
+    uint8_t *pin = nullptr;
+    uint64_t pin_cap = 0;
+    dbeel_stats stats = {};
+    std::string err;
+    bool busy = false;
+};
+
+namespace {
+
+int fail(dbeel_engine *e, int code, const char *what, cudaError_t ce = cudaSuccess) {
+    char buf[512];
+    if (ce != cudaSuccess)
+        snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorName(ce), cudaGetErrorString(ce));
+    else
+        snprintf(buf, sizeof buf, "%s", what);
+    if (e) e->err = buf;
+    return code;
+}
+
+#define CU(call)                                                            \
+    do {                                                                    \
+        cudaError_t ce_ = (call);                                           \
+        if (ce_ != cudaSuccess) return fail(e, DBEEL_ERR_CUDA, #call, ce_); \
+    } while (0)
+
+int ensure_device(dbeel_engine *e, uint8_t **buf, uint64_t *cap, uint64_t need) {
+    if (need <= *cap) return DBEEL_OK;
+    if (*buf) { cudaFree(*buf); *buf = nullptr; *cap = 0; }
+    uint64_t want = align_up(need + need / 8, 1 << 20);
+    cudaError_t ce = cudaMalloc(reinterpret_cast<void **>(buf), want);
+    if (ce != cudaSuccess) {
+        cudaGetLastError();
+        want = align_up(need, 1 << 20);
+        ce = cudaMalloc(reinterpret_cast<void **>(buf), want);
+    }
+    if (ce != cudaSuccess) { cudaGetLastError(); return fail(e, DBEEL_ERR_NOMEM, "cudaMalloc(workspace)", ce); }
+    *cap = want;
+    return DBEEL_OK;
+}
+
+int ensure_pinned(dbeel_engine *e, uint64_t need) {
+    if (need <= e->pin_cap) return DBEEL_OK;
+    if (e->pin) cudaFreeHost(e->pin);
+    e->pin = nullptr;
+    e->pin_cap = 0;
+    cudaError_t ce = cudaHostAlloc(reinterpret_cast<void **>(&e->pin), need, cudaHostAllocDefault);
+    if (ce != cudaSuccess) { cudaGetLastError(); return fail(e, DBEEL_ERR_NOMEM, "cudaHostAlloc", ce); }
+    e->pin_cap = need;
+    return DBEEL_OK;
+}
+
+void default_opts(dbeel_compact_opts *o) {
+    o->keep_tombstones = 0;
+    o->flags = 0;
+    o->bloom_min_size = DBEEL_DEFAULT_BLOOM_MIN_SIZE;
+    o->bloom_fp = DBEEL_DEFAULT_BLOOM_FP;
+    o->bloom_seed = nullptr;
+}
+
+struct JobShape {
+    uint64_t n_total = 0; // sum of index_len / 16
+    uint64_t data_total = 0;
+    uint64_t index_total = 0; // sum of index_len (raw)
+    uint64_t bloom_file = 0;  // 0 = no bloom
+    uint64_t bloom_bits = 0, bloom_words = 0;
+    uint32_t bloom_k = 0;
+};
+
+int shape_of(const dbeel_run *runs, uint32_t n_runs, const dbeel_compact_opts *o, bool flush, JobShape *s) {
+    for (uint32_t r = 0; r < n_runs; r++) {
+        s->n_total += runs[r].index_len / DBEEL_INDEX_ENTRY_SIZE;
+        s->data_total += runs[r].data_len;
+        s->index_total += runs[r].index_len;
+    }
+    // lsm_tree.rs:1026-1034: sized for the INPUT entry count, enabled on input .data bytes
+    if (!flush && s->n_total > 0 && s->data_total > o->bloom_min_size) {
+        uint64_t bytes = dbeel_bloom_bitmap_bytes(s->n_total, o->bloom_fp);
+        s->bloom_bits = bytes * 8;
+        s->bloom_words = (s->bloom_bits + 31) / 32;
+        s->bloom_k = dbeel_bloom_k_num(s->bloom_bits, s->n_total);
+        s->bloom_file = 8 + 4 * s->bloom_words + 8 + 8 + 4 + 144;
+    }
+    return DBEEL_OK;
+}
+
+// The whole device-resident job.  `runs` / `out` hold device pointers.
+int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, const dbeel_compact_opts *o,
+                   bool flush, dbeel_out *out, bool record_start) {
+    JobShape sh;
+    shape_of(runs, n_runs, o, flush, &sh);
+    if (n_runs > DBEEL_MAX_RUNS) return fail(e, DBEEL_ERR_TOO_MANY_RUNS, "too many runs");
+    if (sh.n_total >= 0xFFFFFFFEull) return fail(e, DBEEL_ERR_TOO_MANY_ENTRIES, "too many entries");
+    if (out->data_cap < sh.data_total || out->index_cap < sh.n_total * 16 || out->bloom_cap < sh.bloom_file)
+        return fail(e, DBEEL_ERR_CAPACITY, "output buffer smaller than dbeel_compact_bound");
+    for (uint32_t r = 0; r < n_runs; r++) {
+        if ((runs[r].data_len && !runs[r].data) || (runs[r].index_len >= 16 && !runs[r].index))
+            return fail(e, DBEEL_ERR_INVALID_ARG, "null run buffer");
+        if (((uintptr_t)runs[r].data | (uintptr_t)runs[r].index) & 15)
+            return fail(e, DBEEL_ERR_INVALID_ARG, "device run buffers must be 16-byte aligned");
+    }
+    if (((uintptr_t)out->data | (uintptr_t)out->index | (uintptr_t)out->bloom) & 15)
+        return fail(e, DBEEL_ERR_INVALID_ARG, "device output buffers must be 16-byte aligned");
+    if ((sh.data_total && !out->data) || (sh.n_total && !out->index) || (sh.bloom_file && !out->bloom))
+        return fail(e, DBEEL_ERR_INVALID_ARG, "null output buffer");
+
+    dbeel_stats &st = e->stats;
+    float h2d = st.ms_h2d; // set by the host wrapper before we get here
+    memset(&st, 0, sizeof st);
+    st.ms_h2d = h2d;
+    st.input_bytes = sh.data_total + sh.index_total;
+    st.entries_in = sh.n_total;
+    out->data_len = out->index_len = out->bloom_len = out->items_written = 0;
+
+    const uint32_t N = (uint32_t)sh.n_total;
+    if (N == 0) return DBEEL_OK; // nothing decodable: empty output, no bloom
+
+    // ---- plan the levels
+    Params p;
+    memset(&p, 0, sizeof p);
+    p.n_runs = n_runs;
+    p.n_total = N;
+    p.keep_tombstones = o->keep_tombstones ? 1 : 0;
+    p.mode_flush = flush ? 1 : 0;
+    uint32_t levels = 0;
+    p.nseg[0] = n_runs;
+    while (p.nseg[levels] > 1) {
+        p.nseg[levels + 1] = (p.nseg[levels] + 1) / 2;
+        levels++;
+    }
+    p.n_levels = levels;
+
+    // ---- carve the workspace
+    uint64_t off = 0;
+    auto carve = [&](uint64_t bytes) { uint64_t o2 = off; off = align_up(off + bytes, kAlign); return o2; };
+    // header block (host-initialised, one H2D copy): ctl | runs | first_bad | first_mismatch
+    const uint64_t o_ctl = carve(sizeof(Ctl));
+    const uint64_t o_runs = carve(sizeof(RunDesc) * n_runs);
+    const uint64_t o_fbad = carve(4ull * n_runs);
+    const uint64_t o_fmis = carve(4ull * n_runs);
+    const uint64_t header_bytes = off;
+    uint64_t o_seg[kMaxLevels + 1], o_tb[kMaxLevels];
+    for (uint32_t l = 0; l <= levels; l++) o_seg[l] = carve(sizeof(Seg) * p.nseg[l]);
+    for (uint32_t l = 0; l < levels; l++) o_tb[l] = carve(4ull * (p.nseg[l + 1] + 1));
+    const uint64_t tiles_ub = (uint64_t)(N + kMergeTile - 1) / kMergeTile + (n_runs + 1) / 2;
+    const uint64_t bounds_ub = tiles_ub + (n_runs + 1) / 2 + 1;
+    const uint64_t o_part = carve(4 * bounds_ub);
+    const uint64_t scan_tiles = (uint64_t)(N + kResolveThreads - 1) / kResolveThreads;
+    const uint64_t o_scan = carve(scan_tiles * 4); // status (zeroed per job)
+    const uint64_t o_aggb = carve(scan_tiles * 8), o_incb = carve(scan_tiles * 8);
+    const uint64_t o_aggc = carve(scan_tiles * 4), o_incc = carve(scan_tiles * 4);
+    const uint64_t o_reca = carve(16ull * N), o_recb = carve(levels ? 16ull * N : 0);
+    const uint64_t o_src = carve(8ull * N);
+    int rc = ensure_device(e, &e->ws, &e->ws_cap, off);
+    if (rc) return rc;
+    rc = ensure_pinned(e, header_bytes + sizeof(Ctl) + 64);
+    if (rc) return rc;
+
+    uint8_t *ws = e->ws;
+    p.ctl = reinterpret_cast<Ctl *>(ws + o_ctl);
+    p.runs = reinterpret_cast<RunDesc *>(ws + o_runs);
+    p.first_bad = reinterpret_cast<uint32_t *>(ws + o_fbad);
+    p.first_mismatch = reinterpret_cast<uint32_t *>(ws + o_fmis);
+    for (uint32_t l = 0; l <= levels; l++) p.seg[l] = reinterpret_cast<Seg *>(ws + o_seg[l]);
+    for (uint32_t l = 0; l < levels; l++) p.tile_base[l] = reinterpret_cast<uint32_t *>(ws + o_tb[l]);
+    p.part = reinterpret_cast<uint32_t *>(ws + o_part);
+    p.scan_status = reinterpret_cast<uint32_t *>(ws + o_scan);
+    p.scan_agg_bytes = reinterpret_cast<unsigned long long *>(ws + o_aggb);
+    p.scan_inc_bytes = reinterpret_cast<unsigned long long *>(ws + o_incb);
+    p.scan_agg_cnt = reinterpret_cast<uint32_t *>(ws + o_aggc);
+    p.scan_inc_cnt = reinterpret_cast<uint32_t *>(ws + o_incc);
+    p.rec_a = reinterpret_cast<Rec *>(ws + o_reca);
+    p.rec_b = reinterpret_cast<Rec *>(ws + o_recb);
+    p.src_ptr = reinterpret_cast<unsigned long long *>(ws + o_src);
+    p.out_data = static_cast<uint8_t *>(out->data);
+    p.out_index = static_cast<uint4 *>(out->index);
+
+    // ---- header block
+    uint8_t *h = e->pin;
+    memset(h, 0, header_bytes);
+    RunDesc *hr = reinterpret_cast<RunDesc *>(h + o_runs);
+    uint32_t *hb = reinterpret_cast<uint32_t *>(h + o_fbad), *hm = reinterpret_cast<uint32_t *>(h + o_fmis);
+    uint32_t base = 0;
+    for (uint32_t r = 0; r < n_runs; r++) {
+        hr[r].data = static_cast<const uint8_t *>(runs[r].data);
+        hr[r].data_len = runs[r].data_len;
+        hr[r].index = static_cast<const uint4 *>(runs[r].index);
+        hr[r].n_in = (uint32_t)(runs[r].index_len / DBEEL_INDEX_ENTRY_SIZE);
+        hr[r].base = base;
+        hb[r] = hr[r].n_in;
+        hm[r] = 0xFFFFFFFFu;
+        base += hr[r].n_in;
+    }
+
+    // ---- bloom
+    uint8_t seed[32];
+    if (sh.bloom_file) {
+        if (o->bloom_seed) {
+            memcpy(seed, o->bloom_seed, 32);
+        } else { // Bloom::new -> getrandom(&mut seed)
+            FILE *f = fopen("/dev/urandom", "rb");
+            if (!f || fread(seed, 1, 32, f) != 32) {
+                if (f) fclose(f);
+                return fail(e, DBEEL_ERR_INVALID_ARG, "no entropy source for the bloom seed");
+            }
+            fclose(f);
+        }
+        p.bloom.words = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(out->bloom) + 8);
+        p.bloom.bits = sh.bloom_bits;
+        p.bloom.bits_magic = (uint64_t)((((unsigned __int128)1) << 64) / sh.bloom_bits);
+        p.bloom.k_num = sh.bloom_k;
+        for (int i = 0; i < 4; i++) memcpy(&p.bloom.sip[i], seed + 8 * i, 8);
+    }
+
+    cudaStream_t s = e->stream;
+    uint32_t launches = 0;
+    CU(cudaMemcpyAsync(ws, h, header_bytes, cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(ws + o_scan, 0, scan_tiles * 4, s));
+    if (sh.bloom_file) CU(cudaMemsetAsync(out->bloom, 0, sh.bloom_file, s));
+    if (record_start) CU(cudaEventRecord(e->ev[EV_START], s));
+
+    // ---- K0/K1: prefix, validate, extract (+ conditional redo when a run was truncated)
+    const uint32_t g256 = (N + 255) / 256;
+    k_common_prefix<<<1, 32, 0, s>>>(p, 0);
+    k_extract<<<g256, 256, 0, s>>>(p, 0);
+    k_common_prefix<<<1, 32, 0, s>>>(p, 1);
+    k_extract<<<g256, 256, 0, s>>>(p, 1);
+    k_plan<<<1, 1, 0, s>>>(p);
+    launches += 5;
+    if (o->flags & DBEEL_FLAG_VERIFY_SORTED) {
+        k_verify_sorted<<<g256, 256, 0, s>>>(p);
+        launches++;
+    }
+    CU(cudaEventRecord(e->ev[EV_EXTRACT], s));
+
+    // ---- K2/K3: merge levels, ping-pong between rec_a and rec_b
+    const Rec *src = p.rec_a;
+    Rec *dst = p.rec_b;
+    for (uint32_t l = 0; l < levels; l++) {
+        uint32_t pairs = p.nseg[l + 1];
+        uint64_t t_ub = (uint64_t)(N + kMergeTile - 1) / kMergeTile + pairs;
+        uint64_t b_ub = t_ub + pairs;
+        k_merge_partition<<<(uint32_t)((b_ub + 127) / 128), 128, 0, s>>>(p, l, src);
+        k_merge<<<(uint32_t)t_ub, kMergeThreads, 0, s>>>(p, l, src, dst);
+        launches += 2;
+        const Rec *t = src;
+        src = dst;
+        dst = const_cast<Rec *>(t);
+    }
+    CU(cudaEventRecord(e->ev[EV_MERGE], s));
+
+    // ---- K4: resolve + scan + .index
+    k_resolve<<<(uint32_t)scan_tiles, kResolveThreads, 0, s>>>(p, src);
+    launches++;
+    CU(cudaEventRecord(e->ev[EV_RESOLVE], s));
+
+    // ---- K5: gather + bloom
+    if (sh.bloom_file) {
+        k_bloom_frame<<<1, 1, 0, s>>>(static_cast<uint8_t *>(out->bloom), sh.bloom_words, p.bloom);
+        launches++;
+    }
+    k_gather<<<(N + kGatherEntries - 1) / kGatherEntries, kGatherThreads, 0, s>>>(p);
+    launches++;
+    CU(cudaEventRecord(e->ev[EV_GATHER], s));
+    CU(cudaGetLastError());
+
+    // ---- control block back
+    Ctl *hc = reinterpret_cast<Ctl *>(e->pin + header_bytes);
+    CU(cudaMemcpyAsync(hc, p.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+
+    st.kernel_launches = launches;
+    st.merge_passes = levels;
+    st.key_prefix_len = hc->prefix_len;
+    st.entries_valid = hc->total;
+    st.runs_truncated = hc->runs_truncated;
+    if (record_start) cudaEventElapsedTime(&st.ms_total, e->ev[EV_START], e->ev[EV_GATHER]);
+    if (record_start) cudaEventElapsedTime(&st.ms_extract, e->ev[EV_START], e->ev[EV_EXTRACT]);
+    cudaEventElapsedTime(&st.ms_merge, e->ev[EV_EXTRACT], e->ev[EV_MERGE]);
+    cudaEventElapsedTime(&st.ms_resolve, e->ev[EV_MERGE], e->ev[EV_RESOLVE]);
+    cudaEventElapsedTime(&st.ms_gather, e->ev[EV_RESOLVE], e->ev[EV_GATHER]);
+    if (hc->flags & (kFlagUnsorted | kFlagVerifyFailed))
+        return fail(e, DBEEL_ERR_UNSORTED_RUN, "an input run is not strictly ascending by key");
+
+    out->data_len = hc->out_data_len;
+    out->items_written = hc->out_items;
+    out->index_len = (uint64_t)hc->out_items * 16;
+    out->bloom_len = sh.bloom_file;
+    st.entries_out = hc->out_items;
+    st.output_bytes = out->data_len + out->index_len + out->bloom_len;
+    st.gather_bytes = 2 * out->data_len + out->index_len + 8ull * hc->out_items; // read + write payload, read index + src_ptr
+    return DBEEL_OK;
+}
+
+// host buffers in / out around run_job_device
+int run_job_host(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, const dbeel_compact_opts *o, bool flush,
+                 dbeel_out *out) {
+    JobShape sh;
+    shape_of(runs, n_runs, o, flush, &sh);
+    if (n_runs > DBEEL_MAX_RUNS) return fail(e, DBEEL_ERR_TOO_MANY_RUNS, "too many runs");
+    if (out->data_cap < sh.data_total || out->index_cap < sh.n_total * 16 || out->bloom_cap < sh.bloom_file)
+        return fail(e, DBEEL_ERR_CAPACITY, "output buffer smaller than dbeel_compact_bound");
+    for (uint32_t r = 0; r < n_runs; r++)
+        if ((runs[r].data_len && !runs[r].data) || (runs[r].index_len && !runs[r].index))
+            return fail(e, DBEEL_ERR_INVALID_ARG, "null run buffer");
+
+    // device staging: every buffer 256-aligned with 16 bytes of slack behind it
+    uint64_t in_need = 0;
+    for (uint32_t r = 0; r < n_runs; r++)
+        in_need += align_up(runs[r].data_len + 16, kAlign) + align_up(runs[r].index_len + 16, kAlign);
+    uint64_t out_need = align_up(sh.data_total + 16, kAlign) + align_up(sh.n_total * 16 + 16, kAlign) +
+                        align_up(sh.bloom_file + 16, kAlign);
+    int rc = ensure_device(e, &e->stage_in, &e->stage_in_cap, in_need);
+    if (rc) return rc;
+    rc = ensure_device(e, &e->stage_out, &e->stage_out_cap, out_need);
+    if (rc) return rc;
+
+    cudaStream_t s = e->stream;
+    std::vector<dbeel_run> dr(n_runs);
+    CU(cudaEventRecord(e->ev[EV_H2D0], s));
+    uint64_t off = 0;
+    for (uint32_t r = 0; r < n_runs; r++) {
+        dr[r].data = e->stage_in + off;
+        dr[r].data_len = runs[r].data_len;
+        if (runs[r].data_len)
+            CU(cudaMemcpyAsync(e->stage_in + off, runs[r].data, runs[r].data_len, cudaMemcpyHostToDevice, s));
+        off += align_up(runs[r].data_len + 16, kAlign);
+        dr[r].index = e->stage_in + off;
+        dr[r].index_len = runs[r].index_len;
+        if (runs[r].index_len)
+            CU(cudaMemcpyAsync(e->stage_in + off, runs[r].index, runs[r].index_len, cudaMemcpyHostToDevice, s));
+        off += align_up(runs[r].index_len + 16, kAlign);
+    }
+    CU(cudaEventRecord(e->ev[EV_H2D1], s));
+    CU(cudaEventRecord(e->ev[EV_START], s));
+
+    dbeel_out dout = *out;
+    dout.data = e->stage_out;
+    dout.index = e->stage_out + align_up(sh.data_total + 16, kAlign);
+    dout.bloom = sh.bloom_file ? static_cast<uint8_t *>(dout.index) + align_up(sh.n_total * 16 + 16, kAlign) : nullptr;
+    rc = run_job_device(e, dr.data(), n_runs, o, flush, &dout, /*record_start=*/false);
+    // run_job_device zeroes stats; its START event is ours
+    if (rc) return rc;
+    dbeel_stats &st = e->stats;
+    if (sh.n_total) {
+        cudaEventElapsedTime(&st.ms_h2d, e->ev[EV_H2D0], e->ev[EV_H2D1]);
+        cudaEventElapsedTime(&st.ms_total, e->ev[EV_START], e->ev[EV_GATHER]);
+        cudaEventElapsedTime(&st.ms_extract, e->ev[EV_START], e->ev[EV_EXTRACT]);
+    }
+    CU(cudaEventRecord(e->ev[EV_D2H0], s));
+    if (dout.data_len) CU(cudaMemcpyAsync(out->data, dout.data, dout.data_len, cudaMemcpyDeviceToHost, s));
+    if (dout.index_len) CU(cudaMemcpyAsync(out->index, dout.index, dout.index_len, cudaMemcpyDeviceToHost, s));
+    if (dout.bloom_len) CU(cudaMemcpyAsync(out->bloom, dout.bloom, dout.bloom_len, cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(e->ev[EV_D2H1], s));
+    CU(cudaStreamSynchronize(s));
+    cudaEventElapsedTime(&st.ms_d2h, e->ev[EV_D2H0], e->ev[EV_D2H1]);
+    out->data_len = dout.data_len;
+    out->index_len = dout.index_len;
+    out->bloom_len = dout.bloom_len;
+    out->items_written = dout.items_written;
+    return DBEEL_OK;
+}
+
+struct BusyGuard {
+    dbeel_engine *e;
+    explicit BusyGuard(dbeel_engine *e_) : e(e_) { e->busy = true; }
+    ~BusyGuard() { e->busy = false; }
+};
+
+int entry(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, const dbeel_compact_opts *opts, dbeel_out *out,
+          bool flush, bool device) {
+    if (!e) return DBEEL_ERR_INVALID_ARG;
+    if (!out || (n_runs && !runs)) return fail(e, DBEEL_ERR_INVALID_ARG, "null argument");
+    if (e->busy) return fail(e, DBEEL_ERR_BUSY, "engine busy");
+    BusyGuard g(e);
+    e->err.clear();
+    dbeel_compact_opts o;
+    default_opts(&o);
+    if (opts) o = *opts;
+    if (!(o.bloom_fp > 0.0 && o.bloom_fp < 1.0)) return fail(e, DBEEL_ERR_INVALID_ARG, "bloom_fp must be in (0,1)");
+    cudaError_t ce = cudaSetDevice(e->device);
+    if (ce != cudaSuccess) return fail(e, DBEEL_ERR_CUDA, "cudaSetDevice", ce);
+    e->stats.ms_h2d = 0;
+    return device ? run_job_device(e, runs, n_runs, &o, flush, out, true) : run_job_host(e, runs, n_runs, &o, flush, out);
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------ C ABI
+
+extern "C" {
+
+int dbeel_abi_version(void) { return DBEEL_ABI_VERSION; }
+
+int dbeel_engine_create(int device, dbeel_engine **out) {
+    if (!out) return DBEEL_ERR_INVALID_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+        cudaGetLastError();
+        return DBEEL_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return DBEEL_ERR_CUDA;
+    if (prop.major != 10) return DBEEL_ERR_NO_DEVICE; // sm_100a SASS only: no fallback path
+    if (cudaSetDevice(device) != cudaSuccess) return DBEEL_ERR_CUDA;
+    dbeel_engine *e = new (std::nothrow) dbeel_engine();
+    if (!e) return DBEEL_ERR_NOMEM;
+    e->device = device;
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return DBEEL_ERR_CUDA; }
+    for (int i = 0; i < EV_COUNT; i++)
+        if (cudaEventCreate(&e->ev[i]) != cudaSuccess) { dbeel_engine_destroy(e); return DBEEL_ERR_CUDA; }
+    *out = e;
+    return DBEEL_OK;
+}
+
+void dbeel_engine_destroy(dbeel_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (int i = 0; i < EV_COUNT; i++)
+        if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    if (e->ws) cudaFree(e->ws);
+    if (e->stage_in) cudaFree(e->stage_in);
+    if (e->stage_out) cudaFree(e->stage_out);
+    if (e->pin) cudaFreeHost(e->pin);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+// Bloom::compute_bitmap_size (bloomfilter 1.0.12): ceil(n * ln(p) / (-8 * ln2^2)) in f64
+uint64_t dbeel_bloom_bitmap_bytes(uint64_t items, double fp) {
+    const double ln2 = 0.693147180559945309417232121458176568; // core::f64::consts::LN_2
+    return (uint64_t)ceil((double)items * log(fp) / (-8.0 * (ln2 * ln2)));
+}
+
+// Bloom::optimal_k_num: max(1, ceil(m / n * ln(2.0)))
+uint32_t dbeel_bloom_k_num(uint64_t bitmap_bits, uint64_t items) {
+    uint32_t k = (uint32_t)ceil((double)bitmap_bits / (double)items * log(2.0));
+    return k < 1 ? 1 : k;
+}
+
+uint64_t dbeel_bloom_file_size(uint64_t items, double fp) {
+    uint64_t bits = dbeel_bloom_bitmap_bytes(items, fp) * 8;
+    return 8 + 4 * ((bits + 31) / 32) + 8 + 8 + 4 + 144;
+}
+
+int dbeel_compact_bound(const dbeel_run *runs, uint32_t n_runs, const dbeel_compact_opts *opts, uint64_t *data_cap,
+                        uint64_t *index_cap, uint64_t *bloom_cap) {
+    if (n_runs && !runs) return DBEEL_ERR_INVALID_ARG;
+    dbeel_compact_opts o;
+    default_opts(&o);
+    if (opts) o = *opts;
+    if (!(o.bloom_fp > 0.0 && o.bloom_fp < 1.0)) return DBEEL_ERR_INVALID_ARG;
+    JobShape sh;
+    shape_of(runs, n_runs, &o, false, &sh);
+    if (data_cap) *data_cap = sh.data_total;
+    if (index_cap) *index_cap = sh.n_total * 16;
+    if (bloom_cap) *bloom_cap = sh.bloom_file;
+    return DBEEL_OK;
+}
+
+int dbeel_compact(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, const dbeel_compact_opts *opts,
+                  dbeel_out *out) {
+    return entry(e, runs, n_runs, opts, out, false, false);
+}
+
+int dbeel_compact_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, const dbeel_compact_opts *opts,
+                         dbeel_out *out) {
+    return entry(e, runs, n_runs, opts, out, false, true);
+}
+
+int dbeel_flush(dbeel_engine *e, const dbeel_run *batch, dbeel_out *out) {
+    return entry(e, batch, batch ? 1 : 0, nullptr, out, true, false);
+}
+
+int dbeel_flush_device(dbeel_engine *e, const dbeel_run *batch, dbeel_out *out) {
+    return entry(e, batch, batch ? 1 : 0, nullptr, out, true, true);
+}
+
+void *dbeel_host_alloc(uint64_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void dbeel_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+int dbeel_last_stats(const dbeel_engine *e, dbeel_stats *out) {
+    if (!e || !out) return DBEEL_ERR_INVALID_ARG;
+    *out = e->stats;
+    return DBEEL_OK;
+}
+
+const char *dbeel_last_error(const dbeel_engine *e) { return e ? e->err.c_str() : "null engine"; }
+
+const char *dbeel_strerror(int code) {
+    switch (code) {
+    case DBEEL_OK: return "ok";
+    case DBEEL_ERR_INVALID_ARG: return "invalid argument";
+    case DBEEL_ERR_CAPACITY: return "output buffer too small";
+    case DBEEL_ERR_ITEM_TOO_LARGE: return "item too large";
+    case DBEEL_ERR_CUDA: return "CUDA error";
+    case DBEEL_ERR_NOMEM: return "out of memory";
+    case DBEEL_ERR_TOO_MANY_RUNS: return "too many runs";
+    case DBEEL_ERR_TOO_MANY_ENTRIES: return "too many entries";
+    case DBEEL_ERR_UNSORTED_RUN: return "input run not strictly ascending";
+    case DBEEL_ERR_NO_DEVICE: return "no sm_100 CUDA device";
+    case DBEEL_ERR_BUSY: return "engine busy";
+    default: return "unknown error";
+    }
+}
+
+} // extern "C"

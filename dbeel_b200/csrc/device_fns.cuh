@@ -1,0 +1,199 @@
+// device_fns.cuh -- the scalar building blocks of the compaction kernels.
+//
+// Everything here is free of CUDA-only types: nvcc compiles it as `__device__` code, and
+// g++ compiles the very same text into a host test shim (tests/host_shim.cc) so the
+// arithmetic can be exercised on a box without a GPU.  Memory access is abstracted behind small loader callables so the
+// kernels can use their own (vectorised, read-only-path) loads.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define DB_HD __device__ __forceinline__
+#else
+#define DB_HD inline
+#endif
+
+namespace dbeel {
+
+// ------------------------------------------------------------------------------------
+// Merge record: 16 bytes per input entry, the only thing the merge passes move.
+//
+//   x,y  key bytes [L, L+8)  as a big-endian u64 (x = high word), zero padded
+//   z    key bytes [L+8, L+11) in bits 31..8, zero padded; bits 7..0 = clamp
+//        clamp = min(klen - L, 12); 12 means "the key continues past the window"
+//   w    gid = position of the entry in the concatenation of all input runs
+//        (run-major), so gid order == (run position, index in run)
+//
+// L is the length of the byte prefix shared by every key of the job.  Comparing (x,y,z)
+// as an unsigned tuple orders keys exactly like Rust's Vec<u8>::cmp (mod.rs:77-79)
+// whenever the tuples differ or clamp < 12; equal tuples with clamp == 12 need the bytes
+// past the window (full compare).
+struct Rec {
+    uint32_t x, y, z, w;
+};
+
+constexpr uint32_t kWindowBytes = 11;
+constexpr uint32_t kClampBeyond = 12;
+constexpr uint32_t kMaxPrefix = 255;
+
+DB_HD uint64_t bswap64(uint64_t v) {
+    v = ((v & 0x00FF00FF00FF00FFULL) << 8) | ((v >> 8) & 0x00FF00FF00FF00FFULL);
+    v = ((v & 0x0000FFFF0000FFFFULL) << 16) | ((v >> 16) & 0x0000FFFF0000FFFFULL);
+    return (v << 32) | (v >> 32);
+}
+
+// w0 / w1: little-endian loads of key bytes [L, L+8) and [L+8, L+16); bytes at or past the
+// end of the key may hold anything.  rem = klen - L (bytes of key available from L).
+DB_HD Rec make_rec(uint64_t w0, uint64_t w1, uint64_t rem, uint32_t gid) {
+    uint64_t hi = bswap64(w0);
+    if (rem < 8) hi = rem ? (hi & (~0ULL << (8 * (8 - rem)))) : 0;
+    uint32_t nz = rem > 8 ? (rem - 8 > 3 ? 3u : (uint32_t)(rem - 8)) : 0u; // valid bytes in z
+    uint32_t zb = ((uint32_t)(w1 & 0xFF) << 24) | ((uint32_t)((w1 >> 8) & 0xFF) << 16) |
+                  ((uint32_t)((w1 >> 16) & 0xFF) << 8);
+    zb = nz ? (zb & (~0u << (8 * (4 - nz)))) : 0u;
+    uint32_t clamp = rem > kWindowBytes ? kClampBeyond : (uint32_t)rem;
+    Rec r;
+    r.x = (uint32_t)(hi >> 32);
+    r.y = (uint32_t)hi;
+    r.z = zb | clamp;
+    r.w = gid;
+    return r;
+}
+
+// -1 / 0 / +1 on the window; *undecided = 1 when the tuples tie and both keys continue.
+DB_HD int rec_cmp_window(const Rec &a, const Rec &b, int *undecided) {
+    *undecided = 0;
+    if (a.x != b.x) return a.x < b.x ? -1 : 1;
+    if (a.y != b.y) return a.y < b.y ? -1 : 1;
+    if (a.z != b.z) return a.z < b.z ? -1 : 1;
+    if ((a.z & 0xFF) == kClampBeyond) *undecided = 1;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// SipHash-1-3 over `write_usize(klen) ++ key` -- what `Hash for Vec<u8>` feeds
+// siphasher::sip::SipHasher13 (bloomfilter 1.0.12's item.hash(sip)).  The 8-byte length
+// prefix keeps the key's 8-byte words aligned with SipHash's message words.
+// ld(j) returns the little-endian u64 at key bytes [8j, 8j+8); bytes past klen are ignored.
+
+#define DB_ROTL64(v, b) (((v) << (b)) | ((v) >> (64 - (b))))
+#define DB_SIPROUND(v0, v1, v2, v3)                                     \
+    do {                                                                \
+        v0 += v1; v1 = DB_ROTL64(v1, 13); v1 ^= v0; v0 = DB_ROTL64(v0, 32); \
+        v2 += v3; v3 = DB_ROTL64(v3, 16); v3 ^= v2;                     \
+        v0 += v3; v3 = DB_ROTL64(v3, 21); v3 ^= v0;                     \
+        v2 += v1; v1 = DB_ROTL64(v1, 17); v1 ^= v2; v2 = DB_ROTL64(v2, 32); \
+    } while (0)
+
+struct SipState {
+    uint64_t v0, v1, v2, v3;
+};
+
+DB_HD SipState sip_init(uint64_t k0, uint64_t k1) {
+    SipState s;
+    s.v0 = k0 ^ 0x736f6d6570736575ULL;
+    s.v1 = k1 ^ 0x646f72616e646f6dULL;
+    s.v2 = k0 ^ 0x6c7967656e657261ULL;
+    s.v3 = k1 ^ 0x7465646279746573ULL;
+    return s;
+}
+
+DB_HD void sip_compress(SipState &s, uint64_t m) {
+    s.v3 ^= m;
+    DB_SIPROUND(s.v0, s.v1, s.v2, s.v3);
+    s.v0 ^= m;
+}
+
+DB_HD uint64_t sip_finish(SipState &s, uint64_t last_block) {
+    sip_compress(s, last_block);
+    s.v2 ^= 0xff;
+    DB_SIPROUND(s.v0, s.v1, s.v2, s.v3);
+    DB_SIPROUND(s.v0, s.v1, s.v2, s.v3);
+    DB_SIPROUND(s.v0, s.v1, s.v2, s.v3);
+    return s.v0 ^ s.v1 ^ s.v2 ^ s.v3;
+}
+
+// Both bloom hashes in one walk over the key (the two hashers differ only in their keys).
+template <class LoadU64>
+DB_HD void sip13_pair_vec_u8(const uint64_t k[4], uint64_t klen, LoadU64 ld, uint64_t *h0, uint64_t *h1) {
+    SipState a = sip_init(k[0], k[1]);
+    SipState b = sip_init(k[2], k[3]);
+    sip_compress(a, klen); // write_usize(len)
+    sip_compress(b, klen);
+    uint64_t nfull = klen >> 3;
+    for (uint64_t j = 0; j < nfull; j++) {
+        uint64_t m = ld(j);
+        sip_compress(a, m);
+        sip_compress(b, m);
+    }
+    uint32_t tail = (uint32_t)(klen & 7);
+    uint64_t last = ((klen + 8) & 0xff) << 56;
+    if (tail) last |= ld(nfull) & (~0ULL >> (8 * (8 - tail)));
+    *h0 = sip_finish(a, last);
+    *h1 = sip_finish(b, last);
+}
+
+// ------------------------------------------------------------------------------------
+// Bloom bit positions (bloomfilter 1.0.12 bloom_hash + set).
+
+constexpr uint64_t kBloomPrime = 0xFFFFFFFFFFFFFFC5ULL;
+
+DB_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
+#ifdef __CUDA_ARCH__
+    return __umul64hi(a, b);
+#else
+    return (uint64_t)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+
+// h % d with magic = floor(2^64 / d), d >= 2: the estimate is low by at most one.
+DB_HD uint64_t fastmod(uint64_t h, uint64_t d, uint64_t magic) {
+    uint64_t q = mulhi64(h, magic);
+    uint64_t r = h - q * d;
+    return r >= d ? r - d : r;
+}
+
+// g_i of the double-hashing scheme: i = 0 -> h0, 1 -> h1, else (h0 + i*h1 mod 2^64) % prime.
+DB_HD uint64_t bloom_hash_i(uint64_t h0, uint64_t h1, uint32_t i) {
+    if (i == 0) return h0;
+    if (i == 1) return h1;
+    uint64_t g = h0 + (uint64_t)i * h1;
+    return g >= kBloomPrime ? g - kBloomPrime : g; // prime > 2^63: at most one subtraction
+}
+
+// ------------------------------------------------------------------------------------
+// Byte realignment for the gather kernel: 16 output bytes starting `sh` bytes into the
+// 32-byte window {A, B} (A = lower-address 16 bytes).  sh in [0, 15]; B unused if sh == 0.
+
+DB_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t bits) {
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, bits);
+#else
+    return bits ? (lo >> bits) | (hi << (32 - bits)) : lo;
+#endif
+}
+
+DB_HD void realign16(const uint32_t A[4], const uint32_t B[4], uint32_t sh, uint32_t out[4]) {
+    uint32_t bits = (sh & 3) * 8;
+    uint32_t w0, w1, w2, w3, w4;
+    switch (sh >> 2) {
+    case 0: w0 = A[0]; w1 = A[1]; w2 = A[2]; w3 = A[3]; w4 = B[0]; break;
+    case 1: w0 = A[1]; w1 = A[2]; w2 = A[3]; w3 = B[0]; w4 = B[1]; break;
+    case 2: w0 = A[2]; w1 = A[3]; w2 = B[0]; w3 = B[1]; w4 = B[2]; break;
+    default: w0 = A[3]; w1 = B[0]; w2 = B[1]; w3 = B[2]; w4 = B[3]; break;
+    }
+    out[0] = funnel_r(w0, w1, bits);
+    out[1] = funnel_r(w1, w2, bits);
+    out[2] = funnel_r(w2, w3, bits);
+    out[3] = funnel_r(w3, w4, bits);
+}
+
+// ------------------------------------------------------------------------------------
+// i128 timestamp order (mod.rs:80) on the two little-endian halves.
+
+DB_HD bool ts_greater(uint64_t alo, uint64_t ahi, uint64_t blo, uint64_t bhi) {
+    if (ahi != bhi) return (int64_t)ahi > (int64_t)bhi;
+    return alo > blo;
+}
+
+} // namespace dbeel

@@ -1,0 +1,696 @@
+// kernels.cuh -- sm_100a kernels of the compaction engine.  See DESIGN.md for the pipeline.
+//
+// All work on this path is byte / integer work bounded by HBM bandwidth; there is no dense
+// contraction, so no tensor-core code.  What matters: 128-bit coalesced loads and stores,
+// moving only 16-byte merge records (never payload) through the merge passes, and touching
+// every payload byte exactly once (one read, one write) in the gather kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_fns.cuh"
+
+namespace dbeel {
+
+// ------------------------------------------------------------------------------------
+// device-side job description
+
+struct RunDesc {
+    const uint8_t *data;
+    uint64_t data_len;
+    const uint4 *index;
+    uint32_t n_in; // index_len / 16
+    uint32_t base; // gid of this run's first entry
+};
+
+struct Seg {
+    uint32_t start, len;
+};
+
+enum : uint32_t {
+    kFlagTruncated = 1u,   // some run ended before its last index record
+    kFlagUnsorted = 2u,    // a valid entry does not carry the job's common key prefix
+    kFlagVerifyFailed = 4u // DBEEL_FLAG_VERIFY_SORTED found a descent or duplicate
+};
+
+struct Ctl {
+    uint32_t prefix_len;
+    uint32_t flags;
+    uint32_t total;  // entries that take part in the merge (sum of valid counts)
+    uint32_t ticket; // resolve-kernel tile ticket
+    unsigned long long out_data_len;
+    uint32_t out_items;
+    uint32_t runs_truncated;
+    uint8_t prefix[256];
+};
+
+constexpr int kMergeThreads = 256;
+constexpr int kMergeVT = 8;
+constexpr int kMergeTile = kMergeThreads * kMergeVT; // 2048 records = 32 KB of smem
+constexpr int kResolveThreads = 512;
+constexpr int kGatherThreads = 256;
+constexpr int kGatherEntries = 256; // entries per CTA
+constexpr int kGatherLanes = 8;     // lanes cooperating on one entry
+constexpr int kMaxLevels = 10;      // ceil(log2(DBEEL_MAX_RUNS))
+
+struct BloomParams {
+    uint32_t *words;     // bit-vec storage inside the .bloom buffer (file offset 8); null = off
+    uint64_t bits;       // bitmap_bits
+    uint64_t bits_magic; // floor(2^64 / bits)
+    uint32_t k_num;
+    uint64_t sip[4]; // k0,k1 of hasher 0 ; k0,k1 of hasher 1
+};
+
+struct Params {
+    const RunDesc *runs;
+    uint32_t n_runs;
+    uint32_t n_total; // sum of n_in
+    uint32_t *first_bad;      // [n_runs] in: n_in, out: valid entry count
+    uint32_t *first_mismatch; // [n_runs] first entry lacking the common prefix
+    Ctl *ctl;
+    Seg *seg[kMaxLevels + 1];       // seg[l][j]: sorted segment j entering level l
+    uint32_t *tile_base[kMaxLevels]; // [pairs_l + 1] exclusive tile counts per pair
+    uint32_t nseg[kMaxLevels + 1];
+    uint32_t n_levels;
+    uint32_t *part; // merge-path split points of the current level
+    Rec *rec_a, *rec_b;
+    // resolve / scan
+    uint32_t *scan_status;
+    unsigned long long *scan_agg_bytes, *scan_inc_bytes;
+    uint32_t *scan_agg_cnt, *scan_inc_cnt;
+    int keep_tombstones;
+    int mode_flush; // 1: arrival batch -- winner = last arrival, tombstones kept
+    // outputs
+    uint8_t *out_data;
+    uint4 *out_index;
+    unsigned long long *src_ptr; // [n_total] device address of each surviving entry's bytes
+    BloomParams bloom;
+};
+
+// ------------------------------------------------------------------------------------
+// small load helpers
+
+__device__ __forceinline__ uint64_t ld_u64_unaligned(const uint8_t *p) {
+    // two aligned 8-byte loads; the second is only issued when it holds needed bytes
+    uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint64_t *q = reinterpret_cast<const uint64_t *>(a & ~uintptr_t(7));
+    uint32_t sh = (uint32_t)(a & 7) * 8;
+    uint64_t lo = __ldg(q);
+    if (sh == 0) return lo;
+    uint64_t hi = __ldg(q + 1);
+    return (lo >> sh) | (hi << (64 - sh));
+}
+
+__device__ __forceinline__ Rec ld_rec(const Rec *p) {
+    uint4 v = *reinterpret_cast<const uint4 *>(p);
+    Rec r;
+    r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+    return r;
+}
+__device__ __forceinline__ void st_rec(Rec *p, const Rec &r) {
+    *reinterpret_cast<uint4 *>(p) = make_uint4(r.x, r.y, r.z, r.w);
+}
+
+// run that owns gid: the last run whose base <= gid (empty runs share a base with their
+// successor, and the successor is the owner)
+__device__ __forceinline__ uint32_t find_run(const Params &p, uint32_t gid) {
+    uint32_t lo = 0, hi = p.n_runs; // answer in [lo, hi)
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (p.runs[mid].base <= gid) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+struct KeyRef {
+    const uint8_t *ptr; // first key byte
+    uint32_t klen;
+    const uint8_t *entry;
+    uint32_t full_size;
+};
+
+__device__ __forceinline__ KeyRef key_of_gid(const Params &p, uint32_t gid) {
+    uint32_t r = find_run(p, gid);
+    const RunDesc &rd = p.runs[r];
+    uint4 rec = __ldg(&rd.index[gid - rd.base]);
+    uint64_t off = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
+    KeyRef k;
+    k.entry = rd.data + off;
+    k.ptr = k.entry + 8;
+    k.klen = rec.z - 8;
+    k.full_size = rec.w;
+    return k;
+}
+
+// Vec<u8>::cmp of two keys known to agree on their first `skip` bytes (slow path).
+__device__ __noinline__ int full_key_cmp(const Params &p, uint32_t ga, uint32_t gb, uint32_t skip) {
+    KeyRef a = key_of_gid(p, ga), b = key_of_gid(p, gb);
+    uint32_t m = a.klen < b.klen ? a.klen : b.klen;
+    for (uint32_t i = skip; i < m; i++) {
+        uint8_t ca = __ldg(a.ptr + i), cb = __ldg(b.ptr + i);
+        if (ca != cb) return ca < cb ? -1 : 1;
+    }
+    return a.klen < b.klen ? -1 : (a.klen > b.klen ? 1 : 0);
+}
+
+// strict key order: a < b  (mod.rs:77-79; ties are left to the caller = stable merge)
+__device__ __forceinline__ bool key_less(const Params &p, uint32_t skip, const Rec &a, const Rec &b) {
+    int und;
+    int c = rec_cmp_window(a, b, &und);
+    if (und) c = full_key_cmp(p, a.w, b.w, skip);
+    return c < 0;
+}
+
+__device__ __forceinline__ bool key_equal(const Params &p, uint32_t skip, const Rec &a, const Rec &b) {
+    int und;
+    int c = rec_cmp_window(a, b, &und);
+    if (und) c = full_key_cmp(p, a.w, b.w, skip);
+    return c == 0;
+}
+
+// ------------------------------------------------------------------------------------
+// K0: common key prefix of the job (one warp).
+//
+// Keys ascend inside a run, so the prefix shared by a run's first and last key is shared by
+// every key in between; the job's prefix is the prefix common to all first/last keys.
+// validated = 0: speculative, uses n_in (index records are bounds-checked, nothing else);
+// validated = 1: runs only if some run was truncated, uses the validated counts.
+// mode_flush: arrival batches are not sorted -> no prefix is skipped (L = 0).
+
+__device__ __forceinline__ bool safe_key(const RunDesc &rd, uint32_t i, const uint8_t **ptr, uint32_t *klen) {
+    uint4 rec = __ldg(&rd.index[i]);
+    uint64_t off = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
+    if (rec.z < 8 || off > rd.data_len || (uint64_t)rec.z > rd.data_len - off) return false;
+    *ptr = rd.data + off + 8;
+    *klen = rec.z - 8;
+    return true;
+}
+
+__global__ void k_common_prefix(Params p, int validated) {
+    Ctl *c = p.ctl;
+    if (validated && !(c->flags & kFlagTruncated)) return;
+    const uint32_t lane = threadIdx.x;
+    __shared__ const uint8_t *s_ref;
+    __shared__ uint32_t s_ref_len;
+    if (lane == 0) { s_ref = nullptr; s_ref_len = 0; }
+    __syncwarp();
+    if (validated)
+        for (uint32_t r = lane; r < p.n_runs; r += 32) p.first_mismatch[r] = 0xFFFFFFFFu;
+    // reference key: first key of the first non-empty run
+    if (lane == 0 && !p.mode_flush) {
+        for (uint32_t r = 0; r < p.n_runs; r++) {
+            uint32_t cnt = validated ? p.first_bad[r] : p.runs[r].n_in;
+            if (!cnt) continue;
+            const uint8_t *ptr; uint32_t kl;
+            if (safe_key(p.runs[r], 0, &ptr, &kl)) { s_ref = ptr; s_ref_len = kl; }
+            break; // an unreadable first record means L = 0 (safe)
+        }
+    }
+    __syncwarp();
+    const uint8_t *ref = s_ref;
+    uint32_t L = s_ref_len < kMaxPrefix ? s_ref_len : kMaxPrefix;
+    if (ref == nullptr) L = 0;
+    for (uint32_t r = lane; r < p.n_runs && L; r += 32) {
+        uint32_t cnt = validated ? p.first_bad[r] : p.runs[r].n_in;
+        if (!cnt) continue;
+        for (int which = 0; which < 2; which++) {
+            const uint8_t *ptr; uint32_t kl;
+            if (!safe_key(p.runs[r], which ? cnt - 1 : 0, &ptr, &kl)) { L = 0; break; }
+            uint32_t m = kl < L ? kl : L, i = 0;
+            while (i < m && __ldg(ptr + i) == __ldg(ref + i)) i++;
+            L = i;
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, L, o);
+        L = other < L ? other : L;
+    }
+    for (uint32_t i = lane; i < L; i += 32) c->prefix[i] = __ldg(ref + i);
+    if (lane == 0) c->prefix_len = L;
+}
+
+// ------------------------------------------------------------------------------------
+// K1: validate every index record + entry header and extract the 16-byte merge record.
+//
+// "Valid" restates what the reference's sequential reader needs to decode entry i
+// (lsm_tree.rs:1158-1170): the record lies inside .data at the running offset and
+// bincode-decodes with no trailing bytes (klen/dlen prefixes agree with key_size/full_size).
+// The first invalid entry ends its run (lsm_tree.rs:1014,1063): first_bad[r] = min index.
+
+__global__ void __launch_bounds__(256) k_extract(Params p, int redo) {
+    Ctl *c = p.ctl;
+    if (redo && !(c->flags & kFlagTruncated)) return;
+    uint32_t g = blockIdx.x * 256u + threadIdx.x;
+    if (g >= p.n_total) return;
+    uint32_t r = find_run(p, g);
+    const RunDesc rd = p.runs[r];
+    uint32_t i = g - rd.base;
+    uint4 rec = __ldg(&rd.index[i]);
+    uint64_t off = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
+    uint32_t ks = rec.z, fs = rec.w;
+    bool ok;
+    if (redo) {
+        ok = i < p.first_bad[r];
+    } else {
+        ok = ks >= 8 && (uint64_t)fs >= (uint64_t)ks + 24 && off <= rd.data_len && (uint64_t)fs <= rd.data_len - off;
+        if (ok) {
+            uint64_t expect = 0;
+            if (i) {
+                uint4 pr = __ldg(&rd.index[i - 1]);
+                expect = ((uint64_t)pr.x | ((uint64_t)pr.y << 32)) + pr.w;
+            }
+            ok = off == expect;
+        }
+        if (ok) ok = ld_u64_unaligned(rd.data + off) == (uint64_t)(ks - 8);
+        if (ok) ok = ld_u64_unaligned(rd.data + off + ks) == (uint64_t)(fs - ks - 24);
+        if (!ok) {
+            atomicMin(&p.first_bad[r], i);
+            atomicOr(&c->flags, kFlagTruncated);
+        }
+    }
+    Rec out;
+    out.x = out.y = out.z = 0;
+    out.w = g;
+    if (ok) {
+        const uint32_t L = c->prefix_len;
+        const uint32_t klen = ks - 8;
+        const uint8_t *key = rd.data + off + 8;
+        bool match = klen >= L;
+        for (uint32_t b = 0; match && b < L; b++) match = __ldg(key + b) == c->prefix[b];
+        if (match) {
+            // both loads stay inside the entry: at least 24 bytes (dlen + timestamp) follow the key
+            uint64_t w0 = ld_u64_unaligned(key + L);
+            uint64_t w1 = ld_u64_unaligned(key + L + 8);
+            out = make_rec(w0, w1, klen - L, g);
+        } else {
+            atomicMin(&p.first_mismatch[r], i);
+        }
+    }
+    st_rec(&p.rec_a[g], out);
+}
+
+// ------------------------------------------------------------------------------------
+// K1b: per-run valid counts -> segment tables of every merge level (single thread; the
+// tables have at most 2 * n_runs entries).
+
+__global__ void k_plan(Params p) {
+    if (threadIdx.x || blockIdx.x) return;
+    Ctl *c = p.ctl;
+    uint32_t total = 0, trunc = 0, flags = c->flags;
+    for (uint32_t r = 0; r < p.n_runs; r++) {
+        uint32_t cnt = p.first_bad[r];
+        if (cnt < p.runs[r].n_in) trunc++;
+        if (p.first_mismatch[r] < cnt) flags |= kFlagUnsorted;
+        p.seg[0][r].start = p.runs[r].base;
+        p.seg[0][r].len = cnt;
+        total += cnt;
+    }
+    for (uint32_t l = 0; l < p.n_levels; l++) {
+        uint32_t pairs = p.nseg[l + 1], acc = 0;
+        for (uint32_t j = 0; j < pairs; j++) {
+            Seg a = p.seg[l][2 * j];
+            uint32_t blen = (2 * j + 1 < p.nseg[l]) ? p.seg[l][2 * j + 1].len : 0;
+            p.seg[l + 1][j].start = a.start;
+            p.seg[l + 1][j].len = a.len + blen;
+            p.tile_base[l][j] = acc;
+            acc += (a.len + blen + kMergeTile - 1) / kMergeTile;
+        }
+        p.tile_base[l][pairs] = acc;
+    }
+    c->total = total;
+    c->runs_truncated = trunc;
+    c->flags = flags;
+}
+
+// ------------------------------------------------------------------------------------
+// K2/K3: one merge level = merge-path partition + tile merge.  Pair j of level l merges
+// segments 2j (A) and 2j+1 (B) of `src` into one segment of `dst` starting at A.start.
+// A holds lower run positions than B, and ties take A first, so equal keys stay ordered by
+// run position (= gid) through every level.
+
+__device__ __forceinline__ uint32_t find_pair(const uint32_t *tb, uint32_t pairs, uint32_t v, uint32_t slope) {
+    // largest j in [0, pairs) with tb[j] + slope * j <= v
+    uint32_t lo = 0, hi = pairs;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (tb[mid] + slope * mid <= v) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(128) k_merge_partition(Params p, uint32_t level, const Rec *src) {
+    const uint32_t pairs = p.nseg[level + 1];
+    const uint32_t *tb = p.tile_base[level];
+    const uint32_t n_bound = tb[pairs] + pairs; // every pair has tiles + 1 boundaries
+    uint32_t idx = blockIdx.x * 128u + threadIdx.x;
+    if (idx >= n_bound) return;
+    const uint32_t skip = p.ctl->prefix_len + kWindowBytes;
+    uint32_t j = find_pair(tb, pairs, idx, 1);
+    uint32_t t = idx - (tb[j] + j);
+    Seg a = p.seg[level][2 * j];
+    Seg b;
+    b.start = 0; b.len = 0;
+    if (2 * j + 1 < p.nseg[level]) b = p.seg[level][2 * j + 1];
+    uint64_t d64 = (uint64_t)t * kMergeTile;
+    uint32_t n = a.len + b.len;
+    uint32_t diag = d64 < n ? (uint32_t)d64 : n;
+    uint32_t lo = diag > b.len ? diag - b.len : 0;
+    uint32_t hi = diag < a.len ? diag : a.len;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        Rec ra = ld_rec(&src[a.start + mid]);
+        Rec rb = ld_rec(&src[b.start + (diag - 1 - mid)]);
+        if (!key_less(p, skip, rb, ra)) lo = mid + 1; else hi = mid;
+    }
+    p.part[idx] = lo;
+}
+
+__global__ void __launch_bounds__(kMergeThreads) k_merge(Params p, uint32_t level, const Rec *src, Rec *dst) {
+    __shared__ Rec s[kMergeTile + kMergeVT + 1];
+    const uint32_t pairs = p.nseg[level + 1];
+    const uint32_t *tb = p.tile_base[level];
+    const uint32_t tile = blockIdx.x;
+    if (tile >= tb[pairs]) return;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t skip = p.ctl->prefix_len + kWindowBytes;
+    uint32_t j = find_pair(tb, pairs, tile, 0);
+    uint32_t t = tile - tb[j];
+    Seg a = p.seg[level][2 * j];
+    Seg b;
+    b.start = 0; b.len = 0;
+    if (2 * j + 1 < p.nseg[level]) b = p.seg[level][2 * j + 1];
+    const uint32_t pidx = tb[j] + j + t;
+    const uint32_t a0 = p.part[pidx], a1 = p.part[pidx + 1];
+    const uint32_t total = a.len + b.len;
+    const uint32_t diag0 = t * kMergeTile;
+    const uint32_t diag1 = diag0 + kMergeTile < total ? diag0 + kMergeTile : total;
+    const uint32_t b0 = diag0 - a0, b1 = diag1 - a1;
+    const uint32_t nA = a1 - a0, nB = b1 - b0, n = nA + nB;
+
+    for (uint32_t i = tid; i < nA; i += kMergeThreads) s[i] = ld_rec(&src[a.start + a0 + i]);
+    for (uint32_t i = tid; i < nB; i += kMergeThreads) s[nA + i] = ld_rec(&src[b.start + b0 + i]);
+    __syncthreads();
+
+    uint32_t d = tid * kMergeVT;
+    if (d > n) d = n;
+    uint32_t lo = d > nB ? d - nB : 0;
+    uint32_t hi = d < nA ? d : nA;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (!key_less(p, skip, s[nA + d - 1 - mid], s[mid])) lo = mid + 1; else hi = mid;
+    }
+    uint32_t ai = lo, bi = d - lo;
+    Rec ak = s[ai], bk = s[nA + bi]; // may read one slot past a range: slack + guarded below
+    Rec out[kMergeVT];
+#pragma unroll
+    for (int i = 0; i < kMergeVT; i++) {
+        bool has_a = ai < nA, has_b = bi < nB;
+        bool take_b = has_b && (!has_a || key_less(p, skip, bk, ak));
+        out[i] = take_b ? bk : ak;
+        if (take_b) { bi++; bk = s[nA + bi]; } else { ai++; ak = s[ai]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kMergeVT; i++)
+        if (d + i < n) s[d + i] = out[i];
+    __syncthreads();
+    Rec *o = dst + a.start + diag0;
+    for (uint32_t i = tid; i < n; i += kMergeThreads) st_rec(&o[i], s[i]);
+}
+
+// ------------------------------------------------------------------------------------
+// K4: resolve + scan + .index.  One thread per merged record.
+//
+// A record that starts a group of equal keys ("head") picks the group's winner -- the entry
+// with the greatest (timestamp, run position), lsm_tree.rs:1041-1044 with mod.rs:75-81 and
+// lsm_tree.rs:58-65 -- and emits it unless it is a tombstone that must go
+// (lsm_tree.rs:1045-1046).  Timestamps are only read for groups of two or more.
+// Output offsets come from a single-pass decoupled look-back scan over (bytes, count).
+
+__device__ __forceinline__ void ld_ts(const KeyRef &k, uint64_t *lo, uint64_t *hi) {
+    const uint8_t *t = k.entry + k.full_size - 16;
+    *lo = ld_u64_unaligned(t);
+    *hi = ld_u64_unaligned(t + 8);
+}
+
+__global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec *m) {
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_wb[kResolveThreads / 32];
+    __shared__ uint32_t s_wc[kResolveThreads / 32];
+    __shared__ unsigned long long s_excl_b;
+    __shared__ uint32_t s_excl_c;
+    Ctl *c = p.ctl;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(&c->ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t total = c->total;
+    if ((uint64_t)tile * kResolveThreads >= total) return;
+    const uint32_t n_tiles = (total + kResolveThreads - 1) / kResolveThreads;
+    const uint32_t skip = c->prefix_len + kWindowBytes;
+    const uint32_t i = tile * kResolveThreads + tid;
+
+    uint32_t keep = 0, ks = 0, fs = 0;
+    unsigned long long src = 0;
+    if (i < total) {
+        Rec cur = ld_rec(&m[i]);
+        bool head = true;
+        if (i) head = !key_equal(p, skip, ld_rec(&m[i - 1]), cur);
+        if (head) {
+            uint32_t w = cur.w;
+            KeyRef wk;
+            bool have_wk = false;
+            uint32_t jn = i + 1;
+            if (jn < total) {
+                Rec nx = ld_rec(&m[jn]);
+                if (key_equal(p, skip, cur, nx)) {
+                    wk = key_of_gid(p, w);
+                    have_wk = true;
+                    uint64_t wlo = 0, whi = 0;
+                    if (!p.mode_flush) ld_ts(wk, &wlo, &whi);
+                    do {
+                        KeyRef ck = key_of_gid(p, nx.w);
+                        bool better = true; // flush: the later arrival always wins (lib.rs:509-511)
+                        if (!p.mode_flush) {
+                            uint64_t clo, chi;
+                            ld_ts(ck, &clo, &chi);
+                            // equal timestamps: the later run position (larger gid) wins
+                            better = !ts_greater(wlo, whi, clo, chi);
+                            if (better) { wlo = clo; whi = chi; }
+                        }
+                        if (better) { w = nx.w; wk = ck; }
+                        jn++;
+                        if (jn >= total) break;
+                        nx = ld_rec(&m[jn]);
+                    } while (key_equal(p, skip, cur, nx));
+                }
+            }
+            if (!have_wk) wk = key_of_gid(p, w);
+            ks = wk.klen + 8;
+            fs = wk.full_size;
+            src = (unsigned long long)(uintptr_t)wk.entry;
+            bool tomb = fs == ks + 24;
+            keep = (p.keep_tombstones || p.mode_flush || !tomb) ? 1u : 0u;
+        }
+    }
+
+    // block-wide inclusive scan of (bytes, count)
+    unsigned long long vb = keep ? fs : 0ull;
+    uint32_t vc = keep;
+    unsigned long long ib = vb;
+    uint32_t ic = vc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long tb = __shfl_up_sync(0xFFFFFFFFu, ib, o);
+        uint32_t tc = __shfl_up_sync(0xFFFFFFFFu, ic, o);
+        if (lane >= (uint32_t)o) { ib += tb; ic += tc; }
+    }
+    if (lane == 31) { s_wb[warp] = ib; s_wc[warp] = ic; }
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long wb = lane < kResolveThreads / 32 ? s_wb[lane] : 0ull;
+        uint32_t wc = lane < kResolveThreads / 32 ? s_wc[lane] : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long tb = __shfl_up_sync(0xFFFFFFFFu, wb, o);
+            uint32_t tc = __shfl_up_sync(0xFFFFFFFFu, wc, o);
+            if (lane >= (uint32_t)o) { wb += tb; wc += tc; }
+        }
+        // inclusive over warps; block aggregate sits in the last used lane
+        unsigned long long agg_b = __shfl_sync(0xFFFFFFFFu, wb, kResolveThreads / 32 - 1);
+        uint32_t agg_c = __shfl_sync(0xFFFFFFFFu, wc, kResolveThreads / 32 - 1);
+        if (lane < kResolveThreads / 32) { s_wb[lane] = wb; s_wc[lane] = wc; }
+
+        // decoupled look-back
+        volatile uint32_t *status = p.scan_status;
+        volatile unsigned long long *aggb = p.scan_agg_bytes, *incb = p.scan_inc_bytes;
+        volatile uint32_t *aggc = p.scan_agg_cnt, *incc = p.scan_inc_cnt;
+        unsigned long long excl_b = 0;
+        uint32_t excl_c = 0;
+        if (tile > 0) {
+            if (lane == 0) {
+                aggb[tile] = agg_b;
+                aggc[tile] = agg_c;
+                __threadfence();
+                status[tile] = 1;
+            }
+            int look = (int)tile - 1;
+            while (true) {
+                int idx = look - (int)lane;
+                uint32_t st = 2;
+                if (idx >= 0) {
+                    do { st = status[idx]; } while (st == 0);
+                }
+                __threadfence();
+                uint32_t mask2 = __ballot_sync(0xFFFFFFFFu, st == 2);
+                uint32_t first = mask2 ? (uint32_t)__ffs(mask2) - 1 : 32u;
+                unsigned long long cb = 0;
+                uint32_t cc = 0;
+                if (idx >= 0) {
+                    if (lane < first) { cb = aggb[idx]; cc = aggc[idx]; }
+                    else if (lane == first) { cb = incb[idx]; cc = incc[idx]; }
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    cb += __shfl_xor_sync(0xFFFFFFFFu, cb, o);
+                    cc += __shfl_xor_sync(0xFFFFFFFFu, cc, o);
+                }
+                excl_b += cb;
+                excl_c += cc;
+                if (mask2) break;
+                look -= 32;
+            }
+        }
+        if (lane == 0) {
+            incb[tile] = excl_b + agg_b;
+            incc[tile] = excl_c + agg_c;
+            __threadfence();
+            status[tile] = 2;
+            s_excl_b = excl_b;
+            s_excl_c = excl_c;
+            if (tile == n_tiles - 1) {
+                c->out_data_len = excl_b + agg_b;
+                c->out_items = excl_c + agg_c;
+            }
+        }
+    }
+    __syncthreads();
+    if (keep) {
+        unsigned long long off = s_excl_b + (warp ? s_wb[warp - 1] : 0ull) + (ib - vb);
+        uint32_t pos = s_excl_c + (warp ? s_wc[warp - 1] : 0u) + (ic - vc);
+        p.out_index[pos] = make_uint4((uint32_t)off, (uint32_t)(off >> 32), ks, fs);
+        p.src_ptr[pos] = src;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K5: gather + bloom -- the roofline kernel.  Every surviving entry's bytes are read once
+// from its input run and written once at its output offset.
+//
+// Phase 1 (bloom on): one thread per entry hashes the key (2 x SipHash-1-3, one walk) and
+// sets k bits with atomicOr; the filter (<= ~10 MB at the benchmark shapes) lives in L2.
+// The key bytes it touches are the head of the entry that phase 2 copies next.
+// Phase 2: kGatherLanes lanes per entry.  Destination 16-byte vectors that lie wholly inside
+// the entry are produced from two aligned 16-byte source loads and a byte funnel shift
+// (source and destination are mutually misaligned by an arbitrary byte count); the ragged
+// head and tail (< 16 bytes each) are copied bytewise.
+
+__global__ void __launch_bounds__(kGatherThreads) k_gather(Params p) {
+    const Ctl *c = p.ctl;
+    const uint32_t n_out = c->out_items;
+    const uint32_t e0 = blockIdx.x * kGatherEntries;
+    if (e0 >= n_out) return;
+    const uint32_t e1 = e0 + kGatherEntries < n_out ? e0 + kGatherEntries : n_out;
+    const uint32_t tid = threadIdx.x;
+
+    if (p.bloom.words != nullptr) {
+        for (uint32_t e = e0 + tid; e < e1; e += kGatherThreads) {
+            uint4 rec = p.out_index[e];
+            const uint8_t *key = reinterpret_cast<const uint8_t *>((uintptr_t)p.src_ptr[e]) + 8;
+            uint64_t klen = rec.z - 8;
+            uint64_t h0, h1;
+            sip13_pair_vec_u8(p.bloom.sip, klen, [key](uint64_t j) { return ld_u64_unaligned(key + 8 * j); }, &h0, &h1);
+            for (uint32_t k = 0; k < p.bloom.k_num; k++) {
+                uint64_t bit = fastmod(bloom_hash_i(h0, h1, k), p.bloom.bits, p.bloom.bits_magic);
+                atomicOr(&p.bloom.words[bit >> 5], 1u << (bit & 31));
+            }
+        }
+    }
+
+    const uint32_t grp = tid / kGatherLanes, gl = tid % kGatherLanes;
+    constexpr uint32_t n_grp = kGatherThreads / kGatherLanes;
+    for (uint32_t e = e0 + grp; e < e1; e += n_grp) {
+        uint4 rec = p.out_index[e];
+        const uint64_t d0 = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
+        const uint32_t fs = rec.w;
+        const uint64_t d1 = d0 + fs;
+        const uint8_t *src = reinterpret_cast<const uint8_t *>((uintptr_t)p.src_ptr[e]);
+        uint8_t *dst = p.out_data;
+        uint64_t ha = (d0 + 15) & ~15ull; // first 16-aligned output offset >= d0
+        if (ha > d1) ha = d1;
+        uint64_t tb = d1 & ~15ull;        // last 16-aligned output offset <= d1
+        if (tb < ha) tb = ha;
+        for (uint64_t b = d0 + gl; b < ha; b += kGatherLanes) dst[b] = __ldg(src + (b - d0));
+        for (uint64_t b = tb + gl; b < d1; b += kGatherLanes) dst[b] = __ldg(src + (b - d0));
+        const uint32_t nvec = (uint32_t)((tb - ha) >> 4);
+        if (nvec) {
+            uintptr_t sa = reinterpret_cast<uintptr_t>(src) + (ha - d0);
+            const uint32_t sh = (uint32_t)(sa & 15);
+            const uint4 *sv = reinterpret_cast<const uint4 *>(sa - sh);
+            uint4 *dv = reinterpret_cast<uint4 *>(dst + ha);
+            for (uint32_t v = gl; v < nvec; v += kGatherLanes) {
+                uint4 A = __ldg(sv + v);
+                uint4 o = A;
+                if (sh) {
+                    uint4 B = __ldg(sv + v + 1);
+                    uint32_t a4[4] = {A.x, A.y, A.z, A.w}, b4[4] = {B.x, B.y, B.z, B.w}, o4[4];
+                    realign16(a4, b4, sh, o4);
+                    o = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+                }
+                dv[v] = o;
+            }
+        }
+    }
+}
+
+// .bloom framing around the bit vector (bincode of bloomfilter::Bloom):
+//   u64 n_words | u32 words[n_words] | u64 nbits | u64 bitmap_bits | u32 k_num | 2 x SipHasher13
+__global__ void k_bloom_frame(uint8_t *file, uint64_t n_words, BloomParams b) {
+    if (threadIdx.x || blockIdx.x) return;
+    uint32_t *w = reinterpret_cast<uint32_t *>(file);
+    auto put64 = [&](uint64_t word_idx, uint64_t v) {
+        w[word_idx] = (uint32_t)v;
+        w[word_idx + 1] = (uint32_t)(v >> 32);
+    };
+    put64(0, n_words);
+    uint64_t t = 2 + n_words; // u32 index of the trailer
+    put64(t, b.bits);
+    put64(t + 2, b.bits);
+    w[t + 4] = b.k_num;
+    t += 5;
+    for (int h = 0; h < 2; h++) {
+        uint64_t k0 = b.sip[2 * h], k1 = b.sip[2 * h + 1];
+        put64(t, k0);
+        put64(t + 2, k1);
+        put64(t + 4, 0);                          // length
+        put64(t + 6, k0 ^ 0x736f6d6570736575ULL); // v0
+        put64(t + 8, k0 ^ 0x6c7967656e657261ULL); // v2
+        put64(t + 10, k1 ^ 0x646f72616e646f6dULL); // v1
+        put64(t + 12, k1 ^ 0x7465646279746573ULL); // v3
+        put64(t + 14, 0);                         // tail
+        put64(t + 16, 0);                         // ntail
+        t += 18;
+    }
+}
+
+// DBEEL_FLAG_VERIFY_SORTED: every valid entry i > 0 of a run must have key[i-1] < key[i].
+__global__ void __launch_bounds__(256) k_verify_sorted(Params p) {
+    uint32_t g = blockIdx.x * 256u + threadIdx.x;
+    if (g >= p.n_total) return;
+    uint32_t r = find_run(p, g);
+    uint32_t i = g - p.runs[r].base;
+    if (i == 0 || i >= p.first_bad[r]) return;
+    if (full_key_cmp(p, g - 1, g, 0) >= 0) atomicOr(&p.ctl->flags, kFlagVerifyFailed);
+}
+
+} // namespace dbeel

@@ -1,0 +1,158 @@
+/*
+ * dbeel_compact.h -- C ABI of the B200 compaction engine (libdbeel_compact.so).
+ *
+ * This is the drop-in boundary for ONE hot path of tontinton/dbeel's storage engine: the
+ * merge core of LSMTree::compact, the memtable flush that feeds level 0, and the
+ * bloom / per-entry index build on the output run.  Everything else (file open/create,
+ * the CompactionAction journal, renames, the sstables swap, the page cache, the WAL)
+ * stays with the caller.  The library never touches the filesystem.
+ *
+ * Reference interfaces replaced (paths under /root/reference):
+ *
+ *   dbeel_compact*      <- the body of LSMTree::compact between opening the inputs and
+ *                          writing the bloom file: src/storage_engine/lsm_tree.rs:1002-1076
+ *                          (BinaryHeap<CompactionItem> merge :52-71,:1038-1066,
+ *                          read_next_entry :1158-1170, EntryWriter::write/close
+ *                          src/storage_engine/entry_writer.rs:71-160, Bloom::set + dump
+ *                          lsm_tree.rs:1026-1034,:1049-1051,:1070-1076)
+ *   dbeel_flush*        <- RedBlackTree::set semantics (rbtree_arena/src/lib.rs:497-534) +
+ *                          LSMTree::flush_memtable_to_disk (lsm_tree.rs:925-946)
+ *   dbeel_bloom_*       <- Bloom::new_for_fp_rate sizing (lsm_tree.rs:1028-1031)
+ *   error codes         <- src/error.rs:8-74 (only the variants this path can raise)
+ *
+ * Byte formats are the reference's own (bincode fixint little-endian, mod.rs:45-73):
+ *   .data  record = klen:u64 | key | dlen:u64 | data | ts:i128      (dlen == 0: tombstone)
+ *   .index record = offset:u64 | key_size:u32 (=8+klen) | full_size:u32   (16 bytes)
+ *   .bloom        = bincode(bloomfilter::Bloom) -- see DESIGN.md for the field order
+ *
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary.
+ */
+#ifndef DBEEL_COMPACT_H
+#define DBEEL_COMPACT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DBEEL_ABI_VERSION 1
+
+/* status codes (0 = ok).  No exception or panic ever crosses the ABI. */
+enum {
+    DBEEL_OK = 0,
+    DBEEL_ERR_INVALID_ARG = 1,     /* null pointer, misaligned device buffer, bad option    */
+    DBEEL_ERR_CAPACITY = 2,        /* an output buffer is smaller than dbeel_compact_bound  */
+    DBEEL_ERR_ITEM_TOO_LARGE = 3,  /* Error::ItemTooLarge, entry_writer.rs:72-74            */
+    DBEEL_ERR_CUDA = 4,            /* a CUDA call failed; dbeel_last_error() has the text   */
+    DBEEL_ERR_NOMEM = 5,           /* device or pinned-host allocation failed               */
+    DBEEL_ERR_TOO_MANY_RUNS = 6,   /* more than DBEEL_MAX_RUNS inputs                       */
+    DBEEL_ERR_TOO_MANY_ENTRIES = 7,/* more than 2^32-2 input entries in one job             */
+    DBEEL_ERR_UNSORTED_RUN = 8,    /* an input run violates "keys strictly ascending"       */
+    DBEEL_ERR_NO_DEVICE = 9,       /* no CUDA device / not an sm_100 part                   */
+    DBEEL_ERR_BUSY = 10            /* engine already has a job in flight                    */
+};
+
+#define DBEEL_MAX_RUNS 1024u
+#define DBEEL_INDEX_ENTRY_SIZE 16u            /* mod.rs:33 */
+#define DBEEL_DEFAULT_BLOOM_MIN_SIZE 1048576u /* mod.rs:19 */
+#define DBEEL_DEFAULT_BLOOM_FP 0.01           /* lsm_tree.rs:48 */
+#define DBEEL_DEFAULT_TREE_CAPACITY 8192u     /* mod.rs:18 */
+
+/* One input SSTable: the bytes of its .data and .index files.
+ * For the *_device entry points both pointers are device pointers aligned to 16 bytes. */
+typedef struct dbeel_run {
+    const void *data;
+    uint64_t data_len;
+    const void *index;
+    uint64_t index_len; /* entries = index_len / 16 (lsm_tree.rs:978-979); a ragged tail is ignored */
+} dbeel_run;
+
+/* Output SSTable buffers, owned by the caller.  *_cap in, *_len out. */
+typedef struct dbeel_out {
+    void *data;
+    uint64_t data_cap, data_len;
+    void *index;
+    uint64_t index_cap, index_len;
+    void *bloom;         /* may be NULL when bloom_cap == 0 (no bloom will be produced) */
+    uint64_t bloom_cap, bloom_len; /* bloom_len == 0: no .bloom file (lsm_tree.rs:1026-1034) */
+    uint64_t items_written;        /* lsm_tree.rs:1053 */
+} dbeel_out;
+
+#define DBEEL_FLAG_VERIFY_SORTED 0x1u /* full adjacent-key check of every input run */
+
+typedef struct dbeel_compact_opts {
+    int32_t keep_tombstones;   /* LSMTree::compact's third argument (lsm_tree.rs:954)      */
+    uint32_t flags;            /* DBEEL_FLAG_*                                             */
+    uint64_t bloom_min_size;   /* --sstable-bloom-min-size, strict '>' (lsm_tree.rs:1027)  */
+    double bloom_fp;           /* BLOOM_MAX_ALLOWED_ERROR                                  */
+    const uint8_t *bloom_seed; /* 32 bytes (host memory), or NULL = random like getrandom  */
+} dbeel_compact_opts;
+
+/* What the last job did.  Times are CUDA-event milliseconds on the engine's stream. */
+typedef struct dbeel_stats {
+    uint64_t input_bytes;      /* sum(len(.data)+len(.index))                              */
+    uint64_t output_bytes;     /* len(out.data)+len(out.index)+len(out.bloom)              */
+    uint64_t entries_in;       /* sum(index_len/16)                                        */
+    uint64_t entries_valid;    /* after run truncation at the first undecodable record     */
+    uint64_t entries_out;      /* items_written                                            */
+    uint32_t runs_truncated;   /* runs that ended early (lsm_tree.rs:1014,1063)            */
+    uint32_t key_prefix_len;   /* common key prefix skipped by the comparison window        */
+    uint32_t merge_passes;
+    uint32_t kernel_launches;  /* kernels launched by this job                             */
+    float ms_total;            /* first kernel .. last kernel (device-resident part)       */
+    float ms_extract;          /* validate + key-window extraction                         */
+    float ms_merge;            /* all merge passes                                         */
+    float ms_resolve;          /* winner / tombstone resolution + offsets scan + .index    */
+    float ms_gather;           /* .data gather + bloom (the roofline kernel)               */
+    float ms_h2d, ms_d2h;      /* host entry points only                                   */
+    uint64_t gather_bytes;     /* algorithmic bytes of the gather kernel (read + written)  */
+} dbeel_stats;
+
+typedef struct dbeel_engine dbeel_engine;
+
+/* One engine per calling thread / shard, bound to one GPU and one stream. */
+int dbeel_engine_create(int device, dbeel_engine **out);
+void dbeel_engine_destroy(dbeel_engine *e);
+
+/* Upper bounds for the output buffers of a compaction of `runs` (host-side arithmetic only):
+ * data_cap = sum(data_len), index_cap = 16 * sum(index_len/16), bloom_cap = size of the
+ * .bloom file or 0 when sum(data_len) <= bloom_min_size. */
+int dbeel_compact_bound(const dbeel_run *runs, uint32_t n_runs, const dbeel_compact_opts *opts,
+                        uint64_t *data_cap, uint64_t *index_cap, uint64_t *bloom_cap);
+
+/* Merge `runs` (runs[i] is position i in indices_to_compact: the final tie-break) into one
+ * SSTable.  Host buffers in, host buffers out; copies are part of the call. */
+int dbeel_compact(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs,
+                  const dbeel_compact_opts *opts, dbeel_out *out);
+
+/* Same, inputs and outputs resident in device memory (16-byte aligned).  Returns after the
+ * job has completed on the engine's stream. */
+int dbeel_compact_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs,
+                         const dbeel_compact_opts *opts, dbeel_out *out);
+
+/* Memtable flush: `batch` holds writes in ARRIVAL order in run layout (keys may repeat, not
+ * sorted).  Output = what flush_memtable_to_disk writes for the memtable those writes
+ * build: ascending keys, last arrival per key, tombstones kept, no bloom.  The caller cuts
+ * batches at memtable boundaries (dbeel_memtable_cut helps). */
+int dbeel_flush(dbeel_engine *e, const dbeel_run *batch, dbeel_out *out);
+int dbeel_flush_device(dbeel_engine *e, const dbeel_run *batch, dbeel_out *out);
+
+/* Bloom::new_for_fp_rate arithmetic (bloomfilter 1.0.12). */
+uint64_t dbeel_bloom_bitmap_bytes(uint64_t items, double fp);
+uint32_t dbeel_bloom_k_num(uint64_t bitmap_bits, uint64_t items);
+uint64_t dbeel_bloom_file_size(uint64_t items, double fp);
+
+/* Pinned host memory for the host entry points (optional; any host pointer is accepted). */
+void *dbeel_host_alloc(uint64_t bytes);
+void dbeel_host_free(void *p);
+
+int dbeel_last_stats(const dbeel_engine *e, dbeel_stats *out);
+const char *dbeel_last_error(const dbeel_engine *e);
+const char *dbeel_strerror(int code);
+int dbeel_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DBEEL_COMPACT_H */

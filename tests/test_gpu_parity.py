@@ -1,0 +1,248 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (dbeel_b200.capi -> libdbeel_compact.so),
+must produce byte-identical .data / .index / .bloom to the CPU oracle on the same inputs.
+
+Restates the reference's own compaction test (lsm_tree.rs:1328-1451) against the GPU engine and
+adds the byte-level, tie-break, tombstone, truncation and bloom cases the reference never tests.
+"""
+import dataclasses
+
+import numpy as np
+import pytest
+
+import oracle
+from dbeel_b200 import capi, sstable
+from dbeel_b200 import workloads as W
+
+from helpers import BASE_TS, assert_run_equal, model_compact, model_flush, nasty_keys, random_runs
+
+pytestmark = pytest.mark.gpu
+
+SEED = bytes(range(32))
+
+
+def u16key(n):
+    return int(n).to_bytes(2, "little")
+
+
+def check_against_oracle(engine, runs, keep, bloom_min_size=capi.DEFAULT_BLOOM_MIN_SIZE, what=""):
+    gd, gi, gb, gn = engine.compact(runs, keep_tombstones=keep, bloom_min_size=bloom_min_size, seed=SEED)
+    od, oi, ob, on = oracle.compact(runs, keep_tombstones=keep, bloom_min_size=bloom_min_size, seed=SEED)
+    assert gn == on, f"{what}: items_written {gn} != {on}"
+    assert_run_equal((gd, gi), (od, oi), what)
+    assert (gb is None) == (ob is None), f"{what}: bloom presence"
+    if ob is not None:
+        assert gb.size == ob.size
+        if not np.array_equal(gb, ob):
+            bad = int(np.flatnonzero(gb != ob)[0])
+            raise AssertionError(f"{what}: .bloom differs at byte {bad} of {ob.size}")
+    return gd, gi, gb, gn
+
+
+def test_cfg1_two_way_1k_keys(engine):
+    """BASELINE.json configs[0]: the reference's own CPU-runnable case."""
+    runs = W.make_merge_runs(W.CFG1)
+    _, _, gb, n = check_against_oracle(engine, runs, keep=False, what="cfg1")
+    assert gb is None and 1800 < n < 1900  # 226 KB of .data <= 1 MiB: no bloom (lsm_tree.rs:1027)
+    st = engine.stats()
+    assert st["entries_in"] == 2000 and st["entries_out"] == n and st["merge_passes"] == 1
+    assert st["key_prefix_len"] == 13  # 0xb0 'k' + 11 leading zero digits are common to ids < 1900
+
+
+def test_get_after_compaction(engine):
+    """lsm_tree.rs:1400-1446 through the GPU engine: flushes (0,32),(2,32),(4,32) -> (5, 92)."""
+    writes = [(u16key(n), u16key(n), BASE_TS + n) for n in range(94)]
+    writes += [(u16key(1), b"", BASE_TS + 1000), (u16key(4), b"", BASE_TS + 1001)]
+    runs = [(d, i) for d, i, _ in oracle.memtable_flushes(sstable.build_run(writes), capacity=32)]
+    gd, gi, gb, n = check_against_oracle(engine, runs, keep=False, what="get_after_compaction")
+    assert n == 92 and gb is None
+    got = {k: v for k, v, _ in sstable.parse_run(gd, gi)}
+    assert got[u16key(0)] == u16key(0) and got[u16key(2)] == u16key(2) and got[u16key(10)] == u16key(10)
+    assert u16key(1) not in got and u16key(4) not in got
+    assert [v for k, v, _ in sstable.parse_run(gd, gi) if u16key(1) <= k < u16key(5)] == [u16key(2), u16key(3)]
+    _, _, _, n2 = check_against_oracle(engine, runs, keep=True, what="get_after_compaction keep")
+    assert n2 == 94
+
+
+@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("keep", [False, True])
+def test_adversarial_keys_match_oracle_and_model(engine, seed, keep):
+    rng = np.random.default_rng(100 + seed)
+    pool = nasty_keys(rng, 3000, max_len=48)
+    k = int(rng.integers(1, 12))
+    runs = random_runs(rng, k, [int(rng.integers(0, 2500)) for _ in range(k)], pool)
+    gd, gi, _, n = check_against_oracle(engine, runs, keep, what=f"adversarial {seed}")
+    exp, en = model_compact(runs, keep)
+    assert n == en
+    assert_run_equal((gd, gi), exp, "vs model")
+
+
+def test_tie_breaks(engine):
+    k = b"same"
+    runs = [sstable.build_run([(k, b"r0", 5)]), sstable.build_run([(k, b"r1", 5)]), sstable.build_run([(k, b"r2", -7)])]
+    gd, gi, _, n = check_against_oracle(engine, runs, False, what="ties")
+    assert sstable.parse_run(gd, gi) == [(k, b"r1", 5)]
+    # signed 128-bit order: a negative timestamp loses to zero even though its low word is huge
+    runs = [sstable.build_run([(k, b"neg", -1)]), sstable.build_run([(k, b"zero", 0)]),
+            sstable.build_run([(k, b"big", (1 << 64) + 5)]), sstable.build_run([(k, b"lowword", (1 << 64) - 1)])]
+    gd, gi, _, _ = check_against_oracle(engine, runs, False, what="i128")
+    assert sstable.parse_run(gd, gi) == [(k, b"big", (1 << 64) + 5)]
+    # all timestamps equal over 9 runs: the last run position wins every key
+    ents = [(bytes([65 + j]), b"v", 7) for j in range(20)]
+    runs = [sstable.build_run([(kk, b"run%d" % r, ts) for kk, _, ts in ents]) for r in range(9)]
+    gd, gi, _, n = check_against_oracle(engine, runs, False, what="equal ts")
+    assert n == 20 and all(v == b"run8" for _, v, _ in sstable.parse_run(gd, gi))
+
+
+def test_tombstones(engine):
+    runs = [sstable.build_run([(b"a", b"v", 1), (b"b", b"v", 1), (b"c", b"", 1)]),
+            sstable.build_run([(b"a", b"", 2), (b"c", b"back", 2)])]
+    gd, gi, _, n = check_against_oracle(engine, runs, False, what="tomb drop")
+    assert sstable.parse_run(gd, gi) == [(b"b", b"v", 1), (b"c", b"back", 2)]
+    gd, gi, _, n = check_against_oracle(engine, runs, True, what="tomb keep")
+    assert sstable.parse_run(gd, gi) == [(b"a", b"", 2), (b"b", b"v", 1), (b"c", b"back", 2)]
+    only = [sstable.build_run([(bytes([j]), b"", 1) for j in range(50)])]
+    _, _, _, n = check_against_oracle(engine, only, False, what="all tombstones")
+    assert n == 0
+
+
+def test_empty_and_ragged_inputs(engine):
+    e = (np.zeros(0, np.uint8), np.zeros(0, np.uint8))
+    assert engine.compact([], False)[3] == 0
+    assert engine.compact([e, e], False)[3] == 0
+    a = sstable.build_run([(b"", b"empty key is a key", 1), (b"\x00", b"x", 1)])
+    check_against_oracle(engine, [e, a, e], False, what="empty runs around")
+    b = sstable.build_run([(bytes([n]), b"B" * n, 2) for n in range(5, 15)])
+    ragged = (b[0], np.concatenate([b[1], np.zeros(7, np.uint8)]))
+    check_against_oracle(engine, [a, ragged], False, what="ragged index tail")
+    # 37 runs of wildly different sizes (odd segment counts at every merge level)
+    rng = np.random.default_rng(9)
+    pool = nasty_keys(rng, 2000)
+    runs = random_runs(rng, 37, [int(rng.integers(0, 200)) if r % 5 else 1500 for r in range(37)], pool)
+    check_against_oracle(engine, runs, False, what="37 runs")
+
+
+def test_truncated_and_corrupt_runs_end_silently(engine):
+    """lsm_tree.rs:1014,1063: a run whose next record cannot be read/decoded simply ends."""
+    a = sstable.build_run([(bytes([n]), b"A" * 40, 1) for n in range(100)])
+    b = sstable.build_run([(bytes([n]), b"B" * 33, 2) for n in range(50, 150)])
+    cut = int.from_bytes(bytes(b[1][16 * 30:16 * 30 + 8]), "little") + 5
+    check_against_oracle(engine, [a, (b[0][:cut].copy(), b[1])], False, what="short data")
+    assert engine.stats()["runs_truncated"] == 1 and engine.stats()["entries_valid"] == 130
+    bad_idx = b[1].copy()
+    bad_idx[16 * 20 + 12] += 1  # full_size off by one: decode sees trailing bytes
+    check_against_oracle(engine, [a, (b[0], bad_idx)], False, what="bad full_size")
+    bad_data = b[0].copy()
+    off = int.from_bytes(bytes(b[1][16 * 10:16 * 10 + 8]), "little")
+    bad_data[off] += 1  # klen prefix disagrees with the index
+    check_against_oracle(engine, [(bad_data, b[1]), a], True, what="bad klen")
+    first = b[1].copy()
+    first[8] = 3  # very first record undecodable: whole run contributes nothing
+    check_against_oracle(engine, [a, (b[0], first)], False, what="first record bad")
+
+
+def test_long_shared_prefixes_and_window_ties(engine):
+    """Keys that agree on the common prefix AND on the whole 11-byte window (full compare path)."""
+    rng = np.random.default_rng(21)
+    stem = b"tenant/000042/collection/users/"  # 31 bytes shared by every key
+    mids = [b"AAAAAAAAAAAAAAAA", b"AAAAAAAAAAAAAAAB", b"AAAAAAAAAAA", b"AAAAAAAAAAAA", b"AAAAAAAAAAAB"]
+    pool = sorted({stem + m + bytes(rng.integers(97, 100, int(rng.integers(0, 6)), dtype=np.uint8))
+                   for m in mids for _ in range(200)})
+    runs = random_runs(rng, 5, 150, pool)
+    gd, gi, _, n = check_against_oracle(engine, runs, False, what="window ties")
+    assert engine.stats()["key_prefix_len"] >= len(stem)
+    exp, en = model_compact(runs, False)
+    assert_run_equal((gd, gi), exp, "window ties vs model")
+
+
+def test_bloom_small(engine):
+    rng = np.random.default_rng(5)
+    ents = [(b"\xb0k%015d" % n, bytes(rng.integers(0, 256, 90, dtype=np.uint8)), BASE_TS + n) for n in range(0, 6000, 2)]
+    run_a, run_b = sstable.build_run(ents[:2000]), sstable.build_run(ents[1000:])
+    gd, gi, gb, n = check_against_oracle(engine, [run_a, run_b], False, bloom_min_size=100_000, what="bloom")
+    assert gb is not None and n == 3000
+    assert all(oracle.bloom_check(gb, k) for k, _, _ in ents)
+    total = run_a[0].size + run_b[0].size
+    assert engine.compact([run_a, run_b], False, bloom_min_size=total, seed=SEED)[2] is None  # strict '>'
+    assert engine.compact([run_a, run_b], False, bloom_min_size=total - 1, seed=SEED)[2] is not None
+    # random seed (Bloom::new -> getrandom): still a valid filter for its own seed
+    _, _, rb, _ = engine.compact([run_a, run_b], False, bloom_min_size=100_000, seed=None)
+    assert all(oracle.bloom_check(rb, k) for k, _, _ in ents[:200])
+
+
+def test_variable_key_lengths_in_bloom(engine):
+    rng = np.random.default_rng(6)
+    pool = nasty_keys(rng, 4000, max_len=70)
+    runs = random_runs(rng, 4, 2500, pool, max_doc=200)
+    check_against_oracle(engine, runs, True, bloom_min_size=1000, what="bloom nasty keys")
+
+
+@pytest.mark.parametrize("cfg,keys", [(W.CFG2, 100_000), (W.CFG3, 20_000)])
+def test_scaled_benchmark_shapes(engine, cfg, keys):
+    c = W.scaled(cfg, keys)
+    runs = W.make_merge_runs(c)
+    _, _, gb, n = check_against_oracle(engine, runs, c.keep_tombstones, what=c.name)
+    assert gb is not None
+    eq = W.make_merge_runs(dataclasses.replace(c, seed=c.seed + 100), equal_ts=True)
+    check_against_oracle(engine, eq, True, what=c.name + " equal-ts keep")
+
+
+def test_unsorted_run_is_refused(engine):
+    ents = [(b"\xb0k%015d" % n, b"v" * 20, BASE_TS) for n in range(200)]
+    good = sstable.build_run(ents)
+    swapped = list(ents)
+    swapped[50], swapped[51] = swapped[51], swapped[50]
+    with pytest.raises(capi.DbeelError) as ei:
+        engine.compact([good, sstable.build_run(swapped)], False, flags=capi.FLAG_VERIFY_SORTED)
+    assert ei.value.code == capi.ERR_UNSORTED_RUN
+    engine.compact([good, good], False, flags=capi.FLAG_VERIFY_SORTED)  # sorted input passes the check
+
+
+def test_capacity_and_argument_errors(engine):
+    import ctypes as C
+    run = sstable.build_run([(b"k", b"v", 1)])
+    arr = (capi.Run * 1)(capi.Run(run[0].ctypes.data, run[0].size, run[1].ctypes.data, run[1].size))
+    small = np.empty(8, np.uint8)
+    out = capi.Out(small.ctypes.data, 8, 0, small.ctypes.data, 8, 0, None, 0, 0, 0)
+    opts = capi.make_opts()
+    assert capi.lib().dbeel_compact(engine._h, arr, 1, C.byref(opts), C.byref(out)) == capi.ERR_CAPACITY
+    assert capi.lib().dbeel_compact(engine._h, None, 1, C.byref(opts), C.byref(out)) == capi.ERR_INVALID_ARG
+    assert b"too small" in capi.lib().dbeel_strerror(capi.ERR_CAPACITY)
+
+
+def test_device_resident_entry_point(engine):
+    import torch
+    c = W.scaled(W.CFG2, 50_000)
+    runs = W.make_merge_runs(c)
+    dev = torch.device("cuda:0")
+    t_runs = [(torch.from_numpy(d).to(dev), torch.from_numpy(i).to(dev)) for d, i in runs]
+    opts = capi.make_opts(False, seed=SEED)
+    dc, ic, bc = capi.compact_bound([(d.size, i.size) for d, i in runs], opts)
+    od = torch.empty(dc + 16, dtype=torch.uint8, device=dev)
+    oi = torch.empty(ic + 16, dtype=torch.uint8, device=dev)
+    ob = torch.empty(bc + 16, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    dl, il, bl, n = engine.compact_device([(d.data_ptr(), d.numel(), i.data_ptr(), i.numel()) for d, i in t_runs],
+                                          (od.data_ptr(), dc, oi.data_ptr(), ic, ob.data_ptr(), bc), opts)
+    ed, ei, eb, en = oracle.compact(runs, False, seed=SEED)
+    assert n == en and bl == eb.size
+    assert_run_equal((od[:dl].cpu().numpy(), oi[:il].cpu().numpy()), (ed, ei), "device path")
+    assert np.array_equal(ob[:bl].cpu().numpy(), eb)
+    st = engine.stats()
+    assert st["ms_total"] > 0 and st["kernel_launches"] >= 10
+
+
+def test_flush_matches_memtable(engine):
+    """dbeel_flush == RedBlackTree inserts + flush_memtable_to_disk for one memtable's writes."""
+    rng = np.random.default_rng(31)
+    pool = nasty_keys(rng, 500)
+    writes = []
+    for s in range(3000):
+        k = pool[int(rng.integers(len(pool)))]
+        v = b"" if rng.random() < 0.1 else bytes(rng.integers(0, 256, int(rng.integers(1, 50)), dtype=np.uint8))
+        writes.append((k, v, BASE_TS - s))  # decreasing timestamps: arrival order must win, not time
+    batch = sstable.build_run(writes)
+    gd, gi, n = engine.flush(batch)
+    (od, oi, on), = oracle.memtable_flushes(batch, capacity=1 << 20)
+    assert n == on
+    assert_run_equal((gd, gi), (od, oi), "flush")
+    assert_run_equal((gd, gi), model_flush(batch, 1 << 20)[0], "flush vs model")
