@@ -1,0 +1,17 @@
+#!/bin/bash
+# One gpurun call: parity tests, bench, ncu launch list, ncu full capture of the hot kernels.
+set -u
+mkdir -p gpurun_out
+nvidia-smi -L
+echo "=== pytest -m gpu"
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -15
+echo "=== bench (default)"
+timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
+echo "=== ncu launch list"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
+grep -c . gpurun_out/launches.csv
+echo "=== ncu full"
+timeout 1500 ncu --set full --clock-control none --import-source on -k 'regex:k_gather|k_merge$|k_resolve|k_extract' -s 21 -c 7 \
+    -f -o gpurun_out/prof_full python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/bench_under_ncu_full.log 2>&1
+ls -la gpurun_out/

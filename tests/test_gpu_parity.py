@@ -136,8 +136,25 @@ def test_truncated_and_corrupt_runs_end_silently(engine):
     bad_data[off] += 1  # klen prefix disagrees with the index
     check_against_oracle(engine, [(bad_data, b[1]), a], True, what="bad klen")
     first = b[1].copy()
-    first[8] = 3  # very first record undecodable: whole run contributes nothing
+    first[12] += 2  # very first record undecodable (trailing bytes): whole run contributes nothing
     check_against_oracle(engine, [a, (b[0], first)], False, what="first record bad")
+    assert engine.stats()["entries_valid"] == 100
+
+
+def test_index_fields_are_verified_not_ignored(engine):
+    """Deliberate strictness (DESIGN.md "divergences"): the reference's compaction reader only
+    consults full_size and takes klen from the .data bytes (lsm_tree.rs:1164-1168), so a wrong
+    key_size / offset in .index goes unnoticed there -- while its own point reads
+    (lsm_tree.rs:628-632) trust key_size.  The engine treats such a record as undecodable and
+    ends the run at it, exactly like any other corrupt record."""
+    a = sstable.build_run([(bytes([n]), b"A" * 40, 1) for n in range(100)])
+    b = sstable.build_run([(bytes([n]), b"B" * 33, 2) for n in range(50, 150)])
+    bad = b[1].copy()
+    bad[16 * 40 + 8] += 1  # key_size of record 40
+    gd, gi, _, n = engine.compact([a, (b[0], bad)], False)
+    exp, en = model_compact([a, sstable.build_run([(bytes([n]), b"B" * 33, 2) for n in range(50, 90)])], False)
+    assert n == en and engine.stats()["runs_truncated"] == 1
+    assert_run_equal((gd, gi), exp, "key_size mismatch ends the run")
 
 
 def test_long_shared_prefixes_and_window_ties(engine):
