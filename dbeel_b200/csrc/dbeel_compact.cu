@@ -163,7 +163,8 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     p.keep_tombstones = o->keep_tombstones ? 1 : 0;
     p.mode_flush = flush ? 1 : 0;
     uint32_t levels = 0;
-    p.nseg[0] = n_runs;
+    p.nseg[0] = flush ? (N + kMergeTile - 1) / kMergeTile : n_runs;
+    if (p.nseg[0] > (1u << kMaxLevels)) return fail(e, DBEEL_ERR_TOO_MANY_ENTRIES, "arrival batch too large for one flush");
     while (p.nseg[levels] > 1) {
         p.nseg[levels + 1] = (p.nseg[levels] + 1) / 2;
         levels++;
@@ -182,8 +183,8 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     uint64_t o_seg[kMaxLevels + 1], o_tb[kMaxLevels];
     for (uint32_t l = 0; l <= levels; l++) o_seg[l] = carve(sizeof(Seg) * p.nseg[l]);
     for (uint32_t l = 0; l < levels; l++) o_tb[l] = carve(4ull * (p.nseg[l + 1] + 1));
-    const uint64_t tiles_ub = (uint64_t)(N + kMergeTile - 1) / kMergeTile + (n_runs + 1) / 2;
-    const uint64_t bounds_ub = tiles_ub + (n_runs + 1) / 2 + 1;
+    const uint64_t tiles_ub = (uint64_t)(N + kMergeTile - 1) / kMergeTile + (p.nseg[0] + 1) / 2;
+    const uint64_t bounds_ub = tiles_ub + (p.nseg[0] + 1) / 2 + 1;
     const uint64_t o_part = carve(4 * bounds_ub);
     const uint64_t scan_tiles = (uint64_t)(N + kResolveThreads - 1) / kResolveThreads;
     const uint64_t o_scan = carve(scan_tiles * 4); // status (zeroed per job)
@@ -261,13 +262,21 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
 
     // ---- K0/K1: prefix, validate, extract (+ conditional redo when a run was truncated)
     const uint32_t g256 = (N + 255) / 256;
-    k_common_prefix<<<1, 32, 0, s>>>(p, 0);
-    k_extract<<<g256, 256, 0, s>>>(p, 0);
-    k_common_prefix<<<1, 32, 0, s>>>(p, 1);
-    k_extract<<<g256, 256, 0, s>>>(p, 1);
-    k_plan<<<1, 1, 0, s>>>(p);
+    if (flush) {
+        k_flush_prefix_init<<<1, 1, 0, s>>>(p);
+        k_flush_prefix<<<g256, 256, 0, s>>>(p);
+        k_extract<<<g256, 256, 0, s>>>(p, 0);
+        k_plan<<<1, 1, 0, s>>>(p);
+        k_block_sort<<<p.nseg[0], kMergeThreads, 0, s>>>(p);
+    } else {
+        k_common_prefix<<<1, 32, 0, s>>>(p, 0);
+        k_extract<<<g256, 256, 0, s>>>(p, 0);
+        k_common_prefix<<<1, 32, 0, s>>>(p, 1);
+        k_extract<<<g256, 256, 0, s>>>(p, 1);
+        k_plan<<<1, 1, 0, s>>>(p);
+    }
     launches += 5;
-    if (o->flags & DBEEL_FLAG_VERIFY_SORTED) {
+    if (!flush && (o->flags & DBEEL_FLAG_VERIFY_SORTED)) {
         k_verify_sorted<<<g256, 256, 0, s>>>(p);
         launches++;
     }

@@ -51,7 +51,7 @@ constexpr int kResolveThreads = 512;
 constexpr int kGatherThreads = 256;
 constexpr int kGatherEntries = 256; // entries per CTA
 constexpr int kGatherLanes = 8;     // lanes cooperating on one entry
-constexpr int kMaxLevels = 10;      // ceil(log2(DBEEL_MAX_RUNS))
+constexpr int kMaxLevels = 16;      // >= ceil(log2(DBEEL_MAX_RUNS)); flush: 2^16 tiles of 2048 arrivals
 
 struct BloomParams {
     uint32_t *words;     // bit-vec storage inside the .bloom buffer (file offset 8); null = off
@@ -297,13 +297,25 @@ __global__ void k_plan(Params p) {
     if (threadIdx.x || blockIdx.x) return;
     Ctl *c = p.ctl;
     uint32_t total = 0, trunc = 0, flags = c->flags;
-    for (uint32_t r = 0; r < p.n_runs; r++) {
-        uint32_t cnt = p.first_bad[r];
-        if (cnt < p.runs[r].n_in) trunc++;
-        if (p.first_mismatch[r] < cnt) flags |= kFlagUnsorted;
-        p.seg[0][r].start = p.runs[r].base;
-        p.seg[0][r].len = cnt;
-        total += cnt;
+    if (p.mode_flush) {
+        // one arrival batch: level-0 segments are the tiles k_block_sort leaves sorted
+        uint32_t cnt = p.first_bad[0];
+        if (cnt < p.runs[0].n_in) trunc++;
+        for (uint32_t j = 0; j < p.nseg[0]; j++) {
+            uint32_t s0 = j * (uint32_t)kMergeTile;
+            p.seg[0][j].start = s0;
+            p.seg[0][j].len = cnt > s0 ? (cnt - s0 < (uint32_t)kMergeTile ? cnt - s0 : (uint32_t)kMergeTile) : 0;
+        }
+        total = cnt;
+    } else {
+        for (uint32_t r = 0; r < p.n_runs; r++) {
+            uint32_t cnt = p.first_bad[r];
+            if (cnt < p.runs[r].n_in) trunc++;
+            if (p.first_mismatch[r] < cnt) flags |= kFlagUnsorted;
+            p.seg[0][r].start = p.runs[r].base;
+            p.seg[0][r].len = cnt;
+            total += cnt;
+        }
     }
     for (uint32_t l = 0; l < p.n_levels; l++) {
         uint32_t pairs = p.nseg[l + 1], acc = 0;
@@ -320,6 +332,109 @@ __global__ void k_plan(Params p) {
     c->total = total;
     c->runs_truncated = trunc;
     c->flags = flags;
+}
+
+// ------------------------------------------------------------------------------------
+// Flush (memtable) front end.  An arrival batch is not sorted, so the common prefix is the
+// minimum over ALL keys of their common prefix with arrival 0, and the level-0 segments are
+// produced by an in-CTA merge sort of 2048-record tiles ordered by (key, arrival).
+
+__global__ void k_flush_prefix_init(Params p) {
+    if (threadIdx.x || blockIdx.x) return;
+    Ctl *c = p.ctl;
+    const uint8_t *ptr;
+    uint32_t kl = 0;
+    uint32_t L = 0;
+    if (p.runs[0].n_in && safe_key(p.runs[0], 0, &ptr, &kl)) {
+        L = kl < kMaxPrefix ? kl : kMaxPrefix;
+        for (uint32_t i = 0; i < L; i++) c->prefix[i] = __ldg(ptr + i);
+    }
+    c->prefix_len = L;
+}
+
+__global__ void __launch_bounds__(256) k_flush_prefix(Params p) {
+    Ctl *c = p.ctl;
+    uint32_t g = blockIdx.x * 256u + threadIdx.x;
+    uint32_t L = c->prefix_len; // only ever shrinks; a stale (larger) value is still an upper bound
+    if (g < p.n_total && L) {
+        const uint8_t *ptr;
+        uint32_t kl;
+        if (safe_key(p.runs[0], g, &ptr, &kl)) {
+            uint32_t m = kl < L ? kl : L, i = 0;
+            while (i < m && __ldg(ptr + i) == c->prefix[i]) i++;
+            L = i;
+        }
+        // an unreadable record is cut off by validation later; it must not widen the window
+    }
+    for (int o = 16; o; o >>= 1) {
+        uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, L, o);
+        L = other < L ? other : L;
+    }
+    if ((threadIdx.x & 31) == 0 && L < c->prefix_len) atomicMin(&c->prefix_len, L);
+}
+
+// total order for sorting arrivals: key, then arrival index (= gid)
+__device__ __forceinline__ bool arrival_less(const Params &p, uint32_t skip, const Rec &a, const Rec &b) {
+    int und;
+    int c = rec_cmp_window(a, b, &und);
+    if (und) c = full_key_cmp(p, a.w, b.w, skip);
+    return c < 0 || (c == 0 && a.w < b.w);
+}
+
+__global__ void __launch_bounds__(kMergeThreads) k_block_sort(Params p) {
+    __shared__ Rec s[kMergeTile + kMergeVT + 1];
+    const uint32_t cnt = p.ctl->total;
+    const uint32_t base = blockIdx.x * (uint32_t)kMergeTile;
+    if (base >= cnt) return;
+    const uint32_t n = cnt - base < (uint32_t)kMergeTile ? cnt - base : (uint32_t)kMergeTile;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t skip = p.ctl->prefix_len + kWindowBytes;
+    Rec inf;
+    inf.x = inf.y = inf.z = inf.w = 0xFFFFFFFFu; // clamp byte 0xFF: above every real record, never "undecided"
+    for (uint32_t i = tid; i < (uint32_t)kMergeTile; i += kMergeThreads) s[i] = i < n ? ld_rec(&p.rec_a[base + i]) : inf;
+    __syncthreads();
+    Rec r[kMergeVT];
+#pragma unroll
+    for (int i = 0; i < kMergeVT; i++) r[i] = s[tid * kMergeVT + i];
+    // odd-even transposition sort of the thread's 8 records
+#pragma unroll
+    for (int pass = 0; pass < kMergeVT; pass++) {
+#pragma unroll
+        for (int i = pass & 1; i + 1 < kMergeVT; i += 2) {
+            if (arrival_less(p, skip, r[i + 1], r[i])) { Rec t = r[i]; r[i] = r[i + 1]; r[i + 1] = t; }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kMergeVT; i++) s[tid * kMergeVT + i] = r[i];
+    __syncthreads();
+    for (uint32_t len = kMergeVT; len < (uint32_t)kMergeTile; len <<= 1) {
+        const uint32_t d0 = tid * kMergeVT;
+        const uint32_t pair = d0 / (2 * len);
+        const uint32_t diag = d0 - pair * 2 * len;
+        const Rec *A = s + pair * 2 * len;
+        const Rec *B = A + len;
+        uint32_t lo = diag > len ? diag - len : 0;
+        uint32_t hi = diag < len ? diag : len;
+        while (lo < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (!arrival_less(p, skip, B[diag - 1 - mid], A[mid])) lo = mid + 1; else hi = mid;
+        }
+        uint32_t ai = lo, bi = diag - lo;
+        Rec ak = A[ai < len ? ai : len - 1], bk = B[bi < len ? bi : len - 1];
+#pragma unroll
+        for (int i = 0; i < kMergeVT; i++) {
+            bool has_a = ai < len, has_b = bi < len;
+            bool take_b = has_b && (!has_a || arrival_less(p, skip, bk, ak));
+            r[i] = take_b ? bk : ak;
+            if (take_b) { bi++; if (bi < len) bk = B[bi]; } else { ai++; if (ai < len) ak = A[ai]; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kMergeVT; i++) s[d0 + i] = r[i];
+        __syncthreads();
+    }
+    for (uint32_t i = tid; i < n; i += kMergeThreads) st_rec(&p.rec_a[base + i], s[i]);
 }
 
 // ------------------------------------------------------------------------------------
