@@ -192,6 +192,8 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     const uint64_t o_aggc = carve(scan_tiles * 4), o_incc = carve(scan_tiles * 4);
     const uint64_t o_reca = carve(16ull * N), o_recb = carve(levels ? 16ull * N : 0);
     const uint64_t o_src = carve(8ull * N);
+    const uint64_t gather_tiles = (sh.data_total + kGatherTileBytes - 1) / kGatherTileBytes;
+    const uint64_t o_tfirst = carve(4ull * (gather_tiles + 2));
     int rc = ensure_device(e, &e->ws, &e->ws_cap, off);
     if (rc) return rc;
     rc = ensure_pinned(e, header_bytes + sizeof(Ctl) + 64);
@@ -213,6 +215,7 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     p.rec_a = reinterpret_cast<Rec *>(ws + o_reca);
     p.rec_b = reinterpret_cast<Rec *>(ws + o_recb);
     p.src_ptr = reinterpret_cast<unsigned long long *>(ws + o_src);
+    p.tile_first = reinterpret_cast<uint32_t *>(ws + o_tfirst);
     p.out_data = static_cast<uint8_t *>(out->data);
     p.out_index = static_cast<uint4 *>(out->index);
 
@@ -271,8 +274,8 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     } else {
         k_common_prefix<<<1, 32, 0, s>>>(p, 0);
         k_extract<<<g256, 256, 0, s>>>(p, 0);
-        k_common_prefix<<<1, 32, 0, s>>>(p, 1);
-        k_extract<<<g256, 256, 0, s>>>(p, 1);
+        k_common_prefix<<<1, 32, 0, s>>>(p, 1); // both no-ops unless a run was truncated
+        k_extract<<<g256 < 592 ? g256 : 592, 256, 0, s>>>(p, 1);
         k_plan<<<1, 1, 0, s>>>(p);
     }
     launches += 5;
@@ -308,7 +311,7 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
         k_bloom_frame<<<1, 1, 0, s>>>(static_cast<uint8_t *>(out->bloom), sh.bloom_words, p.bloom);
         launches++;
     }
-    k_gather<<<(N + kGatherEntries - 1) / kGatherEntries, kGatherThreads, 0, s>>>(p);
+    if (gather_tiles) k_gather<<<(uint32_t)gather_tiles, kGatherThreads, 0, s>>>(p);
     launches++;
     CU(cudaEventRecord(e->ev[EV_GATHER], s));
     CU(cudaGetLastError());
@@ -453,6 +456,10 @@ int dbeel_engine_create(int device, dbeel_engine **out) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return DBEEL_ERR_CUDA;
     if (prop.major != 10) return DBEEL_ERR_NO_DEVICE; // sm_100a SASS only: no fallback path
     if (cudaSetDevice(device) != cudaSuccess) return DBEEL_ERR_CUDA;
+    if (const char *g = getenv("DBEEL_L2_FETCH_GRANULARITY")) { // tuning experiment: 32 / 64 / 128 bytes
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
+        cudaGetLastError();
+    }
     dbeel_engine *e = new (std::nothrow) dbeel_engine();
     if (!e) return DBEEL_ERR_NOMEM;
     e->device = device;

@@ -45,12 +45,13 @@ struct Ctl {
 };
 
 constexpr int kMergeThreads = 256;
-constexpr int kMergeVT = 8;
-constexpr int kMergeTile = kMergeThreads * kMergeVT; // 2048 records = 32 KB of smem
-constexpr int kResolveThreads = 512;
+constexpr int kMergeVT = 7; // odd: threads walk smem at a 112-byte stride -> no bank conflicts
+constexpr int kMergeTile = kMergeThreads * kMergeVT; // 1792 records = 28 KB of smem
+constexpr int kResolveThreads = 256;
 constexpr int kGatherThreads = 256;
-constexpr int kGatherEntries = 256; // entries per CTA
-constexpr int kGatherLanes = 8;     // lanes cooperating on one entry
+constexpr int kGatherVecsPerThread = 4;
+constexpr unsigned long long kGatherTileBytes = 16ull * kGatherThreads * kGatherVecsPerThread; // 16 KB of output per CTA
+constexpr int kGatherMaxEntries = (int)(kGatherTileBytes / 32) + 2; // entries are >= 32 bytes
 constexpr int kMaxLevels = 16;      // >= ceil(log2(DBEEL_MAX_RUNS)); flush: 2^16 tiles of 2048 arrivals
 
 struct BloomParams {
@@ -84,6 +85,7 @@ struct Params {
     uint8_t *out_data;
     uint4 *out_index;
     unsigned long long *src_ptr; // [n_total] device address of each surviving entry's bytes
+    uint32_t *tile_first;        // [ceil(data bytes / 16 KB) + 1] entry holding each gather tile's first byte
     BloomParams bloom;
 };
 
@@ -240,8 +242,7 @@ __global__ void k_common_prefix(Params p, int validated) {
 __global__ void __launch_bounds__(256) k_extract(Params p, int redo) {
     Ctl *c = p.ctl;
     if (redo && !(c->flags & kFlagTruncated)) return;
-    uint32_t g = blockIdx.x * 256u + threadIdx.x;
-    if (g >= p.n_total) return;
+    for (uint32_t g = blockIdx.x * 256u + threadIdx.x; g < p.n_total; g += gridDim.x * 256u) {
     uint32_t r = find_run(p, g);
     const RunDesc rd = p.runs[r];
     uint32_t i = g - rd.base;
@@ -287,6 +288,7 @@ __global__ void __launch_bounds__(256) k_extract(Params p, int redo) {
         }
     }
     st_rec(&p.rec_a[g], out);
+    }
 }
 
 // ------------------------------------------------------------------------------------
@@ -480,7 +482,7 @@ __global__ void __launch_bounds__(128) k_merge_partition(Params p, uint32_t leve
     p.part[idx] = lo;
 }
 
-__global__ void __launch_bounds__(kMergeThreads) k_merge(Params p, uint32_t level, const Rec *src, Rec *dst) {
+__global__ void __launch_bounds__(kMergeThreads, 4) k_merge(Params p, uint32_t level, const Rec *src, Rec *dst) {
     __shared__ Rec s[kMergeTile + kMergeVT + 1];
     const uint32_t pairs = p.nseg[level + 1];
     const uint32_t *tb = p.tile_base[level];
@@ -534,24 +536,35 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(Params p, uint32_t leve
 }
 
 // ------------------------------------------------------------------------------------
-// K4: resolve + scan + .index.  One thread per merged record.
+// K4: resolve + scan + .index.  One thread per merged record, 256 records per CTA.
 //
 // A record that starts a group of equal keys ("head") picks the group's winner -- the entry
 // with the greatest (timestamp, run position), lsm_tree.rs:1041-1044 with mod.rs:75-81 and
 // lsm_tree.rs:58-65 -- and emits it unless it is a tombstone that must go
-// (lsm_tree.rs:1045-1046).  Timestamps are only read for groups of two or more.
-// Output offsets come from a single-pass decoupled look-back scan over (bytes, count).
+// (lsm_tree.rs:1045-1046).  Every thread fetches its own entry's index record, and -- only if
+// it sits in a group of two or more -- its own timestamp, so the loads of a group run in
+// parallel; the head then reduces over shared memory.  Output offsets come from a
+// single-pass decoupled look-back scan over (bytes, count).  Besides out_index / src_ptr the
+// kernel records, for every 16 KB tile of the output .data stream, which entry holds the
+// tile's first byte (tile_first) -- the gather kernel's only way into the entry list.
 
-__device__ __forceinline__ void ld_ts(const KeyRef &k, uint64_t *lo, uint64_t *hi) {
-    const uint8_t *t = k.entry + k.full_size - 16;
+__device__ __forceinline__ void ld_ts(const uint8_t *entry, uint32_t full_size, uint64_t *lo, uint64_t *hi) {
+    const uint8_t *t = entry + full_size - 16;
     *lo = ld_u64_unaligned(t);
     *hi = ld_u64_unaligned(t + 8);
 }
 
 __global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec *m) {
+    constexpr int NT = kResolveThreads;
+    constexpr int NW = NT / 32;
     __shared__ uint32_t s_tile;
-    __shared__ unsigned long long s_wb[kResolveThreads / 32];
-    __shared__ uint32_t s_wc[kResolveThreads / 32];
+    __shared__ Rec s_rec[NT + 2];
+    __shared__ unsigned long long s_entry[NT]; // device address of each record's entry
+    __shared__ uint32_t s_ks[NT], s_fs[NT];
+    __shared__ unsigned long long s_tlo[NT], s_thi[NT];
+    __shared__ uint8_t s_eqn[NT]; // record tid has the same key as record tid+1
+    __shared__ unsigned long long s_wb[NW];
+    __shared__ uint32_t s_wc[NW];
     __shared__ unsigned long long s_excl_b;
     __shared__ uint32_t s_excl_c;
     Ctl *c = p.ctl;
@@ -560,53 +573,80 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint32_t total = c->total;
-    if ((uint64_t)tile * kResolveThreads >= total) return;
-    const uint32_t n_tiles = (total + kResolveThreads - 1) / kResolveThreads;
+    if ((uint64_t)tile * NT >= total) return;
+    const uint32_t n_tiles = (total + NT - 1) / NT;
     const uint32_t skip = c->prefix_len + kWindowBytes;
-    const uint32_t i = tile * kResolveThreads + tid;
+    const uint32_t i0 = tile * NT;
+    const uint32_t i = i0 + tid;
+
+    // records i0-1 .. i0+NT (coalesced), so neighbours come from shared memory
+    for (uint32_t k = tid; k < NT + 2; k += NT) {
+        int64_t gi = (int64_t)i0 - 1 + k;
+        if (gi >= 0 && gi < (int64_t)total) s_rec[k] = ld_rec(&m[gi]);
+    }
+    __syncthreads();
+
+    const bool active = i < total;
+    bool eq_prev = false, eq_next = false;
+    Rec cur;
+    cur.x = cur.y = cur.z = cur.w = 0;
+    KeyRef me;
+    me.entry = nullptr; me.ptr = nullptr; me.klen = 0; me.full_size = 0;
+    if (active) {
+        cur = s_rec[tid + 1];
+        if (i) eq_prev = key_equal(p, skip, s_rec[tid], cur);
+        if (i + 1 < total) eq_next = key_equal(p, skip, cur, s_rec[tid + 2]);
+        me = key_of_gid(p, cur.w);
+        uint64_t tlo = 0, thi = 0;
+        if ((eq_prev || eq_next) && !p.mode_flush) ld_ts(me.entry, me.full_size, &tlo, &thi);
+        s_tlo[tid] = tlo;
+        s_thi[tid] = thi;
+    }
+    s_entry[tid] = (unsigned long long)(uintptr_t)me.entry;
+    s_ks[tid] = me.klen + 8;
+    s_fs[tid] = me.full_size;
+    s_eqn[tid] = eq_next ? 1 : 0;
+    __syncthreads();
 
     uint32_t keep = 0, ks = 0, fs = 0;
     unsigned long long src = 0;
-    if (i < total) {
-        Rec cur = ld_rec(&m[i]);
-        bool head = true;
-        if (i) head = !key_equal(p, skip, ld_rec(&m[i - 1]), cur);
-        if (head) {
-            uint32_t w = cur.w;
-            KeyRef wk;
-            bool have_wk = false;
-            uint32_t jn = i + 1;
-            if (jn < total) {
-                Rec nx = ld_rec(&m[jn]);
-                if (key_equal(p, skip, cur, nx)) {
-                    wk = key_of_gid(p, w);
-                    have_wk = true;
-                    uint64_t wlo = 0, whi = 0;
-                    if (!p.mode_flush) ld_ts(wk, &wlo, &whi);
-                    do {
-                        KeyRef ck = key_of_gid(p, nx.w);
-                        bool better = true; // flush: the later arrival always wins (lib.rs:509-511)
-                        if (!p.mode_flush) {
-                            uint64_t clo, chi;
-                            ld_ts(ck, &clo, &chi);
-                            // equal timestamps: the later run position (larger gid) wins
-                            better = !ts_greater(wlo, whi, clo, chi);
-                            if (better) { wlo = clo; whi = chi; }
-                        }
-                        if (better) { w = nx.w; wk = ck; }
-                        jn++;
-                        if (jn >= total) break;
-                        nx = ld_rec(&m[jn]);
-                    } while (key_equal(p, skip, cur, nx));
+    if (active && !eq_prev) { // head of its group
+        uint32_t w = tid; // winner so far, as an index into this tile's shared arrays
+        ks = s_ks[tid]; fs = s_fs[tid]; src = s_entry[tid];
+        if (eq_next) {
+            uint64_t wlo = s_tlo[tid], whi = s_thi[tid];
+            uint32_t j = tid;
+            bool more = true;
+            while (more && j + 1 < NT) { // members inside the tile
+                j++;
+                // the later member wins ties: it comes from a later run position (larger gid);
+                // in flush mode the later arrival always wins (lib.rs:509-511)
+                bool better = p.mode_flush || !ts_greater(wlo, whi, s_tlo[j], s_thi[j]);
+                if (better) { w = j; wlo = s_tlo[j]; whi = s_thi[j]; }
+                more = s_eqn[j] != 0;
+            }
+            ks = s_ks[w]; fs = s_fs[w]; src = s_entry[w];
+            if (more) { // the group runs past the tile: finish it from global memory
+                uint32_t gj = i0 + NT; // first record of the next tile (known equal: s_eqn[NT-1])
+                while (true) {
+                    Rec nx = ld_rec(&m[gj]);
+                    KeyRef ck = key_of_gid(p, nx.w);
+                    bool better = true;
+                    if (!p.mode_flush) {
+                        uint64_t clo, chi;
+                        ld_ts(ck.entry, ck.full_size, &clo, &chi);
+                        better = !ts_greater(wlo, whi, clo, chi);
+                        if (better) { wlo = clo; whi = chi; }
+                    }
+                    if (better) { ks = ck.klen + 8; fs = ck.full_size; src = (unsigned long long)(uintptr_t)ck.entry; }
+                    gj++;
+                    if (gj >= total) break;
+                    if (!key_equal(p, skip, nx, ld_rec(&m[gj]))) break;
                 }
             }
-            if (!have_wk) wk = key_of_gid(p, w);
-            ks = wk.klen + 8;
-            fs = wk.full_size;
-            src = (unsigned long long)(uintptr_t)wk.entry;
-            bool tomb = fs == ks + 24;
-            keep = (p.keep_tombstones || p.mode_flush || !tomb) ? 1u : 0u;
         }
+        bool tomb = fs == ks + 24;
+        keep = (p.keep_tombstones || p.mode_flush || !tomb) ? 1u : 0u;
     }
 
     // block-wide inclusive scan of (bytes, count)
@@ -623,18 +663,17 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec
     if (lane == 31) { s_wb[warp] = ib; s_wc[warp] = ic; }
     __syncthreads();
     if (warp == 0) {
-        unsigned long long wb = lane < kResolveThreads / 32 ? s_wb[lane] : 0ull;
-        uint32_t wc = lane < kResolveThreads / 32 ? s_wc[lane] : 0u;
+        unsigned long long wb = lane < NW ? s_wb[lane] : 0ull;
+        uint32_t wc = lane < NW ? s_wc[lane] : 0u;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             unsigned long long tb = __shfl_up_sync(0xFFFFFFFFu, wb, o);
             uint32_t tc = __shfl_up_sync(0xFFFFFFFFu, wc, o);
             if (lane >= (uint32_t)o) { wb += tb; wc += tc; }
         }
-        // inclusive over warps; block aggregate sits in the last used lane
-        unsigned long long agg_b = __shfl_sync(0xFFFFFFFFu, wb, kResolveThreads / 32 - 1);
-        uint32_t agg_c = __shfl_sync(0xFFFFFFFFu, wc, kResolveThreads / 32 - 1);
-        if (lane < kResolveThreads / 32) { s_wb[lane] = wb; s_wc[lane] = wc; }
+        unsigned long long agg_b = __shfl_sync(0xFFFFFFFFu, wb, NW - 1);
+        uint32_t agg_c = __shfl_sync(0xFFFFFFFFu, wc, NW - 1);
+        if (lane < NW) { s_wb[lane] = wb; s_wc[lane] = wc; }
 
         // decoupled look-back
         volatile uint32_t *status = p.scan_status;
@@ -695,6 +734,9 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec
         uint32_t pos = s_excl_c + (warp ? s_wc[warp - 1] : 0u) + (ic - vc);
         p.out_index[pos] = make_uint4((uint32_t)off, (uint32_t)(off >> 32), ks, fs);
         p.src_ptr[pos] = src;
+        // every gather tile whose first byte lies in [off, off + fs) starts inside this entry
+        unsigned long long b = (off + kGatherTileBytes - 1) / kGatherTileBytes;
+        for (; b * kGatherTileBytes < off + fs; b++) p.tile_first[b] = pos;
     }
 }
 
@@ -702,67 +744,165 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec
 // K5: gather + bloom -- the roofline kernel.  Every surviving entry's bytes are read once
 // from its input run and written once at its output offset.
 //
-// Phase 1 (bloom on): one thread per entry hashes the key (2 x SipHash-1-3, one walk) and
-// sets k bits with atomicOr; the filter (<= ~10 MB at the benchmark shapes) lives in L2.
-// The key bytes it touches are the head of the entry that phase 2 copies next.
-// Phase 2: kGatherLanes lanes per entry.  Destination 16-byte vectors that lie wholly inside
-// the entry are produced from two aligned 16-byte source loads and a byte funnel shift
-// (source and destination are mutually misaligned by an arbitrary byte count); the ragged
-// head and tail (< 16 bytes each) are copied bytewise.
+// The output .data stream is cut into 16 KB tiles (1024 aligned 16-byte vectors), one CTA
+// each.  The CTA stages the metadata of the entries that overlap its tile in shared memory,
+// maps every vector to the entry holding the vector's first byte (mark + max-scan), and then
+// each thread produces 4 vectors, a warp writing 512 contiguous bytes per store:
+//   * a vector that lies inside one entry = two aligned 16-byte source loads + a byte funnel
+//     shift (source and destination are misaligned by an arbitrary byte count);
+//   * a vector that straddles an entry boundary is assembled bytewise.
+// No byte stores, no inter-CTA overlap: every output vector has exactly one writer.
+// Bloom (fused epilogue): after its stores are issued the CTA hashes the key of every entry
+// whose first byte lies in its tile (2 x SipHash-1-3 in one walk, one thread per entry) and
+// sets k bits with atomicOr -- the filter (<= ~10 MB at the benchmark shapes) stays
+// L2-resident and the key bytes are lines the copy has just touched.
+
+__device__ __forceinline__ uint4 realign16_sel(uint4 A, uint4 B, uint32_t sh) {
+    // branch-free version of realign16 for a per-lane shift
+    const uint32_t bits = (sh & 3) * 8;
+    const bool s2 = sh & 8, s1 = sh & 4;
+    uint32_t c0 = s2 ? A.z : A.x, c1 = s2 ? A.w : A.y, c2 = s2 ? B.x : A.z;
+    uint32_t c3 = s2 ? B.y : A.w, c4 = s2 ? B.z : B.x, c5 = s2 ? B.w : B.y;
+    uint32_t d0 = s1 ? c1 : c0, d1 = s1 ? c2 : c1, d2 = s1 ? c3 : c2, d3 = s1 ? c4 : c3, d4 = s1 ? c5 : c4;
+    return make_uint4(__funnelshift_r(d0, d1, bits), __funnelshift_r(d1, d2, bits), __funnelshift_r(d2, d3, bits),
+                      __funnelshift_r(d3, d4, bits));
+}
 
 __global__ void __launch_bounds__(kGatherThreads) k_gather(Params p) {
+    constexpr int NT = kGatherThreads;
+    constexpr int VPT = kGatherVecsPerThread;
+    constexpr int NV = NT * VPT; // vectors per tile
+    __shared__ long long s_r0[kGatherMaxEntries];            // entry start relative to the tile (may be < 0)
+    __shared__ unsigned long long s_src[kGatherMaxEntries]; // device address of the entry's bytes
+    __shared__ uint32_t s_fs[kGatherMaxEntries], s_ks[kGatherMaxEntries];
+    __shared__ uint16_t s_vec[NV];
+    __shared__ uint32_t s_wmax[NT / 32];
     const Ctl *c = p.ctl;
+    const unsigned long long out_len = c->out_data_len;
+    const unsigned long long T0 = (unsigned long long)blockIdx.x * kGatherTileBytes;
+    if (T0 >= out_len) return;
     const uint32_t n_out = c->out_items;
-    const uint32_t e0 = blockIdx.x * kGatherEntries;
-    if (e0 >= n_out) return;
-    const uint32_t e1 = e0 + kGatherEntries < n_out ? e0 + kGatherEntries : n_out;
-    const uint32_t tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tile_len = out_len - T0 < kGatherTileBytes ? (uint32_t)(out_len - T0) : (uint32_t)kGatherTileBytes;
+    const uint32_t e_lo = p.tile_first[blockIdx.x];
+    uint32_t e_hi = n_out - 1;
+    if (T0 + kGatherTileBytes < out_len) e_hi = p.tile_first[blockIdx.x + 1];
+    const uint32_t ne = e_hi - e_lo + 1; // <= kGatherMaxEntries: every entry is >= 32 bytes
 
-    if (p.bloom.words != nullptr) {
-        for (uint32_t e = e0 + tid; e < e1; e += kGatherThreads) {
-            uint4 rec = p.out_index[e];
-            const uint8_t *key = reinterpret_cast<const uint8_t *>((uintptr_t)p.src_ptr[e]) + 8;
-            uint64_t klen = rec.z - 8;
-            uint64_t h0, h1;
-            sip13_pair_vec_u8(p.bloom.sip, klen, [key](uint64_t j) { return ld_u64_unaligned(key + 8 * j); }, &h0, &h1);
-            for (uint32_t k = 0; k < p.bloom.k_num; k++) {
-                uint64_t bit = fastmod(bloom_hash_i(h0, h1, k), p.bloom.bits, p.bloom.bits_magic);
-                atomicOr(&p.bloom.words[bit >> 5], 1u << (bit & 31));
+    // ---- stage entry metadata, mark each entry's first vector, hash keys
+    for (uint32_t v = tid; v < NV; v += NT) s_vec[v] = 0;
+    __syncthreads();
+    for (uint32_t j = tid; j < ne; j += NT) {
+        uint4 rec = p.out_index[e_lo + j];
+        const unsigned long long d0 = (unsigned long long)rec.x | ((unsigned long long)rec.y << 32);
+        const long long r0 = (long long)d0 - (long long)T0;
+        const unsigned long long src = p.src_ptr[e_lo + j];
+        s_r0[j] = r0;
+        s_src[j] = src;
+        s_fs[j] = rec.w;
+        const uint32_t fv = r0 <= 0 ? 0u : (uint32_t)((r0 + 15) >> 4); // first vector starting inside the entry
+        if (fv < NV) s_vec[fv] = (uint16_t)j; // unique per entry (entries are >= 32 bytes)
+        s_ks[j] = rec.z;
+    }
+    __syncthreads();
+
+    // ---- inclusive max-scan of the marks: s_vec[v] = entry that holds byte 16*v of the tile
+    {
+        uint32_t m[VPT];
+        uint32_t run = 0;
+#pragma unroll
+        for (int k = 0; k < VPT; k++) {
+            uint32_t x = s_vec[tid * VPT + k];
+            run = x > run ? x : run;
+            m[k] = run;
+        }
+        uint32_t incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= (uint32_t)o) incl = t > incl ? t : incl;
+        }
+        if (lane == 31) s_wmax[warp] = incl;
+        __syncthreads();
+        uint32_t before = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+        if (lane == 0) before = 0;
+        for (uint32_t w = 0; w < warp; w++) before = s_wmax[w] > before ? s_wmax[w] : before;
+#pragma unroll
+        for (int k = 0; k < VPT; k++) s_vec[tid * VPT + k] = (uint16_t)(m[k] > before ? m[k] : before);
+    }
+    __syncthreads();
+
+    // ---- copy: thread t produces vectors t, t+NT, t+2NT, ...
+    uint8_t *dst_tile = p.out_data + T0;
+    uint4 A[VPT], B[VPT];
+    uint32_t sh[VPT];
+    bool pure[VPT];
+#pragma unroll
+    for (int k = 0; k < VPT; k++) {
+        const uint32_t v = tid + k * NT;
+        const uint32_t b0 = v * 16;
+        pure[k] = false;
+        sh[k] = 0;
+        if (b0 + 16 <= tile_len) {
+            const uint32_t j = s_vec[v];
+            const long long r0 = s_r0[j];
+            if ((long long)b0 + 16 <= r0 + (long long)s_fs[j]) {
+                const uintptr_t sa = (uintptr_t)s_src[j] + (uintptr_t)((long long)b0 - r0);
+                sh[k] = (uint32_t)(sa & 15);
+                const uint4 *sv = reinterpret_cast<const uint4 *>(sa - sh[k]);
+                A[k] = __ldg(sv);
+                B[k] = __ldg(sh[k] ? sv + 1 : sv);
+                pure[k] = true;
             }
         }
     }
+#pragma unroll
+    for (int k = 0; k < VPT; k++) {
+        const uint32_t v = tid + k * NT;
+        if (pure[k]) reinterpret_cast<uint4 *>(dst_tile)[v] = realign16_sel(A[k], B[k], sh[k]);
+    }
+    // ---- vectors that straddle an entry boundary (or the end of the stream): bytewise
+#pragma unroll
+    for (int k = 0; k < VPT; k++) {
+        const uint32_t v = tid + k * NT;
+        const uint32_t b0 = v * 16;
+        if (pure[k] || b0 >= tile_len) continue;
+        uint32_t j = s_vec[v];
+        long long r0 = s_r0[j];
+        long long r1 = r0 + (long long)s_fs[j];
+        const uint8_t *src = reinterpret_cast<const uint8_t *>((uintptr_t)s_src[j]);
+        uint32_t w[4] = {0, 0, 0, 0};
+        const uint32_t nb = tile_len - b0 < 16 ? tile_len - b0 : 16;
+        for (uint32_t b = 0; b < nb; b++) {
+            const long long pos = (long long)b0 + b;
+            if (pos >= r1) { // next entry (entries are >= 32 bytes: at most one switch per vector)
+                j++;
+                r0 = s_r0[j];
+                r1 = r0 + (long long)s_fs[j];
+                src = reinterpret_cast<const uint8_t *>((uintptr_t)s_src[j]);
+            }
+            w[b >> 2] |= (uint32_t)__ldg(src + (pos - r0)) << ((b & 3) * 8);
+        }
+        if (nb == 16) {
+            reinterpret_cast<uint4 *>(dst_tile)[v] = make_uint4(w[0], w[1], w[2], w[3]);
+        } else { // ragged end of the stream: never write past out_data_len
+            for (uint32_t b = 0; b < nb; b++) dst_tile[b0 + b] = (uint8_t)(w[b >> 2] >> ((b & 3) * 8));
+        }
+    }
 
-    const uint32_t grp = tid / kGatherLanes, gl = tid % kGatherLanes;
-    constexpr uint32_t n_grp = kGatherThreads / kGatherLanes;
-    for (uint32_t e = e0 + grp; e < e1; e += n_grp) {
-        uint4 rec = p.out_index[e];
-        const uint64_t d0 = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
-        const uint32_t fs = rec.w;
-        const uint64_t d1 = d0 + fs;
-        const uint8_t *src = reinterpret_cast<const uint8_t *>((uintptr_t)p.src_ptr[e]);
-        uint8_t *dst = p.out_data;
-        uint64_t ha = (d0 + 15) & ~15ull; // first 16-aligned output offset >= d0
-        if (ha > d1) ha = d1;
-        uint64_t tb = d1 & ~15ull;        // last 16-aligned output offset <= d1
-        if (tb < ha) tb = ha;
-        for (uint64_t b = d0 + gl; b < ha; b += kGatherLanes) dst[b] = __ldg(src + (b - d0));
-        for (uint64_t b = tb + gl; b < d1; b += kGatherLanes) dst[b] = __ldg(src + (b - d0));
-        const uint32_t nvec = (uint32_t)((tb - ha) >> 4);
-        if (nvec) {
-            uintptr_t sa = reinterpret_cast<uintptr_t>(src) + (ha - d0);
-            const uint32_t sh = (uint32_t)(sa & 15);
-            const uint4 *sv = reinterpret_cast<const uint4 *>(sa - sh);
-            uint4 *dv = reinterpret_cast<uint4 *>(dst + ha);
-            for (uint32_t v = gl; v < nvec; v += kGatherLanes) {
-                uint4 A = __ldg(sv + v);
-                uint4 o = A;
-                if (sh) {
-                    uint4 B = __ldg(sv + v + 1);
-                    uint32_t a4[4] = {A.x, A.y, A.z, A.w}, b4[4] = {B.x, B.y, B.z, B.w}, o4[4];
-                    realign16(a4, b4, sh, o4);
-                    o = make_uint4(o4[0], o4[1], o4[2], o4[3]);
-                }
-                dv[v] = o;
+    // ---- bloom: entries whose first byte lies in this tile (each entry belongs to exactly one tile).
+    // Done last so the copy's loads are in flight first; the key bytes are L1/L2-hot by now.
+    if (p.bloom.words != nullptr) {
+        for (uint32_t j = tid; j < ne; j += NT) {
+            const long long r0 = s_r0[j];
+            if (r0 < 0 || r0 >= (long long)kGatherTileBytes) continue;
+            const uint8_t *key = reinterpret_cast<const uint8_t *>((uintptr_t)s_src[j]) + 8;
+            const uint64_t klen = s_ks[j] - 8;
+            uint64_t h0, h1;
+            sip13_pair_vec_u8(p.bloom.sip, klen, [key](uint64_t q) { return ld_u64_unaligned(key + 8 * q); }, &h0, &h1);
+            for (uint32_t k = 0; k < p.bloom.k_num; k++) {
+                uint64_t bit = fastmod(bloom_hash_i(h0, h1, k), p.bloom.bits, p.bloom.bits_magic);
+                atomicOr(&p.bloom.words[bit >> 5], 1u << (bit & 31));
             }
         }
     }

@@ -7,6 +7,8 @@ echo "=== pytest -m gpu"
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -15
 echo "=== bench (default)"
 timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
+echo "=== bench (L2 fetch granularity 32)"
+DBEEL_L2_FETCH_GRANULARITY=32 timeout 900 python bench.py --no-cpu --steps 30 > gpurun_out/bench_l2_32.json 2> gpurun_out/bench_l2_32.err; cat gpurun_out/bench_l2_32.json
 echo "=== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
