@@ -186,11 +186,10 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     const uint64_t tiles_ub = (uint64_t)(N + kMergeTile - 1) / kMergeTile + (p.nseg[0] + 1) / 2;
     const uint64_t bounds_ub = tiles_ub + (p.nseg[0] + 1) / 2 + 1;
     const uint64_t o_part = carve(4 * bounds_ub);
-    const uint64_t scan_tiles = (uint64_t)(N + kResolveThreads - 1) / kResolveThreads;
-    const uint64_t o_scan = carve(scan_tiles * 4); // status (zeroed per job)
-    const uint64_t o_aggb = carve(scan_tiles * 8), o_incb = carve(scan_tiles * 8);
-    const uint64_t o_aggc = carve(scan_tiles * 4), o_incc = carve(scan_tiles * 4);
-    const uint64_t o_reca = carve(16ull * N), o_recb = carve(levels ? 16ull * N : 0);
+    const uint64_t scan_tile = (uint64_t)kScanThreads * kScanItemsPerThread;
+    const uint64_t scan_tiles = (N + scan_tile - 1) / scan_tile;
+    const uint64_t o_scan = carve(scan_tiles * 16); // two 64-bit descriptors per tile (zeroed per job)
+    const uint64_t o_reca = carve(16ull * N), o_recb = carve(16ull * N);
     const uint64_t o_src = carve(8ull * N);
     const uint64_t gather_tiles = (sh.data_total + kGatherTileBytes - 1) / kGatherTileBytes;
     const uint64_t o_tfirst = carve(4ull * (gather_tiles + 2));
@@ -207,11 +206,8 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     for (uint32_t l = 0; l <= levels; l++) p.seg[l] = reinterpret_cast<Seg *>(ws + o_seg[l]);
     for (uint32_t l = 0; l < levels; l++) p.tile_base[l] = reinterpret_cast<uint32_t *>(ws + o_tb[l]);
     p.part = reinterpret_cast<uint32_t *>(ws + o_part);
-    p.scan_status = reinterpret_cast<uint32_t *>(ws + o_scan);
-    p.scan_agg_bytes = reinterpret_cast<unsigned long long *>(ws + o_aggb);
-    p.scan_inc_bytes = reinterpret_cast<unsigned long long *>(ws + o_incb);
-    p.scan_agg_cnt = reinterpret_cast<uint32_t *>(ws + o_aggc);
-    p.scan_inc_cnt = reinterpret_cast<uint32_t *>(ws + o_incc);
+    p.scan_desc_bytes = reinterpret_cast<unsigned long long *>(ws + o_scan);
+    p.scan_desc_cnt = p.scan_desc_bytes + scan_tiles;
     p.rec_a = reinterpret_cast<Rec *>(ws + o_reca);
     p.rec_b = reinterpret_cast<Rec *>(ws + o_recb);
     p.src_ptr = reinterpret_cast<unsigned long long *>(ws + o_src);
@@ -259,7 +255,7 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     cudaStream_t s = e->stream;
     uint32_t launches = 0;
     CU(cudaMemcpyAsync(ws, h, header_bytes, cudaMemcpyHostToDevice, s));
-    CU(cudaMemsetAsync(ws + o_scan, 0, scan_tiles * 4, s));
+    CU(cudaMemsetAsync(ws + o_scan, 0, scan_tiles * 16, s));
     if (sh.bloom_file) CU(cudaMemsetAsync(out->bloom, 0, sh.bloom_file, s));
     if (record_start) CU(cudaEventRecord(e->ev[EV_START], s));
 
@@ -302,8 +298,10 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     CU(cudaEventRecord(e->ev[EV_MERGE], s));
 
     // ---- K4: resolve + scan + .index
-    k_resolve<<<(uint32_t)scan_tiles, kResolveThreads, 0, s>>>(p, src);
-    launches++;
+    uint4 *res = reinterpret_cast<uint4 *>(dst); // the ping-pong buffer that does not hold the merged order
+    k_resolve<<<(N + kResolveThreads - 1) / kResolveThreads, kResolveThreads, 0, s>>>(p, src, res);
+    k_scan_emit<<<(uint32_t)scan_tiles, kScanThreads, 0, s>>>(p, res);
+    launches += 2;
     CU(cudaEventRecord(e->ev[EV_RESOLVE], s));
 
     // ---- K5: gather + bloom

@@ -48,6 +48,8 @@ constexpr int kMergeThreads = 256;
 constexpr int kMergeVT = 7; // odd: threads walk smem at a 112-byte stride -> no bank conflicts
 constexpr int kMergeTile = kMergeThreads * kMergeVT; // 1792 records = 28 KB of smem
 constexpr int kResolveThreads = 256;
+constexpr int kScanThreads = 256;
+constexpr int kScanItemsPerThread = 8; // 2048 records per scan tile
 constexpr int kGatherThreads = 256;
 constexpr int kGatherVecsPerThread = 4;
 constexpr unsigned long long kGatherTileBytes = 16ull * kGatherThreads * kGatherVecsPerThread; // 16 KB of output per CTA
@@ -76,9 +78,7 @@ struct Params {
     uint32_t *part; // merge-path split points of the current level
     Rec *rec_a, *rec_b;
     // resolve / scan
-    uint32_t *scan_status;
-    unsigned long long *scan_agg_bytes, *scan_inc_bytes;
-    uint32_t *scan_agg_cnt, *scan_inc_cnt;
+    unsigned long long *scan_desc_bytes, *scan_desc_cnt; // [scan tiles] status(2) | value(62), zeroed per job
     int keep_tombstones;
     int mode_flush; // 1: arrival batch -- winner = last arrival, tombstones kept
     // outputs
@@ -536,17 +536,16 @@ __global__ void __launch_bounds__(kMergeThreads, 4) k_merge(Params p, uint32_t l
 }
 
 // ------------------------------------------------------------------------------------
-// K4: resolve + scan + .index.  One thread per merged record, 256 records per CTA.
+// K4a: resolve.  One thread per merged record, no ordering between CTAs.
 //
 // A record that starts a group of equal keys ("head") picks the group's winner -- the entry
 // with the greatest (timestamp, run position), lsm_tree.rs:1041-1044 with mod.rs:75-81 and
 // lsm_tree.rs:58-65 -- and emits it unless it is a tombstone that must go
 // (lsm_tree.rs:1045-1046).  Every thread fetches its own entry's index record, and -- only if
 // it sits in a group of two or more -- its own timestamp, so the loads of a group run in
-// parallel; the head then reduces over shared memory.  Output offsets come from a
-// single-pass decoupled look-back scan over (bytes, count).  Besides out_index / src_ptr the
-// kernel records, for every 16 KB tile of the output .data stream, which entry holds the
-// tile's first byte (tile_first) -- the gather kernel's only way into the entry list.
+// parallel; the head then reduces over shared memory.
+// Output, in merged order: res[i] = {entry address (u64), key_size, full_size or 0 if nothing
+// is emitted at position i}.
 
 __device__ __forceinline__ void ld_ts(const uint8_t *entry, uint32_t full_size, uint64_t *lo, uint64_t *hi) {
     const uint8_t *t = entry + full_size - 16;
@@ -554,29 +553,19 @@ __device__ __forceinline__ void ld_ts(const uint8_t *entry, uint32_t full_size, 
     *hi = ld_u64_unaligned(t + 8);
 }
 
-__global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec *m) {
+__global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec *m, uint4 *res) {
     constexpr int NT = kResolveThreads;
-    constexpr int NW = NT / 32;
-    __shared__ uint32_t s_tile;
     __shared__ Rec s_rec[NT + 2];
     __shared__ unsigned long long s_entry[NT]; // device address of each record's entry
     __shared__ uint32_t s_ks[NT], s_fs[NT];
     __shared__ unsigned long long s_tlo[NT], s_thi[NT];
     __shared__ uint8_t s_eqn[NT]; // record tid has the same key as record tid+1
-    __shared__ unsigned long long s_wb[NW];
-    __shared__ uint32_t s_wc[NW];
-    __shared__ unsigned long long s_excl_b;
-    __shared__ uint32_t s_excl_c;
-    Ctl *c = p.ctl;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(&c->ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
+    const Ctl *c = p.ctl;
+    const uint32_t tid = threadIdx.x;
     const uint32_t total = c->total;
-    if ((uint64_t)tile * NT >= total) return;
-    const uint32_t n_tiles = (total + NT - 1) / NT;
+    const uint32_t i0 = blockIdx.x * NT;
+    if (i0 >= total) return;
     const uint32_t skip = c->prefix_len + kWindowBytes;
-    const uint32_t i0 = tile * NT;
     const uint32_t i = i0 + tid;
 
     // records i0-1 .. i0+NT (coalesced), so neighbours come from shared memory
@@ -607,10 +596,11 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec
     s_fs[tid] = me.full_size;
     s_eqn[tid] = eq_next ? 1 : 0;
     __syncthreads();
+    if (!active) return;
 
     uint32_t keep = 0, ks = 0, fs = 0;
     unsigned long long src = 0;
-    if (active && !eq_prev) { // head of its group
+    if (!eq_prev) { // head of its group
         uint32_t w = tid; // winner so far, as an index into this tile's shared arrays
         ks = s_ks[tid]; fs = s_fs[tid]; src = s_entry[tid];
         if (eq_next) {
@@ -648,17 +638,59 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec
         bool tomb = fs == ks + 24;
         keep = (p.keep_tombstones || p.mode_flush || !tomb) ? 1u : 0u;
     }
+    res[i] = make_uint4((uint32_t)src, (uint32_t)(src >> 32), ks, keep ? fs : 0u);
+}
 
-    // block-wide inclusive scan of (bytes, count)
-    unsigned long long vb = keep ? fs : 0ull;
-    uint32_t vc = keep;
-    unsigned long long ib = vb;
-    uint32_t ic = vc;
+// ------------------------------------------------------------------------------------
+// K4b: scan + emit.  Stream compaction of res[] with an exclusive scan of (bytes, count):
+// the survivor at merged position i becomes output entry `count before i`, at .data offset
+// `bytes before i` (entry_writer.rs:81-86: offset = running sum of full_size).
+// Single pass, decoupled look-back over 2048-record tiles.  Each tile publishes two
+// self-validating 64-bit descriptors (2 status bits + 62 value bits), so one look-back step
+// is a single round trip to L2, and the tiles are big because the look-back frontier moves
+// at most 32 tiles per round trip.
+// Writes out_index (the output .index file itself), src_ptr, and for every 16 KB tile of
+// the output .data stream the entry that holds the tile's first byte (tile_first).
+
+constexpr unsigned long long kDescValueMask = (1ull << 62) - 1;
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_emit(Params p, const uint4 *res) {
+    constexpr int NT = kScanThreads;
+    constexpr int IPT = kScanItemsPerThread;
+    constexpr int NW = NT / 32;
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_wb[NW];
+    __shared__ uint32_t s_wc[NW];
+    __shared__ unsigned long long s_excl_b;
+    __shared__ uint32_t s_excl_c;
+    Ctl *c = p.ctl;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(&c->ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t total = c->total;
+    constexpr uint32_t TILE = NT * IPT;
+    if ((uint64_t)tile * TILE >= total) return;
+    const uint32_t n_tiles = (total + TILE - 1) / TILE;
+    const uint32_t base = tile * TILE + tid * IPT; // blocked: thread owns IPT consecutive records
+
+    uint4 it[IPT];
+    unsigned long long tb = 0;
+    uint32_t tc = 0;
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+        it[k] = make_uint4(0, 0, 0, 0);
+        if (base + k < total) it[k] = __ldg(&res[base + k]);
+        tb += it[k].w;
+        tc += it[k].w ? 1u : 0u;
+    }
+    unsigned long long ib = tb;
+    uint32_t ic = tc;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        unsigned long long tb = __shfl_up_sync(0xFFFFFFFFu, ib, o);
-        uint32_t tc = __shfl_up_sync(0xFFFFFFFFu, ic, o);
-        if (lane >= (uint32_t)o) { ib += tb; ic += tc; }
+        unsigned long long xb = __shfl_up_sync(0xFFFFFFFFu, ib, o);
+        uint32_t xc = __shfl_up_sync(0xFFFFFFFFu, ic, o);
+        if (lane >= (uint32_t)o) { ib += xb; ic += xc; }
     }
     if (lane == 31) { s_wb[warp] = ib; s_wc[warp] = ic; }
     __syncthreads();
@@ -667,43 +699,35 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec
         uint32_t wc = lane < NW ? s_wc[lane] : 0u;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            unsigned long long tb = __shfl_up_sync(0xFFFFFFFFu, wb, o);
-            uint32_t tc = __shfl_up_sync(0xFFFFFFFFu, wc, o);
-            if (lane >= (uint32_t)o) { wb += tb; wc += tc; }
+            unsigned long long xb = __shfl_up_sync(0xFFFFFFFFu, wb, o);
+            uint32_t xc = __shfl_up_sync(0xFFFFFFFFu, wc, o);
+            if (lane >= (uint32_t)o) { wb += xb; wc += xc; }
         }
-        unsigned long long agg_b = __shfl_sync(0xFFFFFFFFu, wb, NW - 1);
-        uint32_t agg_c = __shfl_sync(0xFFFFFFFFu, wc, NW - 1);
+        const unsigned long long agg_b = __shfl_sync(0xFFFFFFFFu, wb, NW - 1);
+        const uint32_t agg_c = __shfl_sync(0xFFFFFFFFu, wc, NW - 1);
         if (lane < NW) { s_wb[lane] = wb; s_wc[lane] = wc; }
 
-        // decoupled look-back
-        volatile uint32_t *status = p.scan_status;
-        volatile unsigned long long *aggb = p.scan_agg_bytes, *incb = p.scan_inc_bytes;
-        volatile uint32_t *aggc = p.scan_agg_cnt, *incc = p.scan_inc_cnt;
-        unsigned long long excl_b = 0;
-        uint32_t excl_c = 0;
+        volatile unsigned long long *db = p.scan_desc_bytes, *dc = p.scan_desc_cnt;
+        unsigned long long excl_b = 0, excl_c = 0;
         if (tile > 0) {
             if (lane == 0) {
-                aggb[tile] = agg_b;
-                aggc[tile] = agg_c;
-                __threadfence();
-                status[tile] = 1;
+                db[tile] = (1ull << 62) | agg_b;
+                dc[tile] = (1ull << 62) | agg_c;
             }
             int look = (int)tile - 1;
             while (true) {
-                int idx = look - (int)lane;
-                uint32_t st = 2;
+                const int idx = look - (int)lane;
+                unsigned long long vb = 2ull << 62, vc = 2ull << 62; // before tile 0: inclusive prefix 0
                 if (idx >= 0) {
-                    do { st = status[idx]; } while (st == 0);
+                    do { // both words present and of the same kind (aggregate / inclusive)
+                        vb = db[idx];
+                        vc = dc[idx];
+                    } while ((vb >> 62) == 0 || (vb >> 62) != (vc >> 62));
                 }
-                __threadfence();
-                uint32_t mask2 = __ballot_sync(0xFFFFFFFFu, st == 2);
-                uint32_t first = mask2 ? (uint32_t)__ffs(mask2) - 1 : 32u;
-                unsigned long long cb = 0;
-                uint32_t cc = 0;
-                if (idx >= 0) {
-                    if (lane < first) { cb = aggb[idx]; cc = aggc[idx]; }
-                    else if (lane == first) { cb = incb[idx]; cc = incc[idx]; }
-                }
+                const uint32_t mask2 = __ballot_sync(0xFFFFFFFFu, (vb >> 62) == 2);
+                const uint32_t first = mask2 ? (uint32_t)__ffs(mask2) - 1 : 32u;
+                unsigned long long cb = lane <= first ? (vb & kDescValueMask) : 0ull;
+                unsigned long long cc = lane <= first ? (vc & kDescValueMask) : 0ull;
 #pragma unroll
                 for (int o = 16; o; o >>= 1) {
                     cb += __shfl_xor_sync(0xFFFFFFFFu, cb, o);
@@ -716,27 +740,30 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec
             }
         }
         if (lane == 0) {
-            incb[tile] = excl_b + agg_b;
-            incc[tile] = excl_c + agg_c;
-            __threadfence();
-            status[tile] = 2;
+            db[tile] = (2ull << 62) | (excl_b + agg_b);
+            dc[tile] = (2ull << 62) | (excl_c + agg_c);
             s_excl_b = excl_b;
-            s_excl_c = excl_c;
+            s_excl_c = (uint32_t)excl_c;
             if (tile == n_tiles - 1) {
                 c->out_data_len = excl_b + agg_b;
-                c->out_items = excl_c + agg_c;
+                c->out_items = (uint32_t)(excl_c + agg_c);
             }
         }
     }
     __syncthreads();
-    if (keep) {
-        unsigned long long off = s_excl_b + (warp ? s_wb[warp - 1] : 0ull) + (ib - vb);
-        uint32_t pos = s_excl_c + (warp ? s_wc[warp - 1] : 0u) + (ic - vc);
-        p.out_index[pos] = make_uint4((uint32_t)off, (uint32_t)(off >> 32), ks, fs);
-        p.src_ptr[pos] = src;
+    unsigned long long off = s_excl_b + (warp ? s_wb[warp - 1] : 0ull) + (ib - tb);
+    uint32_t pos = s_excl_c + (warp ? s_wc[warp - 1] : 0u) + (ic - tc);
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+        const uint32_t fs = it[k].w;
+        if (!fs) continue;
+        p.out_index[pos] = make_uint4((uint32_t)off, (uint32_t)(off >> 32), it[k].z, fs);
+        p.src_ptr[pos] = (unsigned long long)it[k].x | ((unsigned long long)it[k].y << 32);
         // every gather tile whose first byte lies in [off, off + fs) starts inside this entry
         unsigned long long b = (off + kGatherTileBytes - 1) / kGatherTileBytes;
         for (; b * kGatherTileBytes < off + fs; b++) p.tile_first[b] = pos;
+        off += fs;
+        pos++;
     }
 }
 
@@ -750,8 +777,10 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec
 // each thread produces 4 vectors, a warp writing 512 contiguous bytes per store:
 //   * a vector that lies inside one entry = two aligned 16-byte source loads + a byte funnel
 //     shift (source and destination are misaligned by an arbitrary byte count);
-//   * a vector that straddles an entry boundary is assembled bytewise.
-// No byte stores, no inter-CTA overlap: every output vector has exactly one writer.
+//   * a vector that straddles an entry boundary (one per entry) is built by a second, dense
+//     pass: tail of entry j blended with the shifted head of entry j+1.
+// No byte stores (bar the last <16 bytes of the stream), no overlap between CTAs: every output
+// vector has exactly one writer.
 // Bloom (fused epilogue): after its stores are issued the CTA hashes the key of every entry
 // whose first byte lies in its tile (2 x SipHash-1-3 in one walk, one thread per entry) and
 // sets k bits with atomicOr -- the filter (<= ~10 MB at the benchmark shapes) stays
@@ -861,32 +890,45 @@ __global__ void __launch_bounds__(kGatherThreads) k_gather(Params p) {
         const uint32_t v = tid + k * NT;
         if (pure[k]) reinterpret_cast<uint4 *>(dst_tile)[v] = realign16_sel(A[k], B[k], sh[k]);
     }
-    // ---- vectors that straddle an entry boundary (or the end of the stream): bytewise
-#pragma unroll
-    for (int k = 0; k < VPT; k++) {
-        const uint32_t v = tid + k * NT;
+    // ---- vectors that straddle an entry boundary: one per entry, handled densely -- thread j
+    // builds the vector that holds the last byte of entry j: the tail of j blended with the
+    // head of entry j+1 (entries are >= 32 bytes, so never more than two entries per vector)
+    for (uint32_t j = tid; j < ne; j += NT) {
+        const long long r0 = s_r0[j];
+        const long long r1 = r0 + (long long)s_fs[j];
+        if (r1 <= 0 || (r1 & 15) == 0 || r1 > (long long)tile_len) continue; // ends outside, or on a vector edge
+        const uint32_t v = (uint32_t)(r1 >> 4);
         const uint32_t b0 = v * 16;
-        if (pure[k] || b0 >= tile_len) continue;
-        uint32_t j = s_vec[v];
-        long long r0 = s_r0[j];
-        long long r1 = r0 + (long long)s_fs[j];
-        const uint8_t *src = reinterpret_cast<const uint8_t *>((uintptr_t)s_src[j]);
-        uint32_t w[4] = {0, 0, 0, 0};
-        const uint32_t nb = tile_len - b0 < 16 ? tile_len - b0 : 16;
-        for (uint32_t b = 0; b < nb; b++) {
-            const long long pos = (long long)b0 + b;
-            if (pos >= r1) { // next entry (entries are >= 32 bytes: at most one switch per vector)
-                j++;
-                r0 = s_r0[j];
-                r1 = r0 + (long long)s_fs[j];
-                src = reinterpret_cast<const uint8_t *>((uintptr_t)s_src[j]);
+        const uint32_t t = (uint32_t)(r1 - b0); // tail bytes of entry j in this vector: 1..15
+        // tail: 16 bytes of j's stream from byte b0 (only the first t are meaningful)
+        const uintptr_t sa = (uintptr_t)s_src[j] + (uintptr_t)((long long)b0 - r0);
+        const uint32_t sh = (uint32_t)(sa & 15);
+        const uint4 *sv = reinterpret_cast<const uint4 *>(sa - sh);
+        const uint4 TA = __ldg(sv);
+        const uint4 TB = __ldg(sh + t > 16 ? sv + 1 : sv); // second vector only if the tail reaches into it
+        uint4 o = realign16_sel(TA, TB, sh);
+        if (b0 + 16 <= tile_len) {
+            // head: the first 16 - t bytes of entry j+1, moved up by t bytes
+            const uintptr_t ha = (uintptr_t)s_src[j + 1];
+            const uint32_t hs = (uint32_t)(ha & 15);
+            const uint4 *hv = reinterpret_cast<const uint4 *>(ha - hs);
+            const uint4 HA = __ldg(hv);
+            const uint4 HB = __ldg(hs ? hv + 1 : hv); // entry j+1 is >= 32 bytes: both vectors hold its bytes
+            const uint4 H = realign16_sel(HA, HB, hs);
+            const uint4 Z = make_uint4(0, 0, 0, 0);
+            const uint4 HU = realign16_sel(Z, H, 16 - t); // bytes [16-t, 32-t) of Z|H: t zero bytes, then H
+            const uint32_t wfull = t >> 2, bits = (t & 3) * 8; // words < wfull: tail; word wfull: mixed
+            const uint32_t mmix = bits ? (0xFFFFFFFFu >> (32 - bits)) : 0u;
+            uint32_t ow[4] = {o.x, o.y, o.z, o.w}, hw[4] = {HU.x, HU.y, HU.z, HU.w};
+#pragma unroll
+            for (uint32_t q = 0; q < 4; q++) {
+                const uint32_t mk = q < wfull ? 0xFFFFFFFFu : (q == wfull ? mmix : 0u);
+                ow[q] = (ow[q] & mk) | (hw[q] & ~mk);
             }
-            w[b >> 2] |= (uint32_t)__ldg(src + (pos - r0)) << ((b & 3) * 8);
-        }
-        if (nb == 16) {
-            reinterpret_cast<uint4 *>(dst_tile)[v] = make_uint4(w[0], w[1], w[2], w[3]);
-        } else { // ragged end of the stream: never write past out_data_len
-            for (uint32_t b = 0; b < nb; b++) dst_tile[b0 + b] = (uint8_t)(w[b >> 2] >> ((b & 3) * 8));
+            reinterpret_cast<uint4 *>(dst_tile)[v] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        } else { // ragged end of the whole stream: never write past out_data_len
+            const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+            for (uint32_t b = 0; b < t; b++) dst_tile[b0 + b] = (uint8_t)(ow[b >> 2] >> ((b & 3) * 8));
         }
     }
 

@@ -1,0 +1,76 @@
+"""CPU-only checks of the drop-in boundary: the built library loads and exports every function
+that include/dbeel_compact.h declares; host-side arithmetic entry points agree with the oracle;
+without a GPU the engine refuses to exist (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import oracle
+from dbeel_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "dbeel_compact.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dbeel_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = declared_functions()
+    assert len(names) >= 16 and "dbeel_compact" in names and "dbeel_flush_device" in names
+    lib = capi.lib()
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"declared in the header but not exported: {missing}"
+    assert sorted(capi.EXPORTS) == [n for n in names if n in capi.EXPORTS]
+    assert lib.dbeel_abi_version() == 1
+
+
+def test_bloom_sizing_matches_oracle():
+    lib = capi.lib()
+    for n in [1, 2, 7, 1000, 65_536, 4_000_000, 8_000_000, 123_456_789]:
+        for fp in [0.01, 0.001, 0.3]:
+            assert lib.dbeel_bloom_bitmap_bytes(n, fp) == oracle.bloom_bitmap_bytes(n, fp)
+            bits = oracle.bloom_bitmap_bytes(n, fp) * 8
+            assert lib.dbeel_bloom_k_num(bits, n) == oracle.bloom_k_num(bits, n)
+            assert lib.dbeel_bloom_file_size(n, fp) == oracle.bloom_file_size(n, fp)
+
+
+def test_compact_bound():
+    opts = capi.make_opts(False)
+    d, i, b = capi.compact_bound([(2_000_000, 160_007), (500_000, 32)], opts)
+    assert d == 2_500_000 and i == 16 * (10_000 + 2) and b == oracle.bloom_file_size(10_002)
+    d, i, b = capi.compact_bound([(1_048_576, 1600)], opts)  # strict '>' (lsm_tree.rs:1027)
+    assert b == 0
+    assert capi.compact_bound([], opts) == (0, 0, 0)
+
+
+def test_strerror_and_null_handling():
+    lib = capi.lib()
+    assert lib.dbeel_strerror(0) == b"ok"
+    assert lib.dbeel_strerror(capi.ERR_NO_DEVICE) != lib.dbeel_strerror(12345)
+    assert lib.dbeel_engine_create(0, None) == capi.ERR_INVALID_ARG
+    lib.dbeel_engine_destroy(None)  # no-op
+    lib.dbeel_host_free(None)
+
+
+def test_no_gpu_means_no_engine():
+    """The product path must fail loudly without its device: there is no CPU fallback."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi.DbeelError) as ei:
+        capi.Engine(0)
+    assert ei.value.code == capi.ERR_NO_DEVICE
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "dbeel_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cc", ".h")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
