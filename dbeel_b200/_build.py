@@ -11,8 +11,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdbeel_compact.so")
-SOURCES = ["dbeel_compact.cu"]
-DEPS = ["dbeel_compact.cu", "kernels.cuh", "device_fns.cuh", os.path.join("..", "..", "include", "dbeel_compact.h")]
+SOURCES = ["dbeel_compact.cu", os.path.join("host", "lsm_tree_host.cc")]
+DEPS = ["dbeel_compact.cu", "kernels.cuh", "device_fns.cuh", os.path.join("host", "lsm_tree_host.cc"),
+        os.path.join("..", "..", "include", "dbeel_compact.h"), os.path.join("..", "..", "include", "dbeel_tree.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -1,0 +1,402 @@
+// lsm_tree_host.cc -- the host side of the drop-in: file protocol around the GPU merge core.
+// See include/dbeel_tree.h for the reference functions each entry point mirrors.
+#include <errno.h>
+#include <fcntl.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <filesystem>
+#include <map>
+#include <string>
+#include <string_view>
+#include <unordered_set>
+#include <vector>
+
+#include "../../../include/dbeel_tree.h"
+
+namespace fs = std::filesystem;
+
+namespace {
+
+constexpr int kIndexPadding = 20; // mod.rs:21
+const char *kData = "data", *kIndex = "index", *kBloom = "bloom";
+const char *kCompactData = "compact_data", *kCompactIndex = "compact_index", *kCompactBloom = "compact_bloom",
+           *kCompactAction = "compact_action";
+
+struct SSTable {
+    uint64_t index;
+    uint64_t size; // entries
+};
+
+std::string file_path(const std::string &dir, uint64_t index, const char *ext) { // lsm_tree.rs:284-288
+    char name[64];
+    snprintf(name, sizeof name, "%0*llu.%s", kIndexPadding, (unsigned long long)index, ext);
+    return (fs::path(dir) / name).string();
+}
+
+// "^(\d+)\.<ext>$" (lsm_tree.rs:306-310)
+bool parse_name(const std::string &name, const char *ext, uint64_t *index) {
+    size_t dot = name.find('.');
+    if (dot == std::string::npos || dot == 0 || name.substr(dot + 1) != ext) return false;
+    uint64_t v = 0;
+    for (size_t i = 0; i < dot; i++) {
+        if (name[i] < '0' || name[i] > '9') return false;
+        v = v * 10 + (uint64_t)(name[i] - '0');
+    }
+    *index = v;
+    return true;
+}
+
+struct PinnedBuf { // dbeel_host_alloc'ed: PCIe transfers at full speed
+    uint8_t *p = nullptr;
+    uint64_t len = 0;
+    PinnedBuf() = default;
+    explicit PinnedBuf(uint64_t n) : p(static_cast<uint8_t *>(dbeel_host_alloc(n ? n : 1))), len(n) {}
+    PinnedBuf(const PinnedBuf &) = delete;
+    PinnedBuf &operator=(const PinnedBuf &) = delete;
+    PinnedBuf(PinnedBuf &&o) noexcept : p(o.p), len(o.len) { o.p = nullptr; }
+    PinnedBuf &operator=(PinnedBuf &&o) noexcept {
+        if (this != &o) { dbeel_host_free(p); p = o.p; len = o.len; o.p = nullptr; }
+        return *this;
+    }
+    ~PinnedBuf() { dbeel_host_free(p); }
+};
+
+// bincode (fixint, little-endian) writers for the CompactionAction journal (lsm_tree.rs:73-77)
+void put_u64(std::string &b, uint64_t v) { b.append(reinterpret_cast<const char *>(&v), 8); }
+void put_path(std::string &b, const std::string &p) { put_u64(b, p.size()); b += p; } // PathBuf serializes as str
+
+bool get_u64(const std::string &b, size_t &pos, uint64_t *v) {
+    if (b.size() - pos < 8) return false;
+    memcpy(v, b.data() + pos, 8);
+    pos += 8;
+    return true;
+}
+bool get_path(const std::string &b, size_t &pos, std::string *p) {
+    uint64_t n;
+    if (!get_u64(b, pos, &n) || b.size() - pos < n) return false;
+    p->assign(b, pos, n);
+    pos += n;
+    return true;
+}
+
+} // namespace
+
+struct dbeel_tree {
+    std::string dir;
+    dbeel_engine *engine = nullptr;
+    uint64_t bloom_min_size = DBEEL_DEFAULT_BLOOM_MIN_SIZE;
+    std::vector<SSTable> sstables; // ascending by index (lsm_tree.rs:1136)
+    uint64_t write_sstable_index = 0;
+    std::string err;
+};
+
+namespace {
+
+int io_fail(dbeel_tree *t, const std::string &what) {
+    t->err = what + ": " + strerror(errno);
+    return DBEEL_ERR_IO;
+}
+
+int read_file(dbeel_tree *t, const std::string &path, PinnedBuf *out) {
+    int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) return io_fail(t, "open " + path);
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); return io_fail(t, "fstat " + path); }
+    PinnedBuf buf((uint64_t)st.st_size);
+    if (!buf.p) { close(fd); t->err = "dbeel_host_alloc failed"; return DBEEL_ERR_NOMEM; }
+    uint64_t got = 0;
+    while (got < buf.len) {
+        ssize_t r = read(fd, buf.p + got, buf.len - got);
+        if (r < 0 && errno == EINTR) continue;
+        if (r <= 0) { close(fd); return io_fail(t, "read " + path); }
+        got += (uint64_t)r;
+    }
+    close(fd);
+    *out = std::move(buf);
+    return DBEEL_OK;
+}
+
+int write_file(dbeel_tree *t, const std::string &path, const void *data, uint64_t len) {
+    int fd = open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return io_fail(t, "create " + path);
+    uint64_t put = 0;
+    while (put < len) {
+        ssize_t w = write(fd, static_cast<const uint8_t *>(data) + put, len - put);
+        if (w < 0 && errno == EINTR) continue;
+        if (w <= 0) { close(fd); return io_fail(t, "write " + path); }
+        put += (uint64_t)w;
+    }
+    if (close(fd) != 0) return io_fail(t, "close " + path);
+    return DBEEL_OK;
+}
+
+bool exists(const std::string &p) { struct stat st; return stat(p.c_str(), &st) == 0; }
+
+struct CompactionAction {
+    std::vector<std::pair<std::string, std::string>> renames;
+    std::vector<std::string> deletes;
+};
+
+std::string encode_action(const CompactionAction &a) {
+    std::string b;
+    put_u64(b, a.renames.size());
+    for (auto &r : a.renames) { put_path(b, r.first); put_path(b, r.second); }
+    put_u64(b, a.deletes.size());
+    for (auto &d : a.deletes) put_path(b, d);
+    return b;
+}
+
+bool decode_action(const std::string &b, CompactionAction *a) {
+    size_t pos = 0;
+    uint64_t n;
+    if (!get_u64(b, pos, &n)) return false;
+    for (uint64_t i = 0; i < n; i++) {
+        std::string s, d;
+        if (!get_path(b, pos, &s) || !get_path(b, pos, &d)) return false;
+        a->renames.emplace_back(std::move(s), std::move(d));
+    }
+    if (!get_u64(b, pos, &n)) return false;
+    for (uint64_t i = 0; i < n; i++) {
+        std::string d;
+        if (!get_path(b, pos, &d)) return false;
+        a->deletes.push_back(std::move(d));
+    }
+    return pos == b.size(); // reject_trailing_bytes
+}
+
+// run_compaction_action (lsm_tree.rs:576-590): deletes first, then the renames whose source exists
+int run_action(dbeel_tree *t, const CompactionAction &a) {
+    for (auto &d : a.deletes)
+        if (exists(d)) unlink(d.c_str()); // remove_file_log_on_err: failure is not fatal
+    for (auto &r : a.renames)
+        if (exists(r.first) && rename(r.first.c_str(), r.second.c_str()) != 0) return io_fail(t, "rename " + r.first);
+    return DBEEL_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int dbeel_tree_open(const char *dir, dbeel_engine *engine, uint64_t bloom_min_size, dbeel_tree **out) {
+    if (!dir || !engine || !out) return DBEEL_ERR_INVALID_ARG;
+    *out = nullptr;
+    auto *t = new (std::nothrow) dbeel_tree();
+    if (!t) return DBEEL_ERR_NOMEM;
+    t->dir = dir;
+    t->engine = engine;
+    t->bloom_min_size = bloom_min_size;
+    std::error_code ec;
+    fs::create_directories(t->dir, ec); // lsm_tree.rs:415-420
+    // replay compaction journals (lsm_tree.rs:424-438).  The reference re-creates its reader on
+    // every loop iteration and would spin on a valid journal; each journal holds one action.
+    std::vector<std::string> journals, names;
+    for (auto &de : fs::directory_iterator(t->dir, ec)) names.push_back(de.path().filename().string());
+    uint64_t idx;
+    for (auto &n : names)
+        if (parse_name(n, kCompactAction, &idx)) journals.push_back((fs::path(t->dir) / n).string());
+    for (auto &j : journals) {
+        std::string buf; // journals are tiny: plain memory, no pinned allocation (works without a GPU)
+        {
+            int fd = open(j.c_str(), O_RDONLY);
+            if (fd < 0) { int rc = io_fail(t, "open " + j); delete t; return rc; }
+            char tmp[4096];
+            ssize_t r;
+            while ((r = read(fd, tmp, sizeof tmp)) > 0) buf.append(tmp, (size_t)r);
+            close(fd);
+        }
+        CompactionAction a;
+        if (decode_action(buf, &a)) {
+            int rc = run_action(t, a);
+            if (rc) { delete t; return rc; }
+        }
+        unlink(j.c_str());
+    }
+    // discover SSTables (lsm_tree.rs:440-459): size = len(.index) / 16
+    names.clear();
+    for (auto &de : fs::directory_iterator(t->dir, ec)) names.push_back(de.path().filename().string());
+    std::vector<uint64_t> indices;
+    for (auto &n : names)
+        if (parse_name(n, kData, &idx)) indices.push_back(idx);
+    std::sort(indices.begin(), indices.end());
+    for (uint64_t i : indices) {
+        struct stat st;
+        std::string ip = file_path(t->dir, i, kIndex);
+        if (stat(ip.c_str(), &st) != 0) { int rc = io_fail(t, "stat " + ip); delete t; return rc; }
+        t->sstables.push_back({i, (uint64_t)st.st_size / DBEEL_INDEX_ENTRY_SIZE});
+    }
+    // lsm_tree.rs:461-465
+    t->write_sstable_index = indices.empty() ? 0 : indices.back() + 2 - (indices.back() & 1);
+    *out = t;
+    return DBEEL_OK;
+}
+
+void dbeel_tree_close(dbeel_tree *t) { delete t; }
+
+uint32_t dbeel_tree_sstables(const dbeel_tree *t, uint64_t *indices, uint64_t *sizes, uint32_t cap) {
+    if (!t) return 0;
+    for (uint32_t i = 0; i < t->sstables.size() && i < cap; i++) {
+        if (indices) indices[i] = t->sstables[i].index;
+        if (sizes) sizes[i] = t->sstables[i].size;
+    }
+    return (uint32_t)t->sstables.size();
+}
+
+uint64_t dbeel_tree_write_sstable_index(const dbeel_tree *t) { return t ? t->write_sstable_index : 0; }
+
+const char *dbeel_tree_last_error(const dbeel_tree *t) { return t ? t->err.c_str() : "null tree"; }
+
+int dbeel_tree_compact(dbeel_tree *t, const uint64_t *indices_to_compact, uint32_t n, uint64_t output_index,
+                       int keep_tombstones, const uint8_t *bloom_seed) {
+    if (!t || (n && !indices_to_compact)) return DBEEL_ERR_INVALID_ARG;
+    t->err.clear();
+    // lsm_tree.rs:956-993: open the inputs (here: read them whole into pinned memory)
+    std::vector<PinnedBuf> data(n), index(n);
+    std::vector<dbeel_run> runs(n);
+    for (uint32_t i = 0; i < n; i++) {
+        std::string dp = file_path(t->dir, indices_to_compact[i], kData), ip = file_path(t->dir, indices_to_compact[i], kIndex);
+        if (!exists(dp) || !exists(ip)) { t->err = "no such sstable: " + dp; return DBEEL_ERR_NO_SSTABLE; }
+        int rc = read_file(t, dp, &data[i]);
+        if (!rc) rc = read_file(t, ip, &index[i]);
+        if (rc) return rc;
+        runs[i] = dbeel_run{data[i].p, data[i].len, index[i].p, index[i].len};
+    }
+    dbeel_compact_opts opts;
+    opts.keep_tombstones = keep_tombstones;
+    opts.flags = 0;
+    opts.bloom_min_size = t->bloom_min_size;
+    opts.bloom_fp = DBEEL_DEFAULT_BLOOM_FP;
+    opts.bloom_seed = bloom_seed;
+    uint64_t dc, ic, bc;
+    int rc = dbeel_compact_bound(runs.data(), n, &opts, &dc, &ic, &bc);
+    if (rc) return rc;
+    PinnedBuf od(dc), oi(ic), ob(bc);
+    if (!od.p || !oi.p || !ob.p) { t->err = "dbeel_host_alloc failed"; return DBEEL_ERR_NOMEM; }
+    dbeel_out out{od.p, dc, 0, oi.p, ic, 0, bc ? ob.p : nullptr, bc, 0, 0};
+    // lsm_tree.rs:1002-1076 -- the merge core, on the GPU
+    rc = dbeel_compact(t->engine, runs.data(), n, &opts, &out);
+    if (rc) { t->err = dbeel_last_error(t->engine); return rc; }
+
+    // lsm_tree.rs:995-1000,1068-1076: the compact_* files
+    const std::string cdata = file_path(t->dir, output_index, kCompactData), cindex = file_path(t->dir, output_index, kCompactIndex),
+                      cbloom = file_path(t->dir, output_index, kCompactBloom);
+    rc = write_file(t, cdata, od.p, out.data_len);
+    if (!rc) rc = write_file(t, cindex, oi.p, out.index_len);
+    if (!rc && out.bloom_len) rc = write_file(t, cbloom, ob.p, out.bloom_len);
+    if (rc) return rc;
+
+    // lsm_tree.rs:1078-1105: journal
+    CompactionAction action;
+    action.renames = {{cdata, file_path(t->dir, output_index, kData)},
+                      {cindex, file_path(t->dir, output_index, kIndex)},
+                      {cbloom, file_path(t->dir, output_index, kBloom)}};
+    for (uint32_t i = 0; i < n; i++)
+        for (const char *ext : {kData, kIndex, kBloom}) action.deletes.push_back(file_path(t->dir, indices_to_compact[i], ext));
+    const std::string journal = file_path(t->dir, output_index, kCompactAction);
+    const std::string enc = encode_action(action);
+    rc = write_file(t, journal, enc.data(), enc.size());
+    if (rc) return rc;
+    // lsm_tree.rs:1107-1111: renames whose source exists (no bloom -> that rename is skipped)
+    for (auto &r : action.renames)
+        if (exists(r.first) && rename(r.first.c_str(), r.second.c_str()) != 0) return io_fail(t, "rename " + r.first);
+    // lsm_tree.rs:1113-1139: swap the sstable list
+    std::vector<SSTable> next;
+    for (auto &s : t->sstables)
+        if (std::find(indices_to_compact, indices_to_compact + n, s.index) == indices_to_compact + n) next.push_back(s);
+    next.push_back({output_index, out.items_written});
+    std::sort(next.begin(), next.end(), [](const SSTable &a, const SSTable &b) { return a.index < b.index; });
+    t->sstables.swap(next);
+    // lsm_tree.rs:1147-1153: delete the inputs, then the journal
+    for (auto &d : action.deletes)
+        if (exists(d)) unlink(d.c_str());
+    unlink(journal.c_str());
+    return DBEEL_OK;
+}
+
+int dbeel_tree_flush(dbeel_tree *t, const dbeel_run *batch, uint64_t *written_index, uint64_t *items_written) {
+    if (!t || !batch) return DBEEL_ERR_INVALID_ARG;
+    t->err.clear();
+    if (batch->index_len < DBEEL_INDEX_ENTRY_SIZE) return DBEEL_OK; // flush of an empty memtable is a no-op (lsm_tree.rs:850-852)
+    PinnedBuf od(batch->data_len), oi(batch->index_len);
+    if (!od.p || !oi.p) { t->err = "dbeel_host_alloc failed"; return DBEEL_ERR_NOMEM; }
+    dbeel_out out{od.p, batch->data_len, 0, oi.p, batch->index_len / 16 * 16, 0, nullptr, 0, 0, 0};
+    int rc = dbeel_flush(t->engine, batch, &out);
+    if (rc) { t->err = dbeel_last_error(t->engine); return rc; }
+    const uint64_t idx = t->write_sstable_index; // lsm_tree.rs:875-880
+    rc = write_file(t, file_path(t->dir, idx, kData), od.p, out.data_len);
+    if (!rc) rc = write_file(t, file_path(t->dir, idx, kIndex), oi.p, out.index_len);
+    if (rc) return rc;
+    t->sstables.push_back({idx, out.items_written}); // lsm_tree.rs:903-915 (bloom: None)
+    t->write_sstable_index = idx + 2;
+    if (written_index) *written_index = idx;
+    if (items_written) *items_written = out.items_written;
+    return DBEEL_OK;
+}
+
+uint64_t dbeel_memtable_cut(const dbeel_run *batch, uint64_t first_record, uint32_t capacity) {
+    if (!batch || !capacity) return 0;
+    const uint8_t *ix = static_cast<const uint8_t *>(batch->index), *d = static_cast<const uint8_t *>(batch->data);
+    const uint64_t n = batch->index_len / DBEEL_INDEX_ENTRY_SIZE;
+    std::unordered_set<std::string_view> keys;
+    keys.reserve(capacity * 2);
+    uint64_t i = first_record;
+    for (; i < n; i++) {
+        uint64_t off;
+        uint32_t ks;
+        memcpy(&off, ix + 16 * i, 8);
+        memcpy(&ks, ix + 16 * i + 8, 4);
+        if (ks < 8 || off > batch->data_len || ks > batch->data_len - off) break; // undecodable: the batch ends here
+        keys.emplace(reinterpret_cast<const char *>(d + off + 8), ks - 8);
+        if (keys.size() == capacity) { i++; break; } // active_memtable_full() right after the insert
+    }
+    return i - first_record;
+}
+
+uint32_t dbeel_plan_compactions(const uint64_t *indices, const uint64_t *sizes, uint32_t n, uint32_t compaction_factor,
+                                uint64_t *members, uint32_t *group_start, uint64_t *output_index, int32_t *keep_tombstones) {
+    if (compaction_factor < 2) return 0; // compaction.rs:105-108
+    auto lz = [](uint64_t v) -> uint32_t { return v ? (uint32_t)__builtin_clzll(v) : 64u; };
+    // compaction.rs:38-43
+    uint64_t next_out = 1;
+    for (uint32_t i = 0; i < n; i++)
+        if (indices[i] & 1) next_out = std::max(next_out, indices[i] + 2);
+    // compaction.rs:45-52: group by leading_zeros(size), smallest tables (most zeros) first
+    std::map<uint32_t, std::vector<uint32_t>, std::greater<uint32_t>> groups;
+    for (uint32_t i = 0; i < n; i++) groups[lz(sizes[i])].push_back(i);
+    // compaction.rs:55-80: promote a tier whose summed size crosses into a larger order
+    std::map<uint32_t, std::vector<uint32_t>> optimized; // ascending order = largest tables first
+    for (auto &g : groups) {
+        std::vector<uint32_t> items = g.second;
+        auto it = optimized.find(g.first);
+        if (it != optimized.end()) {
+            items.insert(items.end(), it->second.begin(), it->second.end());
+            optimized.erase(it);
+        }
+        uint64_t sum = 0;
+        for (uint32_t i : items) sum += sizes[i];
+        uint32_t est = lz(sum);
+        uint32_t order = est < g.first ? est : g.first;
+        auto &dst = optimized[order];
+        dst.insert(dst.end(), items.begin(), items.end());
+    }
+    // compaction.rs:82-101 -- enumerate() counts skipped groups too
+    uint32_t n_groups = 0, pos = 0, i = 0;
+    group_start[0] = 0;
+    for (auto &g : optimized) {
+        const bool run = g.second.size() >= 2 && g.second.size() >= compaction_factor;
+        if (run) {
+            for (uint32_t m : g.second) members[pos++] = indices[m];
+            output_index[n_groups] = next_out;
+            keep_tombstones[n_groups] = i > 0 ? 1 : 0;
+            next_out += 2;
+            n_groups++;
+            group_start[n_groups] = pos;
+        }
+        i++;
+    }
+    return n_groups;
+}
+
+} // extern "C"

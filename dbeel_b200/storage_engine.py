@@ -1,0 +1,142 @@
+"""Python face of the host-side mirror (include/dbeel_tree.h, csrc/host/lsm_tree_host.cc).
+
+Names and argument meaning follow the reference's storage engine so the tests read like its own
+(src/storage_engine/lsm_tree.rs): ``LSMTree.open_or_create``, ``.compact(indices_to_compact,
+output_index, keep_tombstones)``, ``.flush``, ``.sstable_indices_and_sizes``; the size-tiered
+picker of src/tasks/compaction.rs:35-102 is ``plan_compactions`` / ``compact_tree``.
+All the work happens in the C++/CUDA library; this file only marshals arguments.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import capi
+
+ERR_IO = 20
+ERR_NO_SSTABLE = 21
+DEFAULT_TREE_CAPACITY = 8192  # mod.rs:18
+DEFAULT_SSTABLE_BLOOM_MIN_SIZE = 1_048_576  # mod.rs:19
+
+_bound = False
+
+
+def _lib():
+    global _bound
+    L = capi.lib()
+    if not _bound:
+        L.dbeel_tree_open.restype = C.c_int
+        L.dbeel_tree_open.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+        L.dbeel_tree_close.restype = None
+        L.dbeel_tree_close.argtypes = [C.c_void_p]
+        L.dbeel_tree_sstables.restype = C.c_uint32
+        L.dbeel_tree_sstables.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_uint32]
+        L.dbeel_tree_write_sstable_index.restype = C.c_uint64
+        L.dbeel_tree_write_sstable_index.argtypes = [C.c_void_p]
+        L.dbeel_tree_compact.restype = C.c_int
+        L.dbeel_tree_compact.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32, C.c_uint64, C.c_int, C.c_char_p]
+        L.dbeel_tree_flush.restype = C.c_int
+        L.dbeel_tree_flush.argtypes = [C.c_void_p, C.POINTER(capi.Run), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.dbeel_tree_last_error.restype = C.c_char_p
+        L.dbeel_tree_last_error.argtypes = [C.c_void_p]
+        L.dbeel_memtable_cut.restype = C.c_uint64
+        L.dbeel_memtable_cut.argtypes = [C.POINTER(capi.Run), C.c_uint64, C.c_uint32]
+        L.dbeel_plan_compactions.restype = C.c_uint32
+        L.dbeel_plan_compactions.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32,
+                                             C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
+                                             C.POINTER(C.c_int32)]
+        _bound = True
+    return L
+
+
+TREE_EXPORTS = ["dbeel_tree_open", "dbeel_tree_close", "dbeel_tree_sstables", "dbeel_tree_write_sstable_index",
+                "dbeel_tree_compact", "dbeel_tree_flush", "dbeel_tree_last_error", "dbeel_memtable_cut",
+                "dbeel_plan_compactions"]
+
+
+def _run_struct(batch) -> Tuple[capi.Run, tuple]:
+    d, i = capi._u8(batch[0]), capi._u8(batch[1])
+    return capi.Run(d.ctypes.data, d.size, i.ctypes.data, i.size), (d, i)
+
+
+def memtable_cut(batch, first_record: int = 0, capacity: int = DEFAULT_TREE_CAPACITY) -> int:
+    """Arrivals from `first_record` on that one memtable of `capacity` distinct keys absorbs."""
+    run, _keep = _run_struct(batch)
+    return int(_lib().dbeel_memtable_cut(C.byref(run), first_record, capacity))
+
+
+def plan_compactions(indices_and_sizes: Sequence[Tuple[int, int]], compaction_factor: int = 2):
+    """compact_tree's picker, deterministic: [(indices_to_compact, output_index, keep_tombstones)]."""
+    n = len(indices_and_sizes)
+    if n == 0:
+        return []
+    idx = (C.c_uint64 * n)(*[i for i, _ in indices_and_sizes])
+    siz = (C.c_uint64 * n)(*[s for _, s in indices_and_sizes])
+    members = (C.c_uint64 * n)()
+    start = (C.c_uint32 * (n + 1))()
+    outs = (C.c_uint64 * n)()
+    keeps = (C.c_int32 * n)()
+    g = _lib().dbeel_plan_compactions(idx, siz, n, compaction_factor, members, start, outs, keeps)
+    return [([int(members[k]) for k in range(start[j], start[j + 1])], int(outs[j]), bool(keeps[j])) for j in range(g)]
+
+
+class LSMTree:
+    """The compaction-facing part of dbeel's LSMTree over a directory of SSTable files."""
+
+    def __init__(self, directory: str, engine, sstable_bloom_min_size: int = DEFAULT_SSTABLE_BLOOM_MIN_SIZE):
+        self._h = C.c_void_p()
+        self._engine = engine
+        eh = engine._h if hasattr(engine, "_h") else engine
+        rc = _lib().dbeel_tree_open(directory.encode(), eh, sstable_bloom_min_size, C.byref(self._h))
+        if rc:
+            raise capi.DbeelError(rc, f"dbeel_tree_open({directory})")
+        self.dir = directory
+
+    open_or_create = classmethod(lambda cls, *a, **k: cls(*a, **k))
+
+    def close(self):
+        if self._h:
+            _lib().dbeel_tree_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc:
+            raise capi.DbeelError(rc, f"{what}: {_lib().dbeel_tree_last_error(self._h).decode()}")
+
+    def sstable_indices_and_sizes(self) -> List[Tuple[int, int]]:
+        n = _lib().dbeel_tree_sstables(self._h, None, None, 0)
+        idx, siz = (C.c_uint64 * max(1, n))(), (C.c_uint64 * max(1, n))()
+        _lib().dbeel_tree_sstables(self._h, idx, siz, n)
+        return [(int(idx[k]), int(siz[k])) for k in range(n)]
+
+    @property
+    def write_sstable_index(self) -> int:
+        return int(_lib().dbeel_tree_write_sstable_index(self._h))
+
+    def compact(self, indices_to_compact: Sequence[int], output_index: int, keep_tombstones: bool,
+                bloom_seed: Optional[bytes] = None) -> None:
+        arr = (C.c_uint64 * max(1, len(indices_to_compact)))(*indices_to_compact)
+        self._check(_lib().dbeel_tree_compact(self._h, arr, len(indices_to_compact), output_index,
+                                              int(keep_tombstones), bloom_seed), "LSMTree.compact")
+
+    def flush(self, batch) -> Tuple[int, int]:
+        """One memtable's arrivals -> the next even-indexed SSTable.  Returns (index, items)."""
+        run, _keep = _run_struct(batch)
+        wi, n = C.c_uint64(), C.c_uint64()
+        self._check(_lib().dbeel_tree_flush(self._h, C.byref(run), C.byref(wi), C.byref(n)), "LSMTree.flush")
+        return int(wi.value), int(n.value)
+
+    def compact_tree(self, compaction_factor: int = 2, bloom_seed: Optional[bytes] = None):
+        """tasks/compaction.rs compact_tree: plan with the picker, run every group."""
+        plan = plan_compactions(self.sstable_indices_and_sizes(), compaction_factor)
+        for indices, out, keep in plan:
+            self.compact(indices, out, keep, bloom_seed)
+        return plan

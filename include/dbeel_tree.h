@@ -1,0 +1,70 @@
+/*
+ * dbeel_tree.h -- host-side mirror of the file protocol AROUND the GPU path, C ABI.
+ *
+ * The reference is Rust (compiled code) and no Rust toolchain exists here, so the host side
+ * above the engine's C ABI is C++ (dbeel_b200/csrc/host/lsm_tree_host.cc), mirroring the
+ * reference's own interface for this path -- same names, argument meaning, error behaviour:
+ *
+ *   dbeel_tree_open        <- LSMTree::open_or_create_ex: journal replay + SSTable discovery
+ *                             (src/storage_engine/lsm_tree.rs:424-465; WAL recovery is out of scope)
+ *   dbeel_tree_compact     <- LSMTree::compact(indices_to_compact, output_index, keep_tombstones)
+ *                             (lsm_tree.rs:950-1156): same files, same CompactionAction journal
+ *                             (:73-77, :1078-1111), same renames / deletes; the merge core
+ *                             (:1002-1076) is dbeel_compact()
+ *   dbeel_tree_flush       <- LSMTree::flush's SSTable part (lsm_tree.rs:875-915): writes the
+ *                             next even index through dbeel_flush(), no bloom
+ *   dbeel_tree_sstables    <- LSMTree::sstable_indices_and_sizes (lsm_tree.rs:592-598)
+ *   dbeel_memtable_cut     <- RedBlackTree::set + active_memtable_full (rbtree_arena lib.rs:497-534,
+ *                             lsm_tree.rs:600-603,757-765): how many arrivals fill one memtable
+ *   dbeel_plan_compactions <- compact_tree's size-tiered picker (src/tasks/compaction.rs:35-102),
+ *                             made deterministic (the reference enumerates a HashMap)
+ */
+#ifndef DBEEL_TREE_H
+#define DBEEL_TREE_H
+
+#include <stdint.h>
+
+#include "dbeel_compact.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DBEEL_ERR_IO 20        /* a filesystem call failed; dbeel_tree_last_error() has errno text */
+#define DBEEL_ERR_NO_SSTABLE 21 /* an index in indices_to_compact has no .data/.index files */
+
+typedef struct dbeel_tree dbeel_tree;
+
+int dbeel_tree_open(const char *dir, dbeel_engine *engine, uint64_t sstable_bloom_min_size, dbeel_tree **out);
+void dbeel_tree_close(dbeel_tree *t);
+
+/* (index, size = entries) of every SSTable, ascending by index.  Returns the count; fills up to cap. */
+uint32_t dbeel_tree_sstables(const dbeel_tree *t, uint64_t *indices, uint64_t *sizes, uint32_t cap);
+uint64_t dbeel_tree_write_sstable_index(const dbeel_tree *t); /* next even index a flush will use */
+
+int dbeel_tree_compact(dbeel_tree *t, const uint64_t *indices_to_compact, uint32_t n, uint64_t output_index,
+                       int keep_tombstones, const uint8_t *bloom_seed /* 32 bytes or NULL */);
+
+/* Flush one memtable's arrivals (host buffers, arrival order) to the next even index. */
+int dbeel_tree_flush(dbeel_tree *t, const dbeel_run *batch, uint64_t *written_index, uint64_t *items_written);
+
+const char *dbeel_tree_last_error(const dbeel_tree *t);
+
+/* Number of arrivals, starting at `first_record`, that a memtable of `capacity` distinct keys
+ * absorbs before it is full (the insert that fills it included); the rest of the batch if it
+ * never fills. */
+uint64_t dbeel_memtable_cut(const dbeel_run *batch, uint64_t first_record, uint32_t capacity);
+
+/* compact_tree's picker.  In: n SSTables (index, size).  Out: groups to compact, flattened:
+ * group g covers members[group_start[g] .. group_start[g+1]) (SSTable indices, in the order they
+ * must be passed as indices_to_compact), writes output_index[g], with keep_tombstones[g].
+ * Groups are ordered largest tables first, so only the final level drops tombstones
+ * (compaction.rs:91-92).  Returns the number of groups (<= n / 2). */
+uint32_t dbeel_plan_compactions(const uint64_t *indices, const uint64_t *sizes, uint32_t n,
+                                uint32_t compaction_factor, uint64_t *members, uint32_t *group_start,
+                                uint64_t *output_index, int32_t *keep_tombstones);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DBEEL_TREE_H */

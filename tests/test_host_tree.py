@@ -1,0 +1,171 @@
+"""Host-side mirror of the file protocol around the GPU path (include/dbeel_tree.h).
+
+CPU tests: the picker (tasks/compaction.rs:35-102), the memtable cut (rbtree_arena set semantics),
+journal replay on open (lsm_tree.rs:424-438,576-590).  GPU tests: LSMTree.compact / flush on real
+files, restating lsm_tree.rs:1328-1451 (get_after_compaction) at the file level."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from dbeel_b200 import capi, sstable, storage_engine as se
+
+from helpers import BASE_TS, assert_run_equal, model_flush, nasty_keys
+
+SEED = bytes(range(32))
+
+
+def u16key(n):
+    return int(n).to_bytes(2, "little")
+
+
+def test_tree_symbols_exported():
+    lib = capi.lib()
+    assert all(hasattr(lib, n) for n in se.TREE_EXPORTS)
+
+
+def test_memtable_cut_counts_distinct_keys():
+    rng = np.random.default_rng(2)
+    pool = nasty_keys(rng, 200)
+    writes = [(pool[int(rng.integers(len(pool)))], b"v", BASE_TS + s) for s in range(3000)]
+    batch = sstable.build_run(writes)
+    pos, cuts = 0, []
+    while pos < len(writes):
+        n = se.memtable_cut(batch, pos, 64)
+        assert n > 0
+        cuts.append(n)
+        pos += n
+    # same boundaries as the red-black-tree replay
+    exp, pos, seen = [], 0, set()
+    for s, (k, _, _) in enumerate(writes):
+        seen.add(k)
+        if len(seen) == 64:
+            exp.append(s + 1 - pos)
+            pos, seen = s + 1, set()
+    if pos < len(writes):
+        exp.append(len(writes) - pos)
+    assert cuts == exp
+    flushed = oracle.memtable_flushes(batch, capacity=64)
+    assert len(flushed) == len(cuts) and all(n <= 64 for _, _, n in flushed)
+
+
+def test_picker_matches_compaction_rs():
+    # three flushed memtables of 32 entries, factor 2: one group [0,2,4] -> output 1, final level drops tombstones
+    assert se.plan_compactions([(0, 32), (2, 32), (4, 32)], 2) == [([0, 2, 4], 1, False)]
+    # factor above the group size: nothing to do (compaction.rs:83-87); factor < 2 disables (:105-108)
+    assert se.plan_compactions([(0, 32), (2, 32), (4, 32)], 4) == []
+    assert se.plan_compactions([(0, 32), (2, 32)], 1) == []
+    # output index = max odd + 2 (compaction.rs:38-43)
+    assert se.plan_compactions([(5, 92), (6, 32), (8, 32)], 2)[0][1] == 7
+    # two tiers: 8 tables of 8192 (order lz=50) and 2 of 65536 (lz=47); the small tier sums to 65536 -> promoted
+    tables = [(2 * i, 8192) for i in range(8)] + [(101, 65536), (103, 65536)]
+    plan = se.plan_compactions(tables, 2)
+    assert len(plan) == 1 and sorted(plan[0][0]) == sorted(i for i, _ in tables) and plan[0][2] is False
+    # no promotion: 3 tables of 8192 (sum 24576, lz 49 < 50 -> promoted to order 49 alone) + 2 big ones
+    plan = se.plan_compactions([(0, 8192), (2, 8192), (4, 8192), (101, 1 << 20), (103, 1 << 20)], 2)
+    assert [sorted(g[0]) for g in plan] == [[101, 103], [0, 2, 4]]
+    assert [g[2] for g in plan] == [False, True]  # only the largest tier drops tombstones
+
+
+def _fake_engine():
+    return C.c_void_p(1)  # dbeel_tree_open never dereferences the engine
+
+
+def test_open_discovers_sstables_and_replays_journal(tmp_path):
+    d = str(tmp_path)
+    run = sstable.build_run([(u16key(n), b"v", 1) for n in range(10)])
+    sstable.write_run_files(d, 0, run)
+    sstable.write_run_files(d, 2, run)
+    # a crash after the journal was written but before the renames: compact_* files + journal on disk
+    out = sstable.build_run([(u16key(n), b"w", 2) for n in range(10)])
+    out[0].tofile(os.path.join(d, sstable.file_name(1, sstable.COMPACT_DATA_FILE_EXT)))
+    out[1].tofile(os.path.join(d, sstable.file_name(1, sstable.COMPACT_INDEX_FILE_EXT)))
+
+    def path(i, ext):
+        return os.path.join(d, sstable.file_name(i, ext)).encode()
+
+    def s(b):
+        return len(b).to_bytes(8, "little") + b
+
+    renames = [(path(1, "compact_data"), path(1, "data")), (path(1, "compact_index"), path(1, "index")),
+               (path(1, "compact_bloom"), path(1, "bloom"))]
+    deletes = [path(i, e) for i in (0, 2) for e in ("data", "index", "bloom")]
+    journal = (len(renames).to_bytes(8, "little") + b"".join(s(a) + s(b) for a, b in renames)
+               + len(deletes).to_bytes(8, "little") + b"".join(s(x) for x in deletes))
+    open(os.path.join(d, sstable.file_name(1, sstable.COMPACT_ACTION_FILE_EXT)), "wb").write(journal)
+
+    t = se.LSMTree(d, _fake_engine())
+    assert t.sstable_indices_and_sizes() == [(1, 10)]  # inputs deleted, output renamed into place
+    assert t.write_sstable_index == 2  # lsm_tree.rs:461-465: odd max index i -> i + 1
+    assert sorted(os.listdir(d)) == [sstable.file_name(1, "data"), sstable.file_name(1, "index")]
+    assert_run_equal(sstable.read_run_files(d, 1), out)
+    t.close()
+    t = se.LSMTree(d, _fake_engine())  # idempotent
+    assert t.sstable_indices_and_sizes() == [(1, 10)]
+
+
+def test_missing_sstable_is_an_error(tmp_path):
+    t = se.LSMTree(str(tmp_path), _fake_engine())
+    assert t.sstable_indices_and_sizes() == [] and t.write_sstable_index == 0
+    with pytest.raises(capi.DbeelError) as ei:
+        t.compact([0, 2], 1, False)
+    assert ei.value.code == se.ERR_NO_SSTABLE
+
+
+@pytest.mark.gpu
+def test_get_after_compaction_on_files(engine, tmp_path):
+    """lsm_tree.rs:1400-1446 with real files: three flushes (0,32),(2,32),(4,32) -> compact(&[0,2,4], 5, false)."""
+    d = str(tmp_path)
+    tree = se.LSMTree.open_or_create(d, engine)
+    assert tree.write_sstable_index == 0 and tree.sstable_indices_and_sizes() == []
+    writes = [(u16key(n), u16key(n), BASE_TS + n) for n in range(94)]
+    writes += [(u16key(1), b"", BASE_TS + 1000), (u16key(4), b"", BASE_TS + 1001)]
+    batch = sstable.build_run(writes)
+    pos = 0
+    while pos < len(writes):
+        n = se.memtable_cut(batch, pos, 32)
+        lo = int.from_bytes(bytes(batch[1][16 * pos:16 * pos + 8]), "little")
+        hi = batch[0].size if pos + n == len(writes) else int.from_bytes(bytes(batch[1][16 * (pos + n):16 * (pos + n) + 8]), "little")
+        sub = sstable.build_run(sstable.parse_run(batch[0], batch[1])[pos:pos + n])
+        assert sub[0].size == hi - lo
+        tree.flush(sub)
+        pos += n
+    assert tree.sstable_indices_and_sizes() == [(0, 32), (2, 32), (4, 32)]
+    for (gd, gi), (od, oi, _) in zip([sstable.read_run_files(d, i) for i in (0, 2, 4)],
+                                     oracle.memtable_flushes(batch, capacity=32)):
+        assert_run_equal((gd, gi), (od, oi), "flushed sstable")
+    inputs = [sstable.read_run_files(d, i) for i in (0, 2, 4)]
+    tree.compact([0, 2, 4], 5, False)
+    assert tree.sstable_indices_and_sizes() == [(5, 32 * 3 - 4)] and tree.write_sstable_index == 6
+    assert sorted(os.listdir(d)) == [sstable.file_name(5, "data"), sstable.file_name(5, "index")]  # no bloom: <= 1 MiB
+    od, oi, _, on = oracle.compact(inputs, False)
+    assert_run_equal(sstable.read_run_files(d, 5), (od, oi), "compacted files")
+    tree.close()
+    tree = se.LSMTree.open_or_create(d, engine)  # reopening the tree (:1439-1443)
+    assert tree.sstable_indices_and_sizes() == [(5, 92)] and tree.write_sstable_index == 6
+
+
+@pytest.mark.gpu
+def test_compact_tree_writes_bloom_file(engine, tmp_path):
+    d = str(tmp_path)
+    rng = np.random.default_rng(8)
+    tree = se.LSMTree(d, engine, sstable_bloom_min_size=50_000)
+    runs = []
+    for r in range(4):
+        ents = [(b"\xb0k%015d" % n, bytes(rng.integers(0, 256, 120, dtype=np.uint8)), BASE_TS + r)
+                for n in sorted(rng.choice(5000, 800, replace=False).tolist())]
+        run = sstable.build_run(ents)
+        runs.append(run)
+        sstable.write_run_files(d, 2 * r, run)
+    tree.close()
+    tree = se.LSMTree(d, engine, sstable_bloom_min_size=50_000)
+    plan = tree.compact_tree(compaction_factor=2, bloom_seed=SEED)
+    assert plan == [([0, 2, 4, 6], 1, False)]
+    od, oi, ob, on = oracle.compact(runs, False, bloom_min_size=50_000, seed=SEED)
+    assert tree.sstable_indices_and_sizes() == [(1, on)]
+    assert_run_equal(sstable.read_run_files(d, 1), (od, oi), "compact_tree output")
+    bloom = np.fromfile(os.path.join(d, sstable.file_name(1, "bloom")), dtype=np.uint8)
+    assert np.array_equal(bloom, ob)
+    assert sorted(os.listdir(d)) == [sstable.file_name(1, e) for e in ("bloom", "data", "index")]
