@@ -44,6 +44,9 @@ struct dbeel_engine {
     dbeel_stats stats = {};
     std::string err;
     bool busy = false;
+    int sm_count = 148;
+    int gather_variant = 1;     // DBEEL_GATHER: 0 = one CTA per tile, 1 = persistent warp-specialized
+    int gather_ctas_per_sm = 4; // DBEEL_GATHER_CTAS
 };
 
 namespace {
@@ -186,9 +189,8 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     const uint64_t tiles_ub = (uint64_t)(N + kMergeTile - 1) / kMergeTile + (p.nseg[0] + 1) / 2;
     const uint64_t bounds_ub = tiles_ub + (p.nseg[0] + 1) / 2 + 1;
     const uint64_t o_part = carve(4 * bounds_ub);
-    const uint64_t scan_tile = (uint64_t)kScanThreads * kScanItemsPerThread;
-    const uint64_t scan_tiles = (N + scan_tile - 1) / scan_tile;
-    const uint64_t o_scan = carve(scan_tiles * 16); // two 64-bit descriptors per tile (zeroed per job)
+    const uint64_t res_tiles = (uint64_t)(N + kResolveThreads - 1) / kResolveThreads;
+    const uint64_t o_tbytes = carve(res_tiles * 8), o_tcount = carve(res_tiles * 4);
     const uint64_t o_reca = carve(16ull * N), o_recb = carve(16ull * N);
     const uint64_t o_src = carve(8ull * N);
     const uint64_t gather_tiles = (sh.data_total + kGatherTileBytes - 1) / kGatherTileBytes;
@@ -206,8 +208,8 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     for (uint32_t l = 0; l <= levels; l++) p.seg[l] = reinterpret_cast<Seg *>(ws + o_seg[l]);
     for (uint32_t l = 0; l < levels; l++) p.tile_base[l] = reinterpret_cast<uint32_t *>(ws + o_tb[l]);
     p.part = reinterpret_cast<uint32_t *>(ws + o_part);
-    p.scan_desc_bytes = reinterpret_cast<unsigned long long *>(ws + o_scan);
-    p.scan_desc_cnt = p.scan_desc_bytes + scan_tiles;
+    p.tile_bytes = reinterpret_cast<unsigned long long *>(ws + o_tbytes);
+    p.tile_count = reinterpret_cast<uint32_t *>(ws + o_tcount);
     p.rec_a = reinterpret_cast<Rec *>(ws + o_reca);
     p.rec_b = reinterpret_cast<Rec *>(ws + o_recb);
     p.src_ptr = reinterpret_cast<unsigned long long *>(ws + o_src);
@@ -255,23 +257,23 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     cudaStream_t s = e->stream;
     uint32_t launches = 0;
     CU(cudaMemcpyAsync(ws, h, header_bytes, cudaMemcpyHostToDevice, s));
-    CU(cudaMemsetAsync(ws + o_scan, 0, scan_tiles * 16, s));
     if (sh.bloom_file) CU(cudaMemsetAsync(out->bloom, 0, sh.bloom_file, s));
     if (record_start) CU(cudaEventRecord(e->ev[EV_START], s));
 
     // ---- K0/K1: prefix, validate, extract (+ conditional redo when a run was truncated)
     const uint32_t g256 = (N + 255) / 256;
+    const uint32_t gext = (N + 256 * kExtractEPT - 1) / (256 * kExtractEPT);
     if (flush) {
         k_flush_prefix_init<<<1, 1, 0, s>>>(p);
         k_flush_prefix<<<g256, 256, 0, s>>>(p);
-        k_extract<<<g256, 256, 0, s>>>(p, 0);
+        k_extract<<<gext, 256, 0, s>>>(p, 0);
         k_plan<<<1, 1, 0, s>>>(p);
         k_block_sort<<<p.nseg[0], kMergeThreads, 0, s>>>(p);
     } else {
         k_common_prefix<<<1, 32, 0, s>>>(p, 0);
-        k_extract<<<g256, 256, 0, s>>>(p, 0);
+        k_extract<<<gext, 256, 0, s>>>(p, 0);
         k_common_prefix<<<1, 32, 0, s>>>(p, 1); // both no-ops unless a run was truncated
-        k_extract<<<g256 < 592 ? g256 : 592, 256, 0, s>>>(p, 1);
+        k_extract<<<gext < 592 ? gext : 592, 256, 0, s>>>(p, 1);
         k_plan<<<1, 1, 0, s>>>(p);
     }
     launches += 5;
@@ -299,9 +301,10 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
 
     // ---- K4: resolve + scan + .index
     uint4 *res = reinterpret_cast<uint4 *>(dst); // the ping-pong buffer that does not hold the merged order
-    k_resolve<<<(N + kResolveThreads - 1) / kResolveThreads, kResolveThreads, 0, s>>>(p, src, res);
-    k_scan_emit<<<(uint32_t)scan_tiles, kScanThreads, 0, s>>>(p, res);
-    launches += 2;
+    k_resolve<<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, src, res);
+    k_scan_tiles<<<1, 1024, 0, s>>>(p);
+    k_emit<<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, res);
+    launches += 3;
     CU(cudaEventRecord(e->ev[EV_RESOLVE], s));
 
     // ---- K5: gather + bloom
@@ -309,7 +312,15 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
         k_bloom_frame<<<1, 1, 0, s>>>(static_cast<uint8_t *>(out->bloom), sh.bloom_words, p.bloom);
         launches++;
     }
-    if (gather_tiles) k_gather<<<(uint32_t)gather_tiles, kGatherThreads, 0, s>>>(p);
+    if (gather_tiles) {
+        if (e->gather_variant == 0) {
+            k_gather<<<(uint32_t)gather_tiles, kGatherThreads, 0, s>>>(p);
+        } else { // persistent, warp-specialized
+            uint64_t grid = (uint64_t)e->sm_count * e->gather_ctas_per_sm;
+            if (grid > gather_tiles) grid = gather_tiles;
+            k_gather_ws<<<(uint32_t)grid, kGatherWsThreads, 0, s>>>(p);
+        }
+    }
     launches++;
     CU(cudaEventRecord(e->ev[EV_GATHER], s));
     CU(cudaGetLastError());
@@ -461,6 +472,9 @@ int dbeel_engine_create(int device, dbeel_engine **out) {
     dbeel_engine *e = new (std::nothrow) dbeel_engine();
     if (!e) return DBEEL_ERR_NOMEM;
     e->device = device;
+    e->sm_count = prop.multiProcessorCount;
+    if (const char *v = getenv("DBEEL_GATHER")) e->gather_variant = atoi(v);
+    if (const char *v = getenv("DBEEL_GATHER_CTAS")) e->gather_ctas_per_sm = atoi(v) > 0 ? atoi(v) : 4;
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return DBEEL_ERR_CUDA; }
     for (int i = 0; i < EV_COUNT; i++)
         if (cudaEventCreate(&e->ev[i]) != cudaSuccess) { dbeel_engine_destroy(e); return DBEEL_ERR_CUDA; }

@@ -48,8 +48,6 @@ constexpr int kMergeThreads = 256;
 constexpr int kMergeVT = 7; // odd: threads walk smem at a 112-byte stride -> no bank conflicts
 constexpr int kMergeTile = kMergeThreads * kMergeVT; // 1792 records = 28 KB of smem
 constexpr int kResolveThreads = 256;
-constexpr int kScanThreads = 256;
-constexpr int kScanItemsPerThread = 8; // 2048 records per scan tile
 constexpr int kGatherThreads = 256;
 constexpr int kGatherVecsPerThread = 4;
 constexpr unsigned long long kGatherTileBytes = 16ull * kGatherThreads * kGatherVecsPerThread; // 16 KB of output per CTA
@@ -78,7 +76,8 @@ struct Params {
     uint32_t *part; // merge-path split points of the current level
     Rec *rec_a, *rec_b;
     // resolve / scan
-    unsigned long long *scan_desc_bytes, *scan_desc_cnt; // [scan tiles] status(2) | value(62), zeroed per job
+    unsigned long long *tile_bytes; // [resolve tiles] bytes emitted by the tile, then (k_scan_tiles) bytes before it
+    uint32_t *tile_count;           // [resolve tiles] same for entries
     int keep_tombstones;
     int mode_flush; // 1: arrival batch -- winner = last arrival, tombstones kept
     // outputs
@@ -239,55 +238,96 @@ __global__ void k_common_prefix(Params p, int validated) {
 // bincode-decodes with no trailing bytes (klen/dlen prefixes agree with key_size/full_size).
 // The first invalid entry ends its run (lsm_tree.rs:1014,1063): first_bad[r] = min index.
 
-__global__ void __launch_bounds__(256) k_extract(Params p, int redo) {
+constexpr int kExtractEPT = 2; // entries per thread: two independent load chains in flight
+
+__global__ void __launch_bounds__(256, 4) k_extract(Params p, int redo) {
     Ctl *c = p.ctl;
     if (redo && !(c->flags & kFlagTruncated)) return;
-    for (uint32_t g = blockIdx.x * 256u + threadIdx.x; g < p.n_total; g += gridDim.x * 256u) {
-    uint32_t r = find_run(p, g);
-    const RunDesc rd = p.runs[r];
-    uint32_t i = g - rd.base;
-    uint4 rec = __ldg(&rd.index[i]);
-    uint64_t off = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
-    uint32_t ks = rec.z, fs = rec.w;
-    bool ok;
-    if (redo) {
-        ok = i < p.first_bad[r];
-    } else {
-        ok = ks >= 8 && (uint64_t)fs >= (uint64_t)ks + 24 && off <= rd.data_len && (uint64_t)fs <= rd.data_len - off;
-        if (ok) {
-            uint64_t expect = 0;
-            if (i) {
-                uint4 pr = __ldg(&rd.index[i - 1]);
-                expect = ((uint64_t)pr.x | ((uint64_t)pr.y << 32)) + pr.w;
+    const uint32_t L = c->prefix_len;
+    const uint64_t *pfx = reinterpret_cast<const uint64_t *>(c->prefix); // 8-byte aligned inside Ctl
+    const uint32_t npw = (L + 7) >> 3;
+    constexpr uint32_t STEP = 256u * kExtractEPT;
+    for (uint32_t g0 = blockIdx.x * STEP + threadIdx.x; g0 < p.n_total; g0 += gridDim.x * STEP) {
+        uint32_t g[kExtractEPT], r[kExtractEPT], i[kExtractEPT], ks[kExtractEPT], fs[kExtractEPT];
+        uint64_t off[kExtractEPT], expect[kExtractEPT], dlen_total[kExtractEPT];
+        const uint8_t *data[kExtractEPT];
+        bool act[kExtractEPT], ok[kExtractEPT];
+        // ---- phase 1: index records (and the predecessor's, for the running-offset check)
+#pragma unroll
+        for (int u = 0; u < kExtractEPT; u++) {
+            g[u] = g0 + u * 256u;
+            act[u] = g[u] < p.n_total;
+            ok[u] = false;
+            if (!act[u]) continue;
+            r[u] = find_run(p, g[u]);
+            const RunDesc &rd = p.runs[r[u]];
+            i[u] = g[u] - rd.base;
+            data[u] = rd.data;
+            dlen_total[u] = rd.data_len;
+            const uint4 rec = __ldg(&rd.index[i[u]]);
+            off[u] = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
+            ks[u] = rec.z;
+            fs[u] = rec.w;
+            expect[u] = 0;
+            if (i[u] && !redo) {
+                const uint4 pr = __ldg(&rd.index[i[u] - 1]);
+                expect[u] = ((uint64_t)pr.x | ((uint64_t)pr.y << 32)) + pr.w;
             }
-            ok = off == expect;
         }
-        if (ok) ok = ld_u64_unaligned(rd.data + off) == (uint64_t)(ks - 8);
-        if (ok) ok = ld_u64_unaligned(rd.data + off + ks) == (uint64_t)(fs - ks - 24);
-        if (!ok) {
-            atomicMin(&p.first_bad[r], i);
-            atomicOr(&c->flags, kFlagTruncated);
+        // ---- phase 2: everything that can be decided from the index alone, then the entry header loads
+        uint64_t klen_w[kExtractEPT], dlen_w[kExtractEPT], w0[kExtractEPT], w1[kExtractEPT];
+        bool match[kExtractEPT];
+#pragma unroll
+        for (int u = 0; u < kExtractEPT; u++) {
+            if (!act[u]) continue;
+            if (redo) {
+                ok[u] = i[u] < p.first_bad[r[u]];
+            } else {
+                ok[u] = ks[u] >= 8 && (uint64_t)fs[u] >= (uint64_t)ks[u] + 24 && off[u] <= dlen_total[u] &&
+                        (uint64_t)fs[u] <= dlen_total[u] - off[u] && off[u] == expect[u];
+            }
+            match[u] = false;
+            klen_w[u] = dlen_w[u] = w0[u] = w1[u] = 0;
+            if (ok[u]) {
+                const uint8_t *e = data[u] + off[u];
+                klen_w[u] = ld_u64_unaligned(e);
+                dlen_w[u] = ld_u64_unaligned(e + ks[u]);
+                const uint32_t klen = ks[u] - 8;
+                match[u] = klen >= L;
+                if (match[u]) {
+                    const uint8_t *key = e + 8;
+                    // every load below stays inside the entry: >= 24 bytes (dlen + timestamp) follow the key
+                    w0[u] = ld_u64_unaligned(key + L);
+                    w1[u] = ld_u64_unaligned(key + L + 8);
+                    for (uint32_t q = 0; q < npw; q++) {
+                        const uint64_t kw = ld_u64_unaligned(key + 8 * q);
+                        const uint32_t nb = L - 8 * q; // prefix bytes in this word (>= 1)
+                        const uint64_t mask = nb >= 8 ? ~0ull : ((1ull << (8 * nb)) - 1);
+                        match[u] = match[u] && (((kw ^ pfx[q]) & mask) == 0);
+                    }
+                }
+            }
         }
-    }
-    Rec out;
-    out.x = out.y = out.z = 0;
-    out.w = g;
-    if (ok) {
-        const uint32_t L = c->prefix_len;
-        const uint32_t klen = ks - 8;
-        const uint8_t *key = rd.data + off + 8;
-        bool match = klen >= L;
-        for (uint32_t b = 0; match && b < L; b++) match = __ldg(key + b) == c->prefix[b];
-        if (match) {
-            // both loads stay inside the entry: at least 24 bytes (dlen + timestamp) follow the key
-            uint64_t w0 = ld_u64_unaligned(key + L);
-            uint64_t w1 = ld_u64_unaligned(key + L + 8);
-            out = make_rec(w0, w1, klen - L, g);
-        } else {
-            atomicMin(&p.first_mismatch[r], i);
+        // ---- phase 3: verdicts and records
+#pragma unroll
+        for (int u = 0; u < kExtractEPT; u++) {
+            if (!act[u]) continue;
+            if (!redo) {
+                if (ok[u]) ok[u] = klen_w[u] == (uint64_t)(ks[u] - 8) && dlen_w[u] == (uint64_t)(fs[u] - ks[u] - 24);
+                if (!ok[u]) {
+                    atomicMin(&p.first_bad[r[u]], i[u]);
+                    atomicOr(&c->flags, kFlagTruncated);
+                }
+            }
+            Rec out;
+            out.x = out.y = out.z = 0;
+            out.w = g[u];
+            if (ok[u]) {
+                if (match[u]) out = make_rec(w0[u], w1[u], (uint64_t)(ks[u] - 8 - L), g[u]);
+                else atomicMin(&p.first_mismatch[r[u]], i[u]);
+            }
+            st_rec(&p.rec_a[g[u]], out);
         }
-    }
-    st_rec(&p.rec_a[g], out);
     }
 }
 
@@ -545,7 +585,7 @@ __global__ void __launch_bounds__(kMergeThreads, 4) k_merge(Params p, uint32_t l
 // it sits in a group of two or more -- its own timestamp, so the loads of a group run in
 // parallel; the head then reduces over shared memory.
 // Output, in merged order: res[i] = {entry address (u64), key_size, full_size or 0 if nothing
-// is emitted at position i}.
+// is emitted at position i}, plus each 256-record tile's (bytes, entries) aggregate.
 
 __device__ __forceinline__ void ld_ts(const uint8_t *entry, uint32_t full_size, uint64_t *lo, uint64_t *hi) {
     const uint8_t *t = entry + full_size - 16;
@@ -596,11 +636,10 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec
     s_fs[tid] = me.full_size;
     s_eqn[tid] = eq_next ? 1 : 0;
     __syncthreads();
-    if (!active) return;
 
     uint32_t keep = 0, ks = 0, fs = 0;
     unsigned long long src = 0;
-    if (!eq_prev) { // head of its group
+    if (active && !eq_prev) { // head of its group
         uint32_t w = tid; // winner so far, as an index into this tile's shared arrays
         ks = s_ks[tid]; fs = s_fs[tid]; src = s_entry[tid];
         if (eq_next) {
@@ -638,54 +677,98 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec
         bool tomb = fs == ks + 24;
         keep = (p.keep_tombstones || p.mode_flush || !tomb) ? 1u : 0u;
     }
-    res[i] = make_uint4((uint32_t)src, (uint32_t)(src >> 32), ks, keep ? fs : 0u);
+    if (active) res[i] = make_uint4((uint32_t)src, (uint32_t)(src >> 32), ks, keep ? fs : 0u);
+
+    // tile aggregate (bytes, entries) for the offsets scan
+    unsigned long long vb = keep ? fs : 0ull;
+    uint32_t vc = keep;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        vb += __shfl_xor_sync(0xFFFFFFFFu, vb, o);
+        vc += __shfl_xor_sync(0xFFFFFFFFu, vc, o);
+    }
+    __syncthreads(); // s_tlo / s_ks are dead: reuse them as the cross-warp scratch
+    if ((tid & 31) == 0) { s_tlo[tid >> 5] = vb; s_ks[tid >> 5] = vc; }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long tb = 0;
+        uint32_t tc = 0;
+        for (int w = 0; w < NT / 32; w++) { tb += s_tlo[w]; tc += s_ks[w]; }
+        p.tile_bytes[blockIdx.x] = tb;
+        p.tile_count[blockIdx.x] = tc;
+    }
 }
 
 // ------------------------------------------------------------------------------------
-// K4b: scan + emit.  Stream compaction of res[] with an exclusive scan of (bytes, count):
-// the survivor at merged position i becomes output entry `count before i`, at .data offset
-// `bytes before i` (entry_writer.rs:81-86: offset = running sum of full_size).
-// Single pass, decoupled look-back over 2048-record tiles.  Each tile publishes two
-// self-validating 64-bit descriptors (2 status bits + 62 value bits), so one look-back step
-// is a single round trip to L2, and the tiles are big because the look-back frontier moves
-// at most 32 tiles per round trip.
-// Writes out_index (the output .index file itself), src_ptr, and for every 16 KB tile of
-// the output .data stream the entry that holds the tile's first byte (tile_first).
+// K4b: offsets.  The survivor at merged position i becomes output entry `count before i`, at
+// .data offset `bytes before i` (entry_writer.rs:81-86: offset = running sum of full_size).
+// Two steps, no inter-CTA waiting: (1) one CTA turns the per-tile aggregates into exclusive
+// prefixes (a few 10k values); (2) every tile rescans its 256 records locally and emits
+// out_index (the output .index file itself), src_ptr, and -- for every 16 KB tile of the
+// output .data stream -- the entry that holds the tile's first byte (tile_first).
 
-constexpr unsigned long long kDescValueMask = (1ull << 62) - 1;
-
-__global__ void __launch_bounds__(kScanThreads) k_scan_emit(Params p, const uint4 *res) {
-    constexpr int NT = kScanThreads;
-    constexpr int IPT = kScanItemsPerThread;
-    constexpr int NW = NT / 32;
-    __shared__ uint32_t s_tile;
-    __shared__ unsigned long long s_wb[NW];
-    __shared__ uint32_t s_wc[NW];
-    __shared__ unsigned long long s_excl_b;
-    __shared__ uint32_t s_excl_c;
+__global__ void __launch_bounds__(1024) k_scan_tiles(Params p) {
+    __shared__ unsigned long long s_b[32];
+    __shared__ uint32_t s_c[32];
     Ctl *c = p.ctl;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(&c->ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    const uint32_t total = c->total;
-    constexpr uint32_t TILE = NT * IPT;
-    if ((uint64_t)tile * TILE >= total) return;
-    const uint32_t n_tiles = (total + TILE - 1) / TILE;
-    const uint32_t base = tile * TILE + tid * IPT; // blocked: thread owns IPT consecutive records
-
-    uint4 it[IPT];
-    unsigned long long tb = 0;
-    uint32_t tc = 0;
+    const uint32_t n_tiles = (c->total + kResolveThreads - 1) / kResolveThreads;
+    const uint32_t per = (n_tiles + 1023) / 1024;
+    const uint32_t t0 = tid * per < n_tiles ? tid * per : n_tiles;
+    const uint32_t t1 = t0 + per < n_tiles ? t0 + per : n_tiles;
+    unsigned long long sb = 0;
+    uint32_t sc = 0;
+    for (uint32_t t = t0; t < t1; t++) { sb += p.tile_bytes[t]; sc += p.tile_count[t]; }
+    unsigned long long ib = sb;
+    uint32_t ic = sc;
 #pragma unroll
-    for (int k = 0; k < IPT; k++) {
-        it[k] = make_uint4(0, 0, 0, 0);
-        if (base + k < total) it[k] = __ldg(&res[base + k]);
-        tb += it[k].w;
-        tc += it[k].w ? 1u : 0u;
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long xb = __shfl_up_sync(0xFFFFFFFFu, ib, o);
+        uint32_t xc = __shfl_up_sync(0xFFFFFFFFu, ic, o);
+        if (lane >= (uint32_t)o) { ib += xb; ic += xc; }
     }
-    unsigned long long ib = tb;
-    uint32_t ic = tc;
+    if (lane == 31) { s_b[warp] = ib; s_c[warp] = ic; }
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long wb = s_b[lane];
+        uint32_t wc = s_c[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long xb = __shfl_up_sync(0xFFFFFFFFu, wb, o);
+            uint32_t xc = __shfl_up_sync(0xFFFFFFFFu, wc, o);
+            if (lane >= (uint32_t)o) { wb += xb; wc += xc; }
+        }
+        s_b[lane] = wb;
+        s_c[lane] = wc;
+        if (lane == 31) { c->out_data_len = wb; c->out_items = wc; }
+    }
+    __syncthreads();
+    unsigned long long eb = (warp ? s_b[warp - 1] : 0ull) + (ib - sb);
+    uint32_t ec = (warp ? s_c[warp - 1] : 0u) + (ic - sc);
+    for (uint32_t t = t0; t < t1; t++) {
+        const unsigned long long b = p.tile_bytes[t];
+        const uint32_t n = p.tile_count[t];
+        p.tile_bytes[t] = eb;
+        p.tile_count[t] = ec;
+        eb += b;
+        ec += n;
+    }
+}
+
+__global__ void __launch_bounds__(kResolveThreads) k_emit(Params p, const uint4 *res) {
+    constexpr int NT = kResolveThreads;
+    __shared__ unsigned long long s_wb[NT / 32];
+    __shared__ uint32_t s_wc[NT / 32];
+    const uint32_t total = p.ctl->total;
+    const uint32_t i0 = blockIdx.x * NT;
+    if (i0 >= total) return;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t i = i0 + tid;
+    uint4 it = make_uint4(0, 0, 0, 0);
+    if (i < total) it = __ldg(&res[i]);
+    const uint32_t fs = it.w;
+    unsigned long long ib = fs;
+    uint32_t ic = fs ? 1u : 0u;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         unsigned long long xb = __shfl_up_sync(0xFFFFFFFFu, ib, o);
@@ -694,77 +777,15 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_emit(Params p, const uint
     }
     if (lane == 31) { s_wb[warp] = ib; s_wc[warp] = ic; }
     __syncthreads();
-    if (warp == 0) {
-        unsigned long long wb = lane < NW ? s_wb[lane] : 0ull;
-        uint32_t wc = lane < NW ? s_wc[lane] : 0u;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned long long xb = __shfl_up_sync(0xFFFFFFFFu, wb, o);
-            uint32_t xc = __shfl_up_sync(0xFFFFFFFFu, wc, o);
-            if (lane >= (uint32_t)o) { wb += xb; wc += xc; }
-        }
-        const unsigned long long agg_b = __shfl_sync(0xFFFFFFFFu, wb, NW - 1);
-        const uint32_t agg_c = __shfl_sync(0xFFFFFFFFu, wc, NW - 1);
-        if (lane < NW) { s_wb[lane] = wb; s_wc[lane] = wc; }
-
-        volatile unsigned long long *db = p.scan_desc_bytes, *dc = p.scan_desc_cnt;
-        unsigned long long excl_b = 0, excl_c = 0;
-        if (tile > 0) {
-            if (lane == 0) {
-                db[tile] = (1ull << 62) | agg_b;
-                dc[tile] = (1ull << 62) | agg_c;
-            }
-            int look = (int)tile - 1;
-            while (true) {
-                const int idx = look - (int)lane;
-                unsigned long long vb = 2ull << 62, vc = 2ull << 62; // before tile 0: inclusive prefix 0
-                if (idx >= 0) {
-                    do { // both words present and of the same kind (aggregate / inclusive)
-                        vb = db[idx];
-                        vc = dc[idx];
-                    } while ((vb >> 62) == 0 || (vb >> 62) != (vc >> 62));
-                }
-                const uint32_t mask2 = __ballot_sync(0xFFFFFFFFu, (vb >> 62) == 2);
-                const uint32_t first = mask2 ? (uint32_t)__ffs(mask2) - 1 : 32u;
-                unsigned long long cb = lane <= first ? (vb & kDescValueMask) : 0ull;
-                unsigned long long cc = lane <= first ? (vc & kDescValueMask) : 0ull;
-#pragma unroll
-                for (int o = 16; o; o >>= 1) {
-                    cb += __shfl_xor_sync(0xFFFFFFFFu, cb, o);
-                    cc += __shfl_xor_sync(0xFFFFFFFFu, cc, o);
-                }
-                excl_b += cb;
-                excl_c += cc;
-                if (mask2) break;
-                look -= 32;
-            }
-        }
-        if (lane == 0) {
-            db[tile] = (2ull << 62) | (excl_b + agg_b);
-            dc[tile] = (2ull << 62) | (excl_c + agg_c);
-            s_excl_b = excl_b;
-            s_excl_c = (uint32_t)excl_c;
-            if (tile == n_tiles - 1) {
-                c->out_data_len = excl_b + agg_b;
-                c->out_items = (uint32_t)(excl_c + agg_c);
-            }
-        }
-    }
-    __syncthreads();
-    unsigned long long off = s_excl_b + (warp ? s_wb[warp - 1] : 0ull) + (ib - tb);
-    uint32_t pos = s_excl_c + (warp ? s_wc[warp - 1] : 0u) + (ic - tc);
-#pragma unroll
-    for (int k = 0; k < IPT; k++) {
-        const uint32_t fs = it[k].w;
-        if (!fs) continue;
-        p.out_index[pos] = make_uint4((uint32_t)off, (uint32_t)(off >> 32), it[k].z, fs);
-        p.src_ptr[pos] = (unsigned long long)it[k].x | ((unsigned long long)it[k].y << 32);
-        // every gather tile whose first byte lies in [off, off + fs) starts inside this entry
-        unsigned long long b = (off + kGatherTileBytes - 1) / kGatherTileBytes;
-        for (; b * kGatherTileBytes < off + fs; b++) p.tile_first[b] = pos;
-        off += fs;
-        pos++;
-    }
+    if (!fs) return;
+    unsigned long long off = p.tile_bytes[blockIdx.x] + ib - fs;
+    uint32_t pos = p.tile_count[blockIdx.x] + ic - 1;
+    for (uint32_t w = 0; w < warp; w++) { off += s_wb[w]; pos += s_wc[w]; }
+    p.out_index[pos] = make_uint4((uint32_t)off, (uint32_t)(off >> 32), it.z, fs);
+    p.src_ptr[pos] = (unsigned long long)it.x | ((unsigned long long)it.y << 32);
+    // every gather tile whose first byte lies in [off, off + fs) starts inside this entry
+    unsigned long long b = (off + kGatherTileBytes - 1) / kGatherTileBytes;
+    for (; b * kGatherTileBytes < off + fs; b++) p.tile_first[b] = pos;
 }
 
 // ------------------------------------------------------------------------------------
@@ -947,6 +968,220 @@ __global__ void __launch_bounds__(kGatherThreads) k_gather(Params p) {
                 atomicOr(&p.bloom.words[bit >> 5], 1u << (bit & 31));
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K5 (persistent, warp-specialized variant).  Same tiles and same byte-level work as k_gather,
+// restructured so the latencies overlap instead of adding up:
+//   * the grid is a few CTAs per SM and every CTA walks tiles blockIdx, blockIdx + grid, ...;
+//   * 8 "copy" warps do mark/scan/copy/straddle for tile q while
+//   * 2 "aux" warps stage tile q+1's entry list into the other shared-memory buffer, look up
+//     tile q+2's entry range, and run the bloom hashing of tile q (the fused epilogue) -- the
+//     SipHash chains execute while the copy warps wait on HBM.
+// Copy warps synchronise among themselves on named barrier 1; the whole CTA meets once per tile.
+
+constexpr int kGatherCopyThreads = 256;
+constexpr int kGatherAuxThreads = 64;
+constexpr int kGatherWsThreads = kGatherCopyThreads + kGatherAuxThreads;
+
+struct GatherTileMeta {
+    unsigned long long adj[kGatherMaxEntries]; // entry address minus its tile-relative start: byte b of the tile lives at adj + b
+    long long r0[kGatherMaxEntries];           // entry start relative to the tile (may be < 0)
+    int r1[kGatherMaxEntries];                 // entry end relative to the tile, clamped to INT_MAX
+    uint32_t ks[kGatherMaxEntries];
+    uint32_t ne;
+    uint32_t tile_len;
+};
+
+__device__ __forceinline__ void copy_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kGatherCopyThreads) : "memory"); }
+
+__device__ __forceinline__ void gather_stage(const Params &p, GatherTileMeta &m, unsigned long long T0, uint32_t e_lo,
+                                             uint32_t ne, uint32_t tile_len, uint32_t t, uint32_t nt) {
+    for (uint32_t j = t; j < ne; j += nt) {
+        const uint4 rec = p.out_index[e_lo + j];
+        const unsigned long long d0 = (unsigned long long)rec.x | ((unsigned long long)rec.y << 32);
+        const long long r0 = (long long)d0 - (long long)T0;
+        const long long r1 = r0 + (long long)rec.w;
+        m.adj[j] = p.src_ptr[e_lo + j] - (unsigned long long)r0;
+        m.r0[j] = r0;
+        m.r1[j] = r1 > 0x7FFFFFFFll ? 0x7FFFFFFF : (int)r1;
+        m.ks[j] = rec.z;
+    }
+    if (t == 0) { m.ne = ne; m.tile_len = tile_len; }
+}
+
+__global__ void __launch_bounds__(kGatherWsThreads, 3) k_gather_ws(Params p) {
+    constexpr int VPT = kGatherVecsPerThread;
+    constexpr int NV = kGatherCopyThreads * VPT;
+    __shared__ GatherTileMeta s_m[2];
+    __shared__ uint16_t s_vec[NV];
+    __shared__ uint32_t s_wmax[kGatherCopyThreads / 32];
+    __shared__ uint32_t s_elo[2], s_ehi[2];
+    const Ctl *c = p.ctl;
+    const unsigned long long out_len = c->out_data_len;
+    const uint32_t n_out = c->out_items;
+    const uint32_t tid = threadIdx.x;
+    const bool is_copy = tid < kGatherCopyThreads;
+    const uint32_t atid = tid - kGatherCopyThreads; // aux-thread index (aux warps only)
+    const unsigned long long G = gridDim.x;
+    unsigned long long tile = blockIdx.x;
+    if (tile * kGatherTileBytes >= out_len) return;
+
+    auto entry_range = [&](unsigned long long tl, uint32_t *lo, uint32_t *hi) {
+        *lo = p.tile_first[tl];
+        *hi = (tl + 1) * kGatherTileBytes < out_len ? p.tile_first[tl + 1] : n_out - 1;
+    };
+    auto tile_len_of = [&](unsigned long long tl) {
+        const unsigned long long T0 = tl * kGatherTileBytes;
+        return out_len - T0 < kGatherTileBytes ? (uint32_t)(out_len - T0) : (uint32_t)kGatherTileBytes;
+    };
+
+    // ---- prologue: entry ranges of this CTA's first two tiles, entry list of the first
+    if (tid < 2) {
+        const unsigned long long tl = tile + tid * G;
+        uint32_t lo = 0, hi = 0;
+        if (tl * kGatherTileBytes < out_len) entry_range(tl, &lo, &hi);
+        s_elo[tid] = lo;
+        s_ehi[tid] = hi;
+    }
+    __syncthreads();
+    gather_stage(p, s_m[0], tile * kGatherTileBytes, s_elo[0], s_ehi[0] - s_elo[0] + 1, tile_len_of(tile), tid, kGatherWsThreads);
+    __syncthreads();
+
+    for (uint32_t q = 0;; q++, tile += G) {
+        GatherTileMeta &m = s_m[q & 1];
+        const unsigned long long T0 = tile * kGatherTileBytes;
+        const unsigned long long next = tile + G;
+        const bool has_next = next * kGatherTileBytes < out_len;
+        if (!is_copy) {
+            // ================= aux warps =================
+            if (has_next) // stage tile q+1 (its entry range was looked up one tile ago)
+                gather_stage(p, s_m[(q + 1) & 1], next * kGatherTileBytes, s_elo[(q + 1) & 1],
+                             s_ehi[(q + 1) & 1] - s_elo[(q + 1) & 1] + 1, tile_len_of(next), atid, kGatherAuxThreads);
+            if (atid == 0) { // entry range of tile q+2 into the slot tile q no longer needs
+                const unsigned long long nn = next + G;
+                uint32_t lo = 0, hi = 0;
+                if (nn * kGatherTileBytes < out_len) entry_range(nn, &lo, &hi);
+                s_elo[q & 1] = lo;
+                s_ehi[q & 1] = hi;
+            }
+            if (p.bloom.words != nullptr) { // bloom of tile q: entries whose first byte lies in this tile
+                const uint32_t ne = m.ne;
+                for (uint32_t j = atid; j < ne; j += kGatherAuxThreads) {
+                    const long long r0 = m.r0[j];
+                    if (r0 < 0 || r0 >= (long long)kGatherTileBytes) continue;
+                    const uint8_t *key = reinterpret_cast<const uint8_t *>((uintptr_t)(m.adj[j] + (unsigned long long)r0)) + 8;
+                    const uint64_t klen = m.ks[j] - 8;
+                    uint64_t h0, h1;
+                    sip13_pair_vec_u8(p.bloom.sip, klen, [key](uint64_t w) { return ld_u64_unaligned(key + 8 * w); }, &h0, &h1);
+                    for (uint32_t k = 0; k < p.bloom.k_num; k++) {
+                        uint64_t bit = fastmod(bloom_hash_i(h0, h1, k), p.bloom.bits, p.bloom.bits_magic);
+                        atomicOr(&p.bloom.words[bit >> 5], 1u << (bit & 31));
+                    }
+                }
+            }
+        } else {
+            // ================= copy warps =================
+            const uint32_t lane = tid & 31, warp = tid >> 5;
+            const uint32_t ne = m.ne, tile_len = m.tile_len;
+            for (uint32_t v = tid; v < NV; v += kGatherCopyThreads) s_vec[v] = 0;
+            copy_bar();
+            for (uint32_t j = tid; j < ne; j += kGatherCopyThreads) {
+                const long long r0 = m.r0[j];
+                const uint32_t fv = r0 <= 0 ? 0u : (uint32_t)((r0 + 15) >> 4); // first vector starting inside the entry
+                if (fv < NV) s_vec[fv] = (uint16_t)j;
+            }
+            copy_bar();
+            { // inclusive max-scan of the marks: s_vec[v] = entry that holds byte 16*v of the tile
+                uint32_t mk[VPT];
+                uint32_t run = 0;
+#pragma unroll
+                for (int k = 0; k < VPT; k++) {
+                    uint32_t x = s_vec[tid * VPT + k];
+                    run = x > run ? x : run;
+                    mk[k] = run;
+                }
+                uint32_t incl = run;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (lane >= (uint32_t)o) incl = t > incl ? t : incl;
+                }
+                if (lane == 31) s_wmax[warp] = incl;
+                copy_bar();
+                uint32_t before = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+                if (lane == 0) before = 0;
+                for (uint32_t w = 0; w < warp; w++) before = s_wmax[w] > before ? s_wmax[w] : before;
+#pragma unroll
+                for (int k = 0; k < VPT; k++) s_vec[tid * VPT + k] = (uint16_t)(mk[k] > before ? mk[k] : before);
+            }
+            copy_bar();
+            uint8_t *dst_tile = p.out_data + T0;
+            uint4 A[VPT], B[VPT];
+            uint32_t sh[VPT];
+            bool pure[VPT];
+#pragma unroll
+            for (int k = 0; k < VPT; k++) {
+                const uint32_t v = tid + k * kGatherCopyThreads;
+                const uint32_t b0 = v * 16;
+                pure[k] = false;
+                sh[k] = 0;
+                if (b0 + 16 <= tile_len) {
+                    const uint32_t j = s_vec[v];
+                    if ((int)(b0 + 16) <= m.r1[j]) {
+                        const uintptr_t sa = (uintptr_t)(m.adj[j] + b0);
+                        sh[k] = (uint32_t)(sa & 15);
+                        const uint4 *sv = reinterpret_cast<const uint4 *>(sa - sh[k]);
+                        A[k] = __ldg(sv);
+                        B[k] = __ldg(sh[k] ? sv + 1 : sv);
+                        pure[k] = true;
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < VPT; k++) {
+                const uint32_t v = tid + k * kGatherCopyThreads;
+                if (pure[k]) reinterpret_cast<uint4 *>(dst_tile)[v] = realign16_sel(A[k], B[k], sh[k]);
+            }
+            // vectors that straddle an entry boundary: one per entry, handled densely (see k_gather)
+            for (uint32_t j = tid; j < ne; j += kGatherCopyThreads) {
+                const int r1 = m.r1[j];
+                if (r1 <= 0 || (r1 & 15) == 0 || r1 > (int)tile_len) continue;
+                const uint32_t v = (uint32_t)r1 >> 4;
+                const uint32_t b0 = v * 16;
+                const uint32_t t = (uint32_t)r1 - b0; // tail bytes of entry j in this vector: 1..15
+                const uintptr_t sa = (uintptr_t)(m.adj[j] + b0);
+                const uint32_t s0 = (uint32_t)(sa & 15);
+                const uint4 *sv = reinterpret_cast<const uint4 *>(sa - s0);
+                const uint4 TA = __ldg(sv);
+                const uint4 TB = __ldg(s0 + t > 16 ? sv + 1 : sv);
+                uint4 o = realign16_sel(TA, TB, s0);
+                if (b0 + 16 <= tile_len) {
+                    const uintptr_t ha = (uintptr_t)(m.adj[j + 1] + (unsigned long long)m.r0[j + 1]); // first byte of entry j+1
+                    const uint32_t hs = (uint32_t)(ha & 15);
+                    const uint4 *hv = reinterpret_cast<const uint4 *>(ha - hs);
+                    const uint4 HA = __ldg(hv);
+                    const uint4 HB = __ldg(hs ? hv + 1 : hv);
+                    const uint4 H = realign16_sel(HA, HB, hs);
+                    const uint4 HU = realign16_sel(make_uint4(0, 0, 0, 0), H, 16 - t);
+                    const uint32_t wfull = t >> 2, bits = (t & 3) * 8;
+                    const uint32_t mmix = bits ? (0xFFFFFFFFu >> (32 - bits)) : 0u;
+                    uint32_t ow[4] = {o.x, o.y, o.z, o.w}, hw[4] = {HU.x, HU.y, HU.z, HU.w};
+#pragma unroll
+                    for (uint32_t w = 0; w < 4; w++) {
+                        const uint32_t mk = w < wfull ? 0xFFFFFFFFu : (w == wfull ? mmix : 0u);
+                        ow[w] = (ow[w] & mk) | (hw[w] & ~mk);
+                    }
+                    reinterpret_cast<uint4 *>(dst_tile)[v] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                } else { // ragged end of the whole stream: never write past out_data_len
+                    const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+                    for (uint32_t b = 0; b < t; b++) dst_tile[b0 + b] = (uint8_t)(ow[b >> 2] >> ((b & 3) * 8));
+                }
+            }
+        }
+        __syncthreads(); // tile q done everywhere; tile q+1's entry list and tile q+2's range are in place
+        if (!has_next) break;
     }
 }
 
