@@ -45,7 +45,8 @@ struct dbeel_engine {
     std::string err;
     bool busy = false;
     int sm_count = 148;
-    int gather_variant = 1;     // DBEEL_GATHER: 0 = one CTA per tile, 1 = persistent warp-specialized
+    int gather_variant = 2;     // DBEEL_GATHER: 0 = one CTA per 16 KB tile, 1 = persistent warp-specialized, 2 = one warp per 2 KB tile
+    int bloom_in_emit = 0;      // DBEEL_BLOOM_IN_EMIT (variants 0/1; variant 2 always hashes in k_emit)
     int gather_ctas_per_sm = 4; // DBEEL_GATHER_CTAS
 };
 
@@ -191,9 +192,12 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     const uint64_t o_part = carve(4 * bounds_ub);
     const uint64_t res_tiles = (uint64_t)(N + kResolveThreads - 1) / kResolveThreads;
     const uint64_t o_tbytes = carve(res_tiles * 8), o_tcount = carve(res_tiles * 4);
+    const uint64_t res_chunks = (res_tiles + 1023) / 1024;
+    const uint64_t o_cbytes = carve(res_chunks * 8), o_ccount = carve(res_chunks * 4);
     const uint64_t o_reca = carve(16ull * N), o_recb = carve(16ull * N);
     const uint64_t o_src = carve(8ull * N);
-    const uint64_t gather_tiles = (sh.data_total + kGatherTileBytes - 1) / kGatherTileBytes;
+    const uint64_t gtb = e->gather_variant == 2 ? kWarpTileBytes : kGatherTileBytes;
+    const uint64_t gather_tiles = (sh.data_total + gtb - 1) / gtb;
     const uint64_t o_tfirst = carve(4ull * (gather_tiles + 2));
     int rc = ensure_device(e, &e->ws, &e->ws_cap, off);
     if (rc) return rc;
@@ -210,10 +214,14 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     p.part = reinterpret_cast<uint32_t *>(ws + o_part);
     p.tile_bytes = reinterpret_cast<unsigned long long *>(ws + o_tbytes);
     p.tile_count = reinterpret_cast<uint32_t *>(ws + o_tcount);
+    p.chunk_bytes = reinterpret_cast<unsigned long long *>(ws + o_cbytes);
+    p.chunk_count = reinterpret_cast<uint32_t *>(ws + o_ccount);
     p.rec_a = reinterpret_cast<Rec *>(ws + o_reca);
     p.rec_b = reinterpret_cast<Rec *>(ws + o_recb);
     p.src_ptr = reinterpret_cast<unsigned long long *>(ws + o_src);
     p.tile_first = reinterpret_cast<uint32_t *>(ws + o_tfirst);
+    p.gather_tile_bytes = gtb;
+    p.bloom_in_emit = e->gather_variant == 2 || e->bloom_in_emit;
     p.out_data = static_cast<uint8_t *>(out->data);
     p.out_index = static_cast<uint4 *>(out->index);
 
@@ -300,20 +308,24 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     CU(cudaEventRecord(e->ev[EV_MERGE], s));
 
     // ---- K4: resolve + scan + .index
-    uint4 *res = reinterpret_cast<uint4 *>(dst); // the ping-pong buffer that does not hold the merged order
-    k_resolve<<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, src, res);
-    k_scan_tiles<<<1, 1024, 0, s>>>(p);
-    k_emit<<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, res);
-    launches += 3;
-    CU(cudaEventRecord(e->ev[EV_RESOLVE], s));
-
-    // ---- K5: gather + bloom
     if (sh.bloom_file) {
         k_bloom_frame<<<1, 1, 0, s>>>(static_cast<uint8_t *>(out->bloom), sh.bloom_words, p.bloom);
         launches++;
     }
+    uint4 *res = reinterpret_cast<uint4 *>(dst); // the ping-pong buffer that does not hold the merged order
+    k_resolve<<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, src, res);
+    k_scan_tiles<<<(uint32_t)res_chunks, 1024, 0, s>>>(p);
+    k_scan_chunks<<<1, 1024, 0, s>>>(p);
+    k_emit<<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, res);
+    launches += 4;
+    CU(cudaEventRecord(e->ev[EV_RESOLVE], s));
+
+    // ---- K5: gather (+ bloom in the CTA-tile variants)
     if (gather_tiles) {
-        if (e->gather_variant == 0) {
+        if (e->gather_variant == 2) { // one warp per 2 KB tile
+            constexpr uint64_t wpb = kGatherWarpThreads / 32;
+            k_gather_warp<<<(uint32_t)((gather_tiles + wpb - 1) / wpb), kGatherWarpThreads, 0, s>>>(p);
+        } else if (e->gather_variant == 0) {
             k_gather<<<(uint32_t)gather_tiles, kGatherThreads, 0, s>>>(p);
         } else { // persistent, warp-specialized
             uint64_t grid = (uint64_t)e->sm_count * e->gather_ctas_per_sm;
@@ -474,6 +486,7 @@ int dbeel_engine_create(int device, dbeel_engine **out) {
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
     if (const char *v = getenv("DBEEL_GATHER")) e->gather_variant = atoi(v);
+    if (const char *v = getenv("DBEEL_BLOOM_IN_EMIT")) e->bloom_in_emit = atoi(v);
     if (const char *v = getenv("DBEEL_GATHER_CTAS")) e->gather_ctas_per_sm = atoi(v) > 0 ? atoi(v) : 4;
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return DBEEL_ERR_CUDA; }
     for (int i = 0; i < EV_COUNT; i++)

@@ -78,13 +78,17 @@ struct Params {
     // resolve / scan
     unsigned long long *tile_bytes; // [resolve tiles] bytes emitted by the tile, then (k_scan_tiles) bytes before it
     uint32_t *tile_count;           // [resolve tiles] same for entries
+    unsigned long long *chunk_bytes; // [resolve tiles / 1024] the same one level up
+    uint32_t *chunk_count;
     int keep_tombstones;
     int mode_flush; // 1: arrival batch -- winner = last arrival, tombstones kept
     // outputs
     uint8_t *out_data;
     uint4 *out_index;
     unsigned long long *src_ptr; // [n_total] device address of each surviving entry's bytes
-    uint32_t *tile_first;        // [ceil(data bytes / 16 KB) + 1] entry holding each gather tile's first byte
+    uint32_t *tile_first;        // [ceil(data bytes / gather_tile_bytes) + 2] entry holding each gather tile's first byte
+    unsigned long long gather_tile_bytes; // 16 KB (CTA tiles) or 2 KB (warp tiles)
+    int bloom_in_emit;           // 1: k_emit sets the bloom bits; 0: the gather kernel does
     BloomParams bloom;
 };
 
@@ -702,25 +706,17 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec
 // ------------------------------------------------------------------------------------
 // K4b: offsets.  The survivor at merged position i becomes output entry `count before i`, at
 // .data offset `bytes before i` (entry_writer.rs:81-86: offset = running sum of full_size).
-// Two steps, no inter-CTA waiting: (1) one CTA turns the per-tile aggregates into exclusive
-// prefixes (a few 10k values); (2) every tile rescans its 256 records locally and emits
+// No inter-CTA waiting: (1) the per-tile aggregates are scanned in chunks of 1024 tiles, (2) one
+// CTA scans the chunk totals, (3) every tile rescans its 256 records locally and emits
 // out_index (the output .index file itself), src_ptr, and -- for every 16 KB tile of the
 // output .data stream -- the entry that holds the tile's first byte (tile_first).
 
-__global__ void __launch_bounds__(1024) k_scan_tiles(Params p) {
-    __shared__ unsigned long long s_b[32];
-    __shared__ uint32_t s_c[32];
-    Ctl *c = p.ctl;
+// block-wide exclusive scan of (bytes, count) over 1024 threads; returns the block totals
+__device__ __forceinline__ void block_excl_scan_1024(unsigned long long &vb, uint32_t &vc, unsigned long long *s_b,
+                                                     uint32_t *s_c, unsigned long long *tot_b, uint32_t *tot_c) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t n_tiles = (c->total + kResolveThreads - 1) / kResolveThreads;
-    const uint32_t per = (n_tiles + 1023) / 1024;
-    const uint32_t t0 = tid * per < n_tiles ? tid * per : n_tiles;
-    const uint32_t t1 = t0 + per < n_tiles ? t0 + per : n_tiles;
-    unsigned long long sb = 0;
-    uint32_t sc = 0;
-    for (uint32_t t = t0; t < t1; t++) { sb += p.tile_bytes[t]; sc += p.tile_count[t]; }
-    unsigned long long ib = sb;
-    uint32_t ic = sc;
+    unsigned long long ib = vb;
+    uint32_t ic = vc;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         unsigned long long xb = __shfl_up_sync(0xFFFFFFFFu, ib, o);
@@ -740,19 +736,55 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(Params p) {
         }
         s_b[lane] = wb;
         s_c[lane] = wc;
-        if (lane == 31) { c->out_data_len = wb; c->out_items = wc; }
     }
     __syncthreads();
-    unsigned long long eb = (warp ? s_b[warp - 1] : 0ull) + (ib - sb);
-    uint32_t ec = (warp ? s_c[warp - 1] : 0u) + (ic - sc);
-    for (uint32_t t = t0; t < t1; t++) {
-        const unsigned long long b = p.tile_bytes[t];
-        const uint32_t n = p.tile_count[t];
-        p.tile_bytes[t] = eb;
-        p.tile_count[t] = ec;
-        eb += b;
-        ec += n;
+    *tot_b = s_b[31];
+    *tot_c = s_c[31];
+    vb = (warp ? s_b[warp - 1] : 0ull) + (ib - vb);
+    vc = (warp ? s_c[warp - 1] : 0u) + (ic - vc);
+}
+
+// step 1: chunks of 1024 tiles, one CTA each: in-place exclusive scan + the chunk's totals
+__global__ void __launch_bounds__(1024) k_scan_tiles(Params p) {
+    __shared__ unsigned long long s_b[32];
+    __shared__ uint32_t s_c[32];
+    const uint32_t n_tiles = (p.ctl->total + kResolveThreads - 1) / kResolveThreads;
+    const uint32_t t = blockIdx.x * 1024u + threadIdx.x;
+    if (blockIdx.x * 1024u >= n_tiles) return;
+    unsigned long long vb = t < n_tiles ? p.tile_bytes[t] : 0ull;
+    uint32_t vc = t < n_tiles ? p.tile_count[t] : 0u;
+    unsigned long long tb;
+    uint32_t tc;
+    block_excl_scan_1024(vb, vc, s_b, s_c, &tb, &tc);
+    if (t < n_tiles) { p.tile_bytes[t] = vb; p.tile_count[t] = vc; }
+    if (threadIdx.x == 0) { p.chunk_bytes[blockIdx.x] = tb; p.chunk_count[blockIdx.x] = tc; }
+}
+
+// step 2: one CTA scans the chunk totals (1024x fewer than tiles) and publishes the job totals
+__global__ void __launch_bounds__(1024) k_scan_chunks(Params p) {
+    __shared__ unsigned long long s_b[32];
+    __shared__ uint32_t s_c[32];
+    Ctl *c = p.ctl;
+    const uint32_t n_tiles = (c->total + kResolveThreads - 1) / kResolveThreads;
+    const uint32_t n_chunks = (n_tiles + 1023) / 1024;
+    const uint32_t per = (n_chunks + 1023) / 1024;
+    const uint32_t c0 = threadIdx.x * per < n_chunks ? threadIdx.x * per : n_chunks;
+    const uint32_t c1 = c0 + per < n_chunks ? c0 + per : n_chunks;
+    unsigned long long vb = 0;
+    uint32_t vc = 0;
+    for (uint32_t k = c0; k < c1; k++) { vb += p.chunk_bytes[k]; vc += p.chunk_count[k]; }
+    unsigned long long tb;
+    uint32_t tc;
+    block_excl_scan_1024(vb, vc, s_b, s_c, &tb, &tc);
+    for (uint32_t k = c0; k < c1; k++) {
+        const unsigned long long b = p.chunk_bytes[k];
+        const uint32_t n = p.chunk_count[k];
+        p.chunk_bytes[k] = vb;
+        p.chunk_count[k] = vc;
+        vb += b;
+        vc += n;
     }
+    if (threadIdx.x == 0) { c->out_data_len = tb; c->out_items = tc; }
 }
 
 __global__ void __launch_bounds__(kResolveThreads) k_emit(Params p, const uint4 *res) {
@@ -778,14 +810,28 @@ __global__ void __launch_bounds__(kResolveThreads) k_emit(Params p, const uint4 
     if (lane == 31) { s_wb[warp] = ib; s_wc[warp] = ic; }
     __syncthreads();
     if (!fs) return;
-    unsigned long long off = p.tile_bytes[blockIdx.x] + ib - fs;
-    uint32_t pos = p.tile_count[blockIdx.x] + ic - 1;
+    unsigned long long off = p.chunk_bytes[blockIdx.x >> 10] + p.tile_bytes[blockIdx.x] + ib - fs;
+    uint32_t pos = p.chunk_count[blockIdx.x >> 10] + p.tile_count[blockIdx.x] + ic - 1;
     for (uint32_t w = 0; w < warp; w++) { off += s_wb[w]; pos += s_wc[w]; }
+    const unsigned long long src = (unsigned long long)it.x | ((unsigned long long)it.y << 32);
     p.out_index[pos] = make_uint4((uint32_t)off, (uint32_t)(off >> 32), it.z, fs);
-    p.src_ptr[pos] = (unsigned long long)it.x | ((unsigned long long)it.y << 32);
+    p.src_ptr[pos] = src;
     // every gather tile whose first byte lies in [off, off + fs) starts inside this entry
-    unsigned long long b = (off + kGatherTileBytes - 1) / kGatherTileBytes;
-    for (; b * kGatherTileBytes < off + fs; b++) p.tile_first[b] = pos;
+    const unsigned long long tb = p.gather_tile_bytes;
+    unsigned long long b = (off + tb - 1) / tb;
+    for (; b * tb < off + fs; b++) p.tile_first[b] = pos;
+    // fused epilogue: the survivor's bloom bits (lsm_tree.rs:1049-1051) are set by the same thread
+    // that writes its .index record
+    if (p.bloom.words != nullptr && p.bloom_in_emit) {
+        const uint8_t *key = reinterpret_cast<const uint8_t *>((uintptr_t)src) + 8;
+        const uint64_t klen = it.z - 8;
+        uint64_t h0, h1;
+        sip13_pair_vec_u8(p.bloom.sip, klen, [key](uint64_t w) { return ld_u64_unaligned(key + 8 * w); }, &h0, &h1);
+        for (uint32_t k = 0; k < p.bloom.k_num; k++) {
+            uint64_t bit = fastmod(bloom_hash_i(h0, h1, k), p.bloom.bits, p.bloom.bits_magic);
+            atomicOr(&p.bloom.words[bit >> 5], 1u << (bit & 31));
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------
@@ -955,7 +1001,7 @@ __global__ void __launch_bounds__(kGatherThreads) k_gather(Params p) {
 
     // ---- bloom: entries whose first byte lies in this tile (each entry belongs to exactly one tile).
     // Done last so the copy's loads are in flight first; the key bytes are L1/L2-hot by now.
-    if (p.bloom.words != nullptr) {
+    if (p.bloom.words != nullptr && !p.bloom_in_emit) {
         for (uint32_t j = tid; j < ne; j += NT) {
             const long long r0 = s_r0[j];
             if (r0 < 0 || r0 >= (long long)kGatherTileBytes) continue;
@@ -1066,7 +1112,7 @@ __global__ void __launch_bounds__(kGatherWsThreads, 3) k_gather_ws(Params p) {
                 s_elo[q & 1] = lo;
                 s_ehi[q & 1] = hi;
             }
-            if (p.bloom.words != nullptr) { // bloom of tile q: entries whose first byte lies in this tile
+            if (p.bloom.words != nullptr && !p.bloom_in_emit) { // bloom of tile q: entries whose first byte lies in this tile
                 const uint32_t ne = m.ne;
                 for (uint32_t j = atid; j < ne; j += kGatherAuxThreads) {
                     const long long r0 = m.r0[j];
@@ -1182,6 +1228,118 @@ __global__ void __launch_bounds__(kGatherWsThreads, 3) k_gather_ws(Params p) {
         }
         __syncthreads(); // tile q done everywhere; tile q+1's entry list and tile q+2's range are in place
         if (!has_next) break;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K5 (warp-tile variant): every WARP owns a 2 KB tile of the output stream (128 vectors, 4 per
+// lane) and works alone -- its entry list lives in a warp-private slice of shared memory, the
+// vector -> entry lookup is a short binary search over the (sorted) entry ends, and nothing
+// ever waits on a block-wide barrier, so 40 warps per SM each keep 8 independent 16-byte
+// loads in flight.  Bloom bits are set by k_emit in this configuration.
+
+constexpr int kWarpTileVecs = 128;
+constexpr unsigned long long kWarpTileBytes = 16ull * kWarpTileVecs;  // 2 KB
+constexpr int kWarpTileMaxEntries = (int)(kWarpTileBytes / 32) + 2;  // 66
+constexpr int kGatherWarpThreads = 256;
+
+__global__ void __launch_bounds__(kGatherWarpThreads) k_gather_warp(Params p) {
+    constexpr int WPB = kGatherWarpThreads / 32;
+    constexpr int VPL = kWarpTileVecs / 32; // vectors per lane
+    __shared__ unsigned long long s_adj[WPB][kWarpTileMaxEntries];
+    __shared__ int s_r1[WPB][kWarpTileMaxEntries];
+    __shared__ int s_r0[WPB][kWarpTileMaxEntries];
+    const Ctl *c = p.ctl;
+    const unsigned long long out_len = c->out_data_len;
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned long long tile = (unsigned long long)blockIdx.x * WPB + w;
+    const unsigned long long T0 = tile * kWarpTileBytes;
+    if (T0 >= out_len) return; // whole warp
+    const uint32_t tile_len = out_len - T0 < kWarpTileBytes ? (uint32_t)(out_len - T0) : (uint32_t)kWarpTileBytes;
+    const uint32_t e_lo = p.tile_first[tile];
+    const uint32_t e_hi = T0 + kWarpTileBytes < out_len ? p.tile_first[tile + 1] : c->out_items - 1;
+    const uint32_t ne = e_hi - e_lo + 1; // <= kWarpTileMaxEntries: every entry is >= 32 bytes
+    unsigned long long *adj = s_adj[w];
+    int *r1s = s_r1[w], *r0s = s_r0[w];
+    for (uint32_t j = lane; j < ne; j += 32) {
+        const uint4 rec = p.out_index[e_lo + j];
+        const unsigned long long d0 = (unsigned long long)rec.x | ((unsigned long long)rec.y << 32);
+        const long long r0 = (long long)d0 - (long long)T0; // < 0 only for the tile's first entry
+        const long long r1 = r0 + (long long)rec.w;
+        adj[j] = p.src_ptr[e_lo + j] - (unsigned long long)r0;
+        r0s[j] = r0 < -0x7FFFFFFFll ? -0x7FFFFFFF : (int)r0;
+        r1s[j] = r1 > 0x7FFFFFFFll ? 0x7FFFFFFF : (int)r1;
+    }
+    __syncwarp();
+    uint32_t steps = 0;
+    while ((1u << steps) < ne) steps++; // binary-search depth, uniform across the warp
+
+    uint8_t *dst_tile = p.out_data + T0;
+    uint4 A[VPL], B[VPL];
+    uint32_t sh[VPL];
+    bool pure[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; k++) {
+        const uint32_t v = lane + 32 * k;
+        const int b0 = (int)(v * 16);
+        pure[k] = false;
+        sh[k] = 0;
+        if ((uint32_t)b0 + 16 <= tile_len) {
+            // entry holding byte b0: the first j with r1[j] > b0 (ends are ascending)
+            uint32_t lo = 0;
+            for (uint32_t st = steps; st-- > 0;) {
+                const uint32_t mid = lo + (1u << st);
+                if (mid < ne && r1s[mid - 1] <= b0) lo = mid;
+            }
+            if (b0 + 16 <= r1s[lo]) {
+                const uintptr_t sa = (uintptr_t)(adj[lo] + (unsigned long long)b0);
+                sh[k] = (uint32_t)(sa & 15);
+                const uint4 *sv = reinterpret_cast<const uint4 *>(sa - sh[k]);
+                A[k] = __ldg(sv);
+                B[k] = __ldg(sh[k] ? sv + 1 : sv);
+                pure[k] = true;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < VPL; k++) {
+        const uint32_t v = lane + 32 * k;
+        if (pure[k]) reinterpret_cast<uint4 *>(dst_tile)[v] = realign16_sel(A[k], B[k], sh[k]);
+    }
+    // the vector that holds the last byte of entry j: tail of j blended with the head of j+1
+    for (uint32_t j = lane; j < ne; j += 32) {
+        const int r1 = r1s[j];
+        if (r1 <= 0 || (r1 & 15) == 0 || r1 > (int)tile_len) continue;
+        const uint32_t v = (uint32_t)r1 >> 4;
+        const uint32_t b0 = v * 16;
+        const uint32_t t = (uint32_t)r1 - b0; // tail bytes of entry j in this vector: 1..15
+        const uintptr_t sa = (uintptr_t)(adj[j] + b0);
+        const uint32_t s0 = (uint32_t)(sa & 15);
+        const uint4 *sv = reinterpret_cast<const uint4 *>(sa - s0);
+        const uint4 TA = __ldg(sv);
+        const uint4 TB = __ldg(s0 + t > 16 ? sv + 1 : sv);
+        uint4 o = realign16_sel(TA, TB, s0);
+        if (b0 + 16 <= tile_len) {
+            const uintptr_t ha = (uintptr_t)(adj[j + 1] + (unsigned long long)(long long)r0s[j + 1]); // first byte of entry j+1 (r0 >= 0)
+            const uint32_t hs = (uint32_t)(ha & 15);
+            const uint4 *hv = reinterpret_cast<const uint4 *>(ha - hs);
+            const uint4 HA = __ldg(hv);
+            const uint4 HB = __ldg(hs ? hv + 1 : hv);
+            const uint4 H = realign16_sel(HA, HB, hs);
+            const uint4 HU = realign16_sel(make_uint4(0, 0, 0, 0), H, 16 - t);
+            const uint32_t wfull = t >> 2, bits = (t & 3) * 8;
+            const uint32_t mmix = bits ? (0xFFFFFFFFu >> (32 - bits)) : 0u;
+            uint32_t ow[4] = {o.x, o.y, o.z, o.w}, hw[4] = {HU.x, HU.y, HU.z, HU.w};
+#pragma unroll
+            for (uint32_t q = 0; q < 4; q++) {
+                const uint32_t mk = q < wfull ? 0xFFFFFFFFu : (q == wfull ? mmix : 0u);
+                ow[q] = (ow[q] & mk) | (hw[q] & ~mk);
+            }
+            reinterpret_cast<uint4 *>(dst_tile)[v] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        } else { // ragged end of the whole stream: never write past out_data_len
+            const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+            for (uint32_t b = 0; b < t; b++) dst_tile[b0 + b] = (uint8_t)(ow[b >> 2] >> ((b & 3) * 8));
+        }
     }
 }
 

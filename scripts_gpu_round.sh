@@ -3,16 +3,14 @@
 set -u
 mkdir -p gpurun_out
 nvidia-smi -L
-echo "=== pytest -m gpu (persistent gather)"
+echo "=== pytest -m gpu (default variant)"
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -15
-echo "=== pytest -m gpu (one-CTA-per-tile gather)"
-DBEEL_GATHER=0 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q 2>&1 | tail -5
 echo "=== bench (default)"
 timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
-for v in "0 4" "1 2" "1 3" "1 4"; do
+for v in "0 0" "0 1" "2 1"; do
   set -- $v
-  echo "=== bench DBEEL_GATHER=$1 DBEEL_GATHER_CTAS=$2"
-  DBEEL_GATHER=$1 DBEEL_GATHER_CTAS=$2 timeout 600 python bench.py --no-cpu --steps 30 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['stage_ms'], d['roofline']['frac'])"
+  echo "=== bench DBEEL_GATHER=$1 DBEEL_BLOOM_IN_EMIT=$2"
+  DBEEL_GATHER=$1 DBEEL_BLOOM_IN_EMIT=$2 timeout 600 python bench.py --no-cpu --steps 30 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['stage_ms'], d['roofline']['frac'])"
 done
 echo "=== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
