@@ -45,7 +45,8 @@ struct dbeel_engine {
     std::string err;
     bool busy = false;
     int sm_count = 148;
-    int gather_variant = 2;     // DBEEL_GATHER: 0 = one CTA per 16 KB tile, 1 = persistent warp-specialized, 2 = one warp per 2 KB tile
+    int gather_variant = 3;     // DBEEL_GATHER: 0 = one CTA per 16 KB tile, 1 = persistent warp-specialized, 2 = one warp per 2 KB tile, 3 = 16 KB CTA tile + warp sub-tiles
+    int merge_variant = 1;      // DBEEL_MERGE: 0 = one CTA per tile, 1 = persistent + cp.async double buffering
     int bloom_in_emit = 0;      // DBEEL_BLOOM_IN_EMIT (variants 0/1; variant 2 always hashes in k_emit)
     int gather_ctas_per_sm = 4; // DBEEL_GATHER_CTAS
 };
@@ -299,7 +300,13 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
         uint64_t t_ub = (uint64_t)(N + kMergeTile - 1) / kMergeTile + pairs;
         uint64_t b_ub = t_ub + pairs;
         k_merge_partition<<<(uint32_t)((b_ub + 127) / 128), 128, 0, s>>>(p, l, src);
-        k_merge<<<(uint32_t)t_ub, kMergeThreads, 0, s>>>(p, l, src, dst);
+        if (e->merge_variant == 0) {
+            k_merge<<<(uint32_t)t_ub, kMergeThreads, 0, s>>>(p, l, src, dst);
+        } else { // persistent, cp.async double-buffered
+            uint64_t grid = (uint64_t)e->sm_count * 3;
+            if (grid > t_ub) grid = t_ub;
+            k_merge_pipe<<<(uint32_t)grid, kMergeThreads, 2 * kMergeBufRecs * sizeof(Rec), s>>>(p, l, src, dst);
+        }
         launches += 2;
         const Rec *t = src;
         src = dst;
@@ -327,6 +334,8 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
             k_gather_warp<<<(uint32_t)((gather_tiles + wpb - 1) / wpb), kGatherWarpThreads, 0, s>>>(p);
         } else if (e->gather_variant == 0) {
             k_gather<<<(uint32_t)gather_tiles, kGatherThreads, 0, s>>>(p);
+        } else if (e->gather_variant == 3) {
+            k_gather_hybrid<<<(uint32_t)gather_tiles, kGatherThreads, 0, s>>>(p);
         } else { // persistent, warp-specialized
             uint64_t grid = (uint64_t)e->sm_count * e->gather_ctas_per_sm;
             if (grid > gather_tiles) grid = gather_tiles;
@@ -486,6 +495,11 @@ int dbeel_engine_create(int device, dbeel_engine **out) {
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
     if (const char *v = getenv("DBEEL_GATHER")) e->gather_variant = atoi(v);
+    if (const char *v = getenv("DBEEL_MERGE")) e->merge_variant = atoi(v);
+    if (cudaFuncSetAttribute(k_merge_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kMergeBufRecs * sizeof(Rec))) != cudaSuccess) {
+        dbeel_engine_destroy(e);
+        return DBEEL_ERR_CUDA;
+    }
     if (const char *v = getenv("DBEEL_BLOOM_IN_EMIT")) e->bloom_in_emit = atoi(v);
     if (const char *v = getenv("DBEEL_GATHER_CTAS")) e->gather_ctas_per_sm = atoi(v) > 0 ? atoi(v) : 4;
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return DBEEL_ERR_CUDA; }

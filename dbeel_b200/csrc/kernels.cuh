@@ -580,6 +580,110 @@ __global__ void __launch_bounds__(kMergeThreads, 4) k_merge(Params p, uint32_t l
 }
 
 // ------------------------------------------------------------------------------------
+// K3 (pipelined variant): persistent CTAs, each walking merge tiles blockIdx, blockIdx+grid, ...
+// with the NEXT tile's records streaming into the other shared-memory buffer (cp.async, 16 B
+// per request) while the current tile is searched and merged, and the tile after that having
+// its split points looked up -- so neither HBM nor L2 latency sits on the critical path.
+
+struct MergeDesc {
+    uint32_t a_src, n_a, b_src, n_b, dst; // record offsets into src / dst, counts
+};
+
+__device__ __forceinline__ MergeDesc merge_desc(const Params &p, uint32_t level, uint32_t tile) {
+    const uint32_t pairs = p.nseg[level + 1];
+    const uint32_t *tb = p.tile_base[level];
+    MergeDesc d;
+    d.a_src = d.n_a = d.b_src = d.n_b = d.dst = 0;
+    if (tile >= tb[pairs]) return d;
+    const uint32_t j = find_pair(tb, pairs, tile, 0);
+    const uint32_t t = tile - tb[j];
+    const Seg a = p.seg[level][2 * j];
+    Seg b;
+    b.start = 0; b.len = 0;
+    if (2 * j + 1 < p.nseg[level]) b = p.seg[level][2 * j + 1];
+    const uint32_t pidx = tb[j] + j + t;
+    const uint32_t a0 = p.part[pidx], a1 = p.part[pidx + 1];
+    const uint32_t total = a.len + b.len;
+    const uint32_t diag0 = t * kMergeTile;
+    const uint32_t diag1 = diag0 + kMergeTile < total ? diag0 + kMergeTile : total;
+    d.a_src = a.start + a0;
+    d.n_a = a1 - a0;
+    d.b_src = b.start + (diag0 - a0);
+    d.n_b = (diag1 - a1) - (diag0 - a0);
+    d.dst = a.start + diag0;
+    return d;
+}
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+
+constexpr int kMergeBufRecs = kMergeTile + kMergeVT + 1;
+
+__global__ void __launch_bounds__(kMergeThreads, 3) k_merge_pipe(Params p, uint32_t level, const Rec *src, Rec *dst) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    Rec *bufs[2] = {reinterpret_cast<Rec *>(s_raw), reinterpret_cast<Rec *>(s_raw) + kMergeBufRecs};
+    const uint32_t tid = threadIdx.x;
+    const uint32_t skip = p.ctl->prefix_len + kWindowBytes;
+    const uint32_t n_tiles = p.tile_base[level][p.nseg[level + 1]];
+    const uint32_t G = gridDim.x;
+    uint32_t tile = blockIdx.x;
+    if (tile >= n_tiles) return;
+
+    auto issue = [&](const MergeDesc &d, Rec *buf) {
+        for (uint32_t i = tid; i < d.n_a; i += kMergeThreads) cp_async16(&buf[i], &src[d.a_src + i]);
+        for (uint32_t i = tid; i < d.n_b; i += kMergeThreads) cp_async16(&buf[d.n_a + i], &src[d.b_src + i]);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    MergeDesc cur = merge_desc(p, level, tile);
+    MergeDesc nxt = merge_desc(p, level, tile + G);
+    issue(cur, bufs[0]);
+    for (uint32_t q = 0;; q++) {
+        Rec *s = bufs[q & 1];
+        const bool has_next = tile + G < n_tiles;
+        if (has_next) issue(nxt, bufs[(q + 1) & 1]);
+        const MergeDesc nn = merge_desc(p, level, tile + 2 * G); // consumed one iteration from now
+        if (has_next) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+
+        const uint32_t nA = cur.n_a, nB = cur.n_b, n = nA + nB;
+        uint32_t d = tid * kMergeVT;
+        if (d > n) d = n;
+        uint32_t lo = d > nB ? d - nB : 0;
+        uint32_t hi = d < nA ? d : nA;
+        while (lo < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (!key_less(p, skip, s[nA + d - 1 - mid], s[mid])) lo = mid + 1; else hi = mid;
+        }
+        uint32_t ai = lo, bi = d - lo;
+        Rec ak = s[ai], bk = s[nA + bi];
+        Rec out[kMergeVT];
+#pragma unroll
+        for (int i = 0; i < kMergeVT; i++) {
+            bool has_a = ai < nA, has_b = bi < nB;
+            bool take_b = has_b && (!has_a || key_less(p, skip, bk, ak));
+            out[i] = take_b ? bk : ak;
+            if (take_b) { bi++; bk = s[nA + bi]; } else { ai++; ak = s[ai]; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kMergeVT; i++)
+            if (d + i < n) s[d + i] = out[i];
+        __syncthreads();
+        Rec *o = dst + cur.dst;
+        for (uint32_t i = tid; i < n; i += kMergeThreads) st_rec(&o[i], s[i]);
+        __syncthreads(); // buffer q&1 is free again: the tile after next streams into it
+        if (!has_next) break;
+        tile += G;
+        cur = nxt;
+        nxt = nn;
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // K4a: resolve.  One thread per merged record, no ordering between CTAs.
 //
 // A record that starts a group of equal keys ("head") picks the group's winner -- the entry
@@ -1339,6 +1443,138 @@ __global__ void __launch_bounds__(kGatherWarpThreads) k_gather_warp(Params p) {
         } else { // ragged end of the whole stream: never write past out_data_len
             const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
             for (uint32_t b = 0; b < t; b++) dst_tile[b0 + b] = (uint8_t)(ow[b >> 2] >> ((b & 3) * 8));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K5 (hybrid variant): 16 KB CTA tiles like k_gather -- one staging pass, ONE block barrier,
+// dense (thread-per-entry) straddle and bloom passes -- but the copy itself is done warp by
+// warp on 2 KB sub-tiles with no mark/scan phase: a warp finds the entry under its first byte
+// with one binary search and then walks the (sorted) entry ends incrementally, 512 bytes at a
+// time, each lane counting how many entries end at or before its own vector.
+
+__global__ void __launch_bounds__(kGatherThreads) k_gather_hybrid(Params p) {
+    constexpr int NT = kGatherThreads;
+    constexpr int VPT = kGatherVecsPerThread;
+    __shared__ unsigned long long s_adj[kGatherMaxEntries]; // entry address minus its tile-relative start
+    __shared__ int s_r0[kGatherMaxEntries], s_r1[kGatherMaxEntries];
+    __shared__ uint32_t s_ks[kGatherMaxEntries];
+    const Ctl *c = p.ctl;
+    const unsigned long long out_len = c->out_data_len;
+    const unsigned long long T0 = (unsigned long long)blockIdx.x * kGatherTileBytes;
+    if (T0 >= out_len) return;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tile_len = out_len - T0 < kGatherTileBytes ? (uint32_t)(out_len - T0) : (uint32_t)kGatherTileBytes;
+    const uint32_t e_lo = p.tile_first[blockIdx.x];
+    const uint32_t e_hi = T0 + kGatherTileBytes < out_len ? p.tile_first[blockIdx.x + 1] : c->out_items - 1;
+    const uint32_t ne = e_hi - e_lo + 1; // <= kGatherMaxEntries: every entry is >= 32 bytes
+    for (uint32_t j = tid; j < ne; j += NT) {
+        const uint4 rec = p.out_index[e_lo + j];
+        const unsigned long long d0 = (unsigned long long)rec.x | ((unsigned long long)rec.y << 32);
+        const long long r0 = (long long)d0 - (long long)T0; // < 0 only for the tile's first entry
+        const long long r1 = r0 + (long long)rec.w;
+        s_adj[j] = p.src_ptr[e_lo + j] - (unsigned long long)r0;
+        s_r0[j] = r0 < -0x7FFFFFFFll ? -0x7FFFFFFF : (int)r0;
+        s_r1[j] = r1 > 0x7FFFFFFFll ? 0x7FFFFFFF : (int)r1;
+        s_ks[j] = rec.z;
+    }
+    __syncthreads();
+
+    // ---- copy: warp w owns bytes [w * 2 KB, (w + 1) * 2 KB) of the tile
+    uint8_t *dst_tile = p.out_data + T0;
+    const int sub0 = (int)(warp * (uint32_t)(32 * VPT * 16));
+    if ((uint32_t)sub0 < tile_len) {
+        uint32_t j; // the entry that holds byte sub0: first entry ending after it (ends ascend)
+        {
+            uint32_t lo = 0, hi = ne - 1;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (s_r1[mid] <= sub0) lo = mid + 1; else hi = mid;
+            }
+            j = lo;
+        }
+        uint4 A[VPT], B[VPT];
+        uint32_t sh[VPT];
+        bool pure[VPT];
+#pragma unroll
+        for (int k = 0; k < VPT; k++) {
+            const int cb = sub0 + k * 512; // this 512-byte chunk: one vector per lane
+            const int b0 = cb + (int)lane * 16;
+            uint32_t cnt = 0, i = j;
+            while (i + 1 < ne && s_r1[i] <= cb + 512) { // entries that end inside the chunk (warp-uniform loop)
+                cnt += s_r1[i] <= b0 ? 1u : 0u;
+                i++;
+            }
+            const uint32_t e = j + cnt; // entry that holds byte b0
+            j = i;                      // entry that holds the next chunk's first byte
+            pure[k] = false;
+            sh[k] = 0;
+            if ((uint32_t)b0 + 16 <= tile_len && b0 + 16 <= s_r1[e]) {
+                const uintptr_t sa = (uintptr_t)(s_adj[e] + (unsigned long long)b0);
+                sh[k] = (uint32_t)(sa & 15);
+                const uint4 *sv = reinterpret_cast<const uint4 *>(sa - sh[k]);
+                A[k] = __ldg(sv);
+                B[k] = __ldg(sh[k] ? sv + 1 : sv);
+                pure[k] = true;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < VPT; k++) {
+            const uint32_t v = (uint32_t)(sub0 >> 4) + (uint32_t)k * 32 + lane;
+            if (pure[k]) reinterpret_cast<uint4 *>(dst_tile)[v] = realign16_sel(A[k], B[k], sh[k]);
+        }
+    }
+
+    // ---- the vector that holds the last byte of entry j: tail of j blended with the head of j+1
+    for (uint32_t j = tid; j < ne; j += NT) {
+        const int r1 = s_r1[j];
+        if (r1 <= 0 || (r1 & 15) == 0 || r1 > (int)tile_len) continue;
+        const uint32_t v = (uint32_t)r1 >> 4;
+        const uint32_t b0 = v * 16;
+        const uint32_t t = (uint32_t)r1 - b0; // tail bytes of entry j in this vector: 1..15
+        const uintptr_t sa = (uintptr_t)(s_adj[j] + b0);
+        const uint32_t s0 = (uint32_t)(sa & 15);
+        const uint4 *sv = reinterpret_cast<const uint4 *>(sa - s0);
+        const uint4 TA = __ldg(sv);
+        const uint4 TB = __ldg(s0 + t > 16 ? sv + 1 : sv);
+        uint4 o = realign16_sel(TA, TB, s0);
+        if (b0 + 16 <= tile_len) {
+            const uintptr_t ha = (uintptr_t)(s_adj[j + 1] + (unsigned long long)(long long)s_r0[j + 1]); // first byte of entry j+1
+            const uint32_t hs = (uint32_t)(ha & 15);
+            const uint4 *hv = reinterpret_cast<const uint4 *>(ha - hs);
+            const uint4 HA = __ldg(hv);
+            const uint4 HB = __ldg(hs ? hv + 1 : hv);
+            const uint4 H = realign16_sel(HA, HB, hs);
+            const uint4 HU = realign16_sel(make_uint4(0, 0, 0, 0), H, 16 - t);
+            const uint32_t wfull = t >> 2, bits = (t & 3) * 8;
+            const uint32_t mmix = bits ? (0xFFFFFFFFu >> (32 - bits)) : 0u;
+            uint32_t ow[4] = {o.x, o.y, o.z, o.w}, hw[4] = {HU.x, HU.y, HU.z, HU.w};
+#pragma unroll
+            for (uint32_t q = 0; q < 4; q++) {
+                const uint32_t mk = q < wfull ? 0xFFFFFFFFu : (q == wfull ? mmix : 0u);
+                ow[q] = (ow[q] & mk) | (hw[q] & ~mk);
+            }
+            reinterpret_cast<uint4 *>(dst_tile)[v] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        } else { // ragged end of the whole stream: never write past out_data_len
+            const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+            for (uint32_t b = 0; b < t; b++) dst_tile[b0 + b] = (uint8_t)(ow[b >> 2] >> ((b & 3) * 8));
+        }
+    }
+
+    // ---- bloom (fused epilogue): entries whose first byte lies in this tile
+    if (p.bloom.words != nullptr && !p.bloom_in_emit) {
+        for (uint32_t j = tid; j < ne; j += NT) {
+            const int r0 = s_r0[j];
+            if (r0 < 0 || r0 >= (int)kGatherTileBytes) continue;
+            const uint8_t *key = reinterpret_cast<const uint8_t *>((uintptr_t)(s_adj[j] + (unsigned long long)r0)) + 8;
+            const uint64_t klen = s_ks[j] - 8;
+            uint64_t h0, h1;
+            sip13_pair_vec_u8(p.bloom.sip, klen, [key](uint64_t q) { return ld_u64_unaligned(key + 8 * q); }, &h0, &h1);
+            for (uint32_t k = 0; k < p.bloom.k_num; k++) {
+                uint64_t bit = fastmod(bloom_hash_i(h0, h1, k), p.bloom.bits, p.bloom.bits_magic);
+                atomicOr(&p.bloom.words[bit >> 5], 1u << (bit & 31));
+            }
         }
     }
 }
