@@ -46,7 +46,7 @@ struct dbeel_engine {
     bool busy = false;
     int sm_count = 148;
     int gather_variant = 3;     // DBEEL_GATHER: 0 = one CTA per 16 KB tile, 1 = persistent warp-specialized, 2 = one warp per 2 KB tile, 3 = 16 KB CTA tile + warp sub-tiles
-    int merge_variant = 1;      // DBEEL_MERGE: 0 = one CTA per tile, 1 = persistent + cp.async double buffering
+    int merge_variant = 0;      // DBEEL_MERGE: 0 = one CTA per tile, 1 = persistent + cp.async double buffering
     int bloom_in_emit = 0;      // DBEEL_BLOOM_IN_EMIT (variants 0/1; variant 2 always hashes in k_emit)
     int gather_ctas_per_sm = 4; // DBEEL_GATHER_CTAS
 };

@@ -1485,29 +1485,33 @@ __global__ void __launch_bounds__(kGatherThreads) k_gather_hybrid(Params p) {
     uint8_t *dst_tile = p.out_data + T0;
     const int sub0 = (int)(warp * (uint32_t)(32 * VPT * 16));
     if ((uint32_t)sub0 < tile_len) {
-        uint32_t j; // the entry that holds byte sub0: first entry ending after it (ends ascend)
-        {
-            uint32_t lo = 0, hi = ne - 1;
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (s_r1[mid] <= sub0) lo = mid + 1; else hi = mid;
-            }
-            j = lo;
+        // j = the entry that holds byte sub0 = number of entries ending at or before it (ends ascend).
+        // Ballot-count 32 entries at a time; the last entry never counts (it ends after every tile byte).
+        uint32_t j = 0;
+        for (uint32_t base = 0; base + 1 < ne; base += 32) {
+            const uint32_t i = base + lane;
+            j += __popc(__ballot_sync(0xFFFFFFFFu, i + 1 < ne && s_r1[i] <= sub0));
         }
         uint4 A[VPT], B[VPT];
         uint32_t sh[VPT];
         bool pure[VPT];
+        const uint32_t lanes_le = 0xFFFFFFFFu >> (31 - lane); // bits 0..lane
 #pragma unroll
         for (int k = 0; k < VPT; k++) {
             const int cb = sub0 + k * 512; // this 512-byte chunk: one vector per lane
             const int b0 = cb + (int)lane * 16;
-            uint32_t cnt = 0, i = j;
-            while (i + 1 < ne && s_r1[i] <= cb + 512) { // entries that end inside the chunk (warp-uniform loop)
-                cnt += s_r1[i] <= b0 ? 1u : 0u;
-                i++;
-            }
+            // Entries that end inside the chunk, i.e. in (cb, cb + 512]: at most 17 (entries are >= 32 bytes),
+            // lane l looks at entry j + l.  An end at r1 precedes the vectors t = ceil((r1 - cb) / 16) .. 31,
+            // and distinct entries have distinct t, so one OR-reduction builds the whole chunk's map.
+            const uint32_t i = j + lane;
+            const int r1 = i + 1 < ne ? s_r1[i] : 0x7FFFFFFF;
+            const bool ends_here = r1 <= cb + 512;
+            const uint32_t t = (uint32_t)((ends_here ? r1 : cb + 16) - cb + 15) >> 4; // 1..32 when ends_here
+            const uint32_t ends = __reduce_or_sync(0xFFFFFFFFu, (ends_here && t < 32) ? (1u << t) : 0u);
+            const uint32_t cnt = __popc(ends & lanes_le); // entries ending at or before my vector's first byte
+            const uint32_t adv = __popc(__ballot_sync(0xFFFFFFFFu, ends_here));
             const uint32_t e = j + cnt; // entry that holds byte b0
-            j = i;                      // entry that holds the next chunk's first byte
+            j += adv;                   // entry that holds the next chunk's first byte
             pure[k] = false;
             sh[k] = 0;
             if ((uint32_t)b0 + 16 <= tile_len && b0 + 16 <= s_r1[e]) {
