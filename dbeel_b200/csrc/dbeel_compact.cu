@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <new>
 #include <string>
 #include <vector>
@@ -38,6 +39,14 @@ struct dbeel_engine {
     // device staging for the host entry points (grow-only)
     uint8_t *stage_in = nullptr, *stage_out = nullptr;
     uint64_t stage_in_cap = 0, stage_out_cap = 0;
+    // pipelined host path: second staging pair, copy streams, shared bloom buffer
+    uint8_t *stage_in2 = nullptr, *stage_out2 = nullptr, *bloom_dev = nullptr;
+    uint64_t stage_in2_cap = 0, stage_out2_cap = 0, bloom_dev_cap = 0;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h2d[2] = {}, ev_comp[2] = {}, ev_d2h[2] = {};
+    int pipeline = 1;                   // DBEEL_PIPELINE: 0 = single-shot host path
+    uint64_t pipeline_min_bytes = 64ull << 20;
+    uint64_t partition_bytes = 128ull << 20; // DBEEL_PARTITION_MB
     // pinned host block: job header going down, control block coming back
     uint8_t *pin = nullptr;
     uint64_t pin_cap = 0;
@@ -129,11 +138,20 @@ int shape_of(const dbeel_run *runs, uint32_t n_runs, const dbeel_compact_opts *o
     return DBEEL_OK;
 }
 
+// Set when a job is one key-range partition of a larger compaction (host entry point, section "pipelined").
+struct JobExtra {
+    const uint64_t *off_base = nullptr; // [n_runs] .data offset of each run slice's first byte; data pointers are pre-biased
+    uint64_t out_offset_base = 0;       // .data bytes the earlier partitions wrote
+    bool external_bloom = false;        // the filter belongs to the whole compaction: set bits only
+    BloomParams bloom = {};
+};
+
 // The whole device-resident job.  `runs` / `out` hold device pointers.
 int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, const dbeel_compact_opts *o,
-                   bool flush, dbeel_out *out, bool record_start) {
+                   bool flush, dbeel_out *out, bool record_start, const JobExtra *extra = nullptr) {
     JobShape sh;
     shape_of(runs, n_runs, o, flush, &sh);
+    if (extra && extra->external_bloom) sh.bloom_file = 0;
     if (n_runs > DBEEL_MAX_RUNS) return fail(e, DBEEL_ERR_TOO_MANY_RUNS, "too many runs");
     if (sh.n_total >= 0xFFFFFFFEull) return fail(e, DBEEL_ERR_TOO_MANY_ENTRIES, "too many entries");
     if (out->data_cap < sh.data_total || out->index_cap < sh.n_total * 16 || out->bloom_cap < sh.bloom_file)
@@ -141,7 +159,7 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     for (uint32_t r = 0; r < n_runs; r++) {
         if ((runs[r].data_len && !runs[r].data) || (runs[r].index_len >= 16 && !runs[r].index))
             return fail(e, DBEEL_ERR_INVALID_ARG, "null run buffer");
-        if (((uintptr_t)runs[r].data | (uintptr_t)runs[r].index) & 15)
+        if ((((uintptr_t)runs[r].data & 15) && !(extra && extra->off_base)) || ((uintptr_t)runs[r].index & 15))
             return fail(e, DBEEL_ERR_INVALID_ARG, "device run buffers must be 16-byte aligned");
     }
     if (((uintptr_t)out->data | (uintptr_t)out->index | (uintptr_t)out->bloom) & 15)
@@ -234,7 +252,8 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     uint32_t base = 0;
     for (uint32_t r = 0; r < n_runs; r++) {
         hr[r].data = static_cast<const uint8_t *>(runs[r].data);
-        hr[r].data_len = runs[r].data_len;
+        hr[r].off_base = extra && extra->off_base ? extra->off_base[r] : 0;
+        hr[r].data_len = hr[r].off_base + runs[r].data_len;
         hr[r].index = static_cast<const uint4 *>(runs[r].index);
         hr[r].n_in = (uint32_t)(runs[r].index_len / DBEEL_INDEX_ENTRY_SIZE);
         hr[r].base = base;
@@ -261,6 +280,10 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
         p.bloom.bits_magic = (uint64_t)((((unsigned __int128)1) << 64) / sh.bloom_bits);
         p.bloom.k_num = sh.bloom_k;
         for (int i = 0; i < 4; i++) memcpy(&p.bloom.sip[i], seed + 8 * i, 8);
+    }
+    if (extra) {
+        p.out_offset_base = extra->out_offset_base;
+        if (extra->external_bloom) p.bloom = extra->bloom;
     }
 
     cudaStream_t s = e->stream;
@@ -374,6 +397,285 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     return DBEEL_OK;
 }
 
+// ------------------------------------------------------------------------------------
+// Pipelined host entry point.  A compaction whose inputs live in host memory is PCIe-bound
+// (~45 ms in + ~36 ms out vs ~2 ms of kernels for 2.5 GB), so the job is cut into key-range
+// partitions: partition i's slices of every run go down on one stream while partition i-1 is
+// merged and partition i-2's output goes up on a third -- both PCIe directions stay busy.
+// Every key lives in exactly one partition (all runs are cut at the same splitter keys with
+// lower_bound), partitions are emitted in key order, .index offsets continue across partitions
+// (out_offset_base) and all partitions set bits in one shared bloom filter sized for the whole
+// compaction, so the output files are byte-identical to the single-shot path.
+
+constexpr int kFallbackSingleShot = -1000; // internal: inputs need the single-shot path (corrupt / odd)
+
+struct HostRun {
+    const uint8_t *data;
+    uint64_t data_len;
+    const uint8_t *index;
+    uint64_t n;
+};
+
+struct HostRec {
+    uint64_t off;
+    uint32_t ks, fs;
+};
+
+inline bool host_rec(const HostRun &r, uint64_t i, HostRec *out) {
+    const uint8_t *p = r.index + 16 * i;
+    memcpy(&out->off, p, 8);
+    memcpy(&out->ks, p + 8, 4);
+    memcpy(&out->fs, p + 12, 4);
+    return out->ks >= 8 && (uint64_t)out->fs >= (uint64_t)out->ks + 24 && out->off <= r.data_len &&
+           (uint64_t)out->fs <= r.data_len - out->off;
+}
+
+inline int host_key_cmp(const uint8_t *a, uint32_t al, const uint8_t *b, uint32_t bl) {
+    const uint32_t m = al < bl ? al : bl;
+    const int c = m ? memcmp(a, b, m) : 0;
+    if (c) return c;
+    return (al > bl) - (al < bl);
+}
+
+struct Splitter {
+    const uint8_t *key;
+    uint32_t klen;
+    uint64_t weight;
+};
+
+int run_job_host_pipelined(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, const dbeel_compact_opts *o,
+                           dbeel_out *out, const JobShape &sh) {
+    // ---- 1. splitters from weighted samples of every run
+    std::vector<HostRun> hr(n_runs);
+    for (uint32_t r = 0; r < n_runs; r++)
+        hr[r] = HostRun{static_cast<const uint8_t *>(runs[r].data), runs[r].data_len,
+                        static_cast<const uint8_t *>(runs[r].index), runs[r].index_len / DBEEL_INDEX_ENTRY_SIZE};
+    uint64_t P = (sh.data_total + sh.index_total + e->partition_bytes - 1) / e->partition_bytes;
+    if (P > 64) P = 64;
+    if (P < 2) return kFallbackSingleShot;
+    constexpr uint64_t kSamples = 256;
+    std::vector<Splitter> samples;
+    for (uint32_t r = 0; r < n_runs; r++) {
+        const uint64_t n = hr[r].n;
+        if (!n) continue;
+        const uint64_t cnt = n < kSamples ? n : kSamples;
+        for (uint64_t q = 0; q < cnt; q++) {
+            const uint64_t i = (2 * q + 1) * n / (2 * cnt);
+            HostRec rec;
+            if (!host_rec(hr[r], i, &rec)) return kFallbackSingleShot;
+            samples.push_back(Splitter{hr[r].data + rec.off + 8, rec.ks - 8, n / cnt + 1});
+        }
+    }
+    if (samples.empty()) return kFallbackSingleShot;
+    std::sort(samples.begin(), samples.end(), [](const Splitter &a, const Splitter &b) {
+        return host_key_cmp(a.key, a.klen, b.key, b.klen) < 0;
+    });
+    uint64_t wsum = 0;
+    for (auto &sm : samples) wsum += sm.weight;
+    std::vector<Splitter> cuts;
+    {
+        uint64_t acc = 0, next = 1;
+        for (auto &sm : samples) {
+            acc += sm.weight;
+            if (next < P && acc * P >= next * wsum) {
+                if (cuts.empty() || host_key_cmp(cuts.back().key, cuts.back().klen, sm.key, sm.klen) < 0) cuts.push_back(sm);
+                while (next < P && acc * P >= next * wsum) next++;
+            }
+        }
+    }
+    const uint32_t np = (uint32_t)cuts.size() + 1;
+    if (np < 2) return kFallbackSingleShot;
+
+    // ---- 2. cut every run at every splitter (lower_bound: equal keys of all runs land in the same partition)
+    std::vector<std::vector<uint64_t>> lo(n_runs, std::vector<uint64_t>(np + 1, 0));
+    std::vector<std::vector<uint64_t>> boff(n_runs, std::vector<uint64_t>(np + 1, 0)); // .data offset at each cut
+    for (uint32_t r = 0; r < n_runs; r++) {
+        const uint64_t n = hr[r].n;
+        lo[r][np] = n;
+        for (uint32_t c = 0; c < np - 1; c++) {
+            uint64_t a = c ? lo[r][c] : 0, b = n;
+            while (a < b) {
+                const uint64_t mid = (a + b) >> 1;
+                HostRec rec;
+                if (!host_rec(hr[r], mid, &rec)) return kFallbackSingleShot;
+                if (host_key_cmp(hr[r].data + rec.off + 8, rec.ks - 8, cuts[c].key, cuts[c].klen) < 0) a = mid + 1; else b = mid;
+            }
+            lo[r][c + 1] = a;
+        }
+        uint64_t end = 0;
+        if (n) {
+            HostRec last;
+            if (!host_rec(hr[r], n - 1, &last)) return kFallbackSingleShot;
+            end = last.off + last.fs;
+        }
+        for (uint32_t c = 0; c <= np; c++) {
+            const uint64_t i = lo[r][c];
+            if (i >= n) { boff[r][c] = end; continue; }
+            HostRec rec;
+            if (!host_rec(hr[r], i, &rec)) return kFallbackSingleShot;
+            if (i) { // the offsets chain must hold across the cut (inside a slice the GPU checks it)
+                HostRec prev;
+                if (!host_rec(hr[r], i - 1, &prev) || prev.off + prev.fs != rec.off) return kFallbackSingleShot;
+            } else if (rec.off != 0) {
+                return kFallbackSingleShot;
+            }
+            boff[r][c] = rec.off;
+        }
+    }
+
+    // ---- 3. staging: two input and two output buffers sized for the largest partition
+    uint64_t max_in = 0, max_out = 0;
+    for (uint32_t c = 0; c < np; c++) {
+        uint64_t in = 0, d = 0, ix = 0;
+        for (uint32_t r = 0; r < n_runs; r++) {
+            const uint64_t dl = boff[r][c + 1] - boff[r][c], il = (lo[r][c + 1] - lo[r][c]) * 16;
+            in += align_up(dl + 32, kAlign) + align_up(il + 16, kAlign);
+            d += dl;
+            ix += il;
+        }
+        const uint64_t o2 = align_up(d + 16, kAlign) + align_up(ix + 16, kAlign);
+        max_in = in > max_in ? in : max_in;
+        max_out = o2 > max_out ? o2 : max_out;
+    }
+    int rc = ensure_device(e, &e->stage_in, &e->stage_in_cap, max_in);
+    if (!rc) rc = ensure_device(e, &e->stage_in2, &e->stage_in2_cap, max_in);
+    if (!rc) rc = ensure_device(e, &e->stage_out, &e->stage_out_cap, max_out);
+    if (!rc) rc = ensure_device(e, &e->stage_out2, &e->stage_out2_cap, max_out);
+    if (!rc && sh.bloom_file) rc = ensure_device(e, &e->bloom_dev, &e->bloom_dev_cap, sh.bloom_file + 16);
+    if (rc) return rc;
+    if (!e->s_h2d) {
+        CU(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CU(cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&e->ev_comp[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&e->ev_d2h[i], cudaEventDisableTiming));
+        }
+    }
+    uint8_t *sin[2] = {e->stage_in, e->stage_in2}, *sout[2] = {e->stage_out, e->stage_out2};
+
+    // ---- 4. the shared bloom filter
+    JobExtra ex;
+    ex.external_bloom = true;
+    if (sh.bloom_file) {
+        uint8_t seed[32];
+        if (o->bloom_seed) {
+            memcpy(seed, o->bloom_seed, 32);
+        } else {
+            FILE *f = fopen("/dev/urandom", "rb");
+            if (!f || fread(seed, 1, 32, f) != 32) {
+                if (f) fclose(f);
+                return fail(e, DBEEL_ERR_INVALID_ARG, "no entropy source for the bloom seed");
+            }
+            fclose(f);
+        }
+        ex.bloom.words = reinterpret_cast<uint32_t *>(e->bloom_dev + 8);
+        ex.bloom.bits = sh.bloom_bits;
+        ex.bloom.bits_magic = (uint64_t)((((unsigned __int128)1) << 64) / sh.bloom_bits);
+        ex.bloom.k_num = sh.bloom_k;
+        for (int i = 0; i < 4; i++) memcpy(&ex.bloom.sip[i], seed + 8 * i, 8);
+        CU(cudaMemsetAsync(e->bloom_dev, 0, sh.bloom_file, e->stream));
+        k_bloom_frame<<<1, 1, 0, e->stream>>>(e->bloom_dev, sh.bloom_words, ex.bloom);
+    }
+
+    // ---- 5. the pipeline
+    std::vector<uint64_t> off_base(n_runs);
+    std::vector<dbeel_run> dr(n_runs);
+    auto enqueue_h2d = [&](uint32_t c) -> int {
+        uint8_t *base = sin[c & 1];
+        uint64_t pos = 0;
+        for (uint32_t r = 0; r < n_runs; r++) {
+            const uint64_t dl = boff[r][c + 1] - boff[r][c], il = (lo[r][c + 1] - lo[r][c]) * 16;
+            if (dl) CU(cudaMemcpyAsync(base + pos, hr[r].data + boff[r][c], dl, cudaMemcpyHostToDevice, e->s_h2d));
+            pos += align_up(dl + 32, kAlign);
+            if (il) CU(cudaMemcpyAsync(base + pos, hr[r].index + 16 * lo[r][c], il, cudaMemcpyHostToDevice, e->s_h2d));
+            pos += align_up(il + 16, kAlign);
+        }
+        CU(cudaEventRecord(e->ev_h2d[c & 1], e->s_h2d));
+        return DBEEL_OK;
+    };
+    dbeel_stats total = {};
+    total.input_bytes = sh.data_total + sh.index_total;
+    total.entries_in = sh.n_total;
+    uint64_t out_data = 0, out_items = 0;
+    uint8_t *h_data = static_cast<uint8_t *>(out->data), *h_index = static_cast<uint8_t *>(out->index);
+    CU(cudaEventRecord(e->ev[EV_H2D0], e->stream));
+    rc = enqueue_h2d(0);
+    if (!rc && np > 1) rc = enqueue_h2d(1);
+    if (rc) return rc;
+    bool truncated = false;
+    for (uint32_t c = 0; c < np; c++) {
+        uint8_t *base = sin[c & 1];
+        uint64_t pos = 0, dsum = 0, isum = 0;
+        for (uint32_t r = 0; r < n_runs; r++) {
+            const uint64_t dl = boff[r][c + 1] - boff[r][c], il = (lo[r][c + 1] - lo[r][c]) * 16;
+            off_base[r] = boff[r][c];
+            dr[r].data = base + pos - boff[r][c]; // biased: .data offset `off` lives at data + off
+            dr[r].data_len = dl;
+            pos += align_up(dl + 32, kAlign);
+            dr[r].index = base + pos;
+            dr[r].index_len = il;
+            pos += align_up(il + 16, kAlign);
+            dsum += dl;
+            isum += il;
+        }
+        dbeel_out dout = {};
+        dout.data = sout[c & 1];
+        dout.data_cap = dsum;
+        dout.index = sout[c & 1] + align_up(dsum + 16, kAlign);
+        dout.index_cap = isum;
+        ex.off_base = off_base.data();
+        ex.out_offset_base = out_data;
+        CU(cudaStreamWaitEvent(e->stream, e->ev_h2d[c & 1], 0));
+        if (c >= 2) CU(cudaStreamWaitEvent(e->stream, e->ev_d2h[c & 1], 0)); // output buffer c&1 drained
+        rc = run_job_device(e, dr.data(), n_runs, o, false, &dout, /*record_start=*/true, &ex); // syncs e->stream
+        if (rc) break;
+        const dbeel_stats &ps = e->stats;
+        if (ps.runs_truncated) { truncated = true; break; }
+        total.entries_valid += ps.entries_valid;
+        total.kernel_launches += ps.kernel_launches;
+        total.merge_passes = ps.merge_passes > total.merge_passes ? ps.merge_passes : total.merge_passes;
+        total.key_prefix_len = ps.key_prefix_len;
+        total.ms_total += ps.ms_total;
+        total.ms_extract += ps.ms_extract;
+        total.ms_merge += ps.ms_merge;
+        total.ms_resolve += ps.ms_resolve;
+        total.ms_gather += ps.ms_gather;
+        total.gather_bytes += ps.gather_bytes;
+        CU(cudaEventRecord(e->ev_comp[c & 1], e->stream));
+        CU(cudaStreamWaitEvent(e->s_d2h, e->ev_comp[c & 1], 0));
+        if (dout.data_len) CU(cudaMemcpyAsync(h_data + out_data, dout.data, dout.data_len, cudaMemcpyDeviceToHost, e->s_d2h));
+        if (dout.index_len) CU(cudaMemcpyAsync(h_index + 16 * out_items, dout.index, dout.index_len, cudaMemcpyDeviceToHost, e->s_d2h));
+        CU(cudaEventRecord(e->ev_d2h[c & 1], e->s_d2h));
+        out_data += dout.data_len;
+        out_items += dout.items_written;
+        if (c + 2 < np) { // input buffer c&1 is free again (the job that read it has completed)
+            rc = enqueue_h2d(c + 2);
+            if (rc) break;
+        }
+    }
+    if (rc || truncated) { // drain, then report / fall back to the exact single-shot semantics
+        cudaStreamSynchronize(e->s_h2d);
+        cudaStreamSynchronize(e->s_d2h);
+        return rc ? rc : kFallbackSingleShot;
+    }
+    if (sh.bloom_file) {
+        CU(cudaStreamWaitEvent(e->s_d2h, e->ev_comp[(np - 1) & 1], 0));
+        CU(cudaMemcpyAsync(out->bloom, e->bloom_dev, sh.bloom_file, cudaMemcpyDeviceToHost, e->s_d2h));
+    }
+    CU(cudaStreamSynchronize(e->s_d2h));
+    CU(cudaStreamSynchronize(e->s_h2d));
+    out->data_len = out_data;
+    out->items_written = out_items;
+    out->index_len = out_items * 16;
+    out->bloom_len = sh.bloom_file;
+    total.entries_out = out_items;
+    total.output_bytes = out->data_len + out->index_len + out->bloom_len;
+    total.kernel_launches += sh.bloom_file ? 1 : 0;
+    e->stats = total;
+    return DBEEL_OK;
+}
+
 // host buffers in / out around run_job_device
 int run_job_host(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, const dbeel_compact_opts *o, bool flush,
                  dbeel_out *out) {
@@ -385,6 +687,12 @@ int run_job_host(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, const 
     for (uint32_t r = 0; r < n_runs; r++)
         if ((runs[r].data_len && !runs[r].data) || (runs[r].index_len && !runs[r].index))
             return fail(e, DBEEL_ERR_INVALID_ARG, "null run buffer");
+    if (e->pipeline && !flush && !(o->flags & DBEEL_FLAG_VERIFY_SORTED) && sh.n_total < 0xFFFFFFFEull &&
+        sh.data_total + sh.index_total >= e->pipeline_min_bytes) {
+        int prc = run_job_host_pipelined(e, runs, n_runs, o, out, sh);
+        if (prc != kFallbackSingleShot) return prc;
+        out->data_len = out->index_len = out->bloom_len = out->items_written = 0;
+    }
 
     // device staging: every buffer 256-aligned with 16 bytes of slack behind it
     uint64_t in_need = 0;
@@ -496,6 +804,10 @@ int dbeel_engine_create(int device, dbeel_engine **out) {
     e->sm_count = prop.multiProcessorCount;
     if (const char *v = getenv("DBEEL_GATHER")) e->gather_variant = atoi(v);
     if (const char *v = getenv("DBEEL_MERGE")) e->merge_variant = atoi(v);
+    if (const char *v = getenv("DBEEL_PIPELINE")) e->pipeline = atoi(v);
+    if (const char *v = getenv("DBEEL_PIPELINE_MIN_KB")) e->pipeline_min_bytes = (uint64_t)(atoi(v) > 0 ? atoi(v) : 1) << 10;
+    if (const char *v = getenv("DBEEL_PARTITION_KB")) e->partition_bytes = (uint64_t)(atoi(v) > 0 ? atoi(v) : 1) << 10;
+    if (const char *v = getenv("DBEEL_PARTITION_MB")) e->partition_bytes = (uint64_t)(atoi(v) > 0 ? atoi(v) : 128) << 20;
     if (cudaFuncSetAttribute(k_merge_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kMergeBufRecs * sizeof(Rec))) != cudaSuccess) {
         dbeel_engine_destroy(e);
         return DBEEL_ERR_CUDA;
@@ -518,6 +830,16 @@ void dbeel_engine_destroy(dbeel_engine *e) {
     if (e->ws) cudaFree(e->ws);
     if (e->stage_in) cudaFree(e->stage_in);
     if (e->stage_out) cudaFree(e->stage_out);
+    if (e->stage_in2) cudaFree(e->stage_in2);
+    if (e->stage_out2) cudaFree(e->stage_out2);
+    if (e->bloom_dev) cudaFree(e->bloom_dev);
+    for (int i = 0; i < 2; i++) {
+        if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]);
+        if (e->ev_comp[i]) cudaEventDestroy(e->ev_comp[i]);
+        if (e->ev_d2h[i]) cudaEventDestroy(e->ev_d2h[i]);
+    }
+    if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
+    if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
     if (e->pin) cudaFreeHost(e->pin);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;

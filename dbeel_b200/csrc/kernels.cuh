@@ -16,10 +16,11 @@ namespace dbeel {
 // device-side job description
 
 struct RunDesc {
-    const uint8_t *data;
-    uint64_t data_len;
+    const uint8_t *data; // address of .data byte 0 (biased by -off_base when only a slice of the file is resident)
+    uint64_t data_len;   // .data offsets below this bound are resident
+    uint64_t off_base;   // ... and at or above this one; the first record of the (slice of the) run starts here
     const uint4 *index;
-    uint32_t n_in; // index_len / 16
+    uint32_t n_in; // index records of the (slice of the) run
     uint32_t base; // gid of this run's first entry
 };
 
@@ -89,6 +90,7 @@ struct Params {
     uint32_t *tile_first;        // [ceil(data bytes / gather_tile_bytes) + 2] entry holding each gather tile's first byte
     unsigned long long gather_tile_bytes; // 16 KB (CTA tiles) or 2 KB (warp tiles)
     int bloom_in_emit;           // 1: k_emit sets the bloom bits; 0: the gather kernel does
+    unsigned long long out_offset_base; // .data bytes written by earlier key-range partitions of the same output file
     BloomParams bloom;
 };
 
@@ -185,7 +187,7 @@ __device__ __forceinline__ bool key_equal(const Params &p, uint32_t skip, const 
 __device__ __forceinline__ bool safe_key(const RunDesc &rd, uint32_t i, const uint8_t **ptr, uint32_t *klen) {
     uint4 rec = __ldg(&rd.index[i]);
     uint64_t off = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
-    if (rec.z < 8 || off > rd.data_len || (uint64_t)rec.z > rd.data_len - off) return false;
+    if (rec.z < 8 || off < rd.off_base || off > rd.data_len || (uint64_t)rec.z > rd.data_len - off) return false;
     *ptr = rd.data + off + 8;
     *klen = rec.z - 8;
     return true;
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(256, 4) k_extract(Params p, int redo) {
             off[u] = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
             ks[u] = rec.z;
             fs[u] = rec.w;
-            expect[u] = 0;
+            expect[u] = rd.off_base;
             if (i[u] && !redo) {
                 const uint4 pr = __ldg(&rd.index[i[u] - 1]);
                 expect[u] = ((uint64_t)pr.x | ((uint64_t)pr.y << 32)) + pr.w;
@@ -914,11 +916,12 @@ __global__ void __launch_bounds__(kResolveThreads) k_emit(Params p, const uint4 
     if (lane == 31) { s_wb[warp] = ib; s_wc[warp] = ic; }
     __syncthreads();
     if (!fs) return;
-    unsigned long long off = p.chunk_bytes[blockIdx.x >> 10] + p.tile_bytes[blockIdx.x] + ib - fs;
+    unsigned long long off = p.chunk_bytes[blockIdx.x >> 10] + p.tile_bytes[blockIdx.x] + ib - fs; // within this job's .data
     uint32_t pos = p.chunk_count[blockIdx.x >> 10] + p.tile_count[blockIdx.x] + ic - 1;
     for (uint32_t w = 0; w < warp; w++) { off += s_wb[w]; pos += s_wc[w]; }
     const unsigned long long src = (unsigned long long)it.x | ((unsigned long long)it.y << 32);
-    p.out_index[pos] = make_uint4((uint32_t)off, (uint32_t)(off >> 32), it.z, fs);
+    const unsigned long long file_off = off + p.out_offset_base; // a key-range partition continues the file of the previous ones
+    p.out_index[pos] = make_uint4((uint32_t)file_off, (uint32_t)(file_off >> 32), it.z, fs);
     p.src_ptr[pos] = src;
     // every gather tile whose first byte lies in [off, off + fs) starts inside this entry
     const unsigned long long tb = p.gather_tile_bytes;
@@ -994,7 +997,7 @@ __global__ void __launch_bounds__(kGatherThreads) k_gather(Params p) {
     __syncthreads();
     for (uint32_t j = tid; j < ne; j += NT) {
         uint4 rec = p.out_index[e_lo + j];
-        const unsigned long long d0 = (unsigned long long)rec.x | ((unsigned long long)rec.y << 32);
+        const unsigned long long d0 = ((unsigned long long)rec.x | ((unsigned long long)rec.y << 32)) - p.out_offset_base;
         const long long r0 = (long long)d0 - (long long)T0;
         const unsigned long long src = p.src_ptr[e_lo + j];
         s_r0[j] = r0;
@@ -1150,7 +1153,7 @@ __device__ __forceinline__ void gather_stage(const Params &p, GatherTileMeta &m,
                                              uint32_t ne, uint32_t tile_len, uint32_t t, uint32_t nt) {
     for (uint32_t j = t; j < ne; j += nt) {
         const uint4 rec = p.out_index[e_lo + j];
-        const unsigned long long d0 = (unsigned long long)rec.x | ((unsigned long long)rec.y << 32);
+        const unsigned long long d0 = ((unsigned long long)rec.x | ((unsigned long long)rec.y << 32)) - p.out_offset_base;
         const long long r0 = (long long)d0 - (long long)T0;
         const long long r1 = r0 + (long long)rec.w;
         m.adj[j] = p.src_ptr[e_lo + j] - (unsigned long long)r0;
@@ -1367,7 +1370,7 @@ __global__ void __launch_bounds__(kGatherWarpThreads) k_gather_warp(Params p) {
     int *r1s = s_r1[w], *r0s = s_r0[w];
     for (uint32_t j = lane; j < ne; j += 32) {
         const uint4 rec = p.out_index[e_lo + j];
-        const unsigned long long d0 = (unsigned long long)rec.x | ((unsigned long long)rec.y << 32);
+        const unsigned long long d0 = ((unsigned long long)rec.x | ((unsigned long long)rec.y << 32)) - p.out_offset_base;
         const long long r0 = (long long)d0 - (long long)T0; // < 0 only for the tile's first entry
         const long long r1 = r0 + (long long)rec.w;
         adj[j] = p.src_ptr[e_lo + j] - (unsigned long long)r0;
@@ -1471,7 +1474,7 @@ __global__ void __launch_bounds__(kGatherThreads) k_gather_hybrid(Params p) {
     const uint32_t ne = e_hi - e_lo + 1; // <= kGatherMaxEntries: every entry is >= 32 bytes
     for (uint32_t j = tid; j < ne; j += NT) {
         const uint4 rec = p.out_index[e_lo + j];
-        const unsigned long long d0 = (unsigned long long)rec.x | ((unsigned long long)rec.y << 32);
+        const unsigned long long d0 = ((unsigned long long)rec.x | ((unsigned long long)rec.y << 32)) - p.out_offset_base;
         const long long r0 = (long long)d0 - (long long)T0; // < 0 only for the tile's first entry
         const long long r1 = r0 + (long long)rec.w;
         s_adj[j] = p.src_ptr[e_lo + j] - (unsigned long long)r0;
