@@ -46,7 +46,7 @@ struct dbeel_engine {
     cudaEvent_t ev_h2d[2] = {}, ev_comp[2] = {}, ev_d2h[2] = {};
     int pipeline = 1;                   // DBEEL_PIPELINE: 0 = single-shot host path
     uint64_t pipeline_min_bytes = 64ull << 20;
-    uint64_t partition_bytes = 128ull << 20; // DBEEL_PARTITION_MB
+    uint64_t partition_bytes = 256ull << 20; // DBEEL_PARTITION_MB
     // pinned host block: job header going down, control block coming back
     uint8_t *pin = nullptr;
     uint64_t pin_cap = 0;
@@ -58,6 +58,7 @@ struct dbeel_engine {
     int merge_variant = 0;      // DBEEL_MERGE: 0 = one CTA per tile, 1 = persistent + cp.async double buffering
     int bloom_in_emit = 0;      // DBEEL_BLOOM_IN_EMIT (variants 0/1; variant 2 always hashes in k_emit)
     int gather_ctas_per_sm = 4; // DBEEL_GATHER_CTAS
+    int gather_tune = 5;        // DBEEL_GATHER_TUNE
 };
 
 namespace {
@@ -324,7 +325,9 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
         uint64_t b_ub = t_ub + pairs;
         k_merge_partition<<<(uint32_t)((b_ub + 127) / 128), 128, 0, s>>>(p, l, src);
         if (e->merge_variant == 0) {
-            k_merge<<<(uint32_t)t_ub, kMergeThreads, 0, s>>>(p, l, src, dst);
+            k_merge<false><<<(uint32_t)t_ub, kMergeThreads, 0, s>>>(p, l, src, dst);
+        } else if (e->merge_variant == 2) {
+            k_merge<true><<<(uint32_t)t_ub, kMergeThreads, 0, s>>>(p, l, src, dst);
         } else { // persistent, cp.async double-buffered
             uint64_t grid = (uint64_t)e->sm_count * 3;
             if (grid > t_ub) grid = t_ub;
@@ -358,7 +361,15 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
         } else if (e->gather_variant == 0) {
             k_gather<<<(uint32_t)gather_tiles, kGatherThreads, 0, s>>>(p);
         } else if (e->gather_variant == 3) {
-            k_gather_hybrid<<<(uint32_t)gather_tiles, kGatherThreads, 0, s>>>(p);
+            const uint32_t gt = (uint32_t)gather_tiles;
+            switch (e->gather_tune) { // DBEEL_GATHER_TUNE = 10 * map + min blocks per SM
+            case 4: k_gather_hybrid<0, 4><<<gt, kGatherThreads, 0, s>>>(p); break;
+            case 6: k_gather_hybrid<0, 6><<<gt, kGatherThreads, 0, s>>>(p); break;
+            case 14: k_gather_hybrid<1, 4><<<gt, kGatherThreads, 0, s>>>(p); break;
+            case 15: k_gather_hybrid<1, 5><<<gt, kGatherThreads, 0, s>>>(p); break;
+            case 16: k_gather_hybrid<1, 6><<<gt, kGatherThreads, 0, s>>>(p); break;
+            default: k_gather_hybrid<0, 5><<<gt, kGatherThreads, 0, s>>>(p); break;
+            }
         } else { // persistent, warp-specialized
             uint64_t grid = (uint64_t)e->sm_count * e->gather_ctas_per_sm;
             if (grid > gather_tiles) grid = gather_tiles;
@@ -813,6 +824,7 @@ int dbeel_engine_create(int device, dbeel_engine **out) {
         return DBEEL_ERR_CUDA;
     }
     if (const char *v = getenv("DBEEL_BLOOM_IN_EMIT")) e->bloom_in_emit = atoi(v);
+    if (const char *v = getenv("DBEEL_GATHER_TUNE")) e->gather_tune = atoi(v);
     if (const char *v = getenv("DBEEL_GATHER_CTAS")) e->gather_ctas_per_sm = atoi(v) > 0 ? atoi(v) : 4;
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return DBEEL_ERR_CUDA; }
     for (int i = 0; i < EV_COUNT; i++)

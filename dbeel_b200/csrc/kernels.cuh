@@ -528,6 +528,7 @@ __global__ void __launch_bounds__(128) k_merge_partition(Params p, uint32_t leve
     p.part[idx] = lo;
 }
 
+template <bool kDirectStore>
 __global__ void __launch_bounds__(kMergeThreads, 4) k_merge(Params p, uint32_t level, const Rec *src, Rec *dst) {
     __shared__ Rec s[kMergeTile + kMergeVT + 1];
     const uint32_t pairs = p.nseg[level + 1];
@@ -572,12 +573,20 @@ __global__ void __launch_bounds__(kMergeThreads, 4) k_merge(Params p, uint32_t l
         out[i] = take_b ? bk : ak;
         if (take_b) { bi++; bk = s[nA + bi]; } else { ai++; ak = s[ai]; }
     }
+    Rec *o = dst + a.start + diag0;
+    if (kDirectStore) {
+        // each thread owns 7 consecutive output records (112 contiguous bytes); a warp's stores cover one
+        // contiguous 3.5 KB span, so L2 sees every sector whole within a few instructions
+#pragma unroll
+        for (int i = 0; i < kMergeVT; i++)
+            if (d + i < n) st_rec(&o[d + i], out[i]);
+        return;
+    }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < kMergeVT; i++)
         if (d + i < n) s[d + i] = out[i];
     __syncthreads();
-    Rec *o = dst + a.start + diag0;
     for (uint32_t i = tid; i < n; i += kMergeThreads) st_rec(&o[i], s[i]);
 }
 
@@ -1457,7 +1466,8 @@ __global__ void __launch_bounds__(kGatherWarpThreads) k_gather_warp(Params p) {
 // with one binary search and then walks the (sorted) entry ends incrementally, 512 bytes at a
 // time, each lane counting how many entries end at or before its own vector.
 
-__global__ void __launch_bounds__(kGatherThreads) k_gather_hybrid(Params p) {
+template <int kMap, int kMinBlocks>
+__global__ void __launch_bounds__(kGatherThreads, kMinBlocks) k_gather_hybrid(Params p) {
     constexpr int NT = kGatherThreads;
     constexpr int VPT = kGatherVecsPerThread;
     __shared__ unsigned long long s_adj[kGatherMaxEntries]; // entry address minus its tile-relative start
@@ -1489,11 +1499,19 @@ __global__ void __launch_bounds__(kGatherThreads) k_gather_hybrid(Params p) {
     const int sub0 = (int)(warp * (uint32_t)(32 * VPT * 16));
     if ((uint32_t)sub0 < tile_len) {
         // j = the entry that holds byte sub0 = number of entries ending at or before it (ends ascend).
-        // Ballot-count 32 entries at a time; the last entry never counts (it ends after every tile byte).
         uint32_t j = 0;
-        for (uint32_t base = 0; base + 1 < ne; base += 32) {
-            const uint32_t i = base + lane;
-            j += __popc(__ballot_sync(0xFFFFFFFFu, i + 1 < ne && s_r1[i] <= sub0));
+        if (kMap == 1) { // ballot-count 32 entries at a time; the last entry never counts
+            for (uint32_t base = 0; base + 1 < ne; base += 32) {
+                const uint32_t i = base + lane;
+                j += __popc(__ballot_sync(0xFFFFFFFFu, i + 1 < ne && s_r1[i] <= sub0));
+            }
+        } else { // warp-uniform binary search
+            uint32_t lo = 0, hi = ne - 1;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (s_r1[mid] <= sub0) lo = mid + 1; else hi = mid;
+            }
+            j = lo;
         }
         uint4 A[VPT], B[VPT];
         uint32_t sh[VPT];
@@ -1503,16 +1521,27 @@ __global__ void __launch_bounds__(kGatherThreads) k_gather_hybrid(Params p) {
         for (int k = 0; k < VPT; k++) {
             const int cb = sub0 + k * 512; // this 512-byte chunk: one vector per lane
             const int b0 = cb + (int)lane * 16;
-            // Entries that end inside the chunk, i.e. in (cb, cb + 512]: at most 17 (entries are >= 32 bytes),
-            // lane l looks at entry j + l.  An end at r1 precedes the vectors t = ceil((r1 - cb) / 16) .. 31,
-            // and distinct entries have distinct t, so one OR-reduction builds the whole chunk's map.
-            const uint32_t i = j + lane;
-            const int r1 = i + 1 < ne ? s_r1[i] : 0x7FFFFFFF;
-            const bool ends_here = r1 <= cb + 512;
-            const uint32_t t = (uint32_t)((ends_here ? r1 : cb + 16) - cb + 15) >> 4; // 1..32 when ends_here
-            const uint32_t ends = __reduce_or_sync(0xFFFFFFFFu, (ends_here && t < 32) ? (1u << t) : 0u);
-            const uint32_t cnt = __popc(ends & lanes_le); // entries ending at or before my vector's first byte
-            const uint32_t adv = __popc(__ballot_sync(0xFFFFFFFFu, ends_here));
+            uint32_t cnt, adv;
+            if (kMap == 1) {
+                // Entries that end inside the chunk, i.e. in (cb, cb + 512]: at most 17 (entries are >= 32 bytes),
+                // lane l looks at entry j + l.  An end at r1 precedes the vectors t = ceil((r1 - cb) / 16) .. 31,
+                // and distinct entries have distinct t, so one OR-reduction builds the whole chunk's map.
+                const uint32_t i = j + lane;
+                const int r1 = i + 1 < ne ? s_r1[i] : 0x7FFFFFFF;
+                const bool ends_here = r1 <= cb + 512;
+                const uint32_t t = (uint32_t)((ends_here ? r1 : cb + 16) - cb + 15) >> 4; // 1..32 when ends_here
+                const uint32_t ends = __reduce_or_sync(0xFFFFFFFFu, (ends_here && t < 32) ? (1u << t) : 0u);
+                cnt = __popc(ends & lanes_le); // entries ending at or before my vector's first byte
+                adv = __popc(__ballot_sync(0xFFFFFFFFu, ends_here));
+            } else {
+                cnt = 0;
+                uint32_t i = j;
+                while (i + 1 < ne && s_r1[i] <= cb + 512) { // entries that end inside the chunk (warp-uniform loop)
+                    cnt += s_r1[i] <= b0 ? 1u : 0u;
+                    i++;
+                }
+                adv = i - j;
+            }
             const uint32_t e = j + cnt; // entry that holds byte b0
             j += adv;                   // entry that holds the next chunk's first byte
             pure[k] = false;
