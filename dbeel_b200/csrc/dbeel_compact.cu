@@ -58,7 +58,8 @@ struct dbeel_engine {
     int merge_variant = 0;      // DBEEL_MERGE: 0 = one CTA per tile, 1 = persistent + cp.async double buffering
     int bloom_in_emit = 0;      // DBEEL_BLOOM_IN_EMIT (variants 0/1; variant 2 always hashes in k_emit)
     int gather_ctas_per_sm = 4; // DBEEL_GATHER_CTAS
-    int gather_tune = 5;        // DBEEL_GATHER_TUNE
+    int gather_tune = 16;       // DBEEL_GATHER_TUNE
+    int narrow_loads = 0;       // DBEEL_NARROW: .L2::64B loads for random accesses in extract / resolve
 };
 
 namespace {
@@ -299,14 +300,14 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     if (flush) {
         k_flush_prefix_init<<<1, 1, 0, s>>>(p);
         k_flush_prefix<<<g256, 256, 0, s>>>(p);
-        k_extract<<<gext, 256, 0, s>>>(p, 0);
+        if (e->narrow_loads) k_extract<true><<<gext, 256, 0, s>>>(p, 0); else k_extract<false><<<gext, 256, 0, s>>>(p, 0);
         k_plan<<<1, 1, 0, s>>>(p);
         k_block_sort<<<p.nseg[0], kMergeThreads, 0, s>>>(p);
     } else {
         k_common_prefix<<<1, 32, 0, s>>>(p, 0);
-        k_extract<<<gext, 256, 0, s>>>(p, 0);
+        if (e->narrow_loads) k_extract<true><<<gext, 256, 0, s>>>(p, 0); else k_extract<false><<<gext, 256, 0, s>>>(p, 0);
         k_common_prefix<<<1, 32, 0, s>>>(p, 1); // both no-ops unless a run was truncated
-        k_extract<<<gext < 592 ? gext : 592, 256, 0, s>>>(p, 1);
+        k_extract<false><<<gext < 592 ? gext : 592, 256, 0, s>>>(p, 1);
         k_plan<<<1, 1, 0, s>>>(p);
     }
     launches += 5;
@@ -346,7 +347,8 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
         launches++;
     }
     uint4 *res = reinterpret_cast<uint4 *>(dst); // the ping-pong buffer that does not hold the merged order
-    k_resolve<<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, src, res);
+    if (e->narrow_loads) k_resolve<true><<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, src, res);
+    else k_resolve<false><<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, src, res);
     k_scan_tiles<<<(uint32_t)res_chunks, 1024, 0, s>>>(p);
     k_scan_chunks<<<1, 1024, 0, s>>>(p);
     k_emit<<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, res);
@@ -824,6 +826,7 @@ int dbeel_engine_create(int device, dbeel_engine **out) {
         return DBEEL_ERR_CUDA;
     }
     if (const char *v = getenv("DBEEL_BLOOM_IN_EMIT")) e->bloom_in_emit = atoi(v);
+    if (const char *v = getenv("DBEEL_NARROW")) e->narrow_loads = atoi(v);
     if (const char *v = getenv("DBEEL_GATHER_TUNE")) e->gather_tune = atoi(v);
     if (const char *v = getenv("DBEEL_GATHER_CTAS")) e->gather_ctas_per_sm = atoi(v) > 0 ? atoi(v) : 4;
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return DBEEL_ERR_CUDA; }

@@ -97,6 +97,29 @@ struct Params {
 // ------------------------------------------------------------------------------------
 // small load helpers
 
+// Loads for RANDOM accesses (entry headers, index records reached through a gid, timestamps): the
+// default L2 policy pulls a whole 128-byte line from HBM on a miss, four times what a 32-byte
+// header needs.  The .L2::64B qualifier caps the fetch at the 64-byte HBM access granule.
+__device__ __forceinline__ uint64_t ldg64_narrow(const uint64_t *q) {
+    uint64_t v;
+    asm volatile("ld.global.nc.L2::64B.u64 %0, [%1];" : "=l"(v) : "l"(q));
+    return v;
+}
+__device__ __forceinline__ uint4 ldg128_narrow(const uint4 *q) {
+    uint4 v;
+    asm volatile("ld.global.nc.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(q));
+    return v;
+}
+__device__ __forceinline__ uint64_t ld_u64_unaligned_narrow(const uint8_t *p) {
+    uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint64_t *q = reinterpret_cast<const uint64_t *>(a & ~uintptr_t(7));
+    uint32_t sh = (uint32_t)(a & 7) * 8;
+    uint64_t lo = ldg64_narrow(q);
+    if (sh == 0) return lo;
+    uint64_t hi = ldg64_narrow(q + 1);
+    return (lo >> sh) | (hi << (64 - sh));
+}
+
 __device__ __forceinline__ uint64_t ld_u64_unaligned(const uint8_t *p) {
     // two aligned 8-byte loads; the second is only issued when it holds needed bytes
     uintptr_t a = reinterpret_cast<uintptr_t>(p);
@@ -246,7 +269,9 @@ __global__ void k_common_prefix(Params p, int validated) {
 
 constexpr int kExtractEPT = 2; // entries per thread: two independent load chains in flight
 
+template <bool kNarrow>
 __global__ void __launch_bounds__(256, 4) k_extract(Params p, int redo) {
+    auto ldu = [](const uint8_t *q) { return kNarrow ? ld_u64_unaligned_narrow(q) : ld_u64_unaligned(q); };
     Ctl *c = p.ctl;
     if (redo && !(c->flags & kFlagTruncated)) return;
     const uint32_t L = c->prefix_len;
@@ -296,17 +321,17 @@ __global__ void __launch_bounds__(256, 4) k_extract(Params p, int redo) {
             klen_w[u] = dlen_w[u] = w0[u] = w1[u] = 0;
             if (ok[u]) {
                 const uint8_t *e = data[u] + off[u];
-                klen_w[u] = ld_u64_unaligned(e);
-                dlen_w[u] = ld_u64_unaligned(e + ks[u]);
+                klen_w[u] = ldu(e);
+                dlen_w[u] = ldu(e + ks[u]);
                 const uint32_t klen = ks[u] - 8;
                 match[u] = klen >= L;
                 if (match[u]) {
                     const uint8_t *key = e + 8;
                     // every load below stays inside the entry: >= 24 bytes (dlen + timestamp) follow the key
-                    w0[u] = ld_u64_unaligned(key + L);
-                    w1[u] = ld_u64_unaligned(key + L + 8);
+                    w0[u] = ldu(key + L);
+                    w1[u] = ldu(key + L + 8);
                     for (uint32_t q = 0; q < npw; q++) {
-                        const uint64_t kw = ld_u64_unaligned(key + 8 * q);
+                        const uint64_t kw = ldu(key + 8 * q);
                         const uint32_t nb = L - 8 * q; // prefix bytes in this word (>= 1)
                         const uint64_t mask = nb >= 8 ? ~0ull : ((1ull << (8 * nb)) - 1);
                         match[u] = match[u] && (((kw ^ pfx[q]) & mask) == 0);
@@ -712,6 +737,7 @@ __device__ __forceinline__ void ld_ts(const uint8_t *entry, uint32_t full_size, 
     *hi = ld_u64_unaligned(t + 8);
 }
 
+template <bool kNarrow>
 __global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec *m, uint4 *res) {
     constexpr int NT = kResolveThreads;
     __shared__ Rec s_rec[NT + 2];
@@ -744,9 +770,27 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec
         cur = s_rec[tid + 1];
         if (i) eq_prev = key_equal(p, skip, s_rec[tid], cur);
         if (i + 1 < total) eq_next = key_equal(p, skip, cur, s_rec[tid + 2]);
-        me = key_of_gid(p, cur.w);
+        if (kNarrow) {
+            const uint32_t r = find_run(p, cur.w);
+            const RunDesc &rd = p.runs[r];
+            const uint4 rec = ldg128_narrow(&rd.index[cur.w - rd.base]);
+            me.entry = rd.data + ((uint64_t)rec.x | ((uint64_t)rec.y << 32));
+            me.ptr = me.entry + 8;
+            me.klen = rec.z - 8;
+            me.full_size = rec.w;
+        } else {
+            me = key_of_gid(p, cur.w);
+        }
         uint64_t tlo = 0, thi = 0;
-        if ((eq_prev || eq_next) && !p.mode_flush) ld_ts(me.entry, me.full_size, &tlo, &thi);
+        if ((eq_prev || eq_next) && !p.mode_flush) {
+            if (kNarrow) {
+                const uint8_t *t = me.entry + me.full_size - 16;
+                tlo = ld_u64_unaligned_narrow(t);
+                thi = ld_u64_unaligned_narrow(t + 8);
+            } else {
+                ld_ts(me.entry, me.full_size, &tlo, &thi);
+            }
+        }
         s_tlo[tid] = tlo;
         s_thi[tid] = thi;
     }
