@@ -59,7 +59,8 @@ struct dbeel_engine {
     int bloom_in_emit = 0;      // DBEEL_BLOOM_IN_EMIT (variants 0/1; variant 2 always hashes in k_emit)
     int gather_ctas_per_sm = 4; // DBEEL_GATHER_CTAS
     int gather_tune = 16;       // DBEEL_GATHER_TUNE
-    int narrow_loads = 0;       // DBEEL_NARROW: .L2::64B loads for random accesses in extract / resolve
+    int extract_tune = 24;      // DBEEL_EXTRACT_TUNE
+    int narrow_loads = 1;       // DBEEL_NARROW: .L2::64B loads for random accesses in extract / resolve
 };
 
 namespace {
@@ -296,18 +297,28 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
 
     // ---- K0/K1: prefix, validate, extract (+ conditional redo when a run was truncated)
     const uint32_t g256 = (N + 255) / 256;
-    const uint32_t gext = (N + 256 * kExtractEPT - 1) / (256 * kExtractEPT);
+    const uint32_t ept = e->extract_tune / 10 ? e->extract_tune / 10 : 2; // DBEEL_EXTRACT_TUNE = 10 * entries per thread + min blocks
+    const uint32_t gext = (N + 256 * ept - 1) / (256 * ept);
+    auto launch_extract = [&](uint32_t grid, int redo) {
+        switch (e->extract_tune) {
+        case 18: k_extract<true, 1, 8><<<grid, 256, 0, s>>>(p, redo); break;
+        case 16: k_extract<true, 1, 6><<<grid, 256, 0, s>>>(p, redo); break;
+        case 25: k_extract<true, 2, 5><<<grid, 256, 0, s>>>(p, redo); break;
+        case 20: k_extract<false, 2, 4><<<grid, 256, 0, s>>>(p, redo); break;
+        default: k_extract<true, 2, 4><<<grid, 256, 0, s>>>(p, redo); break;
+        }
+    };
     if (flush) {
         k_flush_prefix_init<<<1, 1, 0, s>>>(p);
         k_flush_prefix<<<g256, 256, 0, s>>>(p);
-        if (e->narrow_loads) k_extract<true><<<gext, 256, 0, s>>>(p, 0); else k_extract<false><<<gext, 256, 0, s>>>(p, 0);
+        launch_extract(gext, 0);
         k_plan<<<1, 1, 0, s>>>(p);
         k_block_sort<<<p.nseg[0], kMergeThreads, 0, s>>>(p);
     } else {
         k_common_prefix<<<1, 32, 0, s>>>(p, 0);
-        if (e->narrow_loads) k_extract<true><<<gext, 256, 0, s>>>(p, 0); else k_extract<false><<<gext, 256, 0, s>>>(p, 0);
+        launch_extract(gext, 0);
         k_common_prefix<<<1, 32, 0, s>>>(p, 1); // both no-ops unless a run was truncated
-        k_extract<false><<<gext < 592 ? gext : 592, 256, 0, s>>>(p, 1);
+        launch_extract(gext < 592 ? gext : 592, 1);
         k_plan<<<1, 1, 0, s>>>(p);
     }
     launches += 5;
@@ -329,6 +340,10 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
             k_merge<false><<<(uint32_t)t_ub, kMergeThreads, 0, s>>>(p, l, src, dst);
         } else if (e->merge_variant == 2) {
             k_merge<true><<<(uint32_t)t_ub, kMergeThreads, 0, s>>>(p, l, src, dst);
+        } else if (e->merge_variant == 3) { // persistent, TMA bulk loads / stores + mbarrier
+            uint64_t grid = (uint64_t)e->sm_count * 3;
+            if (grid > t_ub) grid = t_ub;
+            k_merge_tma<<<(uint32_t)grid, kMergeThreads, 2 * kMergeBufRecs * sizeof(Rec), s>>>(p, l, src, dst);
         } else { // persistent, cp.async double-buffered
             uint64_t grid = (uint64_t)e->sm_count * 3;
             if (grid > t_ub) grid = t_ub;
@@ -821,12 +836,14 @@ int dbeel_engine_create(int device, dbeel_engine **out) {
     if (const char *v = getenv("DBEEL_PIPELINE_MIN_KB")) e->pipeline_min_bytes = (uint64_t)(atoi(v) > 0 ? atoi(v) : 1) << 10;
     if (const char *v = getenv("DBEEL_PARTITION_KB")) e->partition_bytes = (uint64_t)(atoi(v) > 0 ? atoi(v) : 1) << 10;
     if (const char *v = getenv("DBEEL_PARTITION_MB")) e->partition_bytes = (uint64_t)(atoi(v) > 0 ? atoi(v) : 128) << 20;
-    if (cudaFuncSetAttribute(k_merge_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kMergeBufRecs * sizeof(Rec))) != cudaSuccess) {
+    if (cudaFuncSetAttribute(k_merge_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kMergeBufRecs * sizeof(Rec))) != cudaSuccess ||
+        cudaFuncSetAttribute(k_merge_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kMergeBufRecs * sizeof(Rec))) != cudaSuccess) {
         dbeel_engine_destroy(e);
         return DBEEL_ERR_CUDA;
     }
     if (const char *v = getenv("DBEEL_BLOOM_IN_EMIT")) e->bloom_in_emit = atoi(v);
     if (const char *v = getenv("DBEEL_NARROW")) e->narrow_loads = atoi(v);
+    if (const char *v = getenv("DBEEL_EXTRACT_TUNE")) e->extract_tune = atoi(v);
     if (const char *v = getenv("DBEEL_GATHER_TUNE")) e->gather_tune = atoi(v);
     if (const char *v = getenv("DBEEL_GATHER_CTAS")) e->gather_ctas_per_sm = atoi(v) > 0 ? atoi(v) : 4;
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return DBEEL_ERR_CUDA; }

@@ -267,10 +267,9 @@ __global__ void k_common_prefix(Params p, int validated) {
 // bincode-decodes with no trailing bytes (klen/dlen prefixes agree with key_size/full_size).
 // The first invalid entry ends its run (lsm_tree.rs:1014,1063): first_bad[r] = min index.
 
-constexpr int kExtractEPT = 2; // entries per thread: two independent load chains in flight
-
-template <bool kNarrow>
-__global__ void __launch_bounds__(256, 4) k_extract(Params p, int redo) {
+// kExtractEPT entries per thread = that many independent load chains in flight per thread
+template <bool kNarrow, int kExtractEPT, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks) k_extract(Params p, int redo) {
     auto ldu = [](const uint8_t *q) { return kNarrow ? ld_u64_unaligned_narrow(q) : ld_u64_unaligned(q); };
     Ctl *c = p.ctl;
     if (redo && !(c->flags & kFlagTruncated)) return;
@@ -717,6 +716,108 @@ __global__ void __launch_bounds__(kMergeThreads, 3) k_merge_pipe(Params p, uint3
         cur = nxt;
         nxt = nn;
     }
+}
+
+// ------------------------------------------------------------------------------------
+// K3 (TMA variant): the merge tiles are the one place on this path where data IS a 16-byte-aligned
+// contiguous block (fixed-size records), so the tile's A range and B range come in as two
+// cp.async.bulk (TMA, 1-D) copies completing on an mbarrier, and the merged tile leaves as one
+// bulk store -- no per-thread global loads or stores at all.  Persistent CTAs, two shared-memory
+// buffers: tile q+1 lands while tile q is searched and merged.
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(kMergeThreads, 3) k_merge_tma(Params p, uint32_t level, const Rec *src, Rec *dst) {
+    extern __shared__ __align__(128) uint8_t s_raw[];
+    Rec *bufs[2] = {reinterpret_cast<Rec *>(s_raw), reinterpret_cast<Rec *>(s_raw) + kMergeBufRecs};
+    __shared__ __align__(8) uint64_t s_bar[2];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t skip = p.ctl->prefix_len + kWindowBytes;
+    const uint32_t n_tiles = p.tile_base[level][p.nseg[level + 1]];
+    const uint32_t G = gridDim.x;
+    uint32_t tile = blockIdx.x;
+    if (tile >= n_tiles) return;
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](const MergeDesc &d, Rec *buf, uint64_t *bar) { // thread 0 only
+        mbar_expect_tx(bar, (d.n_a + d.n_b) * 16u);
+        if (d.n_a) tma_load_1d(buf, &src[d.a_src], d.n_a * 16u, bar);
+        if (d.n_b) tma_load_1d(buf + d.n_a, &src[d.b_src], d.n_b * 16u, bar);
+    };
+
+    MergeDesc cur = merge_desc(p, level, tile);
+    MergeDesc nxt = merge_desc(p, level, tile + G);
+    if (tid == 0) issue(cur, bufs[0], &s_bar[0]);
+    for (uint32_t q = 0;; q++) {
+        Rec *s = bufs[q & 1];
+        const bool has_next = tile + G < n_tiles;
+        if (tid == 0 && has_next) {
+            // buffer (q+1)&1 staged tile q-1's output: its bulk store must have finished READING it
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            issue(nxt, bufs[(q + 1) & 1], &s_bar[(q + 1) & 1]);
+        }
+        const MergeDesc nn = merge_desc(p, level, tile + 2 * G); // consumed one iteration from now
+        while (!mbar_try_wait(&s_bar[q & 1], (q >> 1) & 1)) {}
+
+        const uint32_t nA = cur.n_a, nB = cur.n_b, n = nA + nB;
+        uint32_t d = tid * kMergeVT;
+        if (d > n) d = n;
+        uint32_t lo = d > nB ? d - nB : 0;
+        uint32_t hi = d < nA ? d : nA;
+        while (lo < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (!key_less(p, skip, s[nA + d - 1 - mid], s[mid])) lo = mid + 1; else hi = mid;
+        }
+        uint32_t ai = lo, bi = d - lo;
+        Rec ak = s[ai], bk = s[nA + bi];
+        Rec out[kMergeVT];
+#pragma unroll
+        for (int i = 0; i < kMergeVT; i++) {
+            bool has_a = ai < nA, has_b = bi < nB;
+            bool take_b = has_b && (!has_a || key_less(p, skip, bk, ak));
+            out[i] = take_b ? bk : ak;
+            if (take_b) { bi++; bk = s[nA + bi]; } else { ai++; ak = s[ai]; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kMergeVT; i++)
+            if (d + i < n) s[d + i] = out[i];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> visible to the bulk store
+        __syncthreads();
+        if (tid == 0) {
+            tma_store_1d(dst + cur.dst, s, n * 16u);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (!has_next) break;
+        tile += G;
+        cur = nxt;
+        nxt = nn;
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // stores complete before the CTA retires
 }
 
 // ------------------------------------------------------------------------------------
