@@ -182,13 +182,13 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device -- the compaction engine has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from dbeel_b200 import shard_jobs as sj
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        # job hand-off over NCCL: rank 0 owns the job table (one shard seed per rank)
-        table = torch.tensor([40 + r for r in range(world)], dtype=torch.int64, device=dev) if rank == 0 \
-            else torch.zeros(world, dtype=torch.int64, device=dev)
-        dist.broadcast(table, src=0)
-        assert int(table[rank]) == 40 + rank
+    # job hand-off (NCCL broadcast when N > 1): rank 0 owns the table, one independent shard compaction per GPU
+    table = [sj.ShardJob(r, 40 + r if world > 1 else 2, 8, 1_000_000, 256, False) for r in range(world)] if rank == 0 else None
+    mine = sj.hand_off(table, dev)
+    assert len(mine) == 1 and mine[0].shard_id == rank, mine
 
     cfg = shard_config(rank, world)
     t = time.time()
@@ -329,8 +329,8 @@ def run_gpu(args):
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": out_bytes, "steps": e2e_steps,
                 "ms_per_step": round(float(e2e_ms[0]) / e2e_steps, 3),
-                "ms_h2d": round(st_e2e["ms_h2d"], 3), "ms_kernels": round(st_e2e["ms_total"], 3),
-                "ms_d2h": round(st_e2e["ms_d2h"], 3), "api": "dbeel_compact (host pinned buffers)"},
+                "ms_kernels": round(st_e2e["ms_total"], 3), "partitions": st_e2e["partitions"],
+                "api": "dbeel_compact (host pinned buffers; key-range partitions pipelined over H2D / kernels / D2H streams)"},
         "gpu_launches": int(tot[1]),
         "clocks": clocks,
         "parity_vs_oracle": parity,

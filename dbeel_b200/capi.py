@@ -51,7 +51,7 @@ class Stats(C.Structure):
                 ("key_prefix_len", C.c_uint32), ("merge_passes", C.c_uint32), ("kernel_launches", C.c_uint32),
                 ("ms_total", C.c_float), ("ms_extract", C.c_float), ("ms_merge", C.c_float),
                 ("ms_resolve", C.c_float), ("ms_gather", C.c_float), ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),
-                ("gather_bytes", C.c_uint64)]
+                ("gather_bytes", C.c_uint64), ("partitions", C.c_uint32), ("reserved", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

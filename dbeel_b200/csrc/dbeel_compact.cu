@@ -54,13 +54,8 @@ struct dbeel_engine {
     std::string err;
     bool busy = false;
     int sm_count = 148;
-    int gather_variant = 3;     // DBEEL_GATHER: 0 = one CTA per 16 KB tile, 1 = persistent warp-specialized, 2 = one warp per 2 KB tile, 3 = 16 KB CTA tile + warp sub-tiles
-    int merge_variant = 0;      // DBEEL_MERGE: 0 = one CTA per tile, 1 = persistent + cp.async double buffering
-    int bloom_in_emit = 0;      // DBEEL_BLOOM_IN_EMIT (variants 0/1; variant 2 always hashes in k_emit)
-    int gather_ctas_per_sm = 4; // DBEEL_GATHER_CTAS
-    int gather_tune = 16;       // DBEEL_GATHER_TUNE
-    int extract_tune = 24;      // DBEEL_EXTRACT_TUNE
-    int narrow_loads = 1;       // DBEEL_NARROW: .L2::64B loads for random accesses in extract / resolve
+    int merge_variant = 1;      // DBEEL_MERGE: 0 = one CTA per tile with plain loads, 1 = persistent TMA (default)
+    int narrow_loads = 1;       // DBEEL_NARROW: .L2::64B loads for random accesses in extract / resolve (A/B switch)
 };
 
 namespace {
@@ -218,8 +213,7 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     const uint64_t o_cbytes = carve(res_chunks * 8), o_ccount = carve(res_chunks * 4);
     const uint64_t o_reca = carve(16ull * N), o_recb = carve(16ull * N);
     const uint64_t o_src = carve(8ull * N);
-    const uint64_t gtb = e->gather_variant == 2 ? kWarpTileBytes : kGatherTileBytes;
-    const uint64_t gather_tiles = (sh.data_total + gtb - 1) / gtb;
+    const uint64_t gather_tiles = (sh.data_total + kGatherTileBytes - 1) / kGatherTileBytes;
     const uint64_t o_tfirst = carve(4ull * (gather_tiles + 2));
     int rc = ensure_device(e, &e->ws, &e->ws_cap, off);
     if (rc) return rc;
@@ -242,8 +236,6 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     p.rec_b = reinterpret_cast<Rec *>(ws + o_recb);
     p.src_ptr = reinterpret_cast<unsigned long long *>(ws + o_src);
     p.tile_first = reinterpret_cast<uint32_t *>(ws + o_tfirst);
-    p.gather_tile_bytes = gtb;
-    p.bloom_in_emit = e->gather_variant == 2 || e->bloom_in_emit;
     p.out_data = static_cast<uint8_t *>(out->data);
     p.out_index = static_cast<uint4 *>(out->index);
 
@@ -297,16 +289,10 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
 
     // ---- K0/K1: prefix, validate, extract (+ conditional redo when a run was truncated)
     const uint32_t g256 = (N + 255) / 256;
-    const uint32_t ept = e->extract_tune / 10 ? e->extract_tune / 10 : 2; // DBEEL_EXTRACT_TUNE = 10 * entries per thread + min blocks
-    const uint32_t gext = (N + 256 * ept - 1) / (256 * ept);
+    const uint32_t gext = (N + 256 * kExtractEPT - 1) / (256 * kExtractEPT);
     auto launch_extract = [&](uint32_t grid, int redo) {
-        switch (e->extract_tune) {
-        case 18: k_extract<true, 1, 8><<<grid, 256, 0, s>>>(p, redo); break;
-        case 16: k_extract<true, 1, 6><<<grid, 256, 0, s>>>(p, redo); break;
-        case 25: k_extract<true, 2, 5><<<grid, 256, 0, s>>>(p, redo); break;
-        case 20: k_extract<false, 2, 4><<<grid, 256, 0, s>>>(p, redo); break;
-        default: k_extract<true, 2, 4><<<grid, 256, 0, s>>>(p, redo); break;
-        }
+        if (e->narrow_loads) k_extract<true><<<grid, 256, 0, s>>>(p, redo);
+        else k_extract<false><<<grid, 256, 0, s>>>(p, redo);
     };
     if (flush) {
         k_flush_prefix_init<<<1, 1, 0, s>>>(p);
@@ -336,18 +322,12 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
         uint64_t t_ub = (uint64_t)(N + kMergeTile - 1) / kMergeTile + pairs;
         uint64_t b_ub = t_ub + pairs;
         k_merge_partition<<<(uint32_t)((b_ub + 127) / 128), 128, 0, s>>>(p, l, src);
-        if (e->merge_variant == 0) {
-            k_merge<false><<<(uint32_t)t_ub, kMergeThreads, 0, s>>>(p, l, src, dst);
-        } else if (e->merge_variant == 2) {
-            k_merge<true><<<(uint32_t)t_ub, kMergeThreads, 0, s>>>(p, l, src, dst);
-        } else if (e->merge_variant == 3) { // persistent, TMA bulk loads / stores + mbarrier
+        if (e->merge_variant == 0) { // one CTA per tile, plain loads (kept as the A/B baseline of the TMA kernel)
+            k_merge<<<(uint32_t)t_ub, kMergeThreads, 0, s>>>(p, l, src, dst);
+        } else { // persistent, TMA bulk loads / stores + mbarrier
             uint64_t grid = (uint64_t)e->sm_count * 3;
             if (grid > t_ub) grid = t_ub;
             k_merge_tma<<<(uint32_t)grid, kMergeThreads, 2 * kMergeBufRecs * sizeof(Rec), s>>>(p, l, src, dst);
-        } else { // persistent, cp.async double-buffered
-            uint64_t grid = (uint64_t)e->sm_count * 3;
-            if (grid > t_ub) grid = t_ub;
-            k_merge_pipe<<<(uint32_t)grid, kMergeThreads, 2 * kMergeBufRecs * sizeof(Rec), s>>>(p, l, src, dst);
         }
         launches += 2;
         const Rec *t = src;
@@ -372,26 +352,7 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
 
     // ---- K5: gather (+ bloom in the CTA-tile variants)
     if (gather_tiles) {
-        if (e->gather_variant == 2) { // one warp per 2 KB tile
-            constexpr uint64_t wpb = kGatherWarpThreads / 32;
-            k_gather_warp<<<(uint32_t)((gather_tiles + wpb - 1) / wpb), kGatherWarpThreads, 0, s>>>(p);
-        } else if (e->gather_variant == 0) {
-            k_gather<<<(uint32_t)gather_tiles, kGatherThreads, 0, s>>>(p);
-        } else if (e->gather_variant == 3) {
-            const uint32_t gt = (uint32_t)gather_tiles;
-            switch (e->gather_tune) { // DBEEL_GATHER_TUNE = 10 * map + min blocks per SM
-            case 4: k_gather_hybrid<0, 4><<<gt, kGatherThreads, 0, s>>>(p); break;
-            case 6: k_gather_hybrid<0, 6><<<gt, kGatherThreads, 0, s>>>(p); break;
-            case 14: k_gather_hybrid<1, 4><<<gt, kGatherThreads, 0, s>>>(p); break;
-            case 15: k_gather_hybrid<1, 5><<<gt, kGatherThreads, 0, s>>>(p); break;
-            case 16: k_gather_hybrid<1, 6><<<gt, kGatherThreads, 0, s>>>(p); break;
-            default: k_gather_hybrid<0, 5><<<gt, kGatherThreads, 0, s>>>(p); break;
-            }
-        } else { // persistent, warp-specialized
-            uint64_t grid = (uint64_t)e->sm_count * e->gather_ctas_per_sm;
-            if (grid > gather_tiles) grid = gather_tiles;
-            k_gather_ws<<<(uint32_t)grid, kGatherWsThreads, 0, s>>>(p);
-        }
+        k_gather<<<(uint32_t)gather_tiles, kGatherThreads, 0, s>>>(p);
     }
     launches++;
     CU(cudaEventRecord(e->ev[EV_GATHER], s));
@@ -422,6 +383,7 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     st.entries_out = hc->out_items;
     st.output_bytes = out->data_len + out->index_len + out->bloom_len;
     st.gather_bytes = 2 * out->data_len + out->index_len + 8ull * hc->out_items; // read + write payload, read index + src_ptr
+    st.partitions = 1;
     return DBEEL_OK;
 }
 
@@ -700,6 +662,7 @@ int run_job_host_pipelined(dbeel_engine *e, const dbeel_run *runs, uint32_t n_ru
     total.entries_out = out_items;
     total.output_bytes = out->data_len + out->index_len + out->bloom_len;
     total.kernel_launches += sh.bloom_file ? 1 : 0;
+    total.partitions = np;
     e->stats = total;
     return DBEEL_OK;
 }
@@ -822,30 +785,20 @@ int dbeel_engine_create(int device, dbeel_engine **out) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return DBEEL_ERR_CUDA;
     if (prop.major != 10) return DBEEL_ERR_NO_DEVICE; // sm_100a SASS only: no fallback path
     if (cudaSetDevice(device) != cudaSuccess) return DBEEL_ERR_CUDA;
-    if (const char *g = getenv("DBEEL_L2_FETCH_GRANULARITY")) { // tuning experiment: 32 / 64 / 128 bytes
-        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
-        cudaGetLastError();
-    }
     dbeel_engine *e = new (std::nothrow) dbeel_engine();
     if (!e) return DBEEL_ERR_NOMEM;
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
-    if (const char *v = getenv("DBEEL_GATHER")) e->gather_variant = atoi(v);
     if (const char *v = getenv("DBEEL_MERGE")) e->merge_variant = atoi(v);
     if (const char *v = getenv("DBEEL_PIPELINE")) e->pipeline = atoi(v);
     if (const char *v = getenv("DBEEL_PIPELINE_MIN_KB")) e->pipeline_min_bytes = (uint64_t)(atoi(v) > 0 ? atoi(v) : 1) << 10;
     if (const char *v = getenv("DBEEL_PARTITION_KB")) e->partition_bytes = (uint64_t)(atoi(v) > 0 ? atoi(v) : 1) << 10;
     if (const char *v = getenv("DBEEL_PARTITION_MB")) e->partition_bytes = (uint64_t)(atoi(v) > 0 ? atoi(v) : 128) << 20;
-    if (cudaFuncSetAttribute(k_merge_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kMergeBufRecs * sizeof(Rec))) != cudaSuccess ||
-        cudaFuncSetAttribute(k_merge_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kMergeBufRecs * sizeof(Rec))) != cudaSuccess) {
+    if (cudaFuncSetAttribute(k_merge_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kMergeBufRecs * sizeof(Rec))) != cudaSuccess) {
         dbeel_engine_destroy(e);
         return DBEEL_ERR_CUDA;
     }
-    if (const char *v = getenv("DBEEL_BLOOM_IN_EMIT")) e->bloom_in_emit = atoi(v);
     if (const char *v = getenv("DBEEL_NARROW")) e->narrow_loads = atoi(v);
-    if (const char *v = getenv("DBEEL_EXTRACT_TUNE")) e->extract_tune = atoi(v);
-    if (const char *v = getenv("DBEEL_GATHER_TUNE")) e->gather_tune = atoi(v);
-    if (const char *v = getenv("DBEEL_GATHER_CTAS")) e->gather_ctas_per_sm = atoi(v) > 0 ? atoi(v) : 4;
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return DBEEL_ERR_CUDA; }
     for (int i = 0; i < EV_COUNT; i++)
         if (cudaEventCreate(&e->ev[i]) != cudaSuccess) { dbeel_engine_destroy(e); return DBEEL_ERR_CUDA; }

@@ -87,9 +87,7 @@ struct Params {
     uint8_t *out_data;
     uint4 *out_index;
     unsigned long long *src_ptr; // [n_total] device address of each surviving entry's bytes
-    uint32_t *tile_first;        // [ceil(data bytes / gather_tile_bytes) + 2] entry holding each gather tile's first byte
-    unsigned long long gather_tile_bytes; // 16 KB (CTA tiles) or 2 KB (warp tiles)
-    int bloom_in_emit;           // 1: k_emit sets the bloom bits; 0: the gather kernel does
+    uint32_t *tile_first;        // [ceil(data bytes / 16 KB) + 2] entry holding each gather tile's first byte
     unsigned long long out_offset_base; // .data bytes written by earlier key-range partitions of the same output file
     BloomParams bloom;
 };
@@ -267,9 +265,10 @@ __global__ void k_common_prefix(Params p, int validated) {
 // bincode-decodes with no trailing bytes (klen/dlen prefixes agree with key_size/full_size).
 // The first invalid entry ends its run (lsm_tree.rs:1014,1063): first_bad[r] = min index.
 
-// kExtractEPT entries per thread = that many independent load chains in flight per thread
-template <bool kNarrow, int kExtractEPT, int kMinBlocks>
-__global__ void __launch_bounds__(256, kMinBlocks) k_extract(Params p, int redo) {
+constexpr int kExtractEPT = 2; // entries per thread = independent load chains in flight per thread
+
+template <bool kNarrow>
+__global__ void __launch_bounds__(256, 4) k_extract(Params p, int redo) {
     auto ldu = [](const uint8_t *q) { return kNarrow ? ld_u64_unaligned_narrow(q) : ld_u64_unaligned(q); };
     Ctl *c = p.ctl;
     if (redo && !(c->flags & kFlagTruncated)) return;
@@ -552,7 +551,6 @@ __global__ void __launch_bounds__(128) k_merge_partition(Params p, uint32_t leve
     p.part[idx] = lo;
 }
 
-template <bool kDirectStore>
 __global__ void __launch_bounds__(kMergeThreads, 4) k_merge(Params p, uint32_t level, const Rec *src, Rec *dst) {
     __shared__ Rec s[kMergeTile + kMergeVT + 1];
     const uint32_t pairs = p.nseg[level + 1];
@@ -598,14 +596,6 @@ __global__ void __launch_bounds__(kMergeThreads, 4) k_merge(Params p, uint32_t l
         if (take_b) { bi++; bk = s[nA + bi]; } else { ai++; ak = s[ai]; }
     }
     Rec *o = dst + a.start + diag0;
-    if (kDirectStore) {
-        // each thread owns 7 consecutive output records (112 contiguous bytes); a warp's stores cover one
-        // contiguous 3.5 KB span, so L2 sees every sector whole within a few instructions
-#pragma unroll
-        for (int i = 0; i < kMergeVT; i++)
-            if (d + i < n) st_rec(&o[d + i], out[i]);
-        return;
-    }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < kMergeVT; i++)
@@ -615,10 +605,8 @@ __global__ void __launch_bounds__(kMergeThreads, 4) k_merge(Params p, uint32_t l
 }
 
 // ------------------------------------------------------------------------------------
-// K3 (pipelined variant): persistent CTAs, each walking merge tiles blockIdx, blockIdx+grid, ...
-// with the NEXT tile's records streaming into the other shared-memory buffer (cp.async, 16 B
-// per request) while the current tile is searched and merged, and the tile after that having
-// its split points looked up -- so neither HBM nor L2 latency sits on the critical path.
+// Tile descriptors for the persistent merge kernel: which records of src a tile consumes and where
+// its merged output goes.  Looked up two tiles ahead so the lookups never sit on the critical path.
 
 struct MergeDesc {
     uint32_t a_src, n_a, b_src, n_b, dst; // record offsets into src / dst, counts
@@ -649,74 +637,7 @@ __device__ __forceinline__ MergeDesc merge_desc(const Params &p, uint32_t level,
     return d;
 }
 
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
-}
-
 constexpr int kMergeBufRecs = kMergeTile + kMergeVT + 1;
-
-__global__ void __launch_bounds__(kMergeThreads, 3) k_merge_pipe(Params p, uint32_t level, const Rec *src, Rec *dst) {
-    extern __shared__ __align__(16) uint8_t s_raw[];
-    Rec *bufs[2] = {reinterpret_cast<Rec *>(s_raw), reinterpret_cast<Rec *>(s_raw) + kMergeBufRecs};
-    const uint32_t tid = threadIdx.x;
-    const uint32_t skip = p.ctl->prefix_len + kWindowBytes;
-    const uint32_t n_tiles = p.tile_base[level][p.nseg[level + 1]];
-    const uint32_t G = gridDim.x;
-    uint32_t tile = blockIdx.x;
-    if (tile >= n_tiles) return;
-
-    auto issue = [&](const MergeDesc &d, Rec *buf) {
-        for (uint32_t i = tid; i < d.n_a; i += kMergeThreads) cp_async16(&buf[i], &src[d.a_src + i]);
-        for (uint32_t i = tid; i < d.n_b; i += kMergeThreads) cp_async16(&buf[d.n_a + i], &src[d.b_src + i]);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-
-    MergeDesc cur = merge_desc(p, level, tile);
-    MergeDesc nxt = merge_desc(p, level, tile + G);
-    issue(cur, bufs[0]);
-    for (uint32_t q = 0;; q++) {
-        Rec *s = bufs[q & 1];
-        const bool has_next = tile + G < n_tiles;
-        if (has_next) issue(nxt, bufs[(q + 1) & 1]);
-        const MergeDesc nn = merge_desc(p, level, tile + 2 * G); // consumed one iteration from now
-        if (has_next) asm volatile("cp.async.wait_group 1;" ::: "memory");
-        else asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
-
-        const uint32_t nA = cur.n_a, nB = cur.n_b, n = nA + nB;
-        uint32_t d = tid * kMergeVT;
-        if (d > n) d = n;
-        uint32_t lo = d > nB ? d - nB : 0;
-        uint32_t hi = d < nA ? d : nA;
-        while (lo < hi) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (!key_less(p, skip, s[nA + d - 1 - mid], s[mid])) lo = mid + 1; else hi = mid;
-        }
-        uint32_t ai = lo, bi = d - lo;
-        Rec ak = s[ai], bk = s[nA + bi];
-        Rec out[kMergeVT];
-#pragma unroll
-        for (int i = 0; i < kMergeVT; i++) {
-            bool has_a = ai < nA, has_b = bi < nB;
-            bool take_b = has_b && (!has_a || key_less(p, skip, bk, ak));
-            out[i] = take_b ? bk : ak;
-            if (take_b) { bi++; bk = s[nA + bi]; } else { ai++; ak = s[ai]; }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < kMergeVT; i++)
-            if (d + i < n) s[d + i] = out[i];
-        __syncthreads();
-        Rec *o = dst + cur.dst;
-        for (uint32_t i = tid; i < n; i += kMergeThreads) st_rec(&o[i], s[i]);
-        __syncthreads(); // buffer q&1 is free again: the tile after next streams into it
-        if (!has_next) break;
-        tile += G;
-        cur = nxt;
-        nxt = nn;
-    }
-}
 
 // ------------------------------------------------------------------------------------
 // K3 (TMA variant): the merge tiles are the one place on this path where data IS a 16-byte-aligned
@@ -1078,31 +999,16 @@ __global__ void __launch_bounds__(kResolveThreads) k_emit(Params p, const uint4 
     p.out_index[pos] = make_uint4((uint32_t)file_off, (uint32_t)(file_off >> 32), it.z, fs);
     p.src_ptr[pos] = src;
     // every gather tile whose first byte lies in [off, off + fs) starts inside this entry
-    const unsigned long long tb = p.gather_tile_bytes;
+    constexpr unsigned long long tb = kGatherTileBytes;
     unsigned long long b = (off + tb - 1) / tb;
     for (; b * tb < off + fs; b++) p.tile_first[b] = pos;
-    // fused epilogue: the survivor's bloom bits (lsm_tree.rs:1049-1051) are set by the same thread
-    // that writes its .index record
-    if (p.bloom.words != nullptr && p.bloom_in_emit) {
-        const uint8_t *key = reinterpret_cast<const uint8_t *>((uintptr_t)src) + 8;
-        const uint64_t klen = it.z - 8;
-        uint64_t h0, h1;
-        sip13_pair_vec_u8(p.bloom.sip, klen, [key](uint64_t w) { return ld_u64_unaligned(key + 8 * w); }, &h0, &h1);
-        for (uint32_t k = 0; k < p.bloom.k_num; k++) {
-            uint64_t bit = fastmod(bloom_hash_i(h0, h1, k), p.bloom.bits, p.bloom.bits_magic);
-            atomicOr(&p.bloom.words[bit >> 5], 1u << (bit & 31));
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------
 // K5: gather + bloom -- the roofline kernel.  Every surviving entry's bytes are read once
 // from its input run and written once at its output offset.
 //
-// The output .data stream is cut into 16 KB tiles (1024 aligned 16-byte vectors), one CTA
-// each.  The CTA stages the metadata of the entries that overlap its tile in shared memory,
-// maps every vector to the entry holding the vector's first byte (mark + max-scan), and then
-// each thread produces 4 vectors, a warp writing 512 contiguous bytes per store:
+// The output .data stream is cut into 16 KB tiles (1024 aligned 16-byte vectors), one CTA each.
 //   * a vector that lies inside one entry = two aligned 16-byte source loads + a byte funnel
 //     shift (source and destination are misaligned by an arbitrary byte count);
 //   * a vector that straddles an entry boundary (one per entry) is built by a second, dense
@@ -1125,494 +1031,13 @@ __device__ __forceinline__ uint4 realign16_sel(uint4 A, uint4 B, uint32_t sh) {
                       __funnelshift_r(d3, d4, bits));
 }
 
-__global__ void __launch_bounds__(kGatherThreads) k_gather(Params p) {
-    constexpr int NT = kGatherThreads;
-    constexpr int VPT = kGatherVecsPerThread;
-    constexpr int NV = NT * VPT; // vectors per tile
-    __shared__ long long s_r0[kGatherMaxEntries];            // entry start relative to the tile (may be < 0)
-    __shared__ unsigned long long s_src[kGatherMaxEntries]; // device address of the entry's bytes
-    __shared__ uint32_t s_fs[kGatherMaxEntries], s_ks[kGatherMaxEntries];
-    __shared__ uint16_t s_vec[NV];
-    __shared__ uint32_t s_wmax[NT / 32];
-    const Ctl *c = p.ctl;
-    const unsigned long long out_len = c->out_data_len;
-    const unsigned long long T0 = (unsigned long long)blockIdx.x * kGatherTileBytes;
-    if (T0 >= out_len) return;
-    const uint32_t n_out = c->out_items;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t tile_len = out_len - T0 < kGatherTileBytes ? (uint32_t)(out_len - T0) : (uint32_t)kGatherTileBytes;
-    const uint32_t e_lo = p.tile_first[blockIdx.x];
-    uint32_t e_hi = n_out - 1;
-    if (T0 + kGatherTileBytes < out_len) e_hi = p.tile_first[blockIdx.x + 1];
-    const uint32_t ne = e_hi - e_lo + 1; // <= kGatherMaxEntries: every entry is >= 32 bytes
-
-    // ---- stage entry metadata, mark each entry's first vector, hash keys
-    for (uint32_t v = tid; v < NV; v += NT) s_vec[v] = 0;
-    __syncthreads();
-    for (uint32_t j = tid; j < ne; j += NT) {
-        uint4 rec = p.out_index[e_lo + j];
-        const unsigned long long d0 = ((unsigned long long)rec.x | ((unsigned long long)rec.y << 32)) - p.out_offset_base;
-        const long long r0 = (long long)d0 - (long long)T0;
-        const unsigned long long src = p.src_ptr[e_lo + j];
-        s_r0[j] = r0;
-        s_src[j] = src;
-        s_fs[j] = rec.w;
-        const uint32_t fv = r0 <= 0 ? 0u : (uint32_t)((r0 + 15) >> 4); // first vector starting inside the entry
-        if (fv < NV) s_vec[fv] = (uint16_t)j; // unique per entry (entries are >= 32 bytes)
-        s_ks[j] = rec.z;
-    }
-    __syncthreads();
-
-    // ---- inclusive max-scan of the marks: s_vec[v] = entry that holds byte 16*v of the tile
-    {
-        uint32_t m[VPT];
-        uint32_t run = 0;
-#pragma unroll
-        for (int k = 0; k < VPT; k++) {
-            uint32_t x = s_vec[tid * VPT + k];
-            run = x > run ? x : run;
-            m[k] = run;
-        }
-        uint32_t incl = run;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= (uint32_t)o) incl = t > incl ? t : incl;
-        }
-        if (lane == 31) s_wmax[warp] = incl;
-        __syncthreads();
-        uint32_t before = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
-        if (lane == 0) before = 0;
-        for (uint32_t w = 0; w < warp; w++) before = s_wmax[w] > before ? s_wmax[w] : before;
-#pragma unroll
-        for (int k = 0; k < VPT; k++) s_vec[tid * VPT + k] = (uint16_t)(m[k] > before ? m[k] : before);
-    }
-    __syncthreads();
-
-    // ---- copy: thread t produces vectors t, t+NT, t+2NT, ...
-    uint8_t *dst_tile = p.out_data + T0;
-    uint4 A[VPT], B[VPT];
-    uint32_t sh[VPT];
-    bool pure[VPT];
-#pragma unroll
-    for (int k = 0; k < VPT; k++) {
-        const uint32_t v = tid + k * NT;
-        const uint32_t b0 = v * 16;
-        pure[k] = false;
-        sh[k] = 0;
-        if (b0 + 16 <= tile_len) {
-            const uint32_t j = s_vec[v];
-            const long long r0 = s_r0[j];
-            if ((long long)b0 + 16 <= r0 + (long long)s_fs[j]) {
-                const uintptr_t sa = (uintptr_t)s_src[j] + (uintptr_t)((long long)b0 - r0);
-                sh[k] = (uint32_t)(sa & 15);
-                const uint4 *sv = reinterpret_cast<const uint4 *>(sa - sh[k]);
-                A[k] = __ldg(sv);
-                B[k] = __ldg(sh[k] ? sv + 1 : sv);
-                pure[k] = true;
-            }
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < VPT; k++) {
-        const uint32_t v = tid + k * NT;
-        if (pure[k]) reinterpret_cast<uint4 *>(dst_tile)[v] = realign16_sel(A[k], B[k], sh[k]);
-    }
-    // ---- vectors that straddle an entry boundary: one per entry, handled densely -- thread j
-    // builds the vector that holds the last byte of entry j: the tail of j blended with the
-    // head of entry j+1 (entries are >= 32 bytes, so never more than two entries per vector)
-    for (uint32_t j = tid; j < ne; j += NT) {
-        const long long r0 = s_r0[j];
-        const long long r1 = r0 + (long long)s_fs[j];
-        if (r1 <= 0 || (r1 & 15) == 0 || r1 > (long long)tile_len) continue; // ends outside, or on a vector edge
-        const uint32_t v = (uint32_t)(r1 >> 4);
-        const uint32_t b0 = v * 16;
-        const uint32_t t = (uint32_t)(r1 - b0); // tail bytes of entry j in this vector: 1..15
-        // tail: 16 bytes of j's stream from byte b0 (only the first t are meaningful)
-        const uintptr_t sa = (uintptr_t)s_src[j] + (uintptr_t)((long long)b0 - r0);
-        const uint32_t sh = (uint32_t)(sa & 15);
-        const uint4 *sv = reinterpret_cast<const uint4 *>(sa - sh);
-        const uint4 TA = __ldg(sv);
-        const uint4 TB = __ldg(sh + t > 16 ? sv + 1 : sv); // second vector only if the tail reaches into it
-        uint4 o = realign16_sel(TA, TB, sh);
-        if (b0 + 16 <= tile_len) {
-            // head: the first 16 - t bytes of entry j+1, moved up by t bytes
-            const uintptr_t ha = (uintptr_t)s_src[j + 1];
-            const uint32_t hs = (uint32_t)(ha & 15);
-            const uint4 *hv = reinterpret_cast<const uint4 *>(ha - hs);
-            const uint4 HA = __ldg(hv);
-            const uint4 HB = __ldg(hs ? hv + 1 : hv); // entry j+1 is >= 32 bytes: both vectors hold its bytes
-            const uint4 H = realign16_sel(HA, HB, hs);
-            const uint4 Z = make_uint4(0, 0, 0, 0);
-            const uint4 HU = realign16_sel(Z, H, 16 - t); // bytes [16-t, 32-t) of Z|H: t zero bytes, then H
-            const uint32_t wfull = t >> 2, bits = (t & 3) * 8; // words < wfull: tail; word wfull: mixed
-            const uint32_t mmix = bits ? (0xFFFFFFFFu >> (32 - bits)) : 0u;
-            uint32_t ow[4] = {o.x, o.y, o.z, o.w}, hw[4] = {HU.x, HU.y, HU.z, HU.w};
-#pragma unroll
-            for (uint32_t q = 0; q < 4; q++) {
-                const uint32_t mk = q < wfull ? 0xFFFFFFFFu : (q == wfull ? mmix : 0u);
-                ow[q] = (ow[q] & mk) | (hw[q] & ~mk);
-            }
-            reinterpret_cast<uint4 *>(dst_tile)[v] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-        } else { // ragged end of the whole stream: never write past out_data_len
-            const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
-            for (uint32_t b = 0; b < t; b++) dst_tile[b0 + b] = (uint8_t)(ow[b >> 2] >> ((b & 3) * 8));
-        }
-    }
-
-    // ---- bloom: entries whose first byte lies in this tile (each entry belongs to exactly one tile).
-    // Done last so the copy's loads are in flight first; the key bytes are L1/L2-hot by now.
-    if (p.bloom.words != nullptr && !p.bloom_in_emit) {
-        for (uint32_t j = tid; j < ne; j += NT) {
-            const long long r0 = s_r0[j];
-            if (r0 < 0 || r0 >= (long long)kGatherTileBytes) continue;
-            const uint8_t *key = reinterpret_cast<const uint8_t *>((uintptr_t)s_src[j]) + 8;
-            const uint64_t klen = s_ks[j] - 8;
-            uint64_t h0, h1;
-            sip13_pair_vec_u8(p.bloom.sip, klen, [key](uint64_t q) { return ld_u64_unaligned(key + 8 * q); }, &h0, &h1);
-            for (uint32_t k = 0; k < p.bloom.k_num; k++) {
-                uint64_t bit = fastmod(bloom_hash_i(h0, h1, k), p.bloom.bits, p.bloom.bits_magic);
-                atomicOr(&p.bloom.words[bit >> 5], 1u << (bit & 31));
-            }
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------
-// K5 (persistent, warp-specialized variant).  Same tiles and same byte-level work as k_gather,
-// restructured so the latencies overlap instead of adding up:
-//   * the grid is a few CTAs per SM and every CTA walks tiles blockIdx, blockIdx + grid, ...;
-//   * 8 "copy" warps do mark/scan/copy/straddle for tile q while
-//   * 2 "aux" warps stage tile q+1's entry list into the other shared-memory buffer, look up
-//     tile q+2's entry range, and run the bloom hashing of tile q (the fused epilogue) -- the
-//     SipHash chains execute while the copy warps wait on HBM.
-// Copy warps synchronise among themselves on named barrier 1; the whole CTA meets once per tile.
+// One staging pass, ONE block barrier, dense (thread-per-entry) straddle and bloom passes; the copy
+// itself is done warp by warp on 2 KB sub-tiles: a warp finds the entry under its first byte once
+// and then walks the (sorted) entry ends 512 bytes at a time, each lane counting how many entries
+// end at or before its own vector (one OR-reduction + popcount per chunk).
 
-constexpr int kGatherCopyThreads = 256;
-constexpr int kGatherAuxThreads = 64;
-constexpr int kGatherWsThreads = kGatherCopyThreads + kGatherAuxThreads;
-
-struct GatherTileMeta {
-    unsigned long long adj[kGatherMaxEntries]; // entry address minus its tile-relative start: byte b of the tile lives at adj + b
-    long long r0[kGatherMaxEntries];           // entry start relative to the tile (may be < 0)
-    int r1[kGatherMaxEntries];                 // entry end relative to the tile, clamped to INT_MAX
-    uint32_t ks[kGatherMaxEntries];
-    uint32_t ne;
-    uint32_t tile_len;
-};
-
-__device__ __forceinline__ void copy_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kGatherCopyThreads) : "memory"); }
-
-__device__ __forceinline__ void gather_stage(const Params &p, GatherTileMeta &m, unsigned long long T0, uint32_t e_lo,
-                                             uint32_t ne, uint32_t tile_len, uint32_t t, uint32_t nt) {
-    for (uint32_t j = t; j < ne; j += nt) {
-        const uint4 rec = p.out_index[e_lo + j];
-        const unsigned long long d0 = ((unsigned long long)rec.x | ((unsigned long long)rec.y << 32)) - p.out_offset_base;
-        const long long r0 = (long long)d0 - (long long)T0;
-        const long long r1 = r0 + (long long)rec.w;
-        m.adj[j] = p.src_ptr[e_lo + j] - (unsigned long long)r0;
-        m.r0[j] = r0;
-        m.r1[j] = r1 > 0x7FFFFFFFll ? 0x7FFFFFFF : (int)r1;
-        m.ks[j] = rec.z;
-    }
-    if (t == 0) { m.ne = ne; m.tile_len = tile_len; }
-}
-
-__global__ void __launch_bounds__(kGatherWsThreads, 3) k_gather_ws(Params p) {
-    constexpr int VPT = kGatherVecsPerThread;
-    constexpr int NV = kGatherCopyThreads * VPT;
-    __shared__ GatherTileMeta s_m[2];
-    __shared__ uint16_t s_vec[NV];
-    __shared__ uint32_t s_wmax[kGatherCopyThreads / 32];
-    __shared__ uint32_t s_elo[2], s_ehi[2];
-    const Ctl *c = p.ctl;
-    const unsigned long long out_len = c->out_data_len;
-    const uint32_t n_out = c->out_items;
-    const uint32_t tid = threadIdx.x;
-    const bool is_copy = tid < kGatherCopyThreads;
-    const uint32_t atid = tid - kGatherCopyThreads; // aux-thread index (aux warps only)
-    const unsigned long long G = gridDim.x;
-    unsigned long long tile = blockIdx.x;
-    if (tile * kGatherTileBytes >= out_len) return;
-
-    auto entry_range = [&](unsigned long long tl, uint32_t *lo, uint32_t *hi) {
-        *lo = p.tile_first[tl];
-        *hi = (tl + 1) * kGatherTileBytes < out_len ? p.tile_first[tl + 1] : n_out - 1;
-    };
-    auto tile_len_of = [&](unsigned long long tl) {
-        const unsigned long long T0 = tl * kGatherTileBytes;
-        return out_len - T0 < kGatherTileBytes ? (uint32_t)(out_len - T0) : (uint32_t)kGatherTileBytes;
-    };
-
-    // ---- prologue: entry ranges of this CTA's first two tiles, entry list of the first
-    if (tid < 2) {
-        const unsigned long long tl = tile + tid * G;
-        uint32_t lo = 0, hi = 0;
-        if (tl * kGatherTileBytes < out_len) entry_range(tl, &lo, &hi);
-        s_elo[tid] = lo;
-        s_ehi[tid] = hi;
-    }
-    __syncthreads();
-    gather_stage(p, s_m[0], tile * kGatherTileBytes, s_elo[0], s_ehi[0] - s_elo[0] + 1, tile_len_of(tile), tid, kGatherWsThreads);
-    __syncthreads();
-
-    for (uint32_t q = 0;; q++, tile += G) {
-        GatherTileMeta &m = s_m[q & 1];
-        const unsigned long long T0 = tile * kGatherTileBytes;
-        const unsigned long long next = tile + G;
-        const bool has_next = next * kGatherTileBytes < out_len;
-        if (!is_copy) {
-            // ================= aux warps =================
-            if (has_next) // stage tile q+1 (its entry range was looked up one tile ago)
-                gather_stage(p, s_m[(q + 1) & 1], next * kGatherTileBytes, s_elo[(q + 1) & 1],
-                             s_ehi[(q + 1) & 1] - s_elo[(q + 1) & 1] + 1, tile_len_of(next), atid, kGatherAuxThreads);
-            if (atid == 0) { // entry range of tile q+2 into the slot tile q no longer needs
-                const unsigned long long nn = next + G;
-                uint32_t lo = 0, hi = 0;
-                if (nn * kGatherTileBytes < out_len) entry_range(nn, &lo, &hi);
-                s_elo[q & 1] = lo;
-                s_ehi[q & 1] = hi;
-            }
-            if (p.bloom.words != nullptr && !p.bloom_in_emit) { // bloom of tile q: entries whose first byte lies in this tile
-                const uint32_t ne = m.ne;
-                for (uint32_t j = atid; j < ne; j += kGatherAuxThreads) {
-                    const long long r0 = m.r0[j];
-                    if (r0 < 0 || r0 >= (long long)kGatherTileBytes) continue;
-                    const uint8_t *key = reinterpret_cast<const uint8_t *>((uintptr_t)(m.adj[j] + (unsigned long long)r0)) + 8;
-                    const uint64_t klen = m.ks[j] - 8;
-                    uint64_t h0, h1;
-                    sip13_pair_vec_u8(p.bloom.sip, klen, [key](uint64_t w) { return ld_u64_unaligned(key + 8 * w); }, &h0, &h1);
-                    for (uint32_t k = 0; k < p.bloom.k_num; k++) {
-                        uint64_t bit = fastmod(bloom_hash_i(h0, h1, k), p.bloom.bits, p.bloom.bits_magic);
-                        atomicOr(&p.bloom.words[bit >> 5], 1u << (bit & 31));
-                    }
-                }
-            }
-        } else {
-            // ================= copy warps =================
-            const uint32_t lane = tid & 31, warp = tid >> 5;
-            const uint32_t ne = m.ne, tile_len = m.tile_len;
-            for (uint32_t v = tid; v < NV; v += kGatherCopyThreads) s_vec[v] = 0;
-            copy_bar();
-            for (uint32_t j = tid; j < ne; j += kGatherCopyThreads) {
-                const long long r0 = m.r0[j];
-                const uint32_t fv = r0 <= 0 ? 0u : (uint32_t)((r0 + 15) >> 4); // first vector starting inside the entry
-                if (fv < NV) s_vec[fv] = (uint16_t)j;
-            }
-            copy_bar();
-            { // inclusive max-scan of the marks: s_vec[v] = entry that holds byte 16*v of the tile
-                uint32_t mk[VPT];
-                uint32_t run = 0;
-#pragma unroll
-                for (int k = 0; k < VPT; k++) {
-                    uint32_t x = s_vec[tid * VPT + k];
-                    run = x > run ? x : run;
-                    mk[k] = run;
-                }
-                uint32_t incl = run;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                    if (lane >= (uint32_t)o) incl = t > incl ? t : incl;
-                }
-                if (lane == 31) s_wmax[warp] = incl;
-                copy_bar();
-                uint32_t before = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
-                if (lane == 0) before = 0;
-                for (uint32_t w = 0; w < warp; w++) before = s_wmax[w] > before ? s_wmax[w] : before;
-#pragma unroll
-                for (int k = 0; k < VPT; k++) s_vec[tid * VPT + k] = (uint16_t)(mk[k] > before ? mk[k] : before);
-            }
-            copy_bar();
-            uint8_t *dst_tile = p.out_data + T0;
-            uint4 A[VPT], B[VPT];
-            uint32_t sh[VPT];
-            bool pure[VPT];
-#pragma unroll
-            for (int k = 0; k < VPT; k++) {
-                const uint32_t v = tid + k * kGatherCopyThreads;
-                const uint32_t b0 = v * 16;
-                pure[k] = false;
-                sh[k] = 0;
-                if (b0 + 16 <= tile_len) {
-                    const uint32_t j = s_vec[v];
-                    if ((int)(b0 + 16) <= m.r1[j]) {
-                        const uintptr_t sa = (uintptr_t)(m.adj[j] + b0);
-                        sh[k] = (uint32_t)(sa & 15);
-                        const uint4 *sv = reinterpret_cast<const uint4 *>(sa - sh[k]);
-                        A[k] = __ldg(sv);
-                        B[k] = __ldg(sh[k] ? sv + 1 : sv);
-                        pure[k] = true;
-                    }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < VPT; k++) {
-                const uint32_t v = tid + k * kGatherCopyThreads;
-                if (pure[k]) reinterpret_cast<uint4 *>(dst_tile)[v] = realign16_sel(A[k], B[k], sh[k]);
-            }
-            // vectors that straddle an entry boundary: one per entry, handled densely (see k_gather)
-            for (uint32_t j = tid; j < ne; j += kGatherCopyThreads) {
-                const int r1 = m.r1[j];
-                if (r1 <= 0 || (r1 & 15) == 0 || r1 > (int)tile_len) continue;
-                const uint32_t v = (uint32_t)r1 >> 4;
-                const uint32_t b0 = v * 16;
-                const uint32_t t = (uint32_t)r1 - b0; // tail bytes of entry j in this vector: 1..15
-                const uintptr_t sa = (uintptr_t)(m.adj[j] + b0);
-                const uint32_t s0 = (uint32_t)(sa & 15);
-                const uint4 *sv = reinterpret_cast<const uint4 *>(sa - s0);
-                const uint4 TA = __ldg(sv);
-                const uint4 TB = __ldg(s0 + t > 16 ? sv + 1 : sv);
-                uint4 o = realign16_sel(TA, TB, s0);
-                if (b0 + 16 <= tile_len) {
-                    const uintptr_t ha = (uintptr_t)(m.adj[j + 1] + (unsigned long long)m.r0[j + 1]); // first byte of entry j+1
-                    const uint32_t hs = (uint32_t)(ha & 15);
-                    const uint4 *hv = reinterpret_cast<const uint4 *>(ha - hs);
-                    const uint4 HA = __ldg(hv);
-                    const uint4 HB = __ldg(hs ? hv + 1 : hv);
-                    const uint4 H = realign16_sel(HA, HB, hs);
-                    const uint4 HU = realign16_sel(make_uint4(0, 0, 0, 0), H, 16 - t);
-                    const uint32_t wfull = t >> 2, bits = (t & 3) * 8;
-                    const uint32_t mmix = bits ? (0xFFFFFFFFu >> (32 - bits)) : 0u;
-                    uint32_t ow[4] = {o.x, o.y, o.z, o.w}, hw[4] = {HU.x, HU.y, HU.z, HU.w};
-#pragma unroll
-                    for (uint32_t w = 0; w < 4; w++) {
-                        const uint32_t mk = w < wfull ? 0xFFFFFFFFu : (w == wfull ? mmix : 0u);
-                        ow[w] = (ow[w] & mk) | (hw[w] & ~mk);
-                    }
-                    reinterpret_cast<uint4 *>(dst_tile)[v] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-                } else { // ragged end of the whole stream: never write past out_data_len
-                    const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
-                    for (uint32_t b = 0; b < t; b++) dst_tile[b0 + b] = (uint8_t)(ow[b >> 2] >> ((b & 3) * 8));
-                }
-            }
-        }
-        __syncthreads(); // tile q done everywhere; tile q+1's entry list and tile q+2's range are in place
-        if (!has_next) break;
-    }
-}
-
-// ------------------------------------------------------------------------------------
-// K5 (warp-tile variant): every WARP owns a 2 KB tile of the output stream (128 vectors, 4 per
-// lane) and works alone -- its entry list lives in a warp-private slice of shared memory, the
-// vector -> entry lookup is a short binary search over the (sorted) entry ends, and nothing
-// ever waits on a block-wide barrier, so 40 warps per SM each keep 8 independent 16-byte
-// loads in flight.  Bloom bits are set by k_emit in this configuration.
-
-constexpr int kWarpTileVecs = 128;
-constexpr unsigned long long kWarpTileBytes = 16ull * kWarpTileVecs;  // 2 KB
-constexpr int kWarpTileMaxEntries = (int)(kWarpTileBytes / 32) + 2;  // 66
-constexpr int kGatherWarpThreads = 256;
-
-__global__ void __launch_bounds__(kGatherWarpThreads) k_gather_warp(Params p) {
-    constexpr int WPB = kGatherWarpThreads / 32;
-    constexpr int VPL = kWarpTileVecs / 32; // vectors per lane
-    __shared__ unsigned long long s_adj[WPB][kWarpTileMaxEntries];
-    __shared__ int s_r1[WPB][kWarpTileMaxEntries];
-    __shared__ int s_r0[WPB][kWarpTileMaxEntries];
-    const Ctl *c = p.ctl;
-    const unsigned long long out_len = c->out_data_len;
-    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const unsigned long long tile = (unsigned long long)blockIdx.x * WPB + w;
-    const unsigned long long T0 = tile * kWarpTileBytes;
-    if (T0 >= out_len) return; // whole warp
-    const uint32_t tile_len = out_len - T0 < kWarpTileBytes ? (uint32_t)(out_len - T0) : (uint32_t)kWarpTileBytes;
-    const uint32_t e_lo = p.tile_first[tile];
-    const uint32_t e_hi = T0 + kWarpTileBytes < out_len ? p.tile_first[tile + 1] : c->out_items - 1;
-    const uint32_t ne = e_hi - e_lo + 1; // <= kWarpTileMaxEntries: every entry is >= 32 bytes
-    unsigned long long *adj = s_adj[w];
-    int *r1s = s_r1[w], *r0s = s_r0[w];
-    for (uint32_t j = lane; j < ne; j += 32) {
-        const uint4 rec = p.out_index[e_lo + j];
-        const unsigned long long d0 = ((unsigned long long)rec.x | ((unsigned long long)rec.y << 32)) - p.out_offset_base;
-        const long long r0 = (long long)d0 - (long long)T0; // < 0 only for the tile's first entry
-        const long long r1 = r0 + (long long)rec.w;
-        adj[j] = p.src_ptr[e_lo + j] - (unsigned long long)r0;
-        r0s[j] = r0 < -0x7FFFFFFFll ? -0x7FFFFFFF : (int)r0;
-        r1s[j] = r1 > 0x7FFFFFFFll ? 0x7FFFFFFF : (int)r1;
-    }
-    __syncwarp();
-    uint32_t steps = 0;
-    while ((1u << steps) < ne) steps++; // binary-search depth, uniform across the warp
-
-    uint8_t *dst_tile = p.out_data + T0;
-    uint4 A[VPL], B[VPL];
-    uint32_t sh[VPL];
-    bool pure[VPL];
-#pragma unroll
-    for (int k = 0; k < VPL; k++) {
-        const uint32_t v = lane + 32 * k;
-        const int b0 = (int)(v * 16);
-        pure[k] = false;
-        sh[k] = 0;
-        if ((uint32_t)b0 + 16 <= tile_len) {
-            // entry holding byte b0: the first j with r1[j] > b0 (ends are ascending)
-            uint32_t lo = 0;
-            for (uint32_t st = steps; st-- > 0;) {
-                const uint32_t mid = lo + (1u << st);
-                if (mid < ne && r1s[mid - 1] <= b0) lo = mid;
-            }
-            if (b0 + 16 <= r1s[lo]) {
-                const uintptr_t sa = (uintptr_t)(adj[lo] + (unsigned long long)b0);
-                sh[k] = (uint32_t)(sa & 15);
-                const uint4 *sv = reinterpret_cast<const uint4 *>(sa - sh[k]);
-                A[k] = __ldg(sv);
-                B[k] = __ldg(sh[k] ? sv + 1 : sv);
-                pure[k] = true;
-            }
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < VPL; k++) {
-        const uint32_t v = lane + 32 * k;
-        if (pure[k]) reinterpret_cast<uint4 *>(dst_tile)[v] = realign16_sel(A[k], B[k], sh[k]);
-    }
-    // the vector that holds the last byte of entry j: tail of j blended with the head of j+1
-    for (uint32_t j = lane; j < ne; j += 32) {
-        const int r1 = r1s[j];
-        if (r1 <= 0 || (r1 & 15) == 0 || r1 > (int)tile_len) continue;
-        const uint32_t v = (uint32_t)r1 >> 4;
-        const uint32_t b0 = v * 16;
-        const uint32_t t = (uint32_t)r1 - b0; // tail bytes of entry j in this vector: 1..15
-        const uintptr_t sa = (uintptr_t)(adj[j] + b0);
-        const uint32_t s0 = (uint32_t)(sa & 15);
-        const uint4 *sv = reinterpret_cast<const uint4 *>(sa - s0);
-        const uint4 TA = __ldg(sv);
-        const uint4 TB = __ldg(s0 + t > 16 ? sv + 1 : sv);
-        uint4 o = realign16_sel(TA, TB, s0);
-        if (b0 + 16 <= tile_len) {
-            const uintptr_t ha = (uintptr_t)(adj[j + 1] + (unsigned long long)(long long)r0s[j + 1]); // first byte of entry j+1 (r0 >= 0)
-            const uint32_t hs = (uint32_t)(ha & 15);
-            const uint4 *hv = reinterpret_cast<const uint4 *>(ha - hs);
-            const uint4 HA = __ldg(hv);
-            const uint4 HB = __ldg(hs ? hv + 1 : hv);
-            const uint4 H = realign16_sel(HA, HB, hs);
-            const uint4 HU = realign16_sel(make_uint4(0, 0, 0, 0), H, 16 - t);
-            const uint32_t wfull = t >> 2, bits = (t & 3) * 8;
-            const uint32_t mmix = bits ? (0xFFFFFFFFu >> (32 - bits)) : 0u;
-            uint32_t ow[4] = {o.x, o.y, o.z, o.w}, hw[4] = {HU.x, HU.y, HU.z, HU.w};
-#pragma unroll
-            for (uint32_t q = 0; q < 4; q++) {
-                const uint32_t mk = q < wfull ? 0xFFFFFFFFu : (q == wfull ? mmix : 0u);
-                ow[q] = (ow[q] & mk) | (hw[q] & ~mk);
-            }
-            reinterpret_cast<uint4 *>(dst_tile)[v] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-        } else { // ragged end of the whole stream: never write past out_data_len
-            const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
-            for (uint32_t b = 0; b < t; b++) dst_tile[b0 + b] = (uint8_t)(ow[b >> 2] >> ((b & 3) * 8));
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------
-// K5 (hybrid variant): 16 KB CTA tiles like k_gather -- one staging pass, ONE block barrier,
-// dense (thread-per-entry) straddle and bloom passes -- but the copy itself is done warp by
-// warp on 2 KB sub-tiles with no mark/scan phase: a warp finds the entry under its first byte
-// with one binary search and then walks the (sorted) entry ends incrementally, 512 bytes at a
-// time, each lane counting how many entries end at or before its own vector.
-
-template <int kMap, int kMinBlocks>
-__global__ void __launch_bounds__(kGatherThreads, kMinBlocks) k_gather_hybrid(Params p) {
+__global__ void __launch_bounds__(kGatherThreads, 6) k_gather(Params p) {
     constexpr int NT = kGatherThreads;
     constexpr int VPT = kGatherVecsPerThread;
     __shared__ unsigned long long s_adj[kGatherMaxEntries]; // entry address minus its tile-relative start
@@ -1645,18 +1070,9 @@ __global__ void __launch_bounds__(kGatherThreads, kMinBlocks) k_gather_hybrid(Pa
     if ((uint32_t)sub0 < tile_len) {
         // j = the entry that holds byte sub0 = number of entries ending at or before it (ends ascend).
         uint32_t j = 0;
-        if (kMap == 1) { // ballot-count 32 entries at a time; the last entry never counts
-            for (uint32_t base = 0; base + 1 < ne; base += 32) {
-                const uint32_t i = base + lane;
-                j += __popc(__ballot_sync(0xFFFFFFFFu, i + 1 < ne && s_r1[i] <= sub0));
-            }
-        } else { // warp-uniform binary search
-            uint32_t lo = 0, hi = ne - 1;
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (s_r1[mid] <= sub0) lo = mid + 1; else hi = mid;
-            }
-            j = lo;
+        for (uint32_t base = 0; base + 1 < ne; base += 32) { // ballot-count 32 entries at a time; the last entry never counts
+            const uint32_t i = base + lane;
+            j += __popc(__ballot_sync(0xFFFFFFFFu, i + 1 < ne && s_r1[i] <= sub0));
         }
         uint4 A[VPT], B[VPT];
         uint32_t sh[VPT];
@@ -1666,27 +1082,16 @@ __global__ void __launch_bounds__(kGatherThreads, kMinBlocks) k_gather_hybrid(Pa
         for (int k = 0; k < VPT; k++) {
             const int cb = sub0 + k * 512; // this 512-byte chunk: one vector per lane
             const int b0 = cb + (int)lane * 16;
-            uint32_t cnt, adv;
-            if (kMap == 1) {
-                // Entries that end inside the chunk, i.e. in (cb, cb + 512]: at most 17 (entries are >= 32 bytes),
-                // lane l looks at entry j + l.  An end at r1 precedes the vectors t = ceil((r1 - cb) / 16) .. 31,
-                // and distinct entries have distinct t, so one OR-reduction builds the whole chunk's map.
-                const uint32_t i = j + lane;
-                const int r1 = i + 1 < ne ? s_r1[i] : 0x7FFFFFFF;
-                const bool ends_here = r1 <= cb + 512;
-                const uint32_t t = (uint32_t)((ends_here ? r1 : cb + 16) - cb + 15) >> 4; // 1..32 when ends_here
-                const uint32_t ends = __reduce_or_sync(0xFFFFFFFFu, (ends_here && t < 32) ? (1u << t) : 0u);
-                cnt = __popc(ends & lanes_le); // entries ending at or before my vector's first byte
-                adv = __popc(__ballot_sync(0xFFFFFFFFu, ends_here));
-            } else {
-                cnt = 0;
-                uint32_t i = j;
-                while (i + 1 < ne && s_r1[i] <= cb + 512) { // entries that end inside the chunk (warp-uniform loop)
-                    cnt += s_r1[i] <= b0 ? 1u : 0u;
-                    i++;
-                }
-                adv = i - j;
-            }
+            // Entries that end inside the chunk, i.e. in (cb, cb + 512]: at most 17 (entries are >= 32 bytes),
+            // lane l looks at entry j + l.  An end at r1 precedes the vectors t = ceil((r1 - cb) / 16) .. 31,
+            // and distinct entries have distinct t, so one OR-reduction builds the whole chunk's map.
+            const uint32_t i = j + lane;
+            const int r1 = i + 1 < ne ? s_r1[i] : 0x7FFFFFFF;
+            const bool ends_here = r1 <= cb + 512;
+            const uint32_t t = (uint32_t)((ends_here ? r1 : cb + 16) - cb + 15) >> 4; // 1..32 when ends_here
+            const uint32_t ends = __reduce_or_sync(0xFFFFFFFFu, (ends_here && t < 32) ? (1u << t) : 0u);
+            const uint32_t cnt = __popc(ends & lanes_le); // entries ending at or before my vector's first byte
+            const uint32_t adv = __popc(__ballot_sync(0xFFFFFFFFu, ends_here));
             const uint32_t e = j + cnt; // entry that holds byte b0
             j += adv;                   // entry that holds the next chunk's first byte
             pure[k] = false;
@@ -1744,7 +1149,7 @@ __global__ void __launch_bounds__(kGatherThreads, kMinBlocks) k_gather_hybrid(Pa
     }
 
     // ---- bloom (fused epilogue): entries whose first byte lies in this tile
-    if (p.bloom.words != nullptr && !p.bloom_in_emit) {
+    if (p.bloom.words != nullptr) {
         for (uint32_t j = tid; j < ne; j += NT) {
             const int r0 = s_r0[j];
             if (r0 < 0 || r0 >= (int)kGatherTileBytes) continue;

@@ -107,6 +107,8 @@ typedef struct dbeel_stats {
     float ms_gather;           /* .data gather + bloom (the roofline kernel)               */
     float ms_h2d, ms_d2h;      /* host entry points only                                   */
     uint64_t gather_bytes;     /* algorithmic bytes of the gather kernel (read + written)  */
+    uint32_t partitions;       /* host entry points: key-range partitions pipelined (1 = single shot) */
+    uint32_t reserved;
 } dbeel_stats;
 
 typedef struct dbeel_engine dbeel_engine;
