@@ -135,8 +135,10 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------ workload
 
-def shard_config(rank: int, world: int):
+def shard_config(rank: int, world: int, workload: str = "cfg2"):
     from dbeel_b200 import workloads as W
+    if workload == "cfg3":  # BASELINE.json configs[2]: not the headline, kept for cross-checks
+        return W.CFG3
     if world == 1:
         return W.CFG2
     return W.cfg4_shard(rank)
@@ -190,7 +192,7 @@ def run_gpu(args):
     mine = sj.hand_off(table, dev)
     assert len(mine) == 1 and mine[0].shard_id == rank, mine
 
-    cfg = shard_config(rank, world)
+    cfg = shard_config(rank, world, args.workload)
     t = time.time()
     runs = make_runs_parallel(cfg)
     in_bytes = sstable.input_bytes(runs)
@@ -366,8 +368,10 @@ def run_reference(args):
     t = time.perf_counter()
     oracle.compact(probe, False, seed=SEED32, emulate_page_cache=True)
     mbps_1 = sstable.input_bytes(probe) / 1e6 / (time.perf_counter() - t)
-    budget_s = min(4.0, 150.0 / max(1, steps + warm))
-    keys = int(max(20_000, min(1_000_000, budget_s * mbps_1 * 1e6 / (8 * 321.0) * 0.6)))
+    budget_s = min(2.0, 120.0 / max(1, steps + warm))
+    # bounded sample: at most 60k keys per run (154 MB per shard) so that `threads` concurrent compactions and
+    # their outputs stay within a few tens of GB of RAM whatever the core count
+    keys = int(max(10_000, min(60_000, budget_s * mbps_1 * 1e6 / (8 * 321.0) * 0.6)))
     distinct = [W.make_merge_runs(W.scaled(W.cfg4_shard(i), keys)) for i in range(min(threads, 8))]
     shards = [distinct[i % len(distinct)] for i in range(threads)]  # inputs are read-only: threads may share them
     in_bytes = sum(sstable.input_bytes(s) for s in shards)
@@ -410,6 +414,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="dbeel_b200", choices=["dbeel_b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"], help="cfg2 is BASELINE.json's headline config")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -2,17 +2,9 @@
 set -u
 mkdir -p gpurun_out
 nvidia-smi -L
-echo "=== pytest -m gpu (full)"
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -6
-echo "=== bench (default)"
-timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
+echo "=== pytest -m gpu (full, durations)"
+timeout 900 python -m pytest tests -m gpu -q --durations=5 2>&1 | tail -14
+echo "=== tune"
+timeout 600 python tools/tune.py "" DBEEL_MERGE=0 DBEEL_NARROW=0 2>&1 | tail -4
 echo "=== bench reference arm"
-timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -2 gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json
-echo "=== ncu launch list"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
-grep -c . gpurun_out/launches.csv
-echo "=== ncu full"
-timeout 1500 ncu --set full --clock-control none --import-source on -k 'regex:k_gather|k_merge_tma|k_resolve|k_extract|k_emit' -s 18 -c 7 \
-    -f -o gpurun_out/prof_full python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/bench_under_ncu_full.log 2>&1
-ls -la gpurun_out/
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -2 | cut -c1-900

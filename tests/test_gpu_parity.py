@@ -302,3 +302,41 @@ def test_pipelined_path_falls_back_on_corrupt_input(tiny_partition_engine):
     bad[16 * 2000 + 12] += 1  # undecodable record in the middle of run b: everything after it is dropped
     check_against_oracle(eng, [a, (b[0], bad)], False, what="pipelined corrupt")
     assert eng.stats()["runs_truncated"] == 1
+
+
+def test_flush_large_zipf_batch(engine):
+    """cfg5-shaped arrivals: Zipf-skewed key ids, 512-byte docs, enough writes for a dozen sort tiles and
+    four merge levels; cut into memtables of 8192 distinct keys exactly like set_ex would (lsm_tree.rs:757-765)."""
+    from dbeel_b200 import storage_engine as se
+    batch = W.make_arrival_batch(n_writes=30_000, n_ids=20_000, doc_bytes=512, seed=5)
+    ents = sstable.parse_run(*batch)
+    expected = oracle.memtable_flushes(batch, capacity=8192)
+    pos = 0
+    for od, oi, on in expected:
+        n = se.memtable_cut(batch, pos, 8192)
+        sub = sstable.build_run(ents[pos:pos + n])
+        gd, gi, gn = engine.flush(sub)
+        assert gn == on
+        assert_run_equal((gd, gi), (od, oi), f"memtable at arrival {pos}")
+        pos += n
+    assert pos == len(ents) and len(expected) >= 2
+    st = engine.stats()
+    assert st["merge_passes"] >= 1
+
+
+def test_flush_device_entry_point(engine):
+    import torch
+    rng = np.random.default_rng(77)
+    writes = [(b"\xb0k%015d" % int(rng.integers(0, 3000)), bytes(rng.integers(0, 256, 64, dtype=np.uint8)), BASE_TS + s)
+              for s in range(9000)]
+    batch = sstable.build_run(writes)
+    dev = torch.device("cuda:0")
+    d, i = torch.from_numpy(batch[0]).to(dev), torch.from_numpy(batch[1]).to(dev)
+    od = torch.empty(d.numel() + 16, dtype=torch.uint8, device=dev)
+    oi = torch.empty(i.numel() + 16, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    dl, il, n = engine.flush_device((d.data_ptr(), d.numel(), i.data_ptr(), i.numel()), (od.data_ptr(), d.numel(), oi.data_ptr(), i.numel()))
+    (ed, ei, en), = oracle.memtable_flushes(batch, capacity=1 << 20)
+    assert n == en
+    assert_run_equal((od[:dl].cpu().numpy(), oi[:il].cpu().numpy()), (ed, ei), "flush_device")
+    assert engine.stats()["key_prefix_len"] >= 12  # the prefix reduction over ALL arrivals found '\xb0k' + zero digits

@@ -169,3 +169,44 @@ def test_compact_tree_writes_bloom_file(engine, tmp_path):
     bloom = np.fromfile(os.path.join(d, sstable.file_name(1, "bloom")), dtype=np.uint8)
     assert np.array_equal(bloom, ob)
     assert sorted(os.listdir(d)) == [sstable.file_name(1, e) for e in ("bloom", "data", "index")]
+
+
+@pytest.mark.gpu
+def test_cfg5_pipeline_flush_then_tiered_compactions(engine, tmp_path):
+    """BASELINE.json configs[4] in miniature: a Zipf write stream is cut into memtables (distinct-key capacity),
+    every memtable is flushed to the next even index, and after every flush the size-tiered picker runs
+    (tasks/compaction.rs:104-137).  The recorded plan is replayed on the CPU oracle; every file that is left
+    must match byte for byte."""
+    d = str(tmp_path)
+    cap, factor = 2048, 4
+    batch = W_arrivals = __import__("dbeel_b200.workloads", fromlist=["x"]).make_arrival_batch(
+        n_writes=40_000, n_ids=24_000, doc_bytes=100, seed=55)
+    ents = sstable.parse_run(*batch)
+    flushed = oracle.memtable_flushes(batch, capacity=cap)
+    tree = se.LSMTree(d, engine, sstable_bloom_min_size=200_000)
+    model = {}  # index -> (data, index, bloom|None) as the oracle would have them
+    pos = 0
+    n_compactions = 0
+    for od, oi, on in flushed:
+        n = se.memtable_cut(batch, pos, cap)
+        idx, items = tree.flush(sstable.build_run(ents[pos:pos + n]))
+        assert items == on
+        model[idx] = (od, oi, None)
+        pos += n
+        for indices, out_idx, keep in tree.compact_tree(compaction_factor=factor, bloom_seed=SEED):
+            runs = [(model[i][0], model[i][1]) for i in indices]
+            cd, ci, cb, cn = oracle.compact(runs, keep, bloom_min_size=200_000, seed=SEED)
+            for i in indices:
+                del model[i]
+            model[out_idx] = (cd, ci, cb)
+            n_compactions += 1
+    assert pos == len(ents) and n_compactions >= 3
+    assert [i for i, _ in tree.sstable_indices_and_sizes()] == sorted(model)
+    for i, (md, mi, mb) in model.items():
+        assert_run_equal(sstable.read_run_files(d, i), (md, mi), f"sstable {i}")
+        bloom_path = os.path.join(d, sstable.file_name(i, "bloom"))
+        assert os.path.exists(bloom_path) == (mb is not None)
+        if mb is not None:
+            assert np.array_equal(np.fromfile(bloom_path, dtype=np.uint8), mb)
+    # nothing but live SSTable files is left behind (journals and compact_* temporaries are gone)
+    assert all(f.split(".")[1] in ("data", "index", "bloom") for f in os.listdir(d))
