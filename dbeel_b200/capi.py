@@ -24,7 +24,8 @@ DEFAULT_BLOOM_MIN_SIZE = 1_048_576
 DEFAULT_BLOOM_FP = 0.01
 
 EXPORTS = ["dbeel_abi_version", "dbeel_engine_create", "dbeel_engine_destroy", "dbeel_compact_bound",
-           "dbeel_compact", "dbeel_compact_device", "dbeel_flush", "dbeel_flush_device",
+           "dbeel_compact", "dbeel_compact_device", "dbeel_compact_submit", "dbeel_poll", "dbeel_wait",
+           "dbeel_flush", "dbeel_flush_device",
            "dbeel_bloom_bitmap_bytes", "dbeel_bloom_k_num", "dbeel_bloom_file_size", "dbeel_host_alloc",
            "dbeel_host_free", "dbeel_last_stats", "dbeel_last_error", "dbeel_strerror"]
 
@@ -85,6 +86,12 @@ def lib():
             f = getattr(L, name)
             f.restype = C.c_int
             f.argtypes = [C.c_void_p, C.POINTER(Run), C.c_uint32, C.POINTER(Opts), C.POINTER(Out)]
+        L.dbeel_compact_submit.restype = C.c_int
+        L.dbeel_compact_submit.argtypes = [C.c_void_p, C.POINTER(Run), C.c_uint32, C.POINTER(Opts), C.POINTER(Out)]
+        L.dbeel_poll.restype = C.c_int
+        L.dbeel_poll.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        L.dbeel_wait.restype = C.c_int
+        L.dbeel_wait.argtypes = [C.c_void_p]
         for name in ("dbeel_flush", "dbeel_flush_device"):
             f = getattr(L, name)
             f.restype = C.c_int
@@ -208,6 +215,35 @@ class Engine:
         self._check(lib().dbeel_compact(self._h, arr, len(keep), C.byref(opts), C.byref(out)), "dbeel_compact")
         bloom = ob[:out.bloom_len] if out.bloom_len else None
         return od[:out.data_len], oi[:out.index_len], bloom, int(out.items_written)
+
+    def compact_async(self, runs: Sequence[Tuple[object, object]], keep_tombstones: bool = False,
+                      bloom_min_size: int = DEFAULT_BLOOM_MIN_SIZE, seed: Optional[bytes] = None):
+        """dbeel_compact_submit: returns a callable `reap(block)` -> None while running, else the result tuple."""
+        keep = [(_u8(d), _u8(i)) for d, i in runs]
+        arr = (Run * max(1, len(keep)))()
+        for j, (d, i) in enumerate(keep):
+            arr[j] = Run(d.ctypes.data, d.size, i.ctypes.data, i.size)
+        opts = make_opts(keep_tombstones, bloom_min_size, DEFAULT_BLOOM_FP, seed, 0)
+        dc, ic, bc = compact_bound([(d.size, i.size) for d, i in keep], opts)
+        od, oi, ob = np.empty(max(1, dc), np.uint8), np.empty(max(1, ic), np.uint8), np.empty(max(1, bc), np.uint8)
+        out = Out(od.ctypes.data, dc, 0, oi.ctypes.data, ic, 0, ob.ctypes.data if bc else None, bc, 0, 0)
+        self._check(lib().dbeel_compact_submit(self._h, arr, len(keep), C.byref(opts), C.byref(out)), "dbeel_compact_submit")
+        alive = (keep, arr, opts, out, od, oi, ob)  # everything the job points at stays referenced by the closure
+
+        def reap(block: bool = False):
+            if block:
+                rc = lib().dbeel_wait(self._h)
+            else:
+                st = C.c_int(0)
+                if not lib().dbeel_poll(self._h, C.byref(st)):
+                    return None
+                rc = st.value
+            self._check(rc, "dbeel_compact (async)")
+            o = alive[3]
+            bloom = ob[:o.bloom_len] if o.bloom_len else None
+            return od[:o.data_len], oi[:o.index_len], bloom, int(o.items_written)
+
+        return reap
 
     def flush(self, batch: Tuple[object, object]):
         """dbeel_flush: returns (data, index, items_written)."""

@@ -11,7 +11,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <new>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -53,6 +55,13 @@ struct dbeel_engine {
     dbeel_stats stats = {};
     std::string err;
     bool busy = false;
+    // asynchronous jobs (dbeel_compact_submit)
+    std::thread worker;
+    std::atomic<int> async_state{0}; // 0 idle, 1 running, 2 finished (status in async_status)
+    int async_status = 0;
+    std::vector<dbeel_run> async_runs;
+    dbeel_compact_opts async_opts = {};
+    uint8_t async_seed[32] = {};
     int sm_count = 148;
     int merge_variant = 1;      // DBEEL_MERGE: 0 = one CTA per tile with plain loads, 1 = persistent TMA (default)
     int narrow_loads = 1;       // DBEEL_NARROW: .L2::64B loads for random accesses in extract / resolve (A/B switch)
@@ -808,6 +817,7 @@ int dbeel_engine_create(int device, dbeel_engine **out) {
 
 void dbeel_engine_destroy(dbeel_engine *e) {
     if (!e) return;
+    if (e->worker.joinable()) e->worker.join();
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (int i = 0; i < EV_COUNT; i++)
@@ -862,21 +872,67 @@ int dbeel_compact_bound(const dbeel_run *runs, uint32_t n_runs, const dbeel_comp
     return DBEEL_OK;
 }
 
+#define REFUSE_WHILE_ASYNC(e)                                                                  \
+    if ((e) && (e)->async_state.load(std::memory_order_acquire) != 0) return fail((e), DBEEL_ERR_BUSY, "an asynchronous job is in flight")
+
 int dbeel_compact(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, const dbeel_compact_opts *opts,
                   dbeel_out *out) {
+    REFUSE_WHILE_ASYNC(e);
     return entry(e, runs, n_runs, opts, out, false, false);
 }
 
 int dbeel_compact_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, const dbeel_compact_opts *opts,
                          dbeel_out *out) {
+    REFUSE_WHILE_ASYNC(e);
     return entry(e, runs, n_runs, opts, out, false, true);
 }
 
+int dbeel_compact_submit(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, const dbeel_compact_opts *opts,
+                         dbeel_out *out) {
+    if (!e) return DBEEL_ERR_INVALID_ARG;
+    if (!out || (n_runs && !runs)) return fail(e, DBEEL_ERR_INVALID_ARG, "null argument");
+    int expected = 0;
+    if (!e->async_state.compare_exchange_strong(expected, 1)) return fail(e, DBEEL_ERR_BUSY, "engine busy");
+    if (e->worker.joinable()) e->worker.join();
+    e->async_runs.assign(runs, runs + n_runs); // the descriptors are copied; the buffers they point to are not
+    default_opts(&e->async_opts);
+    if (opts) e->async_opts = *opts;
+    if (e->async_opts.bloom_seed) {
+        memcpy(e->async_seed, e->async_opts.bloom_seed, 32);
+        e->async_opts.bloom_seed = e->async_seed;
+    }
+    e->worker = std::thread([e, out]() {
+        e->async_status = entry(e, e->async_runs.data(), (uint32_t)e->async_runs.size(), &e->async_opts, out, false, false);
+        e->async_state.store(2, std::memory_order_release);
+    });
+    return DBEEL_OK;
+}
+
+int dbeel_poll(dbeel_engine *e, int *status) {
+    if (!e) return 0;
+    if (e->async_state.load(std::memory_order_acquire) != 2) return 0;
+    if (e->worker.joinable()) e->worker.join();
+    if (status) *status = e->async_status;
+    e->async_state.store(0, std::memory_order_release);
+    return 1;
+}
+
+int dbeel_wait(dbeel_engine *e) {
+    if (!e) return DBEEL_ERR_INVALID_ARG;
+    if (e->async_state.load(std::memory_order_acquire) == 0) return fail(e, DBEEL_ERR_INVALID_ARG, "no job in flight");
+    if (e->worker.joinable()) e->worker.join();
+    const int st = e->async_status;
+    e->async_state.store(0, std::memory_order_release);
+    return st;
+}
+
 int dbeel_flush(dbeel_engine *e, const dbeel_run *batch, dbeel_out *out) {
+    REFUSE_WHILE_ASYNC(e);
     return entry(e, batch, batch ? 1 : 0, nullptr, out, true, false);
 }
 
 int dbeel_flush_device(dbeel_engine *e, const dbeel_run *batch, dbeel_out *out) {
+    REFUSE_WHILE_ASYNC(e);
     return entry(e, batch, batch ? 1 : 0, nullptr, out, true, true);
 }
 

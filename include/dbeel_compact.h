@@ -140,6 +140,16 @@ int dbeel_compact_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs
 int dbeel_flush(dbeel_engine *e, const dbeel_run *batch, dbeel_out *out);
 int dbeel_flush_device(dbeel_engine *e, const dbeel_run *batch, dbeel_out *out);
 
+/* Asynchronous form of dbeel_compact for callers that must not block their reactor (dbeel's
+ * compaction task runs on a glommio executor, src/tasks/compaction.rs:139-153): submit returns at
+ * once, the job runs on an engine-owned worker thread, poll / wait report its status.  All
+ * buffers (runs, the 32-byte seed, out) must stay valid until the job has been reaped by a
+ * dbeel_wait() or a dbeel_poll() that returned 1.  One job per engine at a time (DBEEL_ERR_BUSY). */
+int dbeel_compact_submit(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs,
+                         const dbeel_compact_opts *opts, dbeel_out *out);
+int dbeel_poll(dbeel_engine *e, int *status); /* returns 1 when finished (then *status = the job's code), else 0 */
+int dbeel_wait(dbeel_engine *e);              /* blocks; returns the job's status code */
+
 /* Bloom::new_for_fp_rate arithmetic (bloomfilter 1.0.12). */
 uint64_t dbeel_bloom_bitmap_bytes(uint64_t items, double fp);
 uint32_t dbeel_bloom_k_num(uint64_t bitmap_bits, uint64_t items);

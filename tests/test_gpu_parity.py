@@ -340,3 +340,26 @@ def test_flush_device_entry_point(engine):
     assert n == en
     assert_run_equal((od[:dl].cpu().numpy(), oi[:il].cpu().numpy()), (ed, ei), "flush_device")
     assert engine.stats()["key_prefix_len"] >= 12  # the prefix reduction over ALL arrivals found '\xb0k' + zero digits
+
+
+def test_async_submit_poll_wait(engine):
+    """dbeel_compact_submit / dbeel_poll / dbeel_wait: the non-blocking form a reactor-driven caller uses."""
+    import time
+    runs = W.make_merge_runs(W.scaled(W.CFG2, 20_000))
+    reap = engine.compact_async(runs, False, seed=SEED)
+    with pytest.raises(capi.DbeelError) as ei:  # one job per engine
+        engine.compact(runs, False, seed=SEED)
+    assert ei.value.code == 10
+    res = None
+    deadline = time.time() + 60
+    while res is None and time.time() < deadline:
+        res = reap(False)
+        time.sleep(0.001)
+    assert res is not None
+    od, oi, ob, on = oracle.compact(runs, False, seed=SEED)
+    assert res[3] == on
+    assert_run_equal((res[0], res[1]), (od, oi), "async")
+    assert np.array_equal(res[2], ob)
+    reap2 = engine.compact_async(runs, True, seed=SEED)
+    r2 = reap2(True)  # blocking wait
+    assert r2[3] == oracle.compact(runs, True, seed=SEED)[3]
