@@ -306,14 +306,14 @@ def test_pipelined_path_falls_back_on_corrupt_input(tiny_partition_engine):
 
 def test_flush_large_zipf_batch(engine):
     """cfg5-shaped arrivals: Zipf-skewed key ids, 512-byte docs, enough writes for a dozen sort tiles and
-    four merge levels; cut into memtables of 8192 distinct keys exactly like set_ex would (lsm_tree.rs:757-765)."""
+    four merge levels; cut into memtables of 3000 distinct keys exactly like set_ex would (lsm_tree.rs:757-765)."""
     from dbeel_b200 import storage_engine as se
     batch = W.make_arrival_batch(n_writes=30_000, n_ids=20_000, doc_bytes=512, seed=5)
     ents = sstable.parse_run(*batch)
-    expected = oracle.memtable_flushes(batch, capacity=8192)
+    expected = oracle.memtable_flushes(batch, capacity=3000)
     pos = 0
     for od, oi, on in expected:
-        n = se.memtable_cut(batch, pos, 8192)
+        n = se.memtable_cut(batch, pos, 3000)
         sub = sstable.build_run(ents[pos:pos + n])
         gd, gi, gn = engine.flush(sub)
         assert gn == on

@@ -200,7 +200,7 @@ def test_cfg5_pipeline_flush_then_tiered_compactions(engine, tmp_path):
                 del model[i]
             model[out_idx] = (cd, ci, cb)
             n_compactions += 1
-    assert pos == len(ents) and n_compactions >= 3
+    assert pos == len(ents) and n_compactions >= 2
     assert [i for i, _ in tree.sstable_indices_and_sizes()] == sorted(model)
     for i, (md, mi, mb) in model.items():
         assert_run_equal(sstable.read_run_files(d, i), (md, mi), f"sstable {i}")
