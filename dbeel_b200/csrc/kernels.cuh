@@ -1108,16 +1108,17 @@ __global__ void __launch_bounds__(kGatherThreads, 6) k_gather(Params p) {
             const uint32_t adv = __popc(__ballot_sync(0xFFFFFFFFu, ends_here));
             const uint32_t e = j + cnt; // entry that holds byte b0
             j += adv;                   // entry that holds the next chunk's first byte
-            pure[k] = false;
-            sh[k] = 0;
-            if ((uint32_t)b0 + 16 <= tile_len && b0 + 16 <= s_r1[e]) {
-                const uintptr_t sa = (uintptr_t)(s_adj[e] + (unsigned long long)b0);
-                sh[k] = (uint32_t)(sa & 15);
-                const uint4 *sv = reinterpret_cast<const uint4 *>(sa - sh[k]);
-                A[k] = __ldg(sv);
-                B[k] = __ldg(sh[k] ? sv + 1 : sv);
-                pure[k] = true;
-            }
+            // Loads are unconditional (no divergent branch around them): a vector that is not wholly inside
+            // entry e -- it straddles e's end, or lies past the end of the stream -- reads the last full vector
+            // of e instead (always valid memory: entries are >= 32 bytes) and simply is not stored.
+            const int r1e = s_r1[e];
+            pure[k] = (uint32_t)b0 + 16 <= tile_len && b0 + 16 <= r1e;
+            const int bl = b0 + 16 <= r1e ? b0 : r1e - 16;
+            const uintptr_t sa = (uintptr_t)(s_adj[e] + (unsigned long long)(long long)bl);
+            sh[k] = (uint32_t)(sa & 15);
+            const uint4 *sv = reinterpret_cast<const uint4 *>(sa - sh[k]);
+            A[k] = __ldg(sv);
+            B[k] = __ldg(sh[k] ? sv + 1 : sv);
         }
 #pragma unroll
         for (int k = 0; k < VPT; k++) {

@@ -363,3 +363,45 @@ def test_async_submit_poll_wait(engine):
     reap2 = engine.compact_async(runs, True, seed=SEED)
     r2 = reap2(True)  # blocking wait
     assert r2[3] == oracle.compact(runs, True, seed=SEED)[3]
+
+
+def test_large_and_tiny_entries_mixed(engine):
+    """Entry sizes from 32 bytes (empty key, tombstone) to ~64 KB (the reference's practical request cap,
+    db_server.rs:399-403): gather tiles that hold hundreds of entries next to entries that span several tiles."""
+    rng = np.random.default_rng(41)
+    sizes = [0, 1, 15, 16, 17, 31, 32, 33, 255, 4095, 4096, 4097, 16383, 16384, 16385, 40000, 65000]
+    runs = []
+    for r in range(3):
+        ents = []
+        for n in range(400):
+            k = b"key-%05d" % (3 * n + r % 2)
+            dl = sizes[int(rng.integers(len(sizes)))]
+            ents.append((k, bytes(rng.integers(0, 256, dl, dtype=np.uint8)), BASE_TS + r))
+        if r == 0:
+            ents.append((b"", b"", BASE_TS))  # 32-byte entry: empty key, tombstone
+        runs.append(sstable.build_run(sorted(ents)))
+    check_against_oracle(engine, runs, True, bloom_min_size=1000, what="mixed sizes keep")
+    check_against_oracle(engine, runs, False, bloom_min_size=1000, what="mixed sizes drop")
+
+
+def test_three_hundred_small_runs(engine):
+    rng = np.random.default_rng(43)
+    pool = [b"\xb0k%015d" % n for n in range(5000)]
+    runs = random_runs(rng, 300, [int(rng.integers(0, 40)) for _ in range(300)], pool, max_doc=30)
+    gd, gi, _, n = check_against_oracle(engine, runs, False, what="300 runs")
+    assert engine.stats()["merge_passes"] == 9
+    exp, en = model_compact(runs, False)
+    assert_run_equal((gd, gi), exp, "300 runs vs model")
+
+
+def test_common_prefix_longer_than_the_cap(engine):
+    """Keys sharing 400 bytes: the skipped prefix is capped at 255, the 11-byte window sits inside the shared
+    part, every comparison ties on it and goes through the full byte compare."""
+    rng = np.random.default_rng(44)
+    stem = bytes(rng.integers(1, 255, 400, dtype=np.uint8))
+    pool = sorted({stem + bytes(rng.integers(0, 256, int(rng.integers(0, 12)), dtype=np.uint8)) for _ in range(600)})
+    runs = random_runs(rng, 4, 250, pool, max_doc=40)
+    gd, gi, _, _ = check_against_oracle(engine, runs, True, bloom_min_size=1000, what="long prefix")
+    assert engine.stats()["key_prefix_len"] == 255
+    exp, _ = model_compact(runs, True)
+    assert_run_equal((gd, gi), exp, "long prefix vs model")
