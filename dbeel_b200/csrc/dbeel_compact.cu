@@ -359,7 +359,7 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     launches += 4;
     CU(cudaEventRecord(e->ev[EV_RESOLVE], s));
 
-    // ---- K5: gather (+ bloom in the CTA-tile variants)
+    // ---- K5: gather + bloom (fused epilogue)
     if (gather_tiles) {
         k_gather<<<(uint32_t)gather_tiles, kGatherThreads, 0, s>>>(p);
     }

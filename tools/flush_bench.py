@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Memtable-flush throughput on one GPU (BASELINE.json configs[4] shape: Zipf(0.99) writes, 512-byte docs,
+memtables of 8192 distinct keys): device-resident dbeel_flush_device per memtable vs the CPU oracle's
+red-black-tree replay + flush_memtable_to_disk.  Usage: tools/flush_bench.py [n_writes]"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import oracle  # noqa: E402
+from dbeel_b200 import capi, sstable, storage_engine as se  # noqa: E402
+from dbeel_b200 import workloads as W  # noqa: E402
+
+
+def main():
+    n_writes = int(sys.argv[1]) if len(sys.argv) > 1 else 400_000
+    batch = W.make_arrival_batch(n_writes=n_writes, n_ids=n_writes // 4, doc_bytes=512, seed=5)
+    nbytes = batch[0].size + batch[1].size
+    # memtable boundaries (host logic, dbeel_memtable_cut)
+    cuts, pos = [], 0
+    while pos < n_writes:
+        n = se.memtable_cut(batch, pos, 8192)
+        cuts.append((pos, n))
+        pos += n
+    idx = batch[1].view("<u8").reshape(-1, 2)[:, 0]
+    dev = torch.device("cuda:0")
+    eng = capi.Engine(0)
+    subs = []
+    for p0, n in cuts:  # each memtable's arrivals as its own batch (offsets restart at 0)
+        lo = int(idx[p0])
+        hi = int(idx[p0 + n]) if p0 + n < n_writes else batch[0].size
+        d = batch[0][lo:hi]
+        ix = batch[1][16 * p0:16 * (p0 + n)].copy()
+        ix.view("<u8").reshape(-1, 2)[:, 0] -= lo
+        subs.append((torch.from_numpy(d.copy()).to(dev), torch.from_numpy(ix).to(dev)))
+    cap_d = max(d.numel() for d, _ in subs) + 16
+    cap_i = max(i.numel() for _, i in subs) + 16
+    od = torch.empty(cap_d, dtype=torch.uint8, device=dev)
+    oi = torch.empty(cap_i, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    def run_all():
+        tot_ms, items = 0.0, 0
+        for d, i in subs:
+            _, _, n = eng.flush_device((d.data_ptr(), d.numel(), i.data_ptr(), i.numel()), (od.data_ptr(), d.numel(), oi.data_ptr(), i.numel()))
+            tot_ms += eng.stats()["ms_total"]
+            items += n
+        return tot_ms, items
+
+    run_all()
+    t0 = time.perf_counter()
+    dev_ms, items = run_all()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    flushed = oracle.memtable_flushes(batch, capacity=8192, emulate_page_cache=True)
+    cpu = time.perf_counter() - t0
+    assert sum(n for _, _, n in flushed) == items
+    print(f"{len(cuts)} memtables, {nbytes / 1e6:.0f} MB of arrivals, {items} entries flushed")
+    print(f"GPU device-resident: {dev_ms:.2f} ms in kernels ({nbytes / 1e6 / dev_ms * 1e3:.0f} MB/s), {wall * 1e3:.1f} ms wall "
+          f"({nbytes / 1e6 / wall:.0f} MB/s incl. launches + control-block read-back per memtable)")
+    print(f"CPU oracle (rb-tree inserts + flush, 1 core): {cpu * 1e3:.0f} ms ({nbytes / 1e6 / cpu:.0f} MB/s)")
+
+
+if __name__ == "__main__":
+    main()
