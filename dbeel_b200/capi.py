@@ -10,7 +10,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdbeel_compact.so")
+LIB_PATH = os.environ.get("DBEEL_LIB") or os.path.join(_HERE, "libdbeel_compact.so")  # DBEEL_LIB: A/B builds only
 
 DBEEL_OK = 0
 ERR_NAMES = {1: "INVALID_ARG", 2: "CAPACITY", 3: "ITEM_TOO_LARGE", 4: "CUDA", 5: "NOMEM", 6: "TOO_MANY_RUNS",

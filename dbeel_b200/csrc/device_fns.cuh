@@ -161,6 +161,21 @@ DB_HD uint64_t bloom_hash_i(uint64_t h0, uint64_t h1, uint32_t i) {
     return g >= kBloomPrime ? g - kBloomPrime : g; // prime > 2^63: at most one subtraction
 }
 
+// All k bit positions of one key, g_i computed incrementally: (h0 + i*h1) mod 2^64 is a running wrapping sum,
+// so no per-probe multiply.  set_bit(bit) is called k_num times, in the order Bloom::set sets them.
+template <class SetBit>
+DB_HD void bloom_probe_all(uint64_t h0, uint64_t h1, uint32_t k_num, uint64_t bits, uint64_t bits_magic, SetBit set_bit) {
+    set_bit(fastmod(h0, bits, bits_magic));
+    if (k_num < 2) return;
+    set_bit(fastmod(h1, bits, bits_magic));
+    uint64_t acc = h0 + h1; // h0 + 1*h1
+    for (uint32_t i = 2; i < k_num; i++) {
+        acc += h1; // h0 + i*h1, wrapping
+        const uint64_t g = acc >= kBloomPrime ? acc - kBloomPrime : acc;
+        set_bit(fastmod(g, bits, bits_magic));
+    }
+}
+
 // ------------------------------------------------------------------------------------
 // Byte realignment for the gather kernel: 16 output bytes starting `sh` bytes into the
 // 32-byte window {A, B} (A = lower-address 16 bytes).  sh in [0, 15]; B unused if sh == 0.

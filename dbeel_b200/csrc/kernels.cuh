@@ -48,8 +48,14 @@ struct Ctl {
 constexpr int kMergeThreads = 256;
 constexpr int kMergeVT = 7; // odd: threads walk smem at a 112-byte stride -> no bank conflicts
 constexpr int kMergeTile = kMergeThreads * kMergeVT; // 1792 records = 28 KB of smem
-constexpr int kResolveThreads = 256;
-constexpr int kGatherThreads = 256;
+#ifndef DBEEL_RESOLVE_THREADS
+#define DBEEL_RESOLVE_THREADS 256
+#endif
+constexpr int kResolveThreads = DBEEL_RESOLVE_THREADS;
+#ifndef DBEEL_GATHER_THREADS
+#define DBEEL_GATHER_THREADS 128
+#endif
+constexpr int kGatherThreads = DBEEL_GATHER_THREADS; // 128 threads = 8 KB tiles at 12 CTAs/SM (measured: 64..512 threads -> see DESIGN.md)
 constexpr int kGatherVecsPerThread = 4;
 constexpr unsigned long long kGatherTileBytes = 16ull * kGatherThreads * kGatherVecsPerThread; // 16 KB of output per CTA
 constexpr int kGatherMaxEntries = (int)(kGatherTileBytes / 32) + 2; // entries are >= 32 bytes
@@ -279,10 +285,16 @@ __global__ void k_common_prefix(Params p, int validated) {
 // bincode-decodes with no trailing bytes (klen/dlen prefixes agree with key_size/full_size).
 // The first invalid entry ends its run (lsm_tree.rs:1014,1063): first_bad[r] = min index.
 
-constexpr int kExtractEPT = 2; // entries per thread = independent load chains in flight per thread
+#ifndef DBEEL_EXTRACT_EPT
+#define DBEEL_EXTRACT_EPT 2
+#endif
+#ifndef DBEEL_EXTRACT_MINB
+#define DBEEL_EXTRACT_MINB 4
+#endif
+constexpr int kExtractEPT = DBEEL_EXTRACT_EPT; // entries per thread = independent load chains in flight per thread
 
 template <bool kNarrow>
-__global__ void __launch_bounds__(256, 4) k_extract(Params p, int redo) {
+__global__ void __launch_bounds__(256, DBEEL_EXTRACT_MINB) k_extract(Params p, int redo) {
     auto ldu = [](const uint8_t *q) { return kNarrow ? ld_u64_unaligned_narrow(q) : ld_u64_unaligned(q); };
     Ctl *c = p.ctl;
     if (redo && !(c->flags & kFlagTruncated)) return;
@@ -1051,7 +1063,7 @@ __device__ __forceinline__ uint4 realign16_sel(uint4 A, uint4 B, uint32_t sh) {
 // and then walks the (sorted) entry ends 512 bytes at a time, each lane counting how many entries
 // end at or before its own vector (one OR-reduction + popcount per chunk).
 
-__global__ void __launch_bounds__(kGatherThreads, 6) k_gather(Params p) {
+__global__ void __launch_bounds__(kGatherThreads, 1536 / kGatherThreads) k_gather(Params p) {
     constexpr int NT = kGatherThreads;
     constexpr int VPT = kGatherVecsPerThread;
     __shared__ unsigned long long s_adj[kGatherMaxEntries]; // entry address minus its tile-relative start
@@ -1078,8 +1090,11 @@ __global__ void __launch_bounds__(kGatherThreads, 6) k_gather(Params p) {
     }
     __syncthreads();
 
-    // ---- copy: warp w owns bytes [w * 2 KB, (w + 1) * 2 KB) of the tile
+    // ---- copy: warp w owns bytes [w * 2 KB, (w + 1) * 2 KB) of the tile; a lane produces 32-byte blocks
+    // (two output vectors from three aligned source vectors), so the entry lookup, the address arithmetic and
+    // one of the loads are shared by two vectors
     uint8_t *dst_tile = p.out_data + T0;
+    constexpr int BPT = VPT / 2; // 32-byte blocks per lane
     const int sub0 = (int)(warp * (uint32_t)(32 * VPT * 16));
     if ((uint32_t)sub0 < tile_len) {
         // j = the entry that holds byte sub0 = number of entries ending at or before it (ends ascend).
@@ -1088,78 +1103,96 @@ __global__ void __launch_bounds__(kGatherThreads, 6) k_gather(Params p) {
             const uint32_t i = base + lane;
             j += __popc(__ballot_sync(0xFFFFFFFFu, i + 1 < ne && s_r1[i] <= sub0));
         }
-        uint4 A[VPT], B[VPT];
-        uint32_t sh[VPT];
-        bool pure[VPT];
+        uint4 A[BPT], B[BPT], Cv[BPT];
+        uint32_t sh[BPT];
+        bool pure[BPT];
         const uint32_t lanes_le = 0xFFFFFFFFu >> (31 - lane); // bits 0..lane
 #pragma unroll
-        for (int k = 0; k < VPT; k++) {
-            const int cb = sub0 + k * 512; // this 512-byte chunk: one vector per lane
-            const int b0 = cb + (int)lane * 16;
-            // Entries that end inside the chunk, i.e. in (cb, cb + 512]: at most 17 (entries are >= 32 bytes),
-            // lane l looks at entry j + l.  An end at r1 precedes the vectors t = ceil((r1 - cb) / 16) .. 31,
+        for (int k = 0; k < BPT; k++) {
+            const int cb = sub0 + k * 1024; // this 1 KB chunk: one 32-byte block per lane
+            const int b0 = cb + (int)lane * 32;
+            // Entries that end inside the chunk, i.e. in (cb, cb + 1024]: at most 32 (entries are >= 32 bytes),
+            // lane l looks at entry j + l.  An end at r1 precedes the blocks t = ceil((r1 - cb) / 32) .. 31,
             // and distinct entries have distinct t, so one OR-reduction builds the whole chunk's map.
             const uint32_t i = j + lane;
             const int r1 = i + 1 < ne ? s_r1[i] : 0x7FFFFFFF;
-            const bool ends_here = r1 <= cb + 512;
-            const uint32_t t = (uint32_t)((ends_here ? r1 : cb + 16) - cb + 15) >> 4; // 1..32 when ends_here
+            const bool ends_here = r1 <= cb + 1024;
+            const uint32_t t = (uint32_t)((ends_here ? r1 : cb + 32) - cb + 31) >> 5; // 1..32 when ends_here
             const uint32_t ends = __reduce_or_sync(0xFFFFFFFFu, (ends_here && t < 32) ? (1u << t) : 0u);
-            const uint32_t cnt = __popc(ends & lanes_le); // entries ending at or before my vector's first byte
+            const uint32_t cnt = __popc(ends & lanes_le); // entries ending at or before my block's first byte
             const uint32_t adv = __popc(__ballot_sync(0xFFFFFFFFu, ends_here));
             const uint32_t e = j + cnt; // entry that holds byte b0
             j += adv;                   // entry that holds the next chunk's first byte
-            // Loads are unconditional (no divergent branch around them): a vector that is not wholly inside
-            // entry e -- it straddles e's end, or lies past the end of the stream -- reads the last full vector
-            // of e instead (always valid memory: entries are >= 32 bytes) and simply is not stored.
+            // Loads are unconditional (no divergent branch around them): a block that is not wholly inside
+            // entry e -- it holds e's end, or lies past the end of the stream -- reads the last 32 bytes of e
+            // instead (always valid memory: entries are >= 32 bytes) and simply is not stored.
             const int r1e = s_r1[e];
-            pure[k] = (uint32_t)b0 + 16 <= tile_len && b0 + 16 <= r1e;
-            const int bl = b0 + 16 <= r1e ? b0 : r1e - 16;
+            pure[k] = (uint32_t)b0 + 32 <= tile_len && b0 + 32 <= r1e;
+            const int bl = b0 + 32 <= r1e ? b0 : r1e - 32;
             const uintptr_t sa = (uintptr_t)(s_adj[e] + (unsigned long long)(long long)bl);
             sh[k] = (uint32_t)(sa & 15);
             const uint4 *sv = reinterpret_cast<const uint4 *>(sa - sh[k]);
             A[k] = __ldg(sv);
-            B[k] = __ldg(sh[k] ? sv + 1 : sv);
+            B[k] = __ldg(sv + 1);
+            Cv[k] = __ldg(sh[k] ? sv + 2 : sv + 1);
         }
 #pragma unroll
-        for (int k = 0; k < VPT; k++) {
-            const uint32_t v = (uint32_t)(sub0 >> 4) + (uint32_t)k * 32 + lane;
-            if (pure[k]) reinterpret_cast<uint4 *>(dst_tile)[v] = realign16_sel(A[k], B[k], sh[k]);
+        for (int k = 0; k < BPT; k++) {
+            const uint32_t v = ((uint32_t)(sub0 >> 5) + (uint32_t)k * 32 + lane) * 2;
+            if (pure[k]) {
+                reinterpret_cast<uint4 *>(dst_tile)[v] = realign16_sel(A[k], B[k], sh[k]);
+                reinterpret_cast<uint4 *>(dst_tile)[v + 1] = realign16_sel(B[k], Cv[k], sh[k]);
+            }
         }
     }
 
-    // ---- the vector that holds the last byte of entry j: tail of j blended with the head of j+1
+    // ---- the 32-byte block that holds the last byte of entry j (dense: one thread per entry).  Its two
+    // vectors are each either wholly inside j, wholly inside j+1, or the tail of j blended with the head of j+1.
     for (uint32_t j = tid; j < ne; j += NT) {
         const int r1 = s_r1[j];
-        if (r1 <= 0 || (r1 & 15) == 0 || r1 > (int)tile_len) continue;
-        const uint32_t v = (uint32_t)r1 >> 4;
-        const uint32_t b0 = v * 16;
-        const uint32_t t = (uint32_t)r1 - b0; // tail bytes of entry j in this vector: 1..15
-        const uintptr_t sa = (uintptr_t)(s_adj[j] + b0);
-        const uint32_t s0 = (uint32_t)(sa & 15);
-        const uint4 *sv = reinterpret_cast<const uint4 *>(sa - s0);
-        const uint4 TA = __ldg(sv);
-        const uint4 TB = __ldg(s0 + t > 16 ? sv + 1 : sv);
-        uint4 o = realign16_sel(TA, TB, s0);
-        if (b0 + 16 <= tile_len) {
-            const uintptr_t ha = (uintptr_t)(s_adj[j + 1] + (unsigned long long)(long long)s_r0[j + 1]); // first byte of entry j+1
-            const uint32_t hs = (uint32_t)(ha & 15);
-            const uint4 *hv = reinterpret_cast<const uint4 *>(ha - hs);
-            const uint4 HA = __ldg(hv);
-            const uint4 HB = __ldg(hs ? hv + 1 : hv);
-            const uint4 H = realign16_sel(HA, HB, hs);
-            const uint4 HU = realign16_sel(make_uint4(0, 0, 0, 0), H, 16 - t);
-            const uint32_t wfull = t >> 2, bits = (t & 3) * 8;
-            const uint32_t mmix = bits ? (0xFFFFFFFFu >> (32 - bits)) : 0u;
-            uint32_t ow[4] = {o.x, o.y, o.z, o.w}, hw[4] = {HU.x, HU.y, HU.z, HU.w};
+        if (r1 <= 0 || (r1 & 31) == 0 || r1 > (int)tile_len) continue; // ends outside the tile, or on a block edge
+        const uint32_t blk = (uint32_t)(r1 - 1) >> 5;
 #pragma unroll
-            for (uint32_t q = 0; q < 4; q++) {
-                const uint32_t mk = q < wfull ? 0xFFFFFFFFu : (q == wfull ? mmix : 0u);
-                ow[q] = (ow[q] & mk) | (hw[q] & ~mk);
+        for (uint32_t half = 0; half < 2; half++) {
+            const uint32_t v = 2 * blk + half;
+            const uint32_t b0 = v * 16;
+            if (b0 >= tile_len) continue; // past the end of the stream
+            if ((int)(b0 + 16) <= r1 || (int)b0 >= r1) { // wholly inside entry j, or wholly inside entry j+1
+                const uint32_t src_e = (int)b0 >= r1 ? j + 1 : j;
+                const uintptr_t sa = (uintptr_t)(s_adj[src_e] + b0);
+                const uint32_t s0 = (uint32_t)(sa & 15);
+                const uint4 *sv = reinterpret_cast<const uint4 *>(sa - s0);
+                reinterpret_cast<uint4 *>(dst_tile)[v] = realign16_sel(__ldg(sv), __ldg(s0 ? sv + 1 : sv), s0);
+                continue;
             }
-            reinterpret_cast<uint4 *>(dst_tile)[v] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-        } else { // ragged end of the whole stream: never write past out_data_len
-            const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
-            for (uint32_t b = 0; b < t; b++) dst_tile[b0 + b] = (uint8_t)(ow[b >> 2] >> ((b & 3) * 8));
+            const uint32_t t = (uint32_t)r1 - b0; // tail bytes of entry j in this vector: 1..15
+            const uintptr_t sa = (uintptr_t)(s_adj[j] + b0);
+            const uint32_t s0 = (uint32_t)(sa & 15);
+            const uint4 *sv = reinterpret_cast<const uint4 *>(sa - s0);
+            const uint4 TA = __ldg(sv);
+            const uint4 TB = __ldg(s0 + t > 16 ? sv + 1 : sv);
+            uint4 o = realign16_sel(TA, TB, s0);
+            if (b0 + 16 <= tile_len) {
+                const uintptr_t ha = (uintptr_t)(s_adj[j + 1] + (unsigned long long)(long long)s_r0[j + 1]); // first byte of entry j+1
+                const uint32_t hs = (uint32_t)(ha & 15);
+                const uint4 *hv = reinterpret_cast<const uint4 *>(ha - hs);
+                const uint4 HA = __ldg(hv);
+                const uint4 HB = __ldg(hs ? hv + 1 : hv);
+                const uint4 H = realign16_sel(HA, HB, hs);
+                const uint4 HU = realign16_sel(make_uint4(0, 0, 0, 0), H, 16 - t);
+                const uint32_t wfull = t >> 2, bits = (t & 3) * 8;
+                const uint32_t mmix = bits ? (0xFFFFFFFFu >> (32 - bits)) : 0u;
+                uint32_t ow[4] = {o.x, o.y, o.z, o.w}, hw[4] = {HU.x, HU.y, HU.z, HU.w};
+#pragma unroll
+                for (uint32_t q = 0; q < 4; q++) {
+                    const uint32_t mk = q < wfull ? 0xFFFFFFFFu : (q == wfull ? mmix : 0u);
+                    ow[q] = (ow[q] & mk) | (hw[q] & ~mk);
+                }
+                reinterpret_cast<uint4 *>(dst_tile)[v] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            } else { // ragged end of the whole stream: never write past out_data_len
+                const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+                for (uint32_t b = 0; b < t; b++) dst_tile[b0 + b] = (uint8_t)(ow[b >> 2] >> ((b & 3) * 8));
+            }
         }
     }
 
@@ -1172,10 +1205,9 @@ __global__ void __launch_bounds__(kGatherThreads, 6) k_gather(Params p) {
             const uint64_t klen = s_ks[j] - 8;
             uint64_t h0, h1;
             sip13_pair_vec_u8(p.bloom.sip, klen, [key](uint64_t q) { return ld_u64_unaligned(key + 8 * q); }, &h0, &h1);
-            for (uint32_t k = 0; k < p.bloom.k_num; k++) {
-                uint64_t bit = fastmod(bloom_hash_i(h0, h1, k), p.bloom.bits, p.bloom.bits_magic);
-                atomicOr(&p.bloom.words[bit >> 5], 1u << (bit & 31));
-            }
+            uint32_t *words = p.bloom.words;
+            bloom_probe_all(h0, h1, p.bloom.k_num, p.bloom.bits, p.bloom.bits_magic,
+                            [words](uint64_t bit) { atomicOr(&words[bit >> 5], 1u << (bit & 31)); });
         }
     }
 }

@@ -40,6 +40,13 @@ uint64_t shim_fastmod(uint64_t h, uint64_t d) {
 
 uint64_t shim_bloom_hash_i(uint64_t h0, uint64_t h1, uint32_t i) { return bloom_hash_i(h0, h1, i); }
 
+uint32_t shim_bloom_probe_all(uint64_t h0, uint64_t h1, uint32_t k_num, uint64_t bits, uint64_t *out) {
+    uint32_t n = 0;
+    const uint64_t magic = (uint64_t)((((unsigned __int128)1) << 64) / bits);
+    bloom_probe_all(h0, h1, k_num, bits, magic, [&](uint64_t bit) { out[n++] = bit; });
+    return n;
+}
+
 void shim_realign16(const uint8_t src32[32], uint32_t sh, uint8_t out16[16]) {
     uint32_t A[4], B[4], O[4];
     memcpy(A, src32, 16);

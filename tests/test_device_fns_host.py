@@ -30,6 +30,8 @@ def shim():
     L.shim_fastmod.argtypes = [C.c_uint64, C.c_uint64]
     L.shim_bloom_hash_i.restype = C.c_uint64
     L.shim_bloom_hash_i.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
+    L.shim_bloom_probe_all.restype = C.c_uint32
+    L.shim_bloom_probe_all.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64)]
     L.shim_make_rec.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
     L.shim_rec_cmp.restype = C.c_int
     L.shim_rec_cmp.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
@@ -96,6 +98,15 @@ def test_fastmod_and_double_hashing(shim):
         for i in range(0, 9):
             exp = h0 if i == 0 else h1 if i == 1 else ((h0 + i * h1) & ((1 << 64) - 1)) % P
             assert shim.shim_bloom_hash_i(h0, h1, i) == exp
+    out = (C.c_uint64 * 16)()
+    for _ in range(300):  # the incremental form used by the kernel == bloomfilter's (h0 + i*h1) % prime % bits
+        h0, h1 = (int(x) for x in rng.integers(0, 1 << 64, 2, dtype=np.uint64))
+        if _ % 3 == 0:
+            h1 = (1 << 64) - int(rng.integers(1, 1000))  # wrap-around heavy
+        for k, bits in [(7, 76_680_472), (1, 8), (2, 24), (13, (1 << 40) + 8)]:
+            n = shim.shim_bloom_probe_all(h0, h1, k, bits, out)
+            exp = [(h0 if i == 0 else h1 if i == 1 else ((h0 + i * h1) & ((1 << 64) - 1)) % P) % bits for i in range(k)]
+            assert n == k and [out[i] for i in range(k)] == exp
     assert shim.shim_bloom_hash_i(P, 0, 2) == 0 and shim.shim_bloom_hash_i((1 << 64) - 1, 0, 5) == ((1 << 64) - 1) % P
 
 

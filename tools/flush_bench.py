@@ -57,13 +57,38 @@ def main():
     dev_ms, items = run_all()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
+
+    # several engines on the same GPU, one per host thread (= several shards sharing a GPU): small jobs overlap
+    import threading
+    def many_engines(T):
+        engs = [capi.Engine(0) for _ in range(T)]
+        outs = [(torch.empty(cap_d, dtype=torch.uint8, device=dev), torch.empty(cap_i, dtype=torch.uint8, device=dev)) for _ in range(T)]
+        torch.cuda.synchronize()
+        def work(t):
+            for k in range(t, len(subs), T):
+                d, i = subs[k]
+                engs[t].flush_device((d.data_ptr(), d.numel(), i.data_ptr(), i.numel()),
+                                     (outs[t][0].data_ptr(), d.numel(), outs[t][1].data_ptr(), i.numel()))
+        for rep in range(2):
+            ths = [threading.Thread(target=work, args=(t,)) for t in range(T)]
+            t1 = time.perf_counter()
+            for th in ths: th.start()
+            for th in ths: th.join()
+            torch.cuda.synchronize()
+            el = time.perf_counter() - t1
+        for e in engs: e.close()
+        return el
+
     t0 = time.perf_counter()
     flushed = oracle.memtable_flushes(batch, capacity=8192, emulate_page_cache=True)
     cpu = time.perf_counter() - t0
     assert sum(n for _, _, n in flushed) == items
     print(f"{len(cuts)} memtables, {nbytes / 1e6:.0f} MB of arrivals, {items} entries flushed")
-    print(f"GPU device-resident: {dev_ms:.2f} ms in kernels ({nbytes / 1e6 / dev_ms * 1e3:.0f} MB/s), {wall * 1e3:.1f} ms wall "
+    print(f"GPU device-resident, 1 engine: {dev_ms:.2f} ms in kernels ({nbytes / 1e6 / dev_ms * 1e3:.0f} MB/s), {wall * 1e3:.1f} ms wall "
           f"({nbytes / 1e6 / wall:.0f} MB/s incl. launches + control-block read-back per memtable)")
+    for T in (2, 4, 8):
+        el = many_engines(T)
+        print(f"GPU device-resident, {T} engines / host threads on one GPU: {el * 1e3:.1f} ms wall ({nbytes / 1e6 / el:.0f} MB/s)")
     print(f"CPU oracle (rb-tree inserts + flush, 1 core): {cpu * 1e3:.0f} ms ({nbytes / 1e6 / cpu:.0f} MB/s)")
 
 
