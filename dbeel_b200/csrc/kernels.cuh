@@ -1090,11 +1090,8 @@ __global__ void __launch_bounds__(kGatherThreads, 1536 / kGatherThreads) k_gathe
     }
     __syncthreads();
 
-    // ---- copy: warp w owns bytes [w * 2 KB, (w + 1) * 2 KB) of the tile; a lane produces 32-byte blocks
-    // (two output vectors from three aligned source vectors), so the entry lookup, the address arithmetic and
-    // one of the loads are shared by two vectors
+    // ---- copy: warp w owns bytes [w * 2 KB, (w + 1) * 2 KB) of the tile
     uint8_t *dst_tile = p.out_data + T0;
-    constexpr int BPT = VPT / 2; // 32-byte blocks per lane
     const int sub0 = (int)(warp * (uint32_t)(32 * VPT * 16));
     if ((uint32_t)sub0 < tile_len) {
         // j = the entry that holds byte sub0 = number of entries ending at or before it (ends ascend).
@@ -1103,96 +1100,78 @@ __global__ void __launch_bounds__(kGatherThreads, 1536 / kGatherThreads) k_gathe
             const uint32_t i = base + lane;
             j += __popc(__ballot_sync(0xFFFFFFFFu, i + 1 < ne && s_r1[i] <= sub0));
         }
-        uint4 A[BPT], B[BPT], Cv[BPT];
-        uint32_t sh[BPT];
-        bool pure[BPT];
+        uint4 A[VPT], B[VPT];
+        uint32_t sh[VPT];
+        bool pure[VPT];
         const uint32_t lanes_le = 0xFFFFFFFFu >> (31 - lane); // bits 0..lane
 #pragma unroll
-        for (int k = 0; k < BPT; k++) {
-            const int cb = sub0 + k * 1024; // this 1 KB chunk: one 32-byte block per lane
-            const int b0 = cb + (int)lane * 32;
-            // Entries that end inside the chunk, i.e. in (cb, cb + 1024]: at most 32 (entries are >= 32 bytes),
-            // lane l looks at entry j + l.  An end at r1 precedes the blocks t = ceil((r1 - cb) / 32) .. 31,
+        for (int k = 0; k < VPT; k++) {
+            const int cb = sub0 + k * 512; // this 512-byte chunk: one vector per lane
+            const int b0 = cb + (int)lane * 16;
+            // Entries that end inside the chunk, i.e. in (cb, cb + 512]: at most 17 (entries are >= 32 bytes),
+            // lane l looks at entry j + l.  An end at r1 precedes the vectors t = ceil((r1 - cb) / 16) .. 31,
             // and distinct entries have distinct t, so one OR-reduction builds the whole chunk's map.
             const uint32_t i = j + lane;
             const int r1 = i + 1 < ne ? s_r1[i] : 0x7FFFFFFF;
-            const bool ends_here = r1 <= cb + 1024;
-            const uint32_t t = (uint32_t)((ends_here ? r1 : cb + 32) - cb + 31) >> 5; // 1..32 when ends_here
+            const bool ends_here = r1 <= cb + 512;
+            const uint32_t t = (uint32_t)((ends_here ? r1 : cb + 16) - cb + 15) >> 4; // 1..32 when ends_here
             const uint32_t ends = __reduce_or_sync(0xFFFFFFFFu, (ends_here && t < 32) ? (1u << t) : 0u);
-            const uint32_t cnt = __popc(ends & lanes_le); // entries ending at or before my block's first byte
+            const uint32_t cnt = __popc(ends & lanes_le); // entries ending at or before my vector's first byte
             const uint32_t adv = __popc(__ballot_sync(0xFFFFFFFFu, ends_here));
             const uint32_t e = j + cnt; // entry that holds byte b0
             j += adv;                   // entry that holds the next chunk's first byte
-            // Loads are unconditional (no divergent branch around them): a block that is not wholly inside
-            // entry e -- it holds e's end, or lies past the end of the stream -- reads the last 32 bytes of e
-            // instead (always valid memory: entries are >= 32 bytes) and simply is not stored.
+            // Loads are unconditional (no divergent branch around them): a vector that is not wholly inside
+            // entry e -- it straddles e's end, or lies past the end of the stream -- reads the last full vector
+            // of e instead (always valid memory: entries are >= 32 bytes) and simply is not stored.
             const int r1e = s_r1[e];
-            pure[k] = (uint32_t)b0 + 32 <= tile_len && b0 + 32 <= r1e;
-            const int bl = b0 + 32 <= r1e ? b0 : r1e - 32;
+            pure[k] = (uint32_t)b0 + 16 <= tile_len && b0 + 16 <= r1e;
+            const int bl = b0 + 16 <= r1e ? b0 : r1e - 16;
             const uintptr_t sa = (uintptr_t)(s_adj[e] + (unsigned long long)(long long)bl);
             sh[k] = (uint32_t)(sa & 15);
             const uint4 *sv = reinterpret_cast<const uint4 *>(sa - sh[k]);
             A[k] = __ldg(sv);
-            B[k] = __ldg(sv + 1);
-            Cv[k] = __ldg(sh[k] ? sv + 2 : sv + 1);
+            B[k] = __ldg(sh[k] ? sv + 1 : sv);
         }
 #pragma unroll
-        for (int k = 0; k < BPT; k++) {
-            const uint32_t v = ((uint32_t)(sub0 >> 5) + (uint32_t)k * 32 + lane) * 2;
-            if (pure[k]) {
-                reinterpret_cast<uint4 *>(dst_tile)[v] = realign16_sel(A[k], B[k], sh[k]);
-                reinterpret_cast<uint4 *>(dst_tile)[v + 1] = realign16_sel(B[k], Cv[k], sh[k]);
-            }
+        for (int k = 0; k < VPT; k++) {
+            const uint32_t v = (uint32_t)(sub0 >> 4) + (uint32_t)k * 32 + lane;
+            if (pure[k]) reinterpret_cast<uint4 *>(dst_tile)[v] = realign16_sel(A[k], B[k], sh[k]);
         }
     }
 
-    // ---- the 32-byte block that holds the last byte of entry j (dense: one thread per entry).  Its two
-    // vectors are each either wholly inside j, wholly inside j+1, or the tail of j blended with the head of j+1.
+    // ---- the vector that holds the last byte of entry j: tail of j blended with the head of j+1
     for (uint32_t j = tid; j < ne; j += NT) {
         const int r1 = s_r1[j];
-        if (r1 <= 0 || (r1 & 31) == 0 || r1 > (int)tile_len) continue; // ends outside the tile, or on a block edge
-        const uint32_t blk = (uint32_t)(r1 - 1) >> 5;
+        if (r1 <= 0 || (r1 & 15) == 0 || r1 > (int)tile_len) continue;
+        const uint32_t v = (uint32_t)r1 >> 4;
+        const uint32_t b0 = v * 16;
+        const uint32_t t = (uint32_t)r1 - b0; // tail bytes of entry j in this vector: 1..15
+        const uintptr_t sa = (uintptr_t)(s_adj[j] + b0);
+        const uint32_t s0 = (uint32_t)(sa & 15);
+        const uint4 *sv = reinterpret_cast<const uint4 *>(sa - s0);
+        const uint4 TA = __ldg(sv);
+        const uint4 TB = __ldg(s0 + t > 16 ? sv + 1 : sv);
+        uint4 o = realign16_sel(TA, TB, s0);
+        if (b0 + 16 <= tile_len) {
+            const uintptr_t ha = (uintptr_t)(s_adj[j + 1] + (unsigned long long)(long long)s_r0[j + 1]); // first byte of entry j+1
+            const uint32_t hs = (uint32_t)(ha & 15);
+            const uint4 *hv = reinterpret_cast<const uint4 *>(ha - hs);
+            const uint4 HA = __ldg(hv);
+            const uint4 HB = __ldg(hs ? hv + 1 : hv);
+            const uint4 H = realign16_sel(HA, HB, hs);
+            const uint4 HU = realign16_sel(make_uint4(0, 0, 0, 0), H, 16 - t);
+            const uint32_t wfull = t >> 2, bits = (t & 3) * 8;
+            const uint32_t mmix = bits ? (0xFFFFFFFFu >> (32 - bits)) : 0u;
+            uint32_t ow[4] = {o.x, o.y, o.z, o.w}, hw[4] = {HU.x, HU.y, HU.z, HU.w};
 #pragma unroll
-        for (uint32_t half = 0; half < 2; half++) {
-            const uint32_t v = 2 * blk + half;
-            const uint32_t b0 = v * 16;
-            if (b0 >= tile_len) continue; // past the end of the stream
-            if ((int)(b0 + 16) <= r1 || (int)b0 >= r1) { // wholly inside entry j, or wholly inside entry j+1
-                const uint32_t src_e = (int)b0 >= r1 ? j + 1 : j;
-                const uintptr_t sa = (uintptr_t)(s_adj[src_e] + b0);
-                const uint32_t s0 = (uint32_t)(sa & 15);
-                const uint4 *sv = reinterpret_cast<const uint4 *>(sa - s0);
-                reinterpret_cast<uint4 *>(dst_tile)[v] = realign16_sel(__ldg(sv), __ldg(s0 ? sv + 1 : sv), s0);
-                continue;
+            for (uint32_t q = 0; q < 4; q++) {
+                const uint32_t mk = q < wfull ? 0xFFFFFFFFu : (q == wfull ? mmix : 0u);
+                ow[q] = (ow[q] & mk) | (hw[q] & ~mk);
             }
-            const uint32_t t = (uint32_t)r1 - b0; // tail bytes of entry j in this vector: 1..15
-            const uintptr_t sa = (uintptr_t)(s_adj[j] + b0);
-            const uint32_t s0 = (uint32_t)(sa & 15);
-            const uint4 *sv = reinterpret_cast<const uint4 *>(sa - s0);
-            const uint4 TA = __ldg(sv);
-            const uint4 TB = __ldg(s0 + t > 16 ? sv + 1 : sv);
-            uint4 o = realign16_sel(TA, TB, s0);
-            if (b0 + 16 <= tile_len) {
-                const uintptr_t ha = (uintptr_t)(s_adj[j + 1] + (unsigned long long)(long long)s_r0[j + 1]); // first byte of entry j+1
-                const uint32_t hs = (uint32_t)(ha & 15);
-                const uint4 *hv = reinterpret_cast<const uint4 *>(ha - hs);
-                const uint4 HA = __ldg(hv);
-                const uint4 HB = __ldg(hs ? hv + 1 : hv);
-                const uint4 H = realign16_sel(HA, HB, hs);
-                const uint4 HU = realign16_sel(make_uint4(0, 0, 0, 0), H, 16 - t);
-                const uint32_t wfull = t >> 2, bits = (t & 3) * 8;
-                const uint32_t mmix = bits ? (0xFFFFFFFFu >> (32 - bits)) : 0u;
-                uint32_t ow[4] = {o.x, o.y, o.z, o.w}, hw[4] = {HU.x, HU.y, HU.z, HU.w};
-#pragma unroll
-                for (uint32_t q = 0; q < 4; q++) {
-                    const uint32_t mk = q < wfull ? 0xFFFFFFFFu : (q == wfull ? mmix : 0u);
-                    ow[q] = (ow[q] & mk) | (hw[q] & ~mk);
-                }
-                reinterpret_cast<uint4 *>(dst_tile)[v] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-            } else { // ragged end of the whole stream: never write past out_data_len
-                const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
-                for (uint32_t b = 0; b < t; b++) dst_tile[b0 + b] = (uint8_t)(ow[b >> 2] >> ((b & 3) * 8));
-            }
+            reinterpret_cast<uint4 *>(dst_tile)[v] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        } else { // ragged end of the whole stream: never write past out_data_len
+            const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+            for (uint32_t b = 0; b < t; b++) dst_tile[b0 + b] = (uint8_t)(ow[b >> 2] >> ((b & 3) * 8));
         }
     }
 
