@@ -49,7 +49,7 @@ constexpr int kMergeThreads = 256;
 constexpr int kMergeVT = 7; // odd: threads walk smem at a 112-byte stride -> no bank conflicts
 constexpr int kMergeTile = kMergeThreads * kMergeVT; // 1792 records = 28 KB of smem
 #ifndef DBEEL_RESOLVE_THREADS
-#define DBEEL_RESOLVE_THREADS 256
+#define DBEEL_RESOLVE_THREADS 128
 #endif
 constexpr int kResolveThreads = DBEEL_RESOLVE_THREADS;
 #ifndef DBEEL_GATHER_THREADS

@@ -75,6 +75,9 @@ def lib():
         L.orc_memtable_flush.restype = C.c_int
         L.orc_memtable_flush.argtypes = [C.POINTER(_Run), C.c_uint64, C.c_uint32, C.c_int,
                                          C.POINTER(_Out), C.POINTER(C.c_uint64)]
+        L.orc_sstable_lookup.restype = C.c_int
+        L.orc_sstable_lookup.argtypes = [C.POINTER(_Run), C.c_void_p, C.c_uint64, C.c_char_p, C.c_uint64,
+                                         C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
         _lib = L
     return _lib
 
@@ -211,3 +214,13 @@ class RbTree:
         if rc:
             raise OracleError(f"orc_rb_flush rc={rc}")
         return d[:out.data_len].copy(), i[:out.index_len].copy(), int(out.items_written)
+
+
+def sstable_lookup(run, bloom, key: bytes):
+    """get_entry's per-SSTable step: (found, index record number | None, bloom_said_no)."""
+    arr, keep = _mk_runs([run])
+    b = _u8(bloom) if bloom is not None else None
+    rec, no = C.c_uint64(0), C.c_int(0)
+    f = lib().orc_sstable_lookup(arr, b.ctypes.data if b is not None else None, b.size if b is not None else 0,
+                                 key, len(key), C.byref(rec), C.byref(no))
+    return bool(f), (int(rec.value) if f else None), bool(no.value)

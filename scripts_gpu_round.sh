@@ -1,9 +1,20 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-echo "=== tune default"
-timeout 300 python tools/tune.py "" 2>&1 | tail -1
-echo "=== tune resolve 128 threads"
-DBEEL_LIB=$PWD/dbeel_b200/libdbeel_compact_r128.so timeout 300 python tools/tune.py "" 2>&1 | tail -1
-echo "=== parity resolve 128"
-DBEEL_LIB=$PWD/dbeel_b200/libdbeel_compact_r128.so timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -2
+nvidia-smi -L
+echo "=== pytest -m gpu (full)"
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4
+echo "=== smoke"
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+echo "=== bench (default)"
+timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -2 gpurun_out/bench.err; cat gpurun_out/bench.json
+echo "=== bench reference arm"
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2>/dev/null; cut -c1-600 gpurun_out/bench_ref.json
+echo "=== ncu launch list (device-resident steps only: DBEEL_PIPELINE=0 keeps the e2e part short)"
+DBEEL_PIPELINE=0 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
+grep -c . gpurun_out/launches.csv
+echo "=== ncu full"
+DBEEL_PIPELINE=0 timeout 1500 ncu --set full --clock-control none --import-source on -k 'regex:k_gather|k_merge_tma|k_resolve|k_extract|k_emit|k_merge_partition' -s 30 -c 10 \
+    -f -o gpurun_out/prof_full python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/bench_under_ncu_full.log 2>&1
+ls -la gpurun_out/ | tail -8
