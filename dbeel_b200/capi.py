@@ -71,9 +71,16 @@ def lib():
     """The loaded library.  Fails loudly when it has not been built (no fallback)."""
     global _lib
     if _lib is None:
+        if not os.path.exists(LIB_PATH) and "DBEEL_LIB" not in os.environ:
+            try:  # a fresh checkout: the .so is git-ignored; build it in-tree if the toolkit is here
+                from . import _build
+                _build.build()
+            except Exception as ex:
+                raise RuntimeError(f"{LIB_PATH} is missing and could not be built ({ex}): run "
+                                   "`python -m dbeel_b200._build` where nvcc is. There is no CPU fallback "
+                                   "for the compaction path.") from ex
         if not os.path.exists(LIB_PATH):
-            raise RuntimeError(f"{LIB_PATH} is missing: run `python -m dbeel_b200._build` (needs nvcc). "
-                               "There is no CPU fallback for the compaction path.")
+            raise RuntimeError(f"{LIB_PATH} is missing. There is no CPU fallback for the compaction path.")
         L = C.CDLL(LIB_PATH)
         L.dbeel_abi_version.restype = C.c_int
         L.dbeel_engine_create.restype = C.c_int

@@ -1,4 +1,8 @@
 #!/bin/bash
+# One gpurun call that validates a build end to end on a B200:
+#   /usr/local/graft/bin/gpurun --timeout 3000 -- './tools/gpu_round.sh'
+# parity tests, smoke, the bench line, the reference arm, the ncu launch list and one --set full capture
+# of the hot kernels (summarise here with tools/ncu_summary.py / tools/sass_hotspots.py, copy into profiles/).
 set -u
 mkdir -p gpurun_out
 nvidia-smi -L
@@ -10,7 +14,7 @@ echo "=== bench (default)"
 timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -2 gpurun_out/bench.err; cat gpurun_out/bench.json
 echo "=== bench reference arm"
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2>/dev/null; cut -c1-600 gpurun_out/bench_ref.json
-echo "=== ncu launch list (device-resident steps only: DBEEL_PIPELINE=0 keeps the e2e part short)"
+echo "=== ncu launch list (DBEEL_PIPELINE=0 keeps the host-path part of bench.py to one job per call)"
 DBEEL_PIPELINE=0 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
 grep -c . gpurun_out/launches.csv
