@@ -25,7 +25,7 @@ DEFAULT_BLOOM_FP = 0.01
 
 EXPORTS = ["dbeel_abi_version", "dbeel_engine_create", "dbeel_engine_destroy", "dbeel_compact_bound",
            "dbeel_compact", "dbeel_compact_device", "dbeel_compact_submit", "dbeel_poll", "dbeel_wait",
-           "dbeel_flush", "dbeel_flush_device",
+           "dbeel_flush", "dbeel_flush_device", "dbeel_flush_many", "dbeel_flush_many_device",
            "dbeel_bloom_bitmap_bytes", "dbeel_bloom_k_num", "dbeel_bloom_file_size", "dbeel_host_alloc",
            "dbeel_host_free", "dbeel_last_stats", "dbeel_last_error", "dbeel_strerror"]
 
@@ -39,6 +39,11 @@ class Out(C.Structure):
                 ("index", C.c_void_p), ("index_cap", C.c_uint64), ("index_len", C.c_uint64),
                 ("bloom", C.c_void_p), ("bloom_cap", C.c_uint64), ("bloom_len", C.c_uint64),
                 ("items_written", C.c_uint64)]
+
+
+class FlushTable(C.Structure):
+    _fields_ = [("data_off", C.c_uint64), ("data_len", C.c_uint64), ("index_off", C.c_uint64),
+                ("index_len", C.c_uint64), ("items", C.c_uint64)]
 
 
 class Opts(C.Structure):
@@ -103,6 +108,10 @@ def lib():
             f = getattr(L, name)
             f.restype = C.c_int
             f.argtypes = [C.c_void_p, C.POINTER(Run), C.POINTER(Out)]
+        for name in ("dbeel_flush_many", "dbeel_flush_many_device"):
+            f = getattr(L, name)
+            f.restype = C.c_int
+            f.argtypes = [C.c_void_p, C.POINTER(Run), C.c_uint32, C.POINTER(Out), C.POINTER(FlushTable)]
         L.dbeel_bloom_bitmap_bytes.restype = C.c_uint64
         L.dbeel_bloom_bitmap_bytes.argtypes = [C.c_uint64, C.c_double]
         L.dbeel_bloom_k_num.restype = C.c_uint32
@@ -260,6 +269,36 @@ class Engine:
         out = Out(od.ctypes.data, d.size, 0, oi.ctypes.data, i.size // 16 * 16, 0, None, 0, 0, 0)
         self._check(lib().dbeel_flush(self._h, C.byref(run), C.byref(out)), "dbeel_flush")
         return od[:out.data_len], oi[:out.index_len], int(out.items_written)
+
+    def flush_many(self, batches: Sequence[Tuple[object, object]]):
+        """dbeel_flush_many: one launch sequence for all memtables; returns [(data, index, items)] per batch."""
+        keep = [(_u8(d), _u8(i)) for d, i in batches]
+        n = len(keep)
+        arr = (Run * max(1, n))()
+        for j, (d, i) in enumerate(keep):
+            arr[j] = Run(d.ctypes.data, d.size, i.ctypes.data, i.size)
+        dc = sum(d.size for d, _ in keep)
+        ic = sum(i.size // 16 * 16 for _, i in keep)
+        od, oi = np.empty(max(1, dc), np.uint8), np.empty(max(1, ic), np.uint8)
+        out = Out(od.ctypes.data, dc, 0, oi.ctypes.data, ic, 0, None, 0, 0, 0)
+        table = (FlushTable * max(1, n))()
+        self._check(lib().dbeel_flush_many(self._h, arr, n, C.byref(out), table), "dbeel_flush_many")
+        return [(od[t.data_off:t.data_off + t.data_len], oi[t.index_off:t.index_off + t.index_len], int(t.items))
+                for t in table[:n]]
+
+    def flush_many_device(self, batches: Sequence[Tuple[int, int, int, int]], out_ptrs: Tuple[int, int, int, int]):
+        """batches: (data_ptr, data_len, index_ptr, index_len) device pointers; out_ptrs: (data_ptr, data_cap,
+        index_ptr, index_cap).  Returns (data_len, index_len, items, table rows as dicts)."""
+        n = len(batches)
+        arr = (Run * max(1, n))()
+        for j, b in enumerate(batches):
+            arr[j] = Run(*b)
+        dp, dc, ip, ic = out_ptrs
+        out = Out(dp, dc, 0, ip, ic, 0, None, 0, 0, 0)
+        table = (FlushTable * max(1, n))()
+        self._check(lib().dbeel_flush_many_device(self._h, arr, n, C.byref(out), table), "dbeel_flush_many_device")
+        rows = [{k: int(getattr(t, k)) for k, _ in FlushTable._fields_} for t in table[:n]]
+        return int(out.data_len), int(out.index_len), int(out.items_written), rows
 
     # ---- device buffers (raw pointers; torch tensors own the memory) -------------------
     def compact_device(self, runs: Sequence[Tuple[int, int, int, int]], out_ptrs: Tuple[int, int, int, int, int, int],

@@ -151,6 +151,7 @@ struct JobExtra {
     uint64_t out_offset_base = 0;       // .data bytes the earlier partitions wrote
     bool external_bloom = false;        // the filter belongs to the whole compaction: set bits only
     BloomParams bloom = {};
+    dbeel_flush_table *flush_table = nullptr; // flush-many: one row per batch (host memory), filled on success
 };
 
 // The whole device-resident job.  `runs` / `out` hold device pointers.
@@ -193,11 +194,34 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     p.keep_tombstones = o->keep_tombstones ? 1 : 0;
     p.mode_flush = flush ? 1 : 0;
     uint32_t levels = 0;
-    p.nseg[0] = flush ? (N + kMergeTile - 1) / kMergeTile : n_runs;
-    if (p.nseg[0] > (1u << kMaxLevels)) return fail(e, DBEEL_ERR_TOO_MANY_ENTRIES, "arrival batch too large for one flush");
-    while (p.nseg[levels] > 1) {
-        p.nseg[levels + 1] = (p.nseg[levels] + 1) / 2;
-        levels++;
+    const bool many = flush && extra && extra->flush_table;
+    if (many) {
+        // every memtable gets the same power-of-two number of leaf slots (sort tiles), so log2(slots) merge levels
+        // finish all memtables and never pair segments of two different ones
+        uint64_t max_tiles = 1;
+        for (uint32_t r = 0; r < n_runs; r++) {
+            const uint64_t t = (runs[r].index_len / DBEEL_INDEX_ENTRY_SIZE + kMergeTile - 1) / kMergeTile;
+            max_tiles = t > max_tiles ? t : max_tiles;
+        }
+        uint32_t slots = 1;
+        while (slots < max_tiles) slots <<= 1;
+        if (slots > (1u << kMaxLevels) || (uint64_t)slots * n_runs > (1ull << 24))
+            return fail(e, DBEEL_ERR_TOO_MANY_ENTRIES, "flush-many: too many sort tiles");
+        p.flush_slots = slots;
+        p.nseg[0] = slots * n_runs;
+        while ((1u << levels) < slots) {
+            p.nseg[levels + 1] = p.nseg[levels] / 2;
+            levels++;
+        }
+        for (uint32_t r = 0; r < n_runs; r++)
+            if (runs[r].index_len >= DBEEL_INDEX_ENTRY_SIZE) { p.flush_ref_run = r; break; }
+    } else {
+        p.nseg[0] = flush ? (N + kMergeTile - 1) / kMergeTile : n_runs;
+        if (p.nseg[0] > (1u << kMaxLevels)) return fail(e, DBEEL_ERR_TOO_MANY_ENTRIES, "arrival batch too large for one flush");
+        while (p.nseg[levels] > 1) {
+            p.nseg[levels + 1] = (p.nseg[levels] + 1) / 2;
+            levels++;
+        }
     }
     p.n_levels = levels;
 
@@ -222,11 +246,12 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     const uint64_t o_cbytes = carve(res_chunks * 8), o_ccount = carve(res_chunks * 4);
     const uint64_t o_reca = carve(16ull * N), o_recb = carve(16ull * N);
     const uint64_t o_src = carve(8ull * N);
+    const uint64_t o_memtab = carve(many ? 16ull * (n_runs + 1) : 0);
     const uint64_t gather_tiles = (sh.data_total + kGatherTileBytes - 1) / kGatherTileBytes;
     const uint64_t o_tfirst = carve(4ull * (gather_tiles + 2));
     int rc = ensure_device(e, &e->ws, &e->ws_cap, off);
     if (rc) return rc;
-    rc = ensure_pinned(e, header_bytes + sizeof(Ctl) + 64);
+    rc = ensure_pinned(e, header_bytes + align_up(sizeof(Ctl), 64) + 64 + (many ? 16ull * (n_runs + 1) : 0));
     if (rc) return rc;
 
     uint8_t *ws = e->ws;
@@ -245,6 +270,7 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     p.rec_b = reinterpret_cast<Rec *>(ws + o_recb);
     p.src_ptr = reinterpret_cast<unsigned long long *>(ws + o_src);
     p.tile_first = reinterpret_cast<uint32_t *>(ws + o_tfirst);
+    p.mem_table = reinterpret_cast<unsigned long long *>(ws + o_memtab);
     p.out_data = static_cast<uint8_t *>(out->data);
     p.out_index = static_cast<uint4 *>(out->index);
 
@@ -357,6 +383,11 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     k_scan_chunks<<<1, 1024, 0, s>>>(p);
     k_emit<<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, res);
     launches += 4;
+    if (many) {
+        k_flush_table<<<(n_runs + 1 + 127) / 128, 128, 0, s>>>(p, res);
+        k_rebase_index<<<g256, 256, 0, s>>>(p);
+        launches += 2;
+    }
     CU(cudaEventRecord(e->ev[EV_RESOLVE], s));
 
     // ---- K5: gather + bloom (fused epilogue)
@@ -370,6 +401,8 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     // ---- control block back
     Ctl *hc = reinterpret_cast<Ctl *>(e->pin + header_bytes);
     CU(cudaMemcpyAsync(hc, p.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, s));
+    unsigned long long *hmt = reinterpret_cast<unsigned long long *>(e->pin + header_bytes + align_up(sizeof(Ctl), 64));
+    if (many) CU(cudaMemcpyAsync(hmt, p.mem_table, 16ull * (n_runs + 1), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
 
     st.kernel_launches = launches;
@@ -393,6 +426,16 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     st.output_bytes = out->data_len + out->index_len + out->bloom_len;
     st.gather_bytes = 2 * out->data_len + out->index_len + 8ull * hc->out_items; // read + write payload, read index + src_ptr
     st.partitions = 1;
+    if (many) {
+        for (uint32_t r = 0; r < n_runs; r++) {
+            dbeel_flush_table &row = extra->flush_table[r];
+            row.data_off = hmt[2 * r];
+            row.data_len = hmt[2 * (r + 1)] - hmt[2 * r];
+            row.items = hmt[2 * (r + 1) + 1] - hmt[2 * r + 1];
+            row.index_off = hmt[2 * r + 1] * 16;
+            row.index_len = row.items * 16;
+        }
+    }
     return DBEEL_OK;
 }
 
@@ -929,6 +972,72 @@ int dbeel_wait(dbeel_engine *e) {
 int dbeel_flush(dbeel_engine *e, const dbeel_run *batch, dbeel_out *out) {
     REFUSE_WHILE_ASYNC(e);
     return entry(e, batch, batch ? 1 : 0, nullptr, out, true, false);
+}
+
+static int flush_many_entry(dbeel_engine *e, const dbeel_run *batches, uint32_t n, dbeel_out *out, dbeel_flush_table *table,
+                            bool device) {
+    if (!e) return DBEEL_ERR_INVALID_ARG;
+    if (!out || !table || (n && !batches)) return fail(e, DBEEL_ERR_INVALID_ARG, "null argument");
+    if (e->busy) return fail(e, DBEEL_ERR_BUSY, "engine busy");
+    BusyGuard g(e);
+    e->err.clear();
+    dbeel_compact_opts o;
+    default_opts(&o);
+    cudaError_t ce = cudaSetDevice(e->device);
+    if (ce != cudaSuccess) return fail(e, DBEEL_ERR_CUDA, "cudaSetDevice", ce);
+    for (uint32_t i = 0; i < n; i++) table[i] = dbeel_flush_table{0, 0, 0, 0, 0};
+    JobExtra ex;
+    ex.flush_table = table;
+    if (device) return run_job_device(e, batches, n, &o, true, out, true, &ex);
+    // host buffers: stage everything down, run, bring the concatenated SSTables back
+    uint64_t in_need = 0, dsum = 0, isum = 0;
+    for (uint32_t r = 0; r < n; r++) {
+        if ((batches[r].data_len && !batches[r].data) || (batches[r].index_len && !batches[r].index))
+            return fail(e, DBEEL_ERR_INVALID_ARG, "null batch buffer");
+        in_need += align_up(batches[r].data_len + 32, kAlign) + align_up(batches[r].index_len + 16, kAlign);
+        dsum += batches[r].data_len;
+        isum += batches[r].index_len / DBEEL_INDEX_ENTRY_SIZE * 16;
+    }
+    if (out->data_cap < dsum || out->index_cap < isum) return fail(e, DBEEL_ERR_CAPACITY, "output buffer too small");
+    int rc = ensure_device(e, &e->stage_in, &e->stage_in_cap, in_need);
+    if (!rc) rc = ensure_device(e, &e->stage_out, &e->stage_out_cap, align_up(dsum + 16, kAlign) + align_up(isum + 16, kAlign));
+    if (rc) return rc;
+    std::vector<dbeel_run> dr(n);
+    uint64_t pos = 0;
+    for (uint32_t r = 0; r < n; r++) {
+        dr[r] = dbeel_run{e->stage_in + pos, batches[r].data_len, nullptr, batches[r].index_len};
+        if (batches[r].data_len) CU(cudaMemcpyAsync(e->stage_in + pos, batches[r].data, batches[r].data_len, cudaMemcpyHostToDevice, e->stream));
+        pos += align_up(batches[r].data_len + 32, kAlign);
+        dr[r].index = e->stage_in + pos;
+        if (batches[r].index_len) CU(cudaMemcpyAsync(e->stage_in + pos, batches[r].index, batches[r].index_len, cudaMemcpyHostToDevice, e->stream));
+        pos += align_up(batches[r].index_len + 16, kAlign);
+    }
+    dbeel_out dout = *out;
+    dout.data = e->stage_out;
+    dout.index = e->stage_out + align_up(dsum + 16, kAlign);
+    dout.bloom = nullptr;
+    dout.bloom_cap = 0;
+    rc = run_job_device(e, dr.data(), n, &o, true, &dout, true, &ex);
+    if (rc) return rc;
+    if (dout.data_len) CU(cudaMemcpyAsync(out->data, dout.data, dout.data_len, cudaMemcpyDeviceToHost, e->stream));
+    if (dout.index_len) CU(cudaMemcpyAsync(out->index, dout.index, dout.index_len, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    out->data_len = dout.data_len;
+    out->index_len = dout.index_len;
+    out->bloom_len = 0;
+    out->items_written = dout.items_written;
+    return DBEEL_OK;
+}
+
+int dbeel_flush_many(dbeel_engine *e, const dbeel_run *batches, uint32_t n_batches, dbeel_out *out, dbeel_flush_table *table) {
+    REFUSE_WHILE_ASYNC(e);
+    return flush_many_entry(e, batches, n_batches, out, table, false);
+}
+
+int dbeel_flush_many_device(dbeel_engine *e, const dbeel_run *batches, uint32_t n_batches, dbeel_out *out,
+                            dbeel_flush_table *table) {
+    REFUSE_WHILE_ASYNC(e);
+    return flush_many_entry(e, batches, n_batches, out, table, true);
 }
 
 int dbeel_flush_device(dbeel_engine *e, const dbeel_run *batch, dbeel_out *out) {

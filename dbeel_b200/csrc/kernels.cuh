@@ -38,7 +38,7 @@ struct Ctl {
     uint32_t prefix_len;
     uint32_t flags;
     uint32_t total;  // entries that take part in the merge (sum of valid counts)
-    uint32_t ticket; // resolve-kernel tile ticket
+    uint32_t span;   // merged positions to walk: == total, except flush-many where every memtable keeps its gid range
     unsigned long long out_data_len;
     uint32_t out_items;
     uint32_t runs_truncated;
@@ -89,6 +89,9 @@ struct Params {
     uint32_t *chunk_count;
     int keep_tombstones;
     int mode_flush; // 1: arrival batch -- winner = last arrival, tombstones kept
+    uint32_t flush_slots;   // flush-many: leaf segments (sort tiles) reserved per memtable, a power of two; 0 otherwise
+    uint32_t flush_ref_run; // flush: the batch whose first arrival seeds the common-prefix reduction
+    unsigned long long *mem_table; // flush-many: [n_runs + 1][2] = {.data bytes, entries} emitted before each memtable
     // outputs
     uint8_t *out_data;
     uint4 *out_index;
@@ -395,15 +398,20 @@ __global__ void k_plan(Params p) {
     Ctl *c = p.ctl;
     uint32_t total = 0, trunc = 0, flags = c->flags;
     if (p.mode_flush) {
-        // one arrival batch: level-0 segments are the tiles k_block_sort leaves sorted
-        uint32_t cnt = p.first_bad[0];
-        if (cnt < p.runs[0].n_in) trunc++;
-        for (uint32_t j = 0; j < p.nseg[0]; j++) {
-            uint32_t s0 = j * (uint32_t)kMergeTile;
-            p.seg[0][j].start = s0;
-            p.seg[0][j].len = cnt > s0 ? (cnt - s0 < (uint32_t)kMergeTile ? cnt - s0 : (uint32_t)kMergeTile) : 0;
+        // arrival batches: level-0 segments are the tiles k_block_sort leaves sorted.  With several memtables
+        // (flush-many) each one owns an aligned block of `slots` leaf segments, so the first log2(slots) merge
+        // levels never pair segments of different memtables -- and there are no further levels.
+        const uint32_t slots = p.flush_slots ? p.flush_slots : p.nseg[0];
+        for (uint32_t m = 0; m < p.n_runs; m++) {
+            const uint32_t cnt = p.first_bad[m];
+            if (cnt < p.runs[m].n_in) trunc++;
+            for (uint32_t j = 0; j < slots; j++) {
+                const uint32_t s0 = j * (uint32_t)kMergeTile;
+                p.seg[0][m * slots + j].start = p.runs[m].base + s0;
+                p.seg[0][m * slots + j].len = cnt > s0 ? (cnt - s0 < (uint32_t)kMergeTile ? cnt - s0 : (uint32_t)kMergeTile) : 0;
+            }
+            total += cnt;
         }
-        total = cnt;
     } else {
         for (uint32_t r = 0; r < p.n_runs; r++) {
             uint32_t cnt = p.first_bad[r];
@@ -427,6 +435,7 @@ __global__ void k_plan(Params p) {
         p.tile_base[l][pairs] = acc;
     }
     c->total = total;
+    c->span = p.flush_slots ? p.n_total : total;
     c->runs_truncated = trunc;
     c->flags = flags;
 }
@@ -442,7 +451,8 @@ __global__ void k_flush_prefix_init(Params p) {
     const uint8_t *ptr;
     uint32_t kl = 0;
     uint32_t L = 0;
-    if (p.runs[0].n_in && safe_key(p.runs[0], 0, &ptr, &kl)) {
+    const RunDesc &rd = p.runs[p.flush_ref_run];
+    if (rd.n_in && safe_key(rd, 0, &ptr, &kl)) {
         L = kl < kMaxPrefix ? kl : kMaxPrefix;
         for (uint32_t i = 0; i < L; i++) c->prefix[i] = __ldg(ptr + i);
     }
@@ -454,9 +464,10 @@ __global__ void __launch_bounds__(256) k_flush_prefix(Params p) {
     uint32_t g = blockIdx.x * 256u + threadIdx.x;
     uint32_t L = c->prefix_len; // only ever shrinks; a stale (larger) value is still an upper bound
     if (g < p.n_total && L) {
+        const uint32_t r = find_run(p, g);
         const uint8_t *ptr;
         uint32_t kl;
-        if (safe_key(p.runs[0], g, &ptr, &kl)) {
+        if (safe_key(p.runs[r], g - p.runs[r].base, &ptr, &kl)) {
             uint32_t m = kl < L ? kl : L, i = 0;
             while (i < m && __ldg(ptr + i) == c->prefix[i]) i++;
             L = i;
@@ -480,10 +491,10 @@ __device__ __forceinline__ bool arrival_less(const Params &p, uint32_t skip, con
 
 __global__ void __launch_bounds__(kMergeThreads) k_block_sort(Params p) {
     __shared__ Rec s[kMergeTile + kMergeVT + 1];
-    const uint32_t cnt = p.ctl->total;
-    const uint32_t base = blockIdx.x * (uint32_t)kMergeTile;
-    if (base >= cnt) return;
-    const uint32_t n = cnt - base < (uint32_t)kMergeTile ? cnt - base : (uint32_t)kMergeTile;
+    const Seg sg = p.seg[0][blockIdx.x]; // the tile this CTA sorts (k_plan)
+    const uint32_t base = sg.start;
+    const uint32_t n = sg.len;
+    if (n == 0) return;
     const uint32_t tid = threadIdx.x;
     const uint32_t skip = p.ctl->prefix_len + kWindowBytes;
     Rec inf;
@@ -795,20 +806,27 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec
     __shared__ uint8_t s_eqn[NT]; // record tid has the same key as record tid+1
     const Ctl *c = p.ctl;
     const uint32_t tid = threadIdx.x;
-    const uint32_t total = c->total;
+    const uint32_t span = c->span;
     const uint32_t i0 = blockIdx.x * NT;
-    if (i0 >= total) return;
+    if (i0 >= span) return;
     const uint32_t skip = c->prefix_len + kWindowBytes;
     const uint32_t i = i0 + tid;
+    // the sorted segment position i belongs to: the whole merged array, or -- flush-many -- one memtable's slice
+    uint32_t lim_lo = 0, lim_hi = c->total;
+    if (p.flush_slots && i < span) {
+        const uint32_t mt = find_run(p, i);
+        lim_lo = p.runs[mt].base;
+        lim_hi = lim_lo + p.first_bad[mt];
+    }
 
     // records i0-1 .. i0+NT (coalesced), so neighbours come from shared memory
     for (uint32_t k = tid; k < NT + 2; k += NT) {
         int64_t gi = (int64_t)i0 - 1 + k;
-        if (gi >= 0 && gi < (int64_t)total) s_rec[k] = ld_rec(&m[gi]);
+        if (gi >= 0 && gi < (int64_t)span) s_rec[k] = ld_rec(&m[gi]);
     }
     __syncthreads();
 
-    const bool active = i < total;
+    const bool active = i < span && i < lim_hi;
     bool eq_prev = false, eq_next = false;
     Rec cur;
     cur.x = cur.y = cur.z = cur.w = 0;
@@ -816,8 +834,8 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec
     me.entry = nullptr; me.ptr = nullptr; me.klen = 0; me.full_size = 0;
     if (active) {
         cur = s_rec[tid + 1];
-        if (i) eq_prev = key_equal(p, skip, s_rec[tid], cur);
-        if (i + 1 < total) eq_next = key_equal(p, skip, cur, s_rec[tid + 2]);
+        if (i > lim_lo) eq_prev = key_equal(p, skip, s_rec[tid], cur);
+        if (i + 1 < lim_hi) eq_next = key_equal(p, skip, cur, s_rec[tid + 2]);
         if (kNarrow) {
             const uint32_t r = find_run(p, cur.w);
             const RunDesc &rd = p.runs[r];
@@ -880,7 +898,7 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec
                     }
                     if (better) { ks = ck.klen + 8; fs = ck.full_size; src = (unsigned long long)(uintptr_t)ck.entry; }
                     gj++;
-                    if (gj >= total) break;
+                    if (gj >= lim_hi) break;
                     if (!key_equal(p, skip, nx, ld_rec(&m[gj]))) break;
                 }
             }
@@ -888,7 +906,7 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec
         bool tomb = fs == ks + 24;
         keep = (p.keep_tombstones || p.mode_flush || !tomb) ? 1u : 0u;
     }
-    if (active) res[i] = make_uint4((uint32_t)src, (uint32_t)(src >> 32), ks, keep ? fs : 0u);
+    if (i < span) res[i] = make_uint4((uint32_t)src, (uint32_t)(src >> 32), ks, keep ? fs : 0u); // holes: nothing emitted
 
     // tile aggregate (bytes, entries) for the offsets scan
     unsigned long long vb = keep ? fs : 0ull;
@@ -955,7 +973,7 @@ __device__ __forceinline__ void block_excl_scan_1024(unsigned long long &vb, uin
 __global__ void __launch_bounds__(1024) k_scan_tiles(Params p) {
     __shared__ unsigned long long s_b[32];
     __shared__ uint32_t s_c[32];
-    const uint32_t n_tiles = (p.ctl->total + kResolveThreads - 1) / kResolveThreads;
+    const uint32_t n_tiles = (p.ctl->span + kResolveThreads - 1) / kResolveThreads;
     const uint32_t t = blockIdx.x * 1024u + threadIdx.x;
     if (blockIdx.x * 1024u >= n_tiles) return;
     unsigned long long vb = t < n_tiles ? p.tile_bytes[t] : 0ull;
@@ -972,7 +990,7 @@ __global__ void __launch_bounds__(1024) k_scan_chunks(Params p) {
     __shared__ unsigned long long s_b[32];
     __shared__ uint32_t s_c[32];
     Ctl *c = p.ctl;
-    const uint32_t n_tiles = (c->total + kResolveThreads - 1) / kResolveThreads;
+    const uint32_t n_tiles = (c->span + kResolveThreads - 1) / kResolveThreads;
     const uint32_t n_chunks = (n_tiles + 1023) / 1024;
     const uint32_t per = (n_chunks + 1023) / 1024;
     const uint32_t c0 = threadIdx.x * per < n_chunks ? threadIdx.x * per : n_chunks;
@@ -998,7 +1016,7 @@ __global__ void __launch_bounds__(kResolveThreads) k_emit(Params p, const uint4 
     constexpr int NT = kResolveThreads;
     __shared__ unsigned long long s_wb[NT / 32];
     __shared__ uint32_t s_wc[NT / 32];
-    const uint32_t total = p.ctl->total;
+    const uint32_t total = p.ctl->span;
     const uint32_t i0 = blockIdx.x * NT;
     if (i0 >= total) return;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1028,6 +1046,55 @@ __global__ void __launch_bounds__(kResolveThreads) k_emit(Params p, const uint4 
     constexpr unsigned long long tb = kGatherTileBytes;
     unsigned long long b = (off + tb - 1) / tb;
     for (; b * tb < off + fs; b++) p.tile_first[b] = pos;
+}
+
+// Flush-many epilogue.  The memtables' SSTables sit back to back in one output stream; every memtable's .index
+// must carry offsets relative to its own .data file (entry_writer.rs:81-86 starts each file at 0).
+// k_flush_table: what had been emitted before each memtable's first record (+ a sentinel row = the totals).
+// k_rebase_index: subtract that from the memtable's index records.
+
+__global__ void k_flush_table(Params p, const uint4 *res) {
+    const uint32_t mt = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mt > p.n_runs) return;
+    const Ctl *c = p.ctl;
+    unsigned long long bytes;
+    unsigned long long items;
+    if (mt == p.n_runs) {
+        bytes = c->out_data_len;
+        items = c->out_items;
+    } else {
+        const uint32_t pos = p.runs[mt].base; // first merged position of the memtable
+        if (pos >= c->span) {
+            bytes = c->out_data_len;
+            items = c->out_items;
+        } else {
+            const uint32_t tile = pos / kResolveThreads;
+            bytes = p.chunk_bytes[tile >> 10] + p.tile_bytes[tile];
+            items = (unsigned long long)p.chunk_count[tile >> 10] + p.tile_count[tile];
+            for (uint32_t i = tile * kResolveThreads; i < pos; i++) {
+                const uint32_t fs = res[i].w;
+                bytes += fs;
+                items += fs ? 1u : 0u;
+            }
+        }
+    }
+    p.mem_table[2 * mt] = bytes;
+    p.mem_table[2 * mt + 1] = items;
+}
+
+__global__ void __launch_bounds__(256) k_rebase_index(Params p) {
+    const uint32_t e = blockIdx.x * 256u + threadIdx.x;
+    if (e >= p.ctl->out_items) return;
+    uint32_t lo = 0, hi = p.n_runs; // last memtable whose first entry is <= e (empty memtables share a boundary)
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (p.mem_table[2 * mid + 1] <= e) lo = mid; else hi = mid;
+    }
+    uint4 rec = p.out_index[e];
+    const unsigned long long off = ((unsigned long long)rec.x | ((unsigned long long)rec.y << 32)) - p.mem_table[2 * lo];
+    rec.x = (uint32_t)off;
+    rec.y = (uint32_t)(off >> 32);
+    p.out_index[e] = rec;
 }
 
 // ------------------------------------------------------------------------------------

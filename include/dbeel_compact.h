@@ -140,6 +140,21 @@ int dbeel_compact_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs
 int dbeel_flush(dbeel_engine *e, const dbeel_run *batch, dbeel_out *out);
 int dbeel_flush_device(dbeel_engine *e, const dbeel_run *batch, dbeel_out *out);
 
+/* Many memtables in one launch sequence (the flush side of a write-heavy shard produces a memtable every few
+ * milliseconds; one job per memtable is launch-bound).  batches[i] is memtable i's arrivals (same layout as
+ * dbeel_flush).  The n SSTables are written back to back into out->data / out->index; table[i] says where
+ * SSTable i lives.  Every SSTable's .index offsets are relative to its own .data start, exactly what n separate
+ * dbeel_flush calls would have produced. */
+typedef struct dbeel_flush_table {
+    uint64_t data_off, data_len;   /* bytes of out->data holding this memtable's .data file   */
+    uint64_t index_off, index_len; /* bytes of out->index holding its .index file             */
+    uint64_t items;                /* entries written (distinct keys of the memtable)          */
+} dbeel_flush_table;
+int dbeel_flush_many(dbeel_engine *e, const dbeel_run *batches, uint32_t n_batches, dbeel_out *out,
+                     dbeel_flush_table *table /* n_batches rows, host memory */);
+int dbeel_flush_many_device(dbeel_engine *e, const dbeel_run *batches, uint32_t n_batches, dbeel_out *out,
+                            dbeel_flush_table *table);
+
 /* Asynchronous form of dbeel_compact for callers that must not block their reactor (dbeel's
  * compaction task runs on a glommio executor, src/tasks/compaction.rs:139-153): submit returns at
  * once, the job runs on an engine-owned worker thread, poll / wait report its status.  All

@@ -405,3 +405,40 @@ def test_common_prefix_longer_than_the_cap(engine):
     assert engine.stats()["key_prefix_len"] == 255
     exp, _ = model_compact(runs, True)
     assert_run_equal((gd, gi), exp, "long prefix vs model")
+
+
+def test_flush_many_equals_separate_flushes(engine):
+    """dbeel_flush_many: several memtables in one launch sequence -- each SSTable must equal what the red-black-tree
+    replay writes for that memtable alone, offsets restarting at 0 per file."""
+    from dbeel_b200 import storage_engine as se
+    rng = np.random.default_rng(91)
+    batches = []
+    # (a) a Zipf stream cut at 3000 distinct keys (multi-tile memtables of different sizes)
+    stream = W.make_arrival_batch(n_writes=30_000, n_ids=20_000, doc_bytes=200, seed=9)
+    ents = sstable.parse_run(*stream)
+    pos = 0
+    while pos < len(ents):
+        n = se.memtable_cut(stream, pos, 3000)
+        batches.append(sstable.build_run(ents[pos:pos + n]))
+        pos += n
+    # (b) odd ones: an empty memtable, a single write, adversarial keys with many overwrites, all tombstones
+    batches.append((np.zeros(0, np.uint8), np.zeros(0, np.uint8)))
+    batches.append(sstable.build_run([(b"only", b"one", 5)]))
+    pool = nasty_keys(rng, 200)
+    batches.append(sstable.build_run([(pool[int(rng.integers(200))], bytes(rng.integers(0, 256, int(rng.integers(0, 40)), dtype=np.uint8)),
+                                       BASE_TS - s) for s in range(2500)]))
+    batches.append(sstable.build_run([(b"k%03d" % (s % 50), b"", s) for s in range(300)]))
+    got = engine.flush_many(batches)
+    assert len(got) == len(batches)
+    for k, (b, (gd, gi, gn)) in enumerate(zip(batches, got)):
+        if b[1].size == 0:
+            assert gn == 0 and gd.size == 0 and gi.size == 0
+            continue
+        (od, oi, on), = oracle.memtable_flushes(b, capacity=1 << 20)
+        assert gn == on, f"memtable {k}"
+        assert_run_equal((gd, gi), (od, oi), f"memtable {k}")
+    # and the same through separate calls
+    for b, (gd, gi, gn) in zip(batches[:3], got[:3]):
+        sd, si, sn = engine.flush(b)
+        assert sn == gn
+        assert_run_equal((sd, si), (gd, gi), "flush vs flush_many")

@@ -58,6 +58,20 @@ def main():
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
 
+    # all memtables in ONE launch sequence (dbeel_flush_many_device)
+    tot_d = sum(d.numel() for d, _ in subs)
+    tot_i = sum(i.numel() for _, i in subs)
+    bd = torch.empty(tot_d + 16, dtype=torch.uint8, device=dev)
+    bi = torch.empty(tot_i + 16, dtype=torch.uint8, device=dev)
+    args = [(d.data_ptr(), d.numel(), i.data_ptr(), i.numel()) for d, i in subs]
+    eng.flush_many_device(args, (bd.data_ptr(), tot_d, bi.data_ptr(), tot_i))
+    t1 = time.perf_counter()
+    _, _, many_items, _ = eng.flush_many_device(args, (bd.data_ptr(), tot_d, bi.data_ptr(), tot_i))
+    torch.cuda.synchronize()
+    many_wall = time.perf_counter() - t1
+    many_ms = eng.stats()["ms_total"]
+    assert many_items == items
+
     # several engines on the same GPU, one per host thread (= several shards sharing a GPU): small jobs overlap
     import threading
     def many_engines(T):
@@ -86,6 +100,8 @@ def main():
     print(f"{len(cuts)} memtables, {nbytes / 1e6:.0f} MB of arrivals, {items} entries flushed")
     print(f"GPU device-resident, 1 engine: {dev_ms:.2f} ms in kernels ({nbytes / 1e6 / dev_ms * 1e3:.0f} MB/s), {wall * 1e3:.1f} ms wall "
           f"({nbytes / 1e6 / wall:.0f} MB/s incl. launches + control-block read-back per memtable)")
+    print(f"GPU device-resident, dbeel_flush_many_device (all {len(cuts)} memtables, one launch sequence): {many_ms:.2f} ms in kernels "
+          f"({nbytes / 1e6 / many_ms * 1e3:.0f} MB/s), {many_wall * 1e3:.1f} ms wall ({nbytes / 1e6 / many_wall:.0f} MB/s)")
     for T in (2, 4, 8):
         el = many_engines(T)
         print(f"GPU device-resident, {T} engines / host threads on one GPU: {el * 1e3:.1f} ms wall ({nbytes / 1e6 / el:.0f} MB/s)")
