@@ -385,8 +385,7 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     launches += 4;
     if (many) {
         k_flush_table<<<(n_runs + 1 + 127) / 128, 128, 0, s>>>(p, res);
-        k_rebase_index<<<g256, 256, 0, s>>>(p);
-        launches += 2;
+        launches++;
     }
     CU(cudaEventRecord(e->ev[EV_RESOLVE], s));
 
@@ -395,6 +394,10 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
         k_gather<<<(uint32_t)gather_tiles, kGatherThreads, 0, s>>>(p);
     }
     launches++;
+    if (many) { // only now may the .index offsets become file-relative: the gather kernel reads them as stream offsets
+        k_rebase_index<<<g256, 256, 0, s>>>(p);
+        launches++;
+    }
     CU(cudaEventRecord(e->ev[EV_GATHER], s));
     CU(cudaGetLastError());
 
