@@ -47,5 +47,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defines: list[str]) -> str:
+    """A/B builds for tools/tune.py (`LIB=<path>` in a spec): same sources, extra -D flags, own file name."""
+    out = os.path.join(HERE, f"libdbeel_compact.{name}.so")
+    cmd = [nvcc_path(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", out, *[os.path.join(CSRC, s) for s in SOURCES]]
+    subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    if "--variant" in sys.argv:  # python -m dbeel_b200._build --variant tpc2 DBEEL_GATHER_TPC=2
+        k = sys.argv.index("--variant")
+        print(build_variant(sys.argv[k + 1], sys.argv[k + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose=True))

@@ -356,7 +356,7 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
         uint32_t pairs = p.nseg[l + 1];
         uint64_t t_ub = (uint64_t)(N + kMergeTile - 1) / kMergeTile + pairs;
         uint64_t b_ub = t_ub + pairs;
-        k_merge_partition<<<(uint32_t)((b_ub + 127) / 128), 128, 0, s>>>(p, l, src);
+        k_merge_partition<<<(uint32_t)((b_ub + 7) / 8), kPartitionThreads, 0, s>>>(p, l, src); // one warp per boundary
         if (e->merge_variant == 0) { // one CTA per tile, plain loads (kept as the A/B baseline of the TMA kernel)
             k_merge<<<(uint32_t)t_ub, kMergeThreads, 0, s>>>(p, l, src, dst);
         } else { // persistent, TMA bulk loads / stores + mbarrier

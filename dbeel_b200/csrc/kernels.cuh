@@ -57,6 +57,7 @@ constexpr int kResolveThreads = DBEEL_RESOLVE_THREADS;
 #endif
 constexpr int kGatherThreads = DBEEL_GATHER_THREADS; // 128 threads = 8 KB tiles at 12 CTAs/SM (measured: 64..512 threads -> see DESIGN.md)
 constexpr int kGatherVecsPerThread = 4;
+
 constexpr unsigned long long kGatherTileBytes = 16ull * kGatherThreads * kGatherVecsPerThread; // 16 KB of output per CTA
 constexpr int kGatherMaxEntries = (int)(kGatherTileBytes / 32) + 2; // entries are >= 32 bytes
 constexpr int kMaxLevels = 16;      // >= ceil(log2(DBEEL_MAX_RUNS)); flush: 2^16 tiles of 2048 arrivals
@@ -561,12 +562,16 @@ __device__ __forceinline__ uint32_t find_pair(const uint32_t *tb, uint32_t pairs
     return lo;
 }
 
-__global__ void __launch_bounds__(128) k_merge_partition(Params p, uint32_t level, const Rec *src) {
+// One WARP per tile boundary: the merge-path search is a 32-ary search (32 probes of the diagonal per round,
+// one ballot), 5 rounds for a 4M-record diagonal instead of 22 dependent global-memory round trips.
+constexpr int kPartitionThreads = 256;
+
+__global__ void __launch_bounds__(kPartitionThreads) k_merge_partition(Params p, uint32_t level, const Rec *src) {
     const uint32_t pairs = p.nseg[level + 1];
     const uint32_t *tb = p.tile_base[level];
     const uint32_t n_bound = tb[pairs] + pairs; // every pair has tiles + 1 boundaries
-    uint32_t idx = blockIdx.x * 128u + threadIdx.x;
-    if (idx >= n_bound) return;
+    const uint32_t idx = (blockIdx.x * (uint32_t)kPartitionThreads + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (idx >= n_bound) return; // warp-uniform
     const uint32_t skip = p.ctl->prefix_len + kWindowBytes;
     uint32_t j = find_pair(tb, pairs, idx, 1);
     uint32_t t = idx - (tb[j] + j);
@@ -579,13 +584,24 @@ __global__ void __launch_bounds__(128) k_merge_partition(Params p, uint32_t leve
     uint32_t diag = d64 < n ? (uint32_t)d64 : n;
     uint32_t lo = diag > b.len ? diag - b.len : 0;
     uint32_t hi = diag < a.len ? diag : a.len;
+    // P(mid) = "B[diag-1-mid] is not less than A[mid]" is true for mid < answer and false from the answer on
     while (lo < hi) {
-        uint32_t mid = (lo + hi) >> 1;
-        Rec ra = ld_rec(&src[a.start + mid]);
-        Rec rb = ld_rec(&src[b.start + (diag - 1 - mid)]);
-        if (!key_less(p, skip, rb, ra)) lo = mid + 1; else hi = mid;
+        const uint32_t range = hi - lo;
+        const uint32_t step = range >= 32 ? range >> 5 : 1;
+        const uint32_t mid = lo + lane * step + (step - 1); // ascending in the lane; < hi for every lane when range >= 32
+        bool pr = false;
+        if (mid < hi) {
+            Rec ra = ld_rec(&src[a.start + mid]);
+            Rec rb = ld_rec(&src[b.start + (diag - 1 - mid)]);
+            pr = !key_less(p, skip, rb, ra);
+        }
+        const uint32_t cnt = __popc(__ballot_sync(0xFFFFFFFFu, pr)); // P is monotone: the true probes are lanes 0..cnt-1
+        const uint32_t first_false = lo + cnt * step + (step - 1);     // probe of lane cnt (if it exists and is < hi)
+        lo = lo + cnt * step;
+        if (cnt < 32 && first_false < hi) hi = first_false;
+        else if (range < 32) hi = lo; // every valid probe was true: the answer is the end of the range
     }
-    p.part[idx] = lo;
+    if (lane == 0) p.part[idx] = lo;
 }
 
 __global__ void __launch_bounds__(kMergeThreads, 4) k_merge(Params p, uint32_t level, const Rec *src, Rec *dst) {
@@ -1138,12 +1154,13 @@ __global__ void __launch_bounds__(kGatherThreads, 1536 / kGatherThreads) k_gathe
     __shared__ uint32_t s_ks[kGatherMaxEntries];
     const Ctl *c = p.ctl;
     const unsigned long long out_len = c->out_data_len;
-    const unsigned long long T0 = (unsigned long long)blockIdx.x * kGatherTileBytes;
-    if (T0 >= out_len) return;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tile_id = blockIdx.x;
+    const unsigned long long T0 = (unsigned long long)tile_id * kGatherTileBytes;
+    if (T0 >= out_len) return;
     const uint32_t tile_len = out_len - T0 < kGatherTileBytes ? (uint32_t)(out_len - T0) : (uint32_t)kGatherTileBytes;
-    const uint32_t e_lo = p.tile_first[blockIdx.x];
-    const uint32_t e_hi = T0 + kGatherTileBytes < out_len ? p.tile_first[blockIdx.x + 1] : c->out_items - 1;
+    const uint32_t e_lo = p.tile_first[tile_id];
+    const uint32_t e_hi = T0 + kGatherTileBytes < out_len ? p.tile_first[tile_id + 1] : c->out_items - 1;
     const uint32_t ne = e_hi - e_lo + 1; // <= kGatherMaxEntries: every entry is >= 32 bytes
     for (uint32_t j = tid; j < ne; j += NT) {
         const uint4 rec = p.out_index[e_lo + j];

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Kernel-variant sweep on one GPU: generates the cfg2 workload once, then times the device-resident
 pipeline for each environment configuration (variants are read from the environment when an engine
-is created).  Usage: tools/tune.py "DBEEL_GATHER_TUNE=6" "DBEEL_GATHER_TUNE=16,DBEEL_MERGE=2" ..."""
+is created; `LIB=<variant>` selects a compile-time variant built by dbeel_b200/_build.py).  Usage: tools/tune.py "DBEEL_GATHER_TUNE=6" "DBEEL_GATHER_TUNE=16,DBEEL_MERGE=2" ..."""
 import os
 import sys
 
@@ -29,10 +29,15 @@ def main():
     d_out = (od.data_ptr(), dc, oi.data_ptr(), ic, ob.data_ptr(), bc)
     torch.cuda.synchronize()
     ref = None
+    default_lib = capi.LIB_PATH
     for spec in sys.argv[1:] or [""]:
         env = dict(kv.split("=") for kv in spec.split(",") if kv)
         for k in [k for k in os.environ if k.startswith("DBEEL_")]:
             del os.environ[k]
+        lib = env.pop("LIB", None)  # an A/B build made by `python -m dbeel_b200._build --variant <name> -D...`
+        want = os.path.join(ROOT, "dbeel_b200", f"libdbeel_compact.{lib}.so") if lib else default_lib
+        if want != capi.LIB_PATH:
+            capi.LIB_PATH, capi._lib = want, None
         os.environ.update(env)
         eng = capi.Engine(0)
         for _ in range(3):
