@@ -14,7 +14,11 @@ LIB_PATH = os.environ.get("DBEEL_LIB") or os.path.join(_HERE, "libdbeel_compact.
 
 DBEEL_OK = 0
 ERR_NAMES = {1: "INVALID_ARG", 2: "CAPACITY", 3: "ITEM_TOO_LARGE", 4: "CUDA", 5: "NOMEM", 6: "TOO_MANY_RUNS",
-             7: "TOO_MANY_ENTRIES", 8: "UNSORTED_RUN", 9: "NO_DEVICE", 10: "BUSY"}
+             7: "TOO_MANY_ENTRIES", 8: "UNSORTED_RUN", 9: "NO_DEVICE", 10: "BUSY", 11: "BAD_BLOOM"}
+ERR_BAD_BLOOM = 11
+LOOKUP_REFERENCE = 0  # the reference's binary_search loop, step for step (lsm_tree.rs:605-670)
+LOOKUP_EXACT = 1      # lower-bound search: every present key is found
+LOOKUP_CORRUPT = 0x80000000
 ERR_UNSORTED_RUN = 8
 ERR_CAPACITY = 2
 ERR_INVALID_ARG = 1
@@ -26,6 +30,7 @@ DEFAULT_BLOOM_FP = 0.01
 EXPORTS = ["dbeel_abi_version", "dbeel_engine_create", "dbeel_engine_destroy", "dbeel_compact_bound",
            "dbeel_compact", "dbeel_compact_device", "dbeel_compact_submit", "dbeel_poll", "dbeel_wait",
            "dbeel_flush", "dbeel_flush_device", "dbeel_flush_many", "dbeel_flush_many_device",
+           "dbeel_get_many", "dbeel_get_many_device",
            "dbeel_bloom_bitmap_bytes", "dbeel_bloom_k_num", "dbeel_bloom_file_size", "dbeel_host_alloc",
            "dbeel_host_free", "dbeel_last_stats", "dbeel_last_error", "dbeel_strerror"]
 
@@ -44,6 +49,27 @@ class Out(C.Structure):
 class FlushTable(C.Structure):
     _fields_ = [("data_off", C.c_uint64), ("data_len", C.c_uint64), ("index_off", C.c_uint64),
                 ("index_len", C.c_uint64), ("items", C.c_uint64)]
+
+
+class Table(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("data_len", C.c_uint64), ("index", C.c_void_p), ("index_len", C.c_uint64),
+                ("bloom", C.c_void_p), ("bloom_len", C.c_uint64)]
+
+
+class LookupResult(C.Structure):
+    _fields_ = [("table", C.c_int32), ("bloom_rejects", C.c_uint32), ("record", C.c_uint64)]
+
+
+LOOKUP_DTYPE = np.dtype([("table", "<i4"), ("bloom_rejects", "<u4"), ("record", "<u8")])
+
+
+def pack_keys(keys: Sequence[bytes]) -> Tuple[np.ndarray, np.ndarray]:
+    """Query keys in the layout dbeel_get_many takes: (bytes back to back, n + 1 offsets)."""
+    off = np.zeros(len(keys) + 1, dtype=np.uint64)
+    if keys:
+        off[1:] = np.cumsum(np.fromiter((len(k) for k in keys), dtype=np.uint64, count=len(keys)))
+    blob = np.frombuffer(b"".join(keys), dtype=np.uint8) if keys else np.zeros(0, np.uint8)
+    return blob, off
 
 
 class Opts(C.Structure):
@@ -112,6 +138,11 @@ def lib():
             f = getattr(L, name)
             f.restype = C.c_int
             f.argtypes = [C.c_void_p, C.POINTER(Run), C.c_uint32, C.POINTER(Out), C.POINTER(FlushTable)]
+        for name in ("dbeel_get_many", "dbeel_get_many_device"):
+            f = getattr(L, name)
+            f.restype = C.c_int
+            f.argtypes = [C.c_void_p, C.POINTER(Table), C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32,
+                          C.c_void_p]
         L.dbeel_bloom_bitmap_bytes.restype = C.c_uint64
         L.dbeel_bloom_bitmap_bytes.argtypes = [C.c_uint64, C.c_double]
         L.dbeel_bloom_k_num.restype = C.c_uint32
@@ -299,6 +330,31 @@ class Engine:
         self._check(lib().dbeel_flush_many_device(self._h, arr, n, C.byref(out), table), "dbeel_flush_many_device")
         rows = [{k: int(getattr(t, k)) for k, _ in FlushTable._fields_} for t in table[:n]]
         return int(out.data_len), int(out.index_len), int(out.items_written), rows
+
+    # ---- N2: batched point lookups -------------------------------------------------------
+    def get_many(self, tables: Sequence[Tuple[object, object, object]], keys: Sequence[bytes],
+                 mode: int = LOOKUP_REFERENCE) -> np.ndarray:
+        """dbeel_get_many over host buffers.  tables: (data, index, bloom | None) oldest first, like
+        LSMTree.sstables.  Returns a structured array (table, bloom_rejects, record), one row per key."""
+        keep = [(_u8(d), _u8(i), _u8(b) if b is not None and len(b) else None) for d, i, b in tables]
+        arr = (Table * max(1, len(keep)))()
+        for j, (d, i, b) in enumerate(keep):
+            arr[j] = Table(d.ctypes.data, d.size, i.ctypes.data, i.size, b.ctypes.data if b is not None else None,
+                           b.size if b is not None else 0)
+        blob, off = pack_keys(keys)
+        res = np.zeros(len(keys), dtype=LOOKUP_DTYPE)
+        self._check(lib().dbeel_get_many(self._h, arr, len(keep), blob.ctypes.data if blob.size else None,
+                                         off.ctypes.data, len(keys), mode, res.ctypes.data), "dbeel_get_many")
+        return res
+
+    def get_many_device(self, tables: Sequence[Tuple[int, int, int, int, int, int]], keys_ptr: int, offsets_ptr: int,
+                        n_keys: int, results_ptr: int, mode: int = LOOKUP_REFERENCE) -> None:
+        """All pointers are device pointers; tables: (data_ptr, data_len, index_ptr, index_len, bloom_ptr, bloom_len)."""
+        arr = (Table * max(1, len(tables)))()
+        for j, t in enumerate(tables):
+            arr[j] = Table(t[0], t[1], t[2], t[3], t[4] if t[5] else None, t[5])
+        self._check(lib().dbeel_get_many_device(self._h, arr, len(tables), keys_ptr, offsets_ptr, n_keys, mode,
+                                                results_ptr), "dbeel_get_many_device")
 
     # ---- device buffers (raw pointers; torch tensors own the memory) -------------------
     def compact_device(self, runs: Sequence[Tuple[int, int, int, int]], out_ptrs: Tuple[int, int, int, int, int, int],

@@ -19,6 +19,7 @@
 
 #include "../../include/dbeel_compact.h"
 #include "kernels.cuh"
+#include "lookup.cuh"
 
 using namespace dbeel;
 
@@ -624,11 +625,18 @@ int run_job_host_pipelined(dbeel_engine *e, const dbeel_run *runs, uint32_t n_ru
     }
 
     // ---- 5. the pipeline
+    const bool trace = getenv("DBEEL_TRACE") != nullptr; // per-partition timeline on stderr (debug aid)
+    std::vector<cudaEvent_t> tev;
+    if (trace) {
+        tev.resize(6 * (size_t)np);
+        for (auto &ev : tev) CU(cudaEventCreate(&ev));
+    }
     std::vector<uint64_t> off_base(n_runs);
     std::vector<dbeel_run> dr(n_runs);
     auto enqueue_h2d = [&](uint32_t c) -> int {
         uint8_t *base = sin[c & 1];
         uint64_t pos = 0;
+        if (trace) CU(cudaEventRecord(tev[6 * c + 0], e->s_h2d));
         for (uint32_t r = 0; r < n_runs; r++) {
             const uint64_t dl = boff[r][c + 1] - boff[r][c], il = (lo[r][c + 1] - lo[r][c]) * 16;
             if (dl) CU(cudaMemcpyAsync(base + pos, hr[r].data + boff[r][c], dl, cudaMemcpyHostToDevice, e->s_h2d));
@@ -637,6 +645,7 @@ int run_job_host_pipelined(dbeel_engine *e, const dbeel_run *runs, uint32_t n_ru
             pos += align_up(il + 16, kAlign);
         }
         CU(cudaEventRecord(e->ev_h2d[c & 1], e->s_h2d));
+        if (trace) CU(cudaEventRecord(tev[6 * c + 1], e->s_h2d));
         return DBEEL_OK;
     };
     dbeel_stats total = {};
@@ -673,6 +682,7 @@ int run_job_host_pipelined(dbeel_engine *e, const dbeel_run *runs, uint32_t n_ru
         ex.out_offset_base = out_data;
         CU(cudaStreamWaitEvent(e->stream, e->ev_h2d[c & 1], 0));
         if (c >= 2) CU(cudaStreamWaitEvent(e->stream, e->ev_d2h[c & 1], 0)); // output buffer c&1 drained
+        if (trace) CU(cudaEventRecord(tev[6 * c + 2], e->stream));
         rc = run_job_device(e, dr.data(), n_runs, o, false, &dout, /*record_start=*/true, &ex); // syncs e->stream
         if (rc) break;
         const dbeel_stats &ps = e->stats;
@@ -688,10 +698,13 @@ int run_job_host_pipelined(dbeel_engine *e, const dbeel_run *runs, uint32_t n_ru
         total.ms_gather += ps.ms_gather;
         total.gather_bytes += ps.gather_bytes;
         CU(cudaEventRecord(e->ev_comp[c & 1], e->stream));
+        if (trace) CU(cudaEventRecord(tev[6 * c + 3], e->stream));
         CU(cudaStreamWaitEvent(e->s_d2h, e->ev_comp[c & 1], 0));
+        if (trace) CU(cudaEventRecord(tev[6 * c + 4], e->s_d2h));
         if (dout.data_len) CU(cudaMemcpyAsync(h_data + out_data, dout.data, dout.data_len, cudaMemcpyDeviceToHost, e->s_d2h));
         if (dout.index_len) CU(cudaMemcpyAsync(h_index + 16 * out_items, dout.index, dout.index_len, cudaMemcpyDeviceToHost, e->s_d2h));
         CU(cudaEventRecord(e->ev_d2h[c & 1], e->s_d2h));
+        if (trace) CU(cudaEventRecord(tev[6 * c + 5], e->s_d2h));
         out_data += dout.data_len;
         out_items += dout.items_written;
         if (c + 2 < np) { // input buffer c&1 is free again (the job that read it has completed)
@@ -710,6 +723,15 @@ int run_job_host_pipelined(dbeel_engine *e, const dbeel_run *runs, uint32_t n_ru
     }
     CU(cudaStreamSynchronize(e->s_d2h));
     CU(cudaStreamSynchronize(e->s_h2d));
+    if (trace) {
+        fprintf(stderr, "[dbeel trace] %u partitions; ms since the first H2D began: h2d[begin,end] kernels[begin,end] d2h[begin,end]\n", np);
+        for (uint32_t c = 0; c < np; c++) {
+            float t[6];
+            for (int k = 0; k < 6; k++) cudaEventElapsedTime(&t[k], tev[0], tev[6 * c + k]);
+            fprintf(stderr, "[dbeel trace] p%02u h2d %6.2f %6.2f  kernels %6.2f %6.2f  d2h %6.2f %6.2f\n", c, t[0], t[1], t[2], t[3], t[4], t[5]);
+        }
+        for (auto &ev : tev) cudaEventDestroy(ev);
+    }
     out->data_len = out_data;
     out->items_written = out_items;
     out->index_len = out_items * 16;
@@ -818,6 +840,127 @@ int entry(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, const dbeel_c
     if (ce != cudaSuccess) return fail(e, DBEEL_ERR_CUDA, "cudaSetDevice", ce);
     e->stats.ms_h2d = 0;
     return device ? run_job_device(e, runs, n_runs, &o, flush, out, true) : run_job_host(e, runs, n_runs, &o, flush, out);
+}
+
+
+// ------------------------------------------------------------------------------------ N2: batched point lookups
+
+constexpr uint64_t kBloomTrailer = 8 + 8 + 4 + 144; // nbits, bitmap_bits, k_num, 2 x SipHasher13 (9 x u64 each)
+
+inline uint64_t rd64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
+inline uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+
+// head = the file's first 8 bytes, tail = its last kBloomTrailer bytes (both in host memory)
+int parse_bloom(dbeel_engine *e, const uint8_t *head, const uint8_t *tail, uint64_t file_len, TableDesc *t) {
+    const uint64_t n_words = rd64(head);
+    if (n_words > (1ull << 40) || file_len != 8 + 4 * n_words + kBloomTrailer) return fail(e, DBEEL_ERR_BAD_BLOOM, "bloom file length does not match its word count");
+    t->bits = rd64(tail + 8); // Bloom.bitmap_bits (the BitVec's own nbits precedes it)
+    t->k_num = rd32(tail + 16);
+    if (t->bits < 2 || t->bits > 32 * n_words || t->k_num == 0) return fail(e, DBEEL_ERR_BAD_BLOOM, "bloom parameters out of range");
+    t->bits_magic = (uint64_t)((((unsigned __int128)1) << 64) / t->bits);
+    for (int h = 0; h < 2; h++) { // SipHasher13 { k0, k1, length, state { v0, v2, v1, v3 }, tail, ntail }
+        t->sip[2 * h] = rd64(tail + 20 + 72 * h);
+        t->sip[2 * h + 1] = rd64(tail + 20 + 72 * h + 8);
+    }
+    return DBEEL_OK;
+}
+
+int lookup_entry(dbeel_engine *e, const dbeel_table *tables, uint32_t n_tables, const void *keys, const uint64_t *key_off,
+                 uint64_t n_keys, uint32_t mode, dbeel_lookup_result *results, bool device) {
+    static_assert(sizeof(dbeel_lookup_result) == 16, "result rows are written as uint4");
+    if (!e) return DBEEL_ERR_INVALID_ARG;
+    if ((n_tables && !tables) || (n_keys && (!key_off || !results))) return fail(e, DBEEL_ERR_INVALID_ARG, "null argument");
+    if (mode > DBEEL_LOOKUP_EXACT) return fail(e, DBEEL_ERR_INVALID_ARG, "unknown lookup mode");
+    if (n_tables > 65536) return fail(e, DBEEL_ERR_TOO_MANY_RUNS, "more than 65536 tables");
+    if (e->busy) return fail(e, DBEEL_ERR_BUSY, "engine busy");
+    BusyGuard g(e);
+    e->err.clear();
+    e->stats = dbeel_stats{};
+    if (n_keys == 0) return DBEEL_OK;
+    cudaError_t ce = cudaSetDevice(e->device);
+    if (ce != cudaSuccess) return fail(e, DBEEL_ERR_CUDA, "cudaSetDevice", ce);
+    cudaStream_t s = e->stream;
+    for (uint32_t i = 0; i < n_tables; i++) {
+        const dbeel_table &t = tables[i];
+        if (t.index_len % DBEEL_INDEX_ENTRY_SIZE) return fail(e, DBEEL_ERR_INVALID_ARG, "index length is not a multiple of 16");
+        if ((t.data_len && !t.data) || (t.index_len && !t.index) || (t.bloom_len && !t.bloom)) return fail(e, DBEEL_ERR_INVALID_ARG, "null table buffer");
+        if (t.bloom_len && (t.bloom_len < 8 + kBloomTrailer || (t.bloom_len - 8 - kBloomTrailer) % 4))
+            return fail(e, DBEEL_ERR_BAD_BLOOM, "bloom file length is not 8 + 4 * words + 164");
+        if (device && (((uintptr_t)t.index & 15) || ((uintptr_t)t.bloom & 3))) return fail(e, DBEEL_ERR_INVALID_ARG, "misaligned device buffer");
+    }
+    std::vector<TableDesc> td(n_tables);
+    const uint8_t *d_keys = static_cast<const uint8_t *>(keys);
+    const uint64_t *d_off = key_off;
+    uint4 *d_res = reinterpret_cast<uint4 *>(results);
+    int rc = ensure_pinned(e, std::max<uint64_t>(4096, (uint64_t)n_tables * (8 + kBloomTrailer) + n_tables * sizeof(TableDesc)));
+    if (rc) return rc;
+    uint8_t *pin_desc = e->pin + (uint64_t)n_tables * (8 + kBloomTrailer);
+    if (device) {
+        for (uint32_t i = 0; i < n_tables; i++) {
+            const dbeel_table &t = tables[i];
+            td[i] = TableDesc{static_cast<const uint8_t *>(t.data), t.data_len, static_cast<const uint4 *>(t.index),
+                              t.index_len / DBEEL_INDEX_ENTRY_SIZE, nullptr, 0, 0, 0, 0, {0, 0, 0, 0}};
+            if (!t.bloom_len) continue;
+            const uint8_t *b = static_cast<const uint8_t *>(t.bloom);
+            uint8_t *hp = e->pin + (uint64_t)i * (8 + kBloomTrailer);
+            CU(cudaMemcpyAsync(hp, b, 8, cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(hp + 8, b + t.bloom_len - kBloomTrailer, kBloomTrailer, cudaMemcpyDeviceToHost, s));
+            td[i].words = reinterpret_cast<const uint32_t *>(b + 8);
+        }
+        CU(cudaStreamSynchronize(s));
+        for (uint32_t i = 0; i < n_tables; i++)
+            if (tables[i].bloom_len) {
+                const uint8_t *hp = e->pin + (uint64_t)i * (8 + kBloomTrailer);
+                if ((rc = parse_bloom(e, hp, hp + 8, tables[i].bloom_len, &td[i]))) return rc;
+            }
+    } else { // host buffers: the tables, the keys and the offsets go down, the result rows come back
+        if (!keys && key_off[n_keys]) return fail(e, DBEEL_ERR_INVALID_ARG, "null argument");
+        const uint64_t key_bytes = key_off[n_keys];
+        uint64_t need = align_up(key_bytes + 16, kAlign) + align_up((n_keys + 1) * 8, kAlign);
+        for (uint32_t i = 0; i < n_tables; i++)
+            need += align_up(tables[i].data_len + 16, kAlign) + align_up(tables[i].index_len + 16, kAlign) + align_up(tables[i].bloom_len + 16, kAlign);
+        rc = ensure_device(e, &e->stage_in, &e->stage_in_cap, need);
+        if (!rc) rc = ensure_device(e, &e->stage_out, &e->stage_out_cap, n_keys * 16);
+        if (rc) return rc;
+        uint64_t pos = 0;
+        auto put = [&](const void *src, uint64_t len, uint64_t slack) -> const uint8_t * {
+            uint8_t *dst = e->stage_in + pos;
+            pos += align_up(len + slack, kAlign);
+            if (len && cudaMemcpyAsync(dst, src, len, cudaMemcpyHostToDevice, s) != cudaSuccess) return nullptr;
+            return dst;
+        };
+        d_keys = put(keys, key_bytes, 16);
+        d_off = reinterpret_cast<const uint64_t *>(put(key_off, (n_keys + 1) * 8, 0));
+        if (!d_keys || !d_off) return fail(e, DBEEL_ERR_CUDA, "cudaMemcpyAsync(keys)", cudaGetLastError());
+        for (uint32_t i = 0; i < n_tables; i++) {
+            const dbeel_table &t = tables[i];
+            const uint8_t *dd = put(t.data, t.data_len, 16), *di = put(t.index, t.index_len, 16), *db = put(t.bloom, t.bloom_len, 16);
+            if (!dd || !di || !db) return fail(e, DBEEL_ERR_CUDA, "cudaMemcpyAsync(table)", cudaGetLastError());
+            td[i] = TableDesc{dd, t.data_len, reinterpret_cast<const uint4 *>(di), t.index_len / DBEEL_INDEX_ENTRY_SIZE, nullptr, 0, 0, 0, 0, {0, 0, 0, 0}};
+            if (!t.bloom_len) continue;
+            const uint8_t *b = static_cast<const uint8_t *>(t.bloom);
+            if ((rc = parse_bloom(e, b, b + t.bloom_len - kBloomTrailer, t.bloom_len, &td[i]))) return rc;
+            td[i].words = reinterpret_cast<const uint32_t *>(db + 8);
+        }
+        d_res = reinterpret_cast<uint4 *>(e->stage_out);
+    }
+    rc = ensure_device(e, &e->ws, &e->ws_cap, std::max<uint64_t>(4096, n_tables * sizeof(TableDesc)));
+    if (rc) return rc;
+    if (n_tables) {
+        memcpy(pin_desc, td.data(), n_tables * sizeof(TableDesc));
+        CU(cudaMemcpyAsync(e->ws, pin_desc, n_tables * sizeof(TableDesc), cudaMemcpyHostToDevice, s));
+    }
+    LookupParams lp{reinterpret_cast<const TableDesc *>(e->ws), n_tables, mode, d_keys, d_off, n_keys, d_res};
+    CU(cudaEventRecord(e->ev[EV_START], s));
+    k_lookup<<<(uint32_t)((n_keys + 255) / 256), 256, 0, s>>>(lp);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(e->ev[EV_GATHER], s));
+    if (!device) CU(cudaMemcpyAsync(results, d_res, n_keys * 16, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    CU(cudaEventElapsedTime(&e->stats.ms_total, e->ev[EV_START], e->ev[EV_GATHER]));
+    e->stats.kernel_launches = 1;
+    e->stats.entries_in = n_keys;
+    return DBEEL_OK;
 }
 
 } // namespace
@@ -1048,6 +1191,18 @@ int dbeel_flush_device(dbeel_engine *e, const dbeel_run *batch, dbeel_out *out) 
     return entry(e, batch, batch ? 1 : 0, nullptr, out, true, true);
 }
 
+int dbeel_get_many(dbeel_engine *e, const dbeel_table *tables, uint32_t n_tables, const void *keys, const uint64_t *key_offsets,
+                   uint64_t n_keys, uint32_t mode, dbeel_lookup_result *results) {
+    REFUSE_WHILE_ASYNC(e);
+    return lookup_entry(e, tables, n_tables, keys, key_offsets, n_keys, mode, results, false);
+}
+
+int dbeel_get_many_device(dbeel_engine *e, const dbeel_table *tables, uint32_t n_tables, const void *keys,
+                          const uint64_t *key_offsets, uint64_t n_keys, uint32_t mode, dbeel_lookup_result *results) {
+    REFUSE_WHILE_ASYNC(e);
+    return lookup_entry(e, tables, n_tables, keys, key_offsets, n_keys, mode, results, true);
+}
+
 void *dbeel_host_alloc(uint64_t bytes) {
     void *p = nullptr;
     if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
@@ -1082,6 +1237,7 @@ const char *dbeel_strerror(int code) {
     case DBEEL_ERR_UNSORTED_RUN: return "input run not strictly ascending";
     case DBEEL_ERR_NO_DEVICE: return "no sm_100 CUDA device";
     case DBEEL_ERR_BUSY: return "engine busy";
+    case DBEEL_ERR_BAD_BLOOM: return "malformed .bloom file";
     default: return "unknown error";
     }
 }

@@ -50,7 +50,8 @@ enum {
     DBEEL_ERR_TOO_MANY_ENTRIES = 7,/* more than 2^32-2 input entries in one job             */
     DBEEL_ERR_UNSORTED_RUN = 8,    /* an input run violates "keys strictly ascending"       */
     DBEEL_ERR_NO_DEVICE = 9,       /* no CUDA device / not an sm_100 part                   */
-    DBEEL_ERR_BUSY = 10            /* engine already has a job in flight                    */
+    DBEEL_ERR_BUSY = 10,           /* engine already has a job in flight                    */
+    DBEEL_ERR_BAD_BLOOM = 11       /* a .bloom file is not a bincode bloomfilter::Bloom      */
 };
 
 #define DBEEL_MAX_RUNS 1024u
@@ -164,6 +165,39 @@ int dbeel_compact_submit(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs
                          const dbeel_compact_opts *opts, dbeel_out *out);
 int dbeel_poll(dbeel_engine *e, int *status); /* returns 1 when finished (then *status = the job's code), else 0 */
 int dbeel_wait(dbeel_engine *e);              /* blocks; returns the job's status code */
+
+/* ---- N2: batched point lookups on the files this engine writes ------------------------------------------------
+ * Replaces the SSTable loop of LSMTree::get_entry (src/storage_engine/lsm_tree.rs:686-719) for a batch of keys:
+ * tables[] is the tree's `sstables` vector (oldest first; the loop walks it newest first, :688), every table is its
+ * three files' bytes.  Per key: Bloom::check on the .bloom bytes (:691-696), then binary_search over .index / .data
+ * (:605-670).  The memtable look-ups in front of it (:677-684) stay on the host.
+ *
+ *   DBEEL_LOOKUP_REFERENCE  binary_search restated step for step.  Its loop leaves right after probing index record 0
+ *                           (`if half == 0 ... break`, :660), so a few present keys are reported absent -- this mode
+ *                           reports exactly what the reference reports.
+ *   DBEEL_LOOKUP_EXACT      lower-bound search: every present key is found.                                        */
+#define DBEEL_LOOKUP_REFERENCE 0u
+#define DBEEL_LOOKUP_EXACT 1u
+#define DBEEL_LOOKUP_CORRUPT 0x80000000u /* in bloom_rejects: an index record pointed outside its .data file (the
+                                            reference's read_at fails there and the whole get returns Err) */
+typedef struct dbeel_table {
+    const void *data;  uint64_t data_len;
+    const void *index; uint64_t index_len;  /* multiple of 16 */
+    const void *bloom; uint64_t bloom_len;  /* the .bloom file, or NULL / 0 when the table has none (:94-101) */
+} dbeel_table;
+typedef struct dbeel_lookup_result {
+    int32_t table;          /* position in tables[] of the SSTable that answered, -1 = key not found      */
+    uint32_t bloom_rejects; /* tables skipped by their filter before the answer (| DBEEL_LOOKUP_CORRUPT)    */
+    uint64_t record;        /* index record number inside that table: its EntryOffset locates the entry    */
+} dbeel_lookup_result;
+/* keys: the query keys back to back; key_offsets: n_keys + 1 byte offsets (key i = keys[key_offsets[i] ..
+ * key_offsets[i+1])).  dbeel_get_many takes host pointers everywhere and uploads the tables for the call (tests,
+ * small tables); dbeel_get_many_device takes device pointers everywhere (tables resident in HBM, e.g. straight
+ * from dbeel_compact_device) -- only the 172-byte trailer of each .bloom is read back to parse its parameters. */
+int dbeel_get_many(dbeel_engine *e, const dbeel_table *tables, uint32_t n_tables, const void *keys,
+                   const uint64_t *key_offsets, uint64_t n_keys, uint32_t mode, dbeel_lookup_result *results);
+int dbeel_get_many_device(dbeel_engine *e, const dbeel_table *tables, uint32_t n_tables, const void *keys,
+                          const uint64_t *key_offsets, uint64_t n_keys, uint32_t mode, dbeel_lookup_result *results);
 
 /* Bloom::new_for_fp_rate arithmetic (bloomfilter 1.0.12). */
 uint64_t dbeel_bloom_bitmap_bytes(uint64_t items, double fp);
