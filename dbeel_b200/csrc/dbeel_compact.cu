@@ -50,8 +50,10 @@ struct dbeel_engine {
     int pipeline = 1;                   // DBEEL_PIPELINE: 0 = single-shot host path
     uint64_t pipeline_min_bytes = 64ull << 20;
     uint64_t partition_bytes = 256ull << 20; // DBEEL_PARTITION_MB
+    int partition_taper = 1;                 // DBEEL_PARTITION_TAPER: small first / last partitions (A/B switch)
     // pinned host block: job header going down, control block coming back
     uint8_t *pin = nullptr;
+    uint8_t *pin_dev = nullptr; // the same block as the GPU sees it (mapped: kernels read the header / write the control block)
     uint64_t pin_cap = 0;
     dbeel_stats stats = {};
     std::string err;
@@ -105,9 +107,12 @@ int ensure_pinned(dbeel_engine *e, uint64_t need) {
     if (need <= e->pin_cap) return DBEEL_OK;
     if (e->pin) cudaFreeHost(e->pin);
     e->pin = nullptr;
+    e->pin_dev = nullptr;
     e->pin_cap = 0;
-    cudaError_t ce = cudaHostAlloc(reinterpret_cast<void **>(&e->pin), need, cudaHostAllocDefault);
+    cudaError_t ce = cudaHostAlloc(reinterpret_cast<void **>(&e->pin), need, cudaHostAllocMapped);
     if (ce != cudaSuccess) { cudaGetLastError(); return fail(e, DBEEL_ERR_NOMEM, "cudaHostAlloc", ce); }
+    ce = cudaHostGetDevicePointer(reinterpret_cast<void **>(&e->pin_dev), e->pin, 0);
+    if (ce != cudaSuccess) { cudaGetLastError(); return fail(e, DBEEL_ERR_CUDA, "cudaHostGetDevicePointer", ce); }
     e->pin_cap = need;
     return DBEEL_OK;
 }
@@ -319,7 +324,13 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
 
     cudaStream_t s = e->stream;
     uint32_t launches = 0;
-    CU(cudaMemcpyAsync(ws, h, header_bytes, cudaMemcpyHostToDevice, s));
+    // The header goes down and the control block comes back through kernels that touch the mapped pinned block, not
+    // through cudaMemcpyAsync: a small copy on this stream would queue on a copy engine behind whatever bulk transfer
+    // of the pipelined host path is in flight there (measured: every partition's kernels waited for the previous
+    // partition's 200 MB D2H).  The compute stream carries kernels and event records only.
+    k_copy_words<<<(uint32_t)((header_bytes / 4 + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint32_t *>(ws),
+                                                                            reinterpret_cast<const uint32_t *>(e->pin_dev), (uint32_t)(header_bytes / 4));
+    launches++;
     if (sh.bloom_file) CU(cudaMemsetAsync(out->bloom, 0, sh.bloom_file, s));
     if (record_start) CU(cudaEventRecord(e->ev[EV_START], s));
 
@@ -403,10 +414,15 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     CU(cudaGetLastError());
 
     // ---- control block back
+    static_assert(sizeof(Ctl) % 4 == 0, "the control block is published word by word");
     Ctl *hc = reinterpret_cast<Ctl *>(e->pin + header_bytes);
-    CU(cudaMemcpyAsync(hc, p.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, s));
-    unsigned long long *hmt = reinterpret_cast<unsigned long long *>(e->pin + header_bytes + align_up(sizeof(Ctl), 64));
-    if (many) CU(cudaMemcpyAsync(hmt, p.mem_table, 16ull * (n_runs + 1), cudaMemcpyDeviceToHost, s));
+    const uint64_t o_hmt = header_bytes + align_up(sizeof(Ctl), 64);
+    unsigned long long *hmt = reinterpret_cast<unsigned long long *>(e->pin + o_hmt);
+    k_publish<<<1, 256, 0, s>>>(reinterpret_cast<uint32_t *>(e->pin_dev + header_bytes), reinterpret_cast<const uint32_t *>(p.ctl),
+                                (uint32_t)(sizeof(Ctl) / 4), reinterpret_cast<uint32_t *>(e->pin_dev + o_hmt),
+                                reinterpret_cast<const uint32_t *>(p.mem_table), many ? 4u * (n_runs + 1) : 0u);
+    launches++;
+    CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s));
 
     st.kernel_launches = launches;
@@ -518,14 +534,34 @@ int run_job_host_pipelined(dbeel_engine *e, const dbeel_run *runs, uint32_t n_ru
     });
     uint64_t wsum = 0;
     for (auto &sm : samples) wsum += sm.weight;
+    // Partition sizes: the pipeline's fill (nothing to merge until the first partition is down) and drain (nothing but
+    // the last partition's D2H) cost one partition's transfer each, so the first and last partitions are small:
+    // 1/4, 1/2, 1, 1, ..., 1, 1/2, 1/4 of the nominal size.
+    std::vector<double> share;
+    if (P >= 4 && e->partition_taper) {
+        share = {0.25, 0.5};
+        const uint64_t mid = P - 1 > 59 ? 59 : P - 1; // 2P-1 quarter units short of the total: one more full partition
+        for (uint64_t k = 0; k < mid; k++) share.push_back(1.0);
+        share.push_back(0.5);
+        share.push_back(0.25);
+    } else {
+        share.assign(P, 1.0);
+    }
+    double share_sum = 0;
+    for (double v : share) share_sum += v;
     std::vector<Splitter> cuts;
     {
-        uint64_t acc = 0, next = 1;
+        uint64_t acc = 0;
+        size_t next = 0; // the cut after partition `next`
+        double target = share[0] / share_sum;
         for (auto &sm : samples) {
             acc += sm.weight;
-            if (next < P && acc * P >= next * wsum) {
+            if (next + 1 < share.size() && (double)acc >= target * (double)wsum) {
                 if (cuts.empty() || host_key_cmp(cuts.back().key, cuts.back().klen, sm.key, sm.klen) < 0) cuts.push_back(sm);
-                while (next < P && acc * P >= next * wsum) next++;
+                while (next + 1 < share.size() && (double)acc >= target * (double)wsum) {
+                    next++;
+                    target += share[next] / share_sum;
+                }
             }
         }
     }
@@ -991,6 +1027,7 @@ int dbeel_engine_create(int device, dbeel_engine **out) {
     if (const char *v = getenv("DBEEL_PIPELINE")) e->pipeline = atoi(v);
     if (const char *v = getenv("DBEEL_PIPELINE_MIN_KB")) e->pipeline_min_bytes = (uint64_t)(atoi(v) > 0 ? atoi(v) : 1) << 10;
     if (const char *v = getenv("DBEEL_PARTITION_KB")) e->partition_bytes = (uint64_t)(atoi(v) > 0 ? atoi(v) : 1) << 10;
+    if (const char *v = getenv("DBEEL_PARTITION_TAPER")) e->partition_taper = atoi(v) != 0;
     if (const char *v = getenv("DBEEL_PARTITION_MB")) e->partition_bytes = (uint64_t)(atoi(v) > 0 ? atoi(v) : 128) << 20;
     if (cudaFuncSetAttribute(k_merge_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kMergeBufRecs * sizeof(Rec))) != cudaSuccess) {
         dbeel_engine_destroy(e);

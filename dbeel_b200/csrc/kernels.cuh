@@ -1275,6 +1275,19 @@ __global__ void __launch_bounds__(kGatherThreads, 1536 / kGatherThreads) k_gathe
     }
 }
 
+// Job header down / control block up without a copy engine: the pinned block is mapped into the GPU's address space.
+__global__ void __launch_bounds__(256) k_copy_words(uint32_t *dst, const uint32_t *src_host, uint32_t n) {
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i < n) dst[i] = src_host[i];
+}
+
+__global__ void __launch_bounds__(256) k_publish(uint32_t *dst_host, const uint32_t *ctl, uint32_t n_ctl, uint32_t *dst2_host,
+                                                 const uint32_t *table, uint32_t n_table) {
+    for (uint32_t i = threadIdx.x; i < n_ctl; i += 256) dst_host[i] = ctl[i];
+    for (uint32_t i = threadIdx.x; i < n_table; i += 256) dst2_host[i] = table[i];
+    __threadfence_system(); // visible to the host before the stream reports completion
+}
+
 // .bloom framing around the bit vector (bincode of bloomfilter::Bloom):
 //   u64 n_words | u32 words[n_words] | u64 nbits | u64 bitmap_bits | u32 k_num | 2 x SipHasher13
 __global__ void k_bloom_frame(uint8_t *file, uint64_t n_words, BloomParams b) {

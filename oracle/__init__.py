@@ -78,6 +78,9 @@ def lib():
         L.orc_sstable_lookup.restype = C.c_int
         L.orc_sstable_lookup.argtypes = [C.POINTER(_Run), C.c_void_p, C.c_uint64, C.c_char_p, C.c_uint64,
                                          C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
+        L.orc_get_many.restype = None
+        L.orc_get_many.argtypes = [C.POINTER(_Run), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_uint32, C.c_void_p,
+                                   C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -224,3 +227,20 @@ def sstable_lookup(run, bloom, key: bytes):
     f = lib().orc_sstable_lookup(arr, b.ctypes.data if b is not None else None, b.size if b is not None else 0,
                                  key, len(key), C.byref(rec), C.byref(no))
     return bool(f), (int(rec.value) if f else None), bool(no.value)
+
+
+def get_many(tables, keys_blob: np.ndarray, key_off: np.ndarray):
+    """get_entry's SSTable loop for a batch: tables = [(data, index, bloom | None)] oldest first, keys packed as
+    (bytes back to back, n + 1 uint64 offsets).  Returns (table int32[n], record uint64[n], bloom_rejects uint32[n])."""
+    arr, keep = _mk_runs([(d, i) for d, i, _ in tables])
+    nt = len(tables)
+    blooms = [(_u8(b) if b is not None and len(b) else None) for _, _, b in tables]
+    bp = (C.c_void_p * max(1, nt))(*[(b.ctypes.data if b is not None else None) for b in blooms])
+    bl = (C.c_uint64 * max(1, nt))(*[(b.size if b is not None else 0) for b in blooms])
+    n = key_off.size - 1
+    blob = np.ascontiguousarray(keys_blob, dtype=np.uint8)
+    off = np.ascontiguousarray(key_off, dtype=np.uint64)
+    t, r, j = np.empty(n, np.int32), np.empty(n, np.uint64), np.empty(n, np.uint32)
+    lib().orc_get_many(arr, bp, bl, nt, blob.ctypes.data if blob.size else None, off.ctypes.data, n, t.ctypes.data,
+                       r.ctypes.data, j.ctypes.data)
+    return t, r, j

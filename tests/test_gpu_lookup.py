@@ -14,27 +14,17 @@ pytestmark = pytest.mark.gpu
 SEED = bytes(range(32))
 
 
-def oracle_get(tables, key):
-    """get_entry's loop over `sstables.iter().rev()` with the oracle doing each table: (table, rejects, record)."""
-    rejects = 0
-    for ti in range(len(tables) - 1, -1, -1):
-        d, i, b = tables[ti]
-        found, rec, said_no = oracle.sstable_lookup((d, i), b, key)
-        if said_no:
-            rejects += 1
-            continue
-        if found:
-            return ti, rejects, rec
-    return -1, rejects, 0
-
-
 def check(engine, tables, keys, mode=capi.LOOKUP_REFERENCE):
+    """GPU rows == the oracle's restatement of get_entry's loop (newest table first, bloom.check, binary_search)."""
     res = engine.get_many(tables, keys, mode)
     assert len(res) == len(keys)
-    for k, r in zip(keys, res):
-        exp = oracle_get(tables, k)
-        got = (int(r["table"]), int(r["bloom_rejects"]), int(r["record"]) if r["table"] >= 0 else 0)
-        assert got == exp, f"key {k!r}: GPU {got} != oracle {exp}"
+    blob, off = capi.pack_keys(keys)
+    et, er, ej = oracle.get_many(tables, blob, off)
+    for name, got, exp in (("table", res["table"], et), ("bloom_rejects", res["bloom_rejects"], ej),
+                           ("record", np.where(res["table"] >= 0, res["record"], 0), er)):
+        if not np.array_equal(got, exp):
+            q = int(np.flatnonzero(got != exp)[0])
+            raise AssertionError(f"key {keys[q]!r}: {name} GPU {got[q]} != oracle {exp[q]}")
     return res
 
 

@@ -275,8 +275,8 @@ def test_reference_point_lookup_loop_restated():
     """The consumer of the files this engine writes is LSMTree::binary_search (lsm_tree.rs:605-670).  Restated
     loop for loop it does NOT find every present key: after probing index 0 it always stops (`if half == 0 ...
     break`), so e.g. the second of four entries is never probed.  Recorded here because it is the reason the
-    batched GPU read path is left for a later round: "identical to the reference" and "correct"
-    part ways on that path, and the bloom / index files produced by compaction are valid either way."""
+    batched GPU read path (dbeel_get_many) has two modes: "identical to the reference" and "finds
+    every key" part ways on that path; the bloom / index files produced by compaction are valid either way."""
     run = sstable.build_run([(bytes([10 * n]), b"v%d" % n, 1) for n in range(4)])
     found = [oracle.sstable_lookup(run, None, bytes([10 * n]))[0] for n in range(4)]
     assert found == [True, False, True, True]
@@ -288,3 +288,29 @@ def test_reference_point_lookup_loop_restated():
     assert 1900 < hits <= 2000  # almost every present key is found; the loop's early exit loses a few
     nos = sum(oracle.sstable_lookup((d, i), bloom, b"\xb0k%015d" % n)[2] for n in range(1, 4000, 2))
     assert nos > 1900  # absent keys: the filter says no ~99% of the time
+
+
+def test_get_many_walks_tables_newest_first():
+    """get_entry (lsm_tree.rs:686-719): `sstables.iter().rev()`, a filter that says no skips the table, the first
+    table whose binary_search finds the key answers.  The batch form must agree with the per-table restatement."""
+    mk = lambda lo, hi, step: sstable.build_run([(b"\xb0k%015d" % n, b"x" * 50, 7) for n in range(lo, hi, step)])
+    tables = []
+    for t, (lo, hi, step) in enumerate([(0, 3000, 1), (1000, 4000, 2), (500, 3500, 3)]):
+        d, i, b, _ = oracle.compact([mk(lo, hi, step)], True, bloom_min_size=1000 if t != 1 else 1 << 40, seed=bytes(range(32)))
+        tables.append((d, i, b))
+    assert tables[1][2] is None and tables[0][2] is not None
+    from dbeel_b200 import capi
+    keys = [b"\xb0k%015d" % n for n in range(0, 4200, 7)] + [b"", b"\xff"]
+    blob, off = capi.pack_keys(keys)
+    tb, rec, rej = oracle.get_many(tables, blob, off)
+    for q, k in enumerate(keys):
+        exp_t, exp_r, exp_j = -1, 0, 0
+        for ti in (2, 1, 0):
+            found, r, no = oracle.sstable_lookup(tables[ti][:2], tables[ti][2], k)
+            if no:
+                exp_j += 1
+            elif found:
+                exp_t, exp_r = ti, r
+                break
+        assert (int(tb[q]), int(rec[q]), int(rej[q])) == (exp_t, exp_r, exp_j), k
+    assert set(tb.tolist()) == {-1, 0, 1, 2}
