@@ -110,16 +110,20 @@ __global__ void __launch_bounds__(256) k_lookup(LookupParams p) {
         if (n == 0) continue;
         bool bad = false;
         if (p.mode == 0) { // the reference's loop, :612-667
+            // Written with one exit test and selects instead of the reference's five `break`s: with early exits the
+            // compiler keeps lanes that left the comparison on different sides apart until the search ends (no
+            // reconvergence point inside the loop), which ran the warp's 32 searches almost one after another.
             uint64_t half = n / 2, high = n - 1, low = 0;
-            for (;;) {
+            bool done = false;
+            while (!done) {
                 const int c = probe(t, half, key, klen, &bad);
-                if (bad) break;
-                if (c == 0) { found_table = (int32_t)ti; record = half; break; }
-                if (c < 0) low = half + 1;
-                else high = (half > 1 ? half : 1) - 1; // std::cmp::max(half, 1) - 1
-                if (half == 0 || half == n) break;
+                const bool hit = c == 0 && !bad;
+                if (hit) { found_table = (int32_t)ti; record = half; }
+                low = c < 0 ? half + 1 : low;                              // Ordering::Less
+                high = c > 0 ? (half > 1 ? half : 1) - 1 : high;           // Ordering::Greater: max(half, 1) - 1
+                done = hit || bad || half == 0 || half == n;               // `if half == 0 || half == length { break }`
                 half = (high + low) / 2;
-                if (low > high) break;
+                done = done || low > high;                                 // `while not: low_index > high_index`
             }
         } else { // every present key is found
             uint64_t lo = 0, hi = n;
