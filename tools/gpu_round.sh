@@ -14,6 +14,9 @@ echo "=== bench (default)"
 timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -2 gpurun_out/bench.err; cat gpurun_out/bench.json
 echo "=== bench reference arm"
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2>/dev/null; cut -c1-600 gpurun_out/bench_ref.json
+echo "=== lookups (N2) and flushes (N1)"
+timeout 600 python tools/lookup_bench.py 2>/dev/null | tee gpurun_out/lookup_bench.txt | tail -9
+timeout 600 python tools/flush_bench.py 400000 2>/dev/null | tee gpurun_out/flush_bench.txt | tail -8
 echo "=== ncu launch list (DBEEL_PIPELINE=0 keeps the host-path part of bench.py to one job per call)"
 DBEEL_PIPELINE=0 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
