@@ -14,8 +14,11 @@ LIB_PATH = os.environ.get("DBEEL_LIB") or os.path.join(_HERE, "libdbeel_compact.
 
 DBEEL_OK = 0
 ERR_NAMES = {1: "INVALID_ARG", 2: "CAPACITY", 3: "ITEM_TOO_LARGE", 4: "CUDA", 5: "NOMEM", 6: "TOO_MANY_RUNS",
-             7: "TOO_MANY_ENTRIES", 8: "UNSORTED_RUN", 9: "NO_DEVICE", 10: "BUSY", 11: "BAD_BLOOM"}
+             7: "TOO_MANY_ENTRIES", 8: "UNSORTED_RUN", 9: "NO_DEVICE", 10: "BUSY", 11: "BAD_BLOOM", 12: "TREE_FULL"}
 ERR_BAD_BLOOM = 11
+ERR_TREE_FULL = 12
+ERR_ITEM_TOO_LARGE = 3
+DEFAULT_TREE_CAPACITY = 8192  # mod.rs:18
 LOOKUP_REFERENCE = 0  # the reference's binary_search loop, step for step (lsm_tree.rs:605-670)
 LOOKUP_EXACT = 1      # lower-bound search: every present key is found
 LOOKUP_CORRUPT = 0x80000000
@@ -30,7 +33,7 @@ DEFAULT_BLOOM_FP = 0.01
 EXPORTS = ["dbeel_abi_version", "dbeel_engine_create", "dbeel_engine_destroy", "dbeel_compact_bound",
            "dbeel_compact", "dbeel_compact_device", "dbeel_compact_submit", "dbeel_poll", "dbeel_wait",
            "dbeel_flush", "dbeel_flush_device", "dbeel_flush_many", "dbeel_flush_many_device",
-           "dbeel_get_many", "dbeel_get_many_device",
+           "dbeel_get_many", "dbeel_get_many_device", "dbeel_wal_flush", "dbeel_wal_flush_device",
            "dbeel_bloom_bitmap_bytes", "dbeel_bloom_k_num", "dbeel_bloom_file_size", "dbeel_host_alloc",
            "dbeel_host_free", "dbeel_last_stats", "dbeel_last_error", "dbeel_strerror"]
 
@@ -143,6 +146,10 @@ def lib():
             f.restype = C.c_int
             f.argtypes = [C.c_void_p, C.POINTER(Table), C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32,
                           C.c_void_p]
+        for name in ("dbeel_wal_flush", "dbeel_wal_flush_device"):
+            f = getattr(L, name)
+            f.restype = C.c_int
+            f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(Out)]
         L.dbeel_bloom_bitmap_bytes.restype = C.c_uint64
         L.dbeel_bloom_bitmap_bytes.argtypes = [C.c_uint64, C.c_double]
         L.dbeel_bloom_k_num.restype = C.c_uint32
@@ -330,6 +337,24 @@ class Engine:
         self._check(lib().dbeel_flush_many_device(self._h, arr, n, C.byref(out), table), "dbeel_flush_many_device")
         rows = [{k: int(getattr(t, k)) for k, _ in FlushTable._fields_} for t in table[:n]]
         return int(out.data_len), int(out.index_len), int(out.items_written), rows
+
+    # ---- N4: write-ahead-log replay + flush ------------------------------------------------
+    def wal_flush(self, wal, capacity: int = DEFAULT_TREE_CAPACITY):
+        """dbeel_wal_flush over a host buffer holding a `.memtable` file: returns (data, index, items_written)."""
+        w = _u8(wal)
+        od = np.empty(max(1, w.size), np.uint8)
+        oi = np.empty(max(16, (w.size + 4095) // 4096 * 16), np.uint8)
+        out = Out(od.ctypes.data, od.size, 0, oi.ctypes.data, oi.size, 0, None, 0, 0, 0)
+        self._check(lib().dbeel_wal_flush(self._h, w.ctypes.data if w.size else None, w.size, capacity, C.byref(out)),
+                    "dbeel_wal_flush")
+        return od[:out.data_len], oi[:out.index_len], int(out.items_written)
+
+    def wal_flush_device(self, wal_ptr: int, wal_len: int, out_ptrs: Tuple[int, int, int, int],
+                         capacity: int = DEFAULT_TREE_CAPACITY):
+        dp, dc, ip, ic = out_ptrs
+        out = Out(dp, dc, 0, ip, ic, 0, None, 0, 0, 0)
+        self._check(lib().dbeel_wal_flush_device(self._h, wal_ptr, wal_len, capacity, C.byref(out)), "dbeel_wal_flush_device")
+        return int(out.data_len), int(out.index_len), int(out.items_written)
 
     # ---- N2: batched point lookups -------------------------------------------------------
     def get_many(self, tables: Sequence[Tuple[object, object, object]], keys: Sequence[bytes],

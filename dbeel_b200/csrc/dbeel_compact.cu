@@ -20,6 +20,7 @@
 #include "../../include/dbeel_compact.h"
 #include "kernels.cuh"
 #include "lookup.cuh"
+#include "wal.cuh"
 
 using namespace dbeel;
 
@@ -52,6 +53,8 @@ struct dbeel_engine {
     uint64_t partition_bytes = 256ull << 20; // DBEEL_PARTITION_MB
     int partition_taper = 1;                 // DBEEL_PARTITION_TAPER: small first / last partitions (A/B switch)
     // pinned host block: job header going down, control block coming back
+    uint8_t *wal_ws = nullptr; // WAL replay: doubling tables + the arrival index (grow-only)
+    uint64_t wal_ws_cap = 0;
     uint8_t *pin = nullptr;
     uint8_t *pin_dev = nullptr; // the same block as the GPU sees it (mapped: kernels read the header / write the control block)
     uint64_t pin_cap = 0;
@@ -158,6 +161,8 @@ struct JobExtra {
     bool external_bloom = false;        // the filter belongs to the whole compaction: set bits only
     BloomParams bloom = {};
     dbeel_flush_table *flush_table = nullptr; // flush-many: one row per batch (host memory), filled on success
+    bool sparse_offsets = false;        // WAL replay: the batch's .data is the log itself, records do not abut
+    uint64_t data_bytes = 0;            // with sparse_offsets: sum of the records' sizes (the output bound)
 };
 
 // The whole device-resident job.  `runs` / `out` hold device pointers.
@@ -166,6 +171,9 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     JobShape sh;
     shape_of(runs, n_runs, o, flush, &sh);
     if (extra && extra->external_bloom) sh.bloom_file = 0;
+    const uint64_t span_total = sh.data_total; // address span of the inputs (sh.data_total becomes the payload bound)
+    if (extra && extra->sparse_offsets) sh.data_total = extra->data_bytes;
+    (void)span_total;
     if (n_runs > DBEEL_MAX_RUNS) return fail(e, DBEEL_ERR_TOO_MANY_RUNS, "too many runs");
     if (sh.n_total >= 0xFFFFFFFEull) return fail(e, DBEEL_ERR_TOO_MANY_ENTRIES, "too many entries");
     if (out->data_cap < sh.data_total || out->index_cap < sh.n_total * 16 || out->bloom_cap < sh.bloom_file)
@@ -318,6 +326,7 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
         for (int i = 0; i < 4; i++) memcpy(&p.bloom.sip[i], seed + 8 * i, 8);
     }
     if (extra) {
+        p.sparse_offsets = extra->sparse_offsets ? 1 : 0;
         p.out_offset_base = extra->out_offset_base;
         if (extra->external_bloom) p.bloom = extra->bloom;
     }
@@ -999,6 +1008,122 @@ int lookup_entry(dbeel_engine *e, const dbeel_table *tables, uint32_t n_tables, 
     return DBEEL_OK;
 }
 
+
+// ------------------------------------------------------------------------------------ N4: WAL replay + flush
+
+int wal_flush_entry(dbeel_engine *e, const void *wal, uint64_t wal_len, uint32_t capacity, dbeel_out *out, bool device) {
+    if (!e) return DBEEL_ERR_INVALID_ARG;
+    if (!out || (wal_len && !wal)) return fail(e, DBEEL_ERR_INVALID_ARG, "null argument");
+    if (e->busy) return fail(e, DBEEL_ERR_BUSY, "engine busy");
+    e->err.clear();
+    out->data_len = out->index_len = out->bloom_len = out->items_written = 0;
+    const uint64_t n_pages64 = (wal_len + kWalPage - 1) / kWalPage;
+    if (n_pages64 >= 0xFFFFFFF0ull) return fail(e, DBEEL_ERR_TOO_MANY_ENTRIES, "write-ahead log too large");
+    if (wal_len == 0) { e->stats = dbeel_stats{}; return DBEEL_OK; }
+    cudaError_t ce = cudaSetDevice(e->device);
+    if (ce != cudaSuccess) return fail(e, DBEEL_ERR_CUDA, "cudaSetDevice", ce);
+    cudaStream_t s = e->stream;
+    const uint32_t n_pages = (uint32_t)n_pages64, nodes = n_pages + 1;
+    uint32_t levels = 0;
+    while ((1ull << levels) < nodes) levels++;
+
+    const uint8_t *d_wal = static_cast<const uint8_t *>(wal);
+    uint64_t data_cap_user = out->data_cap, index_cap_user = out->index_cap;
+    void *user_data = out->data, *user_index = out->index;
+    float ms_h2d = 0;
+    const uint4 *d_index = nullptr;
+    {
+        BusyGuard g(e);
+        if (!device) { // host log: stage it down (the flush below writes into staging too)
+            int rc = ensure_device(e, &e->stage_in, &e->stage_in_cap, align_up(wal_len + 32, kAlign));
+            if (rc) return rc;
+            CU(cudaEventRecord(e->ev[EV_H2D0], s));
+            CU(cudaMemcpyAsync(e->stage_in, wal, wal_len, cudaMemcpyHostToDevice, s));
+            CU(cudaEventRecord(e->ev[EV_H2D1], s));
+            d_wal = e->stage_in;
+        } else if ((uintptr_t)wal & 15) {
+            return fail(e, DBEEL_ERR_INVALID_ARG, "device log buffer must be 16-byte aligned");
+        }
+        // scratch: jump / cnt tables, per-page sizes, the arrival index, 3 totals
+        uint64_t off = 0;
+        auto carve = [&](uint64_t bytes) { uint64_t o2 = off; off = align_up(off + bytes, kAlign); return o2; };
+        const uint64_t o_jump = carve(4ull * (levels + 1) * nodes), o_cnt = carve(4ull * (levels + 1) * nodes);
+        const uint64_t o_sizes = carve(8ull * n_pages), o_index = carve(16ull * n_pages), o_tot = carve(32);
+        int rc = ensure_device(e, &e->wal_ws, &e->wal_ws_cap, off);
+        if (!rc) rc = ensure_pinned(e, 4096);
+        if (rc) return rc;
+        WalParams w;
+        w.wal = d_wal;
+        w.len = wal_len;
+        w.n_pages = n_pages;
+        w.levels = levels;
+        w.jump = reinterpret_cast<uint32_t *>(e->wal_ws + o_jump);
+        w.cnt = reinterpret_cast<uint32_t *>(e->wal_ws + o_cnt);
+        w.sizes = reinterpret_cast<uint2 *>(e->wal_ws + o_sizes);
+        w.index = reinterpret_cast<uint4 *>(e->wal_ws + o_index);
+        d_index = w.index;
+        w.totals = reinterpret_cast<unsigned long long *>(e->wal_ws + o_tot);
+        CU(cudaMemsetAsync(w.totals, 0, 32, s));
+        const uint32_t grid = (nodes + 255) / 256;
+        k_wal_parse<<<grid, 256, 0, s>>>(w);
+        for (uint32_t k = 0; k < levels; k++) k_wal_double<<<grid, 256, 0, s>>>(w, k);
+        k_wal_select<<<(n_pages + 255) / 256, 256, 0, s>>>(w);
+        k_publish<<<1, 256, 0, s>>>(reinterpret_cast<uint32_t *>(e->pin_dev), reinterpret_cast<const uint32_t *>(w.totals), 6,
+                                    nullptr, nullptr, 0);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(s));
+        if (!device) cudaEventElapsedTime(&ms_h2d, e->ev[EV_H2D0], e->ev[EV_H2D1]);
+    }
+    unsigned long long totals[3];
+    memcpy(totals, e->pin, sizeof totals);
+    const uint64_t n_rec = totals[0], bytes = totals[1];
+    const uint32_t wal_launches = levels + 3;
+    if (totals[2] & kWalTooLarge) return fail(e, DBEEL_ERR_ITEM_TOO_LARGE, "a logged entry exceeds u32::MAX bytes");
+    if (n_rec == 0) { e->stats = dbeel_stats{}; e->stats.kernel_launches = wal_launches; return DBEEL_OK; }
+
+    // ---- the flush: the log is the batch's .data, the selected records its (sparse) .index
+    dbeel_compact_opts o;
+    default_opts(&o);
+    JobExtra ex;
+    ex.sparse_offsets = true;
+    ex.data_bytes = bytes;
+    dbeel_run batch{d_wal, wal_len, d_index, n_rec * 16};
+    if (data_cap_user < bytes || index_cap_user < n_rec * 16) return fail(e, DBEEL_ERR_CAPACITY, "output buffer too small for the replayed entries");
+    int rc;
+    if (device) {
+        BusyGuard g(e);
+        e->stats.ms_h2d = 0;
+        rc = run_job_device(e, &batch, 1, &o, true, out, true, &ex);
+    } else {
+        BusyGuard g(e);
+        rc = ensure_device(e, &e->stage_out, &e->stage_out_cap, align_up(bytes + 16, kAlign) + align_up(n_rec * 16 + 16, kAlign));
+        if (rc) return rc;
+        dbeel_out dout = {};
+        dout.data = e->stage_out;
+        dout.data_cap = bytes;
+        dout.index = e->stage_out + align_up(bytes + 16, kAlign);
+        dout.index_cap = n_rec * 16;
+        e->stats.ms_h2d = ms_h2d;
+        rc = run_job_device(e, &batch, 1, &o, true, &dout, true, &ex);
+        if (!rc && dout.items_written <= capacity) {
+            if (dout.data_len) CU(cudaMemcpyAsync(user_data, dout.data, dout.data_len, cudaMemcpyDeviceToHost, s));
+            if (dout.index_len) CU(cudaMemcpyAsync(user_index, dout.index, dout.index_len, cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));
+        }
+        out->data_len = dout.data_len;
+        out->index_len = dout.index_len;
+        out->items_written = dout.items_written;
+    }
+    if (rc) return rc;
+    e->stats.kernel_launches += wal_launches;
+    e->stats.input_bytes = wal_len;
+    if (out->items_written > capacity) { // memtable.set(..)? -> ReachedCapacity (lsm_tree.rs:566, rbtree_arena lib.rs:458-461)
+        out->data_len = out->index_len = out->items_written = 0;
+        return fail(e, DBEEL_ERR_TREE_FULL, "the log holds more distinct keys than the memtable capacity");
+    }
+    return DBEEL_OK;
+}
+
 } // namespace
 
 // ------------------------------------------------------------------------------------ C ABI
@@ -1240,6 +1365,16 @@ int dbeel_get_many_device(dbeel_engine *e, const dbeel_table *tables, uint32_t n
     return lookup_entry(e, tables, n_tables, keys, key_offsets, n_keys, mode, results, true);
 }
 
+int dbeel_wal_flush(dbeel_engine *e, const void *wal, uint64_t wal_len, uint32_t capacity, dbeel_out *out) {
+    REFUSE_WHILE_ASYNC(e);
+    return wal_flush_entry(e, wal, wal_len, capacity, out, false);
+}
+
+int dbeel_wal_flush_device(dbeel_engine *e, const void *wal, uint64_t wal_len, uint32_t capacity, dbeel_out *out) {
+    REFUSE_WHILE_ASYNC(e);
+    return wal_flush_entry(e, wal, wal_len, capacity, out, true);
+}
+
 void *dbeel_host_alloc(uint64_t bytes) {
     void *p = nullptr;
     if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
@@ -1275,6 +1410,7 @@ const char *dbeel_strerror(int code) {
     case DBEEL_ERR_NO_DEVICE: return "no sm_100 CUDA device";
     case DBEEL_ERR_BUSY: return "engine busy";
     case DBEEL_ERR_BAD_BLOOM: return "malformed .bloom file";
+    case DBEEL_ERR_TREE_FULL: return "memtable capacity reached";
     default: return "unknown error";
     }
 }

@@ -211,4 +211,30 @@ DB_HD bool ts_greater(uint64_t alo, uint64_t ahi, uint64_t blo, uint64_t bhi) {
     return alo > blo;
 }
 
+// Does this i128 nanosecond count decode as a timestamp (utils/timestamp_nanos.rs:15-24 ->
+// time 0.3 OffsetDateTime::from_unix_timestamp_nanos)?  The crate floor-divides by 1e9, casts the quotient to
+// i64 (wrapping) and range-checks the seconds against years -9999 ..= 9999.  Only the WAL replay needs it: there an
+// undecodable entry is skipped, not fatal (lsm_tree.rs:562-566).
+DB_HD bool ts_decodes(uint64_t lo, uint64_t hi) {
+    const bool neg = (int64_t)hi < 0;
+    uint64_t mlo = lo, mhi = hi;
+    if (neg) { // magnitude = two's complement negation (2^127 fits in the unsigned pair)
+        mlo = ~lo + 1;
+        mhi = ~hi + (mlo == 0 ? 1 : 0);
+    }
+    constexpr uint64_t D = 1000000000ull;
+    // long division of mhi:mlo by D; only the low 64 bits of the quotient survive the `as i64`
+    uint64_t r = mhi % D;
+    uint64_t t = (r << 32) | (mlo >> 32); // r < 2^30: fits
+    const uint64_t q1 = t / D;
+    r = t % D;
+    t = (r << 32) | (mlo & 0xFFFFFFFFull);
+    const uint64_t q0 = t / D;
+    r = t % D;
+    uint64_t q = (q1 << 32) + q0; // wraps like the cast does
+    if (neg) q = ~(q + (r != 0 ? 1 : 0)) + 1; // floor for negatives, then negate (mod 2^64)
+    const int64_t secs = (int64_t)q;
+    return secs >= -377705116800ll && secs <= 253402300799ll;
+}
+
 } // namespace dbeel

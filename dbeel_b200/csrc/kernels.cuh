@@ -92,6 +92,7 @@ struct Params {
     int mode_flush; // 1: arrival batch -- winner = last arrival, tombstones kept
     uint32_t flush_slots;   // flush-many: leaf segments (sort tiles) reserved per memtable, a power of two; 0 otherwise
     uint32_t flush_ref_run; // flush: the batch whose first arrival seeds the common-prefix reduction
+    uint32_t sparse_offsets; // WAL replay: index offsets point into the log, records do not abut (no running-offset check)
     unsigned long long *mem_table; // flush-many: [n_runs + 1][2] = {.data bytes, entries} emitted before each memtable
     // outputs
     uint8_t *out_data;
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(256, DBEEL_EXTRACT_MINB) k_extract(Params p, i
                 ok[u] = i[u] < p.first_bad[r[u]];
             } else {
                 ok[u] = ks[u] >= 8 && (uint64_t)fs[u] >= (uint64_t)ks[u] + 24 && off[u] <= dlen_total[u] &&
-                        (uint64_t)fs[u] <= dlen_total[u] - off[u] && off[u] == expect[u];
+                        (uint64_t)fs[u] <= dlen_total[u] - off[u] && (off[u] == expect[u] || p.sparse_offsets);
             }
             match[u] = false;
             klen_w[u] = dlen_w[u] = w0[u] = w1[u] = 0;

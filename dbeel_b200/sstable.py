@@ -140,6 +140,21 @@ def build_run_dense(dense: np.ndarray, keys: np.ndarray, ts: np.ndarray, tombsto
     return flat[:total], index.view(np.uint8).reshape(-1)
 
 
+PAGE_SIZE = 4096  # src/storage_engine/mod.rs (DMA block): every WAL write starts on a page boundary
+
+
+def build_wal(entries: Iterable[EntryTuple], pad_byte: int = 0) -> np.ndarray:
+    """The write-ahead log the reference leaves behind for these writes (lsm_tree.rs:740-744,805-811): each
+    bincode Entry at a 4096-aligned offset, padded to ``size + 4096 - size % 4096`` bytes (a whole extra page when
+    the size is a page multiple).  ``pad_byte`` fills the padding (the reference's DMA buffers are not cleared)."""
+    parts = []
+    for k, v, ts in entries:
+        e = encode_entry(k, v, ts)
+        padded = len(e) + PAGE_SIZE - len(e) % PAGE_SIZE
+        parts.append(e + bytes([pad_byte]) * (padded - len(e)))
+    return np.frombuffer(b"".join(parts), dtype=np.uint8).copy() if parts else np.zeros(0, np.uint8)
+
+
 def run_entry_count(index) -> int:
     return len(index) // INDEX_ENTRY_SIZE  # lsm_tree.rs:452-453, 978-979
 

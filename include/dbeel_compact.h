@@ -51,7 +51,8 @@ enum {
     DBEEL_ERR_UNSORTED_RUN = 8,    /* an input run violates "keys strictly ascending"       */
     DBEEL_ERR_NO_DEVICE = 9,       /* no CUDA device / not an sm_100 part                   */
     DBEEL_ERR_BUSY = 10,           /* engine already has a job in flight                    */
-    DBEEL_ERR_BAD_BLOOM = 11       /* a .bloom file is not a bincode bloomfilter::Bloom      */
+    DBEEL_ERR_BAD_BLOOM = 11,      /* a .bloom file is not a bincode bloomfilter::Bloom      */
+    DBEEL_ERR_TREE_FULL = 12       /* rbtree_arena ReachedCapacity (lib.rs:458-461)          */
 };
 
 #define DBEEL_MAX_RUNS 1024u
@@ -198,6 +199,19 @@ int dbeel_get_many(dbeel_engine *e, const dbeel_table *tables, uint32_t n_tables
                    const uint64_t *key_offsets, uint64_t n_keys, uint32_t mode, dbeel_lookup_result *results);
 int dbeel_get_many_device(dbeel_engine *e, const dbeel_table *tables, uint32_t n_tables, const void *keys,
                           const uint64_t *key_offsets, uint64_t n_keys, uint32_t mode, dbeel_lookup_result *results);
+
+/* ---- N4: write-ahead-log replay + flush ------------------------------------------------------------------------
+ * Replaces LSMTree::read_memtable_from_wal_file (lsm_tree.rs:552-574) followed by flush_memtable_to_disk, i.e. the
+ * recovery of an unflushed memtable in open_or_create_ex (:478-513).  `wal` is the whole `.memtable` file: bincode
+ * Entries at 4096-aligned offsets, each padded to `size + 4096 - size % 4096` (:740-744).  Replay rules kept:
+ * the cursor moves to the first page boundary strictly after every record; an entry whose timestamp does not
+ * deserialize is skipped; a record that runs past the end of the file ends the replay; an all-zero page is the entry
+ * (key = [], data = [], timestamp = 0).  `capacity` is the memtable's (DEFAULT_TREE_CAPACITY, mod.rs:18): more distinct
+ * keys than that fail the reference's replay with ReachedCapacity -> DBEEL_ERR_TREE_FULL.  out->data / out->index
+ * receive the SSTable; caps: the sum of the logged entries' sizes (<= wal_len) and 16 bytes per logged entry
+ * (<= 16 * ceil(wal_len / 4096)).  No bloom (lsm_tree.rs:908). */
+int dbeel_wal_flush(dbeel_engine *e, const void *wal, uint64_t wal_len, uint32_t capacity, dbeel_out *out);
+int dbeel_wal_flush_device(dbeel_engine *e, const void *wal, uint64_t wal_len, uint32_t capacity, dbeel_out *out);
 
 /* Bloom::new_for_fp_rate arithmetic (bloomfilter 1.0.12). */
 uint64_t dbeel_bloom_bitmap_bytes(uint64_t items, double fp);

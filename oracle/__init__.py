@@ -78,6 +78,10 @@ def lib():
         L.orc_sstable_lookup.restype = C.c_int
         L.orc_sstable_lookup.argtypes = [C.POINTER(_Run), C.c_void_p, C.c_uint64, C.c_char_p, C.c_uint64,
                                          C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
+        L.orc_timestamp_decodes.restype = C.c_int
+        L.orc_timestamp_decodes.argtypes = [C.c_char_p]
+        L.orc_wal_flush.restype = C.c_int
+        L.orc_wal_flush.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(_Out), C.POINTER(C.c_uint64)]
         L.orc_get_many.restype = None
         L.orc_get_many.argtypes = [C.POINTER(_Run), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_uint32, C.c_void_p,
                                    C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -244,3 +248,23 @@ def get_many(tables, keys_blob: np.ndarray, key_off: np.ndarray):
     lib().orc_get_many(arr, bp, bl, nt, blob.ctypes.data if blob.size else None, off.ctypes.data, n, t.ctypes.data,
                        r.ctypes.data, j.ctypes.data)
     return t, r, j
+
+
+def timestamp_decodes(ts: int) -> bool:
+    """utils/timestamp_nanos.rs:15-24 through time 0.3: does this i128 nanosecond count deserialize?"""
+    return bool(lib().orc_timestamp_decodes(int(ts).to_bytes(16, "little", signed=True)))
+
+
+def wal_flush(wal, capacity: int = DEFAULT_TREE_CAPACITY, emulate_page_cache: bool = False):
+    """read_memtable_from_wal_file (lsm_tree.rs:552-574) + the recovery flush (:478-513).
+    Returns (data, index, items_written, entries_replayed); raises OracleError("ReachedCapacity") like `set(..)?`."""
+    w = _u8(wal)
+    out, (d, i, _) = _mk_out(w.size, w.size // 16 + 16, 0)
+    seen = C.c_uint64(0)
+    rc = lib().orc_wal_flush(w.ctypes.data if w.size else None, w.size, capacity, int(emulate_page_cache), C.byref(out),
+                             C.byref(seen))
+    if rc == 4:
+        raise OracleError("ReachedCapacity")
+    if rc:
+        raise OracleError(f"orc_wal_flush rc={rc}")
+    return d[:out.data_len].copy(), i[:out.index_len].copy(), int(out.items_written), int(seen.value)

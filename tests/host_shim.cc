@@ -55,6 +55,12 @@ void shim_realign16(const uint8_t src32[32], uint32_t sh, uint8_t out16[16]) {
     memcpy(out16, O, 16);
 }
 
+int shim_ts_decodes(const uint8_t ts[16]) {
+    uint64_t lo, hi;
+    memcpy(&lo, ts, 8); memcpy(&hi, ts + 8, 8);
+    return ts_decodes(lo, hi) ? 1 : 0;
+}
+
 int shim_ts_greater(const uint8_t a[16], const uint8_t b[16]) {
     uint64_t al, ah, bl, bh;
     memcpy(&al, a, 8); memcpy(&ah, a + 8, 8); memcpy(&bl, b, 8); memcpy(&bh, b + 8, 8);

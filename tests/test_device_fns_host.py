@@ -37,6 +37,8 @@ def shim():
     L.shim_rec_cmp.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
     L.shim_sip_pair.argtypes = [C.POINTER(C.c_uint64), C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.shim_realign16.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p]
+    L.shim_ts_decodes.restype = C.c_int
+    L.shim_ts_decodes.argtypes = [C.c_char_p]
     L.shim_ts_greater.restype = C.c_int
     L.shim_ts_greater.argtypes = [C.c_char_p, C.c_char_p]
     return L
@@ -124,3 +126,17 @@ def test_i128_order(shim):
         for b in vals:
             got = shim.shim_ts_greater(a.to_bytes(16, "little", signed=True), b.to_bytes(16, "little", signed=True))
             assert got == int(a > b)
+
+
+def test_timestamp_range_check_matches_oracle(shim):
+    """ts_decodes (WAL replay kernel) == the oracle's restatement of time's from_unix_timestamp_nanos, including the
+    wrapping i64 cast of the seconds."""
+    rng = np.random.default_rng(9)
+    lo, hi = -377705116800 * 10**9, 253402300799 * 10**9 + 999_999_999
+    vals = [0, 1, -1, lo, lo - 1, lo + 1, hi, hi + 1, hi - 1, 1 << 100, -(1 << 100), (1 << 127) - 1, -(1 << 127),
+            10**9 << 64, -(10**9 << 64), (10**9 << 64) + 5, 999_999_999, -999_999_999, 10**9, -(10**9)]
+    vals += [int(rng.integers(-2**62, 2**62)) * int(rng.integers(1, 2**40)) for _ in range(3000)]
+    vals += [int(rng.integers(-2**63, 2**63)) << int(rng.integers(0, 64)) for _ in range(3000)]
+    for v in vals:
+        v = max(-(1 << 127), min((1 << 127) - 1, v))
+        assert bool(shim.shim_ts_decodes(v.to_bytes(16, "little", signed=True))) == oracle.timestamp_decodes(v), v

@@ -314,3 +314,79 @@ def test_get_many_walks_tables_newest_first():
                 break
         assert (int(tb[q]), int(rec[q]), int(rej[q])) == (exp_t, exp_r, exp_j), k
     assert set(tb.tolist()) == {-1, 0, 1, 2}
+
+
+# ---- N4: WAL replay (read_memtable_from_wal_file, lsm_tree.rs:552-574) --------------------------------------------
+
+def _wal_case(ents, **kw):
+    return sstable.build_wal(ents, **kw)
+
+
+def test_wal_replay_equals_the_memtable_the_writes_built():
+    """Every set_ex writes the entry to the WAL and to the memtable (lsm_tree.rs:740-768): replaying the log must
+    give the same SSTable as flushing the red-black tree those writes built -- whatever is in the padding."""
+    rng = np.random.default_rng(12)
+    ents = [(b"key%04d" % int(rng.integers(0, 300)), bytes(rng.integers(0, 256, int(rng.integers(0, 700)), dtype=np.uint8)),
+             1_700_000_000_000_000_000 + j) for j in range(1500)]
+    for pad in (0, 0xAB):
+        d, i, n, seen = oracle.wal_flush(_wal_case(ents, pad_byte=pad), capacity=8192)
+        md, mi, mn = oracle.memtable_flushes(sstable.build_run(ents), capacity=8192)[0]
+        assert seen == 1500 and n == mn and np.array_equal(d, md) and np.array_equal(i, mi)
+
+
+def test_wal_page_arithmetic_and_large_records():
+    """`pos + PAGE_SIZE - pos % PAGE_SIZE` jumps STRICTLY past the cursor: an entry whose size is a page multiple is
+    followed by a whole padding page (written that way by set_ex :741, skipped that way by the replay :568-571).
+    A record spanning several pages may hold bytes that look like records at its inner page boundaries."""
+    fake = sstable.encode_entry(b"ghost", b"boo", 5)
+    inner = (b"x" * (4096 - 8 - 3 - 8) + fake).ljust(3 * 4096 - 32 - 3, b"y")  # key is 3 bytes: data starts at byte 19
+    ents = [(b"aaa", inner, 10), (b"bbb", b"v", 11), (b"p" * (4096 - 32 - 100), b"q" * 100, 12), (b"ccc", b"w", 13)]
+    assert len(sstable.encode_entry(*ents[0])) == 3 * 4096 and len(sstable.encode_entry(*ents[2])) == 4096
+    wal = _wal_case(ents)
+    assert wal.size == (4 + 1 + 2 + 1) * 4096
+    assert bytes(wal[4096:4096 + len(fake)]) == fake  # a decodable "record" sits at a page boundary inside entry 0
+    d, i, n, seen = oracle.wal_flush(wal)
+    assert seen == 4 and [k for k, _, _ in sstable.parse_run(d, i)] == [b"aaa", b"bbb", b"ccc", b"p" * (4096 - 132)]
+
+
+def test_wal_zero_pages_corrupt_lengths_and_bad_timestamps():
+    ents = [(b"a", b"1", 100), (b"b", b"2", 101), (b"c", b"3", 102)]
+    wal = _wal_case(ents)
+    # trailing all-zero pages decode as Entry{key: [], data: [], ts: 0} (klen = dlen = 0) and are inserted
+    d, i, n, seen = oracle.wal_flush(np.concatenate([wal, np.zeros(2 * 4096, np.uint8)]))
+    assert seen == 5 and sstable.parse_run(d, i)[0] == (b"", b"", 0) and n == 4
+    # a length that exceeds the rest of the file drains the cursor: nothing after it is replayed
+    bad = wal.copy()
+    bad[4096:4104] = np.frombuffer((1 << 40).to_bytes(8, "little"), np.uint8)
+    d, i, n, seen = oracle.wal_flush(bad)
+    assert seen == 1 and [k for k, _, _ in sstable.parse_run(d, i)] == [b"a"]
+    # a timestamp outside `time`'s range fails to deserialize AFTER its bytes were consumed: skipped, replay continues
+    ents2 = [(b"a", b"1", 100), (b"b", b"2", 1 << 100), (b"c", b"3", 102)]
+    d, i, n, seen = oracle.wal_flush(_wal_case(ents2))
+    assert seen == 2 and [k for k, _, _ in sstable.parse_run(d, i)] == [b"a", b"c"]
+    # a torn tail (crash in the middle of a write): the last record never decodes
+    d, i, n, seen = oracle.wal_flush(wal[:2 * 4096 + 20])
+    assert seen == 2
+    assert oracle.wal_flush(np.zeros(0, np.uint8))[2:] == (0, 0)
+
+
+def test_wal_replay_fails_when_the_memtable_overflows():
+    ents = [(b"k%02d" % j, b"v", j) for j in range(9)]
+    with pytest.raises(oracle.OracleError, match="ReachedCapacity"):
+        oracle.wal_flush(_wal_case(ents), capacity=8)  # memtable.set(..)? (lsm_tree.rs:566, lib.rs:458-461)
+    assert oracle.wal_flush(_wal_case(ents + ents), capacity=9)[2] == 9  # replacements need no new node
+
+
+def test_timestamp_range_check_restated():
+    """time 0.3.30: floor-div by 1e9, `as i64` (wrapping), years -9999 ..= 9999."""
+    lo, hi = -377705116800 * 10**9, 253402300799 * 10**9 + 999_999_999
+
+    def model(v):
+        secs = ((v // 10**9 + 2**63) % 2**64) - 2**63
+        return -377705116800 <= secs <= 253402300799
+
+    for v in (0, lo, lo - 1, hi, hi + 1, -1, 1 << 100, -(1 << 127), (1 << 127) - 1, 10**9 << 64, (10**9 << 64) - 1):
+        assert oracle.timestamp_decodes(v) == model(v), v
+    assert oracle.timestamp_decodes(lo) and not oracle.timestamp_decodes(lo - 1)
+    assert oracle.timestamp_decodes(hi) and not oracle.timestamp_decodes(hi + 1)
+    assert oracle.timestamp_decodes(10**9 << 64)  # 2^64 seconds wrap to 0: the cast, not the value, is range-checked
