@@ -107,6 +107,30 @@ def main():
         print(f"GPU device-resident, {T} engines / host threads on one GPU: {el * 1e3:.1f} ms wall ({nbytes / 1e6 / el:.0f} MB/s)")
     print(f"CPU oracle (rb-tree inserts + flush, 1 core): {cpu * 1e3:.0f} ms ({nbytes / 1e6 / cpu:.0f} MB/s)")
 
+    # N4: recovery of ONE unflushed memtable from its write-ahead log (every write occupies >= one 4096-byte page)
+    p0, n = cuts[0]
+    ents = sstable.parse_run(batch[0], batch[1][:16 * (p0 + n)])[p0:p0 + n]
+    wal = sstable.build_wal(ents)
+    d_wal = torch.from_numpy(wal).to(dev)
+    wd = torch.empty(subs[0][0].numel() + 64, dtype=torch.uint8, device=dev)
+    wi = torch.empty(subs[0][1].numel() + 64, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    for _ in range(2):
+        eng.wal_flush_device(d_wal.data_ptr(), wal.size, (wd.data_ptr(), wd.numel() - 32, wi.data_ptr(), wi.numel() - 32))
+    t2 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        _, _, wn = eng.wal_flush_device(d_wal.data_ptr(), wal.size, (wd.data_ptr(), wd.numel() - 32, wi.data_ptr(), wi.numel() - 32))
+    torch.cuda.synchronize()
+    wal_wall = (time.perf_counter() - t2) / reps
+    t3 = time.perf_counter()
+    _, _, on, _ = oracle.wal_flush(wal, 8192, emulate_page_cache=True)
+    wal_cpu = time.perf_counter() - t3
+    assert wn == on == 8192 or wn == on
+    print(f"WAL replay + flush of one memtable ({n} logged writes, {wal.size / 1e6:.0f} MB log, {wn} distinct keys): GPU device-resident "
+          f"{wal_wall * 1e3:.2f} ms wall ({wal.size / 1e6 / wal_wall:.0f} MB/s of log, {n / wal_wall / 1e6:.1f} M writes/s); "
+          f"CPU oracle {wal_cpu * 1e3:.1f} ms ({n / wal_cpu / 1e6:.2f} M writes/s)")
+
 
 if __name__ == "__main__":
     main()
