@@ -29,6 +29,43 @@ def test_library_exports_every_declared_symbol():
     assert lib.dbeel_abi_version() == 1
 
 
+def test_headers_are_plain_c(tmp_path):
+    """The boundary is a C ABI: both headers compile as C99 (no C++-isms, no torch types), and a C translation unit
+    that uses every struct links against the built library."""
+    import subprocess
+    src = tmp_path / "use_abi.c"
+    src.write_text("""
+#include "dbeel_compact.h"
+#include "dbeel_tree.h"
+#include <stdio.h>
+int main(void) {
+    dbeel_run r = {0, 0, 0, 0};
+    dbeel_out o = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    dbeel_table t = {0, 0, 0, 0, 0, 0};
+    dbeel_lookup_result lr = {-1, 0, 0};
+    dbeel_flush_table ft = {0, 0, 0, 0, 0};
+    dbeel_stats st;
+    dbeel_engine *e = 0;
+    int rc = dbeel_engine_create(-1, &e); /* no such device: must fail, never fall back */
+    (void)r; (void)o; (void)t; (void)lr; (void)ft; (void)st;
+    printf("%d %d %s %llu\\n", dbeel_abi_version(), rc != DBEEL_OK, dbeel_strerror(DBEEL_ERR_TREE_FULL),
+           (unsigned long long)dbeel_bloom_file_size(1000, 0.01));
+    return sizeof(dbeel_lookup_result) == 16 ? 0 : 1;
+}
+""")
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(src)])
+    exe = tmp_path / "use_abi"
+    libdir = os.path.dirname(capi.LIB_PATH)
+    capi.lib()  # builds the library if it is not there yet
+    subprocess.check_call(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-ldbeel_compact",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    fields = out.stdout.split()
+    assert fields[0] == "1" and fields[1] == "1" and int(fields[-1]) == oracle.bloom_file_size(1000)
+
+
 def test_bloom_sizing_matches_oracle():
     lib = capi.lib()
     for n in [1, 2, 7, 1000, 65_536, 4_000_000, 8_000_000, 123_456_789]:
