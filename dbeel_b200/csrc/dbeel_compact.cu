@@ -70,7 +70,6 @@ struct dbeel_engine {
     uint8_t async_seed[32] = {};
     int sm_count = 148;
     int merge_variant = 1;      // DBEEL_MERGE: 0 = one CTA per tile with plain loads, 1 = persistent TMA (default)
-    int zigzag = 1;             // DBEEL_ZIGZAG: consecutive kernels walk their tiles in opposite directions (L2 reuse; A/B switch)
     int narrow_loads = 1;       // DBEEL_NARROW: .L2::64B loads for random accesses in extract / resolve (A/B switch)
 };
 
@@ -372,9 +371,6 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     CU(cudaEventRecord(e->ev[EV_EXTRACT], s));
 
     // ---- K2/K3: merge levels, ping-pong between rec_a and rec_b
-    // extract / block sort wrote the records front to back: the first consumer walks back to front, and so on alternately
-    const uint32_t zz = e->zigzag ? 1u : 0u;
-    uint32_t dir = zz;
     const Rec *src = p.rec_a;
     Rec *dst = p.rec_b;
     for (uint32_t l = 0; l < levels; l++) {
@@ -387,8 +383,7 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
         } else { // persistent, TMA bulk loads / stores + mbarrier
             uint64_t grid = (uint64_t)e->sm_count * 3;
             if (grid > t_ub) grid = t_ub;
-            k_merge_tma<<<(uint32_t)grid, kMergeThreads, 2 * kMergeBufRecs * sizeof(Rec), s>>>(p, l, src, dst, dir);
-            dir ^= zz;
+            k_merge_tma<<<(uint32_t)grid, kMergeThreads, 2 * kMergeBufRecs * sizeof(Rec), s>>>(p, l, src, dst);
         }
         launches += 2;
         const Rec *t = src;
@@ -403,13 +398,11 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
         launches++;
     }
     uint4 *res = reinterpret_cast<uint4 *>(dst); // the ping-pong buffer that does not hold the merged order
-    if (e->narrow_loads) k_resolve<true><<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, src, res, dir);
-    else k_resolve<false><<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, src, res, dir);
-    dir ^= zz;
+    if (e->narrow_loads) k_resolve<true><<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, src, res);
+    else k_resolve<false><<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, src, res);
     k_scan_tiles<<<(uint32_t)res_chunks, 1024, 0, s>>>(p);
     k_scan_chunks<<<1, 1024, 0, s>>>(p);
-    k_emit<<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, res, dir);
-    dir ^= zz;
+    k_emit<<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, res);
     launches += 4;
     if (many) {
         k_flush_table<<<(n_runs + 1 + 127) / 128, 128, 0, s>>>(p, res);
@@ -419,7 +412,7 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
 
     // ---- K5: gather + bloom (fused epilogue)
     if (gather_tiles) {
-        k_gather<<<(uint32_t)gather_tiles, kGatherThreads, 0, s>>>(p, dir);
+        k_gather<<<(uint32_t)gather_tiles, kGatherThreads, 0, s>>>(p);
     }
     launches++;
     if (many) { // only now may the .index offsets become file-relative: the gather kernel reads them as stream offsets
@@ -1159,7 +1152,6 @@ int dbeel_engine_create(int device, dbeel_engine **out) {
     if (const char *v = getenv("DBEEL_PIPELINE")) e->pipeline = atoi(v);
     if (const char *v = getenv("DBEEL_PIPELINE_MIN_KB")) e->pipeline_min_bytes = (uint64_t)(atoi(v) > 0 ? atoi(v) : 1) << 10;
     if (const char *v = getenv("DBEEL_PARTITION_KB")) e->partition_bytes = (uint64_t)(atoi(v) > 0 ? atoi(v) : 1) << 10;
-    if (const char *v = getenv("DBEEL_ZIGZAG")) e->zigzag = atoi(v) != 0;
     if (const char *v = getenv("DBEEL_PARTITION_TAPER")) e->partition_taper = atoi(v) != 0;
     if (const char *v = getenv("DBEEL_PARTITION_MB")) e->partition_bytes = (uint64_t)(atoi(v) > 0 ? atoi(v) : 128) << 20;
     if (cudaFuncSetAttribute(k_merge_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kMergeBufRecs * sizeof(Rec))) != cudaSuccess) {

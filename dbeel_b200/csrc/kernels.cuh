@@ -721,9 +721,7 @@ __device__ __forceinline__ void tma_store_1d(void *gmem_dst, const void *smem_sr
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
 }
 
-// `rev`: visit the tiles from the last to the first.  Consecutive kernels of a job alternate direction, so each one
-// starts on the ~100 MB its predecessor wrote last -- still in the 126 MB L2 -- instead of on what was evicted first.
-__global__ void __launch_bounds__(kMergeThreads, 3) k_merge_tma(Params p, uint32_t level, const Rec *src, Rec *dst, uint32_t rev) {
+__global__ void __launch_bounds__(kMergeThreads, 3) k_merge_tma(Params p, uint32_t level, const Rec *src, Rec *dst) {
     extern __shared__ __align__(128) uint8_t s_raw[];
     Rec *bufs[2] = {reinterpret_cast<Rec *>(s_raw), reinterpret_cast<Rec *>(s_raw) + kMergeBufRecs};
     __shared__ __align__(8) uint64_t s_bar[2];
@@ -746,10 +744,8 @@ __global__ void __launch_bounds__(kMergeThreads, 3) k_merge_tma(Params p, uint32
         if (d.n_b) tma_load_1d(buf + d.n_a, &src[d.b_src], d.n_b * 16u, bar);
     };
 
-    // `tile` counts in visiting order; ph() is the tile actually merged (ids >= n_tiles give empty descriptors either way)
-    auto ph = [&](uint32_t t) { return rev ? (t < n_tiles ? n_tiles - 1 - t : t) : t; };
-    MergeDesc cur = merge_desc(p, level, ph(tile));
-    MergeDesc nxt = merge_desc(p, level, ph(tile + G));
+    MergeDesc cur = merge_desc(p, level, tile);
+    MergeDesc nxt = merge_desc(p, level, tile + G);
     if (tid == 0) issue(cur, bufs[0], &s_bar[0]);
     for (uint32_t q = 0;; q++) {
         Rec *s = bufs[q & 1];
@@ -759,7 +755,7 @@ __global__ void __launch_bounds__(kMergeThreads, 3) k_merge_tma(Params p, uint32
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             issue(nxt, bufs[(q + 1) & 1], &s_bar[(q + 1) & 1]);
         }
-        const MergeDesc nn = merge_desc(p, level, ph(tile + 2 * G)); // consumed one iteration from now
+        const MergeDesc nn = merge_desc(p, level, tile + 2 * G); // consumed one iteration from now
         while (!mbar_try_wait(&s_bar[q & 1], (q >> 1) & 1)) {}
 
         const uint32_t nA = cur.n_a, nB = cur.n_b, n = nA + nB;
@@ -818,7 +814,7 @@ __device__ __forceinline__ void ld_ts(const uint8_t *entry, uint32_t full_size, 
 }
 
 template <bool kNarrow>
-__global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec *m, uint4 *res, uint32_t rev) {
+__global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec *m, uint4 *res) {
     constexpr int NT = kResolveThreads;
     __shared__ Rec s_rec[NT + 2];
     __shared__ unsigned long long s_entry[NT]; // device address of each record's entry
@@ -828,8 +824,7 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec
     const Ctl *c = p.ctl;
     const uint32_t tid = threadIdx.x;
     const uint32_t span = c->span;
-    const uint32_t blk = rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
-    const uint32_t i0 = blk * NT;
+    const uint32_t i0 = blockIdx.x * NT;
     if (i0 >= span) return;
     const uint32_t skip = c->prefix_len + kWindowBytes;
     const uint32_t i = i0 + tid;
@@ -945,8 +940,8 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec
         unsigned long long tb = 0;
         uint32_t tc = 0;
         for (int w = 0; w < NT / 32; w++) { tb += s_tlo[w]; tc += s_ks[w]; }
-        p.tile_bytes[blk] = tb;
-        p.tile_count[blk] = tc;
+        p.tile_bytes[blockIdx.x] = tb;
+        p.tile_count[blockIdx.x] = tc;
     }
 }
 
@@ -1034,13 +1029,12 @@ __global__ void __launch_bounds__(1024) k_scan_chunks(Params p) {
     if (threadIdx.x == 0) { c->out_data_len = tb; c->out_items = tc; }
 }
 
-__global__ void __launch_bounds__(kResolveThreads) k_emit(Params p, const uint4 *res, uint32_t rev) {
+__global__ void __launch_bounds__(kResolveThreads) k_emit(Params p, const uint4 *res) {
     constexpr int NT = kResolveThreads;
     __shared__ unsigned long long s_wb[NT / 32];
     __shared__ uint32_t s_wc[NT / 32];
     const uint32_t total = p.ctl->span;
-    const uint32_t blk = rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
-    const uint32_t i0 = blk * NT;
+    const uint32_t i0 = blockIdx.x * NT;
     if (i0 >= total) return;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t i = i0 + tid;
@@ -1058,8 +1052,8 @@ __global__ void __launch_bounds__(kResolveThreads) k_emit(Params p, const uint4 
     if (lane == 31) { s_wb[warp] = ib; s_wc[warp] = ic; }
     __syncthreads();
     if (!fs) return;
-    unsigned long long off = p.chunk_bytes[blk >> 10] + p.tile_bytes[blk] + ib - fs; // within this job's .data
-    uint32_t pos = p.chunk_count[blk >> 10] + p.tile_count[blk] + ic - 1;
+    unsigned long long off = p.chunk_bytes[blockIdx.x >> 10] + p.tile_bytes[blockIdx.x] + ib - fs; // within this job's .data
+    uint32_t pos = p.chunk_count[blockIdx.x >> 10] + p.tile_count[blockIdx.x] + ic - 1;
     for (uint32_t w = 0; w < warp; w++) { off += s_wb[w]; pos += s_wc[w]; }
     const unsigned long long src = (unsigned long long)it.x | ((unsigned long long)it.y << 32);
     const unsigned long long file_off = off + p.out_offset_base; // a key-range partition continues the file of the previous ones
@@ -1153,10 +1147,7 @@ __device__ __forceinline__ uint4 realign16_sel(uint4 A, uint4 B, uint32_t sh) {
 // and then walks the (sorted) entry ends 512 bytes at a time, each lane counting how many entries
 // end at or before its own vector (one OR-reduction + popcount per chunk).
 
-#ifndef DBEEL_GATHER_MINB
-#define DBEEL_GATHER_MINB (1536 / DBEEL_GATHER_THREADS) // 12 CTAs of 128 threads per SM: 40 registers (a few spills) beat 10 CTAs at 48
-#endif
-__global__ void __launch_bounds__(kGatherThreads, DBEEL_GATHER_MINB) k_gather(Params p, uint32_t rev) {
+__global__ void __launch_bounds__(kGatherThreads, 1536 / kGatherThreads) k_gather(Params p) {
     constexpr int NT = kGatherThreads;
     constexpr int VPT = kGatherVecsPerThread;
     __shared__ unsigned long long s_adj[kGatherMaxEntries]; // entry address minus its tile-relative start
@@ -1165,7 +1156,7 @@ __global__ void __launch_bounds__(kGatherThreads, DBEEL_GATHER_MINB) k_gather(Pa
     const Ctl *c = p.ctl;
     const unsigned long long out_len = c->out_data_len;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t tile_id = rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+    const uint32_t tile_id = blockIdx.x;
     const unsigned long long T0 = (unsigned long long)tile_id * kGatherTileBytes;
     if (T0 >= out_len) return;
     const uint32_t tile_len = out_len - T0 < kGatherTileBytes ? (uint32_t)(out_len - T0) : (uint32_t)kGatherTileBytes;
