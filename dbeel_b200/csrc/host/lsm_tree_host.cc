@@ -21,7 +21,7 @@ namespace fs = std::filesystem;
 namespace {
 
 constexpr int kIndexPadding = 20; // mod.rs:21
-const char *kData = "data", *kIndex = "index", *kBloom = "bloom";
+const char *kData = "data", *kIndex = "index", *kBloom = "bloom", *kMemtable = "memtable";
 const char *kCompactData = "compact_data", *kCompactIndex = "compact_index", *kCompactBloom = "compact_bloom",
            *kCompactAction = "compact_action";
 
@@ -332,6 +332,47 @@ int dbeel_tree_flush(dbeel_tree *t, const dbeel_run *batch, uint64_t *written_in
     t->write_sstable_index = idx + 2;
     if (written_index) *written_index = idx;
     if (items_written) *items_written = out.items_written;
+    return DBEEL_OK;
+}
+
+int dbeel_tree_recover_wal(dbeel_tree *t, uint32_t tree_capacity, uint64_t *wal_file_index, uint64_t *items_written) {
+    if (!t) return DBEEL_ERR_INVALID_ARG;
+    t->err.clear();
+    if (items_written) *items_written = 0;
+    std::error_code ec;
+    std::vector<uint64_t> wal;
+    uint64_t idx;
+    for (auto &de : fs::directory_iterator(t->dir, ec))
+        if (parse_name(de.path().filename().string(), kMemtable, &idx)) wal.push_back(idx);
+    std::sort(wal.begin(), wal.end()); // lsm_tree.rs:467-476
+    uint64_t current = 0;
+    if (wal.size() == 1) {
+        current = wal[0];
+    } else if (wal.size() == 2) { // "A flush did not finish for some reason, do it now." (:481-511)
+        current = wal[1];
+        const std::string old_path = file_path(t->dir, wal[0], kMemtable);
+        PinnedBuf log;
+        int rc = read_file(t, old_path, &log);
+        if (rc) return rc;
+        const uint64_t pages = (log.len + 4095) / 4096;
+        PinnedBuf od(log.len), oi(pages * 16);
+        if (!od.p || !oi.p) { t->err = "dbeel_host_alloc failed"; return DBEEL_ERR_NOMEM; }
+        dbeel_out out{od.p, log.len, 0, oi.p, pages * 16, 0, nullptr, 0, 0, 0};
+        rc = dbeel_wal_flush(t->engine, log.p, log.len, tree_capacity, &out); // read_memtable_from_wal_file + flush_memtable_to_disk
+        if (rc) { t->err = dbeel_last_error(t->engine); return rc; }
+        // The reference writes the recovered table under the NEWER log's index (get_data_file_paths(&dir, wal_file_index),
+        // :491-492), not under the index the interrupted flush would have used, and does not add it to `sstables` for
+        // this open (the list was built before, :440-459): the next open discovers it.  Mirrored as is.
+        rc = write_file(t, file_path(t->dir, current, kData), od.p, out.data_len);
+        if (!rc) rc = write_file(t, file_path(t->dir, current, kIndex), oi.p, out.index_len);
+        if (rc) return rc;
+        if (unlink(old_path.c_str()) != 0) return io_fail(t, "remove " + old_path); // :510
+        if (items_written) *items_written = out.items_written;
+    } else if (wal.size() > 2) {
+        t->err = "Cannot have more than 2 WAL files"; // the reference panics (:513)
+        return DBEEL_ERR_INVALID_ARG;
+    }
+    if (wal_file_index) *wal_file_index = current;
     return DBEEL_OK;
 }
 

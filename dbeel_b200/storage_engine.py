@@ -39,6 +39,8 @@ def _lib():
         L.dbeel_tree_compact.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32, C.c_uint64, C.c_int, C.c_char_p]
         L.dbeel_tree_flush.restype = C.c_int
         L.dbeel_tree_flush.argtypes = [C.c_void_p, C.POINTER(capi.Run), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.dbeel_tree_recover_wal.restype = C.c_int
+        L.dbeel_tree_recover_wal.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.dbeel_tree_last_error.restype = C.c_char_p
         L.dbeel_tree_last_error.argtypes = [C.c_void_p]
         L.dbeel_memtable_cut.restype = C.c_uint64
@@ -52,7 +54,7 @@ def _lib():
 
 
 TREE_EXPORTS = ["dbeel_tree_open", "dbeel_tree_close", "dbeel_tree_sstables", "dbeel_tree_write_sstable_index",
-                "dbeel_tree_compact", "dbeel_tree_flush", "dbeel_tree_last_error", "dbeel_memtable_cut",
+                "dbeel_tree_compact", "dbeel_tree_flush", "dbeel_tree_recover_wal", "dbeel_tree_last_error", "dbeel_memtable_cut",
                 "dbeel_plan_compactions"]
 
 
@@ -132,6 +134,13 @@ class LSMTree:
         run, _keep = _run_struct(batch)
         wi, n = C.c_uint64(), C.c_uint64()
         self._check(_lib().dbeel_tree_flush(self._h, C.byref(run), C.byref(wi), C.byref(n)), "LSMTree.flush")
+        return int(wi.value), int(n.value)
+
+    def recover_wal(self, tree_capacity: int = capi.DEFAULT_TREE_CAPACITY) -> Tuple[int, int]:
+        """open_or_create_ex's WAL step (lsm_tree.rs:466-513): with two `.memtable` files the older one is replayed and
+        flushed.  Returns (index of the log that stays active, entries of the recovered SSTable)."""
+        wi, n = C.c_uint64(), C.c_uint64()
+        self._check(_lib().dbeel_tree_recover_wal(self._h, tree_capacity, C.byref(wi), C.byref(n)), "LSMTree.recover_wal")
         return int(wi.value), int(n.value)
 
     def compact_tree(self, compaction_factor: int = 2, bloom_seed: Optional[bytes] = None):

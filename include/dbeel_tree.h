@@ -6,7 +6,9 @@
  * reference's own interface for this path -- same names, argument meaning, error behaviour:
  *
  *   dbeel_tree_open        <- LSMTree::open_or_create_ex: journal replay + SSTable discovery
- *                             (src/storage_engine/lsm_tree.rs:424-465; WAL recovery is out of scope)
+ *                             (src/storage_engine/lsm_tree.rs:424-465)
+ *   dbeel_tree_recover_wal <- the rest of open_or_create_ex: an unflushed memtable's log is replayed and flushed
+ *                             (lsm_tree.rs:466-513, read_memtable_from_wal_file :552-574) through dbeel_wal_flush()
  *   dbeel_tree_compact     <- LSMTree::compact(indices_to_compact, output_index, keep_tombstones)
  *                             (lsm_tree.rs:950-1156): same files, same CompactionAction journal
  *                             (:73-77, :1078-1111), same renames / deletes; the merge core
@@ -47,6 +49,12 @@ int dbeel_tree_compact(dbeel_tree *t, const uint64_t *indices_to_compact, uint32
 
 /* Flush one memtable's arrivals (host buffers, arrival order) to the next even index. */
 int dbeel_tree_flush(dbeel_tree *t, const dbeel_run *batch, uint64_t *written_index, uint64_t *items_written);
+
+/* WAL recovery step of open_or_create_ex.  0 logs: *wal_file_index = 0; 1 log: its index; 2 logs: the older one is
+ * replayed (memtable of `tree_capacity` entries, DBEEL_ERR_TREE_FULL like the reference's ReachedCapacity), flushed
+ * to `<newer index>.data / .index` exactly as the reference does, and removed; more than 2: error (the reference
+ * panics).  *items_written = entries of the recovered SSTable (0 if nothing was recovered). */
+int dbeel_tree_recover_wal(dbeel_tree *t, uint32_t tree_capacity, uint64_t *wal_file_index, uint64_t *items_written);
 
 const char *dbeel_tree_last_error(const dbeel_tree *t);
 

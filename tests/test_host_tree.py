@@ -210,3 +210,47 @@ def test_cfg5_pipeline_flush_then_tiered_compactions(engine, tmp_path):
             assert np.array_equal(np.fromfile(bloom_path, dtype=np.uint8), mb)
     # nothing but live SSTable files is left behind (journals and compact_* temporaries are gone)
     assert all(f.split(".")[1] in ("data", "index", "bloom") for f in os.listdir(d))
+
+
+def test_wal_recovery_without_an_unflushed_log_needs_no_gpu(tmp_path):
+    """0 or 1 `.memtable` files: nothing to replay (lsm_tree.rs:478-480); 3 is the reference's panic (:513)."""
+    t = se.LSMTree(str(tmp_path), _fake_engine())
+    assert t.recover_wal() == (0, 0)
+    open(os.path.join(str(tmp_path), sstable.file_name(6, "memtable")), "wb").close()
+    assert t.recover_wal() == (6, 0)
+    for i in (8, 10):
+        open(os.path.join(str(tmp_path), sstable.file_name(i, "memtable")), "wb").close()
+    with pytest.raises(capi.DbeelError):
+        t.recover_wal()
+
+
+@pytest.mark.gpu
+def test_unflushed_log_is_replayed_and_flushed_on_open(engine, tmp_path):
+    """lsm_tree.rs:481-511: two logs on disk -> the older one becomes an SSTable under the NEWER log's index (the
+    reference's own choice, :491-492) and is removed; the files equal the oracle's replay + flush."""
+    d = str(tmp_path)
+    rng = np.random.default_rng(8)
+    ents = [(b"user%04d" % int(rng.integers(0, 700)), bytes(rng.integers(0, 256, int(rng.integers(0, 900)), dtype=np.uint8)),
+             BASE_TS + j) for j in range(2500)]
+    wal = sstable.build_wal(ents, pad_byte=0x5A)
+    with open(os.path.join(d, sstable.file_name(4, "memtable")), "wb") as f:
+        f.write(wal.tobytes())
+    with open(os.path.join(d, sstable.file_name(6, "memtable")), "wb") as f:
+        f.write(sstable.build_wal(ents[:3]).tobytes())
+    tree = se.LSMTree.open_or_create(d, engine)
+    current, items = tree.recover_wal()
+    od, oi, on, _ = oracle.wal_flush(wal)
+    assert (current, items) == (6, on)
+    assert_run_equal(sstable.read_run_files(d, 6), (od, oi), "recovered sstable")
+    assert not os.path.exists(os.path.join(d, sstable.file_name(4, "memtable")))
+    assert os.path.exists(os.path.join(d, sstable.file_name(6, "memtable")))
+    assert tree.sstable_indices_and_sizes() == []  # the list was built before the recovery (:440-459): next open sees it
+    tree.close()
+    tree = se.LSMTree.open_or_create(d, engine)
+    assert tree.sstable_indices_and_sizes() == [(6, on)] and tree.recover_wal() == (6, 0)
+    # a log with more distinct keys than the memtable holds cannot be replayed (memtable.set(..)? -> ReachedCapacity)
+    with open(os.path.join(d, sstable.file_name(8, "memtable")), "wb") as f:
+        f.write(wal.tobytes())
+    with pytest.raises(capi.DbeelError) as ei:
+        tree.recover_wal(tree_capacity=100)
+    assert ei.value.code == capi.ERR_TREE_FULL
