@@ -335,6 +335,29 @@ int dbeel_tree_flush(dbeel_tree *t, const dbeel_run *batch, uint64_t *written_in
     return DBEEL_OK;
 }
 
+int dbeel_tree_get_many(dbeel_tree *t, const void *keys, const uint64_t *key_offsets, uint64_t n_keys, uint32_t mode,
+                        dbeel_lookup_result *results) {
+    if (!t || (n_keys && (!key_offsets || !results))) return DBEEL_ERR_INVALID_ARG;
+    t->err.clear();
+    // get_entry walks `self.sstables` (ascending index) newest first (lsm_tree.rs:686-688); every table brings its
+    // .bloom if one exists on disk (SSTable::new_with_bloom_read, :94-101)
+    const size_t n = t->sstables.size();
+    std::vector<PinnedBuf> data(n), index(n), bloom(n);
+    std::vector<dbeel_table> tables(n);
+    for (size_t i = 0; i < n; i++) {
+        const uint64_t idx = t->sstables[i].index;
+        int rc = read_file(t, file_path(t->dir, idx, kData), &data[i]);
+        if (!rc) rc = read_file(t, file_path(t->dir, idx, kIndex), &index[i]);
+        const std::string bp = file_path(t->dir, idx, kBloom);
+        if (!rc && exists(bp)) rc = read_file(t, bp, &bloom[i]);
+        if (rc) return rc;
+        tables[i] = dbeel_table{data[i].p, data[i].len, index[i].p, index[i].len, bloom[i].len ? bloom[i].p : nullptr, bloom[i].len};
+    }
+    int rc = dbeel_get_many(t->engine, tables.data(), (uint32_t)n, keys, key_offsets, n_keys, mode, results);
+    if (rc) t->err = dbeel_last_error(t->engine);
+    return rc;
+}
+
 int dbeel_tree_recover_wal(dbeel_tree *t, uint32_t tree_capacity, uint64_t *wal_file_index, uint64_t *items_written) {
     if (!t) return DBEEL_ERR_INVALID_ARG;
     t->err.clear();

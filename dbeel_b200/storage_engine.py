@@ -39,6 +39,8 @@ def _lib():
         L.dbeel_tree_compact.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32, C.c_uint64, C.c_int, C.c_char_p]
         L.dbeel_tree_flush.restype = C.c_int
         L.dbeel_tree_flush.argtypes = [C.c_void_p, C.POINTER(capi.Run), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.dbeel_tree_get_many.restype = C.c_int
+        L.dbeel_tree_get_many.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
         L.dbeel_tree_recover_wal.restype = C.c_int
         L.dbeel_tree_recover_wal.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.dbeel_tree_last_error.restype = C.c_char_p
@@ -54,7 +56,7 @@ def _lib():
 
 
 TREE_EXPORTS = ["dbeel_tree_open", "dbeel_tree_close", "dbeel_tree_sstables", "dbeel_tree_write_sstable_index",
-                "dbeel_tree_compact", "dbeel_tree_flush", "dbeel_tree_recover_wal", "dbeel_tree_last_error", "dbeel_memtable_cut",
+                "dbeel_tree_compact", "dbeel_tree_flush", "dbeel_tree_recover_wal", "dbeel_tree_get_many", "dbeel_tree_last_error", "dbeel_memtable_cut",
                 "dbeel_plan_compactions"]
 
 
@@ -135,6 +137,31 @@ class LSMTree:
         wi, n = C.c_uint64(), C.c_uint64()
         self._check(_lib().dbeel_tree_flush(self._h, C.byref(run), C.byref(wi), C.byref(n)), "LSMTree.flush")
         return int(wi.value), int(n.value)
+
+    def get_many(self, keys: Sequence[bytes], mode: int = capi.LOOKUP_REFERENCE):
+        """get_entry's SSTable loop for a batch of keys: a list of `data` bytes (b"" = tombstone) or None per key,
+        like LSMTree::get (lsm_tree.rs:722-724) after the memtables missed."""
+        import numpy as np
+        from . import sstable
+        blob, off = capi.pack_keys(keys)
+        res = np.zeros(len(keys), dtype=capi.LOOKUP_DTYPE)
+        self._check(_lib().dbeel_tree_get_many(self._h, blob.ctypes.data if blob.size else None, off.ctypes.data, len(keys), mode,
+                                               res.ctypes.data), "LSMTree.get_many")
+        tables = self.sstable_indices_and_sizes()
+        files = {}
+        out = []
+        for row in res:
+            if row["table"] < 0:
+                out.append(None)
+                continue
+            idx = tables[int(row["table"])][0]
+            if idx not in files:
+                files[idx] = sstable.read_run_files(self.dir, idx)
+            d, i = files[idx]
+            rec = bytes(i[16 * int(row["record"]):16 * int(row["record"]) + 16])
+            o, ks, fs = int.from_bytes(rec[:8], "little"), int.from_bytes(rec[8:12], "little"), int.from_bytes(rec[12:], "little")
+            out.append(bytes(d[o + ks + 8:o + fs - 16]))  # EntryValue.data (entry = key | dlen | data | ts)
+        return out
 
     def recover_wal(self, tree_capacity: int = capi.DEFAULT_TREE_CAPACITY) -> Tuple[int, int]:
         """open_or_create_ex's WAL step (lsm_tree.rs:466-513): with two `.memtable` files the older one is replayed and

@@ -16,6 +16,7 @@
  *   dbeel_tree_flush       <- LSMTree::flush's SSTable part (lsm_tree.rs:875-915): writes the
  *                             next even index through dbeel_flush(), no bloom
  *   dbeel_tree_sstables    <- LSMTree::sstable_indices_and_sizes (lsm_tree.rs:592-598)
+ *   dbeel_tree_get_many    <- the SSTable loop of LSMTree::get_entry (lsm_tree.rs:686-719) through dbeel_get_many()
  *   dbeel_memtable_cut     <- RedBlackTree::set + active_memtable_full (rbtree_arena lib.rs:497-534,
  *                             lsm_tree.rs:600-603,757-765): how many arrivals fill one memtable
  *   dbeel_plan_compactions <- compact_tree's size-tiered picker (src/tasks/compaction.rs:35-102),
@@ -49,6 +50,12 @@ int dbeel_tree_compact(dbeel_tree *t, const uint64_t *indices_to_compact, uint32
 
 /* Flush one memtable's arrivals (host buffers, arrival order) to the next even index. */
 int dbeel_tree_flush(dbeel_tree *t, const dbeel_run *batch, uint64_t *written_index, uint64_t *items_written);
+
+/* The SSTable loop of LSMTree::get_entry (lsm_tree.rs:686-719) for a batch of keys, over the tree's files (each table
+ * with its .bloom if the file exists): results[i].table is a position in dbeel_tree_sstables() order.  Keys / modes /
+ * rows as in dbeel_get_many.  The memtable look-ups in front of it (:677-684) are the caller's. */
+int dbeel_tree_get_many(dbeel_tree *t, const void *keys, const uint64_t *key_offsets, uint64_t n_keys, uint32_t mode,
+                        dbeel_lookup_result *results);
 
 /* WAL recovery step of open_or_create_ex.  0 logs: *wal_file_index = 0; 1 log: its index; 2 logs: the older one is
  * replayed (memtable of `tree_capacity` entries, DBEEL_ERR_TREE_FULL like the reference's ReachedCapacity), flushed

@@ -142,9 +142,16 @@ def test_get_after_compaction_on_files(engine, tmp_path):
     assert sorted(os.listdir(d)) == [sstable.file_name(5, "data"), sstable.file_name(5, "index")]  # no bloom: <= 1 MiB
     od, oi, _, on = oracle.compact(inputs, False)
     assert_run_equal(sstable.read_run_files(d, 5), (od, oi), "compacted files")
+    # validate_tree_after_compaction's reads (:1386-1390), batched through the GPU read path, both search modes
+    for mode in (capi.LOOKUP_REFERENCE, capi.LOOKUP_EXACT):
+        assert tree.get_many([u16key(0), u16key(2), u16key(10), u16key(1), u16key(4)], mode) == \
+            [u16key(0), u16key(2), u16key(10), None, None]
+    assert tree.get_many([u16key(n) for n in range(94)], capi.LOOKUP_EXACT) == \
+        [None if n in (1, 4) else u16key(n) for n in range(94)]
     tree.close()
     tree = se.LSMTree.open_or_create(d, engine)  # reopening the tree (:1439-1443)
     assert tree.sstable_indices_and_sizes() == [(5, 92)] and tree.write_sstable_index == 6
+    assert tree.get_many([u16key(10), u16key(4)]) == [u16key(10), None]
 
 
 @pytest.mark.gpu

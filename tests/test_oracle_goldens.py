@@ -290,6 +290,23 @@ def test_reference_point_lookup_loop_restated():
     assert nos > 1900  # absent keys: the filter says no ~99% of the time
 
 
+def test_point_reads_of_get_after_compaction():
+    """The reference's own read assertions (validate_tree_after_compaction, lsm_tree.rs:1386-1390) through the restated
+    binary_search: after compact(&[0,2,4], 5, false) keys 0, 2 and 10 are found with their values, 1 and 4 are gone.
+    This is the pin of orc_sstable_lookup on the reference's tests."""
+    u = lambda n: int(n).to_bytes(2, "little")
+    writes = [(u(n), u(n), 1_700_000_000_000_000_000 + n) for n in range(94)] + [(u(1), b"", 2 * 10**18), (u(4), b"", 2 * 10**18 + 1)]
+    runs = [(d, i) for d, i, _ in oracle.memtable_flushes(sstable.build_run(writes), capacity=32)]
+    d, i, _, n = oracle.compact(runs, False)
+    assert n == 92
+    ents = sstable.parse_run(d, i)
+    for k in (0, 2, 10):
+        found, rec, _ = oracle.sstable_lookup((d, i), None, u(k))
+        assert found and ents[rec][:2] == (u(k), u(k))
+    for k in (1, 4):
+        assert oracle.sstable_lookup((d, i), None, u(k)) == (False, None, False)
+
+
 def test_get_many_walks_tables_newest_first():
     """get_entry (lsm_tree.rs:686-719): `sstables.iter().rev()`, a filter that says no skips the table, the first
     table whose binary_search finds the key answers.  The batch form must agree with the per-table restatement."""
