@@ -176,6 +176,10 @@ def test_compact_tree_writes_bloom_file(engine, tmp_path):
     bloom = np.fromfile(os.path.join(d, sstable.file_name(1, "bloom")), dtype=np.uint8)
     assert np.array_equal(bloom, ob)
     assert sorted(os.listdir(d)) == [sstable.file_name(1, e) for e in ("bloom", "data", "index")]
+    # reads through the filter the compaction just wrote (SSTable::new_with_bloom_read, lsm_tree.rs:94-101)
+    want = {k: v for k, v, _ in sstable.parse_run(od, oi)}
+    probe = [b"\xb0k%015d" % n for n in range(0, 5000, 7)]
+    assert tree.get_many(probe, capi.LOOKUP_EXACT) == [want.get(k) for k in probe]
 
 
 @pytest.mark.gpu
