@@ -34,6 +34,7 @@ EXPORTS = ["dbeel_abi_version", "dbeel_engine_create", "dbeel_engine_destroy", "
            "dbeel_compact", "dbeel_compact_device", "dbeel_compact_submit", "dbeel_poll", "dbeel_wait",
            "dbeel_flush", "dbeel_flush_device", "dbeel_flush_many", "dbeel_flush_many_device",
            "dbeel_get_many", "dbeel_get_many_device", "dbeel_wal_flush", "dbeel_wal_flush_device",
+           "dbeel_compact_many_bound", "dbeel_compact_many", "dbeel_compact_many_device",
            "dbeel_bloom_bitmap_bytes", "dbeel_bloom_k_num", "dbeel_bloom_file_size", "dbeel_host_alloc",
            "dbeel_host_free", "dbeel_last_stats", "dbeel_last_error", "dbeel_strerror"]
 
@@ -52,6 +53,15 @@ class Out(C.Structure):
 class FlushTable(C.Structure):
     _fields_ = [("data_off", C.c_uint64), ("data_len", C.c_uint64), ("index_off", C.c_uint64),
                 ("index_len", C.c_uint64), ("items", C.c_uint64)]
+
+
+class Job(C.Structure):
+    _fields_ = [("runs", C.POINTER(Run)), ("n_runs", C.c_uint32), ("keep_tombstones", C.c_int32), ("bloom_seed", C.c_char_p)]
+
+
+class JobResult(C.Structure):
+    _fields_ = [("data_off", C.c_uint64), ("data_len", C.c_uint64), ("index_off", C.c_uint64), ("index_len", C.c_uint64),
+                ("bloom_off", C.c_uint64), ("bloom_len", C.c_uint64), ("items_written", C.c_uint64)]
 
 
 class Table(C.Structure):
@@ -146,6 +156,12 @@ def lib():
             f.restype = C.c_int
             f.argtypes = [C.c_void_p, C.POINTER(Table), C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32,
                           C.c_void_p]
+        L.dbeel_compact_many_bound.restype = C.c_int
+        L.dbeel_compact_many_bound.argtypes = [C.POINTER(Job), C.c_uint32, C.c_uint64, C.c_double] + [C.POINTER(C.c_uint64)] * 3
+        for name in ("dbeel_compact_many", "dbeel_compact_many_device"):
+            f = getattr(L, name)
+            f.restype = C.c_int
+            f.argtypes = [C.c_void_p, C.POINTER(Job), C.c_uint32, C.c_uint64, C.c_double, C.POINTER(Out), C.POINTER(JobResult)]
         for name in ("dbeel_wal_flush", "dbeel_wal_flush_device"):
             f = getattr(L, name)
             f.restype = C.c_int
@@ -337,6 +353,53 @@ class Engine:
         self._check(lib().dbeel_flush_many_device(self._h, arr, n, C.byref(out), table), "dbeel_flush_many_device")
         rows = [{k: int(getattr(t, k)) for k, _ in FlushTable._fields_} for t in table[:n]]
         return int(out.data_len), int(out.index_len), int(out.items_written), rows
+
+    # ---- N1: many compactions per launch sequence -------------------------------------------
+    @staticmethod
+    def _jobs_array(jobs_ptrs, seeds):
+        """jobs_ptrs: per job (list of (data_ptr, data_len, index_ptr, index_len), keep_tombstones)."""
+        n = len(jobs_ptrs)
+        arr = (Job * max(1, n))()
+        keep = []
+        for j, (runs, keep_t) in enumerate(jobs_ptrs):
+            ra = (Run * max(1, len(runs)))()
+            for k, r in enumerate(runs):
+                ra[k] = Run(*r)
+            keep.append(ra)
+            arr[j] = Job(ra, len(runs), int(keep_t), seeds[j] if seeds is not None else None)
+        return arr, keep
+
+    def compact_many(self, jobs: Sequence[Tuple[Sequence[Tuple[object, object]], bool]],
+                     bloom_min_size: int = DEFAULT_BLOOM_MIN_SIZE, seeds: Optional[Sequence[Optional[bytes]]] = None,
+                     fp: float = DEFAULT_BLOOM_FP):
+        """dbeel_compact_many over host buffers.  jobs: (runs, keep_tombstones) per compaction.  Returns one
+        (data, index, bloom | None, items_written) per job, each what dbeel_compact would return for it."""
+        hold = [[(_u8(d), _u8(i)) for d, i in runs] for runs, _ in jobs]
+        ptrs = [([(d.ctypes.data, d.size, i.ctypes.data, i.size) for d, i in h], k) for h, (_, k) in zip(hold, jobs)]
+        arr, keep = self._jobs_array(ptrs, seeds)
+        n = len(jobs)
+        dc, ic, bc = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        rc = lib().dbeel_compact_many_bound(arr, n, bloom_min_size, fp, C.byref(dc), C.byref(ic), C.byref(bc))
+        if rc:
+            raise DbeelError(rc, "dbeel_compact_many_bound")
+        od, oi, ob = (np.empty(max(1, c.value), np.uint8) for c in (dc, ic, bc))
+        out = Out(od.ctypes.data, dc.value, 0, oi.ctypes.data, ic.value, 0, ob.ctypes.data, bc.value, 0, 0)
+        res = (JobResult * max(1, n))()
+        self._check(lib().dbeel_compact_many(self._h, arr, n, bloom_min_size, fp, C.byref(out), res), "dbeel_compact_many")
+        return [(od[r.data_off:r.data_off + r.data_len], oi[r.index_off:r.index_off + r.index_len],
+                 ob[r.bloom_off:r.bloom_off + r.bloom_len] if r.bloom_len else None, int(r.items_written)) for r in res[:n]]
+
+    def compact_many_device(self, jobs_ptrs, out_ptrs: Tuple[int, int, int, int, int, int],
+                            bloom_min_size: int = DEFAULT_BLOOM_MIN_SIZE, seeds=None, fp: float = DEFAULT_BLOOM_FP):
+        """Device pointers everywhere.  Returns the JobResult rows as dicts."""
+        arr, keep = self._jobs_array(jobs_ptrs, seeds)
+        n = len(jobs_ptrs)
+        dp, dc, ip, ic, bp, bc = out_ptrs
+        out = Out(dp, dc, 0, ip, ic, 0, bp if bc else None, bc, 0, 0)
+        res = (JobResult * max(1, n))()
+        self._check(lib().dbeel_compact_many_device(self._h, arr, n, bloom_min_size, fp, C.byref(out), res),
+                    "dbeel_compact_many_device")
+        return [{k: int(getattr(r, k)) for k, _ in JobResult._fields_} for r in res[:n]]
 
     # ---- N4: write-ahead-log replay + flush ------------------------------------------------
     def wal_flush(self, wal, capacity: int = DEFAULT_TREE_CAPACITY):

@@ -161,6 +161,12 @@ struct JobExtra {
     bool external_bloom = false;        // the filter belongs to the whole compaction: set bits only
     BloomParams bloom = {};
     dbeel_flush_table *flush_table = nullptr; // flush-many: one row per batch (host memory), filled on success
+    // compact-many: runs[] holds all jobs' runs back to back; job g = runs[job_first[g] .. job_first[g+1])
+    uint32_t n_jobs = 0;
+    const uint32_t *job_first = nullptr;     // [n_jobs + 1]
+    const int32_t *job_keep = nullptr;       // [n_jobs] keep_tombstones
+    const BloomParams *job_bloom = nullptr;  // [n_jobs] device-side filter of each job (words == null: none)
+    dbeel_job_result *job_results = nullptr; // [n_jobs] filled on success (bloom_off / bloom_len are the caller's)
     bool sparse_offsets = false;        // WAL replay: the batch's .data is the log itself, records do not abut
     uint64_t data_bytes = 0;            // with sparse_offsets: sum of the records' sizes (the output bound)
 };
@@ -170,7 +176,7 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
                    bool flush, dbeel_out *out, bool record_start, const JobExtra *extra = nullptr) {
     JobShape sh;
     shape_of(runs, n_runs, o, flush, &sh);
-    if (extra && extra->external_bloom) sh.bloom_file = 0;
+    if (extra && (extra->external_bloom || extra->n_jobs)) sh.bloom_file = 0; // compact-many: per-job filters, sized by the caller
     const uint64_t span_total = sh.data_total; // address span of the inputs (sh.data_total becomes the payload bound)
     if (extra && extra->sparse_offsets) sh.data_total = extra->data_bytes;
     (void)span_total;
@@ -209,7 +215,24 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     p.mode_flush = flush ? 1 : 0;
     uint32_t levels = 0;
     const bool many = flush && extra && extra->flush_table;
-    if (many) {
+    const bool jobs = !flush && extra && extra->n_jobs;
+    if (jobs) {
+        // every job gets the same power-of-two number of leaf slots (its runs, then empty segments): log2(slots)
+        // pairwise levels finish every job and never pair runs of two different ones
+        uint32_t max_runs = 1;
+        for (uint32_t g = 0; g < extra->n_jobs; g++) max_runs = std::max(max_runs, extra->job_first[g + 1] - extra->job_first[g]);
+        uint32_t slots = 1;
+        while (slots < max_runs) slots <<= 1;
+        if ((uint64_t)slots * extra->n_jobs > (1ull << 20)) return fail(e, DBEEL_ERR_TOO_MANY_RUNS, "compact-many: too many run slots");
+        p.group_slots = slots;
+        p.n_groups = extra->n_jobs;
+        p.nseg[0] = slots * extra->n_jobs;
+        while ((1u << levels) < slots) {
+            p.nseg[levels + 1] = p.nseg[levels] / 2;
+            levels++;
+        }
+    } else if (many) {
+        p.n_groups = n_runs;
         // every memtable gets the same power-of-two number of leaf slots (sort tiles), so log2(slots) merge levels
         // finish all memtables and never pair segments of two different ones
         uint64_t max_tiles = 1;
@@ -247,6 +270,7 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     const uint64_t o_runs = carve(sizeof(RunDesc) * n_runs);
     const uint64_t o_fbad = carve(4ull * n_runs);
     const uint64_t o_fmis = carve(4ull * n_runs);
+    const uint64_t o_groups = carve(jobs ? sizeof(GroupDesc) * (uint64_t)extra->n_jobs : 0);
     const uint64_t header_bytes = off;
     uint64_t o_seg[kMaxLevels + 1], o_tb[kMaxLevels];
     for (uint32_t l = 0; l <= levels; l++) o_seg[l] = carve(sizeof(Seg) * p.nseg[l]);
@@ -260,12 +284,13 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     const uint64_t o_cbytes = carve(res_chunks * 8), o_ccount = carve(res_chunks * 4);
     const uint64_t o_reca = carve(16ull * N), o_recb = carve(16ull * N);
     const uint64_t o_src = carve(8ull * N);
-    const uint64_t o_memtab = carve(many ? 16ull * (n_runs + 1) : 0);
+    const uint64_t n_groups = p.n_groups;
+    const uint64_t o_memtab = carve(n_groups ? 16ull * (n_groups + 1) : 0);
     const uint64_t gather_tiles = (sh.data_total + kGatherTileBytes - 1) / kGatherTileBytes;
     const uint64_t o_tfirst = carve(4ull * (gather_tiles + 2));
     int rc = ensure_device(e, &e->ws, &e->ws_cap, off);
     if (rc) return rc;
-    rc = ensure_pinned(e, header_bytes + align_up(sizeof(Ctl), 64) + 64 + (many ? 16ull * (n_runs + 1) : 0));
+    rc = ensure_pinned(e, header_bytes + align_up(sizeof(Ctl), 64) + 64 + (n_groups ? 16ull * (n_groups + 1) : 0));
     if (rc) return rc;
 
     uint8_t *ws = e->ws;
@@ -304,6 +329,18 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
         hb[r] = hr[r].n_in;
         hm[r] = 0xFFFFFFFFu;
         base += hr[r].n_in;
+    }
+    if (jobs) {
+        GroupDesc *hg = reinterpret_cast<GroupDesc *>(h + o_groups);
+        for (uint32_t g = 0; g < extra->n_jobs; g++) {
+            const uint32_t r0 = extra->job_first[g], r1 = extra->job_first[g + 1];
+            hg[g].first_run = r0;
+            hg[g].n_runs = r1 - r0;
+            hg[g].pos_end = r1 > r0 ? hr[r1 - 1].base + hr[r1 - 1].n_in : (r0 < n_runs ? hr[r0].base : base);
+            hg[g].keep_tombstones = extra->job_keep[g] ? 1 : 0;
+            hg[g].bloom = extra->job_bloom[g];
+        }
+        p.groups = reinterpret_cast<const GroupDesc *>(ws + o_groups);
     }
 
     // ---- bloom
@@ -397,6 +434,10 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
         k_bloom_frame<<<1, 1, 0, s>>>(static_cast<uint8_t *>(out->bloom), sh.bloom_words, p.bloom);
         launches++;
     }
+    if (jobs) {
+        k_bloom_frames<<<(extra->n_jobs + 127) / 128, 128, 0, s>>>(p.groups, extra->n_jobs);
+        launches++;
+    }
     uint4 *res = reinterpret_cast<uint4 *>(dst); // the ping-pong buffer that does not hold the merged order
     if (e->narrow_loads) k_resolve<true><<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, src, res);
     else k_resolve<false><<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, src, res);
@@ -404,8 +445,8 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     k_scan_chunks<<<1, 1024, 0, s>>>(p);
     k_emit<<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, res);
     launches += 4;
-    if (many) {
-        k_flush_table<<<(n_runs + 1 + 127) / 128, 128, 0, s>>>(p, res);
+    if (n_groups) {
+        k_flush_table<<<(uint32_t)((n_groups + 1 + 127) / 128), 128, 0, s>>>(p, res);
         launches++;
     }
     CU(cudaEventRecord(e->ev[EV_RESOLVE], s));
@@ -415,7 +456,11 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
         k_gather<<<(uint32_t)gather_tiles, kGatherThreads, 0, s>>>(p);
     }
     launches++;
-    if (many) { // only now may the .index offsets become file-relative: the gather kernel reads them as stream offsets
+    if (jobs) { // per-job filters: their own pass over the output entries
+        k_bloom_many<<<g256, 256, 0, s>>>(p);
+        launches++;
+    }
+    if (n_groups) { // only now may the .index offsets become file-relative: the gather kernel reads them as stream offsets
         k_rebase_index<<<g256, 256, 0, s>>>(p);
         launches++;
     }
@@ -429,7 +474,7 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     unsigned long long *hmt = reinterpret_cast<unsigned long long *>(e->pin + o_hmt);
     k_publish<<<1, 256, 0, s>>>(reinterpret_cast<uint32_t *>(e->pin_dev + header_bytes), reinterpret_cast<const uint32_t *>(p.ctl),
                                 (uint32_t)(sizeof(Ctl) / 4), reinterpret_cast<uint32_t *>(e->pin_dev + o_hmt),
-                                reinterpret_cast<const uint32_t *>(p.mem_table), many ? 4u * (n_runs + 1) : 0u);
+                                reinterpret_cast<const uint32_t *>(p.mem_table), n_groups ? (uint32_t)(4 * (n_groups + 1)) : 0u);
     launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s));
@@ -455,6 +500,16 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     st.output_bytes = out->data_len + out->index_len + out->bloom_len;
     st.gather_bytes = 2 * out->data_len + out->index_len + 8ull * hc->out_items; // read + write payload, read index + src_ptr
     st.partitions = 1;
+    if (jobs) {
+        for (uint32_t g = 0; g < extra->n_jobs; g++) {
+            dbeel_job_result &row = extra->job_results[g];
+            row.data_off = hmt[2 * g];
+            row.data_len = hmt[2 * (g + 1)] - hmt[2 * g];
+            row.items_written = hmt[2 * (g + 1) + 1] - hmt[2 * g + 1];
+            row.index_off = hmt[2 * g + 1] * 16;
+            row.index_len = row.items_written * 16;
+        }
+    }
     if (many) {
         for (uint32_t r = 0; r < n_runs; r++) {
             dbeel_flush_table &row = extra->flush_table[r];
@@ -1124,6 +1179,149 @@ int wal_flush_entry(dbeel_engine *e, const void *wal, uint64_t wal_len, uint32_t
     return DBEEL_OK;
 }
 
+
+// ------------------------------------------------------------------------------------ N1: compact-many
+
+struct JobShapes {
+    std::vector<JobShape> shape;
+    std::vector<uint64_t> bloom_off;
+    uint64_t data = 0, index = 0, bloom = 0, entries = 0, runs = 0;
+};
+
+int job_shapes(dbeel_engine *e, const dbeel_job *jobs, uint32_t n_jobs, uint64_t bloom_min_size, double fp, JobShapes *js) {
+    if (!(fp > 0.0 && fp < 1.0)) return e ? fail(e, DBEEL_ERR_INVALID_ARG, "bloom_fp must be in (0,1)") : DBEEL_ERR_INVALID_ARG;
+    dbeel_compact_opts o;
+    default_opts(&o);
+    o.bloom_min_size = bloom_min_size;
+    o.bloom_fp = fp;
+    js->shape.assign(n_jobs, JobShape{});
+    js->bloom_off.assign(n_jobs, 0);
+    for (uint32_t g = 0; g < n_jobs; g++) {
+        if (jobs[g].n_runs && !jobs[g].runs) return e ? fail(e, DBEEL_ERR_INVALID_ARG, "null run array") : DBEEL_ERR_INVALID_ARG;
+        shape_of(jobs[g].runs, jobs[g].n_runs, &o, false, &js->shape[g]);
+        js->data += js->shape[g].data_total;
+        js->index += js->shape[g].n_total * 16;
+        js->entries += js->shape[g].n_total;
+        js->runs += jobs[g].n_runs;
+        js->bloom_off[g] = js->bloom;
+        js->bloom += align_up(js->shape[g].bloom_file, 16);
+    }
+    return DBEEL_OK;
+}
+
+int compact_many_entry(dbeel_engine *e, const dbeel_job *jobs, uint32_t n_jobs, uint64_t bloom_min_size, double fp, dbeel_out *out,
+                       dbeel_job_result *results, bool device) {
+    if (!e) return DBEEL_ERR_INVALID_ARG;
+    if (!out || (n_jobs && (!jobs || !results))) return fail(e, DBEEL_ERR_INVALID_ARG, "null argument");
+    if (e->busy) return fail(e, DBEEL_ERR_BUSY, "engine busy");
+    BusyGuard g0(e);
+    e->err.clear();
+    out->data_len = out->index_len = out->bloom_len = out->items_written = 0;
+    JobShapes js;
+    int rc = job_shapes(e, jobs, n_jobs, bloom_min_size, fp, &js);
+    if (rc) return rc;
+    for (uint32_t g = 0; g < n_jobs; g++) results[g] = dbeel_job_result{0, 0, 0, 0, 0, 0, 0};
+    if (js.runs > DBEEL_MAX_RUNS) return fail(e, DBEEL_ERR_TOO_MANY_RUNS, "more than DBEEL_MAX_RUNS runs over all jobs");
+    if (js.entries >= 0xFFFFFFFEull) return fail(e, DBEEL_ERR_TOO_MANY_ENTRIES, "too many entries");
+    if (out->data_cap < js.data || out->index_cap < js.index || out->bloom_cap < js.bloom)
+        return fail(e, DBEEL_ERR_CAPACITY, "output buffer smaller than dbeel_compact_many_bound");
+    if (n_jobs == 0 || js.entries == 0) { e->stats = dbeel_stats{}; return DBEEL_OK; }
+    cudaError_t ce = cudaSetDevice(e->device);
+    if (ce != cudaSuccess) return fail(e, DBEEL_ERR_CUDA, "cudaSetDevice", ce);
+    cudaStream_t s = e->stream;
+
+    // all runs back to back; host buffers are staged down first
+    std::vector<dbeel_run> flat;
+    std::vector<uint32_t> first(n_jobs + 1, 0);
+    std::vector<int32_t> keep(n_jobs);
+    for (uint32_t g = 0; g < n_jobs; g++) {
+        first[g] = (uint32_t)flat.size();
+        keep[g] = jobs[g].keep_tombstones;
+        for (uint32_t r = 0; r < jobs[g].n_runs; r++) flat.push_back(jobs[g].runs[r]);
+    }
+    first[n_jobs] = (uint32_t)flat.size();
+    dbeel_out dout = *out;
+    if (!device) {
+        uint64_t in_need = 0;
+        for (auto &r : flat) {
+            if ((r.data_len && !r.data) || (r.index_len && !r.index)) return fail(e, DBEEL_ERR_INVALID_ARG, "null run buffer");
+            in_need += align_up(r.data_len + 32, kAlign) + align_up(r.index_len + 16, kAlign);
+        }
+        rc = ensure_device(e, &e->stage_in, &e->stage_in_cap, in_need);
+        if (!rc) rc = ensure_device(e, &e->stage_out, &e->stage_out_cap,
+                                    align_up(js.data + 16, kAlign) + align_up(js.index + 16, kAlign) + align_up(js.bloom + 16, kAlign));
+        if (rc) return rc;
+        uint64_t pos = 0;
+        for (auto &r : flat) {
+            const void *hd = r.data, *hi = r.index;
+            r.data = e->stage_in + pos;
+            if (r.data_len) CU(cudaMemcpyAsync(e->stage_in + pos, hd, r.data_len, cudaMemcpyHostToDevice, s));
+            pos += align_up(r.data_len + 32, kAlign);
+            r.index = e->stage_in + pos;
+            if (r.index_len) CU(cudaMemcpyAsync(e->stage_in + pos, hi, r.index_len, cudaMemcpyHostToDevice, s));
+            pos += align_up(r.index_len + 16, kAlign);
+        }
+        dout.data = e->stage_out;
+        dout.index = e->stage_out + align_up(js.data + 16, kAlign);
+        dout.bloom = e->stage_out + align_up(js.data + 16, kAlign) + align_up(js.index + 16, kAlign);
+    } else if ((uintptr_t)out->bloom & 15) {
+        return fail(e, DBEEL_ERR_INVALID_ARG, "device output buffers must be 16-byte aligned");
+    }
+    // per-job filters
+    std::vector<BloomParams> bloom(n_jobs);
+    for (uint32_t g = 0; g < n_jobs; g++) {
+        bloom[g] = BloomParams{};
+        const JobShape &sh = js.shape[g];
+        if (!sh.bloom_file) continue;
+        uint8_t seed[32];
+        if (jobs[g].bloom_seed) {
+            memcpy(seed, jobs[g].bloom_seed, 32);
+        } else {
+            FILE *f = fopen("/dev/urandom", "rb");
+            if (!f || fread(seed, 1, 32, f) != 32) {
+                if (f) fclose(f);
+                return fail(e, DBEEL_ERR_INVALID_ARG, "no entropy source for the bloom seed");
+            }
+            fclose(f);
+        }
+        bloom[g].words = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(dout.bloom) + js.bloom_off[g] + 8);
+        bloom[g].bits = sh.bloom_bits;
+        bloom[g].bits_magic = (uint64_t)((((unsigned __int128)1) << 64) / sh.bloom_bits);
+        bloom[g].k_num = sh.bloom_k;
+        for (int i = 0; i < 4; i++) memcpy(&bloom[g].sip[i], seed + 8 * i, 8);
+    }
+    if (js.bloom) CU(cudaMemsetAsync(dout.bloom, 0, js.bloom, s));
+    dbeel_compact_opts o;
+    default_opts(&o);
+    o.bloom_min_size = bloom_min_size;
+    o.bloom_fp = fp;
+    JobExtra ex;
+    ex.n_jobs = n_jobs;
+    ex.job_first = first.data();
+    ex.job_keep = keep.data();
+    ex.job_bloom = bloom.data();
+    ex.job_results = results;
+    e->stats.ms_h2d = 0;
+    rc = run_job_device(e, flat.data(), (uint32_t)flat.size(), &o, false, &dout, true, &ex);
+    if (rc) return rc;
+    for (uint32_t g = 0; g < n_jobs; g++) {
+        results[g].bloom_off = js.bloom_off[g];
+        results[g].bloom_len = js.shape[g].bloom_file;
+    }
+    if (!device) {
+        if (dout.data_len) CU(cudaMemcpyAsync(out->data, dout.data, dout.data_len, cudaMemcpyDeviceToHost, s));
+        if (dout.index_len) CU(cudaMemcpyAsync(out->index, dout.index, dout.index_len, cudaMemcpyDeviceToHost, s));
+        if (js.bloom) CU(cudaMemcpyAsync(out->bloom, dout.bloom, js.bloom, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    out->data_len = dout.data_len;
+    out->index_len = dout.index_len;
+    out->bloom_len = js.bloom;
+    out->items_written = dout.items_written;
+    e->stats.output_bytes += js.bloom;
+    return DBEEL_OK;
+}
+
 } // namespace
 
 // ------------------------------------------------------------------------------------ C ABI
@@ -1363,6 +1561,30 @@ int dbeel_get_many_device(dbeel_engine *e, const dbeel_table *tables, uint32_t n
                           const uint64_t *key_offsets, uint64_t n_keys, uint32_t mode, dbeel_lookup_result *results) {
     REFUSE_WHILE_ASYNC(e);
     return lookup_entry(e, tables, n_tables, keys, key_offsets, n_keys, mode, results, true);
+}
+
+int dbeel_compact_many_bound(const dbeel_job *jobs, uint32_t n_jobs, uint64_t bloom_min_size, double bloom_fp, uint64_t *data_cap,
+                             uint64_t *index_cap, uint64_t *bloom_cap) {
+    if (n_jobs && !jobs) return DBEEL_ERR_INVALID_ARG;
+    JobShapes js;
+    int rc = job_shapes(nullptr, jobs, n_jobs, bloom_min_size, bloom_fp, &js);
+    if (rc) return rc;
+    if (data_cap) *data_cap = js.data;
+    if (index_cap) *index_cap = js.index;
+    if (bloom_cap) *bloom_cap = js.bloom;
+    return DBEEL_OK;
+}
+
+int dbeel_compact_many(dbeel_engine *e, const dbeel_job *jobs, uint32_t n_jobs, uint64_t bloom_min_size, double bloom_fp,
+                       dbeel_out *out, dbeel_job_result *results) {
+    REFUSE_WHILE_ASYNC(e);
+    return compact_many_entry(e, jobs, n_jobs, bloom_min_size, bloom_fp, out, results, false);
+}
+
+int dbeel_compact_many_device(dbeel_engine *e, const dbeel_job *jobs, uint32_t n_jobs, uint64_t bloom_min_size, double bloom_fp,
+                              dbeel_out *out, dbeel_job_result *results) {
+    REFUSE_WHILE_ASYNC(e);
+    return compact_many_entry(e, jobs, n_jobs, bloom_min_size, bloom_fp, out, results, true);
 }
 
 int dbeel_wal_flush(dbeel_engine *e, const void *wal, uint64_t wal_len, uint32_t capacity, dbeel_out *out) {

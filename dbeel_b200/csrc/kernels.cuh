@@ -70,6 +70,17 @@ struct BloomParams {
     uint64_t sip[4]; // k0,k1 of hasher 0 ; k0,k1 of hasher 1
 };
 
+// Several independent jobs in one launch sequence.  A *group* is one of them: a memtable of dbeel_flush_many (one run) or
+// a compaction of dbeel_compact_many (a block of consecutive runs).  Every group owns an aligned block of leaf
+// segments, so merges never pair segments of two groups, and after the last level seg[n_levels][g] IS group g's
+// merged slice.
+struct GroupDesc {
+    uint32_t first_run, n_runs; // compact-many: the job's runs
+    uint32_t pos_end;           // compact-many: one past the job's last record position (start of its padding segments)
+    int keep_tombstones;
+    BloomParams bloom;          // compact-many: the job's own filter (words == null: none)
+};
+
 struct Params {
     const RunDesc *runs;
     uint32_t n_runs;
@@ -93,7 +104,10 @@ struct Params {
     uint32_t flush_slots;   // flush-many: leaf segments (sort tiles) reserved per memtable, a power of two; 0 otherwise
     uint32_t flush_ref_run; // flush: the batch whose first arrival seeds the common-prefix reduction
     uint32_t sparse_offsets; // WAL replay: index offsets point into the log, records do not abut (no running-offset check)
-    unsigned long long *mem_table; // flush-many: [n_runs + 1][2] = {.data bytes, entries} emitted before each memtable
+    uint32_t n_groups;         // flush-many: memtables, compact-many: jobs, 0 for a single job
+    uint32_t group_slots;      // compact-many: leaf segments reserved per job (runs padded to a power of two), else 0
+    const GroupDesc *groups;   // compact-many only
+    unsigned long long *mem_table; // [n_groups + 1][2] = {.data bytes, entries} emitted before each group
     // outputs
     uint8_t *out_data;
     uint4 *out_index;
@@ -157,6 +171,17 @@ __device__ __forceinline__ uint32_t find_run(const Params &p, uint32_t gid) {
     while (hi - lo > 1) {
         uint32_t mid = (lo + hi) >> 1;
         if (p.runs[mid].base <= gid) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// the group whose merged slice holds position i: last g with seg[n_levels][g].start <= i (empty groups share a start)
+__device__ __forceinline__ uint32_t find_group(const Params &p, uint32_t i) {
+    const Seg *fin = p.seg[p.n_levels];
+    uint32_t lo = 0, hi = p.n_groups;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (fin[mid].start <= i) lo = mid; else hi = mid;
     }
     return lo;
 }
@@ -414,6 +439,26 @@ __global__ void k_plan(Params p) {
             }
             total += cnt;
         }
+    } else if (p.group_slots) {
+        // compact-many: job g's runs fill the first slots of its block, the rest are empty segments parked at its end
+        for (uint32_t g = 0; g < p.n_groups; g++) {
+            const GroupDesc gd = p.groups[g];
+            for (uint32_t sl = 0; sl < p.group_slots; sl++) {
+                Seg sg;
+                sg.start = gd.pos_end;
+                sg.len = 0;
+                if (sl < gd.n_runs) {
+                    const uint32_t r = gd.first_run + sl;
+                    const uint32_t cnt = p.first_bad[r];
+                    if (cnt < p.runs[r].n_in) trunc++;
+                    if (p.first_mismatch[r] < cnt) flags |= kFlagUnsorted;
+                    sg.start = p.runs[r].base;
+                    sg.len = cnt;
+                    total += cnt;
+                }
+                p.seg[0][g * p.group_slots + sl] = sg;
+            }
+        }
     } else {
         for (uint32_t r = 0; r < p.n_runs; r++) {
             uint32_t cnt = p.first_bad[r];
@@ -437,7 +482,7 @@ __global__ void k_plan(Params p) {
         p.tile_base[l][pairs] = acc;
     }
     c->total = total;
-    c->span = p.flush_slots ? p.n_total : total;
+    c->span = p.n_groups ? p.n_total : total; // groups keep their slices at their input positions: gaps stay
     c->runs_truncated = trunc;
     c->flags = flags;
 }
@@ -830,10 +875,13 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec
     const uint32_t i = i0 + tid;
     // the sorted segment position i belongs to: the whole merged array, or -- flush-many -- one memtable's slice
     uint32_t lim_lo = 0, lim_hi = c->total;
-    if (p.flush_slots && i < span) {
-        const uint32_t mt = find_run(p, i);
-        lim_lo = p.runs[mt].base;
-        lim_hi = lim_lo + p.first_bad[mt];
+    int keep_tombstones = p.keep_tombstones;
+    if (p.n_groups && i < span) {
+        const uint32_t g = find_group(p, i);
+        const Seg sl = p.seg[p.n_levels][g];
+        lim_lo = sl.start;
+        lim_hi = sl.start + sl.len;
+        if (p.groups) keep_tombstones = p.groups[g].keep_tombstones;
     }
 
     // records i0-1 .. i0+NT (coalesced), so neighbours come from shared memory
@@ -921,7 +969,7 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec
             }
         }
         bool tomb = fs == ks + 24;
-        keep = (p.keep_tombstones || p.mode_flush || !tomb) ? 1u : 0u;
+        keep = (keep_tombstones || p.mode_flush || !tomb) ? 1u : 0u;
     }
     if (i < span) res[i] = make_uint4((uint32_t)src, (uint32_t)(src >> 32), ks, keep ? fs : 0u); // holes: nothing emitted
 
@@ -1072,15 +1120,15 @@ __global__ void __launch_bounds__(kResolveThreads) k_emit(Params p, const uint4 
 
 __global__ void k_flush_table(Params p, const uint4 *res) {
     const uint32_t mt = blockIdx.x * blockDim.x + threadIdx.x;
-    if (mt > p.n_runs) return;
+    if (mt > p.n_groups) return;
     const Ctl *c = p.ctl;
     unsigned long long bytes;
     unsigned long long items;
-    if (mt == p.n_runs) {
+    if (mt == p.n_groups) {
         bytes = c->out_data_len;
         items = c->out_items;
     } else {
-        const uint32_t pos = p.runs[mt].base; // first merged position of the memtable
+        const uint32_t pos = p.seg[p.n_levels][mt].start; // first merged position of the group
         if (pos >= c->span) {
             bytes = c->out_data_len;
             items = c->out_items;
@@ -1102,7 +1150,7 @@ __global__ void k_flush_table(Params p, const uint4 *res) {
 __global__ void __launch_bounds__(256) k_rebase_index(Params p) {
     const uint32_t e = blockIdx.x * 256u + threadIdx.x;
     if (e >= p.ctl->out_items) return;
-    uint32_t lo = 0, hi = p.n_runs; // last memtable whose first entry is <= e (empty memtables share a boundary)
+    uint32_t lo = 0, hi = p.n_groups; // last group whose first entry is <= e (empty groups share a boundary)
     while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
         if (p.mem_table[2 * mid + 1] <= e) lo = mid; else hi = mid;
@@ -1315,6 +1363,61 @@ __global__ void k_bloom_frame(uint8_t *file, uint64_t n_words, BloomParams b) {
         put64(t + 12, k1 ^ 0x7465646279746573ULL); // v3
         put64(t + 14, 0);                         // tail
         put64(t + 16, 0);                         // ntail
+        t += 18;
+    }
+}
+
+// compact-many: the filters are per job (own size, own seed), so they are filled by a pass of their own over the output
+// entries instead of the gather's fused epilogue (which stays untouched for the single-job path): one thread per entry,
+// job = last one whose first output entry is <= e (k_flush_table's rows), key bytes from the entry's source.
+__global__ void __launch_bounds__(256) k_bloom_many(Params p) {
+    const uint32_t e = blockIdx.x * 256u + threadIdx.x;
+    if (e >= p.ctl->out_items) return;
+    uint32_t lo = 0, hi = p.n_groups;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (p.mem_table[2 * mid + 1] <= e) lo = mid; else hi = mid;
+    }
+    const BloomParams bp = p.groups[lo].bloom;
+    uint32_t *words = bp.words;
+    if (words == nullptr) return;
+    const uint8_t *key = reinterpret_cast<const uint8_t *>((uintptr_t)p.src_ptr[e]) + 8;
+    const uint64_t klen = p.out_index[e].z - 8;
+    uint64_t h0, h1;
+    sip13_pair_vec_u8(bp.sip, klen, [key](uint64_t q) { return ld_u64_unaligned(key + 8 * q); }, &h0, &h1);
+    bloom_probe_all(h0, h1, bp.k_num, bp.bits, bp.bits_magic,
+                    [words](uint64_t bit) { atomicOr(&words[bit >> 5], 1u << (bit & 31)); });
+}
+
+// compact-many: one frame per job that has a filter
+__global__ void __launch_bounds__(128) k_bloom_frames(const GroupDesc *groups, uint32_t n_groups) {
+    const uint32_t g = blockIdx.x * 128u + threadIdx.x;
+    if (g >= n_groups) return;
+    const BloomParams b = groups[g].bloom;
+    if (b.words == nullptr) return;
+    uint32_t *w = b.words - 2; // the file starts 8 bytes before the bit vector
+    const uint64_t n_words = (b.bits + 31) / 32;
+    auto put64 = [&](uint64_t word_idx, uint64_t v) {
+        w[word_idx] = (uint32_t)v;
+        w[word_idx + 1] = (uint32_t)(v >> 32);
+    };
+    put64(0, n_words);
+    uint64_t t = 2 + n_words;
+    put64(t, b.bits);
+    put64(t + 2, b.bits);
+    w[t + 4] = b.k_num;
+    t += 5;
+    for (int h = 0; h < 2; h++) {
+        const uint64_t k0 = b.sip[2 * h], k1 = b.sip[2 * h + 1];
+        put64(t, k0);
+        put64(t + 2, k1);
+        put64(t + 4, 0);
+        put64(t + 6, k0 ^ 0x736f6d6570736575ULL);
+        put64(t + 8, k0 ^ 0x6c7967656e657261ULL);
+        put64(t + 10, k1 ^ 0x646f72616e646f6dULL);
+        put64(t + 12, k1 ^ 0x7465646279746573ULL);
+        put64(t + 14, 0);
+        put64(t + 16, 0);
         t += 18;
     }
 }

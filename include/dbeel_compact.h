@@ -157,6 +157,32 @@ int dbeel_flush_many(dbeel_engine *e, const dbeel_run *batches, uint32_t n_batch
 int dbeel_flush_many_device(dbeel_engine *e, const dbeel_run *batches, uint32_t n_batches, dbeel_out *out,
                             dbeel_flush_table *table);
 
+/* ---- N1: many independent compactions in one launch sequence ---------------------------------------------------
+ * compact_tree (src/tasks/compaction.rs:82-101) issues one LSMTree::compact per group of SSTables it picked, and a node
+ * runs one such loop per collection and shard; small level-0 merges are launch-bound one at a time.  Every job here is
+ * exactly one dbeel_compact: its own runs (tie-break = position inside the job), its own keep_tombstones, its own bloom
+ * filter (enabled and sized from ITS inputs, its own 32-byte seed).  Outputs land back to back in out->data /
+ * out->index (file-relative .index offsets per job) and in out->bloom at 16-byte aligned offsets; results[j] says where.
+ * Each job's three files are byte-identical to a separate dbeel_compact with the same arguments. */
+typedef struct dbeel_job {
+    const dbeel_run *runs;     /* in the order of indices_to_compact */
+    uint32_t n_runs;
+    int32_t keep_tombstones;
+    const uint8_t *bloom_seed; /* 32 bytes, or NULL = fresh random seed */
+} dbeel_job;
+typedef struct dbeel_job_result {
+    uint64_t data_off, data_len;
+    uint64_t index_off, index_len;
+    uint64_t bloom_off, bloom_len; /* bloom_len == 0: no filter for this job (lsm_tree.rs:1026-1034) */
+    uint64_t items_written;
+} dbeel_job_result;
+int dbeel_compact_many_bound(const dbeel_job *jobs, uint32_t n_jobs, uint64_t bloom_min_size, double bloom_fp,
+                             uint64_t *data_cap, uint64_t *index_cap, uint64_t *bloom_cap);
+int dbeel_compact_many(dbeel_engine *e, const dbeel_job *jobs, uint32_t n_jobs, uint64_t bloom_min_size, double bloom_fp,
+                       dbeel_out *out, dbeel_job_result *results);
+int dbeel_compact_many_device(dbeel_engine *e, const dbeel_job *jobs, uint32_t n_jobs, uint64_t bloom_min_size,
+                              double bloom_fp, dbeel_out *out, dbeel_job_result *results);
+
 /* Asynchronous form of dbeel_compact for callers that must not block their reactor (dbeel's
  * compaction task runs on a glommio executor, src/tasks/compaction.rs:139-153): submit returns at
  * once, the job runs on an engine-owned worker thread, poll / wait report its status.  All

@@ -442,3 +442,50 @@ def test_flush_many_equals_separate_flushes(engine):
         sd, si, sn = engine.flush(b)
         assert sn == gn
         assert_run_equal((sd, si), (gd, gi), "flush vs flush_many")
+
+
+def _compact_many_check(engine, jobs, bloom_min_size, what):
+    seeds = [bytes([(7 * j + k) % 256 for k in range(32)]) for j in range(len(jobs))]
+    got = engine.compact_many(jobs, bloom_min_size=bloom_min_size, seeds=seeds)
+    assert len(got) == len(jobs)
+    for j, ((runs, keep), (gd, gi, gb, gn)) in enumerate(zip(jobs, got)):
+        od, oi, ob, on = oracle.compact(runs, keep_tombstones=keep, bloom_min_size=bloom_min_size, seed=seeds[j])
+        assert gn == on, f"{what} job {j}: items {gn} != {on}"
+        assert_run_equal((gd, gi), (od, oi), f"{what} job {j}")
+        assert (gb is None) == (ob is None), f"{what} job {j}: bloom presence"
+        if ob is not None:
+            assert np.array_equal(gb, ob), f"{what} job {j}: .bloom differs"
+    return got
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_compact_many_equals_separate_compactions(engine, seed):
+    """N1: many compactions in one launch sequence -- every job's three files equal a separate dbeel_compact
+    (own run count, own keep_tombstones, own filter with its own seed, enabled from its own input size)."""
+    rng = np.random.default_rng(500 + seed)
+    jobs = []
+    for j in range(int(rng.integers(2, 12))):
+        pool = nasty_keys(rng, int(rng.integers(20, 900)), max_len=50)
+        n_runs = int(rng.integers(1, 10))
+        sizes = [int(rng.integers(0, len(pool) + 1)) for _ in range(n_runs)]
+        runs = random_runs(rng, n_runs, sizes, pool, max_doc=int(rng.choice([20, 200, 1500])))
+        jobs.append((runs, bool(rng.integers(2))))
+    _compact_many_check(engine, jobs, bloom_min_size=int(rng.choice([1000, 30_000, 1 << 20])), what=f"many {seed}")
+
+
+def test_compact_many_edge_shapes(engine):
+    rng = np.random.default_rng(77)
+    pool = nasty_keys(rng, 300, max_len=30)
+    empty = sstable.build_run([])
+    one = random_runs(rng, 1, 200, pool)
+    jobs = [([], False), ([empty, empty], True), (one, False), (random_runs(rng, 7, 250, pool), False), ([empty] + one, True),
+            (random_runs(rng, 16, 100, pool, tombstone_frac=0.9), False)]
+    got = _compact_many_check(engine, jobs, bloom_min_size=2000, what="edges")
+    assert got[0][3] == 0 and got[1][3] == 0 and got[0][0].size == 0
+    # a single job through the batch entry point is the ordinary compaction
+    _compact_many_check(engine, [jobs[3]], bloom_min_size=2000, what="single")
+    assert engine.compact_many([]) == []
+    # a corrupt run ends early inside its own job only (lsm_tree.rs:1014,1063)
+    bad_d, bad_i = one[0][0].copy(), one[0][1].copy()
+    bad_i[16 * 50 + 12:16 * 50 + 16] = np.frombuffer((7).to_bytes(4, "little"), np.uint8)
+    _compact_many_check(engine, [(random_runs(rng, 3, 100, pool), False), ([(bad_d, bad_i)] + one, True)], 1 << 20, "truncated job")
