@@ -260,8 +260,9 @@ def test_unflushed_log_is_replayed_and_flushed_on_open(engine, tmp_path):
     tree = se.LSMTree.open_or_create(d, engine)
     assert tree.sstable_indices_and_sizes() == [(6, on)] and tree.recover_wal() == (6, 0)
     # a log with more distinct keys than the memtable holds cannot be replayed (memtable.set(..)? -> ReachedCapacity)
-    with open(os.path.join(d, sstable.file_name(8, "memtable")), "wb") as f:
+    with open(os.path.join(d, sstable.file_name(2, "memtable")), "wb") as f:  # older than the active log 6
         f.write(wal.tobytes())
     with pytest.raises(capi.DbeelError) as ei:
         tree.recover_wal(tree_capacity=100)
     assert ei.value.code == capi.ERR_TREE_FULL
+    assert os.path.exists(os.path.join(d, sstable.file_name(2, "memtable")))  # nothing was removed
