@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Randomised byte-parity sweep against the oracle, through the C ABI, on one GPU: many small jobs of random shape
 (run counts, sizes, key pools with shared prefixes / empty keys / 0x00 / 0xFF, tombstones, colliding timestamps) over
-every entry point: compact (single shot and pipelined in tiny key-range partitions), flush, flush_many, wal_flush,
-get_many.  A mismatch prints the seed and exits 1.  Usage: tools/parity_sweep.py [iterations (default 300)] [first seed]"""
+every entry point: compact (single shot and pipelined in tiny key-range partitions), compact_many, flush, flush_many,
+wal_flush, get_many.  A mismatch prints the seed and exits 1.  Usage: tools/parity_sweep.py [iterations (default 300)] [first seed]"""
 import os
 import sys
 import time
@@ -47,7 +47,7 @@ def main():
     for it in range(iters):
         seed = seed0 + it
         rng = np.random.default_rng(seed)
-        kind = ["compact", "pipelined", "flush", "flush_many", "wal", "get"][it % 6]
+        kind = ["compact", "pipelined", "flush", "flush_many", "wal", "get", "compact_many"][it % 7]
         pool = nasty_keys(rng, int(rng.integers(5, 1500)), max_len=int(rng.integers(4, 90)))
         what = f"seed {seed} ({kind})"
         try:
@@ -64,6 +64,21 @@ def main():
                 ok = gn == on and same(gd, od) and same(gi, oi) and (gb is None) == (ob is None) and (gb is None or same(gb, ob))
                 if kind == "pipelined":
                     counts["partitions>1"] = counts.get("partitions>1", 0) + (e.stats()["partitions"] > 1)
+            elif kind == "compact_many":
+                jobs, seeds = [], []
+                for j in range(int(rng.integers(1, 9))):
+                    n_runs = int(rng.integers(0, 10))
+                    sizes = [int(rng.integers(0, min(len(pool), 1200) + 1)) for _ in range(n_runs)]
+                    jobs.append((random_runs(rng, n_runs, sizes, pool, max_doc=int(rng.choice([8, 60, 600])),
+                                             tombstone_frac=float(rng.choice([0.0, 0.15, 0.6])),
+                                             equal_ts_frac=float(rng.choice([0.0, 0.3, 1.0]))) if n_runs else [], bool(rng.integers(2))))
+                    seeds.append(bytes(rng.integers(0, 256, 32, dtype=np.uint8)))
+                bms = int(rng.choice([1, 5000, 1 << 20]))
+                got = eng.compact_many(jobs, bloom_min_size=bms, seeds=seeds)
+                ok = len(got) == len(jobs)
+                for (runs, keep), sd, (gd, gi, gb, gn) in zip(jobs, seeds, got):
+                    od, oi, ob, on = oracle.compact(runs, keep_tombstones=keep, bloom_min_size=bms, seed=sd)
+                    ok = ok and gn == on and same(gd, od) and same(gi, oi) and (gb is None) == (ob is None) and (gb is None or same(gb, ob))
             elif kind == "flush":
                 ents = arrivals(rng, pool, int(rng.integers(1, 6000)), int(rng.choice([4, 80, 700])))
                 gd, gi, gn = eng.flush(sstable.build_run(ents))
