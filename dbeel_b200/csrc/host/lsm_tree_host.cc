@@ -248,6 +248,49 @@ uint64_t dbeel_tree_write_sstable_index(const dbeel_tree *t) { return t ? t->wri
 
 const char *dbeel_tree_last_error(const dbeel_tree *t) { return t ? t->err.c_str() : "null tree"; }
 
+// Everything LSMTree::compact does after the merge core (lsm_tree.rs:995-1000,1068-1155) for one finished job: the
+// compact_* files, the CompactionAction journal, the renames, the sstable-list swap, the deletes.
+static int commit_compaction(dbeel_tree *t, const uint64_t *indices_to_compact, uint32_t n, uint64_t output_index, const void *data,
+                             uint64_t data_len, const void *index, uint64_t index_len, const void *bloom, uint64_t bloom_len,
+                             uint64_t items_written) {
+    int rc;
+    // lsm_tree.rs:995-1000,1068-1076: the compact_* files
+    const std::string cdata = file_path(t->dir, output_index, kCompactData), cindex = file_path(t->dir, output_index, kCompactIndex),
+                      cbloom = file_path(t->dir, output_index, kCompactBloom);
+    rc = write_file(t, cdata, data, data_len);
+    if (!rc) rc = write_file(t, cindex, index, index_len);
+    if (!rc && bloom_len) rc = write_file(t, cbloom, bloom, bloom_len);
+    if (rc) return rc;
+
+    // lsm_tree.rs:1078-1105: journal
+    CompactionAction action;
+    action.renames = {{cdata, file_path(t->dir, output_index, kData)},
+                      {cindex, file_path(t->dir, output_index, kIndex)},
+                      {cbloom, file_path(t->dir, output_index, kBloom)}};
+    for (uint32_t i = 0; i < n; i++)
+        for (const char *ext : {kData, kIndex, kBloom}) action.deletes.push_back(file_path(t->dir, indices_to_compact[i], ext));
+    const std::string journal = file_path(t->dir, output_index, kCompactAction);
+    const std::string enc = encode_action(action);
+    rc = write_file(t, journal, enc.data(), enc.size());
+    if (rc) return rc;
+    // lsm_tree.rs:1107-1111: renames whose source exists (no bloom -> that rename is skipped)
+    for (auto &r : action.renames)
+        if (exists(r.first) && rename(r.first.c_str(), r.second.c_str()) != 0) return io_fail(t, "rename " + r.first);
+    // lsm_tree.rs:1113-1139: swap the sstable list
+    std::vector<SSTable> next;
+    for (auto &s : t->sstables)
+        if (std::find(indices_to_compact, indices_to_compact + n, s.index) == indices_to_compact + n) next.push_back(s);
+    next.push_back({output_index, items_written});
+    std::sort(next.begin(), next.end(), [](const SSTable &a, const SSTable &b) { return a.index < b.index; });
+    t->sstables.swap(next);
+    // lsm_tree.rs:1147-1153: delete the inputs, then the journal
+    for (auto &d : action.deletes)
+        if (exists(d)) unlink(d.c_str());
+    unlink(journal.c_str());
+    return DBEEL_OK;
+}
+
+
 int dbeel_tree_compact(dbeel_tree *t, const uint64_t *indices_to_compact, uint32_t n, uint64_t output_index,
                        int keep_tombstones, const uint8_t *bloom_seed) {
     if (!t || (n && !indices_to_compact)) return DBEEL_ERR_INVALID_ARG;
@@ -279,39 +322,44 @@ int dbeel_tree_compact(dbeel_tree *t, const uint64_t *indices_to_compact, uint32
     rc = dbeel_compact(t->engine, runs.data(), n, &opts, &out);
     if (rc) { t->err = dbeel_last_error(t->engine); return rc; }
 
-    // lsm_tree.rs:995-1000,1068-1076: the compact_* files
-    const std::string cdata = file_path(t->dir, output_index, kCompactData), cindex = file_path(t->dir, output_index, kCompactIndex),
-                      cbloom = file_path(t->dir, output_index, kCompactBloom);
-    rc = write_file(t, cdata, od.p, out.data_len);
-    if (!rc) rc = write_file(t, cindex, oi.p, out.index_len);
-    if (!rc && out.bloom_len) rc = write_file(t, cbloom, ob.p, out.bloom_len);
-    if (rc) return rc;
+    return commit_compaction(t, indices_to_compact, n, output_index, od.p, out.data_len, oi.p, out.index_len, ob.p, out.bloom_len,
+                             out.items_written);
+}
 
-    // lsm_tree.rs:1078-1105: journal
-    CompactionAction action;
-    action.renames = {{cdata, file_path(t->dir, output_index, kData)},
-                      {cindex, file_path(t->dir, output_index, kIndex)},
-                      {cbloom, file_path(t->dir, output_index, kBloom)}};
-    for (uint32_t i = 0; i < n; i++)
-        for (const char *ext : {kData, kIndex, kBloom}) action.deletes.push_back(file_path(t->dir, indices_to_compact[i], ext));
-    const std::string journal = file_path(t->dir, output_index, kCompactAction);
-    const std::string enc = encode_action(action);
-    rc = write_file(t, journal, enc.data(), enc.size());
+int dbeel_tree_compact_many(dbeel_tree *t, const uint64_t *members, const uint32_t *group_start, uint32_t n_groups,
+                            const uint64_t *output_index, const int32_t *keep_tombstones, const uint8_t *bloom_seeds) {
+    if (!t || (n_groups && (!members || !group_start || !output_index || !keep_tombstones))) return DBEEL_ERR_INVALID_ARG;
+    t->err.clear();
+    const uint32_t total = n_groups ? group_start[n_groups] : 0;
+    std::vector<PinnedBuf> data(total), index(total);
+    std::vector<dbeel_run> runs(total);
+    for (uint32_t i = 0; i < total; i++) { // lsm_tree.rs:956-993 for every group
+        std::string dp = file_path(t->dir, members[i], kData), ip = file_path(t->dir, members[i], kIndex);
+        if (!exists(dp) || !exists(ip)) { t->err = "no such sstable: " + dp; return DBEEL_ERR_NO_SSTABLE; }
+        int rc = read_file(t, dp, &data[i]);
+        if (!rc) rc = read_file(t, ip, &index[i]);
+        if (rc) return rc;
+        runs[i] = dbeel_run{data[i].p, data[i].len, index[i].p, index[i].len};
+    }
+    std::vector<dbeel_job> jobs(n_groups);
+    for (uint32_t g = 0; g < n_groups; g++)
+        jobs[g] = dbeel_job{runs.data() + group_start[g], group_start[g + 1] - group_start[g], keep_tombstones[g],
+                            bloom_seeds ? bloom_seeds + 32 * g : nullptr};
+    uint64_t dc, ic, bc;
+    int rc = dbeel_compact_many_bound(jobs.data(), n_groups, t->bloom_min_size, DBEEL_DEFAULT_BLOOM_FP, &dc, &ic, &bc);
     if (rc) return rc;
-    // lsm_tree.rs:1107-1111: renames whose source exists (no bloom -> that rename is skipped)
-    for (auto &r : action.renames)
-        if (exists(r.first) && rename(r.first.c_str(), r.second.c_str()) != 0) return io_fail(t, "rename " + r.first);
-    // lsm_tree.rs:1113-1139: swap the sstable list
-    std::vector<SSTable> next;
-    for (auto &s : t->sstables)
-        if (std::find(indices_to_compact, indices_to_compact + n, s.index) == indices_to_compact + n) next.push_back(s);
-    next.push_back({output_index, out.items_written});
-    std::sort(next.begin(), next.end(), [](const SSTable &a, const SSTable &b) { return a.index < b.index; });
-    t->sstables.swap(next);
-    // lsm_tree.rs:1147-1153: delete the inputs, then the journal
-    for (auto &d : action.deletes)
-        if (exists(d)) unlink(d.c_str());
-    unlink(journal.c_str());
+    PinnedBuf od(dc), oi(ic), ob(bc);
+    if (!od.p || !oi.p || !ob.p) { t->err = "dbeel_host_alloc failed"; return DBEEL_ERR_NOMEM; }
+    dbeel_out out{od.p, dc, 0, oi.p, ic, 0, bc ? ob.p : nullptr, bc, 0, 0};
+    std::vector<dbeel_job_result> res(n_groups);
+    rc = dbeel_compact_many(t->engine, jobs.data(), n_groups, t->bloom_min_size, DBEEL_DEFAULT_BLOOM_FP, &out, res.data());
+    if (rc) { t->err = dbeel_last_error(t->engine); return rc; }
+    for (uint32_t g = 0; g < n_groups; g++) { // the commit protocol, group by group, in the picker's order
+        const dbeel_job_result &r = res[g];
+        rc = commit_compaction(t, members + group_start[g], group_start[g + 1] - group_start[g], output_index[g], od.p + r.data_off,
+                               r.data_len, oi.p + r.index_off, r.index_len, ob.p + r.bloom_off, r.bloom_len, r.items_written);
+        if (rc) return rc;
+    }
     return DBEEL_OK;
 }
 

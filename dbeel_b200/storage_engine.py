@@ -39,6 +39,9 @@ def _lib():
         L.dbeel_tree_compact.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32, C.c_uint64, C.c_int, C.c_char_p]
         L.dbeel_tree_flush.restype = C.c_int
         L.dbeel_tree_flush.argtypes = [C.c_void_p, C.POINTER(capi.Run), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.dbeel_tree_compact_many.restype = C.c_int
+        L.dbeel_tree_compact_many.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_uint32,
+                                              C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.c_char_p]
         L.dbeel_tree_get_many.restype = C.c_int
         L.dbeel_tree_get_many.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
         L.dbeel_tree_recover_wal.restype = C.c_int
@@ -56,7 +59,7 @@ def _lib():
 
 
 TREE_EXPORTS = ["dbeel_tree_open", "dbeel_tree_close", "dbeel_tree_sstables", "dbeel_tree_write_sstable_index",
-                "dbeel_tree_compact", "dbeel_tree_flush", "dbeel_tree_recover_wal", "dbeel_tree_get_many", "dbeel_tree_last_error", "dbeel_memtable_cut",
+                "dbeel_tree_compact", "dbeel_tree_compact_many", "dbeel_tree_flush", "dbeel_tree_recover_wal", "dbeel_tree_get_many", "dbeel_tree_last_error", "dbeel_memtable_cut",
                 "dbeel_plan_compactions"]
 
 
@@ -170,9 +173,26 @@ class LSMTree:
         self._check(_lib().dbeel_tree_recover_wal(self._h, tree_capacity, C.byref(wi), C.byref(n)), "LSMTree.recover_wal")
         return int(wi.value), int(n.value)
 
-    def compact_tree(self, compaction_factor: int = 2, bloom_seed: Optional[bytes] = None):
-        """tasks/compaction.rs compact_tree: plan with the picker, run every group."""
+    def compact_many(self, plan, bloom_seeds: Optional[Sequence[bytes]] = None) -> None:
+        """All groups of a plan_compactions() result through ONE dbeel_compact_many, committed group by group."""
+        members = [i for indices, _, _ in plan for i in indices]
+        starts = [0]
+        for indices, _, _ in plan:
+            starts.append(starts[-1] + len(indices))
+        n = len(plan)
+        m = (C.c_uint64 * max(1, len(members)))(*members)
+        gs = (C.c_uint32 * (n + 1))(*starts)
+        oi = (C.c_uint64 * max(1, n))(*[o for _, o, _ in plan])
+        kt = (C.c_int32 * max(1, n))(*[int(k) for _, _, k in plan])
+        seeds = b"".join(bloom_seeds) if bloom_seeds is not None else None
+        self._check(_lib().dbeel_tree_compact_many(self._h, m, gs, n, oi, kt, seeds), "LSMTree.compact_many")
+
+    def compact_tree(self, compaction_factor: int = 2, bloom_seed: Optional[bytes] = None, batched: bool = False):
+        """tasks/compaction.rs compact_tree: plan with the picker, run every group (batched: in one launch sequence)."""
         plan = plan_compactions(self.sstable_indices_and_sizes(), compaction_factor)
+        if batched and plan:
+            self.compact_many(plan, [bloom_seed] * len(plan) if bloom_seed is not None else None)
+            return plan
         for indices, out, keep in plan:
             self.compact(indices, out, keep, bloom_seed)
         return plan

@@ -48,6 +48,12 @@ uint64_t dbeel_tree_write_sstable_index(const dbeel_tree *t); /* next even index
 int dbeel_tree_compact(dbeel_tree *t, const uint64_t *indices_to_compact, uint32_t n, uint64_t output_index,
                        int keep_tombstones, const uint8_t *bloom_seed /* 32 bytes or NULL */);
 
+/* compact_tree's loop (tasks/compaction.rs:82-101) in one go: all groups of a dbeel_plan_compactions() result (same
+ * flattened layout) are merged by ONE dbeel_compact_many() call, then committed group by group exactly like
+ * dbeel_tree_compact.  bloom_seeds: 32 bytes per group back to back, or NULL. */
+int dbeel_tree_compact_many(dbeel_tree *t, const uint64_t *members, const uint32_t *group_start, uint32_t n_groups,
+                            const uint64_t *output_index, const int32_t *keep_tombstones, const uint8_t *bloom_seeds);
+
 /* Flush one memtable's arrivals (host buffers, arrival order) to the next even index. */
 int dbeel_tree_flush(dbeel_tree *t, const dbeel_run *batch, uint64_t *written_index, uint64_t *items_written);
 

@@ -266,3 +266,40 @@ def test_unflushed_log_is_replayed_and_flushed_on_open(engine, tmp_path):
         tree.recover_wal(tree_capacity=100)
     assert ei.value.code == capi.ERR_TREE_FULL
     assert os.path.exists(os.path.join(d, sstable.file_name(2, "memtable")))  # nothing was removed
+
+
+@pytest.mark.gpu
+def test_compact_tree_batched_equals_group_by_group(engine, tmp_path):
+    """compact_tree's groups (tasks/compaction.rs:82-101) through one dbeel_compact_many + per-group commit: the
+    directory ends up byte-identical to running LSMTree::compact once per group."""
+    rng = np.random.default_rng(31)
+    sizes = {0: 100, 2: 100, 4: 100, 101: 5000, 103: 5000}
+    tables = {}
+    for idx, n in sizes.items():
+        ents = [(b"\xb0k%015d" % k, b"" if rng.random() < 0.1 else bytes(rng.integers(0, 256, 150, dtype=np.uint8)), BASE_TS + idx)
+                for k in sorted(rng.choice(20_000, n, replace=False).tolist())]
+        tables[idx] = sstable.build_run(ents)
+    dirs = [str(tmp_path / "seq"), str(tmp_path / "batched")]
+    plans = []
+    for d, batched in zip(dirs, (False, True)):
+        os.makedirs(d)
+        for idx, run in tables.items():
+            sstable.write_run_files(d, idx, run)
+        tree = se.LSMTree(d, engine, sstable_bloom_min_size=100_000)
+        plans.append(tree.compact_tree(compaction_factor=2, bloom_seed=SEED, batched=batched))
+        assert tree.sstable_indices_and_sizes() == sorted(tree.sstable_indices_and_sizes())
+        tree.close()
+    assert plans[0] == plans[1] and [sorted(g[0]) for g in plans[0]] == [[101, 103], [0, 2, 4]]
+    assert [g[2] for g in plans[0]] == [False, True]
+    names = sorted(os.listdir(dirs[0]))
+    assert names == sorted(os.listdir(dirs[1])) and any(n.endswith(".bloom") for n in names)
+    for n in names:
+        a, b = (np.fromfile(os.path.join(d, n), dtype=np.uint8) for d in dirs)
+        assert np.array_equal(a, b), n
+    for indices, out, keep in plans[1]:  # and both equal the oracle's compaction of each group
+        od, oi, ob, on = oracle.compact([tables[i] for i in indices], keep, bloom_min_size=100_000, seed=SEED)
+        assert_run_equal(sstable.read_run_files(dirs[1], out), (od, oi), f"group -> {out}")
+        bp = os.path.join(dirs[1], sstable.file_name(out, "bloom"))
+        assert os.path.exists(bp) == (ob is not None)
+        if ob is not None:
+            assert np.array_equal(np.fromfile(bp, dtype=np.uint8), ob)
