@@ -307,6 +307,16 @@ def test_point_reads_of_get_after_compaction():
         assert oracle.sstable_lookup((d, i), None, u(k)) == (False, None, False)
 
 
+def test_point_reads_of_set_and_get_sstable():
+    """lsm_tree.rs:1300-1302,1311-1313: after flushing the 32 u16 keys, get([0,0]), get([1,0]) and get([10,0]) hit."""
+    u = lambda n: int(n).to_bytes(2, "little")
+    d, i, n = oracle.memtable_flushes(sstable.build_run([(u(k), u(k), 10**18 + k) for k in range(32)]), capacity=32)[0]
+    ents = sstable.parse_run(d, i)
+    for k in (0, 1, 10):
+        found, rec, _ = oracle.sstable_lookup((d, i), None, u(k))
+        assert found and ents[rec][1] == u(k)
+
+
 def test_get_many_walks_tables_newest_first():
     """get_entry (lsm_tree.rs:686-719): `sstables.iter().rev()`, a filter that says no skips the table, the first
     table whose binary_search finds the key answers.  The batch form must agree with the per-table restatement."""
@@ -349,6 +359,15 @@ def test_wal_replay_equals_the_memtable_the_writes_built():
         d, i, n, seen = oracle.wal_flush(_wal_case(ents, pad_byte=pad), capacity=8192)
         md, mi, mn = oracle.memtable_flushes(sstable.build_run(ents), capacity=8192)[0]
         assert seen == 1500 and n == mn and np.array_equal(d, md) and np.array_equal(i, mi)
+
+
+def test_wal_replay_of_set_and_get_memtable():
+    """The reference's own WAL round trip (set_and_get_memtable, lsm_tree.rs:1252-1273): set([100], [200]), reopen the
+    tree -> the entry comes back out of the log (:524) and get([100]) == [200], get([0]) == None."""
+    d, i, n, seen = oracle.wal_flush(sstable.build_wal([(bytes([100]), bytes([200]), 10**18)]), capacity=32)
+    assert (n, seen) == (1, 1) and sstable.parse_run(d, i) == [(bytes([100]), bytes([200]), 10**18)]
+    assert oracle.sstable_lookup((d, i), None, bytes([100]))[:2] == (True, 0)
+    assert oracle.sstable_lookup((d, i), None, bytes([0]))[0] is False
 
 
 def test_wal_page_arithmetic_and_large_records():
