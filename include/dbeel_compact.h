@@ -17,6 +17,13 @@
  *                          lsm_tree.rs:1026-1034,:1049-1051,:1070-1076)
  *   dbeel_flush*        <- RedBlackTree::set semantics (rbtree_arena/src/lib.rs:497-534) +
  *                          LSMTree::flush_memtable_to_disk (lsm_tree.rs:925-946)
+ *   dbeel_flush_many*   <- the same for many memtables at once (several collections / shards, or a backlog)
+ *   dbeel_compact_many* <- compact_tree's loop over the groups its picker produced: one LSMTree::compact per
+ *                          group (src/tasks/compaction.rs:82-101), all groups in one launch sequence
+ *   dbeel_get_many*     <- the SSTable loop of LSMTree::get_entry: Bloom::check + binary_search
+ *                          (lsm_tree.rs:605-670, 686-719) for a batch of keys        ["next" row N2]
+ *   dbeel_wal_flush*    <- read_memtable_from_wal_file + the recovery flush of open_or_create_ex
+ *                          (lsm_tree.rs:552-574, 478-513)                            ["next" row N4]
  *   dbeel_bloom_*       <- Bloom::new_for_fp_rate sizing (lsm_tree.rs:1028-1031)
  *   error codes         <- src/error.rs:8-74 (only the variants this path can raise)
  *
