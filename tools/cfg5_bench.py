@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """BASELINE.json configs[4] for one shard, device-resident: a Zipf(0.99) write stream (512-byte documents) is cut into
-memtables of 8192 distinct keys, ALL memtables are flushed by one dbeel_flush_many_device, then the size-tiered picker
-(compaction factor 8) is run to quiescence -- every round's groups merged by ONE dbeel_compact_many_device.  The same
+memtables of 8192 distinct keys; the memtables arrive in waves of 8, every wave is flushed by one
+dbeel_flush_many_device, and after every wave the size-tiered picker (compaction factor 8) runs to quiescence -- every
+round's groups merged by ONE dbeel_compact_many_device.  The same
 recorded plan is replayed on the CPU oracle (red-black-tree memtables, one core) and every table that is left is
 compared byte for byte.  Usage: tools/cfg5_bench.py [n_writes (default 1500000)]"""
 import os
@@ -45,46 +46,51 @@ def main():
     del d_data
     torch.cuda.synchronize()
 
-    # ---- GPU: flush everything, then compact to quiescence
+    # ---- GPU: memtables arrive in waves of FACTOR; each wave is flushed by one dbeel_flush_many_device, then the
+    # picker runs to quiescence (as compact_tree does after flush events), every round's groups in one compact_many
     t0 = time.perf_counter()
-    tot_d = sum(d.numel() for d, _ in subs)
-    tot_i = sum(i.numel() for _, i in subs)
-    fd = torch.empty(tot_d + 64, dtype=torch.uint8, device=dev)
-    fi = torch.empty(tot_i + 64, dtype=torch.uint8, device=dev)
-    _, _, _, rows = eng.flush_many_device([(d.data_ptr(), d.numel(), i.data_ptr(), i.numel()) for d, i in subs],
-                                          (fd.data_ptr(), tot_d, fi.data_ptr(), tot_i))
-    ms_kernels = eng.stats()["ms_total"]
-    launches = eng.stats()["kernel_launches"]
-    # a table = (index number, data tensor view, index tensor view, entries); offsets inside fd / fi are 16-byte aligned
-    # only by luck, so every table is cloned into its own allocation before it becomes a compaction input
+    ms_kernels, launches = 0.0, 0
     tables = {}
-    for m, r in enumerate(rows):
-        tables[2 * m] = (fd[r["data_off"]:r["data_off"] + r["data_len"]].clone(), fi[r["index_off"]:r["index_off"] + r["index_len"]].clone(), r["items"])
-    del fd, fi
     plan_log, rounds = [], 0
-    while True:
-        plan = se.plan_compactions(sorted((i, t[2]) for i, t in tables.items()), FACTOR)
-        if not plan:
-            break
-        rounds += 1
-        jobs = [([(tables[i][0].data_ptr(), tables[i][0].numel(), tables[i][1].data_ptr(), tables[i][1].numel()) for i in indices], keep)
-                for indices, _, keep in plan]
-        dc = sum(tables[i][0].numel() for indices, _, _ in plan for i in indices)
-        ic = sum(tables[i][1].numel() for indices, _, _ in plan for i in indices)
-        bc = sum(16 + capi.lib().dbeel_bloom_file_size(sum(tables[i][2] for i in indices), 0.01) for indices, _, _ in plan)
-        od = torch.empty(dc + 64, dtype=torch.uint8, device=dev)
-        oi = torch.empty(ic + 64, dtype=torch.uint8, device=dev)
-        ob = torch.empty(bc + 64, dtype=torch.uint8, device=dev)
-        seeds = [bytes([(g + rounds) % 256] * 32) for g in range(len(plan))]
-        res = eng.compact_many_device(jobs, (od.data_ptr(), dc, oi.data_ptr(), ic, ob.data_ptr(), bc), seeds=seeds)
+    for w0 in range(0, len(subs), FACTOR):
+        wave = subs[w0:w0 + FACTOR]
+        tot_d = sum(d.numel() for d, _ in wave)
+        tot_i = sum(i.numel() for _, i in wave)
+        fd = torch.empty(tot_d + 64, dtype=torch.uint8, device=dev)
+        fi = torch.empty(tot_i + 64, dtype=torch.uint8, device=dev)
+        _, _, _, rows = eng.flush_many_device([(d.data_ptr(), d.numel(), i.data_ptr(), i.numel()) for d, i in wave],
+                                              (fd.data_ptr(), tot_d, fi.data_ptr(), tot_i))
         ms_kernels += eng.stats()["ms_total"]
         launches += eng.stats()["kernel_launches"]
-        for (indices, out_index, keep), r, seed in zip(plan, res, seeds):
-            for i in indices:
-                del tables[i]
-            tables[out_index] = (od[r["data_off"]:r["data_off"] + r["data_len"]].clone(), oi[r["index_off"]:r["index_off"] + r["index_len"]].clone(),
-                                 r["items_written"], ob[r["bloom_off"]:r["bloom_off"] + r["bloom_len"]].clone() if r["bloom_len"] else None)
-            plan_log.append((indices, out_index, keep, seed))
+        # a table = (data, index, entries[, bloom]); slices of fd / fi are 16-byte aligned only by luck, so every table is
+        # cloned into its own allocation before it becomes a compaction input
+        for m, r in enumerate(rows):
+            tables[2 * (w0 + m)] = (fd[r["data_off"]:r["data_off"] + r["data_len"]].clone(),
+                                    fi[r["index_off"]:r["index_off"] + r["index_len"]].clone(), r["items"])
+        while True:
+            plan = se.plan_compactions(sorted((i, t[2]) for i, t in tables.items()), FACTOR)
+            if not plan:
+                break
+            rounds += 1
+            jobs = [([(tables[i][0].data_ptr(), tables[i][0].numel(), tables[i][1].data_ptr(), tables[i][1].numel()) for i in indices], keep)
+                    for indices, _, keep in plan]
+            dc = sum(tables[i][0].numel() for indices, _, _ in plan for i in indices)
+            ic = sum(tables[i][1].numel() for indices, _, _ in plan for i in indices)
+            bc = sum(16 + capi.lib().dbeel_bloom_file_size(sum(tables[i][2] for i in indices), 0.01) for indices, _, _ in plan)
+            od = torch.empty(dc + 64, dtype=torch.uint8, device=dev)
+            oi = torch.empty(ic + 64, dtype=torch.uint8, device=dev)
+            ob = torch.empty(bc + 64, dtype=torch.uint8, device=dev)
+            seeds = [bytes([(g + rounds) % 256] * 32) for g in range(len(plan))]
+            res = eng.compact_many_device(jobs, (od.data_ptr(), dc, oi.data_ptr(), ic, ob.data_ptr(), bc), seeds=seeds)
+            ms_kernels += eng.stats()["ms_total"]
+            launches += eng.stats()["kernel_launches"]
+            for (indices, out_index, keep), r, seed in zip(plan, res, seeds):
+                for i in indices:
+                    del tables[i]
+                tables[out_index] = (od[r["data_off"]:r["data_off"] + r["data_len"]].clone(),
+                                     oi[r["index_off"]:r["index_off"] + r["index_len"]].clone(), r["items_written"],
+                                     ob[r["bloom_off"]:r["bloom_off"] + r["bloom_len"]].clone() if r["bloom_len"] else None)
+                plan_log.append((indices, out_index, keep, seed))
     torch.cuda.synchronize()
     gpu_wall = time.perf_counter() - t0
 
