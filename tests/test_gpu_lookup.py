@@ -116,7 +116,7 @@ def test_device_resident_lookup_on_compaction_output(engine):
     rng = np.random.default_rng(4)
     keys = [present[j] for j in rng.choice(n, 20_000, replace=False)] + [b"\xb0k%015d" % int(x) for x in rng.integers(0, 1 << 40, 5000)]
     blob, off = capi.pack_keys(keys)
-    d_keys, d_off = torch.from_numpy(blob).to(dev), torch.from_numpy(off.view(np.int64)).to(dev)
+    d_keys, d_off = torch.from_numpy(blob.copy()).to(dev), torch.from_numpy(off.view(np.int64)).to(dev)
     d_res = torch.zeros(len(keys) * 2, dtype=torch.int64, device=dev)
     torch.cuda.synchronize()
     for mode in (capi.LOOKUP_REFERENCE, capi.LOOKUP_EXACT):

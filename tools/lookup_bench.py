@@ -49,7 +49,7 @@ def main():
         m = keys.shape[0]
         blob = np.ascontiguousarray(keys).reshape(-1)
         off = (np.arange(m + 1, dtype=np.uint64) * klen)
-        d_keys, d_off = torch.from_numpy(blob).to(dev), torch.from_numpy(off.view(np.int64)).to(dev)
+        d_keys, d_off = torch.from_numpy(blob.copy()).to(dev), torch.from_numpy(off.view(np.int64)).to(dev)
         d_res = torch.zeros(2 * m, dtype=torch.int64, device=dev)
         table = [(od.data_ptr(), dl, oi.data_ptr(), il, ob.data_ptr(), bl)]
         for mode, mname in ((capi.LOOKUP_REFERENCE, "reference loop"), (capi.LOOKUP_EXACT, "exact")):
