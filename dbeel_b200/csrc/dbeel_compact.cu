@@ -374,11 +374,11 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     // through cudaMemcpyAsync: a small copy on this stream would queue on a copy engine behind whatever bulk transfer
     // of the pipelined host path is in flight there (measured: every partition's kernels waited for the previous
     // partition's 200 MB D2H).  The compute stream carries kernels and event records only.
+    if (record_start) CU(cudaEventRecord(e->ev[EV_START], s)); // ms_total covers the header upload and the filter's memset too
     k_copy_words<<<(uint32_t)((header_bytes / 4 + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint32_t *>(ws),
                                                                             reinterpret_cast<const uint32_t *>(e->pin_dev), (uint32_t)(header_bytes / 4));
     launches++;
     if (sh.bloom_file) CU(cudaMemsetAsync(out->bloom, 0, sh.bloom_file, s));
-    if (record_start) CU(cudaEventRecord(e->ev[EV_START], s));
 
     // ---- K0/K1: prefix, validate, extract (+ conditional redo when a run was truncated)
     const uint32_t g256 = (N + 255) / 256;
