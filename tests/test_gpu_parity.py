@@ -489,3 +489,33 @@ def test_compact_many_edge_shapes(engine):
     bad_d, bad_i = one[0][0].copy(), one[0][1].copy()
     bad_i[16 * 50 + 12:16 * 50 + 16] = np.frombuffer((7).to_bytes(4, "little"), np.uint8)
     _compact_many_check(engine, [(random_runs(rng, 3, 100, pool), False), ([(bad_d, bad_i)] + one, True)], 1 << 20, "truncated job")
+
+
+def test_multi_megabyte_entries_and_keys(engine):
+    """Far beyond the server's request cap: documents of several MB (one entry spans hundreds of gather tiles) and keys of
+    100 KB that differ only in their last byte (the 12-byte comparison window never decides: every comparison walks the
+    full keys), through compact, flush, flush_many and the WAL replay."""
+    rng = np.random.default_rng(91)
+    big = lambda n: bytes(rng.integers(0, 256, n, dtype=np.uint8))
+    stem = big(100_000)
+    keys = [stem + bytes([j]) for j in range(6)] + [b"a", b"b" * 70_000, b"b" * 70_000 + b"\x00"]
+    runs = []
+    for r in range(3):
+        ents = [(k, big(int(rng.choice([0, 10, 3_000_000, 5_500_001]))), BASE_TS + r) for k in keys if rng.random() < 0.8]
+        runs.append(sstable.build_run(sorted(ents)))
+    check_against_oracle(engine, runs, True, bloom_min_size=1000, what="huge entries keep")
+    check_against_oracle(engine, runs, False, bloom_min_size=1000, what="huge entries drop")
+    arrivals = [(keys[int(rng.integers(len(keys)))], big(int(rng.choice([0, 7, 2_100_000]))), BASE_TS + j) for j in range(40)]
+    batch = sstable.build_run(arrivals)
+    od, oi, on = oracle.memtable_flushes(batch, capacity=8192)[0]
+    gd, gi, gn = engine.flush(batch)
+    assert gn == on
+    assert_run_equal((gd, gi), (od, oi), "huge flush")
+    (md, mi, mn), (sd, si, sn) = engine.flush_many([batch, sstable.build_run(arrivals[:5])])
+    assert mn == on and np.array_equal(md, od) and np.array_equal(mi, oi) and sn <= 5
+    wal = sstable.build_wal(arrivals, pad_byte=0x11)
+    wd, wi, wn = engine.wal_flush(wal)
+    assert wn == on and np.array_equal(wd, od) and np.array_equal(wi, oi)
+    res = engine.get_many([(od, oi, None)], keys + [stem, stem + b"\xff"], capi.LOOKUP_EXACT)
+    present = {k for k, _, _ in arrivals}
+    assert [int(t) for t in res["table"]] == [0 if k in present else -1 for k in keys] + [-1, -1]
