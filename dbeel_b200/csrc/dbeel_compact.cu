@@ -418,7 +418,7 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
         if (e->merge_variant == 0) { // one CTA per tile, plain loads (kept as the A/B baseline of the TMA kernel)
             k_merge<<<(uint32_t)t_ub, kMergeThreads, 0, s>>>(p, l, src, dst);
         } else { // persistent, TMA bulk loads / stores + mbarrier
-            uint64_t grid = (uint64_t)e->sm_count * 3;
+            uint64_t grid = (uint64_t)e->sm_count * kMergeCtasPerSM;
             if (grid > t_ub) grid = t_ub;
             k_merge_tma<<<(uint32_t)grid, kMergeThreads, 2 * kMergeBufRecs * sizeof(Rec), s>>>(p, l, src, dst);
         }

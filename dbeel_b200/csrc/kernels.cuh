@@ -46,7 +46,14 @@ struct Ctl {
 };
 
 constexpr int kMergeThreads = 256;
-constexpr int kMergeVT = 7; // odd: threads walk smem at a 112-byte stride -> no bank conflicts
+#ifndef DBEEL_MERGE_VT
+#define DBEEL_MERGE_VT 7
+#endif
+#ifndef DBEEL_MERGE_CTAS
+#define DBEEL_MERGE_CTAS 3
+#endif
+constexpr int kMergeVT = DBEEL_MERGE_VT; // odd: threads walk smem at a 112-byte stride -> no bank conflicts (5 / 9 measured: DESIGN.md)
+constexpr int kMergeCtasPerSM = DBEEL_MERGE_CTAS; // persistent merge CTAs per SM
 constexpr int kMergeTile = kMergeThreads * kMergeVT; // 1792 records = 28 KB of smem
 #ifndef DBEEL_RESOLVE_THREADS
 #define DBEEL_RESOLVE_THREADS 128
@@ -766,7 +773,7 @@ __device__ __forceinline__ void tma_store_1d(void *gmem_dst, const void *smem_sr
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
 }
 
-__global__ void __launch_bounds__(kMergeThreads, 3) k_merge_tma(Params p, uint32_t level, const Rec *src, Rec *dst) {
+__global__ void __launch_bounds__(kMergeThreads, kMergeCtasPerSM) k_merge_tma(Params p, uint32_t level, const Rec *src, Rec *dst) {
     extern __shared__ __align__(128) uint8_t s_raw[];
     Rec *bufs[2] = {reinterpret_cast<Rec *>(s_raw), reinterpret_cast<Rec *>(s_raw) + kMergeBufRecs};
     __shared__ __align__(8) uint64_t s_bar[2];
