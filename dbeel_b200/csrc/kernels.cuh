@@ -865,8 +865,11 @@ __device__ __forceinline__ void ld_ts(const uint8_t *entry, uint32_t full_size, 
     *hi = ld_u64_unaligned(t + 8);
 }
 
+#ifndef DBEEL_RESOLVE_MINB
+#define DBEEL_RESOLVE_MINB 14 // 14 CTAs of 128 threads per SM = a 36-register cap: 0.249 ms vs 0.256 uncapped (40-46 registers)
+#endif
 template <bool kNarrow>
-__global__ void __launch_bounds__(kResolveThreads) k_resolve(Params p, const Rec *m, uint4 *res) {
+__global__ void __launch_bounds__(kResolveThreads, DBEEL_RESOLVE_MINB) k_resolve(Params p, const Rec *m, uint4 *res) {
     constexpr int NT = kResolveThreads;
     __shared__ Rec s_rec[NT + 2];
     __shared__ unsigned long long s_entry[NT]; // device address of each record's entry
