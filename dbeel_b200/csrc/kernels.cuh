@@ -1205,7 +1205,10 @@ __device__ __forceinline__ uint4 realign16_sel(uint4 A, uint4 B, uint32_t sh) {
 // and then walks the (sorted) entry ends 512 bytes at a time, each lane counting how many entries
 // end at or before its own vector (one OR-reduction + popcount per chunk).
 
-__global__ void __launch_bounds__(kGatherThreads, 1536 / kGatherThreads) k_gather(Params p) {
+#ifndef DBEEL_GATHER_MINB
+#define DBEEL_GATHER_MINB (1536 / DBEEL_GATHER_THREADS) // 12 CTAs of 128 threads: 40 registers (10-16 measured: DESIGN.md)
+#endif
+__global__ void __launch_bounds__(kGatherThreads, DBEEL_GATHER_MINB) k_gather(Params p) {
     constexpr int NT = kGatherThreads;
     constexpr int VPT = kGatherVecsPerThread;
     __shared__ unsigned long long s_adj[kGatherMaxEntries]; // entry address minus its tile-relative start
