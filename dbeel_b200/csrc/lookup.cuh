@@ -83,7 +83,11 @@ __device__ __forceinline__ int probe(const TableDesc &t, uint64_t rec, const uin
     return cmp_key_bytes(t.data + off + 8, cur_klen, key, klen);
 }
 
-__global__ void __launch_bounds__(256) k_lookup(LookupParams p) {
+#ifndef DBEEL_LOOKUP_MINB
+#define DBEEL_LOOKUP_MINB 4 // 4 CTAs of 256 threads per SM = a 64-register cap (1 M present keys: 0.641 ms; uncapped 72 registers 0.684,
+                           // 5 / 6 / 8 CTAs 0.672 / 0.686 / 0.763)
+#endif
+__global__ void __launch_bounds__(256, DBEEL_LOOKUP_MINB) k_lookup(LookupParams p) {
     const uint64_t q = (uint64_t)blockIdx.x * 256u + threadIdx.x;
     if (q >= p.n_keys) return;
     const uint64_t k0 = p.key_off[q];
