@@ -85,6 +85,29 @@ def test_compact_bound():
     assert capi.compact_bound([], opts) == (0, 0, 0)
 
 
+def test_compact_many_bound_sizes_every_job_on_its_own_inputs():
+    """dbeel_compact_many_bound: data / index caps are the sums over all jobs; every job gets a filter iff ITS input
+    .data bytes exceed the threshold (lsm_tree.rs:1026-1034), sized for ITS entry count, at a 16-byte aligned offset."""
+    lib = capi.lib()
+    shapes = [[(3_000_000, 16 * 9000), (10, 16)], [(500, 16 * 3)], [], [(1_048_577, 16 * 1)], [(1_048_576, 16 * 7)]]
+    jobs = (capi.Job * len(shapes))()
+    keep = []
+    for j, runs in enumerate(shapes):
+        arr = (capi.Run * max(1, len(runs)))()
+        for k, (dl, il) in enumerate(runs):
+            arr[k] = capi.Run(1, dl, 1, il)  # never dereferenced by the bound function
+        keep.append(arr)
+        jobs[j] = capi.Job(arr, len(runs), 0, None)
+    dc, ic, bc = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    assert lib.dbeel_compact_many_bound(jobs, len(shapes), 1 << 20, 0.01, C.byref(dc), C.byref(ic), C.byref(bc)) == 0
+    assert dc.value == sum(dl for runs in shapes for dl, _ in runs)
+    assert ic.value == sum(il for runs in shapes for _, il in runs)
+    pad16 = lambda n: (n + 15) // 16 * 16
+    assert bc.value == pad16(oracle.bloom_file_size(9001)) + pad16(oracle.bloom_file_size(1))  # jobs 0 and 3 only (strict >)
+    assert lib.dbeel_compact_many_bound(None, 0, 1 << 20, 0.01, C.byref(dc), C.byref(ic), C.byref(bc)) == 0 and dc.value == 0
+    assert lib.dbeel_compact_many_bound(jobs, 1, 1 << 20, 1.5, None, None, None) == capi.ERR_INVALID_ARG
+
+
 def test_strerror_and_null_handling():
     lib = capi.lib()
     assert lib.dbeel_strerror(0) == b"ok"
