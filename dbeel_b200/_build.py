@@ -12,8 +12,17 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdbeel_compact.so")
 SOURCES = ["dbeel_compact.cu", os.path.join("host", "lsm_tree_host.cc")]
-DEPS = ["dbeel_compact.cu", "kernels.cuh", "device_fns.cuh", os.path.join("host", "lsm_tree_host.cc"),
-        os.path.join("..", "..", "include", "dbeel_compact.h"), os.path.join("..", "..", "include", "dbeel_tree.h")]
+
+
+def deps() -> list[str]:
+    """Every file the library is compiled from: csrc/**/*.{cu,cuh,cc,h} and include/*.h."""
+    out = []
+    for root, _, files in os.walk(CSRC):
+        out += [os.path.join(root, f) for f in files if f.endswith((".cu", ".cuh", ".cc", ".h"))]
+    inc = os.path.join(HERE, "..", "include")
+    out += [os.path.join(inc, f) for f in os.listdir(inc) if f.endswith(".h")]
+    return out
+
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -33,7 +42,7 @@ def is_stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+    return any(os.path.getmtime(d) > t for d in deps())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -27,6 +27,7 @@ ERR_CAPACITY = 2
 ERR_INVALID_ARG = 1
 ERR_NO_DEVICE = 9
 FLAG_VERIFY_SORTED = 0x1
+FLAG_REFERENCE_READER = 0x2  # decode runs like read_next_entry (lsm_tree.rs:1158-1170): offset / key_size ignored, timestamps range-checked
 DEFAULT_BLOOM_MIN_SIZE = 1_048_576
 DEFAULT_BLOOM_FP = 0.01
 
@@ -36,7 +37,8 @@ EXPORTS = ["dbeel_abi_version", "dbeel_engine_create", "dbeel_engine_destroy", "
            "dbeel_get_many", "dbeel_get_many_device", "dbeel_wal_flush", "dbeel_wal_flush_device",
            "dbeel_compact_many_bound", "dbeel_compact_many", "dbeel_compact_many_device",
            "dbeel_bloom_bitmap_bytes", "dbeel_bloom_k_num", "dbeel_bloom_file_size", "dbeel_host_alloc",
-           "dbeel_host_free", "dbeel_last_stats", "dbeel_last_error", "dbeel_strerror"]
+           "dbeel_host_free", "dbeel_last_stats", "dbeel_last_error", "dbeel_strerror",
+           "dbeel_murmur3_32", "dbeel_ring_owner", "dbeel_shard_ring", "dbeel_route_device", "dbeel_flush_many_sparse_device"]
 
 
 class Run(C.Structure):
@@ -96,7 +98,7 @@ class Stats(C.Structure):
                 ("key_prefix_len", C.c_uint32), ("merge_passes", C.c_uint32), ("kernel_launches", C.c_uint32),
                 ("ms_total", C.c_float), ("ms_extract", C.c_float), ("ms_merge", C.c_float),
                 ("ms_resolve", C.c_float), ("ms_gather", C.c_float), ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),
-                ("gather_bytes", C.c_uint64), ("partitions", C.c_uint32), ("reserved", C.c_uint32)]
+                ("gather_bytes", C.c_uint64), ("partitions", C.c_uint32), ("index_repaired", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -182,6 +184,18 @@ def lib():
         L.dbeel_last_error.argtypes = [C.c_void_p]
         L.dbeel_strerror.restype = C.c_char_p
         L.dbeel_strerror.argtypes = [C.c_int]
+        L.dbeel_murmur3_32.restype = C.c_uint32
+        L.dbeel_murmur3_32.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32]
+        L.dbeel_ring_owner.restype = C.c_uint32
+        L.dbeel_ring_owner.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        L.dbeel_shard_ring.restype = C.c_int
+        L.dbeel_shard_ring.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.dbeel_route_device.restype = C.c_int
+        L.dbeel_route_device.argtypes = [C.c_void_p, C.POINTER(Run), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]
+        L.dbeel_flush_many_sparse_device.restype = C.c_int
+        L.dbeel_flush_many_sparse_device.argtypes = [C.c_void_p, C.POINTER(Run), C.c_uint32, C.c_uint64, C.POINTER(Out),
+                                                     C.POINTER(FlushTable)]
         _lib = L
     return _lib
 
@@ -354,6 +368,33 @@ class Engine:
         rows = [{k: int(getattr(t, k)) for k, _ in FlushTable._fields_} for t in table[:n]]
         return int(out.data_len), int(out.index_len), int(out.items_written), rows
 
+    def flush_many_sparse_device(self, batches: Sequence[Tuple[int, int, int, int]], payload_bound: int,
+                                 out_ptrs: Tuple[int, int, int, int]):
+        """dbeel_flush_many_sparse_device: like flush_many_device, for slices of a routed stream (shared .data)."""
+        n = len(batches)
+        arr = (Run * max(1, n))()
+        for j, b in enumerate(batches):
+            arr[j] = Run(*b)
+        dp, dc, ip, ic = out_ptrs
+        out = Out(dp, dc, 0, ip, ic, 0, None, 0, 0, 0)
+        table = (FlushTable * max(1, n))()
+        self._check(lib().dbeel_flush_many_sparse_device(self._h, arr, n, payload_bound, C.byref(out), table),
+                    "dbeel_flush_many_sparse_device")
+        rows = [{k: int(getattr(t, k)) for k, _ in FlushTable._fields_} for t in table[:n]]
+        return int(out.data_len), int(out.index_len), int(out.items_written), rows
+
+    def route_device(self, batch: Tuple[int, int, int, int], ring: np.ndarray, out_index_ptr: int, out_index_cap: int,
+                     shard_of_ptr: int = 0):
+        """dbeel_route_device: batch = (data_ptr, data_len, index_ptr, index_len) device pointers.  Returns (counts,
+        payload bytes) per ring position as numpy u64 arrays."""
+        ring = np.ascontiguousarray(ring, np.uint32)
+        run = Run(*batch)
+        counts = np.zeros(ring.size, np.uint64)
+        nbytes = np.zeros(ring.size, np.uint64)
+        self._check(lib().dbeel_route_device(self._h, C.byref(run), ring.ctypes.data, ring.size, out_index_ptr, out_index_cap,
+                                             shard_of_ptr or None, counts.ctypes.data, nbytes.ctypes.data), "dbeel_route_device")
+        return counts, nbytes
+
     # ---- N1: many compactions per launch sequence -------------------------------------------
     @staticmethod
     def _jobs_array(jobs_ptrs, seeds):
@@ -464,3 +505,22 @@ class Engine:
         out = Out(dp, dc, 0, ip, ic, 0, None, 0, 0, 0)
         self._check(lib().dbeel_flush_device(self._h, C.byref(run), C.byref(out)), "dbeel_flush_device")
         return int(out.data_len), int(out.index_len), int(out.items_written)
+
+
+def murmur3_32(data: bytes, seed: int = 0) -> int:
+    return int(lib().dbeel_murmur3_32(bytes(data), len(data), seed))
+
+
+def shard_ring(n_shards: int, node: Optional[str] = None):
+    """(ascending ring hashes, cpu id at each ring position) of a node's shards (shards.rs:213-214,657-670)."""
+    h = np.zeros(n_shards, np.uint32)
+    ids = np.zeros(n_shards, np.uint32)
+    rc = lib().dbeel_shard_ring(node.encode() if node else None, n_shards, h.ctypes.data, ids.ctypes.data)
+    if rc:
+        raise DbeelError(rc, "dbeel_shard_ring")
+    return h, ids
+
+
+def ring_owner(ring: np.ndarray, key_hash: int) -> int:
+    ring = np.ascontiguousarray(ring, np.uint32)
+    return int(lib().dbeel_ring_owner(ring.ctypes.data, ring.size, key_hash))

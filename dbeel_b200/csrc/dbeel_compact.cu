@@ -20,6 +20,7 @@
 #include "../../include/dbeel_compact.h"
 #include "kernels.cuh"
 #include "lookup.cuh"
+#include "route.cuh"
 #include "wal.cuh"
 
 using namespace dbeel;
@@ -55,6 +56,8 @@ struct dbeel_engine {
     // pinned host block: job header going down, control block coming back
     uint8_t *wal_ws = nullptr; // WAL replay: doubling tables + the arrival index (grow-only)
     uint64_t wal_ws_cap = 0;
+    uint8_t *route_ws = nullptr; // shard routing: owners, block histograms, totals (grow-only)
+    uint64_t route_ws_cap = 0;
     uint8_t *pin = nullptr;
     uint8_t *pin_dev = nullptr; // the same block as the GPU sees it (mapped: kernels read the header / write the control block)
     uint64_t pin_cap = 0;
@@ -288,6 +291,8 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     const uint64_t o_memtab = carve(n_groups ? 16ull * (n_groups + 1) : 0);
     const uint64_t gather_tiles = (sh.data_total + kGatherTileBytes - 1) / kGatherTileBytes;
     const uint64_t o_tfirst = carve(4ull * (gather_tiles + 2));
+    const bool ref_reader = !flush && !jobs && (o->flags & DBEEL_FLAG_REFERENCE_READER);
+    const uint64_t o_fix = carve(ref_reader ? 16ull * N : 0);
     int rc = ensure_device(e, &e->ws, &e->ws_cap, off);
     if (rc) return rc;
     rc = ensure_pinned(e, header_bytes + align_up(sizeof(Ctl), 64) + 64 + (n_groups ? 16ull * (n_groups + 1) : 0));
@@ -309,7 +314,10 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     p.rec_b = reinterpret_cast<Rec *>(ws + o_recb);
     p.src_ptr = reinterpret_cast<unsigned long long *>(ws + o_src);
     p.tile_first = reinterpret_cast<uint32_t *>(ws + o_tfirst);
+    p.tile_first_n = (uint32_t)(gather_tiles + 2);
     p.mem_table = reinterpret_cast<unsigned long long *>(ws + o_memtab);
+    p.ref_reader = ref_reader ? 1 : 0;
+    p.fix_index = reinterpret_cast<uint4 *>(ws + o_fix);
     p.out_data = static_cast<uint8_t *>(out->data);
     p.out_index = static_cast<uint4 *>(out->index);
 
@@ -383,9 +391,10 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     // ---- K0/K1: prefix, validate, extract (+ conditional redo when a run was truncated)
     const uint32_t g256 = (N + 255) / 256;
     const uint32_t gext = (N + 256 * kExtractEPT - 1) / (256 * kExtractEPT);
-    auto launch_extract = [&](uint32_t grid, int redo) {
-        if (e->narrow_loads) k_extract<true><<<grid, 256, 0, s>>>(p, redo);
-        else k_extract<false><<<grid, 256, 0, s>>>(p, redo);
+    auto launch_extract = [&](uint32_t grid, int mode) {
+        if (ref_reader) k_extract<true, true><<<grid, 256, 0, s>>>(p, mode);
+        else if (e->narrow_loads) k_extract<true, false><<<grid, 256, 0, s>>>(p, mode);
+        else k_extract<false, false><<<grid, 256, 0, s>>>(p, mode);
     };
     if (flush) {
         k_flush_prefix_init<<<1, 1, 0, s>>>(p);
@@ -396,6 +405,13 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     } else {
         k_common_prefix<<<1, 32, 0, s>>>(p, 0);
         launch_extract(gext, 0);
+        if (ref_reader) { // all four are no-ops unless an index record disagrees with its .data (lsm_tree.rs:1158-1170)
+            k_ref_repair<<<n_runs, 1024, 0, s>>>(p);
+            k_ref_reset<<<1, 256, 0, s>>>(p);
+            k_common_prefix<<<1, 32, 0, s>>>(p, 2);
+            launch_extract(gext < 592 ? gext : 592, 2);
+            launches += 4;
+        }
         k_common_prefix<<<1, 32, 0, s>>>(p, 1); // both no-ops unless a run was truncated
         launch_extract(gext < 592 ? gext : 592, 1);
         k_plan<<<1, 1, 0, s>>>(p);
@@ -484,6 +500,7 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     st.key_prefix_len = hc->prefix_len;
     st.entries_valid = hc->total;
     st.runs_truncated = hc->runs_truncated;
+    st.index_repaired = (hc->flags & kFlagRepaired) ? 1 : 0;
     if (record_start) cudaEventElapsedTime(&st.ms_total, e->ev[EV_START], e->ev[EV_GATHER]);
     if (record_start) cudaEventElapsedTime(&st.ms_extract, e->ev[EV_START], e->ev[EV_EXTRACT]);
     cudaEventElapsedTime(&st.ms_merge, e->ev[EV_EXTRACT], e->ev[EV_MERGE]);
@@ -491,6 +508,8 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     cudaEventElapsedTime(&st.ms_gather, e->ev[EV_RESOLVE], e->ev[EV_GATHER]);
     if (hc->flags & (kFlagUnsorted | kFlagVerifyFailed))
         return fail(e, DBEEL_ERR_UNSORTED_RUN, "an input run is not strictly ascending by key");
+    if (hc->out_data_len > sh.data_total) // only possible with a caller-supplied payload bound (sparse batches)
+        return fail(e, DBEEL_ERR_CAPACITY, "payload bound of a sparse batch is lower than the bytes it holds");
 
     out->data_len = hc->out_data_len;
     out->items_written = hc->out_items;
@@ -786,7 +805,7 @@ int run_job_host_pipelined(dbeel_engine *e, const dbeel_run *runs, uint32_t n_ru
         rc = run_job_device(e, dr.data(), n_runs, o, false, &dout, /*record_start=*/true, &ex); // syncs e->stream
         if (rc) break;
         const dbeel_stats &ps = e->stats;
-        if (ps.runs_truncated) { truncated = true; break; }
+        if (ps.runs_truncated || ps.index_repaired) { truncated = true; break; } // the slices were cut by index offsets: redo exactly
         total.entries_valid += ps.entries_valid;
         total.kernel_launches += ps.kernel_launches;
         total.merge_passes = ps.merge_passes > total.merge_passes ? ps.merge_passes : total.merge_passes;
@@ -1063,6 +1082,76 @@ int lookup_entry(dbeel_engine *e, const dbeel_table *tables, uint32_t n_tables, 
     return DBEEL_OK;
 }
 
+
+// ------------------------------------------------------------------------------------ cfg5: shard routing
+
+// batch / out_index / shard_of are device pointers; ring, counts, bytes live in host memory.
+int route_entry(dbeel_engine *e, const dbeel_run *batch, const uint32_t *ring, uint32_t n_shards, void *out_index, uint64_t out_index_cap,
+                uint32_t *shard_of, uint64_t *counts, uint64_t *bytes) {
+    if (!e) return DBEEL_ERR_INVALID_ARG;
+    if (!batch || !ring || !counts || n_shards == 0) return fail(e, DBEEL_ERR_INVALID_ARG, "null argument");
+    if (n_shards > kRouteMaxShards) return fail(e, DBEEL_ERR_INVALID_ARG, "more shards than DBEEL_MAX_SHARDS");
+    for (uint32_t s = 1; s < n_shards; s++)
+        if (ring[s - 1] >= ring[s]) return fail(e, DBEEL_ERR_INVALID_ARG, "ring hashes must be strictly ascending");
+    if (e->busy) return fail(e, DBEEL_ERR_BUSY, "engine busy");
+    BusyGuard g(e);
+    e->err.clear();
+    const uint64_t n64 = batch->index_len / DBEEL_INDEX_ENTRY_SIZE;
+    for (uint32_t s = 0; s < n_shards; s++) { counts[s] = 0; if (bytes) bytes[s] = 0; }
+    if (n64 >= 0xFFFFFFF0ull) return fail(e, DBEEL_ERR_TOO_MANY_ENTRIES, "too many arrivals in one batch");
+    if (n64 == 0) return DBEEL_OK;
+    if (out_index_cap < n64 * 16 || !out_index) return fail(e, DBEEL_ERR_CAPACITY, "routed index buffer too small");
+    if (((uintptr_t)batch->index | (uintptr_t)out_index) & 15) return fail(e, DBEEL_ERR_INVALID_ARG, "index buffers must be 16-byte aligned");
+    cudaError_t ce = cudaSetDevice(e->device);
+    if (ce != cudaSuccess) return fail(e, DBEEL_ERR_CUDA, "cudaSetDevice", ce);
+    RouteParams p;
+    p.data = static_cast<const uint8_t *>(batch->data);
+    p.data_len = batch->data_len;
+    p.index = static_cast<const uint4 *>(batch->index);
+    p.n = (uint32_t)n64;
+    p.n_shards = n_shards;
+    p.n_blocks = (p.n + kRouteThreads - 1) / kRouteThreads;
+    uint64_t off = 0;
+    auto carve = [&](uint64_t b) { uint64_t o2 = off; off = align_up(off + b, kAlign); return o2; };
+    const uint64_t o_ring = carve(4ull * n_shards), o_tot = carve(8ull * (3 * n_shards + 1));
+    const uint64_t o_hist = carve(4ull * p.n_blocks * n_shards), o_owner = carve(shard_of ? 0 : 4ull * p.n);
+    int rc = ensure_device(e, &e->route_ws, &e->route_ws_cap, off);
+    if (!rc) rc = ensure_pinned(e, 4096 + 8ull * (3 * n_shards + 1));
+    if (rc) return rc;
+    cudaStream_t s = e->stream;
+    // the ring goes down through the mapped pinned block like every small header (no copy-engine traffic on this stream)
+    memcpy(e->pin, ring, 4ull * n_shards);
+    p.ring = reinterpret_cast<const uint32_t *>(e->route_ws + o_ring);
+    p.totals = reinterpret_cast<unsigned long long *>(e->route_ws + o_tot);
+    p.hist = reinterpret_cast<uint32_t *>(e->route_ws + o_hist);
+    p.shard_of = shard_of ? shard_of : reinterpret_cast<uint32_t *>(e->route_ws + o_owner);
+    p.out_index = static_cast<uint4 *>(out_index);
+    CU(cudaEventRecord(e->ev[EV_START], s));
+    k_copy_words<<<(n_shards + 255) / 256, 256, 0, s>>>(reinterpret_cast<uint32_t *>(e->route_ws + o_ring), reinterpret_cast<const uint32_t *>(e->pin_dev), n_shards);
+    CU(cudaMemsetAsync(p.totals, 0, 8ull * 3 * n_shards, s));
+    CU(cudaMemsetAsync(p.totals + 3 * n_shards, 0xFF, 8, s));
+    k_route_hash<<<p.n_blocks, kRouteThreads, 0, s>>>(p);
+    k_route_scan<<<n_shards, 1024, 0, s>>>(p);
+    unsigned long long *host_tot = reinterpret_cast<unsigned long long *>(e->pin + 4096);
+    k_route_starts<<<1, 256, 0, s>>>(p, reinterpret_cast<unsigned long long *>(e->pin_dev + 4096));
+    k_route_scatter<<<p.n_blocks, kRouteThreads, 0, s>>>(p);
+    CU(cudaEventRecord(e->ev[EV_GATHER], s));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s));
+    dbeel_stats &st = e->stats;
+    memset(&st, 0, sizeof st);
+    st.entries_in = n64;
+    st.kernel_launches = 5;
+    cudaEventElapsedTime(&st.ms_total, e->ev[EV_START], e->ev[EV_GATHER]);
+    if (host_tot[3 * n_shards] != ~0ull) return fail(e, DBEEL_ERR_INVALID_ARG, "an arrival's index record does not frame an entry inside .data");
+    for (uint32_t k = 0; k < n_shards; k++) {
+        counts[k] = host_tot[k];
+        if (bytes) bytes[k] = host_tot[n_shards + k];
+    }
+    st.entries_out = n64;
+    st.input_bytes = n64 * 16;
+    return DBEEL_OK;
+}
 
 // ------------------------------------------------------------------------------------ N4: WAL replay + flush
 
@@ -1377,6 +1466,8 @@ void dbeel_engine_destroy(dbeel_engine *e) {
     if (e->stage_in2) cudaFree(e->stage_in2);
     if (e->stage_out2) cudaFree(e->stage_out2);
     if (e->bloom_dev) cudaFree(e->bloom_dev);
+    if (e->wal_ws) cudaFree(e->wal_ws);
+    if (e->route_ws) cudaFree(e->route_ws);
     for (int i = 0; i < 2; i++) {
         if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]);
         if (e->ev_comp[i]) cudaEventDestroy(e->ev_comp[i]);
@@ -1421,8 +1512,10 @@ int dbeel_compact_bound(const dbeel_run *runs, uint32_t n_runs, const dbeel_comp
     return DBEEL_OK;
 }
 
+// While an asynchronous job runs, the worker thread owns e->err and e->stats: a refused call returns the code without
+// touching either (BUSY is an expected answer for a reactor that polls).
 #define REFUSE_WHILE_ASYNC(e)                                                                  \
-    if ((e) && (e)->async_state.load(std::memory_order_acquire) != 0) return fail((e), DBEEL_ERR_BUSY, "an asynchronous job is in flight")
+    if ((e) && (e)->async_state.load(std::memory_order_acquire) != 0) return DBEEL_ERR_BUSY
 
 int dbeel_compact(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, const dbeel_compact_opts *opts,
                   dbeel_out *out) {
@@ -1441,7 +1534,7 @@ int dbeel_compact_submit(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs
     if (!e) return DBEEL_ERR_INVALID_ARG;
     if (!out || (n_runs && !runs)) return fail(e, DBEEL_ERR_INVALID_ARG, "null argument");
     int expected = 0;
-    if (!e->async_state.compare_exchange_strong(expected, 1)) return fail(e, DBEEL_ERR_BUSY, "engine busy");
+    if (!e->async_state.compare_exchange_strong(expected, 1)) return DBEEL_ERR_BUSY; // the worker owns e->err
     if (e->worker.joinable()) e->worker.join();
     e->async_runs.assign(runs, runs + n_runs); // the descriptors are copied; the buffers they point to are not
     default_opts(&e->async_opts);
@@ -1481,7 +1574,7 @@ int dbeel_flush(dbeel_engine *e, const dbeel_run *batch, dbeel_out *out) {
 }
 
 static int flush_many_entry(dbeel_engine *e, const dbeel_run *batches, uint32_t n, dbeel_out *out, dbeel_flush_table *table,
-                            bool device) {
+                            bool device, bool sparse = false, uint64_t payload_bound = 0) {
     if (!e) return DBEEL_ERR_INVALID_ARG;
     if (!out || !table || (n && !batches)) return fail(e, DBEEL_ERR_INVALID_ARG, "null argument");
     if (e->busy) return fail(e, DBEEL_ERR_BUSY, "engine busy");
@@ -1494,6 +1587,10 @@ static int flush_many_entry(dbeel_engine *e, const dbeel_run *batches, uint32_t 
     for (uint32_t i = 0; i < n; i++) table[i] = dbeel_flush_table{0, 0, 0, 0, 0};
     JobExtra ex;
     ex.flush_table = table;
+    if (sparse) { // the batches' index records point into shared .data (routed streams): no running-offset check
+        ex.sparse_offsets = true;
+        ex.data_bytes = payload_bound;
+    }
     if (device) return run_job_device(e, batches, n, &o, true, out, true, &ex);
     // host buffers: stage everything down, run, bring the concatenated SSTables back
     uint64_t in_need = 0, dsum = 0, isum = 0;
@@ -1544,6 +1641,18 @@ int dbeel_flush_many_device(dbeel_engine *e, const dbeel_run *batches, uint32_t 
                             dbeel_flush_table *table) {
     REFUSE_WHILE_ASYNC(e);
     return flush_many_entry(e, batches, n_batches, out, table, true);
+}
+
+int dbeel_flush_many_sparse_device(dbeel_engine *e, const dbeel_run *batches, uint32_t n_batches, uint64_t payload_bound,
+                                   dbeel_out *out, dbeel_flush_table *table) {
+    REFUSE_WHILE_ASYNC(e);
+    return flush_many_entry(e, batches, n_batches, out, table, true, true, payload_bound);
+}
+
+int dbeel_route_device(dbeel_engine *e, const dbeel_run *batch, const uint32_t *ring_hashes, uint32_t n_shards, void *out_index,
+                       uint64_t out_index_cap, uint32_t *shard_of, uint64_t *counts, uint64_t *payload_bytes) {
+    REFUSE_WHILE_ASYNC(e);
+    return route_entry(e, batch, ring_hashes, n_shards, out_index, out_index_cap, shard_of, counts, payload_bytes);
 }
 
 int dbeel_flush_device(dbeel_engine *e, const dbeel_run *batch, dbeel_out *out) {
@@ -1610,13 +1719,19 @@ void dbeel_host_free(void *p) {
     if (p) cudaFreeHost(p);
 }
 
+// Stats and the error text of an asynchronous job belong to its worker thread until dbeel_poll / dbeel_wait has joined it.
 int dbeel_last_stats(const dbeel_engine *e, dbeel_stats *out) {
     if (!e || !out) return DBEEL_ERR_INVALID_ARG;
+    if (e->async_state.load(std::memory_order_acquire) != 0) return DBEEL_ERR_BUSY;
     *out = e->stats;
     return DBEEL_OK;
 }
 
-const char *dbeel_last_error(const dbeel_engine *e) { return e ? e->err.c_str() : "null engine"; }
+const char *dbeel_last_error(const dbeel_engine *e) {
+    if (!e) return "null engine";
+    if (e->async_state.load(std::memory_order_acquire) != 0) return "an asynchronous job is in flight";
+    return e->err.c_str();
+}
 
 const char *dbeel_strerror(int code) {
     switch (code) {

@@ -237,4 +237,57 @@ DB_HD bool ts_decodes(uint64_t lo, uint64_t hi) {
     return secs >= -377705116800ll && secs <= 253402300799ll;
 }
 
+// ------------------------------------------------------------------------------------
+// murmur3_32 (crate murmur3 0.5.2 = MurmurHash3_x86_32): hash_bytes / hash_string of src/shards.rs:95-101, the hash the
+// consistent-hash ring routes keys by.  ld64(q) returns the little-endian u64 at bytes [8q, 8q + 8) of the message; bytes
+// at or past `len` may hold anything.
+
+DB_HD uint32_t rotl32(uint32_t v, uint32_t r) { return (v << r) | (v >> (32 - r)); }
+
+DB_HD uint32_t murmur3_mix_k(uint32_t k) {
+    k *= 0xcc9e2d51u;
+    k = rotl32(k, 15);
+    return k * 0x1b873593u;
+}
+
+template <class LoadU64>
+DB_HD uint32_t murmur3_32(uint64_t len, uint32_t seed, LoadU64 ld64) {
+    uint32_t h = seed;
+    const uint64_t nblocks = len >> 2;
+    uint64_t w = 0;
+    for (uint64_t b = 0; b < nblocks; b++) {
+        if ((b & 1) == 0) w = ld64(b >> 1);
+        const uint32_t k = (b & 1) ? (uint32_t)(w >> 32) : (uint32_t)w;
+        h ^= murmur3_mix_k(k);
+        h = rotl32(h, 13);
+        h = h * 5u + 0xe6546b64u;
+    }
+    const uint32_t tail = (uint32_t)(len & 3);
+    if (tail) {
+        if ((nblocks & 1) == 0) w = ld64(nblocks >> 1);
+        uint32_t k = (nblocks & 1) ? (uint32_t)(w >> 32) : (uint32_t)w;
+        k &= 0xFFFFFFFFu >> (8 * (4 - tail));
+        h ^= murmur3_mix_k(k);
+    }
+    h ^= (uint32_t)len;
+    h ^= h >> 16;
+    h *= 0x85ebca6bu;
+    h ^= h >> 13;
+    h *= 0xc2b2ae35u;
+    h ^= h >> 16;
+    return h;
+}
+
+// MyShard::owns_key with replica_index 0 (shards.rs:586-598, is_between :103-109): the position, on the ascending ring of
+// shard hashes, of the shard that owns key_hash -- the first one whose hash is GREATER than key_hash, wrapping to 0.
+template <class LoadRing>
+DB_HD uint32_t ring_owner(uint32_t n_shards, uint32_t key_hash, LoadRing ring) {
+    uint32_t lo = 0, hi = n_shards; // first position with ring(pos) > key_hash
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (ring(mid) > key_hash) hi = mid; else lo = mid + 1;
+    }
+    return lo == n_shards ? 0u : lo;
+}
+
 } // namespace dbeel

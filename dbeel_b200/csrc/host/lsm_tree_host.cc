@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../../include/dbeel_tree.h"
+#include "../device_fns.cuh" // the scalar arithmetic the kernels use, compiled for the host here (murmur3_32, ring_owner)
 
 namespace fs = std::filesystem;
 
@@ -444,6 +445,39 @@ int dbeel_tree_recover_wal(dbeel_tree *t, uint32_t tree_capacity, uint64_t *wal_
         return DBEEL_ERR_INVALID_ARG;
     }
     if (wal_file_index) *wal_file_index = current;
+    return DBEEL_OK;
+}
+
+// ---- shard ring (src/shards.rs:95-109,213-214,586-598,657-670): host arithmetic, same code text as the routing kernel
+
+uint32_t dbeel_murmur3_32(const void *bytes, uint64_t len, uint32_t seed) {
+    const uint8_t *p = static_cast<const uint8_t *>(bytes);
+    return dbeel::murmur3_32(len, seed, [p, len](uint64_t q) {
+        uint64_t w = 0;
+        const uint64_t left = len - 8 * q;
+        memcpy(&w, p + 8 * q, left < 8 ? left : 8);
+        return w;
+    });
+}
+
+uint32_t dbeel_ring_owner(const uint32_t *ring_hashes, uint32_t n_shards, uint32_t key_hash) {
+    if (!ring_hashes || !n_shards) return 0;
+    return dbeel::ring_owner(n_shards, key_hash, [ring_hashes](uint32_t s) { return ring_hashes[s]; });
+}
+
+int dbeel_shard_ring(const char *node_name, uint32_t n_shards, uint32_t *ring_hashes, uint32_t *ring_ids) {
+    if (!ring_hashes || !ring_ids || !n_shards || n_shards > 65536) return DBEEL_ERR_INVALID_ARG;
+    std::vector<std::pair<uint32_t, uint32_t>> ring;
+    for (uint32_t id = 0; id < n_shards; id++) {
+        const std::string name = std::string(node_name ? node_name : "dbeel") + "-" + std::to_string(id); // shards.rs:213
+        ring.emplace_back(dbeel_murmur3_32(name.data(), name.size(), 0), id);
+    }
+    std::sort(ring.begin(), ring.end());
+    for (uint32_t p = 0; p < n_shards; p++) {
+        if (p && ring[p].first == ring[p - 1].first) return DBEEL_ERR_INVALID_ARG;
+        ring_hashes[p] = ring[p].first;
+        ring_ids[p] = ring[p].second;
+    }
     return DBEEL_OK;
 }
 

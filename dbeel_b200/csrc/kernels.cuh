@@ -31,7 +31,10 @@ struct Seg {
 enum : uint32_t {
     kFlagTruncated = 1u,   // some run ended before its last index record
     kFlagUnsorted = 2u,    // a valid entry does not carry the job's common key prefix
-    kFlagVerifyFailed = 4u // DBEEL_FLAG_VERIFY_SORTED found a descent or duplicate
+    kFlagVerifyFailed = 4u, // DBEEL_FLAG_VERIFY_SORTED found a descent or duplicate
+    // DBEEL_FLAG_REFERENCE_READER only (lsm_tree.rs:1158-1170 never looks at `offset` / `key_size`):
+    kFlagIndexDiffers = 8u, // some index record disagrees with what a sequential read of .data yields
+    kFlagRepaired = 16u     // ... so the job runs on a canonical copy of the index (k_ref_repair)
 };
 
 struct Ctl {
@@ -111,6 +114,8 @@ struct Params {
     uint32_t flush_slots;   // flush-many: leaf segments (sort tiles) reserved per memtable, a power of two; 0 otherwise
     uint32_t flush_ref_run; // flush: the batch whose first arrival seeds the common-prefix reduction
     uint32_t sparse_offsets; // WAL replay: index offsets point into the log, records do not abut (no running-offset check)
+    uint32_t ref_reader;     // DBEEL_FLAG_REFERENCE_READER: decode runs exactly like read_next_entry (lsm_tree.rs:1158-1170)
+    uint4 *fix_index;        // [n_total] canonical index records, written only when an input index disagrees with its .data
     uint32_t n_groups;         // flush-many: memtables, compact-many: jobs, 0 for a single job
     uint32_t group_slots;      // compact-many: leaf segments reserved per job (runs padded to a power of two), else 0
     const GroupDesc *groups;   // compact-many only
@@ -120,6 +125,7 @@ struct Params {
     uint4 *out_index;
     unsigned long long *src_ptr; // [n_total] device address of each surviving entry's bytes
     uint32_t *tile_first;        // [ceil(data bytes / 16 KB) + 2] entry holding each gather tile's first byte
+    uint32_t tile_first_n;       // gather tiles the buffers were sized for (sparse batches: the caller's bound may be too low)
     unsigned long long out_offset_base; // .data bytes written by earlier key-range partitions of the same output file
     BloomParams bloom;
 };
@@ -258,8 +264,9 @@ __device__ __forceinline__ bool key_equal(const Params &p, uint32_t skip, const 
 //
 // Keys ascend inside a run, so the prefix shared by a run's first and last key is shared by
 // every key in between; the job's prefix is the prefix common to all first/last keys.
-// validated = 0: speculative, uses n_in (index records are bounds-checked, nothing else);
-// validated = 1: runs only if some run was truncated, uses the validated counts.
+// mode 0: speculative, uses n_in (index records are bounds-checked, nothing else);
+// mode 1: runs only if some run was truncated, uses the validated counts;
+// mode 2: runs only after an index repair (reference reader), speculative again on the canonical index.
 // mode_flush: arrival batches are not sorted -> no prefix is skipped (L = 0).
 
 __device__ __forceinline__ bool safe_key(const RunDesc &rd, uint32_t i, const uint8_t **ptr, uint32_t *klen) {
@@ -271,9 +278,11 @@ __device__ __forceinline__ bool safe_key(const RunDesc &rd, uint32_t i, const ui
     return true;
 }
 
-__global__ void k_common_prefix(Params p, int validated) {
+__global__ void k_common_prefix(Params p, int mode) {
     Ctl *c = p.ctl;
-    if (validated && !(c->flags & kFlagTruncated)) return;
+    if (mode == 1 && !(c->flags & kFlagTruncated)) return;
+    if (mode == 2 && !(c->flags & kFlagRepaired)) return;
+    const int validated = mode == 1;
     const uint32_t lane = threadIdx.x;
     __shared__ const uint8_t *s_ref;
     __shared__ uint32_t s_ref_len;
@@ -330,11 +339,21 @@ __global__ void k_common_prefix(Params p, int validated) {
 #endif
 constexpr int kExtractEPT = DBEEL_EXTRACT_EPT; // entries per thread = independent load chains in flight per thread
 
-template <bool kNarrow>
-__global__ void __launch_bounds__(256, DBEEL_EXTRACT_MINB) k_extract(Params p, int redo) {
+// kRef = DBEEL_FLAG_REFERENCE_READER.  read_next_entry (lsm_tree.rs:1158-1170) consults `full_size` only: the record's
+// bytes are the next full_size bytes of the .data stream (whatever `offset` says), the key length is the one bincode
+// finds in those bytes (whatever `key_size` says), and an i128 outside `time`'s range fails the decode
+// (utils/timestamp_nanos.rs:15-24).  The default mode instead treats a wrong offset / key_size as an undecodable record.
+// With kRef the first pass only NOTES a disagreement (kFlagIndexDiffers); k_ref_repair then rebuilds a canonical index
+// (offset = running sum of full_size, key_size = 8 + the length prefix found in .data) and pass `mode 2` validates that.
+// mode 0: full validation; mode 1: only if a run was truncated -- re-extract with the shorter prefix; mode 2: full
+// validation again, only after a repair.
+template <bool kNarrow, bool kRef>
+__global__ void __launch_bounds__(256, kRef ? 3 : DBEEL_EXTRACT_MINB) k_extract(Params p, int mode) {
     auto ldu = [](const uint8_t *q) { return kNarrow ? ld_u64_unaligned_narrow(q) : ld_u64_unaligned(q); };
     Ctl *c = p.ctl;
-    if (redo && !(c->flags & kFlagTruncated)) return;
+    if (mode == 1 && !(c->flags & kFlagTruncated)) return;
+    if (mode == 2 && !(c->flags & kFlagRepaired)) return;
+    const bool redo = mode == 1;
     const uint32_t L = c->prefix_len;
     const uint64_t *pfx = reinterpret_cast<const uint64_t *>(c->prefix); // 8-byte aligned inside Ctl
     const uint32_t npw = (L + 7) >> 3;
@@ -368,6 +387,7 @@ __global__ void __launch_bounds__(256, DBEEL_EXTRACT_MINB) k_extract(Params p, i
         }
         // ---- phase 2: everything that can be decided from the index alone, then the entry header loads
         uint64_t klen_w[kExtractEPT], dlen_w[kExtractEPT], w0[kExtractEPT], w1[kExtractEPT];
+        uint64_t ts_lo[kExtractEPT], ts_hi[kExtractEPT];
         bool match[kExtractEPT];
 #pragma unroll
         for (int u = 0; u < kExtractEPT; u++) {
@@ -380,10 +400,15 @@ __global__ void __launch_bounds__(256, DBEEL_EXTRACT_MINB) k_extract(Params p, i
             }
             match[u] = false;
             klen_w[u] = dlen_w[u] = w0[u] = w1[u] = 0;
+            ts_lo[u] = ts_hi[u] = 0;
             if (ok[u]) {
                 const uint8_t *e = data[u] + off[u];
                 klen_w[u] = ldu(e);
                 dlen_w[u] = ldu(e + ks[u]);
+                if (kRef && !redo) {
+                    ts_lo[u] = ldu(e + fs[u] - 16);
+                    ts_hi[u] = ldu(e + fs[u] - 8);
+                }
                 const uint32_t klen = ks[u] - 8;
                 match[u] = klen >= L;
                 if (match[u]) {
@@ -406,6 +431,13 @@ __global__ void __launch_bounds__(256, DBEEL_EXTRACT_MINB) k_extract(Params p, i
             if (!act[u]) continue;
             if (!redo) {
                 if (ok[u]) ok[u] = klen_w[u] == (uint64_t)(ks[u] - 8) && dlen_w[u] == (uint64_t)(fs[u] - ks[u] - 24);
+                if (kRef) {
+                    // hi == 0 covers every non-negative count below 2^64 ns (year 2554): in range without the division
+                    if (ok[u] && ts_hi[u] != 0) ok[u] = ts_decodes(ts_lo[u], ts_hi[u]);
+                    // Anything wrong in pass 0 may be the index's fault rather than the data's: only the canonical index
+                    // can tell, so note it (cheap: the flag is set at most once per bad record).  Pass 2 is final.
+                    if (!ok[u] && mode == 0) atomicOr(&c->flags, kFlagIndexDiffers);
+                }
                 if (!ok[u]) {
                     atomicMin(&p.first_bad[r[u]], i[u]);
                     atomicOr(&c->flags, kFlagTruncated);
@@ -1120,7 +1152,7 @@ __global__ void __launch_bounds__(kResolveThreads) k_emit(Params p, const uint4 
     // every gather tile whose first byte lies in [off, off + fs) starts inside this entry
     constexpr unsigned long long tb = kGatherTileBytes;
     unsigned long long b = (off + tb - 1) / tb;
-    for (; b * tb < off + fs; b++) p.tile_first[b] = pos;
+    for (; b * tb < off + fs && b < p.tile_first_n; b++) p.tile_first[b] = pos;
 }
 
 // Flush-many epilogue.  The memtables' SSTables sit back to back in one output stream; every memtable's .index
@@ -1443,6 +1475,53 @@ __global__ void __launch_bounds__(256) k_verify_sorted(Params p) {
     uint32_t i = g - p.runs[r].base;
     if (i == 0 || i >= p.first_bad[r]) return;
     if (full_key_cmp(p, g - 1, g, 0) >= 0) atomicOr(&p.ctl->flags, kFlagVerifyFailed);
+}
+
+// ------------------------------------------------------------------------------------
+// DBEEL_FLAG_REFERENCE_READER, slow path: some index record disagreed with the data (k_extract<.., true> pass 0).  The
+// reference's reader never notices -- it takes full_size from the index and everything else from the next full_size
+// bytes of .data -- so the job continues on a canonical copy of the index that says what that reader sees:
+//   offset = running sum of full_size (the stream cursor), key_size = 8 + the length prefix found at the cursor.
+// One CTA per run walks it in 1024-record chunks with a carried cursor (a rare path: corrupt or foreign index files).
+__global__ void __launch_bounds__(1024) k_ref_repair(Params p) {
+    __shared__ unsigned long long s_b[32];
+    __shared__ uint32_t s_c[32];
+    if (!(p.ctl->flags & kFlagIndexDiffers)) return;
+    const RunDesc rd = p.runs[blockIdx.x];
+    unsigned long long carry = rd.off_base;
+    for (uint32_t base = 0; base < rd.n_in; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        uint4 rec = make_uint4(0, 0, 0, 0);
+        if (i < rd.n_in) rec = __ldg(&rd.index[i]);
+        unsigned long long vb = rec.w, tb;
+        uint32_t vc = 0, tc;
+        __syncthreads(); // s_b / s_c of the previous chunk are still being read
+        block_excl_scan_1024(vb, vc, s_b, s_c, &tb, &tc);
+        const unsigned long long cur = carry + vb;
+        if (i < rd.n_in) {
+            uint32_t ks = rec.z;
+            if (cur >= rd.off_base && cur <= rd.data_len && rd.data_len - cur >= 8) {
+                const uint64_t klen = ld_u64_unaligned(rd.data + cur);
+                ks = klen > 0xFFFFFFF0ull ? 0xFFFFFFFFu : (uint32_t)klen + 8u;
+            }
+            p.fix_index[rd.base + i] = make_uint4((uint32_t)cur, (uint32_t)(cur >> 32), ks, rec.w);
+        }
+        carry += tb;
+    }
+}
+
+// ... then the job state goes back to "nothing validated yet", now reading the canonical index
+__global__ void k_ref_reset(Params p) {
+    Ctl *c = p.ctl;
+    if (!(c->flags & kFlagIndexDiffers)) return;
+    RunDesc *runs = const_cast<RunDesc *>(p.runs);
+    for (uint32_t r = threadIdx.x; r < p.n_runs; r += blockDim.x) {
+        runs[r].index = p.fix_index + runs[r].base;
+        p.first_bad[r] = runs[r].n_in;
+        p.first_mismatch[r] = 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) c->flags = (c->flags & ~(kFlagIndexDiffers | kFlagTruncated)) | kFlagRepaired;
 }
 
 } // namespace dbeel

@@ -1,0 +1,128 @@
+// route.cuh -- cfg5's shard routing on the GPU: hash every arrival's key with murmur3_32 (seed 0), find the shard that
+// owns the hash on the consistent-hash ring, and split the arrival stream into one stream per shard, arrival order kept.
+//
+// Reference: hash_bytes / hash_string (src/shards.rs:95-101), the ring of shard names "<node>-<cpu id>"
+// (shards.rs:213-214, sorted by hash :657-670), MyShard::owns_key with replica_index 0 (shards.rs:586-598: a shard owns
+// [previous shard's hash, its own hash), is_between :103-109) as checked per request in src/tasks/db_server.rs:119-122.
+//
+// Only the 16-byte index records move.  A routed record keeps pointing into the batch's .data, so a shard's stream is an
+// arrival batch with SPARSE offsets: dbeel_flush_many_sparse_device flushes it without copying a payload byte twice.
+//
+//   k_route_hash     per arrival: validate the frame, murmur3_32(key), owner; per-block histogram of owners
+//   k_route_scan     one CTA per shard: exclusive scan of that shard's column over the blocks
+//   k_route_starts   one warp: shard start positions (counts, bytes) -> pinned host block
+//   k_route_scatter  per arrival: stable position = shard start + blocks before + warps before + lanes before
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_fns.cuh"
+#include "kernels.cuh"
+
+namespace dbeel {
+
+constexpr int kRouteThreads = 256;      // one arrival per thread
+constexpr uint32_t kRouteMaxShards = 256; // smem: 8 warps x 256 counters
+
+struct RouteParams {
+    const uint8_t *data;
+    uint64_t data_len;
+    const uint4 *index;
+    uint32_t n;
+    const uint32_t *ring; // [n_shards] ascending shard hashes (device)
+    uint32_t n_shards;
+    uint32_t n_blocks;
+    uint32_t *shard_of;               // [n] ring position per arrival (0xFFFFFFFF: undecodable)
+    uint32_t *hist;                   // [n_blocks][n_shards] counts, then (k_route_scan) arrivals of the shard in earlier blocks
+    unsigned long long *totals;       // [3 * n_shards + 1]: counts | payload bytes | starts ; [3 n_shards] = first bad record
+    uint4 *out_index;                 // [n] routed records, shard-major
+};
+
+__global__ void __launch_bounds__(kRouteThreads) k_route_hash(RouteParams p) {
+    __shared__ uint32_t s_cnt[kRouteMaxShards];
+    __shared__ unsigned long long s_bytes[kRouteMaxShards];
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t s = tid; s < p.n_shards; s += kRouteThreads) { s_cnt[s] = 0; s_bytes[s] = 0; }
+    __syncthreads();
+    const uint32_t i = blockIdx.x * (uint32_t)kRouteThreads + tid;
+    if (i < p.n) {
+        const uint4 rec = __ldg(&p.index[i]);
+        const uint64_t off = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
+        uint32_t owner = 0xFFFFFFFFu;
+        if (rec.z >= 8 && (uint64_t)rec.w >= (uint64_t)rec.z + 24 && off <= p.data_len && (uint64_t)rec.w <= p.data_len - off) {
+            const uint8_t *key = p.data + off + 8;
+            const uint32_t h = murmur3_32(rec.z - 8, 0u, [key](uint64_t q) { return ld_u64_unaligned_narrow(key + 8 * q); });
+            const uint32_t *ring = p.ring;
+            owner = ring_owner(p.n_shards, h, [ring](uint32_t s) { return __ldg(&ring[s]); });
+            atomicAdd(&s_cnt[owner], 1u);
+            atomicAdd(&s_bytes[owner], (unsigned long long)rec.w);
+        } else {
+            atomicMin(&p.totals[3 * p.n_shards], (unsigned long long)i);
+        }
+        p.shard_of[i] = owner;
+    }
+    __syncthreads();
+    for (uint32_t s = tid; s < p.n_shards; s += kRouteThreads) {
+        p.hist[(uint64_t)blockIdx.x * p.n_shards + s] = s_cnt[s];
+        if (s_bytes[s]) atomicAdd(&p.totals[p.n_shards + s], s_bytes[s]);
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_route_scan(RouteParams p) {
+    __shared__ unsigned long long s_b[32];
+    __shared__ uint32_t s_c[32];
+    const uint32_t s = blockIdx.x;
+    uint32_t carry = 0;
+    for (uint32_t b0 = 0; b0 < p.n_blocks; b0 += 1024) {
+        const uint32_t b = b0 + threadIdx.x;
+        const uint32_t v = b < p.n_blocks ? p.hist[(uint64_t)b * p.n_shards + s] : 0u;
+        unsigned long long vb = 0, tb;
+        uint32_t vc = v, tc;
+        __syncthreads();
+        block_excl_scan_1024(vb, vc, s_b, s_c, &tb, &tc);
+        if (b < p.n_blocks) p.hist[(uint64_t)b * p.n_shards + s] = carry + vc;
+        carry += tc;
+    }
+    if (threadIdx.x == 0) p.totals[s] = carry;
+}
+
+__global__ void k_route_starts(RouteParams p, unsigned long long *host_totals) {
+    if (threadIdx.x == 0) {
+        unsigned long long acc = 0;
+        for (uint32_t s = 0; s < p.n_shards; s++) {
+            p.totals[2 * p.n_shards + s] = acc;
+            acc += p.totals[s];
+        }
+    }
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < 3 * p.n_shards + 1; k += blockDim.x) host_totals[k] = p.totals[k];
+    __threadfence_system();
+}
+
+__global__ void __launch_bounds__(kRouteThreads) k_route_scatter(RouteParams p) {
+    __shared__ uint32_t s_warp[kRouteThreads / 32][kRouteMaxShards]; // arrivals of shard s in warp w, then in the warps before w
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t k = tid; k < (kRouteThreads / 32) * kRouteMaxShards; k += kRouteThreads) (&s_warp[0][0])[k] = 0;
+    __syncthreads();
+    const uint32_t i = blockIdx.x * (uint32_t)kRouteThreads + tid;
+    const uint32_t owner = i < p.n ? p.shard_of[i] : 0xFFFFFFFFu;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, owner);
+    const uint32_t before = __popc(peers & ((1u << lane) - 1u)); // same shard, earlier arrival, same warp
+    if (owner != 0xFFFFFFFFu && before == 0) s_warp[warp][owner] = __popc(peers);
+    __syncthreads();
+    for (uint32_t s = tid; s < p.n_shards; s += kRouteThreads) {
+        uint32_t acc = 0;
+        for (uint32_t w = 0; w < kRouteThreads / 32; w++) {
+            const uint32_t c = s_warp[w][s];
+            s_warp[w][s] = acc;
+            acc += c;
+        }
+    }
+    __syncthreads();
+    if (owner == 0xFFFFFFFFu) return;
+    const unsigned long long pos = p.totals[2 * p.n_shards + owner] + p.hist[(uint64_t)blockIdx.x * p.n_shards + owner] +
+                                   s_warp[warp][owner] + before;
+    p.out_index[pos] = __ldg(&p.index[i]);
+}
+
+} // namespace dbeel

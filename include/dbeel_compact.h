@@ -89,6 +89,16 @@ typedef struct dbeel_out {
 } dbeel_out;
 
 #define DBEEL_FLAG_VERIFY_SORTED 0x1u /* full adjacent-key check of every input run */
+/* Decode the input runs exactly like the reference's sequential reader (read_next_entry, lsm_tree.rs:1158-1170):
+ *   - an index record's `offset` and `key_size` are IGNORED -- the entry is the next full_size bytes of the .data stream
+ *     and its key length is the bincode length prefix found there (the output .index carries the recomputed values,
+ *     entry_writer.rs:76-86);
+ *   - an i128 timestamp outside `time`'s +-9999-year range fails the decode (utils/timestamp_nanos.rs:15-24) and, like
+ *     every decode error, ends that run (lsm_tree.rs:1014,1063).
+ * Without the flag the engine is stricter about the index (a wrong offset / key_size ends the run) and does not range-
+ * check timestamps; on files the reference's own writer produced both modes give byte-identical output.
+ * dbeel_compact / dbeel_compact_device / dbeel_compact_submit only. */
+#define DBEEL_FLAG_REFERENCE_READER 0x2u
 
 typedef struct dbeel_compact_opts {
     int32_t keep_tombstones;   /* LSMTree::compact's third argument (lsm_tree.rs:954)      */
@@ -117,7 +127,7 @@ typedef struct dbeel_stats {
     float ms_h2d, ms_d2h;      /* host entry points only                                   */
     uint64_t gather_bytes;     /* algorithmic bytes of the gather kernel (read + written)  */
     uint32_t partitions;       /* host entry points: key-range partitions pipelined (1 = single shot) */
-    uint32_t reserved;
+    uint32_t index_repaired;   /* DBEEL_FLAG_REFERENCE_READER: 1 = an input index disagreed with its .data and the job ran on the canonical index */
 } dbeel_stats;
 
 typedef struct dbeel_engine dbeel_engine;
@@ -163,6 +173,37 @@ int dbeel_flush_many(dbeel_engine *e, const dbeel_run *batches, uint32_t n_batch
                      dbeel_flush_table *table /* n_batches rows, host memory */);
 int dbeel_flush_many_device(dbeel_engine *e, const dbeel_run *batches, uint32_t n_batches, dbeel_out *out,
                             dbeel_flush_table *table);
+
+/* ---- cfg5: shard routing + flushes of routed streams ---------------------------------------------------------------
+ * A dbeel node runs one shard per core; a key belongs to the shard that owns murmur3_32(key bytes, seed 0) on the
+ * consistent-hash ring of shard names "<node name>-<cpu id>" (hash_bytes / hash_string, src/shards.rs:95-101; names
+ * :213-214).  MyShard::owns_key with replica_index 0 (shards.rs:586-598, checked per request in
+ * src/tasks/db_server.rs:119-122): shard s owns the hashes in [hash of the previous shard on the ring, hash of s), wrapping
+ * -- i.e. the first shard whose hash is GREATER than the key's.  (dbeel_client picks the first shard with hash >= the key's,
+ * dbeel_client/src/lib.rs:344; the two differ only for a key whose hash equals a shard's, which that shard refuses.) */
+#define DBEEL_MAX_SHARDS 256u
+uint32_t dbeel_murmur3_32(const void *bytes, uint64_t len, uint32_t seed);                 /* host arithmetic */
+uint32_t dbeel_ring_owner(const uint32_t *ring_hashes, uint32_t n_shards, uint32_t key_hash); /* host arithmetic: ring position */
+/* Build the ring of `n_shards` shards of node `node_name` (NULL = "dbeel", args.rs): ring_hashes[] ascending,
+ * ring_ids[p] = cpu id of the shard at ring position p.  Returns 0, or DBEEL_ERR_INVALID_ARG on a hash collision. */
+int dbeel_shard_ring(const char *node_name, uint32_t n_shards, uint32_t *ring_hashes, uint32_t *ring_ids);
+
+/* Route an arrival batch (run layout, arrival order; device pointers, 16-byte aligned) to the ring's shards on the GPU.
+ * out_index (device, >= batch->index_len bytes) receives the batch's index records split into one stream per ring
+ * position: position p's arrivals, in arrival order, are records [sum(counts[0..p)), +counts[p]).  The records are
+ * unchanged -- they still point into batch->data -- so a shard's stream is an arrival batch with sparse offsets (below).
+ * shard_of (device, n u32, or NULL) receives every arrival's ring position; counts / payload_bytes (host, n_shards each;
+ * payload_bytes may be NULL) the arrivals and the sum of full_size per position. */
+int dbeel_route_device(dbeel_engine *e, const dbeel_run *batch, const uint32_t *ring_hashes /* host, ascending */,
+                       uint32_t n_shards, void *out_index, uint64_t out_index_cap, uint32_t *shard_of, uint64_t *counts,
+                       uint64_t *payload_bytes);
+
+/* dbeel_flush_many_device for batches whose index records do not abut in .data (slices of a routed stream: every batch's
+ * `data` is the shared arrival buffer, `index` a slice of dbeel_route_device's out_index).  payload_bound >= the sum of
+ * full_size over all batches (e.g. from payload_bytes above); out->data_cap >= payload_bound.  DBEEL_ERR_CAPACITY if the
+ * bound turns out too low (nothing is written past it). */
+int dbeel_flush_many_sparse_device(dbeel_engine *e, const dbeel_run *batches, uint32_t n_batches, uint64_t payload_bound,
+                                   dbeel_out *out, dbeel_flush_table *table);
 
 /* ---- N1: many independent compactions in one launch sequence ---------------------------------------------------
  * compact_tree (src/tasks/compaction.rs:82-101) issues one LSMTree::compact per group of SSTables it picked, and a node

@@ -85,6 +85,12 @@ def lib():
         L.orc_get_many.restype = None
         L.orc_get_many.argtypes = [C.POINTER(_Run), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_uint32, C.c_void_p,
                                    C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_murmur3_32.restype = C.c_uint32
+        L.orc_murmur3_32.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32]
+        L.orc_ring_owner.restype = C.c_uint32
+        L.orc_ring_owner.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        L.orc_route.restype = C.c_uint64
+        L.orc_route.argtypes = [C.POINTER(_Run), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -268,3 +274,31 @@ def wal_flush(wal, capacity: int = DEFAULT_TREE_CAPACITY, emulate_page_cache: bo
     if rc:
         raise OracleError(f"orc_wal_flush rc={rc}")
     return d[:out.data_len].copy(), i[:out.index_len].copy(), int(out.items_written), int(seen.value)
+
+
+def murmur3_32(data: bytes, seed: int = 0) -> int:
+    """murmur3 0.5.2's murmur3_32 = MurmurHash3_x86_32 (shards.rs:95-101 call it with seed 0)."""
+    return int(lib().orc_murmur3_32(bytes(data), len(data), seed))
+
+
+def shard_ring(n_shards: int, node: str = "dbeel") -> np.ndarray:
+    """Ascending hashes of the shard names "<node>-<cpu id>" (shards.rs:213-214, args.rs default name) and the cpu id at
+    each ring position: returns (hashes[u32], ids[u32])."""
+    pairs = sorted((murmur3_32(f"{node}-{i}".encode()), i) for i in range(n_shards))
+    return np.array([h for h, _ in pairs], np.uint32), np.array([i for _, i in pairs], np.uint32)
+
+
+def ring_owner(ring: np.ndarray, key_hash: int) -> int:
+    ring = np.ascontiguousarray(ring, np.uint32)
+    return int(lib().orc_ring_owner(ring.ctypes.data, ring.size, key_hash))
+
+
+def route(batch: Tuple[object, object], ring: np.ndarray):
+    """owns_key (shards.rs:586-598) for every arrival of a batch: (ring position per arrival, key hash per arrival)."""
+    arr, keep = _mk_runs([batch])
+    ring = np.ascontiguousarray(ring, np.uint32)
+    n = keep[0][1].size // 16
+    shard = np.empty(n, np.uint32)
+    hashes = np.empty(n, np.uint32)
+    done = lib().orc_route(arr, ring.ctypes.data, ring.size, shard.ctypes.data, hashes.ctypes.data)
+    return shard[:done], hashes[:done]

@@ -66,4 +66,12 @@ int shim_ts_greater(const uint8_t a[16], const uint8_t b[16]) {
     memcpy(&al, a, 8); memcpy(&ah, a + 8, 8); memcpy(&bl, b, 8); memcpy(&bh, b + 8, 8);
     return ts_greater(al, ah, bl, bh) ? 1 : 0;
 }
+
+uint32_t shim_murmur3_32(const uint8_t *key, uint64_t len, uint32_t seed) {
+    return murmur3_32(len, seed, [&](uint64_t q) { return ld_le(key + 8 * q, len - 8 * q); });
+}
+
+uint32_t shim_ring_owner(const uint32_t *ring, uint32_t n, uint32_t h) {
+    return ring_owner(n, h, [&](uint32_t s) { return ring[s]; });
+}
 }

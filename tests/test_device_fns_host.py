@@ -41,6 +41,10 @@ def shim():
     L.shim_ts_decodes.argtypes = [C.c_char_p]
     L.shim_ts_greater.restype = C.c_int
     L.shim_ts_greater.argtypes = [C.c_char_p, C.c_char_p]
+    L.shim_murmur3_32.restype = C.c_uint32
+    L.shim_murmur3_32.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32]
+    L.shim_ring_owner.restype = C.c_uint32
+    L.shim_ring_owner.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
     return L
 
 
@@ -140,3 +144,20 @@ def test_timestamp_range_check_matches_oracle(shim):
     for v in vals:
         v = max(-(1 << 127), min((1 << 127) - 1, v))
         assert bool(shim.shim_ts_decodes(v.to_bytes(16, "little", signed=True))) == oracle.timestamp_decodes(v), v
+
+
+def test_murmur3_32_and_ring_owner(shim):
+    """The routing kernel's arithmetic (device_fns.cuh) against the sklearn-generated goldens and the oracle's ring walk."""
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "murmur3_32.json")))
+    for v in g["vectors"]:
+        b = bytes.fromhex(v["hex"])
+        assert shim.shim_murmur3_32(b + b"\x77" * 9, len(b), v["seed"]) == v["hash"], v  # garbage past the end is ignored
+    ring, _ = oracle.shard_ring(8)
+    rng = np.random.default_rng(4)
+    probes = [0, 1, 2**32 - 1] + [int(h) + d for h in ring for d in (-1, 0, 1)] + [int(x) for x in rng.integers(0, 2**32, 3000)]
+    for n in (1, 2, 3, 8):
+        sub = np.ascontiguousarray(ring[:n])
+        for h in probes:
+            h %= 2**32
+            assert shim.shim_ring_owner(sub.ctypes.data, n, h) == oracle.ring_owner(sub, h), (n, h)
