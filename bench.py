@@ -3,11 +3,13 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A *step* is one pass of the hot path over one batch of synthetic input: one 8-way compaction
-of 1M-key x 256-byte-doc runs (BASELINE.json configs[1], "cfg2": 2.57 GB of .data+.index in,
-bloom on, tombstones dropped).  With N > 1 every rank compacts its own independent shard of
-that shape (configs[3], weak scaling, no data-path collective; NCCL only hands the job table
-out and closes the barriers).
+A *step* is one pass of the hot path over one batch of synthetic input: the 8 independent shard
+compactions of BASELINE.json configs[3] -- each one configs[1]'s 8-way merge of 1M-key x 256-byte-doc
+runs ("cfg2" shape: 2.55 GB of .data+.index in, bloom on, tombstones dropped; seeds 40..47).  The 8 jobs
+are the same at every N: rank r runs the jobs of shards r, r+N, ... one after the other (8 / 4 / 2 / 1
+jobs per GPU at N = 1 / 2 / 4 / 8), so N = 1 does the same work as N = 8 (strong
+scaling, no data-path collective; NCCL only hands the job table out, closes the barriers and reduces the
+report).  Per-job figures (ms_per_job, stage_ms, roofline) are configs[1]'s.
 
 `value`    whole-job MB/s of input bytes with the runs resident in HBM (all kernels of the
            pipeline; timed with CUDA events on the engine's stream, max over ranks)
@@ -17,8 +19,9 @@ out and closes the barriers).
            measured HBM copy peak
 `cpu_baseline` the CPU oracle (port of the reference's single-threaded compact()) on one core
 
---impl reference times the CPU path alone with every host core busy (one shard compaction per
-core, the way dbeel's thread-per-core runtime would run them).
+--impl reference times the CPU path alone with every host core busy (one full-size shard compaction
+per core, the way dbeel's thread-per-core runtime would run them).
+--workload cfg5 runs BASELINE.json configs[4] instead (dbeel_b200/cfg5.py).
 """
 from __future__ import annotations
 
@@ -39,6 +42,8 @@ METRIC = "compaction throughput MB/s (input bytes) at 1/2/4/8 B200 vs CPU shards
 UNIT = "MB/s"
 SEED32 = bytes(range(32))
 FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+GATHER_KERNEL = "k_gather"
+SEED32_DEFAULT_MIN = 1_048_576  # oracle.compact's bloom_min_size positional (mod.rs:19)
 
 
 def log(*a):
@@ -55,13 +60,14 @@ def hbm_peak():
 
 
 def gather_traffic_from_profile():
-    """dram read+write bytes per k_gather launch from the committed ncu summary, if any."""
+    """(dram read+write bytes per gather launch, the ncu capture it was read from) from the committed summary, if any."""
     p = os.path.join(ROOT, "profiles", "gather_traffic.json")
     try:
         with open(p) as f:
-            return json.load(f).get("dram_bytes_per_launch")
+            j = json.load(f)
+        return j.get("dram_bytes_per_launch"), j.get("source")
     except Exception:
-        return None
+        return None, None
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -135,18 +141,25 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------ workload
 
-def shard_config(rank: int, world: int, workload: str = "cfg2"):
+N_JOBS = 8  # BASELINE.json configs[3]: 8 independent shard compactions, the same 8 at every N
+WORKLOAD_NAME = "cfg4: 8 independent shard compactions, each cfg2-shaped (8-way, 1M keys/run, 256 B docs; seeds 40-47)"
+
+
+def common_config():
+    """The part of `config` both arms print (the driver compares the two)."""
+    return {"workload": WORKLOAD_NAME, "runs": 8, "keys_per_run": 1_000_000, "doc_bytes": 256, "jobs": N_JOBS,
+            "keep_tombstones": False, "bloom": True}
+
+
+def job_config(job, workload: str = "cfg2"):
     from dbeel_b200 import workloads as W
     if workload == "cfg3":  # BASELINE.json configs[2]: not the headline, kept for cross-checks
         return W.CFG3
-    if world == 1:
-        return W.CFG2
-    return W.cfg4_shard(rank)
+    return W.cfg4_shard(job.shard_id)
 
 
 def make_runs_parallel(cfg):
     """make_merge_runs, one thread per run (numpy releases the GIL in the heavy parts)."""
-    import dataclasses
     from concurrent.futures import ThreadPoolExecutor
 
     from dbeel_b200 import workloads as W
@@ -165,17 +178,87 @@ def make_runs_parallel(cfg):
         return list(ex.map(one, range(cfg.n_runs)))
 
 
+def same_output(a, b) -> bool:
+    """(data, index, bloom | None, items) of the engine vs the oracle, byte for byte."""
+    return bool(a[3] == b[3] and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+                and (a[2] is None) == (b[2] is None) and (a[2] is None or np.array_equal(a[2], b[2])))
+
+
 # ------------------------------------------------------------------------------------ GPU arm
 
-def run_gpu(args):
-    import torch
-    import torch.distributed as dist
+def device_resident_job(eng, torch, dev, runs, opts, steps, warmup):
+    """One compaction, inputs and outputs in HBM: (sum of CUDA-event ms over `steps`, stage sums, last stats, result)."""
+    from dbeel_b200 import capi
+    dc, ic, bc = capi.compact_bound([(d.size, i.size) for d, i in runs], opts)
+    t_runs = [(torch.from_numpy(d).to(dev), torch.from_numpy(i).to(dev)) for d, i in runs]
+    od = torch.empty(dc + 16, dtype=torch.uint8, device=dev)
+    oi = torch.empty(ic + 16, dtype=torch.uint8, device=dev)
+    ob = torch.empty(bc + 16, dtype=torch.uint8, device=dev)
+    d_runs = [(d.data_ptr(), d.numel(), i.data_ptr(), i.numel()) for d, i in t_runs]
+    d_out = (od.data_ptr(), dc, oi.data_ptr(), ic, ob.data_ptr(), bc)
+    for _ in range(warmup):
+        res = eng.compact_device(d_runs, d_out, opts)
+    ms = 0.0
+    stage = {"ms_extract": 0.0, "ms_merge": 0.0, "ms_resolve": 0.0, "ms_gather": 0.0}
+    for _ in range(steps):
+        res = eng.compact_device(d_runs, d_out, opts)
+        st = eng.stats()
+        ms += st["ms_total"]
+        for k in stage:
+            stage[k] += st[k]
+    out = (od[:res[0]].cpu().numpy(), oi[:res[1]].cpu().numpy(), ob[:res[2]].cpu().numpy() if res[2] else None, res[3])
+    return ms, stage, eng.stats(), out
 
+
+def other_configs(eng, torch, dev, peak):
+    """Evidence for the configs that are not the headline, outside every timed headline region (rank 0, N = 1)."""
+    import oracle
     from dbeel_b200 import capi, sstable
+    from dbeel_b200 import workloads as W
+    out = {}
+    # configs[0]: the reference's own CPU-runnable case, host entry point
+    runs = W.make_merge_runs(W.CFG1)
+    got = eng.compact(runs, False, seed=SEED32)
+    out["cfg1"] = {"workload": W.CFG1.name, "parity_vs_oracle": same_output(got, oracle.compact(runs, False, seed=SEED32)),
+                   "entries_out": got[3]}
+    # configs[2]: full size, device-resident
+    t = time.time()
+    runs = make_runs_parallel(W.CFG3)
+    opts = capi.make_opts(W.CFG3.keep_tombstones, seed=SEED32)
+    steps = 10
+    ms, stage, st, got = device_resident_job(eng, torch, dev, runs, opts, steps, 3)
+    algo = st["input_bytes"] + st["output_bytes"]
+    exp = oracle.compact(runs, W.CFG3.keep_tombstones, seed=SEED32, emulate_page_cache=True)
+    out["cfg3"] = {"workload": W.CFG3.name, "input_bytes": st["input_bytes"], "ms_per_step": round(ms / steps, 4),
+                   "value": round(st["input_bytes"] / 1e6 / (ms / steps / 1e3), 1), "unit": UNIT,
+                   "stage_ms": {k: round(v / steps, 4) for k, v in stage.items()},
+                   "pipeline_roofline": {"algo_bytes": algo, "frac": round(algo / 1e9 / (ms / steps / 1e3) / peak, 4),
+                                         "read_only_frac": round(st["input_bytes"] / 1e9 / (ms / steps / 1e3) / peak, 4)},
+                   "parity_vs_oracle": same_output(got, exp), "entries_out": got[3]}
+    log(f"[bench] other configs: cfg1 parity {out['cfg1']['parity_vs_oracle']}, cfg3 {out['cfg3']['ms_per_step']} ms/step "
+        f"parity {out['cfg3']['parity_vs_oracle']} ({time.time() - t:.0f}s)")
+    del runs, got, exp
+    try:  # configs[4], one shard's stream (the 8-GPU run is --workload cfg5)
+        from dbeel_b200 import cfg5
+        out["cfg5_one_shard"] = cfg5.run_one_shard(eng, torch, dev, n_writes=1_500_000)
+    except Exception as ex:  # pragma: no cover
+        out["cfg5_one_shard"] = {"error": repr(ex)}
+    return out
 
+
+def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # Host placement first: the thread (and every thread torch / numpy start later) moves next to this rank's GPU, so the
+    # pinned staging buffers allocated below are first-touched on the GPU's own NUMA node (main.rs:51-60 pins shards too).
+    from dbeel_b200 import capi, sstable
+    numa_node, numa_cpus = (-1, 0)
+    if not os.environ.get("DBEEL_NO_NUMA_BIND"):
+        numa_node, numa_cpus = capi.bind_to_gpu(local)
+    import torch
+    import torch.distributed as dist
+
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             log(f"[bench] --gpus {args.gpus} needs torchrun with {args.gpus} ranks; running 1 GPU")
@@ -187,27 +270,35 @@ def run_gpu(args):
     from dbeel_b200 import shard_jobs as sj
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    # job hand-off (NCCL broadcast when N > 1): rank 0 owns the table, one independent shard compaction per GPU
-    table = [sj.ShardJob(r, 40 + r if world > 1 else 2, 8, 1_000_000, 256, False) for r in range(world)] if rank == 0 else None
+    if args.workload == "cfg5":
+        from dbeel_b200 import cfg5
+        return cfg5.bench(args, torch, dist, dev, rank, world, local, ClockSampler, hbm_peak, METRIC, UNIT, log)
+    # job hand-off (NCCL broadcast when N > 1): rank 0 owns the table; shard i's compaction runs on GPU i mod N
+    n_jobs = N_JOBS if args.workload == "cfg2" else 1
+    table = [sj.ShardJob(i, 40 + i, 8, 1_000_000, 256, False) for i in range(n_jobs)] if rank == 0 else None
     mine = sj.hand_off(table, dev)
-    assert len(mine) == 1 and mine[0].shard_id == rank, mine
+    assert [j.shard_id % world for j in mine] == [rank] * len(mine), mine
 
-    cfg = shard_config(rank, world, args.workload)
     t = time.time()
-    runs = make_runs_parallel(cfg)
-    in_bytes = sstable.input_bytes(runs)
-    log(f"[bench r{rank}] generated {cfg.name}: {in_bytes / 1e6:.1f} MB in {time.time() - t:.1f}s")
+    cfgs = [job_config(j, args.workload) for j in mine]
+    jobs_runs = [make_runs_parallel(c) for c in cfgs]
+    in_bytes_job = [sstable.input_bytes(r) for r in jobs_runs]
+    in_bytes = sum(in_bytes_job)
+    log(f"[bench r{rank}] numa node {numa_node} ({numa_cpus} cpus); generated {len(mine)} job(s) of {cfgs[0].name if cfgs else '-'}: "
+        f"{in_bytes / 1e6:.1f} MB in {time.time() - t:.1f}s")
 
     eng = capi.Engine(local)
-    opts = capi.make_opts(cfg.keep_tombstones, seed=SEED32)
-    dc, ic, bc = capi.compact_bound([(d.size, i.size) for d, i in runs], opts)
+    keep = cfgs[0].keep_tombstones if cfgs else False
+    opts = capi.make_opts(keep, seed=SEED32)
+    bounds = [capi.compact_bound([(d.size, i.size) for d, i in runs], opts) for runs in jobs_runs]
+    dc, ic, bc = (max(b[k] for b in bounds) for k in range(3)) if bounds else (0, 0, 0)
 
-    # device-resident inputs / outputs (torch only owns the memory)
-    t_runs = [(torch.from_numpy(d).to(dev), torch.from_numpy(i).to(dev)) for d, i in runs]
+    # device-resident inputs of every job of this rank; ONE output SSTable buffer set, reused job after job
+    t_jobs = [[(torch.from_numpy(d).to(dev), torch.from_numpy(i).to(dev)) for d, i in runs] for runs in jobs_runs]
     od = torch.empty(dc + 16, dtype=torch.uint8, device=dev)
     oi = torch.empty(ic + 16, dtype=torch.uint8, device=dev)
     ob = torch.empty(bc + 16, dtype=torch.uint8, device=dev)
-    d_runs = [(d.data_ptr(), d.numel(), i.data_ptr(), i.numel()) for d, i in t_runs]
+    d_jobs = [[(d.data_ptr(), d.numel(), i.data_ptr(), i.numel()) for d, i in t_runs] for t_runs in t_jobs]
     d_out = (od.data_ptr(), dc, oi.data_ptr(), ic, ob.data_ptr(), bc)
     torch.cuda.synchronize()
 
@@ -216,71 +307,123 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step():
-        return eng.compact_device(d_runs, d_out, opts)
+    acc = {"ms_total": 0.0, "ms_extract": 0.0, "ms_merge": 0.0, "ms_resolve": 0.0, "ms_gather": 0.0, "kernel_launches": 0,
+           "gather_bytes": 0, "input_bytes": 0, "output_bytes": 0}
+
+    def step(record: bool):
+        for d_runs in d_jobs:
+            eng.compact_device(d_runs, d_out, opts)
+            if record:
+                st = eng.stats()
+                for k in acc:
+                    acc[k] += st[k]
 
     for _ in range(max(3, args.warmup)):
-        res = step()
+        step(False)
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
     t0 = time.perf_counter()
-    dev_ms = 0.0
-    gather_ms = 0.0
-    launches = 0
-    stage = {"ms_extract": 0.0, "ms_merge": 0.0, "ms_resolve": 0.0, "ms_gather": 0.0}
     for _ in range(args.steps):
-        res = step()
-        st = eng.stats()
-        dev_ms += st["ms_total"]
-        gather_ms += st["ms_gather"]
-        launches += st["kernel_launches"]
-        for k in stage:
-            stage[k] += st[k]
+        step(True)
     barrier()
     t1 = time.perf_counter()
     sampler.stop()
     wall_ms = (t1 - t0) * 1e3
     clocks = sampler.summary(t0, t1)
-    st = eng.stats()
-    dl, il, bl, items = res
 
-    # max over ranks of the device time (CUDA events on the engine's stream, summed over K steps)
-    tm = torch.tensor([dev_ms, wall_ms, gather_ms], dtype=torch.float64, device=dev)
-    tot = torch.tensor([float(in_bytes), float(launches)], dtype=torch.float64, device=dev)
+    # max over ranks of the device time (CUDA events on the engine's stream, summed over the rank's jobs and the K steps)
+    tm = torch.tensor([acc["ms_total"], wall_ms], dtype=torch.float64, device=dev)
+    sums = torch.tensor([float(in_bytes), float(acc["kernel_launches"]), acc["ms_total"], acc["ms_extract"], acc["ms_merge"],
+                         acc["ms_resolve"], acc["ms_gather"], float(acc["gather_bytes"]), float(acc["input_bytes"]),
+                         float(acc["output_bytes"]), float(len(mine))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    dev_ms_max, wall_ms_max, gather_ms_max = (float(x) for x in tm.tolist())
-    total_in = float(tot[0])
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    dev_ms_max, wall_ms_max = (float(x) for x in tm.tolist())
+    (total_in, launches, s_total, s_extract, s_merge, s_resolve, s_gather, s_gbytes, s_in, s_out, jobs_all) = (float(x) for x in sums.tolist())
     value = total_in * args.steps / 1e6 / (dev_ms_max / 1e3)
+    job_runs = jobs_all * args.steps  # compactions executed inside the timed region, all ranks
 
     # ---- end to end through the host entry point (pinned host buffers, H2D + D2H timed)
-    e2e_steps = max(2, min(5, args.steps))
-    pins = []
-    h_runs = []
-    for d, i in runs:
-        pd, pi = capi.PinnedBuffer(d.size), capi.PinnedBuffer(i.size)
-        pd.array[:] = d
-        pi.array[:] = i
-        pins += [pd, pi]
-        h_runs.append((pd.array, pi.array))
-    pod, poi, pob = capi.PinnedBuffer(max(1, dc)), capi.PinnedBuffer(max(1, ic)), capi.PinnedBuffer(max(1, bc))
-    del t_runs, od, oi, ob
+    del t_jobs, d_jobs, od, oi, ob
     torch.cuda.empty_cache()
-    hres = eng.compact(h_runs, cfg.keep_tombstones, seed=SEED32, out_buffers=(pod.array, poi.array, pob.array))
+    e2e_steps = max(2, min(3 if world == 1 else 5, args.steps))
+    t = time.time()
+    pins, h_jobs = [], []
+    for runs in jobs_runs:
+        h_runs = []
+        for d, i in runs:
+            pd, pi = capi.PinnedBuffer(d.size), capi.PinnedBuffer(i.size)
+            pd.array[:] = d
+            pi.array[:] = i
+            pins += [pd, pi]
+            h_runs.append((pd.array, pi.array))
+        h_jobs.append(h_runs)
+    pod, poi, pob = capi.PinnedBuffer(max(1, dc)), capi.PinnedBuffer(max(1, ic)), capi.PinnedBuffer(max(1, bc))
+    log(f"[bench r{rank}] pinned {sum(p.nbytes for p in pins) / 1e9:.1f} GB of host input in {time.time() - t:.1f}s")
+    out_bufs = (pod.array, poi.array, pob.array)
+    hres = None
+    for h_runs in h_jobs[:1]:
+        hres = eng.compact(h_runs, keep, seed=SEED32, out_buffers=out_bufs)
     barrier()
     e0 = time.perf_counter()
+    e2e_kernel_ms, e2e_parts = 0.0, 0
     for _ in range(e2e_steps):
-        hres = eng.compact(h_runs, cfg.keep_tombstones, seed=SEED32, out_buffers=(pod.array, poi.array, pob.array))
+        for h_runs in h_jobs:
+            hres = eng.compact(h_runs, keep, seed=SEED32, out_buffers=out_bufs)
+            e2e_kernel_ms += eng.stats()["ms_total"]
+            e2e_parts = eng.stats()["partitions"]
+    torch.cuda.synchronize()
+    e_rank = (time.perf_counter() - e0) * 1e3  # this rank's own time, before the closing barrier
     barrier()
     e1 = time.perf_counter()
-    st_e2e = eng.stats()
+    out_bytes_job = int(hres[0].size + hres[1].size + (hres[2].size if hres[2] is not None else 0)) if hres else 0
     e2e_ms = torch.tensor([(e1 - e0) * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = total_in * e2e_steps / 1e6 / (float(e2e_ms[0]) / 1e3)
-    out_bytes = int(hres[0].size + hres[1].size + (hres[2].size if hres[2] is not None else 0))
+    # per-rank host-link rates (input + output bytes of the rank's jobs over its own e2e time)
+    link = torch.zeros(world, dtype=torch.float64, device=dev)
+    link[rank] = (in_bytes + out_bytes_job * len(mine)) * e2e_steps / 1e9 / (e_rank / 1e3) if e_rank > 0 else 0.0
+    if world > 1:
+        dist.all_reduce(link, op=dist.ReduceOp.SUM)
+
+    # ---- byte parity of every job of every rank against the CPU oracle (outside the timed regions)
+    cpu = None
+    parity_mine = None
+    if not args.no_cpu:
+        import oracle
+        from concurrent.futures import ThreadPoolExecutor
+        t = time.perf_counter()
+        first = oracle.compact(jobs_runs[0], keep, seed=SEED32, emulate_page_cache=True) if jobs_runs else None
+        cpu_s = time.perf_counter() - t
+        if rank == 0 and world == 1 and first is not None:
+            cpu = {"value": round(in_bytes_job[0] / 1e6 / cpu_s, 2), "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"one full job of the workload ({cfgs[0].name}: {in_bytes_job[0] / 1e6:.0f} MB in, {cpu_s:.1f} s), 1 pass, "
+                             "C oracle port of LSMTree::compact incl. page-cache write-through copies, RAM-resident files"}
+        parity_mine = True
+        with ThreadPoolExecutor(max_workers=max(1, min(len(jobs_runs), 8))) as ex:
+            futs = [None] + [ex.submit(oracle.compact, r, keep, SEED32_DEFAULT_MIN, SEED32, True) for r in jobs_runs[1:]]
+            for k, h_runs in enumerate(h_jobs):
+                got = eng.compact(h_runs, keep, seed=SEED32, out_buffers=out_bufs)
+                exp = first if k == 0 else futs[k].result()
+                ok = same_output(got, exp)
+                parity_mine = parity_mine and ok
+                if not ok:
+                    log(f"[bench r{rank}] job {mine[k].shard_id}: output differs from the oracle")
+                futs[k] = None
+        log(f"[bench r{rank}] byte parity of {len(h_jobs)} job(s) vs the oracle: {parity_mine} ({time.perf_counter() - t:.0f}s)")
+    par = torch.tensor([1.0 if parity_mine in (True, None) else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(par, op=dist.ReduceOp.MIN)
+    parity_all = None if args.no_cpu else bool(par[0] > 0.5)
+
+    peak, peak_src = hbm_peak()
+    others = None
+    if rank == 0 and world == 1 and not args.no_cpu and args.workload == "cfg2" and not args.no_others:
+        del pins, h_jobs, jobs_runs
+        others = other_configs(eng, torch, dev, peak)
 
     if rank != 0:
         if world > 1:
@@ -288,54 +431,48 @@ def run_gpu(args):
             dist.destroy_process_group()
         return
 
-    # ---- CPU baseline + byte parity of this very run (rank 0, N = 1 only)
-    cpu = None
-    parity = None
-    if world == 1 and not args.no_cpu:
-        import oracle
-        t = time.perf_counter()
-        cd, ci, cb, cn = oracle.compact(runs, cfg.keep_tombstones, seed=SEED32, emulate_page_cache=True)
-        cpu_s = time.perf_counter() - t
-        cpu = {"value": round(in_bytes / 1e6 / cpu_s, 2), "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"the full {cfg.name} workload, 1 pass ({in_bytes / 1e6:.0f} MB in, {cpu_s:.1f} s), "
-                         "C oracle port of LSMTree::compact incl. page-cache write-through copies, RAM-resident files"}
-        parity = bool(cn == hres[3] and np.array_equal(cd, hres[0]) and np.array_equal(ci, hres[1])
-                      and cb is not None and hres[2] is not None and np.array_equal(cb, hres[2]))
-        log(f"[bench] cpu oracle {cpu['value']} MB/s; byte parity of the benchmarked output: {parity}")
-
-    peak, peak_src = hbm_peak()
-    gbytes = st["gather_bytes"]
-    g_ms = gather_ms_max / args.steps
+    ms_job = s_total / job_runs                       # mean CUDA-event ms of one compaction (configs[1] shape)
+    g_ms = s_gather / job_runs
+    gbytes = s_gbytes / job_runs
     achieved = gbytes / 1e9 / (g_ms / 1e3)
-    algo_total = st["input_bytes"] + st["output_bytes"]
+    algo_job = (s_in + s_out) / job_runs
+    traffic, traffic_src = gather_traffic_from_profile()
+    cfg_line = common_config() if args.workload == "cfg2" else {"workload": cfgs[0].name, "runs": cfgs[0].n_runs,
+                                                                "keys_per_run": cfgs[0].keys_per_run, "doc_bytes": cfgs[0].doc_bytes,
+                                                                "jobs": 1, "keep_tombstones": keep, "bloom": True}
+    cfg_line.update({"jobs_per_gpu": len(mine), "input_bytes_per_step": int(total_in), "input_bytes_per_job": in_bytes_job[0] if in_bytes_job else 0,
+                     "output_bytes_per_job": out_bytes_job,
+                     "l2_policy": "inputs_larger_than_l2 (2.55 GB per job vs 126 MB L2)",
+                     "parallelism": f"{int(jobs_all)} independent shard compactions over {world} GPU(s), shard i on GPU i mod N, no data-path collective",
+                     "timing": "sum over the rank's jobs and the K steps of CUDA-event time on the engine stream (first to last kernel), max over ranks",
+                     "host_placement": {"numa_node": numa_node, "cpus": numa_cpus}})
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": round(dev_ms_max / args.steps, 4), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": cfg.name if world == 1 else "cfg4: one cfg2-shaped shard compaction per GPU (seeds 40+rank)",
-                   "runs": cfg.n_runs, "keys_per_run": cfg.keys_per_run, "doc_bytes": cfg.doc_bytes,
-                   "input_bytes_per_step_per_gpu": in_bytes, "output_bytes_per_step": out_bytes,
-                   "entries_out": items, "bloom": bool(bl), "keep_tombstones": cfg.keep_tombstones,
-                   "l2_policy": "inputs_larger_than_l2 (2.57 GB per step vs 126 MB L2)",
-                   "parallelism": f"{world} independent shard(s), one per GPU, no data-path collective",
-                   "timing": "sum over steps of CUDA-event time on the engine stream (first to last kernel), max over ranks"},
+        "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": cfg_line,
         "wall_ms_per_step": round(wall_ms_max / args.steps, 4),
-        "stage_ms": {k: round(v / args.steps, 4) for k, v in stage.items()},
-        "pipeline_roofline": {"algo_bytes": algo_total, "achieved_gbs": round(algo_total / 1e9 / (dev_ms / args.steps / 1e3), 1),
-                              "frac": round(algo_total / 1e9 / (dev_ms / args.steps / 1e3) / peak, 4),
-                              "read_only_frac": round(st["input_bytes"] / 1e9 / (dev_ms / args.steps / 1e3) / peak, 4)},
-        "roofline": {"kernel": "k_gather", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4), "traffic": gather_traffic_from_profile(),
-                     "algo_bytes_per_launch": gbytes, "ms_per_launch": round(g_ms, 4), "peak_source": peak_src},
+        "ms_per_job": round(ms_job, 4),
+        "stage_ms": {"ms_extract": round(s_extract / job_runs, 4), "ms_merge": round(s_merge / job_runs, 4),
+                     "ms_resolve": round(s_resolve / job_runs, 4), "ms_gather": round(g_ms, 4)},
+        "pipeline_roofline": {"algo_bytes": int(algo_job), "achieved_gbs": round(algo_job / 1e9 / (ms_job / 1e3), 1),
+                              "frac": round(algo_job / 1e9 / (ms_job / 1e3) / peak, 4),
+                              "read_only_frac": round(s_in / job_runs / 1e9 / (ms_job / 1e3) / peak, 4), "per": "job (configs[1] shape)"},
+        "roofline": {"kernel": GATHER_KERNEL, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+                     "algo_bytes_per_launch": int(gbytes), "ms_per_launch": round(g_ms, 4), "peak_source": peak_src},
         "cpu_baseline": cpu,
-        "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": in_bytes,
-                "d2h_bytes_per_step": out_bytes, "steps": e2e_steps,
+        "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(total_in),
+                "d2h_bytes_per_step": int(out_bytes_job * jobs_all), "steps": e2e_steps,
                 "ms_per_step": round(float(e2e_ms[0]) / e2e_steps, 3),
-                "ms_kernels": round(st_e2e["ms_total"], 3), "partitions": st_e2e["partitions"],
+                "ms_kernels_per_job": round(e2e_kernel_ms / max(1, e2e_steps * len(mine)), 3), "partitions": e2e_parts,
+                "host_link_gbs_per_rank": [round(float(x), 1) for x in link.tolist()],
                 "api": "dbeel_compact (host pinned buffers; key-range partitions pipelined over H2D / kernels / D2H streams)"},
-        "gpu_launches": int(tot[1]),
+        "gpu_launches": int(launches),
         "clocks": clocks,
-        "parity_vs_oracle": parity,
+        "parity_vs_oracle": parity_all,
+        "parity_all_ranks": parity_all,
+        "other_configs": others,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -345,10 +482,21 @@ def run_gpu(args):
 
 # ------------------------------------------------------------------------------------ reference arm
 
+def mem_available_bytes() -> int:
+    try:
+        with open("/proc/meminfo") as f:
+            for ln in f:
+                if ln.startswith("MemAvailable:"):
+                    return int(ln.split()[1]) * 1024
+    except Exception:
+        pass
+    return 64 << 30
+
+
 def run_reference(args):
-    """The reference's CPU implementation of the path on this box's host cores: the C oracle
-    port of LSMTree::compact (the Rust reference cannot be built here: no cargo/rustc), one
-    single-threaded shard compaction per core, all cores busy -- dbeel's thread-per-core model."""
+    """The reference's CPU implementation of the path on this box's host cores: the C oracle port of LSMTree::compact
+    (the Rust reference cannot be built here: no cargo/rustc), one single-threaded FULL-SIZE shard compaction per core,
+    all cores busy -- dbeel's thread-per-core model (main.rs:51-60) on the GPU arm's own config."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -361,22 +509,18 @@ def run_reference(args):
         cores = len(os.sched_getaffinity(0))
     except Exception:
         pass
-    threads = max(1, min(cores, 64))
     steps, warm = args.steps, args.warmup
-    # calibrate the per-thread sample so the whole run stays within ~2.5 minutes
-    probe = W.make_merge_runs(W.scaled(W.CFG2, 20_000))
-    t = time.perf_counter()
-    oracle.compact(probe, False, seed=SEED32, emulate_page_cache=True)
-    mbps_1 = sstable.input_bytes(probe) / 1e6 / (time.perf_counter() - t)
-    budget_s = min(2.0, 120.0 / max(1, steps + warm))
-    # bounded sample: at most 60k keys per run (154 MB per shard) so that `threads` concurrent compactions and
-    # their outputs stay within a few tens of GB of RAM whatever the core count
-    keys = int(max(10_000, min(60_000, budget_s * mbps_1 * 1e6 / (8 * 321.0) * 0.6)))
-    distinct = [W.make_merge_runs(W.scaled(W.cfg4_shard(i), keys)) for i in range(min(threads, 8))]
+    # every thread compacts one full cfg2-shaped shard: ~2.1 GB of output + the reader / heap state, inputs shared
+    # read-only between threads (8 distinct shards, 20 GB) -> budget 5 GB per thread
+    distinct_n = min(N_JOBS, cores)
+    budget = int(mem_available_bytes() * 0.6) - distinct_n * (3 << 30)
+    threads = max(1, min(cores, 64, budget // (5 << 30)))
+    t = time.time()
+    distinct = [make_runs_parallel(W.cfg4_shard(i)) for i in range(distinct_n)]
     shards = [distinct[i % len(distinct)] for i in range(threads)]  # inputs are read-only: threads may share them
     in_bytes = sum(sstable.input_bytes(s) for s in shards)
-    log(f"[bench ref] {threads} threads x 8-way x {keys} keys ({in_bytes / 1e6:.0f} MB per step), "
-        f"1-thread probe {mbps_1:.0f} MB/s")
+    log(f"[bench ref] {threads} threads x one full cfg2-shaped compaction each ({in_bytes / 1e6:.0f} MB per step), "
+        f"{distinct_n} distinct shards generated in {time.time() - t:.0f}s")
 
     def one(s):
         oracle.compact(s, False, seed=SEED32, emulate_page_cache=True)
@@ -395,13 +539,18 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     value = in_bytes * steps / 1e6 / dt
-    sample = (f"{threads} concurrent single-threaded shard compactions per step, each 8 runs x {keys} keys x 256 B docs "
-              f"(cfg2 shape scaled; {in_bytes / 1e6:.0f} MB in per step), RAM-resident files, page-cache copies emulated")
+    # secondary: one thread alone on the same shape (no memory-bandwidth sharing)
+    t1 = time.perf_counter()
+    one(shards[0])
+    alone = sstable.input_bytes(shards[0]) / 1e6 / (time.perf_counter() - t1)
+    sample = (f"{threads} concurrent single-threaded shard compactions per step, each the FULL job of the GPU arm's config "
+              f"(8 runs x 1,000,000 keys x 256 B docs, seeds 40+i; {in_bytes / 1e6:.0f} MB in per step), RAM-resident files, "
+              "page-cache write-through copies emulated")
+    cfg_line = common_config()
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": round(dt / steps * 1e3, 2), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "cfg2-8way-1M-256B (bounded sample per core)", "runs": 8, "keys_per_run": keys,
-                       "doc_bytes": 256, "threads": threads},
+            "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": cfg_line, "threads": threads, "jobs_per_step": threads, "one_thread_alone_mbs": round(alone, 1),
             "cpu_baseline": {"value": round(value, 2), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": round(value, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -410,11 +559,14 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="dbeel_b200", choices=["dbeel_b200", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"], help="cfg2 is BASELINE.json's headline config")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the oracle legs: cpu_baseline, byte parity, other_configs (profiling runs)")
+    ap.add_argument("--no-others", action="store_true", help="skip the other_configs block (cfg1 / cfg3 / cfg5-shard evidence)")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg5"],
+                    help="cfg2 (default): BASELINE.json's headline, 8 shard jobs of configs[1]'s shape; cfg5: configs[4]")
+    ap.add_argument("--writes", type=int, default=0, help="cfg5: arrivals in the stream (default 32M)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

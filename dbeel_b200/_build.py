@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdbeel_compact.so")
-SOURCES = ["dbeel_compact.cu", os.path.join("host", "lsm_tree_host.cc")]
+SOURCES = ["dbeel_compact.cu", os.path.join("host", "lsm_tree_host.cc"), os.path.join("host", "numa_bind.cc")]
 
 
 def deps() -> list[str]:

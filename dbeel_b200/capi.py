@@ -38,7 +38,8 @@ EXPORTS = ["dbeel_abi_version", "dbeel_engine_create", "dbeel_engine_destroy", "
            "dbeel_compact_many_bound", "dbeel_compact_many", "dbeel_compact_many_device",
            "dbeel_bloom_bitmap_bytes", "dbeel_bloom_k_num", "dbeel_bloom_file_size", "dbeel_host_alloc",
            "dbeel_host_free", "dbeel_last_stats", "dbeel_last_error", "dbeel_strerror",
-           "dbeel_murmur3_32", "dbeel_ring_owner", "dbeel_shard_ring", "dbeel_route_device", "dbeel_flush_many_sparse_device"]
+           "dbeel_murmur3_32", "dbeel_ring_owner", "dbeel_shard_ring", "dbeel_route_device", "dbeel_flush_many_sparse_device",
+           "dbeel_gpu_numa_node", "dbeel_bind_to_gpu", "dbeel_memtable_cuts_device"]
 
 
 class Run(C.Structure):
@@ -184,6 +185,10 @@ def lib():
         L.dbeel_last_error.argtypes = [C.c_void_p]
         L.dbeel_strerror.restype = C.c_char_p
         L.dbeel_strerror.argtypes = [C.c_int]
+        L.dbeel_gpu_numa_node.restype = C.c_int
+        L.dbeel_gpu_numa_node.argtypes = [C.c_int]
+        L.dbeel_bind_to_gpu.restype = C.c_int
+        L.dbeel_bind_to_gpu.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.dbeel_murmur3_32.restype = C.c_uint32
         L.dbeel_murmur3_32.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32]
         L.dbeel_ring_owner.restype = C.c_uint32
@@ -192,7 +197,10 @@ def lib():
         L.dbeel_shard_ring.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p]
         L.dbeel_route_device.restype = C.c_int
         L.dbeel_route_device.argtypes = [C.c_void_p, C.POINTER(Run), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
-                                         C.c_void_p, C.c_void_p]
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
+        L.dbeel_memtable_cuts_device.restype = C.c_int
+        L.dbeel_memtable_cuts_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                                 C.c_uint32]
         L.dbeel_flush_many_sparse_device.restype = C.c_int
         L.dbeel_flush_many_sparse_device.argtypes = [C.c_void_p, C.POINTER(Run), C.c_uint32, C.c_uint64, C.POINTER(Out),
                                                      C.POINTER(FlushTable)]
@@ -383,8 +391,19 @@ class Engine:
         rows = [{k: int(getattr(t, k)) for k, _ in FlushTable._fields_} for t in table[:n]]
         return int(out.data_len), int(out.index_len), int(out.items_written), rows
 
+    def memtable_cuts_device(self, key_hash64_ptr: int, stream_starts, capacity: int = DEFAULT_TREE_CAPACITY):
+        """dbeel_memtable_cuts_device: per stream the list of cumulative arrival counts at which a full memtable ends."""
+        starts = np.ascontiguousarray(stream_starts, np.uint64)
+        n = starts.size - 1
+        cap = int((starts[-1] - starts[0]) // max(1, capacity)) + n + 1
+        cuts = np.zeros(cap, np.uint32)
+        cs = np.zeros(n + 1, np.uint32)
+        self._check(lib().dbeel_memtable_cuts_device(self._h, key_hash64_ptr or None, starts.ctypes.data, n, capacity, cuts.ctypes.data,
+                                                     cs.ctypes.data, cap), "dbeel_memtable_cuts_device")
+        return [cuts[cs[s]:cs[s + 1]].astype(np.int64) for s in range(n)]
+
     def route_device(self, batch: Tuple[int, int, int, int], ring: np.ndarray, out_index_ptr: int, out_index_cap: int,
-                     shard_of_ptr: int = 0):
+                     shard_of_ptr: int = 0, out_hash64_ptr: int = 0):
         """dbeel_route_device: batch = (data_ptr, data_len, index_ptr, index_len) device pointers.  Returns (counts,
         payload bytes) per ring position as numpy u64 arrays."""
         ring = np.ascontiguousarray(ring, np.uint32)
@@ -392,7 +411,8 @@ class Engine:
         counts = np.zeros(ring.size, np.uint64)
         nbytes = np.zeros(ring.size, np.uint64)
         self._check(lib().dbeel_route_device(self._h, C.byref(run), ring.ctypes.data, ring.size, out_index_ptr, out_index_cap,
-                                             shard_of_ptr or None, counts.ctypes.data, nbytes.ctypes.data), "dbeel_route_device")
+                                             shard_of_ptr or None, out_hash64_ptr or None, counts.ctypes.data, nbytes.ctypes.data),
+                    "dbeel_route_device")
         return counts, nbytes
 
     # ---- N1: many compactions per launch sequence -------------------------------------------
@@ -524,3 +544,12 @@ def shard_ring(n_shards: int, node: Optional[str] = None):
 def ring_owner(ring: np.ndarray, key_hash: int) -> int:
     ring = np.ascontiguousarray(ring, np.uint32)
     return int(lib().dbeel_ring_owner(ring.ctypes.data, ring.size, key_hash))
+
+
+def bind_to_gpu(device: int):
+    """dbeel_bind_to_gpu: (numa node, cpus) the calling thread was bound to, (-1, 0) when there is no NUMA topology."""
+    node, cpus = C.c_int(-1), C.c_int(0)
+    rc = lib().dbeel_bind_to_gpu(device, C.byref(node), C.byref(cpus))
+    if rc:
+        raise DbeelError(rc, "dbeel_bind_to_gpu")
+    return node.value, cpus.value

@@ -74,6 +74,8 @@ struct dbeel_engine {
     int sm_count = 148;
     int merge_variant = 1;      // DBEEL_MERGE: 0 = one CTA per tile with plain loads, 1 = persistent TMA (default)
     int narrow_loads = 1;       // DBEEL_NARROW: .L2::64B loads for random accesses in extract / resolve (A/B switch)
+    int gather_variant = 1;     // DBEEL_GATHER: 0 = 16 bytes per lane (k_gather), 1 = 32 bytes per lane + 256-bit stores (k_gather32)
+    int bloom_in_extract = 1;   // DBEEL_BLOOM_EXTRACT: 1 = k_extract hashes, k_resolve sets the bits; 0 = the gather's fused epilogue
 };
 
 namespace {
@@ -293,6 +295,9 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     const uint64_t o_tfirst = carve(4ull * (gather_tiles + 2));
     const bool ref_reader = !flush && !jobs && (o->flags & DBEEL_FLAG_REFERENCE_READER);
     const uint64_t o_fix = carve(ref_reader ? 16ull * N : 0);
+    // single job with a filter: k_extract leaves both SipHash values of every key here and k_resolve sets the survivors' bits
+    const bool hash_early = e->bloom_in_extract && !flush && !jobs && (sh.bloom_file || (extra && extra->external_bloom && extra->bloom.words));
+    const uint64_t o_hash = carve(hash_early ? 16ull * N : 0);
     int rc = ensure_device(e, &e->ws, &e->ws_cap, off);
     if (rc) return rc;
     rc = ensure_pinned(e, header_bytes + align_up(sizeof(Ctl), 64) + 64 + (n_groups ? 16ull * (n_groups + 1) : 0));
@@ -318,6 +323,7 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     p.mem_table = reinterpret_cast<unsigned long long *>(ws + o_memtab);
     p.ref_reader = ref_reader ? 1 : 0;
     p.fix_index = reinterpret_cast<uint4 *>(ws + o_fix);
+    p.hash_rec = hash_early ? reinterpret_cast<uint4 *>(ws + o_hash) : nullptr;
     p.out_data = static_cast<uint8_t *>(out->data);
     p.out_index = static_cast<uint4 *>(out->index);
 
@@ -392,9 +398,11 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     const uint32_t g256 = (N + 255) / 256;
     const uint32_t gext = (N + 256 * kExtractEPT - 1) / (256 * kExtractEPT);
     auto launch_extract = [&](uint32_t grid, int mode) {
-        if (ref_reader) k_extract<true, true><<<grid, 256, 0, s>>>(p, mode);
-        else if (e->narrow_loads) k_extract<true, false><<<grid, 256, 0, s>>>(p, mode);
-        else k_extract<false, false><<<grid, 256, 0, s>>>(p, mode);
+        if (ref_reader && hash_early) k_extract<true, true, true><<<grid, 256, 0, s>>>(p, mode);
+        else if (ref_reader) k_extract<true, true, false><<<grid, 256, 0, s>>>(p, mode);
+        else if (hash_early) k_extract<true, false, true><<<grid, 256, 0, s>>>(p, mode);
+        else if (e->narrow_loads) k_extract<true, false, false><<<grid, 256, 0, s>>>(p, mode);
+        else k_extract<false, false, false><<<grid, 256, 0, s>>>(p, mode);
     };
     if (flush) {
         k_flush_prefix_init<<<1, 1, 0, s>>>(p);
@@ -469,7 +477,8 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
 
     // ---- K5: gather + bloom (fused epilogue)
     if (gather_tiles) {
-        k_gather<<<(uint32_t)gather_tiles, kGatherThreads, 0, s>>>(p);
+        if (e->gather_variant == 1 && ((uintptr_t)out->data & 31) == 0) k_gather32<<<(uint32_t)gather_tiles, kGatherThreads, 0, s>>>(p);
+        else k_gather<<<(uint32_t)gather_tiles, kGatherThreads, 0, s>>>(p);
     }
     launches++;
     if (jobs) { // per-job filters: their own pass over the output entries
@@ -1087,7 +1096,7 @@ int lookup_entry(dbeel_engine *e, const dbeel_table *tables, uint32_t n_tables, 
 
 // batch / out_index / shard_of are device pointers; ring, counts, bytes live in host memory.
 int route_entry(dbeel_engine *e, const dbeel_run *batch, const uint32_t *ring, uint32_t n_shards, void *out_index, uint64_t out_index_cap,
-                uint32_t *shard_of, uint64_t *counts, uint64_t *bytes) {
+                uint32_t *shard_of, void *out_hash64, uint64_t *counts, uint64_t *bytes) {
     if (!e) return DBEEL_ERR_INVALID_ARG;
     if (!batch || !ring || !counts || n_shards == 0) return fail(e, DBEEL_ERR_INVALID_ARG, "null argument");
     if (n_shards > kRouteMaxShards) return fail(e, DBEEL_ERR_INVALID_ARG, "more shards than DBEEL_MAX_SHARDS");
@@ -1115,6 +1124,7 @@ int route_entry(dbeel_engine *e, const dbeel_run *batch, const uint32_t *ring, u
     auto carve = [&](uint64_t b) { uint64_t o2 = off; off = align_up(off + b, kAlign); return o2; };
     const uint64_t o_ring = carve(4ull * n_shards), o_tot = carve(8ull * (3 * n_shards + 1));
     const uint64_t o_hist = carve(4ull * p.n_blocks * n_shards), o_owner = carve(shard_of ? 0 : 4ull * p.n);
+    const uint64_t o_h64 = carve(out_hash64 ? 8ull * p.n : 0);
     int rc = ensure_device(e, &e->route_ws, &e->route_ws_cap, off);
     if (!rc) rc = ensure_pinned(e, 4096 + 8ull * (3 * n_shards + 1));
     if (rc) return rc;
@@ -1126,6 +1136,8 @@ int route_entry(dbeel_engine *e, const dbeel_run *batch, const uint32_t *ring, u
     p.hist = reinterpret_cast<uint32_t *>(e->route_ws + o_hist);
     p.shard_of = shard_of ? shard_of : reinterpret_cast<uint32_t *>(e->route_ws + o_owner);
     p.out_index = static_cast<uint4 *>(out_index);
+    p.hash64 = out_hash64 ? reinterpret_cast<unsigned long long *>(e->route_ws + o_h64) : nullptr;
+    p.out_hash64 = static_cast<unsigned long long *>(out_hash64);
     CU(cudaEventRecord(e->ev[EV_START], s));
     k_copy_words<<<(n_shards + 255) / 256, 256, 0, s>>>(reinterpret_cast<uint32_t *>(e->route_ws + o_ring), reinterpret_cast<const uint32_t *>(e->pin_dev), n_shards);
     CU(cudaMemsetAsync(p.totals, 0, 8ull * 3 * n_shards, s));
@@ -1150,6 +1162,79 @@ int route_entry(dbeel_engine *e, const dbeel_run *batch, const uint32_t *ring, u
     }
     st.entries_out = n64;
     st.input_bytes = n64 * 16;
+    return DBEEL_OK;
+}
+
+// key_hash64: device; stream_starts / cuts / cut_starts: host
+int cuts_entry(dbeel_engine *e, const void *key_hash64, const uint64_t *stream_starts, uint32_t n_streams, uint32_t capacity,
+               uint32_t *cuts, uint32_t *cut_starts, uint32_t max_cuts_total) {
+    if (!e) return DBEEL_ERR_INVALID_ARG;
+    if (!stream_starts || !cuts || !cut_starts || !n_streams) return fail(e, DBEEL_ERR_INVALID_ARG, "null argument");
+    if (capacity < 1 || capacity > kCutMaxCapacity) return fail(e, DBEEL_ERR_INVALID_ARG, "capacity above what the device cut supports (use dbeel_memtable_cut)");
+    if (e->busy) return fail(e, DBEEL_ERR_BUSY, "engine busy");
+    BusyGuard g(e);
+    e->err.clear();
+    cudaError_t ce = cudaSetDevice(e->device);
+    if (ce != cudaSuccess) return fail(e, DBEEL_ERR_CUDA, "cudaSetDevice", ce);
+    // a stream of n arrivals has at most n / capacity full memtables
+    std::vector<uint32_t> base(n_streams + 1, 0);
+    for (uint32_t s = 0; s < n_streams; s++) {
+        if (stream_starts[s + 1] < stream_starts[s] || stream_starts[s + 1] - stream_starts[s] >= 0xFFFFFFF0ull)
+            return fail(e, DBEEL_ERR_INVALID_ARG, "stream_starts must ascend");
+        base[s + 1] = base[s] + (uint32_t)((stream_starts[s + 1] - stream_starts[s]) / capacity);
+    }
+    const uint32_t total_max = base[n_streams];
+    for (uint32_t s = 0; s <= n_streams; s++) cut_starts[s] = 0;
+    if (stream_starts[n_streams] == stream_starts[0]) return DBEEL_OK;
+    if (!key_hash64) return fail(e, DBEEL_ERR_INVALID_ARG, "null key identities");
+    uint64_t off = 0;
+    auto carve = [&](uint64_t b) { uint64_t o2 = off; off = align_up(off + b, kAlign); return o2; };
+    const uint64_t o_starts = carve(8ull * (n_streams + 1)), o_base = carve(4ull * n_streams), o_n = carve(4ull * n_streams);
+    const uint64_t o_cuts = carve(4ull * (total_max + 1));
+    const uint64_t hdr = o_n; // starts | base go down, n_cuts | cuts come back
+    int rc = ensure_device(e, &e->route_ws, &e->route_ws_cap, off);
+    if (!rc) rc = ensure_pinned(e, off);
+    if (rc) return rc;
+    memcpy(e->pin + o_starts, stream_starts, 8ull * (n_streams + 1));
+    memcpy(e->pin + o_base, base.data(), 4ull * n_streams);
+    cudaStream_t s = e->stream;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(k_memtable_cuts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(12ull * kCutSlots)));
+        attr_set = true;
+    }
+    CU(cudaEventRecord(e->ev[EV_START], s));
+    k_copy_words<<<(uint32_t)((hdr / 4 + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint32_t *>(e->route_ws), reinterpret_cast<const uint32_t *>(e->pin_dev),
+                                                                    (uint32_t)(hdr / 4));
+    CutParams p;
+    p.hash64 = static_cast<const unsigned long long *>(key_hash64);
+    p.starts = reinterpret_cast<const unsigned long long *>(e->route_ws + o_starts);
+    p.n_streams = n_streams;
+    p.capacity = capacity;
+    p.max_cuts = total_max;
+    p.cut_base = reinterpret_cast<const uint32_t *>(e->route_ws + o_base);
+    p.cuts = reinterpret_cast<uint32_t *>(e->route_ws + o_cuts);
+    p.n_cuts = reinterpret_cast<uint32_t *>(e->route_ws + o_n);
+    k_memtable_cuts<<<n_streams, 1024, 12ull * kCutSlots, s>>>(p);
+    k_publish<<<1, 256, 0, s>>>(reinterpret_cast<uint32_t *>(e->pin_dev + o_n), p.n_cuts, n_streams, reinterpret_cast<uint32_t *>(e->pin_dev + o_cuts),
+                                p.cuts, total_max);
+    CU(cudaEventRecord(e->ev[EV_GATHER], s));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s));
+    dbeel_stats &st = e->stats;
+    memset(&st, 0, sizeof st);
+    st.kernel_launches = 3;
+    st.entries_in = stream_starts[n_streams] - stream_starts[0];
+    cudaEventElapsedTime(&st.ms_total, e->ev[EV_START], e->ev[EV_GATHER]);
+    const uint32_t *hn = reinterpret_cast<const uint32_t *>(e->pin + o_n), *hc = reinterpret_cast<const uint32_t *>(e->pin + o_cuts);
+    uint32_t w = 0;
+    for (uint32_t k = 0; k < n_streams; k++) {
+        cut_starts[k] = w;
+        const uint32_t nc = hn[k] < base[k + 1] - base[k] ? hn[k] : base[k + 1] - base[k];
+        if (w + nc > max_cuts_total) return fail(e, DBEEL_ERR_CAPACITY, "cuts array too small");
+        for (uint32_t c = 0; c < nc; c++) cuts[w++] = hc[base[k] + c];
+    }
+    cut_starts[n_streams] = w;
     return DBEEL_OK;
 }
 
@@ -1446,6 +1531,8 @@ int dbeel_engine_create(int device, dbeel_engine **out) {
         return DBEEL_ERR_CUDA;
     }
     if (const char *v = getenv("DBEEL_NARROW")) e->narrow_loads = atoi(v);
+    if (const char *v = getenv("DBEEL_GATHER")) e->gather_variant = atoi(v);
+    if (const char *v = getenv("DBEEL_BLOOM_EXTRACT")) e->bloom_in_extract = atoi(v);
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return DBEEL_ERR_CUDA; }
     for (int i = 0; i < EV_COUNT; i++)
         if (cudaEventCreate(&e->ev[i]) != cudaSuccess) { dbeel_engine_destroy(e); return DBEEL_ERR_CUDA; }
@@ -1650,9 +1737,15 @@ int dbeel_flush_many_sparse_device(dbeel_engine *e, const dbeel_run *batches, ui
 }
 
 int dbeel_route_device(dbeel_engine *e, const dbeel_run *batch, const uint32_t *ring_hashes, uint32_t n_shards, void *out_index,
-                       uint64_t out_index_cap, uint32_t *shard_of, uint64_t *counts, uint64_t *payload_bytes) {
+                       uint64_t out_index_cap, uint32_t *shard_of, void *out_key_hash64, uint64_t *counts, uint64_t *payload_bytes) {
     REFUSE_WHILE_ASYNC(e);
-    return route_entry(e, batch, ring_hashes, n_shards, out_index, out_index_cap, shard_of, counts, payload_bytes);
+    return route_entry(e, batch, ring_hashes, n_shards, out_index, out_index_cap, shard_of, out_key_hash64, counts, payload_bytes);
+}
+
+int dbeel_memtable_cuts_device(dbeel_engine *e, const void *key_hash64, const uint64_t *stream_starts, uint32_t n_streams,
+                               uint32_t capacity, uint32_t *cuts, uint32_t *cut_starts, uint32_t max_cuts_total) {
+    REFUSE_WHILE_ASYNC(e);
+    return cuts_entry(e, key_hash64, stream_starts, n_streams, capacity, cuts, cut_starts, max_cuts_total);
 }
 
 int dbeel_flush_device(dbeel_engine *e, const dbeel_run *batch, dbeel_out *out) {

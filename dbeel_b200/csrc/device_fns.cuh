@@ -278,6 +278,38 @@ DB_HD uint32_t murmur3_32(uint64_t len, uint32_t seed, LoadU64 ld64) {
     return h;
 }
 
+// Two murmur3_32 hashes (two seeds) in one walk over the message.
+template <class LoadU64>
+DB_HD void murmur3_32_pair(uint64_t len, uint32_t seed_a, uint32_t seed_b, LoadU64 ld64, uint32_t *out_a, uint32_t *out_b) {
+    uint32_t ha = seed_a, hb = seed_b;
+    const uint64_t nblocks = len >> 2;
+    uint64_t w = 0;
+    for (uint64_t b = 0; b < nblocks; b++) {
+        if ((b & 1) == 0) w = ld64(b >> 1);
+        const uint32_t k = murmur3_mix_k((b & 1) ? (uint32_t)(w >> 32) : (uint32_t)w);
+        ha = rotl32(ha ^ k, 13) * 5u + 0xe6546b64u;
+        hb = rotl32(hb ^ k, 13) * 5u + 0xe6546b64u;
+    }
+    const uint32_t tail = (uint32_t)(len & 3);
+    if (tail) {
+        if ((nblocks & 1) == 0) w = ld64(nblocks >> 1);
+        uint32_t k = (nblocks & 1) ? (uint32_t)(w >> 32) : (uint32_t)w;
+        k = murmur3_mix_k(k & (0xFFFFFFFFu >> (8 * (4 - tail))));
+        ha ^= k;
+        hb ^= k;
+    }
+    uint32_t h[2] = {ha ^ (uint32_t)len, hb ^ (uint32_t)len};
+    for (int i = 0; i < 2; i++) {
+        h[i] ^= h[i] >> 16;
+        h[i] *= 0x85ebca6bu;
+        h[i] ^= h[i] >> 13;
+        h[i] *= 0xc2b2ae35u;
+        h[i] ^= h[i] >> 16;
+    }
+    *out_a = h[0];
+    *out_b = h[1];
+}
+
 // MyShard::owns_key with replica_index 0 (shards.rs:586-598, is_between :103-109): the position, on the ascending ring of
 // shard hashes, of the shard that owns key_hash -- the first one whose hash is GREATER than key_hash, wrapping to 0.
 template <class LoadRing>

@@ -128,6 +128,7 @@ struct Params {
     uint32_t tile_first_n;       // gather tiles the buffers were sized for (sparse batches: the caller's bound may be too low)
     unsigned long long out_offset_base; // .data bytes written by earlier key-range partitions of the same output file
     BloomParams bloom;
+    uint4 *hash_rec; // [n_total] {h0, h1} = both SipHash-1-3 values of every entry's key (k_extract), or null: the gather hashes
 };
 
 // ------------------------------------------------------------------------------------
@@ -347,7 +348,7 @@ constexpr int kExtractEPT = DBEEL_EXTRACT_EPT; // entries per thread = independe
 // (offset = running sum of full_size, key_size = 8 + the length prefix found in .data) and pass `mode 2` validates that.
 // mode 0: full validation; mode 1: only if a run was truncated -- re-extract with the shorter prefix; mode 2: full
 // validation again, only after a repair.
-template <bool kNarrow, bool kRef>
+template <bool kNarrow, bool kRef, bool kHash>
 __global__ void __launch_bounds__(256, kRef ? 3 : DBEEL_EXTRACT_MINB) k_extract(Params p, int mode) {
     auto ldu = [](const uint8_t *q) { return kNarrow ? ld_u64_unaligned_narrow(q) : ld_u64_unaligned(q); };
     Ctl *c = p.ctl;
@@ -451,6 +452,18 @@ __global__ void __launch_bounds__(256, kRef ? 3 : DBEEL_EXTRACT_MINB) k_extract(
                 else atomicMin(&p.first_mismatch[r[u]], i[u]);
             }
             st_rec(&p.rec_a[g[u]], out);
+        }
+        // ---- bloom hashes, here rather than in the gather: this kernel waits on memory with its issue slots idle, the key
+        // bytes are in L1, and the gather is the kernel that has no instruction to spare
+        if (kHash && !redo && p.hash_rec != nullptr) {
+#pragma unroll
+            for (int u = 0; u < kExtractEPT; u++) {
+                if (!act[u] || !ok[u]) continue;
+                const uint8_t *key = data[u] + off[u] + 8;
+                uint64_t h0, h1;
+                sip13_pair_vec_u8(p.bloom.sip, (uint64_t)(ks[u] - 8), [key](uint64_t q) { return ld_u64_unaligned(key + 8 * q); }, &h0, &h1);
+                p.hash_rec[g[u]] = make_uint4((uint32_t)h0, (uint32_t)(h0 >> 32), (uint32_t)h1, (uint32_t)(h1 >> 32));
+            }
         }
     }
 }
@@ -973,11 +986,12 @@ __global__ void __launch_bounds__(kResolveThreads, DBEEL_RESOLVE_MINB) k_resolve
     s_eqn[tid] = eq_next ? 1 : 0;
     __syncthreads();
 
-    uint32_t keep = 0, ks = 0, fs = 0;
+    uint32_t keep = 0, ks = 0, fs = 0, wgid = 0;
     unsigned long long src = 0;
     if (active && !eq_prev) { // head of its group
         uint32_t w = tid; // winner so far, as an index into this tile's shared arrays
         ks = s_ks[tid]; fs = s_fs[tid]; src = s_entry[tid];
+        wgid = cur.w;
         if (eq_next) {
             uint64_t wlo = s_tlo[tid], whi = s_thi[tid];
             uint32_t j = tid;
@@ -991,6 +1005,7 @@ __global__ void __launch_bounds__(kResolveThreads, DBEEL_RESOLVE_MINB) k_resolve
                 more = s_eqn[j] != 0;
             }
             ks = s_ks[w]; fs = s_fs[w]; src = s_entry[w];
+            wgid = s_rec[w + 1].w;
             if (more) { // the group runs past the tile: finish it from global memory
                 uint32_t gj = i0 + NT; // first record of the next tile (known equal: s_eqn[NT-1])
                 while (true) {
@@ -1003,7 +1018,7 @@ __global__ void __launch_bounds__(kResolveThreads, DBEEL_RESOLVE_MINB) k_resolve
                         better = !ts_greater(wlo, whi, clo, chi);
                         if (better) { wlo = clo; whi = chi; }
                     }
-                    if (better) { ks = ck.klen + 8; fs = ck.full_size; src = (unsigned long long)(uintptr_t)ck.entry; }
+                    if (better) { ks = ck.klen + 8; fs = ck.full_size; src = (unsigned long long)(uintptr_t)ck.entry; wgid = nx.w; }
                     gj++;
                     if (gj >= lim_hi) break;
                     if (!key_equal(p, skip, nx, ld_rec(&m[gj]))) break;
@@ -1012,6 +1027,13 @@ __global__ void __launch_bounds__(kResolveThreads, DBEEL_RESOLVE_MINB) k_resolve
         }
         bool tomb = fs == ks + 24;
         keep = (keep_tombstones || p.mode_flush || !tomb) ? 1u : 0u;
+        // Bloom::set for every entry that is written (lsm_tree.rs:1049-1051), from the hashes k_extract left behind
+        if (keep && p.hash_rec != nullptr && p.bloom.words != nullptr) {
+            const uint4 hv = __ldg(&p.hash_rec[wgid]);
+            uint32_t *words = p.bloom.words;
+            bloom_probe_all((uint64_t)hv.x | ((uint64_t)hv.y << 32), (uint64_t)hv.z | ((uint64_t)hv.w << 32), p.bloom.k_num, p.bloom.bits,
+                            p.bloom.bits_magic, [words](uint64_t bit) { atomicOr(&words[bit >> 5], 1u << (bit & 31)); });
+        }
     }
     if (i < span) res[i] = make_uint4((uint32_t)src, (uint32_t)(src >> 32), ks, keep ? fs : 0u); // holes: nothing emitted
 
@@ -1354,7 +1376,184 @@ __global__ void __launch_bounds__(kGatherThreads, DBEEL_GATHER_MINB) k_gather(Pa
     }
 
     // ---- bloom (fused epilogue): entries whose first byte lies in this tile
-    if (p.bloom.words != nullptr) {
+    if (p.bloom.words != nullptr && p.hash_rec == nullptr) {
+        for (uint32_t j = tid; j < ne; j += NT) {
+            const int r0 = s_r0[j];
+            if (r0 < 0 || r0 >= (int)kGatherTileBytes) continue;
+            const uint8_t *key = reinterpret_cast<const uint8_t *>((uintptr_t)(s_adj[j] + (unsigned long long)r0)) + 8;
+            const uint64_t klen = s_ks[j] - 8;
+            uint64_t h0, h1;
+            sip13_pair_vec_u8(p.bloom.sip, klen, [key](uint64_t q) { return ld_u64_unaligned(key + 8 * q); }, &h0, &h1);
+            uint32_t *words = p.bloom.words;
+            bloom_probe_all(h0, h1, p.bloom.k_num, p.bloom.bits, p.bloom.bits_magic,
+                            [words](uint64_t bit) { atomicOr(&words[bit >> 5], 1u << (bit & 31)); });
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K5, 32 bytes per lane (the default).  Same tiles, same staging, same one barrier as k_gather; what changes is the
+// granule every lane moves: a 32-byte block = three aligned 16-byte loads + one 256-bit store (STG.E.256, new with
+// sm_100) instead of 2 x (two loads + one 128-bit store).  Per output byte that halves the vector -> entry mapping
+// (one OR-reduction + popcount now covers 1 KB), the address arithmetic and the store instructions, and takes the load
+// over-fetch from 2x to 1.5x.  A block that holds an entry boundary (one per entry at most: entries are >= 32 bytes) is
+// left to a second, dense pass that writes its two 16-byte halves: tail of entry j, head of entry j + 1, or a blend.
+// The bloom epilogue only runs when k_extract did not hash (p.hash_rec == null).
+
+__device__ __forceinline__ void realign32(const uint4 A, const uint4 B, const uint4 C, uint32_t sh, uint32_t out[8]) {
+    // 32 output bytes starting `sh` (0..15) bytes into the 48-byte window {A, B, C}; C is not read when sh == 0
+    const uint32_t bits = (sh & 3) * 8;
+    const bool s2 = sh & 8, s1 = sh & 4;
+    const uint32_t w[12] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w, C.x, C.y, C.z, C.w};
+    uint32_t c[10], d[9];
+#pragma unroll
+    for (int i = 0; i < 10; i++) c[i] = s2 ? w[i + 2] : w[i];
+#pragma unroll
+    for (int i = 0; i < 9; i++) d[i] = s1 ? c[i + 1] : c[i];
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = __funnelshift_r(d[i], d[i + 1], bits);
+}
+
+__device__ __forceinline__ void stg256(void *dst, const uint32_t v[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+
+// 16 bytes at an arbitrary address, `need` of them wanted: the second aligned load is skipped when the first one holds them all
+__device__ __forceinline__ uint4 ld16_any(uintptr_t sa, uint32_t need) {
+    const uint32_t s0 = (uint32_t)(sa & 15);
+    const uint4 *sv = reinterpret_cast<const uint4 *>(sa - s0);
+    const uint4 TA = __ldg(sv);
+    const uint4 TB = __ldg(s0 + need > 16 ? sv + 1 : sv);
+    return realign16_sel(TA, TB, s0);
+}
+
+constexpr int kG32Vpt = (int)(kGatherTileBytes / (32ull * kGatherThreads)); // 1 KB chunks per warp
+static_assert(kGatherTileBytes == 32ull * kGatherThreads * kG32Vpt, "gather tile = 32 bytes x lanes x chunks");
+
+#ifndef DBEEL_GATHER32_MINB
+#define DBEEL_GATHER32_MINB (1536 / DBEEL_GATHER_THREADS)
+#endif
+__global__ void __launch_bounds__(kGatherThreads, DBEEL_GATHER32_MINB) k_gather32(Params p) {
+    constexpr int NT = kGatherThreads;
+    __shared__ unsigned long long s_adj[kGatherMaxEntries]; // entry address minus its tile-relative start
+    __shared__ int s_r0[kGatherMaxEntries], s_r1[kGatherMaxEntries];
+    __shared__ uint32_t s_ks[kGatherMaxEntries];
+    const Ctl *c = p.ctl;
+    const unsigned long long out_len = c->out_data_len;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tile_id = blockIdx.x;
+    const unsigned long long T0 = (unsigned long long)tile_id * kGatherTileBytes;
+    if (T0 >= out_len) return;
+    const uint32_t tile_len = out_len - T0 < kGatherTileBytes ? (uint32_t)(out_len - T0) : (uint32_t)kGatherTileBytes;
+    const uint32_t e_lo = p.tile_first[tile_id];
+    const uint32_t e_hi = T0 + kGatherTileBytes < out_len ? p.tile_first[tile_id + 1] : c->out_items - 1;
+    const uint32_t ne = e_hi - e_lo + 1; // <= kGatherMaxEntries: every entry is >= 32 bytes
+    const bool hash_here = p.bloom.words != nullptr && p.hash_rec == nullptr;
+    for (uint32_t j = tid; j < ne; j += NT) {
+        const uint4 rec = p.out_index[e_lo + j];
+        const unsigned long long d0 = ((unsigned long long)rec.x | ((unsigned long long)rec.y << 32)) - p.out_offset_base;
+        const long long r0 = (long long)d0 - (long long)T0; // < 0 only for the tile's first entry
+        const long long r1 = r0 + (long long)rec.w;
+        s_adj[j] = p.src_ptr[e_lo + j] - (unsigned long long)r0;
+        s_r0[j] = r0 < -0x7FFFFFFFll ? -0x7FFFFFFF : (int)r0;
+        s_r1[j] = r1 > 0x7FFFFFFFll ? 0x7FFFFFFF : (int)r1;
+        if (hash_here) s_ks[j] = rec.z;
+    }
+    __syncthreads();
+
+    // ---- copy: warp w owns bytes [w * 2 KB, (w + 1) * 2 KB) of the tile, 1 KB (32 lanes x 32 bytes) at a time
+    uint8_t *dst_tile = p.out_data + T0;
+    const int sub0 = (int)(warp * (uint32_t)(kG32Vpt * 1024));
+    if ((uint32_t)sub0 < tile_len) {
+        uint32_t j = 0; // the entry that holds byte sub0 = number of entries ending at or before it (ends ascend)
+        for (uint32_t base = 0; base + 1 < ne; base += 32) {
+            const uint32_t i = base + lane;
+            j += __popc(__ballot_sync(0xFFFFFFFFu, i + 1 < ne && s_r1[i] <= sub0));
+        }
+        uint4 A[kG32Vpt], B[kG32Vpt], C[kG32Vpt];
+        uint32_t sh[kG32Vpt];
+        bool pure[kG32Vpt];
+        const uint32_t lanes_le = 0xFFFFFFFFu >> (31 - lane); // bits 0..lane
+#pragma unroll
+        for (int k = 0; k < kG32Vpt; k++) {
+            const int cb = sub0 + k * 1024;
+            const int b0 = cb + (int)lane * 32;
+            // Entries that end inside the chunk, i.e. in (cb, cb + 1024]: at most 32, lane l looks at entry j + l.  An end at
+            // r1 precedes the blocks t = ceil((r1 - cb) / 32) .. 31; distinct entries have distinct t.
+            const uint32_t i = j + lane;
+            const int r1 = i + 1 < ne ? s_r1[i] : 0x7FFFFFFF;
+            const bool ends_here = r1 <= cb + 1024;
+            const uint32_t t = (uint32_t)((ends_here ? r1 : cb + 32) - cb + 31) >> 5; // 1..32 when ends_here
+            const uint32_t ends = __reduce_or_sync(0xFFFFFFFFu, (ends_here && t < 32) ? (1u << t) : 0u);
+            const uint32_t cnt = __popc(ends & lanes_le); // entries ending at or before my block's first byte
+            const uint32_t adv = __popc(__ballot_sync(0xFFFFFFFFu, ends_here));
+            const uint32_t e = j + cnt; // entry that holds byte b0
+            j += adv;                   // entry that holds the next chunk's first byte
+            // Unconditional loads: a block that is not wholly inside entry e (it holds e's end, or lies past the end of the
+            // stream) reads the last 32 bytes of e instead (always valid: entries are >= 32 bytes) and is not stored here.
+            const int r1e = s_r1[e];
+            pure[k] = (uint32_t)b0 + 32 <= tile_len && b0 + 32 <= r1e;
+            const int bl = b0 + 32 <= r1e ? b0 : r1e - 32;
+            const uintptr_t sa = (uintptr_t)(s_adj[e] + (unsigned long long)(long long)bl);
+            sh[k] = (uint32_t)(sa & 15);
+            const uint4 *sv = reinterpret_cast<const uint4 *>(sa - sh[k]);
+            A[k] = __ldg(sv);
+            B[k] = __ldg(sv + 1);
+            C[k] = __ldg(sh[k] ? sv + 2 : sv + 1);
+        }
+#pragma unroll
+        for (int k = 0; k < kG32Vpt; k++) {
+            if (pure[k]) {
+                uint32_t o[8];
+                realign32(A[k], B[k], C[k], sh[k], o);
+                stg256(dst_tile + sub0 + k * 1024 + (int)lane * 32, o);
+            }
+        }
+    }
+
+    // ---- the 32-byte block that holds the last byte of entry j (unless j ends on a block boundary): its two halves
+    for (uint32_t j = tid; j < ne; j += NT) {
+        const int r1 = s_r1[j];
+        if (r1 <= 0 || (r1 & 31) == 0 || r1 > (int)tile_len) continue;
+        const bool has_next = j + 1 < ne;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const uint32_t b0 = ((uint32_t)r1 & ~31u) + 16u * half;
+            if (b0 >= tile_len) continue;     // past the end of the stream
+            const int t = r1 - (int)b0;       // bytes of entry j in this vector: <= 0 none, >= 16 all
+            uint4 o;
+            if (t >= 16) {
+                o = ld16_any((uintptr_t)(s_adj[j] + b0), 16);
+            } else if (t <= 0) {
+                if (!has_next) continue;
+                o = ld16_any((uintptr_t)(s_adj[j + 1] + b0), 16);
+            } else {
+                o = ld16_any((uintptr_t)(s_adj[j] + b0), (uint32_t)t);
+                if (b0 + 16 <= tile_len) { // blend with the head of entry j + 1
+                    const uint4 H = ld16_any((uintptr_t)(s_adj[j + 1] + (unsigned long long)(long long)r1), 16);
+                    const uint4 HU = realign16_sel(make_uint4(0, 0, 0, 0), H, 16 - (uint32_t)t);
+                    const uint32_t wfull = (uint32_t)t >> 2, bits = ((uint32_t)t & 3) * 8;
+                    const uint32_t mmix = bits ? (0xFFFFFFFFu >> (32 - bits)) : 0u;
+                    uint32_t ow[4] = {o.x, o.y, o.z, o.w}, hw[4] = {HU.x, HU.y, HU.z, HU.w};
+#pragma unroll
+                    for (uint32_t q = 0; q < 4; q++) {
+                        const uint32_t mk = q < wfull ? 0xFFFFFFFFu : (q == wfull ? mmix : 0u);
+                        ow[q] = (ow[q] & mk) | (hw[q] & ~mk);
+                    }
+                    o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                } else { // ragged end of the whole stream: never write past out_data_len
+                    const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+                    for (int b = 0; b < t; b++) dst_tile[b0 + b] = (uint8_t)(ow[b >> 2] >> ((b & 3) * 8));
+                    continue;
+                }
+            }
+            reinterpret_cast<uint4 *>(dst_tile)[b0 >> 4] = o;
+        }
+    }
+
+    // ---- bloom (fused epilogue), only when k_extract did not hash: entries whose first byte lies in this tile
+    if (hash_here) {
         for (uint32_t j = tid; j < ne; j += NT) {
             const int r0 = s_r0[j];
             if (r0 < 0 || r0 >= (int)kGatherTileBytes) continue;

@@ -36,7 +36,11 @@ struct RouteParams {
     uint32_t *hist;                   // [n_blocks][n_shards] counts, then (k_route_scan) arrivals of the shard in earlier blocks
     unsigned long long *totals;       // [3 * n_shards + 1]: counts | payload bytes | starts ; [3 n_shards] = first bad record
     uint4 *out_index;                 // [n] routed records, shard-major
+    unsigned long long *hash64;       // [n] arrival order: (murmur3_32(key, kCutSeed) << 32) | murmur3_32(key, 0), or null
+    unsigned long long *out_hash64;   // [n] the same, shard-major (input of k_memtable_cuts)
 };
+
+constexpr uint32_t kCutSeed = 0x9747b28cu; // second murmur seed: the pair is the 64-bit key identity of the memtable cut
 
 __global__ void __launch_bounds__(kRouteThreads) k_route_hash(RouteParams p) {
     __shared__ uint32_t s_cnt[kRouteMaxShards];
@@ -51,7 +55,9 @@ __global__ void __launch_bounds__(kRouteThreads) k_route_hash(RouteParams p) {
         uint32_t owner = 0xFFFFFFFFu;
         if (rec.z >= 8 && (uint64_t)rec.w >= (uint64_t)rec.z + 24 && off <= p.data_len && (uint64_t)rec.w <= p.data_len - off) {
             const uint8_t *key = p.data + off + 8;
-            const uint32_t h = murmur3_32(rec.z - 8, 0u, [key](uint64_t q) { return ld_u64_unaligned_narrow(key + 8 * q); });
+            uint32_t h, h2;
+            murmur3_32_pair(rec.z - 8, 0u, kCutSeed, [key](uint64_t q) { return ld_u64_unaligned_narrow(key + 8 * q); }, &h, &h2);
+            if (p.hash64) p.hash64[i] = ((unsigned long long)h2 << 32) | h;
             const uint32_t *ring = p.ring;
             owner = ring_owner(p.n_shards, h, [ring](uint32_t s) { return __ldg(&ring[s]); });
             atomicAdd(&s_cnt[owner], 1u);
@@ -123,6 +129,89 @@ __global__ void __launch_bounds__(kRouteThreads) k_route_scatter(RouteParams p) 
     const unsigned long long pos = p.totals[2 * p.n_shards + owner] + p.hist[(uint64_t)blockIdx.x * p.n_shards + owner] +
                                    s_warp[warp][owner] + before;
     p.out_index[pos] = __ldg(&p.index[i]);
+    if (p.out_hash64) p.out_hash64[pos] = p.hash64[i];
+}
+
+// ------------------------------------------------------------------------------------
+// Memtable-full trigger on the device (a11: lsm_tree.rs:747-765, the flush starts right after the insert that makes the
+// tree hold `capacity` keys).  Input: one shard's stream of 64-bit key identities in arrival order; output: where every
+// memtable ends.  One CTA per stream walks it 1024 arrivals at a time with a hash SET of the current memtable's keys in
+// shared memory: insert (CAS), decide which thread of the chunk saw each new key FIRST (atomicMin of the thread index),
+// prefix-sum those flags, and cut at the arrival that brings the count to `capacity`.
+//
+// The identity is a pair of murmur3 hashes, not the key bytes: two different keys colliding on all 64 bits would make a
+// memtable one key too large.  The flush reports every memtable's exact distinct count, so callers verify
+// items == capacity for every memtable but the last of a stream and fall back to dbeel_memtable_cut (exact, host) if not.
+
+constexpr uint32_t kCutSlots = 16384; // shared memory: 128 KB of identities + 64 KB of first-seen thread ids
+constexpr uint32_t kCutMaxCapacity = 9216; // load factor <= (capacity + 1024) / slots = 0.625
+
+struct CutParams {
+    const unsigned long long *hash64; // shard-major
+    const unsigned long long *starts; // [n_streams + 1] device
+    uint32_t n_streams, capacity, max_cuts;
+    const uint32_t *cut_base;         // [n_streams] device: first slot of stream s in `cuts`
+    uint32_t *cuts;                   // arrivals of the stream consumed up to and including each FULL memtable
+    uint32_t *n_cuts;                 // [n_streams]
+};
+
+__global__ void __launch_bounds__(1024) k_memtable_cuts(CutParams p) {
+    extern __shared__ __align__(128) uint8_t s_raw[];
+    unsigned long long *tab = reinterpret_cast<unsigned long long *>(s_raw);
+    uint32_t *first = reinterpret_cast<uint32_t *>(s_raw + 8ull * kCutSlots);
+    __shared__ unsigned long long s_b[32];
+    __shared__ uint32_t s_c[32];
+    __shared__ uint32_t s_cut;
+    const uint32_t tid = threadIdx.x, stream = blockIdx.x;
+    const unsigned long long base = p.starts[stream];
+    const uint32_t n = (uint32_t)(p.starts[stream + 1] - base);
+    const unsigned long long *h64 = p.hash64 + base;
+    uint32_t *cuts = p.cuts + p.cut_base[stream];
+    for (uint32_t k = tid; k < kCutSlots; k += 1024) { tab[k] = 0; first[k] = 0; }
+    __syncthreads();
+    uint32_t pos = 0, count = 0, ncut = 0;
+    while (pos < n) {
+        const uint32_t i = pos + tid;
+        const bool act = i < n;
+        unsigned long long h = act ? h64[i] : 0;
+        if (act && h == 0) h = 1; // 0 marks an empty slot
+        uint32_t slot = 0;
+        bool won = false;
+        if (act) {
+            slot = (uint32_t)(h ^ (h >> 29)) & (kCutSlots - 1);
+            while (true) {
+                const unsigned long long cur = atomicCAS(&tab[slot], 0ull, h);
+                if (cur == 0) { won = true; break; }
+                if (cur == h) break;
+                slot = (slot + 1) & (kCutSlots - 1);
+            }
+        }
+        if (tid == 0) s_cut = 0xFFFFFFFFu;
+        if (won) first[slot] = 0xFFFFFFFFu; // new in this chunk: someone's thread id goes here
+        __syncthreads();
+        if (act && first[slot] != 0) atomicMin(&first[slot], tid + 1);
+        __syncthreads();
+        const uint32_t flag = (act && first[slot] == tid + 1) ? 1u : 0u;
+        unsigned long long vb = 0, tb;
+        uint32_t vc = flag, tc;
+        block_excl_scan_1024(vb, vc, s_b, s_c, &tb, &tc);
+        if (flag && count + vc + 1 == p.capacity) s_cut = tid; // the insert that fills the tree
+        __syncthreads();
+        const uint32_t cut = s_cut;
+        if (cut != 0xFFFFFFFFu) {
+            pos += cut + 1;
+            if (tid == 0 && ncut < p.max_cuts) cuts[ncut] = pos;
+            ncut++;
+            count = 0;
+            for (uint32_t k = tid; k < kCutSlots; k += 1024) { tab[k] = 0; first[k] = 0; }
+        } else {
+            if (won) first[slot] = 0; // the key is old news for the chunks that follow
+            count += tc;
+            pos += 1024;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) p.n_cuts[stream] = ncut;
 }
 
 } // namespace dbeel

@@ -136,6 +136,15 @@ typedef struct dbeel_engine dbeel_engine;
 int dbeel_engine_create(int device, dbeel_engine **out);
 void dbeel_engine_destroy(dbeel_engine *e);
 
+/* Host placement.  dbeel pins one executor thread per core (src/main.rs:51-60); with one GPU per shard that thread and
+ * the pinned buffers it stages through should sit on the GPU's NUMA node, or every byte crosses the socket interconnect on
+ * its way to the PCIe root complex.  dbeel_bind_to_gpu moves the CALLING thread onto the CPUs of `device`'s NUMA node
+ * (within the process's allowed set) and prefers that node for its future page allocations; call it before
+ * dbeel_host_alloc / before touching the buffers.  numa_node / n_cpus (nullable) report what was applied (-1 / 0 when the
+ * machine exposes no NUMA topology: not an error). */
+int dbeel_gpu_numa_node(int device);
+int dbeel_bind_to_gpu(int device, int *numa_node, int *n_cpus);
+
 /* Upper bounds for the output buffers of a compaction of `runs` (host-side arithmetic only):
  * data_cap = sum(data_len), index_cap = 16 * sum(index_len/16), bloom_cap = size of the
  * .bloom file or 0 when sum(data_len) <= bloom_min_size. */
@@ -193,10 +202,24 @@ int dbeel_shard_ring(const char *node_name, uint32_t n_shards, uint32_t *ring_ha
  * position: position p's arrivals, in arrival order, are records [sum(counts[0..p)), +counts[p]).  The records are
  * unchanged -- they still point into batch->data -- so a shard's stream is an arrival batch with sparse offsets (below).
  * shard_of (device, n u32, or NULL) receives every arrival's ring position; counts / payload_bytes (host, n_shards each;
- * payload_bytes may be NULL) the arrivals and the sum of full_size per position. */
+ * payload_bytes may be NULL) the arrivals and the sum of full_size per position.
+ * out_key_hash64 (device, n u64, or NULL): a 64-bit identity of every arrival's key, in the same shard-major order as
+ * out_index -- the input of dbeel_memtable_cuts_device. */
 int dbeel_route_device(dbeel_engine *e, const dbeel_run *batch, const uint32_t *ring_hashes /* host, ascending */,
-                       uint32_t n_shards, void *out_index, uint64_t out_index_cap, uint32_t *shard_of, uint64_t *counts,
-                       uint64_t *payload_bytes);
+                       uint32_t n_shards, void *out_index, uint64_t out_index_cap, uint32_t *shard_of, void *out_key_hash64,
+                       uint64_t *counts, uint64_t *payload_bytes);
+
+/* The memtable-full trigger (lsm_tree.rs:747-765, 600-603: a flush starts right after the insert that makes the tree hold
+ * `capacity` keys) for whole streams at once, on the device.  Stream s = key identities [stream_starts[s],
+ * stream_starts[s+1]) of key_hash64 (arrival order).  cuts[cut_starts[s] .. cut_starts[s+1]) receive, for every FULL memtable
+ * of stream s, the number of the stream's arrivals consumed up to and including it; what follows the last cut is the
+ * memtable still filling.  capacity <= 9216 (shared-memory set); max_cuts_total >= sum(len(s) / capacity).
+ * The identities are 64-bit hashes: a collision inside one memtable would cut one key late.  The flush reports every
+ * SSTable's exact entry count -- a full memtable must yield exactly `capacity` -- so callers check that and fall back to the
+ * exact host function dbeel_memtable_cut (dbeel_tree.h) on a mismatch. */
+int dbeel_memtable_cuts_device(dbeel_engine *e, const void *key_hash64, const uint64_t *stream_starts /* host */,
+                               uint32_t n_streams, uint32_t capacity, uint32_t *cuts /* host */, uint32_t *cut_starts /* host */,
+                               uint32_t max_cuts_total);
 
 /* dbeel_flush_many_device for batches whose index records do not abut in .data (slices of a routed stream: every batch's
  * `data` is the shared arrival buffer, `index` a slice of dbeel_route_device's out_index).  payload_bound >= the sum of

@@ -139,6 +139,44 @@ def test_route_then_sparse_flush_equals_flushing_each_shards_stream(engine):
         assert r["items"] == en
         assert np.array_equal(od[r["data_off"]:r["data_off"] + r["data_len"]].cpu().numpy(), ed)
         assert np.array_equal(oi[r["index_off"]:r["index_off"] + r["index_len"]].cpu().numpy(), ei)
+    written = sum(r["data_len"] for r in rows)  # < bound: arrivals of one key inside a memtable collapse
     with pytest.raises(capi.DbeelError) as ei_:
-        engine.flush_many_sparse_device(batches, bound - 1000, (od.data_ptr(), bound, oi.data_ptr(), ix.numel()))
+        engine.flush_many_sparse_device(batches, written - 1, (od.data_ptr(), bound, oi.data_ptr(), ix.numel()))
     assert ei_.value.code == 2  # DBEEL_ERR_CAPACITY: the bound was too low, nothing past it was written
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,cap,n_ids", [(40_000, 512, 3000), (100_000, 8192, 60_000), (30_000, 1, 50), (5_000, 9000, 100_000),
+                                         (70_000, 1000, 1001)])
+def test_device_memtable_cuts_match_the_host_trigger(engine, n, cap, n_ids):
+    """dbeel_memtable_cuts_device (64-bit key identities, one CTA per stream) against dbeel_memtable_cut (exact, key bytes)
+    on every shard's stream: lsm_tree.rs:747-765 -- the flush starts right after the insert that fills the tree."""
+    import torch
+    from dbeel_b200 import storage_engine as se
+    batch = W.make_arrival_batch(n_writes=n, n_ids=n_ids, doc_bytes=40, seed=cap)
+    ring, _ = oracle.shard_ring(8)
+    shard, _ = oracle.route(batch, ring)
+    dev = torch.device("cuda:0")
+    d = torch.from_numpy(np.ascontiguousarray(batch[0])).to(dev)
+    ix = torch.from_numpy(np.ascontiguousarray(batch[1])).to(dev)
+    routed = torch.empty(ix.numel() + 16, dtype=torch.uint8, device=dev)
+    h64 = torch.empty(n, dtype=torch.int64, device=dev)
+    counts, _ = engine.route_device((d.data_ptr(), d.numel(), ix.data_ptr(), ix.numel()), ring, routed.data_ptr(), ix.numel(), 0,
+                                    h64.data_ptr())
+    starts = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint64)
+    got = engine.memtable_cuts_device(h64.data_ptr(), starts, cap)
+    recs = batch[1].reshape(-1, 16)
+    for s in range(8):
+        stream = (batch[0], np.ascontiguousarray(recs[shard == s]).ravel())
+        exp, pos, cnt = [], 0, int(counts[s])
+        while pos < cnt:
+            m = se.memtable_cut(stream, pos, cap)
+            pos += m
+            exp.append(pos)
+        # the host loop also reports the memtable that is still filling when the stream ends; the device reports full ones
+        full = exp if (exp and _distinct(stream, exp[-2] if len(exp) > 1 else 0, exp[-1]) == cap) else exp[:-1]
+        assert list(got[s]) == full, (s, list(got[s])[:5], full[:5])
+
+
+def _distinct(stream, lo, hi):
+    return len({k for k, _, _ in sstable.parse_run(stream[0], stream[1][16 * lo:16 * hi])})
