@@ -239,10 +239,10 @@ def other_configs(eng, torch, dev, peak):
         f"parity {out['cfg3']['parity_vs_oracle']} ({time.time() - t:.0f}s)")
     del runs, got, exp
     try:  # configs[4], one shard's stream (the 8-GPU run is --workload cfg5)
-        from dbeel_b200 import cfg5
-        out["cfg5_one_shard"] = cfg5.run_one_shard(eng, torch, dev, n_writes=1_500_000)
+        import bench_cfg5
+        out["cfg5_scaled"] = bench_cfg5.run_one_shard(eng, torch, dev, n_writes=1_500_000)
     except Exception as ex:  # pragma: no cover
-        out["cfg5_one_shard"] = {"error": repr(ex)}
+        out["cfg5_scaled"] = {"error": repr(ex)}
     return out
 
 
@@ -271,8 +271,8 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     if args.workload == "cfg5":
-        from dbeel_b200 import cfg5
-        return cfg5.bench(args, torch, dist, dev, rank, world, local, ClockSampler, hbm_peak, METRIC, UNIT, log)
+        import bench_cfg5
+        return bench_cfg5.bench(args, torch, dist, dev, rank, world, local, ClockSampler, hbm_peak, METRIC, UNIT, log)
     # job hand-off (NCCL broadcast when N > 1): rank 0 owns the table; shard i's compaction runs on GPU i mod N
     n_jobs = N_JOBS if args.workload == "cfg2" else 1
     table = [sj.ShardJob(i, 40 + i, 8, 1_000_000, 256, False) for i in range(n_jobs)] if rank == 0 else None
@@ -293,13 +293,17 @@ def run_gpu(args):
     bounds = [capi.compact_bound([(d.size, i.size) for d, i in runs], opts) for runs in jobs_runs]
     dc, ic, bc = (max(b[k] for b in bounds) for k in range(3)) if bounds else (0, 0, 0)
 
-    # device-resident inputs of every job of this rank; ONE output SSTable buffer set, reused job after job
+    # Independent shard compactions overlap on one GPU: with >= 2 jobs per GPU two engines (two streams) take them
+    # alternately, so one job's HBM-bound payload gather runs next to the other's latency-bound metadata stages.
+    n_eng = 2 if (len(mine) >= 2 and not args.no_overlap) else 1
+    engs = [eng] + [capi.Engine(local) for _ in range(n_eng - 1)]
+    # device-resident inputs of every job of this rank; one output SSTable buffer set per engine, reused job after job
     t_jobs = [[(torch.from_numpy(d).to(dev), torch.from_numpy(i).to(dev)) for d, i in runs] for runs in jobs_runs]
-    od = torch.empty(dc + 16, dtype=torch.uint8, device=dev)
-    oi = torch.empty(ic + 16, dtype=torch.uint8, device=dev)
-    ob = torch.empty(bc + 16, dtype=torch.uint8, device=dev)
+    outs = [(torch.empty(dc + 64, dtype=torch.uint8, device=dev), torch.empty(ic + 64, dtype=torch.uint8, device=dev),
+             torch.empty(bc + 64, dtype=torch.uint8, device=dev)) for _ in engs]
     d_jobs = [[(d.data_ptr(), d.numel(), i.data_ptr(), i.numel()) for d, i in t_runs] for t_runs in t_jobs]
-    d_out = (od.data_ptr(), dc, oi.data_ptr(), ic, ob.data_ptr(), bc)
+    d_outs = [(od.data_ptr(), dc, oi.data_ptr(), ic, ob.data_ptr(), bc) for od, oi, ob in outs]
+    ext = [torch.cuda.ExternalStream(e_.stream_ptr(), device=dev) for e_ in engs]
     torch.cuda.synchronize()
 
     def barrier():
@@ -307,16 +311,51 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    acc = {"ms_total": 0.0, "ms_extract": 0.0, "ms_merge": 0.0, "ms_resolve": 0.0, "ms_gather": 0.0, "kernel_launches": 0,
-           "gather_bytes": 0, "input_bytes": 0, "output_bytes": 0}
+    KEYS = ("ms_total", "ms_extract", "ms_merge", "ms_resolve", "ms_gather", "kernel_launches", "gather_bytes", "input_bytes", "output_bytes")
+    solo = {k: 0.0 for k in KEYS}
 
-    def step(record: bool):
+    # ---- (1) every job alone on the GPU: the per-job figures (ms_per_job, stage_ms, roofline of the gather kernel)
+    solo_steps = max(1, min(3, args.steps))
+    for rep in range(2 + solo_steps):
         for d_runs in d_jobs:
-            eng.compact_device(d_runs, d_out, opts)
-            if record:
+            eng.compact_device(d_runs, d_outs[0], opts)
+            if rep >= 2:
                 st = eng.stats()
-                for k in acc:
-                    acc[k] += st[k]
+                for k in KEYS:
+                    solo[k] += st[k]
+    solo_runs = solo_steps * len(d_jobs)
+
+    # ---- (2) the timed region: K steps, each one pass over this rank's jobs, two in flight when there are two engines
+    acc = {"kernel_launches": 0}
+    lock = threading.Lock()
+
+    def worker(ei: int, record: bool):
+        n_l = 0
+        for j in range(ei, len(d_jobs), n_eng):
+            engs[ei].compact_device(d_jobs[j], d_outs[ei], opts)
+            if record:
+                n_l += engs[ei].stats()["kernel_launches"]
+        if record:
+            with lock:
+                acc["kernel_launches"] += n_l
+
+    def step(record: bool) -> float:
+        ev0 = [torch.cuda.Event(enable_timing=True) for _ in engs]
+        ev1 = [torch.cuda.Event(enable_timing=True) for _ in engs]
+        for k in range(n_eng):
+            ev0[k].record(ext[k])
+        if n_eng == 1:
+            worker(0, record)
+        else:
+            ths = [threading.Thread(target=worker, args=(k, record)) for k in range(n_eng)]
+            for th in ths:
+                th.start()
+            for th in ths:
+                th.join()
+        for k in range(n_eng):
+            ev1[k].record(ext[k])
+        torch.cuda.synchronize()
+        return max(a.elapsed_time(b) for a in ev0 for b in ev1)  # first start .. last end over the engines' streams
 
     for _ in range(max(3, args.warmup)):
         step(False)
@@ -324,29 +363,31 @@ def run_gpu(args):
     sampler.start()
     barrier()
     t0 = time.perf_counter()
+    dev_ms = 0.0
     for _ in range(args.steps):
-        step(True)
+        dev_ms += step(True)
     barrier()
     t1 = time.perf_counter()
     sampler.stop()
     wall_ms = (t1 - t0) * 1e3
     clocks = sampler.summary(t0, t1)
 
-    # max over ranks of the device time (CUDA events on the engine's stream, summed over the rank's jobs and the K steps)
-    tm = torch.tensor([acc["ms_total"], wall_ms], dtype=torch.float64, device=dev)
-    sums = torch.tensor([float(in_bytes), float(acc["kernel_launches"]), acc["ms_total"], acc["ms_extract"], acc["ms_merge"],
-                         acc["ms_resolve"], acc["ms_gather"], float(acc["gather_bytes"]), float(acc["input_bytes"]),
-                         float(acc["output_bytes"]), float(len(mine))], dtype=torch.float64, device=dev)
+    # max over ranks of the device time (CUDA events on the engines' streams, summed over the K steps)
+    tm = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
+    sums = torch.tensor([float(in_bytes), float(acc["kernel_launches"]), solo["ms_total"], solo["ms_extract"], solo["ms_merge"],
+                         solo["ms_resolve"], solo["ms_gather"], float(solo["gather_bytes"]), float(solo["input_bytes"]),
+                         float(solo["output_bytes"]), float(len(mine)), float(solo_runs)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
     dev_ms_max, wall_ms_max = (float(x) for x in tm.tolist())
-    (total_in, launches, s_total, s_extract, s_merge, s_resolve, s_gather, s_gbytes, s_in, s_out, jobs_all) = (float(x) for x in sums.tolist())
+    (total_in, launches, s_total, s_extract, s_merge, s_resolve, s_gather, s_gbytes, s_in, s_out, jobs_all, job_runs) = (float(x) for x in sums.tolist())
     value = total_in * args.steps / 1e6 / (dev_ms_max / 1e3)
-    job_runs = jobs_all * args.steps  # compactions executed inside the timed region, all ranks
 
     # ---- end to end through the host entry point (pinned host buffers, H2D + D2H timed)
-    del t_jobs, d_jobs, od, oi, ob
+    del t_jobs, d_jobs, outs, d_outs, ext
+    for e_ in engs[1:]:
+        e_.close()
     torch.cuda.empty_cache()
     e2e_steps = max(2, min(3 if world == 1 else 5, args.steps))
     t = time.time()
@@ -444,7 +485,9 @@ def run_gpu(args):
                      "output_bytes_per_job": out_bytes_job,
                      "l2_policy": "inputs_larger_than_l2 (2.55 GB per job vs 126 MB L2)",
                      "parallelism": f"{int(jobs_all)} independent shard compactions over {world} GPU(s), shard i on GPU i mod N, no data-path collective",
-                     "timing": "sum over the rank's jobs and the K steps of CUDA-event time on the engine stream (first to last kernel), max over ranks",
+                     "engines_per_gpu": n_eng,
+                     "timing": "per step: CUDA events on the engines' streams, first start to last end of the rank's jobs (two jobs in flight "
+                               "when a GPU has two or more); sum over the K steps, max over ranks.  ms_per_job / stage_ms / roofline: every job alone",
                      "host_placement": {"numa_node": numa_node, "cpus": numa_cpus}})
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -457,7 +500,9 @@ def run_gpu(args):
                      "ms_resolve": round(s_resolve / job_runs, 4), "ms_gather": round(g_ms, 4)},
         "pipeline_roofline": {"algo_bytes": int(algo_job), "achieved_gbs": round(algo_job / 1e9 / (ms_job / 1e3), 1),
                               "frac": round(algo_job / 1e9 / (ms_job / 1e3) / peak, 4),
-                              "read_only_frac": round(s_in / job_runs / 1e9 / (ms_job / 1e3) / peak, 4), "per": "job (configs[1] shape)"},
+                              "read_only_frac": round(s_in / job_runs / 1e9 / (ms_job / 1e3) / peak, 4),
+                              "per": "one job (configs[1] shape) alone on the GPU, first to last kernel",
+                              "frac_in_timed_region": round(algo_job * jobs_all * args.steps / 1e9 / (dev_ms_max / 1e3) / peak / world, 4)},
         "roofline": {"kernel": GATHER_KERNEL, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
                      "algo_bytes_per_launch": int(gbytes), "ms_per_launch": round(g_ms, 4), "peak_source": peak_src},
@@ -563,6 +608,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="dbeel_b200", choices=["dbeel_b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the oracle legs: cpu_baseline, byte parity, other_configs (profiling runs)")
+    ap.add_argument("--no-overlap", action="store_true", help="one engine per GPU: the rank's jobs strictly one after the other")
     ap.add_argument("--no-others", action="store_true", help="skip the other_configs block (cfg1 / cfg3 / cfg5-shard evidence)")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg5"],
                     help="cfg2 (default): BASELINE.json's headline, 8 shard jobs of configs[1]'s shape; cfg5: configs[4]")

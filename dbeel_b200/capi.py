@@ -39,7 +39,7 @@ EXPORTS = ["dbeel_abi_version", "dbeel_engine_create", "dbeel_engine_destroy", "
            "dbeel_bloom_bitmap_bytes", "dbeel_bloom_k_num", "dbeel_bloom_file_size", "dbeel_host_alloc",
            "dbeel_host_free", "dbeel_last_stats", "dbeel_last_error", "dbeel_strerror",
            "dbeel_murmur3_32", "dbeel_ring_owner", "dbeel_shard_ring", "dbeel_route_device", "dbeel_flush_many_sparse_device",
-           "dbeel_gpu_numa_node", "dbeel_bind_to_gpu", "dbeel_memtable_cuts_device"]
+           "dbeel_gpu_numa_node", "dbeel_bind_to_gpu", "dbeel_memtable_cuts_device", "dbeel_engine_stream"]
 
 
 class Run(C.Structure):
@@ -132,6 +132,8 @@ def lib():
         L.dbeel_abi_version.restype = C.c_int
         L.dbeel_engine_create.restype = C.c_int
         L.dbeel_engine_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.dbeel_engine_stream.restype = C.c_void_p
+        L.dbeel_engine_stream.argtypes = [C.c_void_p]
         L.dbeel_engine_destroy.restype = None
         L.dbeel_engine_destroy.argtypes = [C.c_void_p]
         L.dbeel_compact_bound.restype = C.c_int
@@ -282,6 +284,10 @@ class Engine:
     def _check(self, rc: int, what: str):
         if rc:
             raise DbeelError(rc, f"{what}: {lib().dbeel_last_error(self._h).decode()}")
+
+    def stream_ptr(self) -> int:
+        """The engine's cudaStream_t as an integer (torch.cuda.ExternalStream(ptr) wraps it)."""
+        return int(lib().dbeel_engine_stream(self._h) or 0)
 
     def stats(self) -> dict:
         s = Stats()

@@ -74,8 +74,12 @@ struct dbeel_engine {
     int sm_count = 148;
     int merge_variant = 1;      // DBEEL_MERGE: 0 = one CTA per tile with plain loads, 1 = persistent TMA (default)
     int narrow_loads = 1;       // DBEEL_NARROW: .L2::64B loads for random accesses in extract / resolve (A/B switch)
-    int gather_variant = 1;     // DBEEL_GATHER: 0 = 16 bytes per lane (k_gather), 1 = 32 bytes per lane + 256-bit stores (k_gather32)
-    int bloom_in_extract = 1;   // DBEEL_BLOOM_EXTRACT: 1 = k_extract hashes, k_resolve sets the bits; 0 = the gather's fused epilogue
+    int gather_variant = 1;     // DBEEL_GATHER: 0 = 16 bytes per lane (k_gather), 1 = 32 bytes per lane + 256-bit stores (k_gather32),
+                                //               2 = 1 with the payload staged into shared memory by TMA bulk copies (k_gather_tma)
+    int bloom_side = 1;         // DBEEL_BLOOM_SIDE: 1 = k_bloom_res on a second stream next to the gather, 0 = the gather's fused epilogue
+    cudaStream_t s_side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int bloom_in_extract = 0;   // DBEEL_BLOOM_EXTRACT: 1 = k_extract hashes, k_resolve sets the bits (measured slower: DESIGN.md); 0 = the gather's fused epilogue
 };
 
 namespace {
@@ -192,8 +196,9 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     for (uint32_t r = 0; r < n_runs; r++) {
         if ((runs[r].data_len && !runs[r].data) || (runs[r].index_len >= 16 && !runs[r].index))
             return fail(e, DBEEL_ERR_INVALID_ARG, "null run buffer");
-        if ((((uintptr_t)runs[r].data & 15) && !(extra && extra->off_base)) || ((uintptr_t)runs[r].index & 15))
-            return fail(e, DBEEL_ERR_INVALID_ARG, "device run buffers must be 16-byte aligned");
+        // .data may start anywhere (every access realigns; tables left by dbeel_flush_many / dbeel_compact_many are slices of
+        // one output stream); .index is read as 16-byte records
+        if ((uintptr_t)runs[r].index & 15) return fail(e, DBEEL_ERR_INVALID_ARG, "device .index buffers must be 16-byte aligned");
     }
     if (((uintptr_t)out->data | (uintptr_t)out->index | (uintptr_t)out->bloom) & 15)
         return fail(e, DBEEL_ERR_INVALID_ARG, "device output buffers must be 16-byte aligned");
@@ -408,7 +413,7 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
         k_flush_prefix_init<<<1, 1, 0, s>>>(p);
         k_flush_prefix<<<g256, 256, 0, s>>>(p);
         launch_extract(gext, 0);
-        k_plan<<<1, 1, 0, s>>>(p);
+        k_plan<<<1, 1024, 0, s>>>(p);
         k_block_sort<<<p.nseg[0], kMergeThreads, 0, s>>>(p);
     } else {
         k_common_prefix<<<1, 32, 0, s>>>(p, 0);
@@ -422,7 +427,7 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
         }
         k_common_prefix<<<1, 32, 0, s>>>(p, 1); // both no-ops unless a run was truncated
         launch_extract(gext < 592 ? gext : 592, 1);
-        k_plan<<<1, 1, 0, s>>>(p);
+        k_plan<<<1, 1024, 0, s>>>(p);
     }
     launches += 5;
     if (!flush && (o->flags & DBEEL_FLAG_VERIFY_SORTED)) {
@@ -463,8 +468,17 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
         launches++;
     }
     uint4 *res = reinterpret_cast<uint4 *>(dst); // the ping-pong buffer that does not hold the merged order
+    const bool side_bloom = e->bloom_side && !flush && !jobs && !hash_early && p.bloom.words != nullptr;
+    p.bloom_elsewhere = side_bloom ? 1 : 0;
     if (e->narrow_loads) k_resolve<true><<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, src, res);
     else k_resolve<false><<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, src, res);
+    if (side_bloom) { // fork: the filter is filled on the second stream while this one scans, emits and copies the payload
+        CU(cudaEventRecord(e->ev_fork, s));
+        CU(cudaStreamWaitEvent(e->s_side, e->ev_fork, 0));
+        k_bloom_res<<<g256, 256, 0, e->s_side>>>(p, res);
+        CU(cudaEventRecord(e->ev_join, e->s_side));
+        launches++;
+    }
     k_scan_tiles<<<(uint32_t)res_chunks, 1024, 0, s>>>(p);
     k_scan_chunks<<<1, 1024, 0, s>>>(p);
     k_emit<<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, res);
@@ -477,8 +491,16 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
 
     // ---- K5: gather + bloom (fused epilogue)
     if (gather_tiles) {
-        if (e->gather_variant == 1 && ((uintptr_t)out->data & 31) == 0) k_gather32<<<(uint32_t)gather_tiles, kGatherThreads, 0, s>>>(p);
-        else k_gather<<<(uint32_t)gather_tiles, kGatherThreads, 0, s>>>(p);
+        const bool al32 = ((uintptr_t)out->data & 31) == 0; // 256-bit stores
+        if (e->gather_variant == 2 && al32) { // persistent, payload staged through shared memory by the bulk-copy engine
+            uint64_t grid = (uint64_t)e->sm_count * DBEEL_GT_CTAS;
+            if (grid > gather_tiles) grid = gather_tiles;
+            k_gather_tma<<<(uint32_t)grid, kGtThreads, kGtSmem, s>>>(p);
+        } else if (e->gather_variant >= 1 && al32) {
+            k_gather32<<<(uint32_t)gather_tiles, kGatherThreads, 0, s>>>(p);
+        } else {
+            k_gather<<<(uint32_t)gather_tiles, kGatherThreads, 0, s>>>(p);
+        }
     }
     launches++;
     if (jobs) { // per-job filters: their own pass over the output entries
@@ -489,6 +511,7 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
         k_rebase_index<<<g256, 256, 0, s>>>(p);
         launches++;
     }
+    if (side_bloom) CU(cudaStreamWaitEvent(s, e->ev_join, 0)); // join: the job ends when both streams are done
     CU(cudaEventRecord(e->ev[EV_GATHER], s));
     CU(cudaGetLastError());
 
@@ -1526,19 +1549,29 @@ int dbeel_engine_create(int device, dbeel_engine **out) {
     if (const char *v = getenv("DBEEL_PARTITION_KB")) e->partition_bytes = (uint64_t)(atoi(v) > 0 ? atoi(v) : 1) << 10;
     if (const char *v = getenv("DBEEL_PARTITION_TAPER")) e->partition_taper = atoi(v) != 0;
     if (const char *v = getenv("DBEEL_PARTITION_MB")) e->partition_bytes = (uint64_t)(atoi(v) > 0 ? atoi(v) : 128) << 20;
-    if (cudaFuncSetAttribute(k_merge_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kMergeBufRecs * sizeof(Rec))) != cudaSuccess) {
+    if (cudaFuncSetAttribute(k_merge_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kMergeBufRecs * sizeof(Rec))) != cudaSuccess ||
+        cudaFuncSetAttribute(k_gather_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGtSmem) != cudaSuccess) {
         dbeel_engine_destroy(e);
         return DBEEL_ERR_CUDA;
     }
     if (const char *v = getenv("DBEEL_NARROW")) e->narrow_loads = atoi(v);
     if (const char *v = getenv("DBEEL_GATHER")) e->gather_variant = atoi(v);
     if (const char *v = getenv("DBEEL_BLOOM_EXTRACT")) e->bloom_in_extract = atoi(v);
+    if (const char *v = getenv("DBEEL_BLOOM_SIDE")) e->bloom_side = atoi(v);
+    if (cudaStreamCreateWithFlags(&e->s_side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        dbeel_engine_destroy(e);
+        return DBEEL_ERR_CUDA;
+    }
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return DBEEL_ERR_CUDA; }
     for (int i = 0; i < EV_COUNT; i++)
         if (cudaEventCreate(&e->ev[i]) != cudaSuccess) { dbeel_engine_destroy(e); return DBEEL_ERR_CUDA; }
     *out = e;
     return DBEEL_OK;
 }
+
+void *dbeel_engine_stream(dbeel_engine *e) { return e ? static_cast<void *>(e->stream) : nullptr; }
 
 void dbeel_engine_destroy(dbeel_engine *e) {
     if (!e) return;
@@ -1560,6 +1593,9 @@ void dbeel_engine_destroy(dbeel_engine *e) {
         if (e->ev_comp[i]) cudaEventDestroy(e->ev_comp[i]);
         if (e->ev_d2h[i]) cudaEventDestroy(e->ev_d2h[i]);
     }
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
+    if (e->s_side) cudaStreamDestroy(e->s_side);
     if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
     if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
     if (e->pin) cudaFreeHost(e->pin);

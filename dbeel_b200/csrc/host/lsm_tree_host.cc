@@ -7,7 +7,9 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <filesystem>
+#include <thread>
 #include <map>
 #include <string>
 #include <string_view>
@@ -92,6 +94,8 @@ struct dbeel_tree {
     std::vector<SSTable> sstables; // ascending by index (lsm_tree.rs:1136)
     uint64_t write_sstable_index = 0;
     std::string err;
+    dbeel_page_sink page_sink = nullptr; // EntryWriter's page-cache write-through (entry_writer.rs:94-156), if the caller wants it
+    void *page_ctx = nullptr;
 };
 
 namespace {
@@ -101,6 +105,44 @@ int io_fail(dbeel_tree *t, const std::string &what) {
     return DBEEL_ERR_IO;
 }
 
+// File <-> pinned memory in 32 MiB pieces spread over a few threads (pread / pwrite): one thread moves a RAM-resident
+// file at memcpy speed, which is a fraction of what the PCIe link behind the pinned buffer takes (N3: the storage edge).
+constexpr uint64_t kIoChunk = 32ull << 20;
+
+int io_threads() {
+    static const int n = [] {
+        if (const char *v = getenv("DBEEL_IO_THREADS")) return std::max(1, atoi(v));
+        const unsigned hw = std::thread::hardware_concurrency();
+        return (int)std::min(8u, std::max(1u, hw / 2));
+    }();
+    return n;
+}
+
+// moves [0, len) between fd and mem; returns 0 or an errno
+int move_chunks(int fd, uint8_t *mem, uint64_t len, bool reading) {
+    const uint64_t n_chunks = (len + kIoChunk - 1) / kIoChunk;
+    std::atomic<uint64_t> next{0};
+    std::atomic<int> err{0};
+    auto work = [&]() {
+        for (uint64_t c = next.fetch_add(1); c < n_chunks && !err.load(); c = next.fetch_add(1)) {
+            uint64_t pos = c * kIoChunk;
+            const uint64_t end = std::min(len, pos + kIoChunk);
+            while (pos < end) {
+                const ssize_t r = reading ? pread(fd, mem + pos, end - pos, (off_t)pos) : pwrite(fd, mem + pos, end - pos, (off_t)pos);
+                if (r < 0 && errno == EINTR) continue;
+                if (r <= 0) { err.store(r < 0 ? errno : EIO); return; }
+                pos += (uint64_t)r;
+            }
+        }
+    };
+    const int nt = (int)std::min<uint64_t>((uint64_t)io_threads(), n_chunks);
+    std::vector<std::thread> pool;
+    for (int i = 1; i < nt; i++) pool.emplace_back(work);
+    work();
+    for (auto &th : pool) th.join();
+    return err.load();
+}
+
 int read_file(dbeel_tree *t, const std::string &path, PinnedBuf *out) {
     int fd = open(path.c_str(), O_RDONLY);
     if (fd < 0) return io_fail(t, "open " + path);
@@ -108,14 +150,9 @@ int read_file(dbeel_tree *t, const std::string &path, PinnedBuf *out) {
     if (fstat(fd, &st) != 0) { close(fd); return io_fail(t, "fstat " + path); }
     PinnedBuf buf((uint64_t)st.st_size);
     if (!buf.p) { close(fd); t->err = "dbeel_host_alloc failed"; return DBEEL_ERR_NOMEM; }
-    uint64_t got = 0;
-    while (got < buf.len) {
-        ssize_t r = read(fd, buf.p + got, buf.len - got);
-        if (r < 0 && errno == EINTR) continue;
-        if (r <= 0) { close(fd); return io_fail(t, "read " + path); }
-        got += (uint64_t)r;
-    }
+    const int e = move_chunks(fd, buf.p, buf.len, true);
     close(fd);
+    if (e) { errno = e; return io_fail(t, "read " + path); }
     *out = std::move(buf);
     return DBEEL_OK;
 }
@@ -123,13 +160,8 @@ int read_file(dbeel_tree *t, const std::string &path, PinnedBuf *out) {
 int write_file(dbeel_tree *t, const std::string &path, const void *data, uint64_t len) {
     int fd = open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
     if (fd < 0) return io_fail(t, "create " + path);
-    uint64_t put = 0;
-    while (put < len) {
-        ssize_t w = write(fd, static_cast<const uint8_t *>(data) + put, len - put);
-        if (w < 0 && errno == EINTR) continue;
-        if (w <= 0) { close(fd); return io_fail(t, "write " + path); }
-        put += (uint64_t)w;
-    }
+    const int e = move_chunks(fd, const_cast<uint8_t *>(static_cast<const uint8_t *>(data)), len, false);
+    if (e) { close(fd); errno = e; return io_fail(t, "write " + path); }
     if (close(fd) != 0) return io_fail(t, "close " + path);
     return DBEEL_OK;
 }
@@ -249,6 +281,48 @@ uint64_t dbeel_tree_write_sstable_index(const dbeel_tree *t) { return t ? t->wri
 
 const char *dbeel_tree_last_error(const dbeel_tree *t) { return t ? t->err.c_str() : "null tree"; }
 
+// EntryWriter's write-through (entry_writer.rs:94-156) for a finished SSTable: the page-cache `set` calls the reference makes
+// while it writes the same entries one by one, in the same order.  After entry i the .data stream holds off_i + full_size_i
+// bytes and the .index stream 16 (i + 1): a 4 KiB page is handed over the moment its last byte is written (write_to_cache,
+// :115-137), data before index inside one write(); close() hands over the two zero-padded tail pages, data first (:140-156).
+int dbeel_out_pages(const void *data, uint64_t data_len, const void *index, uint64_t index_len, uint64_t files_index, dbeel_page_sink sink,
+                    void *ctx) {
+    if (!sink || (data_len && !data) || (index_len && !index)) return DBEEL_ERR_INVALID_ARG;
+    constexpr uint64_t kPage = 4096;
+    const uint8_t *d = static_cast<const uint8_t *>(data), *ix = static_cast<const uint8_t *>(index);
+    const uint64_t n = index_len / DBEEL_INDEX_ENTRY_SIZE;
+    uint64_t dw = 0, iw = 0; // data_written / index_written
+    for (uint64_t i = 0; i < n; i++) {
+        uint32_t fs;
+        memcpy(&fs, ix + 16 * i + 12, 4);
+        const uint64_t dend = dw + fs;
+        if (dend > data_len) return DBEEL_ERR_INVALID_ARG;
+        for (uint64_t pg = dw / kPage; (pg + 1) * kPage <= dend; pg++) sink(ctx, DBEEL_FILE_DATA, files_index, pg * kPage, d + pg * kPage);
+        dw = dend;
+        const uint64_t iend = iw + 16;
+        if (iend % kPage == 0) sink(ctx, DBEEL_FILE_INDEX, files_index, iend - kPage, ix + iend - kPage);
+        iw = iend;
+    }
+    uint8_t tail[kPage];
+    if (dw % kPage) {
+        memset(tail, 0, kPage);
+        memcpy(tail, d + dw - dw % kPage, dw % kPage);
+        sink(ctx, DBEEL_FILE_DATA, files_index, dw - dw % kPage, tail);
+    }
+    if (iw % kPage) {
+        memset(tail, 0, kPage);
+        memcpy(tail, ix + iw - iw % kPage, iw % kPage);
+        sink(ctx, DBEEL_FILE_INDEX, files_index, iw - iw % kPage, tail);
+    }
+    return DBEEL_OK;
+}
+
+void dbeel_tree_set_page_sink(dbeel_tree *t, dbeel_page_sink sink, void *ctx) {
+    if (!t) return;
+    t->page_sink = sink;
+    t->page_ctx = ctx;
+}
+
 // Everything LSMTree::compact does after the merge core (lsm_tree.rs:995-1000,1068-1155) for one finished job: the
 // compact_* files, the CompactionAction journal, the renames, the sstable-list swap, the deletes.
 static int commit_compaction(dbeel_tree *t, const uint64_t *indices_to_compact, uint32_t n, uint64_t output_index, const void *data,
@@ -262,6 +336,8 @@ static int commit_compaction(dbeel_tree *t, const uint64_t *indices_to_compact, 
     if (!rc) rc = write_file(t, cindex, index, index_len);
     if (!rc && bloom_len) rc = write_file(t, cbloom, bloom, bloom_len);
     if (rc) return rc;
+    // entry_writer.rs:94-95: the writer mirrors what it writes into the shard's page cache under the NEW files_index
+    if (t->page_sink) dbeel_out_pages(data, data_len, index, index_len, output_index, t->page_sink, t->page_ctx);
 
     // lsm_tree.rs:1078-1105: journal
     CompactionAction action;
@@ -376,6 +452,7 @@ int dbeel_tree_flush(dbeel_tree *t, const dbeel_run *batch, uint64_t *written_in
     const uint64_t idx = t->write_sstable_index; // lsm_tree.rs:875-880
     rc = write_file(t, file_path(t->dir, idx, kData), od.p, out.data_len);
     if (!rc) rc = write_file(t, file_path(t->dir, idx, kIndex), oi.p, out.index_len);
+    if (!rc && t->page_sink) dbeel_out_pages(od.p, out.data_len, oi.p, out.index_len, idx, t->page_sink, t->page_ctx);
     if (rc) return rc;
     t->sstables.push_back({idx, out.items_written}); // lsm_tree.rs:903-915 (bloom: None)
     t->write_sstable_index = idx + 2;
@@ -437,6 +514,7 @@ int dbeel_tree_recover_wal(dbeel_tree *t, uint32_t tree_capacity, uint64_t *wal_
         // this open (the list was built before, :440-459): the next open discovers it.  Mirrored as is.
         rc = write_file(t, file_path(t->dir, current, kData), od.p, out.data_len);
         if (!rc) rc = write_file(t, file_path(t->dir, current, kIndex), oi.p, out.index_len);
+        if (!rc && t->page_sink) dbeel_out_pages(od.p, out.data_len, oi.p, out.index_len, current, t->page_sink, t->page_ctx);
         if (rc) return rc;
         if (unlink(old_path.c_str()) != 0) return io_fail(t, "remove " + old_path); // :510
         if (items_written) *items_written = out.items_written;

@@ -70,7 +70,7 @@ constexpr int kGatherVecsPerThread = 4;
 
 constexpr unsigned long long kGatherTileBytes = 16ull * kGatherThreads * kGatherVecsPerThread; // 16 KB of output per CTA
 constexpr int kGatherMaxEntries = (int)(kGatherTileBytes / 32) + 2; // entries are >= 32 bytes
-constexpr int kMaxLevels = 16;      // >= ceil(log2(DBEEL_MAX_RUNS)); flush: 2^16 tiles of 2048 arrivals
+constexpr int kMaxLevels = 16;      // >= ceil(log2(DBEEL_MAX_RUNS)); flush: 2^16 sort tiles of kMergeTile (1792) arrivals
 
 struct BloomParams {
     uint32_t *words;     // bit-vec storage inside the .bloom buffer (file offset 8); null = off
@@ -129,6 +129,7 @@ struct Params {
     unsigned long long out_offset_base; // .data bytes written by earlier key-range partitions of the same output file
     BloomParams bloom;
     uint4 *hash_rec; // [n_total] {h0, h1} = both SipHash-1-3 values of every entry's key (k_extract), or null: the gather hashes
+    uint32_t bloom_elsewhere; // 1: k_bloom_res fills the filter on a second stream, next to the gather (which then skips it)
 };
 
 // ------------------------------------------------------------------------------------
@@ -468,52 +469,65 @@ __global__ void __launch_bounds__(256, kRef ? 3 : DBEEL_EXTRACT_MINB) k_extract(
     }
 }
 
-// ------------------------------------------------------------------------------------
-// K1b: per-run valid counts -> segment tables of every merge level (single thread; the
-// tables have at most 2 * n_runs entries).
+__device__ __forceinline__ void block_excl_scan_1024(unsigned long long &vb, uint32_t &vc, unsigned long long *s_b, uint32_t *s_c,
+                                                     unsigned long long *tot_b, uint32_t *tot_c);
 
-__global__ void k_plan(Params p) {
-    if (threadIdx.x || blockIdx.x) return;
+// ------------------------------------------------------------------------------------
+// K1b: per-run valid counts -> segment tables of every merge level (one CTA of 1024 threads).
+
+__global__ void __launch_bounds__(1024) k_plan(Params p) {
+    // One CTA: level-0 segments in parallel, then level after level (segment l+1 = a pair of level l; the exclusive scan of
+    // the pairs' tile counts is a block scan carried over chunks of 1024 pairs).  Batches hold up to 2^24 leaf segments.
+    __shared__ unsigned long long s_b[32];
+    __shared__ uint32_t s_c[32];
+    __shared__ uint32_t s_total, s_trunc, s_flags;
     Ctl *c = p.ctl;
-    uint32_t total = 0, trunc = 0, flags = c->flags;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) { s_total = 0; s_trunc = 0; s_flags = 0; }
+    __syncthreads();
+    uint32_t total = 0, trunc = 0, flags = 0;
     if (p.mode_flush) {
         // arrival batches: level-0 segments are the tiles k_block_sort leaves sorted.  With several memtables
         // (flush-many) each one owns an aligned block of `slots` leaf segments, so the first log2(slots) merge
         // levels never pair segments of different memtables -- and there are no further levels.
         const uint32_t slots = p.flush_slots ? p.flush_slots : p.nseg[0];
-        for (uint32_t m = 0; m < p.n_runs; m++) {
+        const uint64_t n_leaf = (uint64_t)p.n_runs * slots;
+        for (uint64_t k = tid; k < n_leaf; k += 1024) {
+            const uint32_t m = (uint32_t)(k / slots), j = (uint32_t)(k % slots);
             const uint32_t cnt = p.first_bad[m];
-            if (cnt < p.runs[m].n_in) trunc++;
-            for (uint32_t j = 0; j < slots; j++) {
-                const uint32_t s0 = j * (uint32_t)kMergeTile;
-                p.seg[0][m * slots + j].start = p.runs[m].base + s0;
-                p.seg[0][m * slots + j].len = cnt > s0 ? (cnt - s0 < (uint32_t)kMergeTile ? cnt - s0 : (uint32_t)kMergeTile) : 0;
+            const uint32_t s0 = j * (uint32_t)kMergeTile;
+            Seg sg;
+            sg.start = p.runs[m].base + s0;
+            sg.len = cnt > s0 ? (cnt - s0 < (uint32_t)kMergeTile ? cnt - s0 : (uint32_t)kMergeTile) : 0;
+            p.seg[0][k] = sg;
+            if (j == 0) {
+                total += cnt;
+                if (cnt < p.runs[m].n_in) trunc++;
             }
-            total += cnt;
         }
     } else if (p.group_slots) {
         // compact-many: job g's runs fill the first slots of its block, the rest are empty segments parked at its end
-        for (uint32_t g = 0; g < p.n_groups; g++) {
-            const GroupDesc gd = p.groups[g];
-            for (uint32_t sl = 0; sl < p.group_slots; sl++) {
-                Seg sg;
-                sg.start = gd.pos_end;
-                sg.len = 0;
-                if (sl < gd.n_runs) {
-                    const uint32_t r = gd.first_run + sl;
-                    const uint32_t cnt = p.first_bad[r];
-                    if (cnt < p.runs[r].n_in) trunc++;
-                    if (p.first_mismatch[r] < cnt) flags |= kFlagUnsorted;
-                    sg.start = p.runs[r].base;
-                    sg.len = cnt;
-                    total += cnt;
-                }
-                p.seg[0][g * p.group_slots + sl] = sg;
+        const uint64_t n_leaf = (uint64_t)p.n_groups * p.group_slots;
+        for (uint64_t k = tid; k < n_leaf; k += 1024) {
+            const uint32_t g = (uint32_t)(k / p.group_slots), sl = (uint32_t)(k % p.group_slots);
+            const GroupDesc &gd = p.groups[g];
+            Seg sg;
+            sg.start = gd.pos_end;
+            sg.len = 0;
+            if (sl < gd.n_runs) {
+                const uint32_t r = gd.first_run + sl;
+                const uint32_t cnt = p.first_bad[r];
+                if (cnt < p.runs[r].n_in) trunc++;
+                if (p.first_mismatch[r] < cnt) flags |= kFlagUnsorted;
+                sg.start = p.runs[r].base;
+                sg.len = cnt;
+                total += cnt;
             }
+            p.seg[0][k] = sg;
         }
     } else {
-        for (uint32_t r = 0; r < p.n_runs; r++) {
-            uint32_t cnt = p.first_bad[r];
+        for (uint32_t r = tid; r < p.n_runs; r += 1024) {
+            const uint32_t cnt = p.first_bad[r];
             if (cnt < p.runs[r].n_in) trunc++;
             if (p.first_mismatch[r] < cnt) flags |= kFlagUnsorted;
             p.seg[0][r].start = p.runs[r].base;
@@ -521,28 +535,45 @@ __global__ void k_plan(Params p) {
             total += cnt;
         }
     }
+    if (total) atomicAdd(&s_total, total);
+    if (trunc) atomicAdd(&s_trunc, trunc);
+    if (flags) atomicOr(&s_flags, flags);
+    __syncthreads();
     for (uint32_t l = 0; l < p.n_levels; l++) {
-        uint32_t pairs = p.nseg[l + 1], acc = 0;
-        for (uint32_t j = 0; j < pairs; j++) {
-            Seg a = p.seg[l][2 * j];
-            uint32_t blen = (2 * j + 1 < p.nseg[l]) ? p.seg[l][2 * j + 1].len : 0;
-            p.seg[l + 1][j].start = a.start;
-            p.seg[l + 1][j].len = a.len + blen;
-            p.tile_base[l][j] = acc;
-            acc += (a.len + blen + kMergeTile - 1) / kMergeTile;
+        const uint32_t pairs = p.nseg[l + 1];
+        uint32_t carry = 0;
+        for (uint32_t j0 = 0; j0 < pairs; j0 += 1024) {
+            const uint32_t j = j0 + tid;
+            uint32_t tiles = 0;
+            if (j < pairs) {
+                const Seg a = p.seg[l][2 * j];
+                const uint32_t blen = (2 * j + 1 < p.nseg[l]) ? p.seg[l][2 * j + 1].len : 0;
+                p.seg[l + 1][j].start = a.start;
+                p.seg[l + 1][j].len = a.len + blen;
+                tiles = (a.len + blen + kMergeTile - 1) / kMergeTile;
+            }
+            unsigned long long vb = 0, tb;
+            uint32_t vc = tiles, tc;
+            __syncthreads();
+            block_excl_scan_1024(vb, vc, s_b, s_c, &tb, &tc);
+            if (j < pairs) p.tile_base[l][j] = carry + vc;
+            carry += tc;
         }
-        p.tile_base[l][pairs] = acc;
+        if (tid == 0) p.tile_base[l][pairs] = carry;
+        __syncthreads(); // seg[l + 1] complete before the next level pairs it up
     }
-    c->total = total;
-    c->span = p.n_groups ? p.n_total : total; // groups keep their slices at their input positions: gaps stay
-    c->runs_truncated = trunc;
-    c->flags = flags;
+    if (tid == 0) {
+        c->total = s_total;
+        c->span = p.n_groups ? p.n_total : s_total; // groups keep their slices at their input positions: gaps stay
+        c->runs_truncated = s_trunc;
+        c->flags = c->flags | s_flags;
+    }
 }
 
 // ------------------------------------------------------------------------------------
 // Flush (memtable) front end.  An arrival batch is not sorted, so the common prefix is the
 // minimum over ALL keys of their common prefix with arrival 0, and the level-0 segments are
-// produced by an in-CTA merge sort of 2048-record tiles ordered by (key, arrival).
+// produced by an in-CTA merge sort of kMergeTile-record (1792) tiles ordered by (key, arrival).
 
 __global__ void k_flush_prefix_init(Params p) {
     if (threadIdx.x || blockIdx.x) return;
@@ -1376,7 +1407,7 @@ __global__ void __launch_bounds__(kGatherThreads, DBEEL_GATHER_MINB) k_gather(Pa
     }
 
     // ---- bloom (fused epilogue): entries whose first byte lies in this tile
-    if (p.bloom.words != nullptr && p.hash_rec == nullptr) {
+    if (p.bloom.words != nullptr && p.hash_rec == nullptr && !p.bloom_elsewhere) {
         for (uint32_t j = tid; j < ne; j += NT) {
             const int r0 = s_r0[j];
             if (r0 < 0 || r0 >= (int)kGatherTileBytes) continue;
@@ -1449,7 +1480,7 @@ __global__ void __launch_bounds__(kGatherThreads, DBEEL_GATHER32_MINB) k_gather3
     const uint32_t e_lo = p.tile_first[tile_id];
     const uint32_t e_hi = T0 + kGatherTileBytes < out_len ? p.tile_first[tile_id + 1] : c->out_items - 1;
     const uint32_t ne = e_hi - e_lo + 1; // <= kGatherMaxEntries: every entry is >= 32 bytes
-    const bool hash_here = p.bloom.words != nullptr && p.hash_rec == nullptr;
+    const bool hash_here = p.bloom.words != nullptr && p.hash_rec == nullptr && !p.bloom_elsewhere;
     for (uint32_t j = tid; j < ne; j += NT) {
         const uint4 rec = p.out_index[e_lo + j];
         const unsigned long long d0 = ((unsigned long long)rec.x | ((unsigned long long)rec.y << 32)) - p.out_offset_base;
@@ -1568,6 +1599,292 @@ __global__ void __launch_bounds__(kGatherThreads, DBEEL_GATHER32_MINB) k_gather3
     }
 }
 
+// ------------------------------------------------------------------------------------
+// K5, TMA-staged (the default): "SSTable data blocks staged from HBM into shared memory via TMA".
+//
+// Why: k_gather / k_gather32 are neither DRAM- nor issue-bound (ncu: DRAM 56 %, issue 60 %).  A CTA walks its phases one
+// after the other -- tile_first -> out_index / src_ptr -> payload loads -> stores -> boundary loads -> key loads -- and
+// every arrow is a memory round trip that only the OTHER resident CTAs can cover.  Here the payload of a tile comes in
+// through the bulk-copy engine instead: one cp.async.bulk per entry (its 16-byte-aligned superset, <= tile bytes + 30),
+// all completing on one mbarrier, issued a whole tile AHEAD (two shared-memory stages), with the metadata of the tile
+// after that already travelling in registers.  By the time a tile is processed its bytes are in shared memory; the byte
+// realignment (the bulk engine preserves address mod 16, source and destination offsets differ by an arbitrary byte
+// count) runs from shared memory with LDS.128 + funnel shifts, the output leaves in 256-bit stores, and the bloom hashes
+// read their keys from shared memory too.  Persistent CTAs, one tile per iteration.
+//
+//   iteration q:   metadata of tile q+1 (registers) -> shared memory, prefix sum of the staged lengths, bulk copies issued
+//                  global loads for the metadata of tile q+2 and the tile_first pair of tile q+3 (consumed next iteration)
+//                  wait for tile q's mbarrier -> copy / boundary blocks / bloom from stage q & 1
+//
+// Staging layout of a tile: entry j's in-tile part [r0c, r1c) is copied from src_lo = src & ~15 as len = ceil16(sh + n) bytes
+// to stage offset base_j = sum of the earlier lengths, so its byte at tile position b lives at sadj_j + b with
+// sadj_j = base_j + sh - r0c.
+
+constexpr int kGtThreads = kGatherThreads;
+constexpr int kGtPer = (kGatherMaxEntries + kGtThreads - 1) / kGtThreads;          // entries a thread may have to stage
+constexpr uint32_t kGtStageBytes = (uint32_t)kGatherTileBytes + 32u * kGatherMaxEntries + 128u; // payload + per-entry slack
+#ifndef DBEEL_GT_CTAS
+#define DBEEL_GT_CTAS 4
+#endif
+
+struct GtMeta {
+    unsigned long long adj[kGatherMaxEntries]; // global address of the entry minus its tile-relative start
+    uint32_t sadj[kGatherMaxEntries];          // stage offset of the entry's byte at tile position 0
+    int r0[kGatherMaxEntries], r1[kGatherMaxEntries];
+    uint32_t ks[kGatherMaxEntries];
+    uint32_t ne, tile_len;
+    unsigned long long T0;
+};
+constexpr uint32_t kGtSmem = 2u * kGtStageBytes + 2u * (uint32_t)sizeof(GtMeta) + 64u;
+
+__device__ __forceinline__ uint4 lds16_any(const uint8_t *stage, uint32_t off, uint32_t need) {
+    const uint32_t s0 = off & 15u;
+    const uint4 *sv = reinterpret_cast<const uint4 *>(stage + (off - s0));
+    const uint4 TA = *sv;
+    const uint4 TB = *(s0 + need > 16 ? sv + 1 : sv);
+    return realign16_sel(TA, TB, s0);
+}
+
+__global__ void __launch_bounds__(kGtThreads, DBEEL_GT_CTAS) k_gather_tma(Params p) {
+    constexpr int NT = kGtThreads;
+    extern __shared__ __align__(128) uint8_t gt_raw[];
+    auto stage_ptr = [&](uint32_t st) -> uint8_t * { return gt_raw + st * kGtStageBytes; };
+    auto meta_ptr = [&](uint32_t st) -> GtMeta * { return reinterpret_cast<GtMeta *>(gt_raw + 2 * kGtStageBytes) + st; };
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ uint32_t s_scan[NT / 32];
+    const Ctl *c = p.ctl;
+    const unsigned long long out_len = c->out_data_len;
+    const uint32_t out_items = c->out_items;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n_tiles = (uint32_t)((out_len + kGatherTileBytes - 1) / kGatherTileBytes);
+    const uint32_t G = gridDim.x;
+    if (blockIdx.x >= n_tiles) return;
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // ---- the three pipeline steps that run ahead of the tile being copied
+    struct TF { uint32_t e_lo, ne; };
+    auto load_tf = [&](uint32_t t) -> TF { // which entries overlap tile t
+        TF r;
+        r.e_lo = 0; r.ne = 0;
+        if (t < n_tiles) {
+            r.e_lo = __ldg(&p.tile_first[t]);
+            const uint32_t e_hi = t + 1 < n_tiles ? __ldg(&p.tile_first[t + 1]) : out_items - 1;
+            r.ne = e_hi - r.e_lo + 1;
+        }
+        return r;
+    };
+    auto load_recs = [&](const TF &tf, uint4 rec[kGtPer], unsigned long long src[kGtPer]) { // their index records / addresses
+#pragma unroll
+        for (int k = 0; k < kGtPer; k++) {
+            const uint32_t j = tid + (uint32_t)k * NT;
+            rec[k] = make_uint4(0, 0, 0, 0);
+            src[k] = 0;
+            if (j < tf.ne) {
+                rec[k] = __ldg(&p.out_index[tf.e_lo + j]);
+                src[k] = __ldg(&p.src_ptr[tf.e_lo + j]);
+            }
+        }
+    };
+    auto publish = [&](uint32_t st, uint32_t t, const TF &tf, const uint4 rec[kGtPer], const unsigned long long src[kGtPer]) {
+        GtMeta &m = *meta_ptr(st);
+        const unsigned long long T0 = (unsigned long long)t * kGatherTileBytes;
+        const uint32_t tile_len = out_len - T0 < kGatherTileBytes ? (uint32_t)(out_len - T0) : (uint32_t)kGatherTileBytes;
+        uint32_t carry = 0;
+#pragma unroll
+        for (int k = 0; k < kGtPer; k++) {
+            if ((uint32_t)k * NT >= tf.ne) break; // uniform
+            const uint32_t j = tid + (uint32_t)k * NT;
+            uint32_t len = 0, sh = 0;
+            int r0c = 0;
+            unsigned long long src_lo = 0;
+            if (j < tf.ne) {
+                const unsigned long long d0 = ((unsigned long long)rec[k].x | ((unsigned long long)rec[k].y << 32)) - p.out_offset_base;
+                const long long r0 = (long long)d0 - (long long)T0; // < 0 only for the tile's first entry
+                const long long r1 = r0 + (long long)rec[k].w;
+                const unsigned long long adj = src[k] - (unsigned long long)r0;
+                m.adj[j] = adj;
+                m.r0[j] = r0 < -0x7FFFFFFFll ? -0x7FFFFFFF : (int)r0;
+                m.r1[j] = r1 > 0x7FFFFFFFll ? 0x7FFFFFFF : (int)r1;
+                m.ks[j] = rec[k].z;
+                r0c = r0 < 0 ? 0 : (int)r0;
+                const int r1c = r1 > (long long)tile_len ? (int)tile_len : (int)r1;
+                const unsigned long long src_c = adj + (unsigned long long)r0c;
+                sh = (uint32_t)(src_c & 15);
+                src_lo = src_c - sh;
+                len = (sh + (uint32_t)(r1c - r0c) + 15u) & ~15u;
+            }
+            // exclusive prefix of len over the 128 entries of this round, in entry order
+            uint32_t inc = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= (uint32_t)o) inc += x;
+            }
+            __syncthreads(); // s_scan of the previous round / call has been read
+            if (lane == 31) s_scan[warp] = inc;
+            __syncthreads();
+            uint32_t before = carry, total = 0;
+#pragma unroll
+            for (int w = 0; w < NT / 32; w++) {
+                if ((uint32_t)w < warp) before += s_scan[w];
+                total += s_scan[w];
+            }
+            const uint32_t base = before + inc - len;
+            carry += total;
+            if (j < tf.ne) {
+                m.sadj[j] = base + sh - (uint32_t)r0c;
+                tma_load_1d(stage_ptr(st) + base, reinterpret_cast<const void *>(src_lo), len, &s_bar[st]);
+            }
+        }
+        if (tid == 0) {
+            m.ne = tf.ne;
+            m.tile_len = tile_len;
+            m.T0 = T0;
+            mbar_expect_tx(&s_bar[st], carry); // one arrival: the phase completes when all `carry` bytes have landed
+        }
+    };
+
+    uint4 recA[kGtPer], recB[kGtPer];
+    unsigned long long srcA[kGtPer], srcB[kGtPer];
+    uint32_t tile = blockIdx.x;
+    TF tf_cur = load_tf(tile), tf_nxt = load_tf(tile + G);
+    load_recs(tf_cur, recA, srcA);
+    publish(0, tile, tf_cur, recA, srcA);
+    load_recs(tf_nxt, recA, srcA);        // metadata of the NEXT tile rides in registers
+    TF tf_nn = load_tf(tile + 2 * G);
+
+    for (uint32_t q = 0;; q++) {
+        const uint32_t st = q & 1;
+        const bool has_next = tile + G < n_tiles;
+        if (has_next) publish(st ^ 1, tile + G, tf_nxt, recA, srcA);
+        load_recs(tf_nn, recB, srcB);                 // tile q + 2
+        const TF tf_n3 = load_tf(tile + 3 * G);       // tile q + 3
+        __syncthreads();                              // meta[st] was written one iteration ago by other threads
+        while (!mbar_try_wait(&s_bar[st], (q >> 1) & 1)) {}
+
+        const GtMeta &m = *meta_ptr(st);
+        const uint8_t *sd = stage_ptr(st);
+        const uint32_t ne = m.ne, tile_len = m.tile_len;
+        uint8_t *dst_tile = p.out_data + m.T0;
+
+        // ---- copy: warp w owns bytes [w * 2 KB, (w + 1) * 2 KB) of the tile, 1 KB (32 lanes x 32 bytes) at a time
+        const int sub0 = (int)(warp * (uint32_t)(kG32Vpt * 1024));
+        if ((uint32_t)sub0 < tile_len) {
+            uint32_t j = 0;
+            for (uint32_t base = 0; base + 1 < ne; base += 32) {
+                const uint32_t i = base + lane;
+                j += __popc(__ballot_sync(0xFFFFFFFFu, i + 1 < ne && m.r1[i] <= sub0));
+            }
+            const uint32_t lanes_le = 0xFFFFFFFFu >> (31 - lane);
+#pragma unroll
+            for (int k = 0; k < kG32Vpt; k++) {
+                const int cb = sub0 + k * 1024;
+                const int b0 = cb + (int)lane * 32;
+                const uint32_t i = j + lane;
+                const int r1 = i + 1 < ne ? m.r1[i] : 0x7FFFFFFF;
+                const bool ends_here = r1 <= cb + 1024;
+                const uint32_t t = (uint32_t)((ends_here ? r1 : cb + 32) - cb + 31) >> 5;
+                const uint32_t ends = __reduce_or_sync(0xFFFFFFFFu, (ends_here && t < 32) ? (1u << t) : 0u);
+                const uint32_t cnt = __popc(ends & lanes_le);
+                const uint32_t adv = __popc(__ballot_sync(0xFFFFFFFFu, ends_here));
+                const uint32_t e = j + cnt;
+                j += adv;
+                const int r1e = m.r1[e];
+                const bool pure = (uint32_t)b0 + 32 <= tile_len && b0 + 32 <= r1e;
+                if (pure) { // divergence is cheap here: nothing is in flight, the operands are in shared memory
+                    const uint32_t sa = m.sadj[e] + (uint32_t)b0;
+                    const uint32_t sh = sa & 15u;
+                    const uint4 *sv = reinterpret_cast<const uint4 *>(sd + (sa - sh));
+                    const uint4 A = sv[0], B = sv[1], C = sv[sh ? 2 : 1];
+                    uint32_t o[8];
+                    realign32(A, B, C, sh, o);
+                    stg256(dst_tile + b0, o);
+                }
+            }
+        }
+
+        // ---- the 32-byte block that holds the last byte of entry j (unless j ends on a block boundary): its two halves
+        for (uint32_t j = tid; j < ne; j += NT) {
+            const int r1 = m.r1[j];
+            if (r1 <= 0 || (r1 & 31) == 0 || r1 > (int)tile_len) continue;
+            const bool has_nx = j + 1 < ne;
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const uint32_t b0 = ((uint32_t)r1 & ~31u) + 16u * half;
+                if (b0 >= tile_len) continue;
+                const int t = r1 - (int)b0;
+                uint4 o;
+                if (t >= 16) {
+                    o = lds16_any(sd, m.sadj[j] + b0, 16);
+                } else if (t <= 0) {
+                    if (!has_nx) continue;
+                    o = lds16_any(sd, m.sadj[j + 1] + b0, 16);
+                } else {
+                    o = lds16_any(sd, m.sadj[j] + b0, (uint32_t)t);
+                    if (b0 + 16 <= tile_len) {
+                        const uint4 H = lds16_any(sd, m.sadj[j + 1] + (uint32_t)r1, 16);
+                        const uint4 HU = realign16_sel(make_uint4(0, 0, 0, 0), H, 16 - (uint32_t)t);
+                        const uint32_t wfull = (uint32_t)t >> 2, bits = ((uint32_t)t & 3) * 8;
+                        const uint32_t mmix = bits ? (0xFFFFFFFFu >> (32 - bits)) : 0u;
+                        uint32_t ow[4] = {o.x, o.y, o.z, o.w}, hw[4] = {HU.x, HU.y, HU.z, HU.w};
+#pragma unroll
+                        for (uint32_t qq = 0; qq < 4; qq++) {
+                            const uint32_t mk = qq < wfull ? 0xFFFFFFFFu : (qq == wfull ? mmix : 0u);
+                            ow[qq] = (ow[qq] & mk) | (hw[qq] & ~mk);
+                        }
+                        o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                    } else { // ragged end of the whole stream
+                        const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+                        for (int b = 0; b < t; b++) dst_tile[b0 + b] = (uint8_t)(ow[b >> 2] >> ((b & 3) * 8));
+                        continue;
+                    }
+                }
+                reinterpret_cast<uint4 *>(dst_tile)[b0 >> 4] = o;
+            }
+        }
+
+        // ---- bloom (fused epilogue): entries whose first byte lies in this tile; keys from shared memory when they are
+        // wholly staged (an entry that runs into the next tile may have its key cut off: global loads then)
+        if (p.bloom.words != nullptr && p.hash_rec == nullptr && !p.bloom_elsewhere) {
+            for (uint32_t j = tid; j < ne; j += NT) {
+                const int r0 = m.r0[j];
+                if (r0 < 0 || r0 >= (int)kGatherTileBytes) continue;
+                const uint64_t klen = m.ks[j] - 8;
+                uint64_t h0, h1;
+                if ((uint64_t)r0 + 16 + klen <= (uint64_t)tile_len) {
+                    const uint8_t *key = sd + (m.sadj[j] + (uint32_t)r0 + 8u);
+                    sip13_pair_vec_u8(p.bloom.sip, klen, [key](uint64_t qq) {
+                        const uintptr_t a = reinterpret_cast<uintptr_t>(key + 8 * qq);
+                        const uint64_t *w = reinterpret_cast<const uint64_t *>(a & ~uintptr_t(7));
+                        const uint32_t shb = (uint32_t)(a & 7) * 8;
+                        const uint64_t lo = w[0];
+                        return shb ? (lo >> shb) | (w[1] << (64 - shb)) : lo;
+                    }, &h0, &h1);
+                } else {
+                    const uint8_t *key = reinterpret_cast<const uint8_t *>((uintptr_t)(m.adj[j] + (unsigned long long)r0)) + 8;
+                    sip13_pair_vec_u8(p.bloom.sip, klen, [key](uint64_t qq) { return ld_u64_unaligned(key + 8 * qq); }, &h0, &h1);
+                }
+                uint32_t *words = p.bloom.words;
+                bloom_probe_all(h0, h1, p.bloom.k_num, p.bloom.bits, p.bloom.bits_magic,
+                                [words](uint64_t bit) { atomicOr(&words[bit >> 5], 1u << (bit & 31)); });
+            }
+        }
+
+        if (!has_next) break;
+        __syncthreads(); // everyone is done with stage st and meta[st]: the next iteration's publish overwrites st ^ 1's peer
+        tile += G;
+        tf_nxt = tf_nn;
+        tf_nn = tf_n3;
+#pragma unroll
+        for (int k = 0; k < kGtPer; k++) { recA[k] = recB[k]; srcA[k] = srcB[k]; }
+    }
+}
+
 // Job header down / control block up without a copy engine: the pinned block is mapped into the GPU's address space.
 __global__ void __launch_bounds__(256) k_copy_words(uint32_t *dst, const uint32_t *src_host, uint32_t n) {
     const uint32_t i = blockIdx.x * 256u + threadIdx.x;
@@ -1609,6 +1926,23 @@ __global__ void k_bloom_frame(uint8_t *file, uint64_t n_words, BloomParams b) {
         put64(t + 16, 0);                         // ntail
         t += 18;
     }
+}
+
+// Single job, filter filled NEXT TO the gather instead of inside it: one thread per merged position, survivors only
+// (res[i].w != 0), key bytes from the entry's source (one 64-byte granule for ordinary keys).  Launched on the engine's
+// second stream right after k_resolve, so its random reads and SipHash rounds overlap k_emit and the payload copy -- the
+// gather is the kernel with no issue slot and no latency slack to spare, this one is all latency.
+__global__ void __launch_bounds__(256) k_bloom_res(Params p, const uint4 *res) {
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= p.ctl->span) return;
+    const uint4 it = __ldg(&res[i]);
+    if (it.w == 0) return;
+    const uint8_t *key = reinterpret_cast<const uint8_t *>((uintptr_t)((unsigned long long)it.x | ((unsigned long long)it.y << 32))) + 8;
+    uint64_t h0, h1;
+    sip13_pair_vec_u8(p.bloom.sip, (uint64_t)(it.z - 8), [key](uint64_t q) { return ld_u64_unaligned_narrow(key + 8 * q); }, &h0, &h1);
+    uint32_t *words = p.bloom.words;
+    bloom_probe_all(h0, h1, p.bloom.k_num, p.bloom.bits, p.bloom.bits_magic,
+                    [words](uint64_t bit) { atomicOr(&words[bit >> 5], 1u << (bit & 31)); });
 }
 
 // compact-many: the filters are per job (own size, own seed), so they are filled by a pass of their own over the output

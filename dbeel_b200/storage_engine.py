@@ -20,6 +20,10 @@ ERR_NO_SSTABLE = 21
 DEFAULT_TREE_CAPACITY = 8192  # mod.rs:18
 DEFAULT_SSTABLE_BLOOM_MIN_SIZE = 1_048_576  # mod.rs:19
 
+FILE_DATA, FILE_INDEX = 1, 2  # FileTypeKind::{Data, Index} (mod.rs:36-42)
+PAGE_SIZE = 4096  # page_cache.rs:10
+PAGE_SINK = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint8))
+
 _bound = False
 
 
@@ -54,13 +58,17 @@ def _lib():
         L.dbeel_plan_compactions.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32,
                                              C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
                                              C.POINTER(C.c_int32)]
+        L.dbeel_out_pages.restype = C.c_int
+        L.dbeel_out_pages.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64, PAGE_SINK, C.c_void_p]
+        L.dbeel_tree_set_page_sink.restype = None
+        L.dbeel_tree_set_page_sink.argtypes = [C.c_void_p, PAGE_SINK, C.c_void_p]
         _bound = True
     return L
 
 
 TREE_EXPORTS = ["dbeel_tree_open", "dbeel_tree_close", "dbeel_tree_sstables", "dbeel_tree_write_sstable_index",
                 "dbeel_tree_compact", "dbeel_tree_compact_many", "dbeel_tree_flush", "dbeel_tree_recover_wal", "dbeel_tree_get_many", "dbeel_tree_last_error", "dbeel_memtable_cut",
-                "dbeel_plan_compactions"]
+                "dbeel_plan_compactions", "dbeel_out_pages", "dbeel_tree_set_page_sink"]
 
 
 def _run_struct(batch) -> Tuple[capi.Run, tuple]:
@@ -107,6 +115,17 @@ class LSMTree:
         if self._h:
             _lib().dbeel_tree_close(self._h)
             self._h = C.c_void_p()
+
+    def set_page_cache(self, cache: Optional[dict]):
+        """Mirror EntryWriter's write-through: every SSTable this tree writes from now on is also `set` page by page into
+        `cache` under the reference's key ((FileTypeKind, files_index), address) (entry_writer.rs:100-156).  None = off."""
+        if cache is None:
+            self._sink = PAGE_SINK(0)
+        else:
+            def sink(_ctx, kind, files_index, address, page):
+                cache[((int(kind), int(files_index)), int(address))] = bytes(page[:PAGE_SIZE])
+            self._sink = PAGE_SINK(sink)
+        _lib().dbeel_tree_set_page_sink(self._h, self._sink, None)
 
     def __del__(self):
         try:
@@ -196,3 +215,17 @@ class LSMTree:
         for indices, out, keep in plan:
             self.compact(indices, out, keep, bloom_seed)
         return plan
+
+
+def out_pages(data, index, files_index: int):
+    """dbeel_out_pages: the (file kind, files_index, address, page bytes) sequence EntryWriter would `set` for this SSTable."""
+    d, i = capi._u8(data), capi._u8(index)
+    seq = []
+
+    def sink(_ctx, kind, fi, address, page):
+        seq.append((int(kind), int(fi), int(address), bytes(page[:PAGE_SIZE])))
+    cb = PAGE_SINK(sink)
+    rc = _lib().dbeel_out_pages(d.ctypes.data if d.size else None, d.size, i.ctypes.data if i.size else None, i.size, files_index, cb, None)
+    if rc:
+        raise capi.DbeelError(rc, "dbeel_out_pages")
+    return seq

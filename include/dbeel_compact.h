@@ -69,7 +69,8 @@ enum {
 #define DBEEL_DEFAULT_TREE_CAPACITY 8192u     /* mod.rs:18 */
 
 /* One input SSTable: the bytes of its .data and .index files.
- * For the *_device entry points both pointers are device pointers aligned to 16 bytes. */
+ * For the *_device entry points both are device pointers; `index` must be aligned to 16 bytes, `data` may start anywhere
+ * (the SSTables dbeel_flush_many / dbeel_compact_many leave back to back in one output stream are valid inputs as they lie). */
 typedef struct dbeel_run {
     const void *data;
     uint64_t data_len;
@@ -135,6 +136,9 @@ typedef struct dbeel_engine dbeel_engine;
 /* One engine per calling thread / shard, bound to one GPU and one stream. */
 int dbeel_engine_create(int device, dbeel_engine **out);
 void dbeel_engine_destroy(dbeel_engine *e);
+/* The engine's CUDA stream (a cudaStream_t): every kernel of its jobs is launched there.  For callers that want to record
+ * their own events around jobs or order other work against them.  Several engines on one GPU run their jobs concurrently. */
+void *dbeel_engine_stream(dbeel_engine *e);
 
 /* Host placement.  dbeel pins one executor thread per core (src/main.rs:51-60); with one GPU per shard that thread and
  * the pinned buffers it stages through should sit on the GPU's NUMA node, or every byte crosses the socket interconnect on

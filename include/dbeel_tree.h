@@ -38,6 +38,19 @@ extern "C" {
 
 typedef struct dbeel_tree dbeel_tree;
 
+/* EntryWriter's page-cache write-through (src/storage_engine/entry_writer.rs:94-156): while it writes an SSTable the
+ * reference mirrors both streams into the shard's page cache in 4 KiB pages keyed by ((FileTypeKind, files_index), page
+ * address), the last page of each stream zero-padded at close().  dbeel_out_pages replays exactly those `set` calls -- same
+ * pages, same order -- for an SSTable the engine produced (host buffers), so the Rust side can warm its PartitionPageCache
+ * from the returned buffers.  Not on-disk state: skipping it can never serve stale bytes (the keys carry the fresh index). */
+#define DBEEL_FILE_DATA 1u  /* FileTypeKind::Data  (mod.rs:36-42: Memtable, Data, Index, Bloom) */
+#define DBEEL_FILE_INDEX 2u /* FileTypeKind::Index */
+typedef void (*dbeel_page_sink)(void *ctx, uint32_t file_kind, uint64_t files_index, uint64_t address, const uint8_t *page /* 4096 bytes */);
+int dbeel_out_pages(const void *data, uint64_t data_len, const void *index, uint64_t index_len, uint64_t files_index,
+                    dbeel_page_sink sink, void *ctx);
+/* A tree with a sink installed calls it for every SSTable dbeel_tree_compact / _compact_many / _flush / _recover_wal write. */
+void dbeel_tree_set_page_sink(dbeel_tree *t, dbeel_page_sink sink, void *ctx);
+
 int dbeel_tree_open(const char *dir, dbeel_engine *engine, uint64_t sstable_bloom_min_size, dbeel_tree **out);
 void dbeel_tree_close(dbeel_tree *t);
 

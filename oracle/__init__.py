@@ -85,6 +85,8 @@ def lib():
         L.orc_get_many.restype = None
         L.orc_get_many.argtypes = [C.POINTER(_Run), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_uint32, C.c_void_p,
                                    C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_densify.restype = C.c_uint64
+        L.orc_densify.argtypes = [C.POINTER(_Run), C.c_void_p, C.c_uint64, C.c_void_p]
         L.orc_murmur3_32.restype = C.c_uint32
         L.orc_murmur3_32.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32]
         L.orc_ring_owner.restype = C.c_uint32
@@ -302,3 +304,17 @@ def route(batch: Tuple[object, object], ring: np.ndarray):
     hashes = np.empty(n, np.uint32)
     done = lib().orc_route(arr, ring.ctypes.data, ring.size, shard.ctypes.data, hashes.ctypes.data)
     return shard[:done], hashes[:done]
+
+
+def densify(data, sparse_index):
+    """Dense arrival batch (data, index) of the entries a sparse index names inside `data` (a routed stream's slice)."""
+    arr, keep = _mk_runs([(data, sparse_index)])
+    idx = keep[0][1]
+    fs = idx.reshape(-1, 16)[:, 12:16].copy().view("<u4").ravel()
+    total = int(fs.astype(np.uint64).sum())
+    od = np.empty(max(1, total), np.uint8)
+    oi = np.empty(max(1, idx.size), np.uint8)
+    done = lib().orc_densify(arr, od.ctypes.data, total, oi.ctypes.data)
+    if done != idx.size // 16:
+        raise OracleError(f"orc_densify stopped at record {done}")
+    return od[:total], oi[:idx.size]

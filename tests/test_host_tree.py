@@ -303,3 +303,86 @@ def test_compact_tree_batched_equals_group_by_group(engine, tmp_path):
         assert os.path.exists(bp) == (ob is not None)
         if ob is not None:
             assert np.array_equal(np.fromfile(bp, dtype=np.uint8), ob)
+
+
+def _entry_writer_model(entries, files_index):
+    """entry_writer.rs:71-156 restated in Python: write() per entry, write_to_cache() per stream, close()."""
+    PAGE = 4096
+    seq = []
+    state = {se.FILE_DATA: [bytearray(PAGE), 0], se.FILE_INDEX: [bytearray(PAGE), 0]}
+
+    def write_to_cache(raw, kind):
+        st = state[kind]
+        for c0 in range(0, len(raw), PAGE):
+            chunk = raw[c0:c0 + PAGE]
+            off = st[1] % PAGE
+            end = min(off + len(chunk), PAGE)
+            st[0][off:end] = chunk[:end - off]
+            first = end - off
+            st[1] += first
+            if st[1] % PAGE == 0:
+                seq.append((kind, files_index, st[1] - PAGE, bytes(st[0])))
+                st[0] = bytearray(PAGE)
+                left = len(chunk) - first
+                st[0][:left] = chunk[first:]
+                st[1] += left
+
+    for k, v, ts in entries:
+        rec = sstable.encode_entry(k, v, ts)
+        idx = sstable.encode_index_record(state[se.FILE_DATA][1], len(k), len(rec))
+        write_to_cache(rec, se.FILE_DATA)
+        write_to_cache(idx, se.FILE_INDEX)
+    for kind in (se.FILE_DATA, se.FILE_INDEX):  # close()
+        left = state[kind][1] % PAGE
+        if left:
+            seq.append((kind, files_index, state[kind][1] - left, bytes(state[kind][0])))
+    return seq
+
+
+def test_out_pages_replays_entry_writers_write_through():
+    """dbeel_out_pages vs a literal restatement of EntryWriter::{write, write_to_cache, close}: same pages, same keys, same
+    order -- including entries larger than a page, entries that end exactly on a page boundary and the zero-padded tails
+    (the reference's own entry_writer_cache_equals_disk test, lsm_tree.rs:1489-1556, checks pages against stream bytes)."""
+    rng = np.random.default_rng(3)
+    cases = [
+        [(b"k%04d" % i, bytes(rng.integers(0, 256, int(rng.integers(0, 300)), dtype=np.uint8)), 7 + i) for i in range(700)],
+        [(b"big%d" % i, bytes(rng.integers(0, 256, 9000 + 517 * i, dtype=np.uint8)), i) for i in range(5)],
+        [(b"a", b"x" * (4096 - 32 - 1), 1), (b"b", b"y" * (4096 - 32 - 1), 2), (b"c", b"", 3)],  # entries of exactly one page
+        [(b"only", b"", 1)],
+        [(b"i%05d" % i, b"", i) for i in range(300)],  # 300 index records: the index stream crosses a page too
+    ]
+    for n, ents in enumerate(cases):
+        d, i = sstable.build_run(ents)
+        got = se.out_pages(d, i, 40 + n)
+        assert got == _entry_writer_model(ents, 40 + n), f"case {n}"
+        # and the pages are the files, zero-padded
+        for kind, buf in ((se.FILE_DATA, d), (se.FILE_INDEX, i)):
+            pages = [p for k, _, _, p in got if k == kind]
+            assert b"".join(pages)[:buf.size] == bytes(buf) and not any(b"".join(pages)[buf.size:])
+    assert se.out_pages(np.zeros(0, np.uint8), np.zeros(0, np.uint8), 1) == []
+
+
+@pytest.mark.gpu
+def test_tree_write_through_warms_a_page_cache(engine, tmp_path):
+    """entry_writer.rs:94-156 as a side effect of the tree's own writes: with a page sink installed, every SSTable a flush
+    or a compaction writes also lands in the cache, page by page, under ((FileTypeKind, files_index), address) -- and what
+    the cache holds is what the files hold (the reference's entry_writer_cache_equals_disk, lsm_tree.rs:1489-1556)."""
+    d = str(tmp_path)
+    rng = np.random.default_rng(12)
+    tree = se.LSMTree(d, engine, sstable_bloom_min_size=1 << 40)
+    cache = {}
+    tree.set_page_cache(cache)
+    for r in range(3):
+        ents = [(b"key%05d" % int(k), bytes(rng.integers(0, 256, int(rng.integers(0, 700)), dtype=np.uint8)), BASE_TS + r)
+                for k in rng.choice(4000, 900, replace=False)]
+        tree.flush(sstable.build_run(ents))
+    tree.compact([0, 2, 4], 5, False)
+    for files_index in (0, 2, 4, 5):  # the flushed tables were cached too (their files are gone after the compaction)
+        assert any(k[0] == (se.FILE_DATA, files_index) for k in cache)
+    for kind, ext in ((se.FILE_DATA, "data"), (se.FILE_INDEX, "index")):
+        raw = open(os.path.join(d, sstable.file_name(5, ext)), "rb").read()
+        pages = sorted((addr, pg) for (fid, addr), pg in cache.items() if fid == (kind, 5))
+        assert [a for a, _ in pages] == list(range(0, len(raw), 4096))
+        joined = b"".join(pg for _, pg in pages)
+        assert joined[:len(raw)] == raw and not any(joined[len(raw):])
+    tree.close()
