@@ -293,9 +293,10 @@ def run_gpu(args):
     bounds = [capi.compact_bound([(d.size, i.size) for d, i in runs], opts) for runs in jobs_runs]
     dc, ic, bc = (max(b[k] for b in bounds) for k in range(3)) if bounds else (0, 0, 0)
 
-    # Independent shard compactions overlap on one GPU: with >= 2 jobs per GPU two engines (two streams) take them
-    # alternately, so one job's HBM-bound payload gather runs next to the other's latency-bound metadata stages.
-    n_eng = 2 if (len(mine) >= 2 and not args.no_overlap) else 1
+    # --overlap: two engines (two streams) take a GPU's jobs alternately.  Measured on B200: no gain (13.48 vs 13.59 ms for 8
+    # jobs) -- every kernel of a job fills the GPU, and the block scheduler drains one grid before it starts the next
+    # stream's, so two jobs' stages do not co-run.  Off by default; the rank's jobs run one after the other.
+    n_eng = 2 if (len(mine) >= 2 and args.overlap) else 1
     engs = [eng] + [capi.Engine(local) for _ in range(n_eng - 1)]
     # device-resident inputs of every job of this rank; one output SSTable buffer set per engine, reused job after job
     t_jobs = [[(torch.from_numpy(d).to(dev), torch.from_numpy(i).to(dev)) for d, i in runs] for runs in jobs_runs]
@@ -487,7 +488,7 @@ def run_gpu(args):
                      "parallelism": f"{int(jobs_all)} independent shard compactions over {world} GPU(s), shard i on GPU i mod N, no data-path collective",
                      "engines_per_gpu": n_eng,
                      "timing": "per step: CUDA events on the engines' streams, first start to last end of the rank's jobs (two jobs in flight "
-                               "when a GPU has two or more); sum over the K steps, max over ranks.  ms_per_job / stage_ms / roofline: every job alone",
+                               "with --overlap); sum over the K steps, max over ranks.  ms_per_job / stage_ms / roofline: every job alone",
                      "host_placement": {"numa_node": numa_node, "cpus": numa_cpus}})
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -608,7 +609,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="dbeel_b200", choices=["dbeel_b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the oracle legs: cpu_baseline, byte parity, other_configs (profiling runs)")
-    ap.add_argument("--no-overlap", action="store_true", help="one engine per GPU: the rank's jobs strictly one after the other")
+    ap.add_argument("--overlap", action="store_true", help="two engines per GPU taking the rank's jobs alternately (measured: no gain)")
     ap.add_argument("--no-others", action="store_true", help="skip the other_configs block (cfg1 / cfg3 / cfg5-shard evidence)")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg5"],
                     help="cfg2 (default): BASELINE.json's headline, 8 shard jobs of configs[1]'s shape; cfg5: configs[4]")

@@ -76,7 +76,9 @@ struct dbeel_engine {
     int narrow_loads = 1;       // DBEEL_NARROW: .L2::64B loads for random accesses in extract / resolve (A/B switch)
     int gather_variant = 1;     // DBEEL_GATHER: 0 = 16 bytes per lane (k_gather), 1 = 32 bytes per lane + 256-bit stores (k_gather32),
                                 //               2 = 1 with the payload staged into shared memory by TMA bulk copies (k_gather_tma)
-    int bloom_side = 1;         // DBEEL_BLOOM_SIDE: 1 = k_bloom_res on a second stream next to the gather, 0 = the gather's fused epilogue
+    int fused_emit = 0;         // DBEEL_FUSED_EMIT: 1 = resolve + offsets scan + .index writes in one kernel (single jobs), 0 = four kernels
+    int bloom_side = 0;         // DBEEL_BLOOM_SIDE: 1 = k_bloom_res on a second stream (measured: kernels of two streams do not co-run, the
+                                // filter pass just moves in front of k_emit: +0.16 ms per job); 0 = the gather's fused epilogue
     cudaStream_t s_side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int bloom_in_extract = 0;   // DBEEL_BLOOM_EXTRACT: 1 = k_extract hashes, k_resolve sets the bits (measured slower: DESIGN.md); 0 = the gather's fused epilogue
@@ -303,6 +305,9 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     // single job with a filter: k_extract leaves both SipHash values of every key here and k_resolve sets the survivors' bits
     const bool hash_early = e->bloom_in_extract && !flush && !jobs && (sh.bloom_file || (extra && extra->external_bloom && extra->bloom.words));
     const uint64_t o_hash = carve(hash_early ? 16ull * N : 0);
+    // single compaction: resolve, the offsets scan and the .index writes in one kernel (chained scan over the tiles)
+    const bool fused_emit = e->fused_emit && !flush && !jobs && !many && !hash_early && !(e->bloom_side && sh.bloom_file);
+    const uint64_t o_scan = carve(fused_emit ? 16ull * res_tiles + 64 : 0);
     int rc = ensure_device(e, &e->ws, &e->ws_cap, off);
     if (rc) return rc;
     rc = ensure_pinned(e, header_bytes + align_up(sizeof(Ctl), 64) + 64 + (n_groups ? 16ull * (n_groups + 1) : 0));
@@ -329,6 +334,8 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     p.ref_reader = ref_reader ? 1 : 0;
     p.fix_index = reinterpret_cast<uint4 *>(ws + o_fix);
     p.hash_rec = hash_early ? reinterpret_cast<uint4 *>(ws + o_hash) : nullptr;
+    p.scan_state = reinterpret_cast<unsigned long long *>(ws + o_scan);
+    p.scan_ticket = reinterpret_cast<uint32_t *>(ws + o_scan + 16ull * res_tiles);
     p.out_data = static_cast<uint8_t *>(out->data);
     p.out_index = static_cast<uint4 *>(out->index);
 
@@ -398,6 +405,7 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
                                                                             reinterpret_cast<const uint32_t *>(e->pin_dev), (uint32_t)(header_bytes / 4));
     launches++;
     if (sh.bloom_file) CU(cudaMemsetAsync(out->bloom, 0, sh.bloom_file, s));
+    if (fused_emit) CU(cudaMemsetAsync(ws + o_scan, 0, 16ull * res_tiles + 64, s));
 
     // ---- K0/K1: prefix, validate, extract (+ conditional redo when a run was truncated)
     const uint32_t g256 = (N + 255) / 256;
@@ -470,8 +478,10 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     uint4 *res = reinterpret_cast<uint4 *>(dst); // the ping-pong buffer that does not hold the merged order
     const bool side_bloom = e->bloom_side && !flush && !jobs && !hash_early && p.bloom.words != nullptr;
     p.bloom_elsewhere = side_bloom ? 1 : 0;
-    if (e->narrow_loads) k_resolve<true><<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, src, res);
-    else k_resolve<false><<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, src, res);
+    if (hash_early) k_resolve<true, false, true><<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, src, res);
+    else if (fused_emit) k_resolve<true, true, false><<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, src, res);
+    else if (e->narrow_loads) k_resolve<true, false, false><<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, src, res);
+    else k_resolve<false, false, false><<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, src, res);
     if (side_bloom) { // fork: the filter is filled on the second stream while this one scans, emits and copies the payload
         CU(cudaEventRecord(e->ev_fork, s));
         CU(cudaStreamWaitEvent(e->s_side, e->ev_fork, 0));
@@ -479,10 +489,13 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
         CU(cudaEventRecord(e->ev_join, e->s_side));
         launches++;
     }
-    k_scan_tiles<<<(uint32_t)res_chunks, 1024, 0, s>>>(p);
-    k_scan_chunks<<<1, 1024, 0, s>>>(p);
-    k_emit<<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, res);
-    launches += 4;
+    if (!fused_emit) {
+        k_scan_tiles<<<(uint32_t)res_chunks, 1024, 0, s>>>(p);
+        k_scan_chunks<<<1, 1024, 0, s>>>(p);
+        k_emit<<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, res);
+        launches += 3;
+    }
+    launches += 1;
     if (n_groups) {
         k_flush_table<<<(uint32_t)((n_groups + 1 + 127) / 128), 128, 0, s>>>(p, res);
         launches++;
@@ -496,8 +509,14 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
             uint64_t grid = (uint64_t)e->sm_count * DBEEL_GT_CTAS;
             if (grid > gather_tiles) grid = gather_tiles;
             k_gather_tma<<<(uint32_t)grid, kGtThreads, kGtSmem, s>>>(p);
+        } else if (e->gather_variant == 3 && al32) { // persistent, next tile's metadata prefetched with cp.async
+            uint64_t grid = (uint64_t)e->sm_count * DBEEL_GP_CTAS;
+            if (grid > gather_tiles) grid = gather_tiles;
+            k_gather_p<<<(uint32_t)grid, kGatherThreads, 0, s>>>(p);
+        } else if (e->gather_variant == 4 && al32) { // k_gather32 + a fifth warp per CTA that only fills the filter
+            k_gather32<true><<<(uint32_t)gather_tiles, kGatherThreads + 32, 0, s>>>(p);
         } else if (e->gather_variant >= 1 && al32) {
-            k_gather32<<<(uint32_t)gather_tiles, kGatherThreads, 0, s>>>(p);
+            k_gather32<false><<<(uint32_t)gather_tiles, kGatherThreads, 0, s>>>(p);
         } else {
             k_gather<<<(uint32_t)gather_tiles, kGatherThreads, 0, s>>>(p);
         }
@@ -1558,6 +1577,7 @@ int dbeel_engine_create(int device, dbeel_engine **out) {
     if (const char *v = getenv("DBEEL_GATHER")) e->gather_variant = atoi(v);
     if (const char *v = getenv("DBEEL_BLOOM_EXTRACT")) e->bloom_in_extract = atoi(v);
     if (const char *v = getenv("DBEEL_BLOOM_SIDE")) e->bloom_side = atoi(v);
+    if (const char *v = getenv("DBEEL_FUSED_EMIT")) e->fused_emit = atoi(v);
     if (cudaStreamCreateWithFlags(&e->s_side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) {

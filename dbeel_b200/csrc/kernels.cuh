@@ -130,6 +130,9 @@ struct Params {
     BloomParams bloom;
     uint4 *hash_rec; // [n_total] {h0, h1} = both SipHash-1-3 values of every entry's key (k_extract), or null: the gather hashes
     uint32_t bloom_elsewhere; // 1: k_bloom_res fills the filter on a second stream, next to the gather (which then skips it)
+    // fused resolve + emit (single jobs): chained scan of the tiles' (bytes, entries), decoupled look-back
+    unsigned long long *scan_state; // [resolve tiles][2]: {status << 62 | bytes, status << 32 | entries}, zeroed per job
+    uint32_t *scan_ticket;          // tiles are numbered in the order their CTAs start
 };
 
 // ------------------------------------------------------------------------------------
@@ -944,8 +947,26 @@ __device__ __forceinline__ void ld_ts(const uint8_t *entry, uint32_t full_size, 
 #ifndef DBEEL_RESOLVE_MINB
 #define DBEEL_RESOLVE_MINB 14 // 14 CTAs of 128 threads per SM = a 36-register cap: 0.249 ms vs 0.256 uncapped (40-46 registers)
 #endif
-template <bool kNarrow>
-__global__ void __launch_bounds__(kResolveThreads, DBEEL_RESOLVE_MINB) k_resolve(Params p, const Rec *m, uint4 *res) {
+constexpr unsigned long long kScanAgg = 1, kScanPrefix = 2; // 0 = nothing published yet
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *q) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(q) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long *q, unsigned long long v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(q), "l"(v) : "memory");
+}
+
+// kFused: the offsets scan and k_emit's writes happen here too -- every tile publishes its (bytes, entries) aggregate, looks
+// back over its predecessors' aggregates / inclusive prefixes (one warp, 32 predecessors per step) and writes its survivors'
+// .index records, source addresses and gather-tile markers directly.  Saves the res[] round trip (2 x 16 B per merged
+// record), two scan kernels and k_emit's launch.  Single jobs only: the grouped paths cut the stream by res[] afterwards.
+#ifndef DBEEL_RESOLVE_FUSED_MINB
+#define DBEEL_RESOLVE_FUSED_MINB 12
+#endif
+template <bool kNarrow, bool kFused, bool kHashRec>
+__global__ void __launch_bounds__(kResolveThreads, kFused ? DBEEL_RESOLVE_FUSED_MINB : DBEEL_RESOLVE_MINB) k_resolve(Params p, const Rec *m, uint4 *res) {
     constexpr int NT = kResolveThreads;
     __shared__ Rec s_rec[NT + 2];
     __shared__ unsigned long long s_entry[NT]; // device address of each record's entry
@@ -955,7 +976,13 @@ __global__ void __launch_bounds__(kResolveThreads, DBEEL_RESOLVE_MINB) k_resolve
     const Ctl *c = p.ctl;
     const uint32_t tid = threadIdx.x;
     const uint32_t span = c->span;
-    const uint32_t i0 = blockIdx.x * NT;
+    __shared__ uint32_t s_tile;
+    if (kFused) { // tiles numbered by starting order: a tile only ever waits for tiles that are already running
+        if (tid == 0) s_tile = atomicAdd(p.scan_ticket, 1u);
+        __syncthreads();
+    }
+    const uint32_t tile_id = kFused ? s_tile : blockIdx.x;
+    const uint32_t i0 = tile_id * NT;
     if (i0 >= span) return;
     const uint32_t skip = c->prefix_len + kWindowBytes;
     const uint32_t i = i0 + tid;
@@ -1019,7 +1046,17 @@ __global__ void __launch_bounds__(kResolveThreads, DBEEL_RESOLVE_MINB) k_resolve
 
     uint32_t keep = 0, ks = 0, fs = 0, wgid = 0;
     unsigned long long src = 0;
-    if (active && !eq_prev) { // head of its group
+    if (p.mode_flush) {
+        // Arrival batches: the winner of a group of equal keys is simply its LAST member (RedBlackTree::set replaces in place,
+        // lib.rs:509-511), and every member knows locally whether it is the last one.  No walk over the group: a hot key of a
+        // Zipf stream fills hundreds of consecutive positions of a memtable, and a head thread stepping through them one
+        // dependent load at a time was 93 % of the flush (10.6 of 11.4 ms for 60 memtables, profiles/r02_cfg5.md).
+        if (active && !eq_next) {
+            keep = 1; // tombstones are ordinary entries of a flush (lsm_tree.rs:790-795)
+            ks = s_ks[tid]; fs = s_fs[tid]; src = s_entry[tid];
+            wgid = cur.w;
+        }
+    } else if (active && !eq_prev) { // head of its group
         uint32_t w = tid; // winner so far, as an index into this tile's shared arrays
         ks = s_ks[tid]; fs = s_fs[tid]; src = s_entry[tid];
         wgid = cur.w;
@@ -1059,33 +1096,127 @@ __global__ void __launch_bounds__(kResolveThreads, DBEEL_RESOLVE_MINB) k_resolve
         bool tomb = fs == ks + 24;
         keep = (keep_tombstones || p.mode_flush || !tomb) ? 1u : 0u;
         // Bloom::set for every entry that is written (lsm_tree.rs:1049-1051), from the hashes k_extract left behind
-        if (keep && p.hash_rec != nullptr && p.bloom.words != nullptr) {
+        if (kHashRec && keep && p.hash_rec != nullptr && p.bloom.words != nullptr) {
             const uint4 hv = __ldg(&p.hash_rec[wgid]);
             uint32_t *words = p.bloom.words;
             bloom_probe_all((uint64_t)hv.x | ((uint64_t)hv.y << 32), (uint64_t)hv.z | ((uint64_t)hv.w << 32), p.bloom.k_num, p.bloom.bits,
                             p.bloom.bits_magic, [words](uint64_t bit) { atomicOr(&words[bit >> 5], 1u << (bit & 31)); });
         }
     }
-    if (i < span) res[i] = make_uint4((uint32_t)src, (uint32_t)(src >> 32), ks, keep ? fs : 0u); // holes: nothing emitted
+    if (!kFused) {
+        if (i < span) res[i] = make_uint4((uint32_t)src, (uint32_t)(src >> 32), ks, keep ? fs : 0u); // holes: nothing emitted
 
-    // tile aggregate (bytes, entries) for the offsets scan
-    unsigned long long vb = keep ? fs : 0ull;
-    uint32_t vc = keep;
+        // tile aggregate (bytes, entries) for the offsets scan
+        unsigned long long vb = keep ? fs : 0ull;
+        uint32_t vc = keep;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        vb += __shfl_xor_sync(0xFFFFFFFFu, vb, o);
-        vc += __shfl_xor_sync(0xFFFFFFFFu, vc, o);
+        for (int o = 16; o; o >>= 1) {
+            vb += __shfl_xor_sync(0xFFFFFFFFu, vb, o);
+            vc += __shfl_xor_sync(0xFFFFFFFFu, vc, o);
+        }
+        __syncthreads(); // s_tlo / s_ks are dead: reuse them as the cross-warp scratch
+        if ((tid & 31) == 0) { s_tlo[tid >> 5] = vb; s_ks[tid >> 5] = vc; }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long tb = 0;
+            uint32_t tc = 0;
+            for (int w = 0; w < NT / 32; w++) { tb += s_tlo[w]; tc += s_ks[w]; }
+            p.tile_bytes[blockIdx.x] = tb;
+            p.tile_count[blockIdx.x] = tc;
+        }
+        return;
     }
-    __syncthreads(); // s_tlo / s_ks are dead: reuse them as the cross-warp scratch
-    if ((tid & 31) == 0) { s_tlo[tid >> 5] = vb; s_ks[tid >> 5] = vc; }
+
+    // ---- fused: in-tile inclusive scan, chained scan over the tiles, then the writes k_emit would do
+    const uint32_t lane = tid & 31, warp = tid >> 5;
+    unsigned long long ib = keep ? fs : 0ull;
+    uint32_t ic = keep;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long xb = __shfl_up_sync(0xFFFFFFFFu, ib, o);
+        const uint32_t xc = __shfl_up_sync(0xFFFFFFFFu, ic, o);
+        if (lane >= (uint32_t)o) { ib += xb; ic += xc; }
+    }
+    __syncthreads(); // s_tlo / s_ks / s_thi are dead: cross-warp scratch
+    if (lane == 31) { s_tlo[warp] = ib; s_ks[warp] = ic; }
     __syncthreads();
-    if (tid == 0) {
-        unsigned long long tb = 0;
-        uint32_t tc = 0;
-        for (int w = 0; w < NT / 32; w++) { tb += s_tlo[w]; tc += s_ks[w]; }
-        p.tile_bytes[blockIdx.x] = tb;
-        p.tile_count[blockIdx.x] = tc;
+    unsigned long long tb = 0, wb = 0;
+    uint32_t tc = 0, wc = 0;
+    for (int w = 0; w < NT / 32; w++) {
+        if ((uint32_t)w < warp) { wb += s_tlo[w]; wc += s_ks[w]; }
+        tb += s_tlo[w];
+        tc += s_ks[w];
     }
+    if (warp == 0) {
+        unsigned long long *mine = p.scan_state + 2ull * tile_id;
+        unsigned long long eb = 0;
+        uint32_t ec = 0;
+        if (tile_id == 0) {
+            if (lane == 0) {
+                st_volatile_u64(mine, (kScanPrefix << 62) | tb);
+                __threadfence();
+                st_volatile_u64(mine + 1, (kScanPrefix << 32) | tc);
+            }
+        } else {
+            if (lane == 0) { // bytes word first, entries word second: a reader that sees the second sees the first
+                st_volatile_u64(mine, (kScanAgg << 62) | tb);
+                __threadfence();
+                st_volatile_u64(mine + 1, (kScanAgg << 32) | tc);
+            }
+            int t = (int)tile_id - 1;
+            while (true) {
+                const int idx = t - (int)lane;
+                unsigned long long vb2 = 0, vc2 = 0, stat = kScanPrefix;
+                if (idx >= 0) {
+                    const unsigned long long *q = p.scan_state + 2ull * (uint32_t)idx;
+                    while (true) { // entries word, then bytes word; both must be at the same stage
+                        vc2 = ld_volatile_u64(q + 1);
+                        __threadfence();
+                        vb2 = ld_volatile_u64(q);
+                        if ((vc2 >> 32) != 0 && (vc2 >> 32) == (vb2 >> 62)) break;
+                    }
+                    stat = vc2 >> 32;
+                }
+                // lanes below the nearest tile that already holds an inclusive prefix add their aggregates, that tile its prefix
+                const uint32_t pm = __ballot_sync(0xFFFFFFFFu, stat == kScanPrefix);
+                const uint32_t first = (uint32_t)__ffs((int)pm) - 1; // pm != 0: lanes with idx < 0 report "prefix" (of nothing)
+                unsigned long long cb = (lane <= first && idx >= 0) ? (vb2 & ((1ull << 62) - 1)) : 0ull;
+                uint32_t cc = (lane <= first && idx >= 0) ? (uint32_t)vc2 : 0u;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    cb += __shfl_xor_sync(0xFFFFFFFFu, cb, o);
+                    cc += __shfl_xor_sync(0xFFFFFFFFu, cc, o);
+                }
+                eb += cb;
+                ec += cc;
+                if (pm) break;
+                t -= 32;
+            }
+            if (lane == 0) {
+                st_volatile_u64(mine, (kScanPrefix << 62) | (eb + tb));
+                __threadfence();
+                st_volatile_u64(mine + 1, (kScanPrefix << 32) | (unsigned long long)(ec + tc));
+            }
+        }
+        if (lane == 0) {
+            s_thi[0] = eb;
+            s_fs[0] = ec;
+            if ((unsigned long long)(tile_id + 1) * NT >= span) { // the last tile holds the totals
+                Ctl *cw = p.ctl;
+                cw->out_data_len = eb + tb;
+                cw->out_items = ec + tc;
+            }
+        }
+    }
+    __syncthreads();
+    if (!keep) return;
+    const unsigned long long off = s_thi[0] + wb + ib - fs; // within this job's .data
+    const uint32_t pos = s_fs[0] + wc + ic - 1;
+    const unsigned long long file_off = off + p.out_offset_base;
+    p.out_index[pos] = make_uint4((uint32_t)file_off, (uint32_t)(file_off >> 32), ks, fs);
+    p.src_ptr[pos] = src;
+    constexpr unsigned long long gt = kGatherTileBytes;
+    for (unsigned long long bq = (off + gt - 1) / gt; bq * gt < off + fs && bq < p.tile_first_n; bq++) p.tile_first[bq] = pos;
 }
 
 // ------------------------------------------------------------------------------------
@@ -1465,8 +1596,17 @@ static_assert(kGatherTileBytes == 32ull * kGatherThreads * kG32Vpt, "gather tile
 #ifndef DBEEL_GATHER32_MINB
 #define DBEEL_GATHER32_MINB (1536 / DBEEL_GATHER_THREADS)
 #endif
-__global__ void __launch_bounds__(kGatherThreads, DBEEL_GATHER32_MINB) k_gather32(Params p) {
-    constexpr int NT = kGatherThreads;
+#ifndef DBEEL_GATHER32W_MINB
+#define DBEEL_GATHER32W_MINB 9
+#endif
+// kBloomWarp: a fifth warp does nothing but the filter -- the tile's keys are hashed WHILE the four copy warps wait for their
+// payload loads, instead of after their stores by the same threads (the fused epilogue is a ~600-instruction dependent chain
+// per entry on 27 of 128 lanes: it lengthens every CTA's life by about a fifth).
+template <bool kBloomWarp>
+__global__ void __launch_bounds__(kGatherThreads + (kBloomWarp ? 32 : 0), kBloomWarp ? DBEEL_GATHER32W_MINB : DBEEL_GATHER32_MINB)
+k_gather32(Params p) {
+    constexpr int NT = kGatherThreads;            // copy threads
+    constexpr int NTA = NT + (kBloomWarp ? 32 : 0); // all threads
     __shared__ unsigned long long s_adj[kGatherMaxEntries]; // entry address minus its tile-relative start
     __shared__ int s_r0[kGatherMaxEntries], s_r1[kGatherMaxEntries];
     __shared__ uint32_t s_ks[kGatherMaxEntries];
@@ -1481,7 +1621,7 @@ __global__ void __launch_bounds__(kGatherThreads, DBEEL_GATHER32_MINB) k_gather3
     const uint32_t e_hi = T0 + kGatherTileBytes < out_len ? p.tile_first[tile_id + 1] : c->out_items - 1;
     const uint32_t ne = e_hi - e_lo + 1; // <= kGatherMaxEntries: every entry is >= 32 bytes
     const bool hash_here = p.bloom.words != nullptr && p.hash_rec == nullptr && !p.bloom_elsewhere;
-    for (uint32_t j = tid; j < ne; j += NT) {
+    for (uint32_t j = tid; j < ne; j += NTA) {
         const uint4 rec = p.out_index[e_lo + j];
         const unsigned long long d0 = ((unsigned long long)rec.x | ((unsigned long long)rec.y << 32)) - p.out_offset_base;
         const long long r0 = (long long)d0 - (long long)T0; // < 0 only for the tile's first entry
@@ -1492,6 +1632,23 @@ __global__ void __launch_bounds__(kGatherThreads, DBEEL_GATHER32_MINB) k_gather3
         if (hash_here) s_ks[j] = rec.z;
     }
     __syncthreads();
+
+    if (kBloomWarp && warp == NT / 32) { // the filter warp: entries whose first byte lies in this tile
+        if (hash_here) {
+            for (uint32_t j = lane; j < ne; j += 32) {
+                const int r0 = s_r0[j];
+                if (r0 < 0 || r0 >= (int)kGatherTileBytes) continue;
+                const uint8_t *key = reinterpret_cast<const uint8_t *>((uintptr_t)(s_adj[j] + (unsigned long long)r0)) + 8;
+                const uint64_t klen = s_ks[j] - 8;
+                uint64_t h0, h1;
+                sip13_pair_vec_u8(p.bloom.sip, klen, [key](uint64_t q) { return ld_u64_unaligned(key + 8 * q); }, &h0, &h1);
+                uint32_t *words = p.bloom.words;
+                bloom_probe_all(h0, h1, p.bloom.k_num, p.bloom.bits, p.bloom.bits_magic,
+                                [words](uint64_t bit) { atomicOr(&words[bit >> 5], 1u << (bit & 31)); });
+            }
+        }
+        return;
+    }
 
     // ---- copy: warp w owns bytes [w * 2 KB, (w + 1) * 2 KB) of the tile, 1 KB (32 lanes x 32 bytes) at a time
     uint8_t *dst_tile = p.out_data + T0;
@@ -1584,7 +1741,7 @@ __global__ void __launch_bounds__(kGatherThreads, DBEEL_GATHER32_MINB) k_gather3
     }
 
     // ---- bloom (fused epilogue), only when k_extract did not hash: entries whose first byte lies in this tile
-    if (hash_here) {
+    if (!kBloomWarp && hash_here) {
         for (uint32_t j = tid; j < ne; j += NT) {
             const int r0 = s_r0[j];
             if (r0 < 0 || r0 >= (int)kGatherTileBytes) continue;
@@ -1883,6 +2040,192 @@ __global__ void __launch_bounds__(kGtThreads, DBEEL_GT_CTAS) k_gather_tma(Params
 #pragma unroll
         for (int k = 0; k < kGtPer; k++) { recA[k] = recB[k]; srcA[k] = srcB[k]; }
     }
+}
+
+// ------------------------------------------------------------------------------------
+// K5, persistent with prefetched metadata (k_gather32's copy, different skeleton).  In k_gather32 a CTA's life is a chain
+// of memory round trips -- tile_first -> out_index / src_ptr -> payload -> boundary / key bytes -- and only the other
+// resident CTAs cover them.  Here a CTA keeps going tile after tile, and the first two links of the NEXT tile's chain run
+// while the current tile is copied: the tile_first pair two tiles ahead travels in registers, the out_index / src_ptr
+// records of the next tile arrive in shared memory through cp.async (LDGSTS: no registers held).  What is left on a
+// tile's critical path is one payload round trip.
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+#ifndef DBEEL_GP_CTAS
+#define DBEEL_GP_CTAS 10
+#endif
+__global__ void __launch_bounds__(kGatherThreads, DBEEL_GP_CTAS) k_gather_p(Params p) {
+    constexpr int NT = kGatherThreads;
+    __shared__ __align__(16) uint4 s_rawi[2][kGatherMaxEntries];
+    __shared__ __align__(8) unsigned long long s_raws[2][kGatherMaxEntries];
+    __shared__ unsigned long long s_adj[kGatherMaxEntries];
+    __shared__ int s_r0[kGatherMaxEntries], s_r1[kGatherMaxEntries];
+    __shared__ uint32_t s_ks[kGatherMaxEntries];
+    const Ctl *c = p.ctl;
+    const unsigned long long out_len = c->out_data_len;
+    const uint32_t out_items = c->out_items;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n_tiles = (uint32_t)((out_len + kGatherTileBytes - 1) / kGatherTileBytes);
+    const uint32_t G = gridDim.x;
+    uint32_t tile = blockIdx.x;
+    if (tile >= n_tiles) return;
+    const bool hash_here = p.bloom.words != nullptr && p.hash_rec == nullptr && !p.bloom_elsewhere;
+
+    auto tf_lo = [&](uint32_t t) -> uint32_t { return t < n_tiles ? __ldg(&p.tile_first[t]) : 0u; };
+    auto tf_ne = [&](uint32_t t, uint32_t lo) -> uint32_t {
+        if (t >= n_tiles) return 0u;
+        const uint32_t hi = t + 1 < n_tiles ? __ldg(&p.tile_first[t + 1]) : out_items - 1;
+        return hi - lo + 1;
+    };
+    auto prefetch = [&](uint32_t buf, uint32_t lo, uint32_t ne) {
+        for (uint32_t j = tid; j < ne; j += NT) {
+            cp_async16(&s_rawi[buf][j], &p.out_index[lo + j]);
+            cp_async8(&s_raws[buf][j], &p.src_ptr[lo + j]);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    uint32_t lo0 = tf_lo(tile), ne0 = tf_ne(tile, lo0);
+    prefetch(0, lo0, ne0);
+    uint32_t lo1 = tf_lo(tile + G), ne1 = tf_ne(tile + G, lo1);
+
+    for (uint32_t q = 0;; q++) {
+        const uint32_t buf = q & 1;
+        const bool has_next = tile + G < n_tiles;
+        prefetch(buf ^ 1, lo1, ne1); // an empty group when there is no next tile
+        const uint32_t lo2 = tf_lo(tile + 2 * G), ne2 = tf_ne(tile + 2 * G, lo2); // consumed one iteration from now
+        asm volatile("cp.async.wait_group 1;" ::: "memory"); // everything but the group just committed has landed
+        __syncthreads();
+
+        const unsigned long long T0 = (unsigned long long)tile * kGatherTileBytes;
+        const uint32_t tile_len = out_len - T0 < kGatherTileBytes ? (uint32_t)(out_len - T0) : (uint32_t)kGatherTileBytes;
+        const uint32_t ne = ne0;
+        for (uint32_t j = tid; j < ne; j += NT) {
+            const uint4 rec = s_rawi[buf][j];
+            const unsigned long long d0 = ((unsigned long long)rec.x | ((unsigned long long)rec.y << 32)) - p.out_offset_base;
+            const long long r0 = (long long)d0 - (long long)T0;
+            const long long r1 = r0 + (long long)rec.w;
+            s_adj[j] = s_raws[buf][j] - (unsigned long long)r0;
+            s_r0[j] = r0 < -0x7FFFFFFFll ? -0x7FFFFFFF : (int)r0;
+            s_r1[j] = r1 > 0x7FFFFFFFll ? 0x7FFFFFFF : (int)r1;
+            if (hash_here) s_ks[j] = rec.z;
+        }
+        __syncthreads();
+
+        // ---- copy (k_gather32's): warp w owns bytes [w * 2 KB, (w + 1) * 2 KB) of the tile, 1 KB at a time
+        uint8_t *dst_tile = p.out_data + T0;
+        const int sub0 = (int)(warp * (uint32_t)(kG32Vpt * 1024));
+        if ((uint32_t)sub0 < tile_len) {
+            uint32_t j = 0;
+            for (uint32_t base = 0; base + 1 < ne; base += 32) {
+                const uint32_t i = base + lane;
+                j += __popc(__ballot_sync(0xFFFFFFFFu, i + 1 < ne && s_r1[i] <= sub0));
+            }
+            uint4 A[kG32Vpt], B[kG32Vpt], C[kG32Vpt];
+            uint32_t sh[kG32Vpt];
+            bool pure[kG32Vpt];
+            const uint32_t lanes_le = 0xFFFFFFFFu >> (31 - lane);
+#pragma unroll
+            for (int k = 0; k < kG32Vpt; k++) {
+                const int cb = sub0 + k * 1024;
+                const int b0 = cb + (int)lane * 32;
+                const uint32_t i = j + lane;
+                const int r1 = i + 1 < ne ? s_r1[i] : 0x7FFFFFFF;
+                const bool ends_here = r1 <= cb + 1024;
+                const uint32_t t = (uint32_t)((ends_here ? r1 : cb + 32) - cb + 31) >> 5;
+                const uint32_t ends = __reduce_or_sync(0xFFFFFFFFu, (ends_here && t < 32) ? (1u << t) : 0u);
+                const uint32_t cnt = __popc(ends & lanes_le);
+                const uint32_t adv = __popc(__ballot_sync(0xFFFFFFFFu, ends_here));
+                const uint32_t e = j + cnt;
+                j += adv;
+                const int r1e = s_r1[e];
+                pure[k] = (uint32_t)b0 + 32 <= tile_len && b0 + 32 <= r1e;
+                const int bl = b0 + 32 <= r1e ? b0 : r1e - 32;
+                const uintptr_t sa = (uintptr_t)(s_adj[e] + (unsigned long long)(long long)bl);
+                sh[k] = (uint32_t)(sa & 15);
+                const uint4 *sv = reinterpret_cast<const uint4 *>(sa - sh[k]);
+                A[k] = __ldg(sv);
+                B[k] = __ldg(sv + 1);
+                C[k] = __ldg(sh[k] ? sv + 2 : sv + 1);
+            }
+#pragma unroll
+            for (int k = 0; k < kG32Vpt; k++) {
+                if (pure[k]) {
+                    uint32_t o[8];
+                    realign32(A[k], B[k], C[k], sh[k], o);
+                    stg256(dst_tile + sub0 + k * 1024 + (int)lane * 32, o);
+                }
+            }
+        }
+
+        // ---- the 32-byte block that holds the last byte of entry j: its two halves
+        for (uint32_t j = tid; j < ne; j += NT) {
+            const int r1 = s_r1[j];
+            if (r1 <= 0 || (r1 & 31) == 0 || r1 > (int)tile_len) continue;
+            const bool has_nx = j + 1 < ne;
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const uint32_t b0 = ((uint32_t)r1 & ~31u) + 16u * half;
+                if (b0 >= tile_len) continue;
+                const int t = r1 - (int)b0;
+                uint4 o;
+                if (t >= 16) {
+                    o = ld16_any((uintptr_t)(s_adj[j] + b0), 16);
+                } else if (t <= 0) {
+                    if (!has_nx) continue;
+                    o = ld16_any((uintptr_t)(s_adj[j + 1] + b0), 16);
+                } else {
+                    o = ld16_any((uintptr_t)(s_adj[j] + b0), (uint32_t)t);
+                    if (b0 + 16 <= tile_len) {
+                        const uint4 H = ld16_any((uintptr_t)(s_adj[j + 1] + (unsigned long long)(long long)r1), 16);
+                        const uint4 HU = realign16_sel(make_uint4(0, 0, 0, 0), H, 16 - (uint32_t)t);
+                        const uint32_t wfull = (uint32_t)t >> 2, bits = ((uint32_t)t & 3) * 8;
+                        const uint32_t mmix = bits ? (0xFFFFFFFFu >> (32 - bits)) : 0u;
+                        uint32_t ow[4] = {o.x, o.y, o.z, o.w}, hw[4] = {HU.x, HU.y, HU.z, HU.w};
+#pragma unroll
+                        for (uint32_t qq = 0; qq < 4; qq++) {
+                            const uint32_t mk = qq < wfull ? 0xFFFFFFFFu : (qq == wfull ? mmix : 0u);
+                            ow[qq] = (ow[qq] & mk) | (hw[qq] & ~mk);
+                        }
+                        o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                    } else {
+                        const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+                        for (int b = 0; b < t; b++) dst_tile[b0 + b] = (uint8_t)(ow[b >> 2] >> ((b & 3) * 8));
+                        continue;
+                    }
+                }
+                reinterpret_cast<uint4 *>(dst_tile)[b0 >> 4] = o;
+            }
+        }
+
+        // ---- bloom (fused epilogue) unless it runs elsewhere
+        if (hash_here) {
+            for (uint32_t j = tid; j < ne; j += NT) {
+                const int r0 = s_r0[j];
+                if (r0 < 0 || r0 >= (int)kGatherTileBytes) continue;
+                const uint8_t *key = reinterpret_cast<const uint8_t *>((uintptr_t)(s_adj[j] + (unsigned long long)r0)) + 8;
+                const uint64_t klen = s_ks[j] - 8;
+                uint64_t h0, h1;
+                sip13_pair_vec_u8(p.bloom.sip, klen, [key](uint64_t qq) { return ld_u64_unaligned(key + 8 * qq); }, &h0, &h1);
+                uint32_t *words = p.bloom.words;
+                bloom_probe_all(h0, h1, p.bloom.k_num, p.bloom.bits, p.bloom.bits_magic,
+                                [words](uint64_t bit) { atomicOr(&words[bit >> 5], 1u << (bit & 31)); });
+            }
+        }
+
+        if (!has_next) break;
+        __syncthreads(); // s_adj / s_r0 / s_r1 and raw buffer `buf` are free again
+        tile += G;
+        lo0 = lo1; ne0 = ne1;
+        lo1 = lo2; ne1 = ne2;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // Job header down / control block up without a copy engine: the pinned block is mapped into the GPU's address space.

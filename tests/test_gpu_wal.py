@@ -109,3 +109,29 @@ def test_device_resident_log(engine):
     # and the same bytes the ordinary flush of the same arrivals produces
     fd, fi, fn = engine.flush(sstable.build_run(ents))
     assert fn == n and np.array_equal(fd, ed) and np.array_equal(fi, ei)
+
+
+def test_engines_give_their_device_memory_back():
+    """Every grow-only scratch buffer of an engine (compaction workspace, WAL replay tables, routing tables, staging) is freed
+    by dbeel_engine_destroy: create / use / destroy in a loop must not move cudaMemGetInfo's free figure."""
+    import torch
+    from dbeel_b200 import workloads as W
+    rng = np.random.default_rng(2)
+    ents = [(b"k%06d" % int(rng.integers(0, 3000)), bytes(rng.integers(0, 256, 200, dtype=np.uint8)), BASE_TS + j) for j in range(6000)]
+    wal = sstable.build_wal(ents)
+    runs = W.make_merge_runs(W.scaled(W.CFG2, 5000))
+
+    def cycle():
+        eng = capi.Engine(0)
+        eng.wal_flush(wal, capacity=8192)
+        eng.compact(runs, False, seed=bytes(32))
+        eng.close()
+
+    cycle()  # first use may load modules / grow the context's own pools
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info(0)
+    for _ in range(5):
+        cycle()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info(0)
+    assert free0 - free1 < (8 << 20), f"device memory leaked: {free0 - free1} bytes over 5 engine lifetimes"
