@@ -19,6 +19,7 @@
 
 #include "../../include/dbeel_compact.h"
 #include "kernels.cuh"
+#include "merge_final.cuh"
 #include "lookup.cuh"
 #include "route.cuh"
 #include "wal.cuh"
@@ -81,6 +82,11 @@ struct dbeel_engine {
                                 // filter pass just moves in front of k_emit: +0.16 ms per job); 0 = the gather's fused epilogue
     cudaStream_t s_side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int fused_final = 1;        // DBEEL_FUSED_FINAL: 1 = last merge level + resolve + offsets scan + .index writes in one persistent kernel
+                                // (k_merge_final, single compactions), 0 = round 1's five kernels
+    int fin_ctas_per_sm = 0;    // co-resident k_merge_final CTAs per SM (occupancy query at engine creation): its chained scan needs them all resident
+    int pdl = 0;                // DBEEL_PDL: 1 = the job's kernels are launched with programmatic stream serialization (griddepcontrol)
+    int stage_events = 1;       // DBEEL_STAGE_EVENTS: 0 = no per-stage event records inside a job (stage_ms read 0)
     int bloom_in_extract = 0;   // DBEEL_BLOOM_EXTRACT: 1 = k_extract hashes, k_resolve sets the bits (measured slower: DESIGN.md); 0 = the gather's fused epilogue
 };
 
@@ -137,6 +143,23 @@ void default_opts(dbeel_compact_opts *o) {
     o->bloom_min_size = DBEEL_DEFAULT_BLOOM_MIN_SIZE;
     o->bloom_fp = DBEEL_DEFAULT_BLOOM_FP;
     o->bloom_seed = nullptr;
+}
+
+// Kernel launch with (optionally) the programmatic-stream-serialization attribute: the kernel may be scheduled while its
+// predecessor in the stream drains; every kernel starts with griddepcontrol.wait, so stream order is kept (kernels.cuh).
+template <typename... KArgs, typename... Args>
+void launch_k(const dbeel_engine *e, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = e->pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 struct JobShape {
@@ -287,9 +310,10 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     uint64_t o_seg[kMaxLevels + 1], o_tb[kMaxLevels];
     for (uint32_t l = 0; l <= levels; l++) o_seg[l] = carve(sizeof(Seg) * p.nseg[l]);
     for (uint32_t l = 0; l < levels; l++) o_tb[l] = carve(4ull * (p.nseg[l + 1] + 1));
-    const uint64_t tiles_ub = (uint64_t)(N + kMergeTile - 1) / kMergeTile + (p.nseg[0] + 1) / 2;
+    const uint64_t tiles_ub = (uint64_t)(N + kFinNominal - 1) / kFinNominal + (p.nseg[0] + 1) / 2; // kFinNominal < kMergeTile: covers both
     const uint64_t bounds_ub = tiles_ub + (p.nseg[0] + 1) / 2 + 1;
     const uint64_t o_part = carve(4 * bounds_ub);
+    const uint64_t o_pext = carve(4 * bounds_ub);
     const uint64_t res_tiles = (uint64_t)(N + kResolveThreads - 1) / kResolveThreads;
     const uint64_t o_tbytes = carve(res_tiles * 8), o_tcount = carve(res_tiles * 4);
     const uint64_t res_chunks = (res_tiles + 1023) / 1024;
@@ -307,7 +331,13 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     const uint64_t o_hash = carve(hash_early ? 16ull * N : 0);
     // single compaction: resolve, the offsets scan and the .index writes in one kernel (chained scan over the tiles)
     const bool fused_emit = e->fused_emit && !flush && !jobs && !many && !hash_early && !(e->bloom_side && sh.bloom_file);
-    const uint64_t o_scan = carve(fused_emit ? 16ull * res_tiles + 64 : 0);
+    // single compaction: the last merge level, resolve, the offsets scan and the .index writes in one persistent kernel
+    const bool fused_final = e->fused_final && e->fin_ctas_per_sm > 0 && !flush && !jobs && !many && !hash_early && !fused_emit && levels >= 1 &&
+                             !(e->bloom_side && sh.bloom_file);
+    const uint64_t fin_tiles_ub = (uint64_t)(N + kFinNominal - 1) / kFinNominal + 1;
+    p.fin_tile = fused_final ? (uint32_t)kFinNominal : 0u;
+    const uint64_t scan_bytes = fused_emit ? 16ull * res_tiles + 64 : (fused_final ? 16ull * fin_tiles_ub + 64 : 0);
+    const uint64_t o_scan = carve(scan_bytes);
     int rc = ensure_device(e, &e->ws, &e->ws_cap, off);
     if (rc) return rc;
     rc = ensure_pinned(e, header_bytes + align_up(sizeof(Ctl), 64) + 64 + (n_groups ? 16ull * (n_groups + 1) : 0));
@@ -321,6 +351,7 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     for (uint32_t l = 0; l <= levels; l++) p.seg[l] = reinterpret_cast<Seg *>(ws + o_seg[l]);
     for (uint32_t l = 0; l < levels; l++) p.tile_base[l] = reinterpret_cast<uint32_t *>(ws + o_tb[l]);
     p.part = reinterpret_cast<uint32_t *>(ws + o_part);
+    p.part_ext = reinterpret_cast<uint32_t *>(ws + o_pext);
     p.tile_bytes = reinterpret_cast<unsigned long long *>(ws + o_tbytes);
     p.tile_count = reinterpret_cast<uint32_t *>(ws + o_tcount);
     p.chunk_bytes = reinterpret_cast<unsigned long long *>(ws + o_cbytes);
@@ -401,87 +432,100 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     // of the pipelined host path is in flight there (measured: every partition's kernels waited for the previous
     // partition's 200 MB D2H).  The compute stream carries kernels and event records only.
     if (record_start) CU(cudaEventRecord(e->ev[EV_START], s)); // ms_total covers the header upload and the filter's memset too
-    k_copy_words<<<(uint32_t)((header_bytes / 4 + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint32_t *>(ws),
-                                                                            reinterpret_cast<const uint32_t *>(e->pin_dev), (uint32_t)(header_bytes / 4));
+    launch_k(e, k_copy_words, (uint32_t)((header_bytes / 4 + 255) / 256), 256, 0, s, reinterpret_cast<uint32_t *>(ws),
+             reinterpret_cast<const uint32_t *>(e->pin_dev), (uint32_t)(header_bytes / 4));
     launches++;
     if (sh.bloom_file) CU(cudaMemsetAsync(out->bloom, 0, sh.bloom_file, s));
-    if (fused_emit) CU(cudaMemsetAsync(ws + o_scan, 0, 16ull * res_tiles + 64, s));
+    if (scan_bytes) CU(cudaMemsetAsync(ws + o_scan, 0, scan_bytes, s));
 
     // ---- K0/K1: prefix, validate, extract (+ conditional redo when a run was truncated)
     const uint32_t g256 = (N + 255) / 256;
     const uint32_t gext = (N + 256 * kExtractEPT - 1) / (256 * kExtractEPT);
     auto launch_extract = [&](uint32_t grid, int mode) {
-        if (ref_reader && hash_early) k_extract<true, true, true><<<grid, 256, 0, s>>>(p, mode);
-        else if (ref_reader) k_extract<true, true, false><<<grid, 256, 0, s>>>(p, mode);
-        else if (hash_early) k_extract<true, false, true><<<grid, 256, 0, s>>>(p, mode);
-        else if (e->narrow_loads) k_extract<true, false, false><<<grid, 256, 0, s>>>(p, mode);
-        else k_extract<false, false, false><<<grid, 256, 0, s>>>(p, mode);
+        if (ref_reader && hash_early) launch_k(e, k_extract<true, true, true>, grid, 256, 0, s, p, mode);
+        else if (ref_reader) launch_k(e, k_extract<true, true, false>, grid, 256, 0, s, p, mode);
+        else if (hash_early) launch_k(e, k_extract<true, false, true>, grid, 256, 0, s, p, mode);
+        else if (e->narrow_loads) launch_k(e, k_extract<true, false, false>, grid, 256, 0, s, p, mode);
+        else launch_k(e, k_extract<false, false, false>, grid, 256, 0, s, p, mode);
     };
     if (flush) {
-        k_flush_prefix_init<<<1, 1, 0, s>>>(p);
-        k_flush_prefix<<<g256, 256, 0, s>>>(p);
+        launch_k(e, k_flush_prefix_init, 1, 1, 0, s, p);
+        launch_k(e, k_flush_prefix, g256, 256, 0, s, p);
         launch_extract(gext, 0);
-        k_plan<<<1, 1024, 0, s>>>(p);
-        k_block_sort<<<p.nseg[0], kMergeThreads, 0, s>>>(p);
+        launch_k(e, k_plan, 1, 1024, 0, s, p);
+        launch_k(e, k_block_sort, p.nseg[0], kMergeThreads, 0, s, p);
     } else {
-        k_common_prefix<<<1, 32, 0, s>>>(p, 0);
+        launch_k(e, k_common_prefix, 1, 32, 0, s, p, 0);
         launch_extract(gext, 0);
         if (ref_reader) { // all four are no-ops unless an index record disagrees with its .data (lsm_tree.rs:1158-1170)
-            k_ref_repair<<<n_runs, 1024, 0, s>>>(p);
-            k_ref_reset<<<1, 256, 0, s>>>(p);
-            k_common_prefix<<<1, 32, 0, s>>>(p, 2);
+            launch_k(e, k_ref_repair, n_runs, 1024, 0, s, p);
+            launch_k(e, k_ref_reset, 1, 256, 0, s, p);
+            launch_k(e, k_common_prefix, 1, 32, 0, s, p, 2);
             launch_extract(gext < 592 ? gext : 592, 2);
             launches += 4;
         }
-        k_common_prefix<<<1, 32, 0, s>>>(p, 1); // both no-ops unless a run was truncated
+        launch_k(e, k_common_prefix, 1, 32, 0, s, p, 1); // both no-ops unless a run was truncated
         launch_extract(gext < 592 ? gext : 592, 1);
-        k_plan<<<1, 1024, 0, s>>>(p);
+        launch_k(e, k_plan, 1, 1024, 0, s, p);
     }
     launches += 5;
     if (!flush && (o->flags & DBEEL_FLAG_VERIFY_SORTED)) {
-        k_verify_sorted<<<g256, 256, 0, s>>>(p);
+        launch_k(e, k_verify_sorted, g256, 256, 0, s, p);
         launches++;
     }
-    CU(cudaEventRecord(e->ev[EV_EXTRACT], s));
+    const bool stage_ev = e->stage_events != 0;
+    if (stage_ev) CU(cudaEventRecord(e->ev[EV_EXTRACT], s));
 
     // ---- K2/K3: merge levels, ping-pong between rec_a and rec_b
     const Rec *src = p.rec_a;
     Rec *dst = p.rec_b;
+    if (sh.bloom_file) { // independent of everything else: its launch overlaps the merges
+        launch_k(e, k_bloom_frame, 1, 1, 0, s, static_cast<uint8_t *>(out->bloom), sh.bloom_words, p.bloom);
+        launches++;
+    }
     for (uint32_t l = 0; l < levels; l++) {
         uint32_t pairs = p.nseg[l + 1];
-        uint64_t t_ub = (uint64_t)(N + kMergeTile - 1) / kMergeTile + pairs;
+        const bool last_fused = fused_final && l + 1 == levels;
+        const uint64_t tl = last_fused ? kFinNominal : kMergeTile;
+        uint64_t t_ub = (uint64_t)(N + tl - 1) / tl + pairs;
         uint64_t b_ub = t_ub + pairs;
-        k_merge_partition<<<(uint32_t)((b_ub + 7) / 8), kPartitionThreads, 0, s>>>(p, l, src); // one warp per boundary
-        if (e->merge_variant == 0) { // one CTA per tile, plain loads (kept as the A/B baseline of the TMA kernel)
-            k_merge<<<(uint32_t)t_ub, kMergeThreads, 0, s>>>(p, l, src, dst);
+        if (last_fused && stage_ev) CU(cudaEventRecord(e->ev[EV_MERGE], s)); // the fused last level is booked under ms_resolve
+        launch_k(e, k_merge_partition, (uint32_t)((b_ub + 7) / 8), kPartitionThreads, 0, s, p, l, src); // one warp per boundary
+        if (last_fused) { // persistent; merged tile -> resolve -> chained scan -> .index, all from shared memory
+            uint64_t grid = (uint64_t)e->sm_count * e->fin_ctas_per_sm;
+            if (grid > t_ub) grid = t_ub;
+            if (e->narrow_loads) launch_k(e, k_merge_final<true>, (uint32_t)grid, kFinThreads, kFinSmem, s, p, l, src);
+            else launch_k(e, k_merge_final<false>, (uint32_t)grid, kFinThreads, kFinSmem, s, p, l, src);
+        } else if (e->merge_variant == 0) { // one CTA per tile, plain loads (kept as the A/B baseline of the TMA kernel)
+            launch_k(e, k_merge, (uint32_t)t_ub, kMergeThreads, 0, s, p, l, src, dst);
         } else { // persistent, TMA bulk loads / stores + mbarrier
             uint64_t grid = (uint64_t)e->sm_count * kMergeCtasPerSM;
             if (grid > t_ub) grid = t_ub;
-            k_merge_tma<<<(uint32_t)grid, kMergeThreads, 2 * kMergeBufRecs * sizeof(Rec), s>>>(p, l, src, dst);
+            launch_k(e, k_merge_tma, (uint32_t)grid, kMergeThreads, 2 * kMergeBufRecs * sizeof(Rec), s, p, l, src, dst);
         }
         launches += 2;
+        if (last_fused) break; // src stays the last level's input: nothing was written to dst
         const Rec *t = src;
         src = dst;
         dst = const_cast<Rec *>(t);
     }
-    CU(cudaEventRecord(e->ev[EV_MERGE], s));
+    if (!fused_final && stage_ev) CU(cudaEventRecord(e->ev[EV_MERGE], s));
 
     // ---- K4: resolve + scan + .index
-    if (sh.bloom_file) {
-        k_bloom_frame<<<1, 1, 0, s>>>(static_cast<uint8_t *>(out->bloom), sh.bloom_words, p.bloom);
-        launches++;
-    }
     if (jobs) {
-        k_bloom_frames<<<(extra->n_jobs + 127) / 128, 128, 0, s>>>(p.groups, extra->n_jobs);
+        launch_k(e, k_bloom_frames, (extra->n_jobs + 127) / 128, 128, 0, s, p.groups, extra->n_jobs);
         launches++;
     }
     uint4 *res = reinterpret_cast<uint4 *>(dst); // the ping-pong buffer that does not hold the merged order
     const bool side_bloom = e->bloom_side && !flush && !jobs && !hash_early && p.bloom.words != nullptr;
     p.bloom_elsewhere = side_bloom ? 1 : 0;
-    if (hash_early) k_resolve<true, false, true><<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, src, res);
-    else if (fused_emit) k_resolve<true, true, false><<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, src, res);
-    else if (e->narrow_loads) k_resolve<true, false, false><<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, src, res);
-    else k_resolve<false, false, false><<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, src, res);
+    if (!fused_final) {
+        if (hash_early) launch_k(e, k_resolve<true, false, true>, (uint32_t)res_tiles, kResolveThreads, 0, s, p, src, res);
+        else if (fused_emit) launch_k(e, k_resolve<true, true, false>, (uint32_t)res_tiles, kResolveThreads, 0, s, p, src, res);
+        else if (e->narrow_loads) launch_k(e, k_resolve<true, false, false>, (uint32_t)res_tiles, kResolveThreads, 0, s, p, src, res);
+        else launch_k(e, k_resolve<false, false, false>, (uint32_t)res_tiles, kResolveThreads, 0, s, p, src, res);
+        launches += 1;
+    }
     if (side_bloom) { // fork: the filter is filled on the second stream while this one scans, emits and copies the payload
         CU(cudaEventRecord(e->ev_fork, s));
         CU(cudaStreamWaitEvent(e->s_side, e->ev_fork, 0));
@@ -489,18 +533,17 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
         CU(cudaEventRecord(e->ev_join, e->s_side));
         launches++;
     }
-    if (!fused_emit) {
-        k_scan_tiles<<<(uint32_t)res_chunks, 1024, 0, s>>>(p);
-        k_scan_chunks<<<1, 1024, 0, s>>>(p);
-        k_emit<<<(uint32_t)res_tiles, kResolveThreads, 0, s>>>(p, res);
+    if (!fused_emit && !fused_final) {
+        launch_k(e, k_scan_tiles, (uint32_t)res_chunks, 1024, 0, s, p);
+        launch_k(e, k_scan_chunks, 1, 1024, 0, s, p);
+        launch_k(e, k_emit, (uint32_t)res_tiles, kResolveThreads, 0, s, p, res);
         launches += 3;
     }
-    launches += 1;
     if (n_groups) {
-        k_flush_table<<<(uint32_t)((n_groups + 1 + 127) / 128), 128, 0, s>>>(p, res);
+        launch_k(e, k_flush_table, (uint32_t)((n_groups + 1 + 127) / 128), 128, 0, s, p, res);
         launches++;
     }
-    CU(cudaEventRecord(e->ev[EV_RESOLVE], s));
+    if (stage_ev) CU(cudaEventRecord(e->ev[EV_RESOLVE], s));
 
     // ---- K5: gather + bloom (fused epilogue)
     if (gather_tiles) {
@@ -508,26 +551,28 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
         if (e->gather_variant == 2 && al32) { // persistent, payload staged through shared memory by the bulk-copy engine
             uint64_t grid = (uint64_t)e->sm_count * DBEEL_GT_CTAS;
             if (grid > gather_tiles) grid = gather_tiles;
-            k_gather_tma<<<(uint32_t)grid, kGtThreads, kGtSmem, s>>>(p);
+            launch_k(e, k_gather_tma, (uint32_t)grid, kGtThreads, kGtSmem, s, p);
         } else if (e->gather_variant == 3 && al32) { // persistent, next tile's metadata prefetched with cp.async
             uint64_t grid = (uint64_t)e->sm_count * DBEEL_GP_CTAS;
             if (grid > gather_tiles) grid = gather_tiles;
-            k_gather_p<<<(uint32_t)grid, kGatherThreads, 0, s>>>(p);
+            launch_k(e, k_gather_p, (uint32_t)grid, kGatherThreads, 0, s, p);
         } else if (e->gather_variant == 4 && al32) { // k_gather32 + a fifth warp per CTA that only fills the filter
-            k_gather32<true><<<(uint32_t)gather_tiles, kGatherThreads + 32, 0, s>>>(p);
-        } else if (e->gather_variant >= 1 && al32) {
-            k_gather32<false><<<(uint32_t)gather_tiles, kGatherThreads, 0, s>>>(p);
+            launch_k(e, k_gather32<true, false>, (uint32_t)gather_tiles, kGatherThreads + 32, 0, s, p);
+        } else if (e->gather_variant == 5 && al32) { // k_gather32, every warp does the whole epilogue of its own entries (round 2 baseline)
+            launch_k(e, k_gather32<false, false>, (uint32_t)gather_tiles, kGatherThreads, 0, s, p);
+        } else if (e->gather_variant >= 1 && al32) { // k_gather32, boundary blocks and filter on different warps
+            launch_k(e, k_gather32<false, true>, (uint32_t)gather_tiles, kGatherThreads, 0, s, p);
         } else {
-            k_gather<<<(uint32_t)gather_tiles, kGatherThreads, 0, s>>>(p);
+            launch_k(e, k_gather, (uint32_t)gather_tiles, kGatherThreads, 0, s, p);
         }
     }
     launches++;
     if (jobs) { // per-job filters: their own pass over the output entries
-        k_bloom_many<<<g256, 256, 0, s>>>(p);
+        launch_k(e, k_bloom_many, g256, 256, 0, s, p);
         launches++;
     }
     if (n_groups) { // only now may the .index offsets become file-relative: the gather kernel reads them as stream offsets
-        k_rebase_index<<<g256, 256, 0, s>>>(p);
+        launch_k(e, k_rebase_index, g256, 256, 0, s, p);
         launches++;
     }
     if (side_bloom) CU(cudaStreamWaitEvent(s, e->ev_join, 0)); // join: the job ends when both streams are done
@@ -539,9 +584,9 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     Ctl *hc = reinterpret_cast<Ctl *>(e->pin + header_bytes);
     const uint64_t o_hmt = header_bytes + align_up(sizeof(Ctl), 64);
     unsigned long long *hmt = reinterpret_cast<unsigned long long *>(e->pin + o_hmt);
-    k_publish<<<1, 256, 0, s>>>(reinterpret_cast<uint32_t *>(e->pin_dev + header_bytes), reinterpret_cast<const uint32_t *>(p.ctl),
-                                (uint32_t)(sizeof(Ctl) / 4), reinterpret_cast<uint32_t *>(e->pin_dev + o_hmt),
-                                reinterpret_cast<const uint32_t *>(p.mem_table), n_groups ? (uint32_t)(4 * (n_groups + 1)) : 0u);
+    launch_k(e, k_publish, 1, 256, 0, s, reinterpret_cast<uint32_t *>(e->pin_dev + header_bytes), reinterpret_cast<const uint32_t *>(p.ctl),
+             (uint32_t)(sizeof(Ctl) / 4), reinterpret_cast<uint32_t *>(e->pin_dev + o_hmt),
+             reinterpret_cast<const uint32_t *>(p.mem_table), n_groups ? (uint32_t)(4 * (n_groups + 1)) : 0u);
     launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s));
@@ -553,10 +598,12 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     st.runs_truncated = hc->runs_truncated;
     st.index_repaired = (hc->flags & kFlagRepaired) ? 1 : 0;
     if (record_start) cudaEventElapsedTime(&st.ms_total, e->ev[EV_START], e->ev[EV_GATHER]);
-    if (record_start) cudaEventElapsedTime(&st.ms_extract, e->ev[EV_START], e->ev[EV_EXTRACT]);
-    cudaEventElapsedTime(&st.ms_merge, e->ev[EV_EXTRACT], e->ev[EV_MERGE]);
-    cudaEventElapsedTime(&st.ms_resolve, e->ev[EV_MERGE], e->ev[EV_RESOLVE]);
-    cudaEventElapsedTime(&st.ms_gather, e->ev[EV_RESOLVE], e->ev[EV_GATHER]);
+    if (stage_ev) {
+        if (record_start) cudaEventElapsedTime(&st.ms_extract, e->ev[EV_START], e->ev[EV_EXTRACT]);
+        cudaEventElapsedTime(&st.ms_merge, e->ev[EV_EXTRACT], e->ev[EV_MERGE]);
+        cudaEventElapsedTime(&st.ms_resolve, e->ev[EV_MERGE], e->ev[EV_RESOLVE]);
+        cudaEventElapsedTime(&st.ms_gather, e->ev[EV_RESOLVE], e->ev[EV_GATHER]);
+    }
     if (hc->flags & (kFlagUnsorted | kFlagVerifyFailed))
         return fail(e, DBEEL_ERR_UNSORTED_RUN, "an input run is not strictly ascending by key");
     if (hc->out_data_len > sh.data_total) // only possible with a caller-supplied payload bound (sparse batches)
@@ -1578,6 +1625,22 @@ int dbeel_engine_create(int device, dbeel_engine **out) {
     if (const char *v = getenv("DBEEL_BLOOM_EXTRACT")) e->bloom_in_extract = atoi(v);
     if (const char *v = getenv("DBEEL_BLOOM_SIDE")) e->bloom_side = atoi(v);
     if (const char *v = getenv("DBEEL_FUSED_EMIT")) e->fused_emit = atoi(v);
+    if (const char *v = getenv("DBEEL_FUSED_FINAL")) e->fused_final = atoi(v);
+    if (const char *v = getenv("DBEEL_PDL")) e->pdl = atoi(v);
+    if (const char *v = getenv("DBEEL_STAGE_EVENTS")) e->stage_events = atoi(v);
+    {
+        int nb_t = 0, nb_f = 0;
+        if (cudaFuncSetAttribute(k_merge_final<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinSmem) == cudaSuccess &&
+            cudaFuncSetAttribute(k_merge_final<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinSmem) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_t, k_merge_final<true>, kFinThreads, kFinSmem) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_f, k_merge_final<false>, kFinThreads, kFinSmem) == cudaSuccess) {
+            e->fin_ctas_per_sm = std::min(std::min(nb_t, nb_f), (int)DBEEL_FIN_CTAS);
+        } else {
+            cudaGetLastError();
+            e->fin_ctas_per_sm = 0; // the five-kernel path
+        }
+        if (const char *v = getenv("DBEEL_FIN_CTAS_RT")) e->fin_ctas_per_sm = std::min(e->fin_ctas_per_sm, std::max(1, atoi(v)));
+    }
     if (cudaStreamCreateWithFlags(&e->s_side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) {

@@ -131,9 +131,19 @@ struct Params {
     uint4 *hash_rec; // [n_total] {h0, h1} = both SipHash-1-3 values of every entry's key (k_extract), or null: the gather hashes
     uint32_t bloom_elsewhere; // 1: k_bloom_res fills the filter on a second stream, next to the gather (which then skips it)
     // fused resolve + emit (single jobs): chained scan of the tiles' (bytes, entries), decoupled look-back
+    uint32_t fin_tile;   // k_merge_final: nominal records per tile of the LAST level (< kMergeTile: room for the extensions), 0 = off
+    uint32_t *part_ext;  // [boundaries of the last level] records with the boundary's key that follow it in A (bits 0-7) and B (8-15)
     unsigned long long *scan_state; // [resolve tiles][2]: {status << 62 | bytes, status << 32 | entries}, zeroed per job
     uint32_t *scan_ticket;          // tiles are numbered in the order their CTAs start
 };
+
+// ------------------------------------------------------------------------------------
+// Programmatic dependent launch (sm_90+).  Every kernel of a job starts with trigger + wait: the trigger lets the NEXT kernel
+// of the stream be scheduled while this one drains (its CTAs become resident as slots free up, launch latency and prologue
+// hidden), the wait blocks until every earlier kernel has completed and flushed -- so ordering and visibility are exactly
+// those of plain stream order.  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------
 // small load helpers
@@ -284,6 +294,8 @@ __device__ __forceinline__ bool safe_key(const RunDesc &rd, uint32_t i, const ui
 }
 
 __global__ void k_common_prefix(Params p, int mode) {
+    pdl_trigger();
+    pdl_wait();
     Ctl *c = p.ctl;
     if (mode == 1 && !(c->flags & kFlagTruncated)) return;
     if (mode == 2 && !(c->flags & kFlagRepaired)) return;
@@ -354,6 +366,8 @@ constexpr int kExtractEPT = DBEEL_EXTRACT_EPT; // entries per thread = independe
 // validation again, only after a repair.
 template <bool kNarrow, bool kRef, bool kHash>
 __global__ void __launch_bounds__(256, kRef ? 3 : DBEEL_EXTRACT_MINB) k_extract(Params p, int mode) {
+    pdl_trigger();
+    pdl_wait();
     auto ldu = [](const uint8_t *q) { return kNarrow ? ld_u64_unaligned_narrow(q) : ld_u64_unaligned(q); };
     Ctl *c = p.ctl;
     if (mode == 1 && !(c->flags & kFlagTruncated)) return;
@@ -479,6 +493,8 @@ __device__ __forceinline__ void block_excl_scan_1024(unsigned long long &vb, uin
 // K1b: per-run valid counts -> segment tables of every merge level (one CTA of 1024 threads).
 
 __global__ void __launch_bounds__(1024) k_plan(Params p) {
+    pdl_trigger();
+    pdl_wait();
     // One CTA: level-0 segments in parallel, then level after level (segment l+1 = a pair of level l; the exclusive scan of
     // the pairs' tile counts is a block scan carried over chunks of 1024 pairs).  Batches hold up to 2^24 leaf segments.
     __shared__ unsigned long long s_b[32];
@@ -553,7 +569,8 @@ __global__ void __launch_bounds__(1024) k_plan(Params p) {
                 const uint32_t blen = (2 * j + 1 < p.nseg[l]) ? p.seg[l][2 * j + 1].len : 0;
                 p.seg[l + 1][j].start = a.start;
                 p.seg[l + 1][j].len = a.len + blen;
-                tiles = (a.len + blen + kMergeTile - 1) / kMergeTile;
+                const uint32_t tl = (p.fin_tile && l + 1 == p.n_levels) ? p.fin_tile : (uint32_t)kMergeTile;
+                tiles = (a.len + blen + tl - 1) / tl;
             }
             unsigned long long vb = 0, tb;
             uint32_t vc = tiles, tc;
@@ -579,6 +596,8 @@ __global__ void __launch_bounds__(1024) k_plan(Params p) {
 // produced by an in-CTA merge sort of kMergeTile-record (1792) tiles ordered by (key, arrival).
 
 __global__ void k_flush_prefix_init(Params p) {
+    pdl_trigger();
+    pdl_wait();
     if (threadIdx.x || blockIdx.x) return;
     Ctl *c = p.ctl;
     const uint8_t *ptr;
@@ -593,6 +612,8 @@ __global__ void k_flush_prefix_init(Params p) {
 }
 
 __global__ void __launch_bounds__(256) k_flush_prefix(Params p) {
+    pdl_trigger();
+    pdl_wait();
     Ctl *c = p.ctl;
     uint32_t g = blockIdx.x * 256u + threadIdx.x;
     uint32_t L = c->prefix_len; // only ever shrinks; a stale (larger) value is still an upper bound
@@ -623,6 +644,8 @@ __device__ __forceinline__ bool arrival_less(const Params &p, uint32_t skip, con
 }
 
 __global__ void __launch_bounds__(kMergeThreads) k_block_sort(Params p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ Rec s[kMergeTile + kMergeVT + 1];
     const Seg sg = p.seg[0][blockIdx.x]; // the tile this CTA sorts (k_plan)
     const uint32_t base = sg.start;
@@ -699,6 +722,8 @@ __device__ __forceinline__ uint32_t find_pair(const uint32_t *tb, uint32_t pairs
 constexpr int kPartitionThreads = 256;
 
 __global__ void __launch_bounds__(kPartitionThreads) k_merge_partition(Params p, uint32_t level, const Rec *src) {
+    pdl_trigger();
+    pdl_wait();
     const uint32_t pairs = p.nseg[level + 1];
     const uint32_t *tb = p.tile_base[level];
     const uint32_t n_bound = tb[pairs] + pairs; // every pair has tiles + 1 boundaries
@@ -711,7 +736,8 @@ __global__ void __launch_bounds__(kPartitionThreads) k_merge_partition(Params p,
     Seg b;
     b.start = 0; b.len = 0;
     if (2 * j + 1 < p.nseg[level]) b = p.seg[level][2 * j + 1];
-    uint64_t d64 = (uint64_t)t * kMergeTile;
+    const bool fin = p.fin_tile && level + 1 == p.n_levels;
+    uint64_t d64 = (uint64_t)t * (fin ? p.fin_tile : (uint32_t)kMergeTile);
     uint32_t n = a.len + b.len;
     uint32_t diag = d64 < n ? (uint32_t)d64 : n;
     uint32_t lo = diag > b.len ? diag - b.len : 0;
@@ -734,9 +760,36 @@ __global__ void __launch_bounds__(kPartitionThreads) k_merge_partition(Params p,
         else if (range < 32) hi = lo; // every valid probe was true: the answer is the end of the range
     }
     if (lane == 0) p.part[idx] = lo;
+    if (fin) {
+        // k_merge_final: a group of equal keys must not straddle a tile border, or the head's thread would have to walk the
+        // rest of the group through global memory while its whole CTA (and, through the chained scan, every later tile)
+        // waits.  So the border moves forward past the records that carry the key of the last record before it: up to 31
+        // of A and 31 of B (more only with hundreds of runs holding one key: then the kernel's walk does the rest).
+        uint32_t ext = 0;
+        if (diag > 0 && diag < n) {
+            const uint32_t ai = lo, bi = diag - lo;
+            Rec K;
+            if (ai == 0) K = ld_rec(&src[b.start + bi - 1]);
+            else if (bi == 0) K = ld_rec(&src[a.start + ai - 1]);
+            else {
+                const Rec ka = ld_rec(&src[a.start + ai - 1]), kb = ld_rec(&src[b.start + bi - 1]);
+                K = key_less(p, skip, ka, kb) ? kb : ka;
+            }
+            const bool ea = ai + lane < a.len && key_equal(p, skip, K, ld_rec(&src[a.start + ai + lane]));
+            const bool eb = bi + lane < b.len && key_equal(p, skip, K, ld_rec(&src[b.start + bi + lane]));
+            const uint32_t ma = __ballot_sync(0xFFFFFFFFu, ea), mb = __ballot_sync(0xFFFFFFFFu, eb);
+            uint32_t xa = (uint32_t)__ffs((int)~ma), xb = (uint32_t)__ffs((int)~mb); // 1 + leading run of equal records; 0 = all 32
+            xa = xa ? xa - 1 : 32;
+            xb = xb ? xb - 1 : 32;
+            ext = (xa > 31 ? 31u : xa) | ((xb > 31 ? 31u : xb) << 8);
+        }
+        if (lane == 0) p.part_ext[idx] = ext;
+    }
 }
 
 __global__ void __launch_bounds__(kMergeThreads, 4) k_merge(Params p, uint32_t level, const Rec *src, Rec *dst) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ Rec s[kMergeTile + kMergeVT + 1];
     const uint32_t pairs = p.nseg[level + 1];
     const uint32_t *tb = p.tile_base[level];
@@ -853,6 +906,8 @@ __device__ __forceinline__ void tma_store_1d(void *gmem_dst, const void *smem_sr
 }
 
 __global__ void __launch_bounds__(kMergeThreads, kMergeCtasPerSM) k_merge_tma(Params p, uint32_t level, const Rec *src, Rec *dst) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(128) uint8_t s_raw[];
     Rec *bufs[2] = {reinterpret_cast<Rec *>(s_raw), reinterpret_cast<Rec *>(s_raw) + kMergeBufRecs};
     __shared__ __align__(8) uint64_t s_bar[2];
@@ -967,6 +1022,8 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long *q, unsigned 
 #endif
 template <bool kNarrow, bool kFused, bool kHashRec>
 __global__ void __launch_bounds__(kResolveThreads, kFused ? DBEEL_RESOLVE_FUSED_MINB : DBEEL_RESOLVE_MINB) k_resolve(Params p, const Rec *m, uint4 *res) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int NT = kResolveThreads;
     __shared__ Rec s_rec[NT + 2];
     __shared__ unsigned long long s_entry[NT]; // device address of each record's entry
@@ -1262,6 +1319,8 @@ __device__ __forceinline__ void block_excl_scan_1024(unsigned long long &vb, uin
 
 // step 1: chunks of 1024 tiles, one CTA each: in-place exclusive scan + the chunk's totals
 __global__ void __launch_bounds__(1024) k_scan_tiles(Params p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ unsigned long long s_b[32];
     __shared__ uint32_t s_c[32];
     const uint32_t n_tiles = (p.ctl->span + kResolveThreads - 1) / kResolveThreads;
@@ -1278,6 +1337,8 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(Params p) {
 
 // step 2: one CTA scans the chunk totals (1024x fewer than tiles) and publishes the job totals
 __global__ void __launch_bounds__(1024) k_scan_chunks(Params p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ unsigned long long s_b[32];
     __shared__ uint32_t s_c[32];
     Ctl *c = p.ctl;
@@ -1304,6 +1365,8 @@ __global__ void __launch_bounds__(1024) k_scan_chunks(Params p) {
 }
 
 __global__ void __launch_bounds__(kResolveThreads) k_emit(Params p, const uint4 *res) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int NT = kResolveThreads;
     __shared__ unsigned long long s_wb[NT / 32];
     __shared__ uint32_t s_wc[NT / 32];
@@ -1345,6 +1408,8 @@ __global__ void __launch_bounds__(kResolveThreads) k_emit(Params p, const uint4 
 // k_rebase_index: subtract that from the memtable's index records.
 
 __global__ void k_flush_table(Params p, const uint4 *res) {
+    pdl_trigger();
+    pdl_wait();
     const uint32_t mt = blockIdx.x * blockDim.x + threadIdx.x;
     if (mt > p.n_groups) return;
     const Ctl *c = p.ctl;
@@ -1374,6 +1439,8 @@ __global__ void k_flush_table(Params p, const uint4 *res) {
 }
 
 __global__ void __launch_bounds__(256) k_rebase_index(Params p) {
+    pdl_trigger();
+    pdl_wait();
     const uint32_t e = blockIdx.x * 256u + threadIdx.x;
     if (e >= p.ctl->out_items) return;
     uint32_t lo = 0, hi = p.n_groups; // last group whose first entry is <= e (empty groups share a boundary)
@@ -1425,6 +1492,8 @@ __device__ __forceinline__ uint4 realign16_sel(uint4 A, uint4 B, uint32_t sh) {
 #define DBEEL_GATHER_MINB (1536 / DBEEL_GATHER_THREADS) // 12 CTAs of 128 threads: 40 registers (10-16 measured: DESIGN.md)
 #endif
 __global__ void __launch_bounds__(kGatherThreads, DBEEL_GATHER_MINB) k_gather(Params p) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int NT = kGatherThreads;
     constexpr int VPT = kGatherVecsPerThread;
     __shared__ unsigned long long s_adj[kGatherMaxEntries]; // entry address minus its tile-relative start
@@ -1602,9 +1671,15 @@ static_assert(kGatherTileBytes == 32ull * kGatherThreads * kG32Vpt, "gather tile
 // kBloomWarp: a fifth warp does nothing but the filter -- the tile's keys are hashed WHILE the four copy warps wait for their
 // payload loads, instead of after their stores by the same threads (the fused epilogue is a ~600-instruction dependent chain
 // per entry on 27 of 128 lanes: it lengthens every CTA's life by about a fifth).
-template <bool kBloomWarp>
+// kRot: the two dense per-entry passes run on DIFFERENT warps -- entry j's boundary block is written by thread (j + 96) mod 128
+// (warp 3 first), its key is hashed by thread (j + 32) mod 128 (warp 1 first).  A tile holds ~27 entries of 305 bytes, so with
+// the plain j = tid mapping warp 0 alone walks copy -> boundary loads -> key loads -> 600 dependent hash instructions while
+// warps 1-3 have exited but still hold their slots: the CTA lives as long as its slowest warp.
+template <bool kBloomWarp, bool kRot>
 __global__ void __launch_bounds__(kGatherThreads + (kBloomWarp ? 32 : 0), kBloomWarp ? DBEEL_GATHER32W_MINB : DBEEL_GATHER32_MINB)
 k_gather32(Params p) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int NT = kGatherThreads;            // copy threads
     constexpr int NTA = NT + (kBloomWarp ? 32 : 0); // all threads
     __shared__ unsigned long long s_adj[kGatherMaxEntries]; // entry address minus its tile-relative start
@@ -1701,7 +1776,7 @@ k_gather32(Params p) {
     }
 
     // ---- the 32-byte block that holds the last byte of entry j (unless j ends on a block boundary): its two halves
-    for (uint32_t j = tid; j < ne; j += NT) {
+    for (uint32_t j = kRot ? (tid + NT - 96u) % NT : tid; j < ne; j += NT) {
         const int r1 = s_r1[j];
         if (r1 <= 0 || (r1 & 31) == 0 || r1 > (int)tile_len) continue;
         const bool has_next = j + 1 < ne;
@@ -1742,7 +1817,7 @@ k_gather32(Params p) {
 
     // ---- bloom (fused epilogue), only when k_extract did not hash: entries whose first byte lies in this tile
     if (!kBloomWarp && hash_here) {
-        for (uint32_t j = tid; j < ne; j += NT) {
+        for (uint32_t j = kRot ? (tid + NT - 32u) % NT : tid; j < ne; j += NT) {
             const int r0 = s_r0[j];
             if (r0 < 0 || r0 >= (int)kGatherTileBytes) continue;
             const uint8_t *key = reinterpret_cast<const uint8_t *>((uintptr_t)(s_adj[j] + (unsigned long long)r0)) + 8;
@@ -1803,6 +1878,8 @@ __device__ __forceinline__ uint4 lds16_any(const uint8_t *stage, uint32_t off, u
 }
 
 __global__ void __launch_bounds__(kGtThreads, DBEEL_GT_CTAS) k_gather_tma(Params p) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int NT = kGtThreads;
     extern __shared__ __align__(128) uint8_t gt_raw[];
     auto stage_ptr = [&](uint32_t st) -> uint8_t * { return gt_raw + st * kGtStageBytes; };
@@ -2061,6 +2138,8 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) 
 #define DBEEL_GP_CTAS 10
 #endif
 __global__ void __launch_bounds__(kGatherThreads, DBEEL_GP_CTAS) k_gather_p(Params p) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int NT = kGatherThreads;
     __shared__ __align__(16) uint4 s_rawi[2][kGatherMaxEntries];
     __shared__ __align__(8) unsigned long long s_raws[2][kGatherMaxEntries];
@@ -2230,12 +2309,16 @@ __global__ void __launch_bounds__(kGatherThreads, DBEEL_GP_CTAS) k_gather_p(Para
 
 // Job header down / control block up without a copy engine: the pinned block is mapped into the GPU's address space.
 __global__ void __launch_bounds__(256) k_copy_words(uint32_t *dst, const uint32_t *src_host, uint32_t n) {
+    pdl_trigger();
+    pdl_wait();
     const uint32_t i = blockIdx.x * 256u + threadIdx.x;
     if (i < n) dst[i] = src_host[i];
 }
 
 __global__ void __launch_bounds__(256) k_publish(uint32_t *dst_host, const uint32_t *ctl, uint32_t n_ctl, uint32_t *dst2_host,
                                                  const uint32_t *table, uint32_t n_table) {
+    pdl_trigger();
+    pdl_wait();
     for (uint32_t i = threadIdx.x; i < n_ctl; i += 256) dst_host[i] = ctl[i];
     for (uint32_t i = threadIdx.x; i < n_table; i += 256) dst2_host[i] = table[i];
     __threadfence_system(); // visible to the host before the stream reports completion
@@ -2244,6 +2327,8 @@ __global__ void __launch_bounds__(256) k_publish(uint32_t *dst_host, const uint3
 // .bloom framing around the bit vector (bincode of bloomfilter::Bloom):
 //   u64 n_words | u32 words[n_words] | u64 nbits | u64 bitmap_bits | u32 k_num | 2 x SipHasher13
 __global__ void k_bloom_frame(uint8_t *file, uint64_t n_words, BloomParams b) {
+    pdl_trigger();
+    pdl_wait();
     if (threadIdx.x || blockIdx.x) return;
     uint32_t *w = reinterpret_cast<uint32_t *>(file);
     auto put64 = [&](uint64_t word_idx, uint64_t v) {
@@ -2276,6 +2361,8 @@ __global__ void k_bloom_frame(uint8_t *file, uint64_t n_words, BloomParams b) {
 // second stream right after k_resolve, so its random reads and SipHash rounds overlap k_emit and the payload copy -- the
 // gather is the kernel with no issue slot and no latency slack to spare, this one is all latency.
 __global__ void __launch_bounds__(256) k_bloom_res(Params p, const uint4 *res) {
+    pdl_trigger();
+    pdl_wait();
     const uint32_t i = blockIdx.x * 256u + threadIdx.x;
     if (i >= p.ctl->span) return;
     const uint4 it = __ldg(&res[i]);
@@ -2292,6 +2379,8 @@ __global__ void __launch_bounds__(256) k_bloom_res(Params p, const uint4 *res) {
 // entries instead of the gather's fused epilogue (which stays untouched for the single-job path): one thread per entry,
 // job = last one whose first output entry is <= e (k_flush_table's rows), key bytes from the entry's source.
 __global__ void __launch_bounds__(256) k_bloom_many(Params p) {
+    pdl_trigger();
+    pdl_wait();
     const uint32_t e = blockIdx.x * 256u + threadIdx.x;
     if (e >= p.ctl->out_items) return;
     uint32_t lo = 0, hi = p.n_groups;
@@ -2312,6 +2401,8 @@ __global__ void __launch_bounds__(256) k_bloom_many(Params p) {
 
 // compact-many: one frame per job that has a filter
 __global__ void __launch_bounds__(128) k_bloom_frames(const GroupDesc *groups, uint32_t n_groups) {
+    pdl_trigger();
+    pdl_wait();
     const uint32_t g = blockIdx.x * 128u + threadIdx.x;
     if (g >= n_groups) return;
     const BloomParams b = groups[g].bloom;
@@ -2345,6 +2436,8 @@ __global__ void __launch_bounds__(128) k_bloom_frames(const GroupDesc *groups, u
 
 // DBEEL_FLAG_VERIFY_SORTED: every valid entry i > 0 of a run must have key[i-1] < key[i].
 __global__ void __launch_bounds__(256) k_verify_sorted(Params p) {
+    pdl_trigger();
+    pdl_wait();
     uint32_t g = blockIdx.x * 256u + threadIdx.x;
     if (g >= p.n_total) return;
     uint32_t r = find_run(p, g);
@@ -2360,6 +2453,8 @@ __global__ void __launch_bounds__(256) k_verify_sorted(Params p) {
 //   offset = running sum of full_size (the stream cursor), key_size = 8 + the length prefix found at the cursor.
 // One CTA per run walks it in 1024-record chunks with a carried cursor (a rare path: corrupt or foreign index files).
 __global__ void __launch_bounds__(1024) k_ref_repair(Params p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ unsigned long long s_b[32];
     __shared__ uint32_t s_c[32];
     if (!(p.ctl->flags & kFlagIndexDiffers)) return;
@@ -2388,6 +2483,8 @@ __global__ void __launch_bounds__(1024) k_ref_repair(Params p) {
 
 // ... then the job state goes back to "nothing validated yet", now reading the canonical index
 __global__ void k_ref_reset(Params p) {
+    pdl_trigger();
+    pdl_wait();
     Ctl *c = p.ctl;
     if (!(c->flags & kFlagIndexDiffers)) return;
     RunDesc *runs = const_cast<RunDesc *>(p.runs);

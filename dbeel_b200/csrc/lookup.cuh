@@ -88,6 +88,8 @@ __device__ __forceinline__ int probe(const TableDesc &t, uint64_t rec, const uin
                            // 5 / 6 / 8 CTAs 0.672 / 0.686 / 0.763)
 #endif
 __global__ void __launch_bounds__(256, DBEEL_LOOKUP_MINB) k_lookup(LookupParams p) {
+    pdl_trigger();
+    pdl_wait();
     const uint64_t q = (uint64_t)blockIdx.x * 256u + threadIdx.x;
     if (q >= p.n_keys) return;
     const uint64_t k0 = p.key_off[q];

@@ -43,6 +43,8 @@ struct RouteParams {
 constexpr uint32_t kCutSeed = 0x9747b28cu; // second murmur seed: the pair is the 64-bit key identity of the memtable cut
 
 __global__ void __launch_bounds__(kRouteThreads) k_route_hash(RouteParams p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ uint32_t s_cnt[kRouteMaxShards];
     __shared__ unsigned long long s_bytes[kRouteMaxShards];
     const uint32_t tid = threadIdx.x;
@@ -75,6 +77,8 @@ __global__ void __launch_bounds__(kRouteThreads) k_route_hash(RouteParams p) {
 }
 
 __global__ void __launch_bounds__(1024) k_route_scan(RouteParams p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ unsigned long long s_b[32];
     __shared__ uint32_t s_c[32];
     const uint32_t s = blockIdx.x;
@@ -93,6 +97,8 @@ __global__ void __launch_bounds__(1024) k_route_scan(RouteParams p) {
 }
 
 __global__ void k_route_starts(RouteParams p, unsigned long long *host_totals) {
+    pdl_trigger();
+    pdl_wait();
     if (threadIdx.x == 0) {
         unsigned long long acc = 0;
         for (uint32_t s = 0; s < p.n_shards; s++) {
@@ -106,6 +112,8 @@ __global__ void k_route_starts(RouteParams p, unsigned long long *host_totals) {
 }
 
 __global__ void __launch_bounds__(kRouteThreads) k_route_scatter(RouteParams p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ uint32_t s_warp[kRouteThreads / 32][kRouteMaxShards]; // arrivals of shard s in warp w, then in the warps before w
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (uint32_t k = tid; k < (kRouteThreads / 32) * kRouteMaxShards; k += kRouteThreads) (&s_warp[0][0])[k] = 0;
@@ -156,6 +164,8 @@ struct CutParams {
 };
 
 __global__ void __launch_bounds__(1024) k_memtable_cuts(CutParams p) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(128) uint8_t s_raw[];
     unsigned long long *tab = reinterpret_cast<unsigned long long *>(s_raw);
     uint32_t *first = reinterpret_cast<uint32_t *>(s_raw + 8ull * kCutSlots);

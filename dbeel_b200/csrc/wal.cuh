@@ -37,6 +37,8 @@ struct WalParams {
 __device__ __forceinline__ uint64_t wal_ld64(const uint8_t *p) { return ld_u64_unaligned(p); }
 
 __global__ void __launch_bounds__(256) k_wal_parse(WalParams w) {
+    pdl_trigger();
+    pdl_wait();
     const uint32_t pg = blockIdx.x * 256u + threadIdx.x;
     const uint32_t stride = w.n_pages + 1;
     if (pg > w.n_pages) return;
@@ -76,6 +78,8 @@ __global__ void __launch_bounds__(256) k_wal_parse(WalParams w) {
 }
 
 __global__ void __launch_bounds__(256) k_wal_double(WalParams w, uint32_t k) {
+    pdl_trigger();
+    pdl_wait();
     const uint32_t pg = blockIdx.x * 256u + threadIdx.x;
     const uint32_t stride = w.n_pages + 1;
     if (pg >= stride) return;
@@ -86,6 +90,8 @@ __global__ void __launch_bounds__(256) k_wal_double(WalParams w, uint32_t k) {
 }
 
 __global__ void __launch_bounds__(256) k_wal_select(WalParams w) {
+    pdl_trigger();
+    pdl_wait();
     const uint32_t stride = w.n_pages + 1;
     const uint32_t total = w.cnt[(uint64_t)w.levels * stride]; // records replayed from page 0 on
     const uint32_t i = blockIdx.x * 256u + threadIdx.x;

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Attribute an ncu SASS-level profile to source lines: pairs the per-instruction counters of
 `ncu --page source --csv` with the line table of the locally built cubin (same build).
-Usage: tools/sass_hotspots.py <ncu-rep> <kernel-substring> [top]"""
+Usage: tools/sass_hotspots.py <ncu-rep> <kernel-substring> [top] [cubin-section-substring] [inst|smp]"""
 import csv
 import io
 import os
@@ -17,6 +17,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def main():
     rep, kern = sys.argv[1], sys.argv[2]
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 30
+    sect = sys.argv[4] if len(sys.argv) > 4 else kern  # template instances: the mangled name picks one (e.g. k_merge_finalILb1E)
+    order = 1 if len(sys.argv) > 5 and sys.argv[5] == "smp" else 0
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", kern],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -34,7 +36,7 @@ def main():
                    capture_output=True)
     dis = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, "dbeel_compact.sm_100a.cubin")],
                          capture_output=True, text=True).stdout.splitlines()
-    start = next(i for i, l in enumerate(dis) if l.startswith(".text.") and kern in l)
+    start = next(i for i, l in enumerate(dis) if l.startswith(".text.") and sect in l)
     lines = []
     cur = None
     for l in dis[start + 1:]:
@@ -44,7 +46,7 @@ def main():
         if m:
             cur = (os.path.basename(m.group(1)), int(m.group(2)))
             continue
-        if re.match(r"\s+/\*[0-9a-f]{4}\*/", l):
+        if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l):
             lines.append(cur)
     if len(lines) != len(prof):
         print(f"warning: {len(lines)} SASS instructions locally vs {len(prof)} in the report", file=sys.stderr)
@@ -57,7 +59,7 @@ def main():
         tot_s += smp
     srcs = {}
     print(f"{kern}: {tot_i} warp-instructions, {tot_s} samples")
-    for ln, (n, smp) in sorted(by_line.items(), key=lambda kv: -kv[1][0])[:top]:
+    for ln, (n, smp) in sorted(by_line.items(), key=lambda kv: -kv[1][order])[:top]:
         text = ""
         if ln:
             f = os.path.join(ROOT, "dbeel_b200", "csrc", ln[0])
