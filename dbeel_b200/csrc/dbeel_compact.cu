@@ -82,8 +82,9 @@ struct dbeel_engine {
                                 // filter pass just moves in front of k_emit: +0.16 ms per job); 0 = the gather's fused epilogue
     cudaStream_t s_side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    int fused_final = 1;        // DBEEL_FUSED_FINAL: 1 = last merge level + resolve + offsets scan + .index writes in one persistent kernel
-                                // (k_merge_final, single compactions), 0 = round 1's five kernels
+    int fused_final = 0;        // DBEEL_FUSED_FINAL: 1 = last merge level + resolve + offsets scan + .index writes in one persistent kernel
+                                // (k_merge_final, single compactions: 0.4 GB less DRAM traffic per cfg2 job, but 0.45 ms against 0.34 ms for
+                                // the five kernels it replaces -- latency-bound at 2 CTAs/SM), 0 = the five kernels
     int fin_ctas_per_sm = 0;    // co-resident k_merge_final CTAs per SM (occupancy query at engine creation): its chained scan needs them all resident
     int pdl = 0;                // DBEEL_PDL: 1 = the job's kernels are launched with programmatic stream serialization (griddepcontrol)
     int stage_events = 1;       // DBEEL_STAGE_EVENTS: 0 = no per-stage event records inside a job (stage_ms read 0)
@@ -314,6 +315,8 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     const uint64_t bounds_ub = tiles_ub + (p.nseg[0] + 1) / 2 + 1;
     const uint64_t o_part = carve(4 * bounds_ub);
     const uint64_t o_pext = carve(4 * bounds_ub);
+    const uint64_t o_bnd = carve(16 * (bounds_ub + 1));
+    const uint64_t o_tbnd = carve(4 * (tiles_ub + 1));
     const uint64_t res_tiles = (uint64_t)(N + kResolveThreads - 1) / kResolveThreads;
     const uint64_t o_tbytes = carve(res_tiles * 8), o_tcount = carve(res_tiles * 4);
     const uint64_t res_chunks = (res_tiles + 1023) / 1024;
@@ -352,6 +355,8 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
     for (uint32_t l = 0; l < levels; l++) p.tile_base[l] = reinterpret_cast<uint32_t *>(ws + o_tb[l]);
     p.part = reinterpret_cast<uint32_t *>(ws + o_part);
     p.part_ext = reinterpret_cast<uint32_t *>(ws + o_pext);
+    p.bnd = reinterpret_cast<uint4 *>(ws + o_bnd);
+    p.tile_bnd = reinterpret_cast<uint32_t *>(ws + o_tbnd);
     p.tile_bytes = reinterpret_cast<unsigned long long *>(ws + o_tbytes);
     p.tile_count = reinterpret_cast<uint32_t *>(ws + o_tcount);
     p.chunk_bytes = reinterpret_cast<unsigned long long *>(ws + o_cbytes);
@@ -557,11 +562,16 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
             if (grid > gather_tiles) grid = gather_tiles;
             launch_k(e, k_gather_p, (uint32_t)grid, kGatherThreads, 0, s, p);
         } else if (e->gather_variant == 4 && al32) { // k_gather32 + a fifth warp per CTA that only fills the filter
-            launch_k(e, k_gather32<true, false>, (uint32_t)gather_tiles, kGatherThreads + 32, 0, s, p);
-        } else if (e->gather_variant == 5 && al32) { // k_gather32, every warp does the whole epilogue of its own entries (round 2 baseline)
-            launch_k(e, k_gather32<false, false>, (uint32_t)gather_tiles, kGatherThreads, 0, s, p);
-        } else if (e->gather_variant >= 1 && al32) { // k_gather32, boundary blocks and filter on different warps
-            launch_k(e, k_gather32<false, true>, (uint32_t)gather_tiles, kGatherThreads, 0, s, p);
+            launch_k(e, k_gather32<true, false, false>, (uint32_t)gather_tiles, kGatherThreads + 32, 0, s, p);
+        } else if (e->gather_variant == 5 && al32) { // k_gather32, boundary blocks and filter on different warps (no gain)
+            launch_k(e, k_gather32<false, true, false>, (uint32_t)gather_tiles, kGatherThreads, 0, s, p);
+        } else if (e->gather_variant == 6 && al32 && p.bloom.words != nullptr && p.hash_rec == nullptr && !p.bloom_elsewhere &&
+                   gather_tiles + (N + kGatherThreads - 1) / kGatherThreads < 0x7FFFFFFFull) {
+            // k_gather32 with the filter on CTAs of their own, interleaved with the copy CTAs of the same grid
+            p.bloom_ctas = (uint32_t)((N + kGatherThreads - 1) / kGatherThreads); // one key per thread; N bounds the output entries
+            launch_k(e, k_gather32<false, false, true>, (uint32_t)(gather_tiles + p.bloom_ctas), kGatherThreads, 0, s, p);
+        } else if (e->gather_variant >= 1 && al32) { // k_gather32, filter as the copy CTA's epilogue
+            launch_k(e, k_gather32<false, false, false>, (uint32_t)gather_tiles, kGatherThreads, 0, s, p);
         } else {
             launch_k(e, k_gather, (uint32_t)gather_tiles, kGatherThreads, 0, s, p);
         }

@@ -103,6 +103,8 @@ struct Params {
     uint32_t nseg[kMaxLevels + 1];
     uint32_t n_levels;
     uint32_t *part; // merge-path split points of the current level
+    uint4 *bnd;          // [boundaries of the current level] {first A record, first B record, first output record} after the boundary (absolute)
+    uint32_t *tile_bnd;  // [tiles of the current level] index of the boundary a tile starts at (its end is the next one)
     Rec *rec_a, *rec_b;
     // resolve / scan
     unsigned long long *tile_bytes; // [resolve tiles] bytes emitted by the tile, then (k_scan_tiles) bytes before it
@@ -129,6 +131,7 @@ struct Params {
     unsigned long long out_offset_base; // .data bytes written by earlier key-range partitions of the same output file
     BloomParams bloom;
     uint4 *hash_rec; // [n_total] {h0, h1} = both SipHash-1-3 values of every entry's key (k_extract), or null: the gather hashes
+    uint32_t bloom_ctas;      // k_gather32<.., kSplit>: filter blocks interleaved with the copy blocks of the grid
     uint32_t bloom_elsewhere; // 1: k_bloom_res fills the filter on a second stream, next to the gather (which then skips it)
     // fused resolve + emit (single jobs): chained scan of the tiles' (bytes, entries), decoupled look-back
     uint32_t fin_tile;   // k_merge_final: nominal records per tile of the LAST level (< kMergeTile: room for the extensions), 0 = off
@@ -321,16 +324,23 @@ __global__ void k_common_prefix(Params p, int mode) {
     const uint8_t *ref = s_ref;
     uint32_t L = s_ref_len < kMaxPrefix ? s_ref_len : kMaxPrefix;
     if (ref == nullptr) L = 0;
-    for (uint32_t r = lane; r < p.n_runs && L; r += 32) {
+    // one lane per (run, first | last key): 16 keys of an 8-way job are compared at once, eight bytes per step
+    for (uint32_t q = lane; q < 2 * p.n_runs && L; q += 32) {
+        const uint32_t r = q >> 1, which = q & 1;
         uint32_t cnt = validated ? p.first_bad[r] : p.runs[r].n_in;
         if (!cnt) continue;
-        for (int which = 0; which < 2; which++) {
-            const uint8_t *ptr; uint32_t kl;
-            if (!safe_key(p.runs[r], which ? cnt - 1 : 0, &ptr, &kl)) { L = 0; break; }
-            uint32_t m = kl < L ? kl : L, i = 0;
-            while (i < m && __ldg(ptr + i) == __ldg(ref + i)) i++;
-            L = i;
+        const uint8_t *ptr; uint32_t kl;
+        if (!safe_key(p.runs[r], which ? cnt - 1 : 0, &ptr, &kl)) { L = 0; break; }
+        const uint32_t m = kl < L ? kl : L;
+        uint32_t i = 0;
+        bool diff = false;
+        while (i + 8 <= m) { // aligned 8-byte words that hold a needed byte lie inside the mapped buffers
+            const uint64_t x = ld_u64_unaligned(ptr + i) ^ ld_u64_unaligned(ref + i);
+            if (x) { i += (uint32_t)(__ffsll((long long)x) - 1) >> 3; diff = true; break; }
+            i += 8;
         }
+        if (!diff) while (i < m && __ldg(ptr + i) == __ldg(ref + i)) i++;
+        L = i;
     }
     for (int o = 16; o; o >>= 1) {
         uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, L, o);
@@ -759,7 +769,13 @@ __global__ void __launch_bounds__(kPartitionThreads) k_merge_partition(Params p,
         if (cnt < 32 && first_false < hi) hi = first_false;
         else if (range < 32) hi = lo; // every valid probe was true: the answer is the end of the range
     }
-    if (lane == 0) p.part[idx] = lo;
+    if (lane == 0) {
+        p.part[idx] = lo;
+        // everything a merge tile needs, one record per boundary: the persistent merge kernels read two of them per tile
+        // (one round trip, issued a tile ahead) instead of walking tile_base / seg / part (five dependent ones)
+        if (!fin) p.bnd[idx] = make_uint4(a.start + lo, b.start + (diag - lo), a.start + diag, j);
+        if (t * (uint64_t)(fin ? p.fin_tile : (uint32_t)kMergeTile) < n) p.tile_bnd[tb[j] + t] = idx; // a tile starts here
+    }
     if (fin) {
         // k_merge_final: a group of equal keys must not straddle a tile border, or the head's thread would have to walk the
         // rest of the group through global memory while its whole CTA (and, through the chained scan, every later tile)
@@ -783,7 +799,10 @@ __global__ void __launch_bounds__(kPartitionThreads) k_merge_partition(Params p,
             xb = xb ? xb - 1 : 32;
             ext = (xa > 31 ? 31u : xa) | ((xb > 31 ? 31u : xb) << 8);
         }
-        if (lane == 0) p.part_ext[idx] = ext;
+        if (lane == 0) {
+            p.part_ext[idx] = ext;
+            p.bnd[idx] = make_uint4(a.start + lo + (ext & 0xFF), b.start + (diag - lo) + (ext >> 8), a.start + diag, j);
+        }
     }
 }
 
@@ -930,8 +949,22 @@ __global__ void __launch_bounds__(kMergeThreads, kMergeCtasPerSM) k_merge_tma(Pa
         if (d.n_b) tma_load_1d(buf + d.n_a, &src[d.b_src], d.n_b * 16u, bar);
     };
 
-    MergeDesc cur = merge_desc(p, level, tile);
-    MergeDesc nxt = merge_desc(p, level, tile + G);
+    // Tile descriptors from the boundary records k_merge_partition left: tile -> boundary index (one load, issued three tiles
+    // ahead), then the two boundary records (two loads, issued two tiles ahead): no dependent chain inside an iteration.
+    auto ld_bidx = [&](uint32_t t) -> uint32_t { return t < n_tiles ? __ldg(&p.tile_bnd[t]) : 0xFFFFFFFFu; };
+    auto mk_desc = [&](uint32_t bidx) -> MergeDesc {
+        MergeDesc d;
+        d.a_src = d.n_a = d.b_src = d.n_b = d.dst = 0;
+        if (bidx == 0xFFFFFFFFu) return d;
+        const uint4 b0 = __ldg(&p.bnd[bidx]), b1 = __ldg(&p.bnd[bidx + 1]);
+        d.a_src = b0.x; d.n_a = b1.x - b0.x;
+        d.b_src = b0.y; d.n_b = b1.y - b0.y;
+        d.dst = b0.z;
+        return d;
+    };
+    MergeDesc cur = mk_desc(ld_bidx(tile));
+    MergeDesc nxt = mk_desc(ld_bidx(tile + G));
+    uint32_t bidx2 = ld_bidx(tile + 2 * G);
     if (tid == 0) issue(cur, bufs[0], &s_bar[0]);
     for (uint32_t q = 0;; q++) {
         Rec *s = bufs[q & 1];
@@ -941,7 +974,8 @@ __global__ void __launch_bounds__(kMergeThreads, kMergeCtasPerSM) k_merge_tma(Pa
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             issue(nxt, bufs[(q + 1) & 1], &s_bar[(q + 1) & 1]);
         }
-        const MergeDesc nn = merge_desc(p, level, tile + 2 * G); // consumed one iteration from now
+        const MergeDesc nn = mk_desc(bidx2);           // consumed one iteration from now
+        const uint32_t bidx3 = ld_bidx(tile + 3 * G);  // ... and two iterations from now
         while (!mbar_try_wait(&s_bar[q & 1], (q >> 1) & 1)) {}
 
         const uint32_t nA = cur.n_a, nB = cur.n_b, n = nA + nB;
@@ -977,6 +1011,7 @@ __global__ void __launch_bounds__(kMergeThreads, kMergeCtasPerSM) k_merge_tma(Pa
         tile += G;
         cur = nxt;
         nxt = nn;
+        bidx2 = bidx3;
     }
     if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // stores complete before the CTA retires
 }
@@ -1675,27 +1710,53 @@ static_assert(kGatherTileBytes == 32ull * kGatherThreads * kG32Vpt, "gather tile
 // (warp 3 first), its key is hashed by thread (j + 32) mod 128 (warp 1 first).  A tile holds ~27 entries of 305 bytes, so with
 // the plain j = tid mapping warp 0 alone walks copy -> boundary loads -> key loads -> 600 dependent hash instructions while
 // warps 1-3 have exited but still hold their slots: the CTA lives as long as its slowest warp.
-template <bool kBloomWarp, bool kRot>
+// kSplit: the filter is filled by CTAs OF THEIR OWN, interleaved with the copy CTAs in the same grid (every ~5th block): a
+// filter CTA takes 128 consecutive output entries, one key per thread, all lanes busy, and runs on an SM next to copy CTAs
+// that are waiting for their payload -- its ~600 dependent hash instructions per key fill issue slots the copy leaves idle
+// instead of lengthening every copy CTA's life.  (Two kernels on two streams do not co-run when each fills the GPU; blocks
+// of one grid do.)  The key bytes are the first granule of an entry the copy CTA of the same region touches within a few
+// microseconds either way: an L2 hit for whichever comes second.  Block b is a filter block iff floor((b+1) nb / G) >
+// floor(b nb / G) (nb filter blocks spread evenly over the G blocks of the grid); it is filter block floor(b nb / G), and
+// a copy block is tile b - floor(b nb / G).
+template <bool kBloomWarp, bool kRot, bool kSplit>
 __global__ void __launch_bounds__(kGatherThreads + (kBloomWarp ? 32 : 0), kBloomWarp ? DBEEL_GATHER32W_MINB : DBEEL_GATHER32_MINB)
 k_gather32(Params p) {
     pdl_trigger();
     pdl_wait();
     constexpr int NT = kGatherThreads;            // copy threads
     constexpr int NTA = NT + (kBloomWarp ? 32 : 0); // all threads
+    uint32_t tile_of_block = blockIdx.x;
+    if (kSplit) {
+        const uint64_t nb = p.bloom_ctas, G = gridDim.x;
+        const uint32_t q0 = (uint32_t)((uint64_t)blockIdx.x * nb / G), q1 = (uint32_t)(((uint64_t)blockIdx.x + 1) * nb / G);
+        if (q1 != q0) { // filter block q0: output entries [128 q0, 128 q0 + 128)
+            const uint32_t e = q0 * (uint32_t)NT + threadIdx.x;
+            if (p.bloom.words == nullptr || e >= p.ctl->out_items) return;
+            const uint8_t *key = reinterpret_cast<const uint8_t *>((uintptr_t)__ldg(&p.src_ptr[e])) + 8;
+            const uint64_t klen = __ldg(&p.out_index[e]).z - 8;
+            uint64_t h0, h1;
+            sip13_pair_vec_u8(p.bloom.sip, klen, [key](uint64_t q) { return ld_u64_unaligned(key + 8 * q); }, &h0, &h1);
+            uint32_t *words = p.bloom.words;
+            bloom_probe_all(h0, h1, p.bloom.k_num, p.bloom.bits, p.bloom.bits_magic,
+                            [words](uint64_t bit) { atomicOr(&words[bit >> 5], 1u << (bit & 31)); });
+            return;
+        }
+        tile_of_block = blockIdx.x - q0;
+    }
     __shared__ unsigned long long s_adj[kGatherMaxEntries]; // entry address minus its tile-relative start
     __shared__ int s_r0[kGatherMaxEntries], s_r1[kGatherMaxEntries];
     __shared__ uint32_t s_ks[kGatherMaxEntries];
     const Ctl *c = p.ctl;
     const unsigned long long out_len = c->out_data_len;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t tile_id = blockIdx.x;
+    const uint32_t tile_id = tile_of_block;
     const unsigned long long T0 = (unsigned long long)tile_id * kGatherTileBytes;
     if (T0 >= out_len) return;
     const uint32_t tile_len = out_len - T0 < kGatherTileBytes ? (uint32_t)(out_len - T0) : (uint32_t)kGatherTileBytes;
     const uint32_t e_lo = p.tile_first[tile_id];
     const uint32_t e_hi = T0 + kGatherTileBytes < out_len ? p.tile_first[tile_id + 1] : c->out_items - 1;
     const uint32_t ne = e_hi - e_lo + 1; // <= kGatherMaxEntries: every entry is >= 32 bytes
-    const bool hash_here = p.bloom.words != nullptr && p.hash_rec == nullptr && !p.bloom_elsewhere;
+    const bool hash_here = !kSplit && p.bloom.words != nullptr && p.hash_rec == nullptr && !p.bloom_elsewhere;
     for (uint32_t j = tid; j < ne; j += NTA) {
         const uint4 rec = p.out_index[e_lo + j];
         const unsigned long long d0 = ((unsigned long long)rec.x | ((unsigned long long)rec.y << 32)) - p.out_offset_base;

@@ -42,37 +42,6 @@ struct FinDesc {
     uint32_t nb;                     // bit 0: A[a0-1] exists, 1: A[a1] exists, 2: B[b0-1] exists, 3: B[b1] exists
 };
 
-__device__ __forceinline__ FinDesc fin_desc(const Params &p, uint32_t level, uint32_t tile) {
-    const uint32_t pairs = p.nseg[level + 1];
-    const uint32_t *tb = p.tile_base[level];
-    FinDesc d;
-    d.a_src = d.n_a = d.b_src = d.n_b = d.a_end = d.b_end = d.diag0 = d.nb = 0;
-    if (tile >= tb[pairs]) return d;
-    const uint32_t j = find_pair(tb, pairs, tile, 0);
-    const uint32_t t = tile - tb[j];
-    const Seg a = p.seg[level][2 * j];
-    Seg b;
-    b.start = 0; b.len = 0;
-    if (2 * j + 1 < p.nseg[level]) b = p.seg[level][2 * j + 1];
-    const uint32_t pidx = tb[j] + j + t;
-    // nominal merge-path split points, moved forward past the rest of the group that straddles them (k_merge_partition)
-    const uint32_t x0 = p.part_ext[pidx], x1 = p.part_ext[pidx + 1];
-    const uint32_t total = a.len + b.len;
-    const uint32_t diag0 = t * p.fin_tile;
-    const uint32_t diag1 = diag0 + p.fin_tile < total ? diag0 + p.fin_tile : total;
-    const uint32_t a0 = p.part[pidx] + (x0 & 0xFF), a1 = p.part[pidx + 1] + (x1 & 0xFF);
-    const uint32_t b0 = diag0 - p.part[pidx] + (x0 >> 8), b1 = diag1 - p.part[pidx + 1] + (x1 >> 8);
-    d.a_src = a.start + a0;
-    d.n_a = a1 - a0;
-    d.b_src = b.start + b0;
-    d.n_b = b1 - b0;
-    d.a_end = a.start + a.len;
-    d.b_end = b.start + b.len;
-    d.diag0 = diag0;
-    d.nb = (a0 > 0 ? 1u : 0u) | (a1 < a.len ? 2u : 0u) | (b0 > 0 ? 4u : 0u) | (b1 < b.len ? 8u : 0u);
-    return d;
-}
-
 template <bool kNarrow>
 __global__ void __launch_bounds__(kFinThreads, DBEEL_FIN_CTAS) k_merge_final(Params p, uint32_t level, const Rec *src) {
     constexpr int NT = kFinThreads, VT = kFinVT;
@@ -88,7 +57,8 @@ __global__ void __launch_bounds__(kFinThreads, DBEEL_FIN_CTAS) k_merge_final(Par
     __shared__ unsigned long long s_pref_b;
     __shared__ uint32_t s_pref_c;
     __shared__ uint32_t s_first[NT / 32];
-    __shared__ uint32_t s_rbase[kFinMaxRunsSmem];
+    __shared__ uint32_t s_rbase[kFinMaxRunsSmem + 1];
+    __shared__ uint8_t s_rlut[256]; // run that holds gid (b << lut_shift): a record's run is that one or a close successor
     __shared__ const uint4 *s_rindex[kFinMaxRunsSmem];
     __shared__ const uint8_t *s_rdata[kFinMaxRunsSmem];
 
@@ -101,12 +71,16 @@ __global__ void __launch_bounds__(kFinThreads, DBEEL_FIN_CTAS) k_merge_final(Par
     uint32_t tile = blockIdx.x;
     if (tile >= n_tiles) return;
     const bool runs_cached = p.n_runs <= (uint32_t)kFinMaxRunsSmem;
+    uint32_t lut_shift = 0;
+    while (((uint64_t)p.n_total >> lut_shift) > 256) lut_shift++; // gid >> lut_shift < 256 for every gid < n_total
     if (runs_cached) {
         for (uint32_t r = tid; r < p.n_runs; r += NT) {
             s_rbase[r] = p.runs[r].base;
             s_rindex[r] = p.runs[r].index;
             s_rdata[r] = p.runs[r].data;
         }
+        if (tid == 0) s_rbase[p.n_runs] = 0xFFFFFFFFu; // sentinel: no run starts above any gid
+        s_rlut[tid] = (uint8_t)find_run(p, (uint32_t)(((uint64_t)tid << lut_shift) < p.n_total ? (uint64_t)tid << lut_shift : p.n_total - 1));
     }
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
@@ -118,12 +92,9 @@ __global__ void __launch_bounds__(kFinThreads, DBEEL_FIN_CTAS) k_merge_final(Par
     // entry address / key_size / full_size of the entry behind a gid: its run's index record (64-byte granule)
     auto run_of = [&](uint32_t gid) -> uint32_t {
         if (!runs_cached) return find_run(p, gid);
-        uint32_t lo = 0, hi = p.n_runs;
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (s_rbase[mid] <= gid) lo = mid; else hi = mid;
-        }
-        return lo;
+        uint32_t r = s_rlut[gid >> lut_shift]; // owner of the bucket's first gid; ours is the last run whose base <= gid
+        while (s_rbase[r + 1] <= gid) r++;
+        return r;
     };
     auto index_ptr = [&](uint32_t gid, uint32_t r) -> const uint4 * {
         return runs_cached ? s_rindex[r] + (gid - s_rbase[r]) : p.runs[r].index + (gid - p.runs[r].base);
@@ -139,8 +110,30 @@ __global__ void __launch_bounds__(kFinThreads, DBEEL_FIN_CTAS) k_merge_final(Par
         if (cb) tma_load_1d(buf + d.n_a + 3 - bp, &src[d.b_src - bp], cb * 16u, bar);
     };
 
-    FinDesc cur = fin_desc(p, level, tile);
-    FinDesc nxt = fin_desc(p, level, tile + G);
+    // Tile descriptors from k_merge_partition's boundary records (already moved past straddling groups): the boundary index
+    // three tiles ahead, the two records two tiles ahead -- no dependent chain inside an iteration.  The last level of a
+    // single compaction is one pair: segments 0 (A) and 1 (B).
+    const Seg segA = p.seg[level][0];
+    Seg segB;
+    segB.start = 0; segB.len = 0;
+    if (p.nseg[level] > 1) segB = p.seg[level][1];
+    auto ld_bidx = [&](uint32_t t) -> uint32_t { return t < n_tiles ? __ldg(&p.tile_bnd[t]) : 0xFFFFFFFFu; };
+    auto mk_desc = [&](uint32_t bidx) -> FinDesc {
+        FinDesc d;
+        d.a_src = d.n_a = d.b_src = d.n_b = d.a_end = d.b_end = d.diag0 = d.nb = 0;
+        if (bidx == 0xFFFFFFFFu) return d;
+        const uint4 b0 = __ldg(&p.bnd[bidx]), b1 = __ldg(&p.bnd[bidx + 1]);
+        d.a_src = b0.x; d.n_a = b1.x - b0.x;
+        d.b_src = b0.y; d.n_b = b1.y - b0.y;
+        d.a_end = segA.start + segA.len;
+        d.b_end = segB.start + segB.len;
+        d.diag0 = b0.z;
+        d.nb = (b0.x > segA.start ? 1u : 0u) | (b1.x < d.a_end ? 2u : 0u) | (b0.y > segB.start ? 4u : 0u) | (b1.y < d.b_end ? 8u : 0u);
+        return d;
+    };
+    FinDesc cur = mk_desc(ld_bidx(tile));
+    FinDesc nxt = mk_desc(ld_bidx(tile + G));
+    uint32_t bidx2 = ld_bidx(tile + 2 * G);
     if (tid == 0) issue(cur, bufs[0], &s_bar[0]);
     const int keep_tombstones = p.keep_tombstones;
 
@@ -149,7 +142,8 @@ __global__ void __launch_bounds__(kFinThreads, DBEEL_FIN_CTAS) k_merge_final(Par
         uint4 *s4 = reinterpret_cast<uint4 *>(s);
         const bool has_next = tile + G < n_tiles;
         if (tid == 0 && has_next) issue(nxt, bufs[(q + 1) & 1], &s_bar[(q + 1) & 1]);
-        const FinDesc nn = fin_desc(p, level, tile + 2 * G); // consumed one iteration from now
+        const FinDesc nn = mk_desc(bidx2);            // consumed one iteration from now
+        const uint32_t bidx3 = ld_bidx(tile + 3 * G); // ... and two iterations from now
         while (!mbar_try_wait(&s_bar[q & 1], (q >> 1) & 1)) {}
 
         // ---- merge-path: thread t produces merged records [7t, 7t + 7) of the tile
@@ -421,6 +415,7 @@ __global__ void __launch_bounds__(kFinThreads, DBEEL_FIN_CTAS) k_merge_final(Par
         tile += G;
         cur = nxt;
         nxt = nn;
+        bidx2 = bidx3;
     }
 }
 

@@ -519,3 +519,4 @@ def test_multi_megabyte_entries_and_keys(engine):
     res = engine.get_many([(od, oi, None)], keys + [stem, stem + b"\xff"], capi.LOOKUP_EXACT)
     present = {k for k, _, _ in arrivals}
     assert [int(t) for t in res["table"]] == [0 if k in present else -1 for k in keys] + [-1, -1]
+
