@@ -89,6 +89,8 @@ struct dbeel_engine {
     int fin_ctas_per_sm = 0;    // co-resident k_merge_final CTAs per SM (occupancy query at engine creation): its chained scan needs them all resident
     int pdl = 0;                // DBEEL_PDL: 1 = the job's kernels are launched with programmatic stream serialization (griddepcontrol)
     int stage_events = 1;       // DBEEL_STAGE_EVENTS: 0 = no per-stage event records inside a job (stage_ms read 0)
+    int extract_persist = 0;    // DBEEL_EXTRACT_PERSIST: > 0 = k_extract runs as that many CTAs per SM, each thread fetching the next step's index
+                                // records while the current step's entry headers travel
     int bloom_in_extract = 0;   // DBEEL_BLOOM_EXTRACT: 1 = k_extract hashes, k_resolve sets the bits (measured slower: DESIGN.md); 0 = the gather's fused epilogue
 };
 
@@ -451,6 +453,8 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
         if (ref_reader && hash_early) launch_k(e, k_extract<true, true, true>, grid, 256, 0, s, p, mode);
         else if (ref_reader) launch_k(e, k_extract<true, true, false>, grid, 256, 0, s, p, mode);
         else if (hash_early) launch_k(e, k_extract<true, false, true>, grid, 256, 0, s, p, mode);
+        else if (e->narrow_loads && e->extract_persist > 0 && mode == 0) // one resident wave, index records fetched a step ahead
+            launch_k(e, k_extract<true, false, false, true>, std::min<uint32_t>(grid, (uint32_t)(e->sm_count * e->extract_persist)), 256, 0, s, p, mode);
         else if (e->narrow_loads) launch_k(e, k_extract<true, false, false>, grid, 256, 0, s, p, mode);
         else launch_k(e, k_extract<false, false, false>, grid, 256, 0, s, p, mode);
     };
@@ -1639,6 +1643,7 @@ int dbeel_engine_create(int device, dbeel_engine **out) {
     if (const char *v = getenv("DBEEL_BLOOM_SIDE")) e->bloom_side = atoi(v);
     if (const char *v = getenv("DBEEL_FUSED_EMIT")) e->fused_emit = atoi(v);
     if (const char *v = getenv("DBEEL_FUSED_FINAL")) e->fused_final = atoi(v);
+    if (const char *v = getenv("DBEEL_EXTRACT_PERSIST")) e->extract_persist = atoi(v);
     if (const char *v = getenv("DBEEL_PDL")) e->pdl = atoi(v);
     if (const char *v = getenv("DBEEL_STAGE_EVENTS")) e->stage_events = atoi(v);
     {

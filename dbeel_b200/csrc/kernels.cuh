@@ -374,8 +374,14 @@ constexpr int kExtractEPT = DBEEL_EXTRACT_EPT; // entries per thread = independe
 // (offset = running sum of full_size, key_size = 8 + the length prefix found in .data) and pass `mode 2` validates that.
 // mode 0: full validation; mode 1: only if a run was truncated -- re-extract with the shorter prefix; mode 2: full
 // validation again, only after a repair.
-template <bool kNarrow, bool kRef, bool kHash>
-__global__ void __launch_bounds__(256, kRef ? 3 : DBEEL_EXTRACT_MINB) k_extract(Params p, int mode) {
+// kPersist: launched with a grid that fits the GPU once (DBEEL_EXTRACT_PERSIST CTAs per SM); every thread walks several steps
+// and fetches the NEXT step's index records before it starts on the current step's entry headers, so a step exposes one DRAM
+// round trip (the headers) instead of two (index record, then header).
+#ifndef DBEEL_EXTRACT_PERSIST_MINB
+#define DBEEL_EXTRACT_PERSIST_MINB 3
+#endif
+template <bool kNarrow, bool kRef, bool kHash, bool kPersist = false>
+__global__ void __launch_bounds__(256, kRef ? 3 : (kPersist ? DBEEL_EXTRACT_PERSIST_MINB : DBEEL_EXTRACT_MINB)) k_extract(Params p, int mode) {
     pdl_trigger();
     pdl_wait();
     auto ldu = [](const uint8_t *q) { return kNarrow ? ld_u64_unaligned_narrow(q) : ld_u64_unaligned(q); };
@@ -387,30 +393,55 @@ __global__ void __launch_bounds__(256, kRef ? 3 : DBEEL_EXTRACT_MINB) k_extract(
     const uint64_t *pfx = reinterpret_cast<const uint64_t *>(c->prefix); // 8-byte aligned inside Ctl
     const uint32_t npw = (L + 7) >> 3;
     constexpr uint32_t STEP = 256u * kExtractEPT;
+    // index records of a step (and their predecessors', for the running-offset check), fetched a step ahead when kPersist
+    uint4 n_rec[kExtractEPT], n_pr[kExtractEPT];
+    uint32_t n_run[kExtractEPT];
+    auto fetch = [&](uint64_t g0n, uint4 rec[kExtractEPT], uint4 pr[kExtractEPT], uint32_t run[kExtractEPT]) {
+#pragma unroll
+        for (int u = 0; u < kExtractEPT; u++) {
+            const uint64_t gg = g0n + u * 256u;
+            rec[u] = pr[u] = make_uint4(0, 0, 0, 0);
+            run[u] = 0;
+            if (gg >= p.n_total) continue;
+            run[u] = find_run(p, (uint32_t)gg);
+            const RunDesc &rd = p.runs[run[u]];
+            const uint32_t ii = (uint32_t)gg - rd.base;
+            rec[u] = __ldg(&rd.index[ii]);
+            if (ii && !redo) pr[u] = __ldg(&rd.index[ii - 1]);
+        }
+    };
+    if (kPersist) fetch((uint64_t)blockIdx.x * STEP + threadIdx.x, n_rec, n_pr, n_run);
     for (uint32_t g0 = blockIdx.x * STEP + threadIdx.x; g0 < p.n_total; g0 += gridDim.x * STEP) {
         uint32_t g[kExtractEPT], r[kExtractEPT], i[kExtractEPT], ks[kExtractEPT], fs[kExtractEPT];
         uint64_t off[kExtractEPT], expect[kExtractEPT], dlen_total[kExtractEPT];
         const uint8_t *data[kExtractEPT];
         bool act[kExtractEPT], ok[kExtractEPT];
-        // ---- phase 1: index records (and the predecessor's, for the running-offset check)
+        uint4 c_rec[kExtractEPT], c_pr[kExtractEPT];
+        if (kPersist) {
+#pragma unroll
+            for (int u = 0; u < kExtractEPT; u++) { c_rec[u] = n_rec[u]; c_pr[u] = n_pr[u]; r[u] = n_run[u]; }
+            fetch((uint64_t)g0 + (uint64_t)gridDim.x * STEP, n_rec, n_pr, n_run); // travels while this step's headers do
+        } else {
+            fetch(g0, c_rec, c_pr, r);
+        }
+        // ---- phase 1: what the index records say
 #pragma unroll
         for (int u = 0; u < kExtractEPT; u++) {
             g[u] = g0 + u * 256u;
             act[u] = g[u] < p.n_total;
             ok[u] = false;
             if (!act[u]) continue;
-            r[u] = find_run(p, g[u]);
             const RunDesc &rd = p.runs[r[u]];
             i[u] = g[u] - rd.base;
             data[u] = rd.data;
             dlen_total[u] = rd.data_len;
-            const uint4 rec = __ldg(&rd.index[i[u]]);
+            const uint4 rec = c_rec[u];
             off[u] = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
             ks[u] = rec.z;
             fs[u] = rec.w;
             expect[u] = rd.off_base;
             if (i[u] && !redo) {
-                const uint4 pr = __ldg(&rd.index[i[u] - 1]);
+                const uint4 pr = c_pr[u];
                 expect[u] = ((uint64_t)pr.x | ((uint64_t)pr.y << 32)) + pr.w;
             }
         }
