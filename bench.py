@@ -246,10 +246,29 @@ def other_configs(eng, torch, dev, peak):
     return out
 
 
+def spread_device(local_rank: int, local_world: int) -> int:
+    """Which GPU of the node a rank drives.  With fewer ranks than GPUs the ranks are spread evenly over the node (rank r ->
+    GPU r * n_gpus / N: 0,4 for two ranks, 0,2,4,6 for four) instead of packed onto GPUs 0..N-1: host-memory DMA is capped per
+    CPU socket (profiles/r02_pcie_topology.txt: 91 GB/s for one GPU, 155 for two and 189 for four on ONE socket, 379 for all
+    eight over both), so ranks that share a socket share that cap and the end-to-end path is the first to feel it."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        n_dev = pynvml.nvmlDeviceGetCount()
+    except Exception:
+        return local_rank
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        n_dev = len([v for v in vis.split(",") if v.strip()])
+    if local_world <= 1 or n_dev <= local_world or n_dev % local_world or os.environ.get("DBEEL_NO_SPREAD"):
+        return local_rank
+    return local_rank * (n_dev // local_world)
+
+
 def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    local = spread_device(int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))
     # Host placement first: the thread (and every thread torch / numpy start later) moves next to this rank's GPU, so the
     # pinned staging buffers allocated below are first-touched on the GPU's own NUMA node (main.rs:51-60 pins shards too).
     from dbeel_b200 import capi, sstable
@@ -489,7 +508,8 @@ def run_gpu(args):
                      "engines_per_gpu": n_eng,
                      "timing": "per step: CUDA events on the engines' streams, first start to last end of the rank's jobs (two jobs in flight "
                                "with --overlap); sum over the K steps, max over ranks.  ms_per_job / stage_ms / roofline: every job alone",
-                     "host_placement": {"numa_node": numa_node, "cpus": numa_cpus}})
+                     "host_placement": {"numa_node": numa_node, "cpus": numa_cpus, "rank0_gpu": local,
+                                        "ranks_to_gpus": "rank r -> GPU r * n_gpus / N (spread over both CPU sockets)"}})
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": round(dev_ms_max / args.steps, 4), "higher_is_better": True,
@@ -513,6 +533,9 @@ def run_gpu(args):
                 "ms_per_step": round(float(e2e_ms[0]) / e2e_steps, 3),
                 "ms_kernels_per_job": round(e2e_kernel_ms / max(1, e2e_steps * len(mine)), 3), "partitions": e2e_parts,
                 "host_link_gbs_per_rank": [round(float(x), 1) for x in link.tolist()],
+                "host_dma_ceiling_gbs_per_gpu": {"1_gpu": 91.4, "2_gpus_two_sockets": 91.9, "4_gpus_two_sockets": 77.9, "4_gpus_one_socket": 47.2,
+                                                 "8_gpus": 47.3, "what": "plain cudaMemcpyAsync H2D + D2H at once, pinned NUMA-local memory, "
+                                                 "cfg2-sized buffers, all listed GPUs at once", "source": "profiles/r02_pcie_topology.txt"},
                 "api": "dbeel_compact (host pinned buffers; key-range partitions pipelined over H2D / kernels / D2H streams)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
