@@ -21,6 +21,7 @@
 #include "kernels.cuh"
 #include "merge_final.cuh"
 #include "gather_async.cuh"
+#include "gather_fb.cuh"
 #include "lookup.cuh"
 #include "route.cuh"
 #include "wal.cuh"
@@ -568,6 +569,8 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
             launch_k(e, k_gather_p, (uint32_t)grid, kGatherThreads, 0, s, p);
         } else if (e->gather_variant == 4 && al32) { // k_gather32 + a fifth warp per CTA that only fills the filter
             launch_k(e, k_gather32<true, false, false>, (uint32_t)gather_tiles, kGatherThreads + 32, 0, s, p);
+        } else if (e->gather_variant == 8 && al32) { // entry-boundary blocks built by the lane that owns them in the copy loop
+            launch_k(e, k_gather_fb, (uint32_t)gather_tiles, kFbThreads, 0, s, p);
         } else if (e->gather_variant == 7 && al32) { // payload lands in shared memory (cp.async), boundary blocks + filter while it travels
             launch_k(e, k_gather_async, (uint32_t)gather_tiles, kGatherThreads, 0, s, p);
         } else if (e->gather_variant == 5 && al32) { // k_gather32, boundary blocks and filter on different warps (no gain)
