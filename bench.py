@@ -210,7 +210,72 @@ def device_resident_job(eng, torch, dev, runs, opts, steps, warmup):
     return ms, stage, eng.stats(), out
 
 
-def other_configs(eng, torch, dev, peak):
+def file_fed_job(eng, expected):
+    """Row N3, the storage edge: one headline job (shard 0 of configs[3]) file to file through dbeel_tree_compact on tmpfs --
+    open, read, H2D, kernels, D2H, write, journal, renames, all inside the timed call.  Streamed through the engine's pinned
+    rings (dbeel_compact_stream, the default) against the same call reading every file whole first (DBEEL_TREE_STREAM=0)."""
+    import shutil
+    import tempfile
+    from dbeel_b200 import sstable, storage_engine as se
+    from dbeel_b200 import workloads as W
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    if shutil.disk_usage(base).free < 12e9:
+        return {"skipped": f"less than 12 GB free under {base}"}
+    cfg = W.cfg4_shard(0)
+    runs = make_runs_parallel(cfg)
+    in_bytes = sstable.input_bytes(runs)
+    root = tempfile.mkdtemp(prefix="dbeel_file_fed_", dir=base)
+    try:
+        master = os.path.join(root, "master")
+        os.makedirs(master)
+        for r, run in enumerate(runs):
+            sstable.write_run_files(master, 2 * r, run)
+        del runs
+        idx = [2 * r for r in range(cfg.n_runs)]
+        out_index = 2 * cfg.n_runs - 1
+
+        def one(tag, streamed):
+            d = os.path.join(root, tag)
+            os.makedirs(d)
+            for name in os.listdir(master):  # hard links: the tree deletes its inputs, the bytes stay in `master`
+                os.link(os.path.join(master, name), os.path.join(d, name))
+            os.environ["DBEEL_TREE_STREAM"] = "1" if streamed else "0"
+            tree = se.LSMTree(d, eng)
+            t0 = time.perf_counter()
+            tree.compact(idx, out_index, cfg.keep_tombstones, bloom_seed=SEED32)
+            dt = time.perf_counter() - t0
+            st = eng.stats()
+            tree.close()
+            return d, dt, st
+
+        res = {"workload": cfg.name + ", files on tmpfs (" + base + ")", "input_bytes": in_bytes, "unit": UNIT}
+        _, _, _ = one("warm", True)  # the rings are page-locked on first use (grow-only)
+        shutil.rmtree(os.path.join(root, "warm"))
+        best = None
+        for k in range(3):
+            d, dt, st = one(f"s{k}", True)
+            best = dt if best is None else min(best, dt)
+            if k < 2:
+                shutil.rmtree(d)
+        res["streamed"] = {"value": round(in_bytes / 1e6 / best, 1), "ms": round(best * 1e3, 1), "partitions": st["partitions"],
+                           "api": "dbeel_tree_compact -> dbeel_compact_stream (pread / pwrite threads <-> pinned rings <-> H2D / kernels / D2H)"}
+        if expected is not None:
+            gd, gi = sstable.read_run_files(d, out_index)
+            gb = np.fromfile(os.path.join(d, sstable.file_name(out_index, "bloom")), dtype=np.uint8)
+            res["parity_vs_oracle"] = bool(np.array_equal(gd, expected[0]) and np.array_equal(gi, expected[1]) and
+                                           expected[2] is not None and np.array_equal(gb, expected[2]))
+            del gd, gi, gb
+        shutil.rmtree(d)
+        d, dt, st = one("whole", False)
+        res["whole_buffers"] = {"value": round(in_bytes / 1e6 / dt, 1), "ms": round(dt * 1e3, 1),
+                                "api": "dbeel_tree_compact, DBEEL_TREE_STREAM=0: files read whole into fresh pinned buffers, dbeel_compact, files written"}
+        return res
+    finally:
+        os.environ.pop("DBEEL_TREE_STREAM", None)
+        shutil.rmtree(root, ignore_errors=True)
+
+
+def other_configs(eng, torch, dev, peak, job0_expected=None):
     """Evidence for the configs that are not the headline, outside every timed headline region (rank 0, N = 1)."""
     import oracle
     from dbeel_b200 import capi, sstable
@@ -238,6 +303,12 @@ def other_configs(eng, torch, dev, peak):
     log(f"[bench] other configs: cfg1 parity {out['cfg1']['parity_vs_oracle']}, cfg3 {out['cfg3']['ms_per_step']} ms/step "
         f"parity {out['cfg3']['parity_vs_oracle']} ({time.time() - t:.0f}s)")
     del runs, got, exp
+    try:  # row N3: the headline job file to file
+        t = time.time()
+        out["file_fed"] = file_fed_job(eng, job0_expected)
+        log(f"[bench] file-fed job: {out['file_fed']} ({time.time() - t:.0f}s)")
+    except Exception as ex:  # pragma: no cover
+        out["file_fed"] = {"error": repr(ex)}
     try:  # configs[4], one shard's stream (the 8-GPU run is --workload cfg5)
         import bench_cfg5
         out["cfg5_scaled"] = bench_cfg5.run_one_shard(eng, torch, dev, n_writes=1_500_000)
@@ -484,7 +555,7 @@ def run_gpu(args):
     others = None
     if rank == 0 and world == 1 and not args.no_cpu and args.workload == "cfg2" and not args.no_others:
         del pins, h_jobs, jobs_runs
-        others = other_configs(eng, torch, dev, peak)
+        others = other_configs(eng, torch, dev, peak, job0_expected=first)
 
     if rank != 0:
         if world > 1:

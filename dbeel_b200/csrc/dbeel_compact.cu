@@ -12,6 +12,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <deque>
+#include <memory>
 #include <new>
 #include <thread>
 #include <string>
@@ -25,6 +27,7 @@
 #include "lookup.cuh"
 #include "route.cuh"
 #include "wal.cuh"
+#include "host/stream_pump.h"
 
 using namespace dbeel;
 
@@ -56,6 +59,11 @@ struct dbeel_engine {
     uint64_t pipeline_min_bytes = 64ull << 20;
     uint64_t partition_bytes = 256ull << 20; // DBEEL_PARTITION_MB
     int partition_taper = 1;                 // DBEEL_PARTITION_TAPER: small first / last partitions (A/B switch)
+    // streaming host path (dbeel_compact_stream): pinned rings the file bytes pass through, the runs' .index files, the filter
+    // on its way out (grow-only, page-locked)
+    uint8_t *ring_in = nullptr, *ring_out = nullptr, *pin_index = nullptr, *pin_bloom = nullptr;
+    uint64_t ring_in_cap = 0, ring_out_cap = 0, pin_index_cap = 0, pin_bloom_cap = 0;
+    int stream_ring = 3;                     // DBEEL_STREAM_RING: slots per ring (>= 2)
     // pinned host block: job header going down, control block coming back
     uint8_t *wal_ws = nullptr; // WAL replay: doubling tables + the arrival index (grow-only)
     uint64_t wal_ws_cap = 0;
@@ -140,6 +148,45 @@ int ensure_pinned(dbeel_engine *e, uint64_t need) {
     if (ce != cudaSuccess) { cudaGetLastError(); return fail(e, DBEEL_ERR_CUDA, "cudaHostGetDevicePointer", ce); }
     e->pin_cap = need;
     return DBEEL_OK;
+}
+
+// grow-only page-locked host buffer (the streaming path's rings)
+int ensure_host(dbeel_engine *e, uint8_t **buf, uint64_t *cap, uint64_t need) {
+    if (need <= *cap) return DBEEL_OK;
+    if (*buf) { cudaFreeHost(*buf); *buf = nullptr; *cap = 0; }
+    const uint64_t want = align_up(need + need / 8, 1 << 20);
+    cudaError_t ce = cudaHostAlloc(reinterpret_cast<void **>(buf), want, cudaHostAllocDefault);
+    if (ce != cudaSuccess) { cudaGetLastError(); *buf = nullptr; return fail(e, DBEEL_ERR_NOMEM, "cudaHostAlloc(stream ring)", ce); }
+    *cap = want;
+    return DBEEL_OK;
+}
+
+int stream_threads() {
+    static const int n = [] {
+        if (const char *v = getenv("DBEEL_IO_THREADS")) return std::max(1, atoi(v));
+        const unsigned hw = std::thread::hardware_concurrency();
+        return (int)std::min(8u, std::max(1u, hw / 2));
+    }();
+    return n;
+}
+
+// n independent pieces of callback I/O over a few threads; the first nonzero return code wins
+template <class F>
+int parallel_pieces(size_t n, F fn) {
+    std::atomic<size_t> next{0};
+    std::atomic<int> err{0};
+    auto work = [&]() {
+        for (size_t k = next.fetch_add(1); k < n && !err.load(); k = next.fetch_add(1)) {
+            const int rc = fn(k);
+            if (rc) { int z = 0; err.compare_exchange_strong(z, rc); }
+        }
+    };
+    const int nt = (int)std::min<size_t>((size_t)stream_threads(), n);
+    std::vector<std::thread> pool;
+    for (int i = 1; i < nt; i++) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+    return err.load();
 }
 
 void default_opts(dbeel_compact_opts *o) {
@@ -706,16 +753,52 @@ struct Splitter {
     uint64_t weight;
 };
 
+// io != null: the streaming variant (dbeel_compact_stream).  The runs' pointers are ignored: the .index files are pulled
+// whole into pinned memory first (16 bytes per entry), the keys the planner looks at come through small reads, and the
+// .data slices of partition c travel file -> pinned ring -> device while the outputs travel device -> pinned ring -> file
+// on the threads of a StreamPump (host/stream_pump.h).
 int run_job_host_pipelined(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, const dbeel_compact_opts *o,
-                           dbeel_out *out, const JobShape &sh) {
+                           dbeel_out *out, const JobShape &sh, const dbeel_stream_io *io = nullptr) {
     // ---- 1. splitters from weighted samples of every run
     std::vector<HostRun> hr(n_runs);
     for (uint32_t r = 0; r < n_runs; r++)
-        hr[r] = HostRun{static_cast<const uint8_t *>(runs[r].data), runs[r].data_len,
-                        static_cast<const uint8_t *>(runs[r].index), runs[r].index_len / DBEEL_INDEX_ENTRY_SIZE};
+        hr[r] = HostRun{io ? nullptr : static_cast<const uint8_t *>(runs[r].data), runs[r].data_len,
+                        io ? nullptr : static_cast<const uint8_t *>(runs[r].index), runs[r].index_len / DBEEL_INDEX_ENTRY_SIZE};
     uint64_t P = (sh.data_total + sh.index_total + e->partition_bytes - 1) / e->partition_bytes;
     if (P > 64) P = 64;
     if (P < 2) return kFallbackSingleShot;
+    if (io) { // the .index files, whole, into page-locked memory (they are also what the H2D copies of the index slices read)
+        std::vector<uint64_t> ioff(n_runs);
+        uint64_t need = 0;
+        for (uint32_t r = 0; r < n_runs; r++) {
+            ioff[r] = need;
+            need += align_up(hr[r].n * 16 + 16, kAlign);
+        }
+        int rc = ensure_host(e, &e->pin_index, &e->pin_index_cap, need);
+        if (rc) return rc;
+        std::vector<StreamPump::ReadTask> rt;
+        for (uint32_t r = 0; r < n_runs; r++) {
+            hr[r].index = e->pin_index + ioff[r];
+            for (uint64_t done = 0; done < hr[r].n * 16; done += StreamPump::kPiece)
+                rt.push_back(StreamPump::ReadTask{0, r, DBEEL_STREAM_INDEX, done, std::min<uint64_t>(StreamPump::kPiece, hr[r].n * 16 - done),
+                                                  e->pin_index + ioff[r] + done});
+        }
+        rc = parallel_pieces(rt.size(), [&](size_t k) { return io->read(io->ctx, rt[k].run, rt[k].kind, rt[k].off, rt[k].len, rt[k].dst); });
+        if (rc) return fail(e, rc, "stream read callback failed (.index)");
+    }
+    // a key the planner compares: in memory, or fetched through the read callback into `store`
+    std::deque<std::vector<uint8_t>> key_store;
+    int key_rc = 0;
+    auto key_of = [&](uint32_t r, const HostRec &rec, bool keep) -> const uint8_t * {
+        if (!io) return hr[r].data + rec.off + 8;
+        if (!keep && !key_store.empty()) key_store.pop_back(); // the previous probe's scratch
+        key_store.emplace_back(rec.ks - 8 ? rec.ks - 8 : 1);
+        if (rec.ks > 8) {
+            const int rc = io->read(io->ctx, r, DBEEL_STREAM_DATA, rec.off + 8, rec.ks - 8, key_store.back().data());
+            if (rc && !key_rc) key_rc = rc;
+        }
+        return key_store.back().data();
+    };
     constexpr uint64_t kSamples = 256;
     std::vector<Splitter> samples;
     for (uint32_t r = 0; r < n_runs; r++) {
@@ -726,9 +809,11 @@ int run_job_host_pipelined(dbeel_engine *e, const dbeel_run *runs, uint32_t n_ru
             const uint64_t i = (2 * q + 1) * n / (2 * cnt);
             HostRec rec;
             if (!host_rec(hr[r], i, &rec)) return kFallbackSingleShot;
-            samples.push_back(Splitter{hr[r].data + rec.off + 8, rec.ks - 8, n / cnt + 1});
+            samples.push_back(Splitter{key_of(r, rec, true), rec.ks - 8, n / cnt + 1});
         }
     }
+    if (key_rc) return fail(e, key_rc, "stream read callback failed (sample keys)");
+    if (io) key_store.emplace_back(1); // scratch slot the probes below recycle
     if (samples.empty()) return kFallbackSingleShot;
     std::sort(samples.begin(), samples.end(), [](const Splitter &a, const Splitter &b) {
         return host_key_cmp(a.key, a.klen, b.key, b.klen) < 0;
@@ -781,7 +866,7 @@ int run_job_host_pipelined(dbeel_engine *e, const dbeel_run *runs, uint32_t n_ru
                 const uint64_t mid = (a + b) >> 1;
                 HostRec rec;
                 if (!host_rec(hr[r], mid, &rec)) return kFallbackSingleShot;
-                if (host_key_cmp(hr[r].data + rec.off + 8, rec.ks - 8, cuts[c].key, cuts[c].klen) < 0) a = mid + 1; else b = mid;
+                if (host_key_cmp(key_of(r, rec, false), rec.ks - 8, cuts[c].key, cuts[c].klen) < 0) a = mid + 1; else b = mid;
             }
             lo[r][c + 1] = a;
         }
@@ -805,6 +890,8 @@ int run_job_host_pipelined(dbeel_engine *e, const dbeel_run *runs, uint32_t n_ru
             boff[r][c] = rec.off;
         }
     }
+
+    if (key_rc) return fail(e, key_rc, "stream read callback failed (splitter probes)");
 
     // ---- 3. staging: two input and two output buffers sized for the largest partition
     uint64_t max_in = 0, max_out = 0;
@@ -836,6 +923,35 @@ int run_job_host_pipelined(dbeel_engine *e, const dbeel_run *runs, uint32_t n_ru
         }
     }
     uint8_t *sin[2] = {e->stage_in, e->stage_in2}, *sout[2] = {e->stage_out, e->stage_out2};
+    // streaming: R-slot pinned rings on both sides, one event per partition for the writer threads, the pump itself.
+    // Declared in this order so that the pump's threads are joined before the events they wait on are destroyed.
+    struct EventList {
+        std::vector<cudaEvent_t> ev;
+        ~EventList() { for (auto &x : ev) if (x) cudaEventDestroy(x); }
+    } ev_out;
+    std::unique_ptr<StreamPump> pump;
+    const uint32_t R = (uint32_t)std::max(2, e->stream_ring);
+    if (io) {
+        rc = ensure_host(e, &e->ring_in, &e->ring_in_cap, (uint64_t)R * max_in);
+        if (!rc) rc = ensure_host(e, &e->ring_out, &e->ring_out_cap, (uint64_t)R * max_out);
+        if (!rc && sh.bloom_file) rc = ensure_host(e, &e->pin_bloom, &e->pin_bloom_cap, sh.bloom_file);
+        if (rc) return rc;
+        ev_out.ev.assign(np, nullptr);
+        for (uint32_t c = 0; c < np; c++) CU(cudaEventCreateWithFlags(&ev_out.ev[c], cudaEventDisableTiming | cudaEventBlockingSync));
+        const int dev = e->device;
+        EventList *evl = &ev_out;
+        pump.reset(new StreamPump(io, np, R, stream_threads(), [evl](uint32_t c) { cudaEventSynchronize(evl->ev[c]); }, [dev]() { cudaSetDevice(dev); }));
+        for (uint32_t c = 0; c < np; c++) {
+            uint8_t *slot = e->ring_in + (uint64_t)(c % R) * max_in;
+            uint64_t pos = 0;
+            for (uint32_t r = 0; r < n_runs; r++) {
+                const uint64_t dl = boff[r][c + 1] - boff[r][c], il = (lo[r][c + 1] - lo[r][c]) * 16;
+                if (dl) pump->add_read(c, r, DBEEL_STREAM_DATA, boff[r][c], dl, slot + pos);
+                pos += align_up(dl + 32, kAlign) + align_up(il + 16, kAlign);
+            }
+        }
+        pump->start();
+    }
 
     // ---- 4. the shared bloom filter
     JobExtra ex;
@@ -873,10 +989,15 @@ int run_job_host_pipelined(dbeel_engine *e, const dbeel_run *runs, uint32_t n_ru
     auto enqueue_h2d = [&](uint32_t c) -> int {
         uint8_t *base = sin[c & 1];
         uint64_t pos = 0;
+        const uint8_t *slot = io ? e->ring_in + (uint64_t)(c % R) * max_in : nullptr;
+        if (io) { // partition c's slices have to be in their ring slot
+            const int prc = pump->wait_reads(c);
+            if (prc) return fail(e, prc, "stream read callback failed (.data)");
+        }
         if (trace) CU(cudaEventRecord(tev[6 * c + 0], e->s_h2d));
         for (uint32_t r = 0; r < n_runs; r++) {
             const uint64_t dl = boff[r][c + 1] - boff[r][c], il = (lo[r][c + 1] - lo[r][c]) * 16;
-            if (dl) CU(cudaMemcpyAsync(base + pos, hr[r].data + boff[r][c], dl, cudaMemcpyHostToDevice, e->s_h2d));
+            if (dl) CU(cudaMemcpyAsync(base + pos, io ? slot + pos : hr[r].data + boff[r][c], dl, cudaMemcpyHostToDevice, e->s_h2d));
             pos += align_up(dl + 32, kAlign);
             if (il) CU(cudaMemcpyAsync(base + pos, hr[r].index + 16 * lo[r][c], il, cudaMemcpyHostToDevice, e->s_h2d));
             pos += align_up(il + 16, kAlign);
@@ -922,6 +1043,7 @@ int run_job_host_pipelined(dbeel_engine *e, const dbeel_run *runs, uint32_t n_ru
         if (trace) CU(cudaEventRecord(tev[6 * c + 2], e->stream));
         rc = run_job_device(e, dr.data(), n_runs, o, false, &dout, /*record_start=*/true, &ex); // syncs e->stream
         if (rc) break;
+        if (io) pump->release_input(c); // the kernels have read device buffer c & 1, which the H2D out of ring slot c mod R filled
         const dbeel_stats &ps = e->stats;
         if (ps.runs_truncated || ps.index_repaired) { truncated = true; break; } // the slices were cut by index offsets: redo exactly
         total.entries_valid += ps.entries_valid;
@@ -938,8 +1060,22 @@ int run_job_host_pipelined(dbeel_engine *e, const dbeel_run *runs, uint32_t n_ru
         if (trace) CU(cudaEventRecord(tev[6 * c + 3], e->stream));
         CU(cudaStreamWaitEvent(e->s_d2h, e->ev_comp[c & 1], 0));
         if (trace) CU(cudaEventRecord(tev[6 * c + 4], e->s_d2h));
-        if (dout.data_len) CU(cudaMemcpyAsync(h_data + out_data, dout.data, dout.data_len, cudaMemcpyDeviceToHost, e->s_d2h));
-        if (dout.index_len) CU(cudaMemcpyAsync(h_index + 16 * out_items, dout.index, dout.index_len, cudaMemcpyDeviceToHost, e->s_d2h));
+        if (io) { // device -> ring slot c mod R (once partition c - R has left it) -> the writer threads
+            rc = pump->wait_out_slot(c);
+            if (rc) { fail(e, rc, "stream write callback failed"); break; }
+            uint8_t *oslot = e->ring_out + (uint64_t)(c % R) * max_out;
+            uint8_t *oindex = oslot + align_up(dout.data_len + 16, kAlign);
+            if (dout.data_len) CU(cudaMemcpyAsync(oslot, dout.data, dout.data_len, cudaMemcpyDeviceToHost, e->s_d2h));
+            if (dout.index_len) CU(cudaMemcpyAsync(oindex, dout.index, dout.index_len, cudaMemcpyDeviceToHost, e->s_d2h));
+            CU(cudaEventRecord(ev_out.ev[c], e->s_d2h));
+            StreamPump::OutPart op;
+            op.data = oslot; op.data_len = dout.data_len; op.data_off = out_data;
+            op.index = oindex; op.index_len = dout.index_len; op.index_off = 16 * out_items;
+            pump->publish_out(c, op);
+        } else {
+            if (dout.data_len) CU(cudaMemcpyAsync(h_data + out_data, dout.data, dout.data_len, cudaMemcpyDeviceToHost, e->s_d2h));
+            if (dout.index_len) CU(cudaMemcpyAsync(h_index + 16 * out_items, dout.index, dout.index_len, cudaMemcpyDeviceToHost, e->s_d2h));
+        }
         CU(cudaEventRecord(e->ev_d2h[c & 1], e->s_d2h));
         if (trace) CU(cudaEventRecord(tev[6 * c + 5], e->s_d2h));
         out_data += dout.data_len;
@@ -952,14 +1088,23 @@ int run_job_host_pipelined(dbeel_engine *e, const dbeel_run *runs, uint32_t n_ru
     if (rc || truncated) { // drain, then report / fall back to the exact single-shot semantics
         cudaStreamSynchronize(e->s_h2d);
         cudaStreamSynchronize(e->s_d2h);
+        if (pump) pump->abort(rc ? rc : DBEEL_ERR_INVALID_ARG); // its threads are joined when it goes out of scope
         return rc ? rc : kFallbackSingleShot;
     }
     if (sh.bloom_file) {
         CU(cudaStreamWaitEvent(e->s_d2h, e->ev_comp[(np - 1) & 1], 0));
-        CU(cudaMemcpyAsync(out->bloom, e->bloom_dev, sh.bloom_file, cudaMemcpyDeviceToHost, e->s_d2h));
+        CU(cudaMemcpyAsync(io ? (void *)e->pin_bloom : out->bloom, e->bloom_dev, sh.bloom_file, cudaMemcpyDeviceToHost, e->s_d2h));
     }
     CU(cudaStreamSynchronize(e->s_d2h));
     CU(cudaStreamSynchronize(e->s_h2d));
+    if (io) {
+        if (sh.bloom_file) {
+            const int wrc = io->write(io->ctx, DBEEL_STREAM_BLOOM, 0, e->pin_bloom, sh.bloom_file);
+            if (wrc) return fail(e, wrc, "stream write callback failed (.bloom)");
+        }
+        const int frc = pump->finish(); // every partition's bytes have gone through the write callback
+        if (frc) return fail(e, frc, "stream write callback failed");
+    }
     if (trace) {
         fprintf(stderr, "[dbeel trace] %u partitions; ms since the first H2D began: h2d[begin,end] kernels[begin,end] d2h[begin,end]\n", np);
         for (uint32_t c = 0; c < np; c++) {
@@ -1061,6 +1206,95 @@ struct BusyGuard {
     explicit BusyGuard(dbeel_engine *e_) : e(e_) { e->busy = true; }
     ~BusyGuard() { e->busy = false; }
 };
+
+// ------------------------------------------------------------------------------------ N3: the storage edge
+// dbeel_compact_stream for a job the pipeline does not take (too small to partition, an index the planner does not trust,
+// a run that ended early): every file whole into page-locked memory, the single-shot host path, the outputs whole through
+// the write callback -- the exact semantics of dbeel_compact, the callbacks just replace the caller's buffers.
+struct HostBlock {
+    uint8_t *p = nullptr;
+    ~HostBlock() { if (p) cudaFreeHost(p); }
+    bool alloc(uint64_t n) {
+        if (cudaHostAlloc(reinterpret_cast<void **>(&p), n ? n : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); p = nullptr; }
+        return p != nullptr;
+    }
+};
+
+int run_job_stream_whole(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, const dbeel_compact_opts *o, const dbeel_stream_io *io,
+                         dbeel_out *out, const JobShape &sh) {
+    std::vector<uint64_t> doff(n_runs), ioff(n_runs);
+    uint64_t pos = 0;
+    for (uint32_t r = 0; r < n_runs; r++) {
+        doff[r] = pos;
+        pos += align_up(runs[r].data_len + 16, kAlign);
+        ioff[r] = pos;
+        pos += align_up(runs[r].index_len + 16, kAlign);
+    }
+    HostBlock in, ob;
+    if (!in.alloc(pos)) return fail(e, DBEEL_ERR_NOMEM, "cudaHostAlloc(stream inputs)");
+    std::vector<StreamPump::ReadTask> rt;
+    std::vector<dbeel_run> hr(n_runs);
+    for (uint32_t r = 0; r < n_runs; r++) {
+        hr[r] = dbeel_run{in.p + doff[r], runs[r].data_len, in.p + ioff[r], runs[r].index_len};
+        for (uint64_t d = 0; d < runs[r].data_len; d += StreamPump::kPiece)
+            rt.push_back(StreamPump::ReadTask{0, r, DBEEL_STREAM_DATA, d, std::min<uint64_t>(StreamPump::kPiece, runs[r].data_len - d), in.p + doff[r] + d});
+        for (uint64_t d = 0; d < runs[r].index_len; d += StreamPump::kPiece)
+            rt.push_back(StreamPump::ReadTask{0, r, DBEEL_STREAM_INDEX, d, std::min<uint64_t>(StreamPump::kPiece, runs[r].index_len - d), in.p + ioff[r] + d});
+    }
+    int rc = parallel_pieces(rt.size(), [&](size_t k) { return io->read(io->ctx, rt[k].run, rt[k].kind, rt[k].off, rt[k].len, rt[k].dst); });
+    if (rc) return fail(e, rc, "stream read callback failed");
+    const uint64_t dc = sh.data_total, ic = sh.n_total * 16, bc = sh.bloom_file;
+    const uint64_t o_index = align_up(dc + 16, kAlign), o_bloom = o_index + align_up(ic + 16, kAlign);
+    if (!ob.alloc(o_bloom + align_up(bc + 16, kAlign))) return fail(e, DBEEL_ERR_NOMEM, "cudaHostAlloc(stream outputs)");
+    dbeel_out o2 = {ob.p, dc, 0, ob.p + o_index, ic, 0, bc ? ob.p + o_bloom : nullptr, bc, 0, 0};
+    const int saved = e->pipeline;
+    e->pipeline = 0;
+    rc = run_job_host(e, hr.data(), n_runs, o, false, &o2);
+    e->pipeline = saved;
+    if (rc) return rc;
+    struct WTask { uint32_t kind; uint64_t off, len; const uint8_t *src; };
+    std::vector<WTask> wt;
+    for (uint64_t d = 0; d < o2.data_len; d += StreamPump::kPiece)
+        wt.push_back(WTask{DBEEL_STREAM_DATA, d, std::min<uint64_t>(StreamPump::kPiece, o2.data_len - d), ob.p + d});
+    for (uint64_t d = 0; d < o2.index_len; d += StreamPump::kPiece)
+        wt.push_back(WTask{DBEEL_STREAM_INDEX, d, std::min<uint64_t>(StreamPump::kPiece, o2.index_len - d), ob.p + o_index + d});
+    if (o2.bloom_len) wt.push_back(WTask{DBEEL_STREAM_BLOOM, 0, o2.bloom_len, ob.p + o_bloom});
+    rc = parallel_pieces(wt.size(), [&](size_t k) { return io->write(io->ctx, wt[k].kind, wt[k].off, wt[k].src, wt[k].len); });
+    if (rc) return fail(e, rc, "stream write callback failed");
+    out->data_len = o2.data_len;
+    out->index_len = o2.index_len;
+    out->bloom_len = o2.bloom_len;
+    out->items_written = o2.items_written;
+    return DBEEL_OK;
+}
+
+int stream_entry(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, const dbeel_compact_opts *opts, const dbeel_stream_io *io,
+                 dbeel_out *out) {
+    if (!e) return DBEEL_ERR_INVALID_ARG;
+    if (!out || !io || !io->read || !io->write || (n_runs && !runs)) return fail(e, DBEEL_ERR_INVALID_ARG, "null argument");
+    if (e->async_state.load(std::memory_order_acquire) != 0) return DBEEL_ERR_BUSY;
+    if (e->busy) return fail(e, DBEEL_ERR_BUSY, "engine busy");
+    BusyGuard g(e);
+    e->err.clear();
+    dbeel_compact_opts o;
+    default_opts(&o);
+    if (opts) o = *opts;
+    if (!(o.bloom_fp > 0.0 && o.bloom_fp < 1.0)) return fail(e, DBEEL_ERR_INVALID_ARG, "bloom_fp must be in (0,1)");
+    if (n_runs > DBEEL_MAX_RUNS) return fail(e, DBEEL_ERR_TOO_MANY_RUNS, "too many runs");
+    cudaError_t ce = cudaSetDevice(e->device);
+    if (ce != cudaSuccess) return fail(e, DBEEL_ERR_CUDA, "cudaSetDevice", ce);
+    e->stats.ms_h2d = 0;
+    out->data_len = out->index_len = out->bloom_len = out->items_written = 0;
+    JobShape sh;
+    shape_of(runs, n_runs, &o, false, &sh);
+    if (e->pipeline && !(o.flags & DBEEL_FLAG_VERIFY_SORTED) && sh.n_total < 0xFFFFFFFEull &&
+        sh.data_total + sh.index_total >= e->pipeline_min_bytes) {
+        const int prc = run_job_host_pipelined(e, runs, n_runs, &o, out, sh, io);
+        if (prc != kFallbackSingleShot) return prc;
+        out->data_len = out->index_len = out->bloom_len = out->items_written = 0;
+    }
+    return run_job_stream_whole(e, runs, n_runs, &o, io, out, sh);
+}
 
 int entry(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, const dbeel_compact_opts *opts, dbeel_out *out,
           bool flush, bool device) {
@@ -1634,6 +1868,7 @@ int dbeel_engine_create(int device, dbeel_engine **out) {
     if (const char *v = getenv("DBEEL_PIPELINE_MIN_KB")) e->pipeline_min_bytes = (uint64_t)(atoi(v) > 0 ? atoi(v) : 1) << 10;
     if (const char *v = getenv("DBEEL_PARTITION_KB")) e->partition_bytes = (uint64_t)(atoi(v) > 0 ? atoi(v) : 1) << 10;
     if (const char *v = getenv("DBEEL_PARTITION_TAPER")) e->partition_taper = atoi(v) != 0;
+    if (const char *v = getenv("DBEEL_STREAM_RING")) e->stream_ring = std::max(2, atoi(v));
     if (const char *v = getenv("DBEEL_PARTITION_MB")) e->partition_bytes = (uint64_t)(atoi(v) > 0 ? atoi(v) : 128) << 20;
     if (cudaFuncSetAttribute(k_merge_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kMergeBufRecs * sizeof(Rec))) != cudaSuccess ||
         cudaFuncSetAttribute(k_gather_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGtSmem) != cudaSuccess) {
@@ -1703,6 +1938,10 @@ void dbeel_engine_destroy(dbeel_engine *e) {
     if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
     if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
     if (e->pin) cudaFreeHost(e->pin);
+    if (e->ring_in) cudaFreeHost(e->ring_in);
+    if (e->ring_out) cudaFreeHost(e->ring_out);
+    if (e->pin_index) cudaFreeHost(e->pin_index);
+    if (e->pin_bloom) cudaFreeHost(e->pin_bloom);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -1748,6 +1987,11 @@ int dbeel_compact(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, const
                   dbeel_out *out) {
     REFUSE_WHILE_ASYNC(e);
     return entry(e, runs, n_runs, opts, out, false, false);
+}
+
+int dbeel_compact_stream(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, const dbeel_compact_opts *opts,
+                         const dbeel_stream_io *io, dbeel_out *out) {
+    return stream_entry(e, runs, n_runs, opts, io, out);
 }
 
 int dbeel_compact_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, const dbeel_compact_opts *opts,

@@ -323,22 +323,12 @@ void dbeel_tree_set_page_sink(dbeel_tree *t, dbeel_page_sink sink, void *ctx) {
     t->page_ctx = ctx;
 }
 
-// Everything LSMTree::compact does after the merge core (lsm_tree.rs:995-1000,1068-1155) for one finished job: the
-// compact_* files, the CompactionAction journal, the renames, the sstable-list swap, the deletes.
-static int commit_compaction(dbeel_tree *t, const uint64_t *indices_to_compact, uint32_t n, uint64_t output_index, const void *data,
-                             uint64_t data_len, const void *index, uint64_t index_len, const void *bloom, uint64_t bloom_len,
-                             uint64_t items_written) {
+// Everything LSMTree::compact does once the compact_* files are complete (lsm_tree.rs:1078-1155): the CompactionAction
+// journal, the renames, the sstable-list swap, the deletes.
+static int commit_written(dbeel_tree *t, const uint64_t *indices_to_compact, uint32_t n, uint64_t output_index, uint64_t items_written) {
     int rc;
-    // lsm_tree.rs:995-1000,1068-1076: the compact_* files
     const std::string cdata = file_path(t->dir, output_index, kCompactData), cindex = file_path(t->dir, output_index, kCompactIndex),
                       cbloom = file_path(t->dir, output_index, kCompactBloom);
-    rc = write_file(t, cdata, data, data_len);
-    if (!rc) rc = write_file(t, cindex, index, index_len);
-    if (!rc && bloom_len) rc = write_file(t, cbloom, bloom, bloom_len);
-    if (rc) return rc;
-    // entry_writer.rs:94-95: the writer mirrors what it writes into the shard's page cache under the NEW files_index
-    if (t->page_sink) dbeel_out_pages(data, data_len, index, index_len, output_index, t->page_sink, t->page_ctx);
-
     // lsm_tree.rs:1078-1105: journal
     CompactionAction action;
     action.renames = {{cdata, file_path(t->dir, output_index, kData)},
@@ -367,11 +357,124 @@ static int commit_compaction(dbeel_tree *t, const uint64_t *indices_to_compact, 
     return DBEEL_OK;
 }
 
+// ... for a job whose output sits in host buffers: the compact_* files first (lsm_tree.rs:995-1000,1068-1076), then the rest.
+static int commit_compaction(dbeel_tree *t, const uint64_t *indices_to_compact, uint32_t n, uint64_t output_index, const void *data,
+                             uint64_t data_len, const void *index, uint64_t index_len, const void *bloom, uint64_t bloom_len,
+                             uint64_t items_written) {
+    const std::string cdata = file_path(t->dir, output_index, kCompactData), cindex = file_path(t->dir, output_index, kCompactIndex),
+                      cbloom = file_path(t->dir, output_index, kCompactBloom);
+    int rc = write_file(t, cdata, data, data_len);
+    if (!rc) rc = write_file(t, cindex, index, index_len);
+    if (!rc && bloom_len) rc = write_file(t, cbloom, bloom, bloom_len);
+    if (rc) return rc;
+    // entry_writer.rs:94-95: the writer mirrors what it writes into the shard's page cache under the NEW files_index
+    if (t->page_sink) dbeel_out_pages(data, data_len, index, index_len, output_index, t->page_sink, t->page_ctx);
+    return commit_written(t, indices_to_compact, n, output_index, items_written);
+}
+
+// The file edge of a streamed compaction (dbeel_compact_stream): the inputs' descriptors stand where the reference holds
+// DmaStreamReaders (lsm_tree.rs:984-991), the compact_* descriptors where it holds EntryWriter's DMA files (:995-1000).
+namespace {
+struct StreamFiles {
+    std::vector<int> data_fd, index_fd;
+    int out_fd[4] = {-1, -1, -1, -1}; // by DBEEL_STREAM_* kind
+    std::atomic<int> saved_errno{0};
+    ~StreamFiles() {
+        for (int fd : data_fd) if (fd >= 0) close(fd);
+        for (int fd : index_fd) if (fd >= 0) close(fd);
+        for (int fd : out_fd) if (fd >= 0) close(fd);
+    }
+};
+
+int stream_read(void *ctx, uint32_t run, uint32_t kind, uint64_t off, uint64_t len, void *dst) {
+    auto *f = static_cast<StreamFiles *>(ctx);
+    const int fd = kind == DBEEL_STREAM_DATA ? f->data_fd[run] : f->index_fd[run];
+    uint8_t *p = static_cast<uint8_t *>(dst);
+    while (len) {
+        const ssize_t r = pread(fd, p, len, (off_t)off);
+        if (r < 0 && errno == EINTR) continue;
+        if (r <= 0) { f->saved_errno.store(r < 0 ? errno : EIO); return DBEEL_ERR_IO; }
+        p += r; off += (uint64_t)r; len -= (uint64_t)r;
+    }
+    return 0;
+}
+
+int stream_write(void *ctx, uint32_t kind, uint64_t off, const void *src, uint64_t len) {
+    auto *f = static_cast<StreamFiles *>(ctx);
+    if (kind < 1 || kind > 3) return DBEEL_ERR_INVALID_ARG;
+    const uint8_t *p = static_cast<const uint8_t *>(src);
+    while (len) {
+        const ssize_t r = pwrite(f->out_fd[kind], p, len, (off_t)off);
+        if (r < 0 && errno == EINTR) continue;
+        if (r <= 0) { f->saved_errno.store(r < 0 ? errno : EIO); return DBEEL_ERR_IO; }
+        p += r; off += (uint64_t)r; len -= (uint64_t)r;
+    }
+    return 0;
+}
+
+bool tree_streams() { // DBEEL_TREE_STREAM=0: every compaction takes the whole-buffer path (A/B switch, read per call)
+    const char *v = getenv("DBEEL_TREE_STREAM");
+    return !v || atoi(v) != 0;
+}
+} // namespace
+
+// dbeel_tree_compact, files streamed through the engine's pinned rings: nothing is held whole in memory
+static int tree_compact_streamed(dbeel_tree *t, const uint64_t *indices_to_compact, uint32_t n, uint64_t output_index, int keep_tombstones,
+                                 const uint8_t *bloom_seed) {
+    StreamFiles f;
+    f.data_fd.assign(n, -1);
+    f.index_fd.assign(n, -1);
+    std::vector<dbeel_run> runs(n);
+    for (uint32_t i = 0; i < n; i++) { // lsm_tree.rs:956-993: open the inputs
+        const std::string dp = file_path(t->dir, indices_to_compact[i], kData), ip = file_path(t->dir, indices_to_compact[i], kIndex);
+        if (!exists(dp) || !exists(ip)) { t->err = "no such sstable: " + dp; return DBEEL_ERR_NO_SSTABLE; }
+        f.data_fd[i] = open(dp.c_str(), O_RDONLY);
+        f.index_fd[i] = open(ip.c_str(), O_RDONLY);
+        struct stat sd, si;
+        if (f.data_fd[i] < 0 || f.index_fd[i] < 0 || fstat(f.data_fd[i], &sd) != 0 || fstat(f.index_fd[i], &si) != 0) return io_fail(t, "open " + dp);
+        runs[i] = dbeel_run{nullptr, (uint64_t)sd.st_size, nullptr, (uint64_t)si.st_size};
+    }
+    // lsm_tree.rs:995-1000: the compact_* files
+    const std::string cpath[4] = {"", file_path(t->dir, output_index, kCompactData), file_path(t->dir, output_index, kCompactIndex),
+                                  file_path(t->dir, output_index, kCompactBloom)};
+    auto drop_outputs = [&]() { for (int k = 1; k <= 3; k++) unlink(cpath[k].c_str()); };
+    for (int k = 1; k <= 3; k++) {
+        f.out_fd[k] = open(cpath[k].c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (f.out_fd[k] < 0) { const int rc = io_fail(t, "create " + cpath[k]); drop_outputs(); return rc; }
+    }
+    dbeel_compact_opts opts;
+    opts.keep_tombstones = keep_tombstones;
+    opts.flags = 0;
+    opts.bloom_min_size = t->bloom_min_size;
+    opts.bloom_fp = DBEEL_DEFAULT_BLOOM_FP;
+    opts.bloom_seed = bloom_seed;
+    dbeel_stream_io io{stream_read, stream_write, &f};
+    dbeel_out out = {};
+    // lsm_tree.rs:1002-1076 -- the merge core, on the GPU
+    int rc = dbeel_compact_stream(t->engine, runs.data(), n, &opts, &io, &out);
+    if (rc) {
+        if (rc == DBEEL_ERR_IO) { errno = f.saved_errno.load(); io_fail(t, "streamed compaction"); }
+        else t->err = dbeel_last_error(t->engine);
+        drop_outputs();
+        return rc;
+    }
+    const uint64_t lens[4] = {0, out.data_len, out.index_len, out.bloom_len};
+    for (int k = 1; k <= 3; k++) { // a redone job may have written past the final length
+        if (ftruncate(f.out_fd[k], (off_t)lens[k]) != 0 || close(f.out_fd[k]) != 0) { f.out_fd[k] = -1; rc = io_fail(t, "close " + cpath[k]); drop_outputs(); return rc; }
+        f.out_fd[k] = -1;
+    }
+    if (!out.bloom_len) unlink(cpath[3].c_str()); // no filter: no .bloom file (lsm_tree.rs:1068-1076)
+    return commit_written(t, indices_to_compact, n, output_index, out.items_written);
+}
+
 
 int dbeel_tree_compact(dbeel_tree *t, const uint64_t *indices_to_compact, uint32_t n, uint64_t output_index,
                        int keep_tombstones, const uint8_t *bloom_seed) {
     if (!t || (n && !indices_to_compact)) return DBEEL_ERR_INVALID_ARG;
     t->err.clear();
+    // The default: stream the files through the engine.  A page sink needs the finished SSTable in memory (dbeel_out_pages
+    // replays the writer's `set` calls in entry order), so a tree with one installed takes the whole-buffer path below.
+    if (tree_streams() && !t->page_sink) return tree_compact_streamed(t, indices_to_compact, n, output_index, keep_tombstones, bloom_seed);
     // lsm_tree.rs:956-993: open the inputs (here: read them whole into pinned memory)
     std::vector<PinnedBuf> data(n), index(n);
     std::vector<dbeel_run> runs(n);

@@ -20,6 +20,9 @@
  *   dbeel_flush_many*   <- the same for many memtables at once (several collections / shards, or a backlog)
  *   dbeel_compact_many* <- compact_tree's loop over the groups its picker produced: one LSMTree::compact per
  *                          group (src/tasks/compaction.rs:82-101), all groups in one launch sequence
+ *   dbeel_compact_stream<- the same merge core with the reference's file edge around it: the DmaStreamReaders of the
+ *                          inputs (lsm_tree.rs:984-991) and EntryWriter's DMA files (entry_writer.rs:30-69) become
+ *                          read / write callbacks feeding a pinned ring                 ["next" row N3]
  *   dbeel_get_many*     <- the SSTable loop of LSMTree::get_entry: Bloom::check + binary_search
  *                          (lsm_tree.rs:605-670, 686-719) for a batch of keys        ["next" row N2]
  *   dbeel_wal_flush*    <- read_memtable_from_wal_file + the recovery flush of open_or_create_ex
@@ -159,6 +162,30 @@ int dbeel_compact_bound(const dbeel_run *runs, uint32_t n_runs, const dbeel_comp
  * SSTable.  Host buffers in, host buffers out; copies are part of the call. */
 int dbeel_compact(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs,
                   const dbeel_compact_opts *opts, dbeel_out *out);
+
+/* The same compaction fed from files ["next" row N3: the storage edge].  The reference reads its inputs through
+ * DmaStreamReaders (lsm_tree.rs:984-991) and writes through EntryWriter's buffered DMA files (entry_writer.rs:30-69); here
+ * the caller hands over two callbacks instead of buffers, and the engine moves the bytes
+ *     file -> read() -> pinned ring -> H2D -> kernels -> D2H -> pinned ring -> write() -> file
+ * one key-range partition at a time, so file reads, both PCIe directions and file writes overlap and the page-locked
+ * memory is a few partitions however large the SSTables are.  runs[i].data / .index are ignored (lengths only).
+ *   read : fill dst with [offset, offset + len) of run `run`'s .data (DBEEL_STREAM_DATA) or .index (DBEEL_STREAM_INDEX)
+ *   write: store len bytes at `offset` of the output's .data / .index / .bloom (DBEEL_STREAM_BLOOM: one call, offset 0)
+ * Both are called from several engine threads at once (pread / pwrite are fine) and return 0 or an error code of the
+ * caller's, which dbeel_compact_stream returns unchanged.  Output pieces arrive in no particular order; when an input turns
+ * out to need the one-piece path (a run that ends early, lsm_tree.rs:1014,1063) the outputs are written again from offset
+ * 0, so the caller truncates each output to out->*_len afterwards (bloom_len == 0: no .bloom file).  `out` returns
+ * lengths only; its pointers are ignored.  Same bytes as dbeel_compact. */
+#define DBEEL_STREAM_DATA 1u  /* = FileTypeKind::Data  (mod.rs:36-42) */
+#define DBEEL_STREAM_INDEX 2u /* = FileTypeKind::Index */
+#define DBEEL_STREAM_BLOOM 3u /* = FileTypeKind::Bloom */
+typedef struct dbeel_stream_io {
+    int (*read)(void *ctx, uint32_t run, uint32_t kind, uint64_t offset, uint64_t len, void *dst);
+    int (*write)(void *ctx, uint32_t kind, uint64_t offset, const void *src, uint64_t len);
+    void *ctx;
+} dbeel_stream_io;
+int dbeel_compact_stream(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, const dbeel_compact_opts *opts,
+                         const dbeel_stream_io *io, dbeel_out *out);
 
 /* Same, inputs and outputs resident in device memory (16-byte aligned).  Returns after the
  * job has completed on the engine's stream. */

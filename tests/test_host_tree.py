@@ -386,3 +386,135 @@ def test_tree_write_through_warms_a_page_cache(engine, tmp_path):
         joined = b"".join(pg for _, pg in pages)
         assert joined[:len(raw)] == raw and not any(joined[len(raw):])
     tree.close()
+
+
+# ---- row N3: compactions streamed file -> pinned ring -> GPU -> pinned ring -> file (dbeel_compact_stream)
+
+@pytest.fixture()
+def tiny_partition_stream_engine(monkeypatch):
+    """An engine that cuts even small jobs into many key-range partitions, so a few hundred KB of files exercise the
+    whole streaming pipeline (reader / writer threads, ring reuse)."""
+    monkeypatch.setenv("DBEEL_PIPELINE_MIN_KB", "1")
+    monkeypatch.setenv("DBEEL_PARTITION_KB", "24")
+    monkeypatch.setenv("DBEEL_IO_THREADS", "3")
+    eng = capi.Engine(0)
+    yield eng
+    eng.close()
+
+
+def _random_tree_runs(rng, n_runs, n_keys, id_space, doc=120):
+    runs = []
+    for r in range(n_runs):
+        ids = sorted(rng.choice(id_space, n_keys, replace=False).tolist())
+        ents = [(b"\xb0k%015d" % n, b"" if rng.random() < 0.02 else bytes(rng.integers(0, 256, int(rng.integers(1, doc)), dtype=np.uint8)),
+                 BASE_TS + r * 10_000 + j) for j, n in enumerate(ids)]
+        runs.append(sstable.build_run(ents))
+    return runs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ring", [2, 3])
+def test_streamed_compaction_is_byte_identical(monkeypatch, tmp_path, ring):
+    """dbeel_tree_compact streams its files through the engine's pinned rings (the default).  Same files as the oracle's
+    compaction and as the whole-buffer path, bloom included; many partitions actually ran."""
+    monkeypatch.setenv("DBEEL_PIPELINE_MIN_KB", "1")
+    monkeypatch.setenv("DBEEL_PARTITION_KB", "24")
+    monkeypatch.setenv("DBEEL_IO_THREADS", "3")
+    monkeypatch.setenv("DBEEL_STREAM_RING", str(ring))
+    eng = capi.Engine(0)
+    try:
+        rng = np.random.default_rng(70 + ring)
+        runs = _random_tree_runs(rng, 5, 1500, 6000)
+        od, oi, ob, on = oracle.compact(runs, False, bloom_min_size=50_000, seed=SEED)
+        outs = {}
+        for mode in ("1", "0"):  # streamed, then whole buffers
+            d = str(tmp_path / f"stream{mode}")
+            os.makedirs(d)
+            for r, run in enumerate(runs):
+                sstable.write_run_files(d, 2 * r, run)
+            monkeypatch.setenv("DBEEL_TREE_STREAM", mode)
+            tree = se.LSMTree(d, eng, sstable_bloom_min_size=50_000)
+            tree.compact([0, 2, 4, 6, 8], 9, False, bloom_seed=SEED)
+            assert tree.sstable_indices_and_sizes() == [(9, on)]
+            assert sorted(os.listdir(d)) == [sstable.file_name(9, e) for e in ("bloom", "data", "index")]
+            gd, gi = sstable.read_run_files(d, 9)
+            assert_run_equal((gd, gi), (od, oi), f"streamed={mode}")
+            assert np.array_equal(np.fromfile(os.path.join(d, sstable.file_name(9, "bloom")), dtype=np.uint8), ob)
+            outs[mode] = eng.stats()
+            tree.close()
+        assert outs["1"]["partitions"] > 4 and outs["1"]["kernel_launches"] > 60
+    finally:
+        eng.close()
+
+
+@pytest.mark.gpu
+def test_streamed_compaction_small_job_and_damaged_run(tiny_partition_stream_engine, monkeypatch, tmp_path):
+    """The two ways out of the pipeline: a job too small to partition (one piece, files whole through the callbacks), and a
+    run that ends early -- its .data file cut short -- which is redone in one piece; the files are truncated to the final
+    lengths.  Both equal the oracle."""
+    eng = tiny_partition_stream_engine
+    rng = np.random.default_rng(91)
+    # (a) below the partition threshold: no bloom, a single piece
+    monkeypatch.setenv("DBEEL_PIPELINE_MIN_KB", "100000")
+    small = capi.Engine(0)
+    try:
+        d = str(tmp_path / "small")
+        os.makedirs(d)
+        runs = _random_tree_runs(rng, 3, 200, 500)
+        for r, run in enumerate(runs):
+            sstable.write_run_files(d, 2 * r, run)
+        tree = se.LSMTree(d, small)
+        tree.compact([0, 2, 4], 5, True)
+        od, oi, _, on = oracle.compact(runs, True)
+        assert tree.sstable_indices_and_sizes() == [(5, on)]
+        assert sorted(os.listdir(d)) == [sstable.file_name(5, "data"), sstable.file_name(5, "index")]
+        assert_run_equal(sstable.read_run_files(d, 5), (od, oi), "small streamed job")
+        tree.close()
+    finally:
+        small.close()
+    # (b) a run whose .data stops in the middle of an entry (lsm_tree.rs:1014,1063: the run simply ends there)
+    d = str(tmp_path / "cut")
+    os.makedirs(d)
+    runs = _random_tree_runs(rng, 4, 1200, 4000)
+    cut = (runs[2][0][: runs[2][0].size * 2 // 3 + 5].copy(), runs[2][1])
+    runs[2] = cut
+    for r, run in enumerate(runs):
+        sstable.write_run_files(d, 2 * r, run)
+    tree = se.LSMTree(d, eng, sstable_bloom_min_size=50_000)
+    tree.compact([0, 2, 4, 6], 7, False, bloom_seed=SEED)
+    od, oi, ob, on = oracle.compact(runs, False, bloom_min_size=50_000, seed=SEED)
+    assert tree.sstable_indices_and_sizes() == [(7, on)]
+    assert_run_equal(sstable.read_run_files(d, 7), (od, oi), "streamed job with a run that ends early")
+    assert np.array_equal(np.fromfile(os.path.join(d, sstable.file_name(7, "bloom")), dtype=np.uint8), ob)
+    tree.close()
+    # (c) an entry header in the middle of a run disagrees with its index record: the planner does not see it, the partition
+    # that holds it reports a run that ended early, the job is redone in one piece over what the pipeline had already written
+    d = str(tmp_path / "mid")
+    os.makedirs(d)
+    runs = _random_tree_runs(rng, 4, 1200, 4000)
+    data1 = runs[1][0].copy()
+    off = int.from_bytes(bytes(runs[1][1][16 * 700:16 * 700 + 8]), "little")
+    data1[off] ^= 0x40  # the key-length prefix of entry 700
+    runs[1] = (data1, runs[1][1])
+    for r, run in enumerate(runs):
+        sstable.write_run_files(d, 2 * r, run)
+    tree = se.LSMTree(d, eng, sstable_bloom_min_size=50_000)
+    tree.compact([0, 2, 4, 6], 7, False, bloom_seed=SEED)
+    od, oi, ob, on = oracle.compact(runs, False, bloom_min_size=50_000, seed=SEED)
+    assert tree.sstable_indices_and_sizes() == [(7, on)]
+    assert eng.stats()["runs_truncated"] == 1
+    assert_run_equal(sstable.read_run_files(d, 7), (od, oi), "streamed job with a damaged entry")
+    assert np.array_equal(np.fromfile(os.path.join(d, sstable.file_name(7, "bloom")), dtype=np.uint8), ob)
+    tree.close()
+
+
+@pytest.mark.gpu
+def test_streamed_compaction_reports_a_missing_input(tiny_partition_stream_engine, tmp_path):
+    d = str(tmp_path)
+    run = sstable.build_run([(b"k%04d" % n, b"v", BASE_TS + n) for n in range(50)])
+    sstable.write_run_files(d, 0, run)
+    tree = se.LSMTree(d, tiny_partition_stream_engine)
+    with pytest.raises(capi.DbeelError):
+        tree.compact([0, 2], 3, False)
+    assert sorted(os.listdir(d)) == [sstable.file_name(0, "data"), sstable.file_name(0, "index")]  # nothing left behind
+    tree.close()
