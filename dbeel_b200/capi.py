@@ -32,7 +32,7 @@ DEFAULT_BLOOM_MIN_SIZE = 1_048_576
 DEFAULT_BLOOM_FP = 0.01
 
 EXPORTS = ["dbeel_abi_version", "dbeel_engine_create", "dbeel_engine_destroy", "dbeel_compact_bound",
-           "dbeel_compact", "dbeel_compact_device", "dbeel_compact_submit", "dbeel_poll", "dbeel_wait",
+           "dbeel_compact", "dbeel_compact_stream", "dbeel_compact_device", "dbeel_compact_submit", "dbeel_poll", "dbeel_wait",
            "dbeel_flush", "dbeel_flush_device", "dbeel_flush_many", "dbeel_flush_many_device",
            "dbeel_get_many", "dbeel_get_many_device", "dbeel_wal_flush", "dbeel_wal_flush_device",
            "dbeel_compact_many_bound", "dbeel_compact_many", "dbeel_compact_many_device",
@@ -44,6 +44,14 @@ EXPORTS = ["dbeel_abi_version", "dbeel_engine_create", "dbeel_engine_destroy", "
 
 class Run(C.Structure):
     _fields_ = [("data", C.c_void_p), ("data_len", C.c_uint64), ("index", C.c_void_p), ("index_len", C.c_uint64)]
+
+
+STREAM_READ_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p)
+STREAM_WRITE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64)
+
+
+class StreamIO(C.Structure):
+    _fields_ = [("read", STREAM_READ_FN), ("write", STREAM_WRITE_FN), ("ctx", C.c_void_p)]
 
 
 class Out(C.Structure):
@@ -142,6 +150,8 @@ def lib():
             f = getattr(L, name)
             f.restype = C.c_int
             f.argtypes = [C.c_void_p, C.POINTER(Run), C.c_uint32, C.POINTER(Opts), C.POINTER(Out)]
+        L.dbeel_compact_stream.restype = C.c_int
+        L.dbeel_compact_stream.argtypes = [C.c_void_p, C.POINTER(Run), C.c_uint32, C.POINTER(Opts), C.POINTER(StreamIO), C.POINTER(Out)]
         L.dbeel_compact_submit.restype = C.c_int
         L.dbeel_compact_submit.argtypes = [C.c_void_p, C.POINTER(Run), C.c_uint32, C.POINTER(Opts), C.POINTER(Out)]
         L.dbeel_poll.restype = C.c_int
@@ -313,6 +323,53 @@ class Engine:
         self._check(lib().dbeel_compact(self._h, arr, len(keep), C.byref(opts), C.byref(out)), "dbeel_compact")
         bloom = ob[:out.bloom_len] if out.bloom_len else None
         return od[:out.data_len], oi[:out.index_len], bloom, int(out.items_written)
+
+    def compact_stream(self, runs: Sequence[Tuple[object, object]], keep_tombstones: bool = False,
+                       bloom_min_size: int = DEFAULT_BLOOM_MIN_SIZE, seed: Optional[bytes] = None, flags: int = 0,
+                       fail_read_at: int = -1, fail_write_at: int = -1):
+        """dbeel_compact_stream with in-memory "files": the engine pulls the runs through a read callback and pushes the
+        output through a write callback (both called from several engine threads).  Returns (data, index, bloom|None,
+        items_written) like compact(); fail_*_at = n makes the n-th callback call return error code 4242 (tests)."""
+        keep = [(_u8(d), _u8(i)) for d, i in runs]
+        arr = (Run * max(1, len(keep)))()
+        for j, (d, i) in enumerate(keep):
+            arr[j] = Run(None, d.size, None, i.size)
+        opts = make_opts(keep_tombstones, bloom_min_size, DEFAULT_BLOOM_FP, seed, flags)
+        dc, ic, bc = compact_bound([(d.size, i.size) for d, i in keep], opts)
+        outs = {1: np.zeros(max(1, dc), np.uint8), 2: np.zeros(max(1, ic), np.uint8), 3: np.zeros(max(1, bc), np.uint8)}
+        calls = {"r": 0, "w": 0}
+        import threading
+        mu = threading.Lock()
+
+        def rd(_ctx, run, kind, off, n, dst):
+            with mu:
+                k = calls["r"]
+                calls["r"] += 1
+            if k == fail_read_at:
+                return 4242
+            src = keep[run][0] if kind == 1 else keep[run][1]
+            if off + n > src.size:
+                return 4243
+            C.memmove(dst, src.ctypes.data + off, n)
+            return 0
+
+        def wr(_ctx, kind, off, src, n):
+            with mu:
+                k = calls["w"]
+                calls["w"] += 1
+            if k == fail_write_at:
+                return 4242
+            dst = outs.get(kind)
+            if dst is None or off + n > dst.size:
+                return 4244
+            C.memmove(dst.ctypes.data + off, src, n)
+            return 0
+
+        io = StreamIO(STREAM_READ_FN(rd), STREAM_WRITE_FN(wr), None)
+        out = Out(None, 0, 0, None, 0, 0, None, 0, 0, 0)
+        self._check(lib().dbeel_compact_stream(self._h, arr, len(keep), C.byref(opts), C.byref(io), C.byref(out)), "dbeel_compact_stream")
+        bloom = outs[3][:out.bloom_len] if out.bloom_len else None
+        return outs[1][:out.data_len], outs[2][:out.index_len], bloom, int(out.items_written)
 
     def compact_async(self, runs: Sequence[Tuple[object, object]], keep_tombstones: bool = False,
                       bloom_min_size: int = DEFAULT_BLOOM_MIN_SIZE, seed: Optional[bytes] = None):

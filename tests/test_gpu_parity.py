@@ -520,3 +520,38 @@ def test_multi_megabyte_entries_and_keys(engine):
     present = {k for k, _, _ in arrivals}
     assert [int(t) for t in res["table"]] == [0 if k in present else -1 for k in keys] + [-1, -1]
 
+
+
+# ---- row N3: dbeel_compact_stream -- the same compaction with read / write callbacks instead of buffers
+
+@pytest.mark.parametrize("seed", range(3))
+def test_compact_stream_equals_compact_and_the_oracle(tiny_partition_engine, seed):
+    """In-memory "files" behind ctypes callbacks: many partitions through the pinned rings, same bytes as the oracle."""
+    eng = tiny_partition_engine
+    rng = np.random.default_rng(900 + seed)
+    pool = nasty_keys(rng, 5000, max_len=40)
+    k = int(rng.integers(2, 9))
+    runs = random_runs(rng, k, [int(rng.integers(0, 3000)) for _ in range(k)], pool, max_doc=120)
+    keep = bool(seed & 1)
+    exp = oracle.compact(runs, keep, bloom_min_size=10_000, seed=SEED)
+    got = eng.compact_stream(runs, keep, bloom_min_size=10_000, seed=SEED)
+    assert got[3] == exp[3]
+    assert_run_equal(got[:2], exp[:2], f"stream {seed}")
+    assert (got[2] is None) == (exp[2] is None) and (got[2] is None or np.array_equal(got[2], exp[2]))
+    assert eng.stats()["partitions"] > 3
+    # the reference's reader semantics (DBEEL_FLAG_REFERENCE_READER) through the same callbacks
+    got = eng.compact_stream(runs, keep, bloom_min_size=10_000, seed=SEED, flags=capi.FLAG_REFERENCE_READER)
+    assert_run_equal(got[:2], exp[:2], f"stream, reference reader {seed}")
+
+
+def test_compact_stream_returns_the_callbacks_error_code(tiny_partition_engine):
+    eng = tiny_partition_engine
+    runs = W.make_merge_runs(W.scaled(W.CFG2, 3000))
+    for kw in ({"fail_read_at": 0}, {"fail_read_at": 200}, {"fail_write_at": 0}, {"fail_write_at": 7}):
+        with pytest.raises(capi.DbeelError) as ei:
+            eng.compact_stream(runs, False, bloom_min_size=10_000, seed=SEED, **kw)
+        assert ei.value.code == 4242, kw
+    # the engine is usable afterwards
+    exp = oracle.compact(runs, False, bloom_min_size=10_000, seed=SEED)
+    got = eng.compact_stream(runs, False, bloom_min_size=10_000, seed=SEED)
+    assert_run_equal(got[:2], exp[:2], "stream after failures")
