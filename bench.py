@@ -258,7 +258,7 @@ def file_fed_job(eng, expected):
             if k < 2:
                 shutil.rmtree(d)
         res["streamed"] = {"value": round(in_bytes / 1e6 / best, 1), "ms": round(best * 1e3, 1), "partitions": st["partitions"],
-                           "api": "dbeel_tree_compact -> dbeel_compact_stream (pread / pwrite threads <-> pinned rings <-> H2D / kernels / D2H)"}
+                           "api": "dbeel_tree_compact -> dbeel_compact_stream (pread threads -> pinned ring -> H2D / kernels / D2H -> pinned ring -> writer threads copying into the mapped output files)"}
         if expected is not None:
             gd, gi = sstable.read_run_files(d, out_index)
             gb = np.fromfile(os.path.join(d, sstable.file_name(out_index, "bloom")), dtype=np.uint8)

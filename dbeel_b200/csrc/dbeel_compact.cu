@@ -165,7 +165,7 @@ int stream_threads() {
     static const int n = [] {
         if (const char *v = getenv("DBEEL_IO_THREADS")) return std::max(1, atoi(v));
         const unsigned hw = std::thread::hardware_concurrency();
-        return (int)std::min(8u, std::max(1u, hw / 2));
+        return (int)std::min(8u, std::max(2u, hw / 8)); // readers and writers each (measured on the 128-thread box: 8 + 8 = 16 + 16, 32 + 32 loses)
     }();
     return n;
 }
