@@ -85,7 +85,8 @@ struct dbeel_engine {
     int sm_count = 148;
     int merge_variant = 1;      // DBEEL_MERGE: 0 = one CTA per tile with plain loads, 1 = persistent TMA (default)
     int narrow_loads = 1;       // DBEEL_NARROW: .L2::64B loads for random accesses in extract / resolve (A/B switch)
-    int gather_variant = 1;     // DBEEL_GATHER: 0 = 16 bytes per lane (k_gather), 1 = 32 bytes per lane + 256-bit stores (k_gather32),
+    int gather_variant = 10;    // DBEEL_GATHER: 10 = k_gather32 with the lean entry-boundary pass (default), 0 = 16 bytes per lane (k_gather),
+                                //               1 = 32 bytes per lane + 256-bit stores (k_gather32, round 1's boundary pass),
                                 //               2 = 1 with the payload staged into shared memory by TMA bulk copies (k_gather_tma)
     int fused_emit = 0;         // DBEEL_FUSED_EMIT: 1 = resolve + offsets scan + .index writes in one kernel (single jobs), 0 = four kernels
     int bloom_side = 0;         // DBEEL_BLOOM_SIDE: 1 = k_bloom_res on a second stream (measured: kernels of two streams do not co-run, the
@@ -620,6 +621,8 @@ int run_job_device(dbeel_engine *e, const dbeel_run *runs, uint32_t n_runs, cons
             launch_k(e, k_gather_fb, (uint32_t)gather_tiles, kFbThreads, 0, s, p);
         } else if (e->gather_variant == 7 && al32) { // payload lands in shared memory (cp.async), boundary blocks + filter while it travels
             launch_k(e, k_gather_async, (uint32_t)gather_tiles, kGatherThreads, 0, s, p);
+        } else if (e->gather_variant >= 9 && al32) { // the default: k_gather32 with the lean entry-boundary pass (LDG.E.256, one store per block)
+            launch_k(e, k_gather32<false, false, false, true>, (uint32_t)gather_tiles, kGatherThreads, 0, s, p);
         } else if (e->gather_variant == 5 && al32) { // k_gather32, boundary blocks and filter on different warps (no gain)
             launch_k(e, k_gather32<false, true, false>, (uint32_t)gather_tiles, kGatherThreads, 0, s, p);
         } else if (e->gather_variant == 6 && al32 && p.bloom.words != nullptr && p.hash_rec == nullptr && !p.bloom_elsewhere &&

@@ -203,6 +203,29 @@ DB_HD void realign16(const uint32_t A[4], const uint32_t B[4], uint32_t sh, uint
     out[3] = funnel_r(w3, w4, bits);
 }
 
+// 32 output bytes starting `s0` (0..31) bytes into the 64-byte window w[0..16) (little-endian words, lower address first).
+// Words of the window that hold no wanted byte may contain anything.
+DB_HD void window32(const uint32_t w[16], uint32_t s0, uint32_t out[8]) {
+    const uint32_t bits = (s0 & 3) * 8;
+    const bool s4 = (s0 & 16) != 0, s2 = (s0 & 8) != 0, s1 = (s0 & 4) != 0;
+    uint32_t c[13], d[11], e[9]; // after the 16-, 8- and 4-byte steps
+    for (int i = 0; i < 12; i++) c[i] = s4 ? w[i + 4] : w[i];
+    c[12] = s4 ? 0u : w[12]; // only read when the shift is below 16 bytes
+    for (int i = 0; i < 11; i++) d[i] = s2 ? c[i + 2] : c[i];
+    for (int i = 0; i < 9; i++) e[i] = s1 ? d[i + 1] : d[i];
+    for (int i = 0; i < 8; i++) out[i] = funnel_r(e[i], e[i + 1], bits);
+}
+
+// out = bytes [0, t) of T followed by bytes [t, 32) of H, t in 0..32.
+DB_HD void blend32(const uint32_t T[8], const uint32_t H[8], uint32_t t, uint32_t out[8]) {
+    const uint32_t wfull = t >> 2, bits = (t & 3) * 8;
+    const uint32_t mmix = bits ? (0xFFFFFFFFu >> (32 - bits)) : 0u;
+    for (uint32_t q = 0; q < 8; q++) {
+        const uint32_t mk = q < wfull ? 0xFFFFFFFFu : (q == wfull ? mmix : 0u);
+        out[q] = (T[q] & mk) | (H[q] & ~mk);
+    }
+}
+
 // ------------------------------------------------------------------------------------
 // i128 timestamp order (mod.rs:80) on the two little-endian halves.
 

@@ -1725,6 +1725,24 @@ __device__ __forceinline__ uint4 ld16_any(uintptr_t sa, uint32_t need) {
     return realign16_sel(TA, TB, s0);
 }
 
+__device__ __forceinline__ void ldg256_nc(const void *p, uint32_t v[8]) { // LDG.E.256 (sm_100): one 32-byte aligned chunk
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
+}
+
+// 32 bytes at an arbitrary address of which bytes [lo, hi) are wanted (0 <= lo < hi <= 32): only the aligned 32-byte chunks
+// that hold wanted bytes are loaded (a lane that needs one chunk costs the L1 data pipe one wavefront, not two)
+__device__ __forceinline__ void ld32_any(uintptr_t a, uint32_t lo, uint32_t hi, uint32_t out[8]) {
+    const uint32_t s0 = (uint32_t)(a & 31);
+    const uintptr_t base = a - s0;
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = 0u;
+    if (lo < 32u - s0) ldg256_nc(reinterpret_cast<const void *>(base), w);          // chunk 0 = bytes [0, 32 - s0) of the block
+    if (hi > 32u - s0) ldg256_nc(reinterpret_cast<const void *>(base + 32), w + 8); // chunk 1 = bytes [32 - s0, 32)
+    window32(w, s0, out);
+}
+
 constexpr int kG32Vpt = (int)(kGatherTileBytes / (32ull * kGatherThreads)); // 1 KB chunks per warp
 static_assert(kGatherTileBytes == 32ull * kGatherThreads * kG32Vpt, "gather tile = 32 bytes x lanes x chunks");
 
@@ -1749,7 +1767,14 @@ static_assert(kGatherTileBytes == 32ull * kGatherThreads * kG32Vpt, "gather tile
 // microseconds either way: an L2 hit for whichever comes second.  Block b is a filter block iff floor((b+1) nb / G) >
 // floor(b nb / G) (nb filter blocks spread evenly over the G blocks of the grid); it is filter block floor(b nb / G), and
 // a copy block is tile b - floor(b nb / G).
-template <bool kBloomWarp, bool kRot, bool kSplit>
+// kLean (the default since round 2, DBEEL_GATHER=10; 1 = the two-halves pass below): the entry-boundary blocks with fewer trips
+// through the L1 data pipe, where every lane's access is a wavefront of its own (ncu: the kernel's busiest unit; of its ~750
+// wavefronts per tile the copy proper is a quarter, the boundary blocks 216, the key loads 162, the filter's REDs 189).  The
+// tail of entry j and the head of entry j + 1 each come from the aligned 32-byte chunks that hold wanted bytes (LDG.E.256,
+// one or two per side), are blended in registers and leave in one 256-bit store: ~4 accesses per entry instead of 6 loads +
+// 2 stores.  0.924 -> 0.877 ms on the cfg2 job.  The same idea applied to the key loads (two aligned 16-byte chunks per key,
+// or two lanes per key with one SipHash each) measured SLOWER (0.95-1.26 ms): profiles/r02_experiments.md.
+template <bool kBloomWarp, bool kRot, bool kSplit, bool kLean = false>
 __global__ void __launch_bounds__(kGatherThreads + (kBloomWarp ? 32 : 0), kBloomWarp ? DBEEL_GATHER32W_MINB : DBEEL_GATHER32_MINB)
 k_gather32(Params p) {
     pdl_trigger();
@@ -1867,8 +1892,28 @@ k_gather32(Params p) {
         }
     }
 
-    // ---- the 32-byte block that holds the last byte of entry j (unless j ends on a block boundary): its two halves
-    for (uint32_t j = kRot ? (tid + NT - 96u) % NT : tid; j < ne; j += NT) {
+    // ---- the 32-byte block that holds the last byte of entry j (unless j ends on a block boundary)
+    if (kLean) {
+        for (uint32_t j = tid; j < ne; j += NT) {
+            const int r1 = s_r1[j];
+            if (r1 <= 0 || (r1 & 31) == 0 || r1 > (int)tile_len) continue;
+            const uint32_t b0 = (uint32_t)r1 & ~31u, t = (uint32_t)r1 - b0; // t = 1..31 bytes of entry j in this block
+            uint32_t T[8];
+            ld32_any((uintptr_t)(s_adj[j] + b0), 0u, t, T);
+            if (b0 + 32u <= tile_len) { // the rest of the block is the head of entry j + 1 (entries are >= 32 bytes)
+                uint32_t H[8], O[8];
+                ld32_any((uintptr_t)(s_adj[j + 1] + b0), t, 32u, H);
+                blend32(T, H, t, O);
+                stg256(dst_tile + b0, O);
+            } else { // ragged end of the whole stream: never write past out_data_len
+                uint32_t tw[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) tw[q] = T[q];
+                for (uint32_t b = 0; b < t; b++) dst_tile[b0 + b] = (uint8_t)(tw[b >> 2] >> ((b & 3) * 8));
+            }
+        }
+    }
+    for (uint32_t j = kLean ? ne : (kRot ? (tid + NT - 96u) % NT : tid); j < ne; j += NT) {
         const int r1 = s_r1[j];
         if (r1 <= 0 || (r1 & 31) == 0 || r1 > (int)tile_len) continue;
         const bool has_next = j + 1 < ne;

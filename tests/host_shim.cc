@@ -55,6 +55,21 @@ void shim_realign16(const uint8_t src32[32], uint32_t sh, uint8_t out16[16]) {
     memcpy(out16, O, 16);
 }
 
+void shim_window32(const uint8_t src64[64], uint32_t s0, uint8_t out32[32]) {
+    uint32_t w[16], o[8];
+    memcpy(w, src64, 64);
+    window32(w, s0, o);
+    memcpy(out32, o, 32);
+}
+
+void shim_blend32(const uint8_t t32[32], const uint8_t h32[32], uint32_t t, uint8_t out32[32]) {
+    uint32_t T[8], H[8], O[8];
+    memcpy(T, t32, 32);
+    memcpy(H, h32, 32);
+    blend32(T, H, t, O);
+    memcpy(out32, O, 32);
+}
+
 int shim_ts_decodes(const uint8_t ts[16]) {
     uint64_t lo, hi;
     memcpy(&lo, ts, 8); memcpy(&hi, ts + 8, 8);

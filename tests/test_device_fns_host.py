@@ -37,6 +37,8 @@ def shim():
     L.shim_rec_cmp.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
     L.shim_sip_pair.argtypes = [C.POINTER(C.c_uint64), C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.shim_realign16.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p]
+    L.shim_window32.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p]
+    L.shim_blend32.argtypes = [C.c_char_p, C.c_char_p, C.c_uint32, C.c_char_p]
     L.shim_ts_decodes.restype = C.c_int
     L.shim_ts_decodes.argtypes = [C.c_char_p]
     L.shim_ts_greater.restype = C.c_int
@@ -161,3 +163,21 @@ def test_murmur3_32_and_ring_owner(shim):
         for h in probes:
             h %= 2**32
             assert shim.shim_ring_owner(sub.ctypes.data, n, h) == oracle.ring_owner(sub, h), (n, h)
+
+
+def test_window32_and_blend32(shim):
+    """The 32-byte realignment of the gather's entry-boundary blocks: any 32 bytes out of a 64-byte window, and the blend of the
+    tail of one entry with the head of the next at any byte."""
+    rng = np.random.default_rng(17)
+    for _ in range(200):
+        src = bytes(rng.integers(0, 256, 64, dtype=np.uint8))
+        for s0 in range(32):
+            out = C.create_string_buffer(32)
+            shim.shim_window32(src, s0, out)
+            assert out.raw == src[s0:s0 + 32], s0
+    for _ in range(50):
+        t32, h32 = bytes(rng.integers(0, 256, 32, dtype=np.uint8)), bytes(rng.integers(0, 256, 32, dtype=np.uint8))
+        for t in range(33):
+            out = C.create_string_buffer(32)
+            shim.shim_blend32(t32, h32, t, out)
+            assert out.raw == t32[:t] + h32[t:], t
