@@ -3,14 +3,14 @@
 # parity suite and memcheck with the variants selected
 mkdir -p gpurun_out
 nvidia-smi -L | head -1
-timeout 600 python tools/tune.py "" "DBEEL_GATHER=10" "DBEEL_GATHER=9" "DBEEL_GATHER=11" "DBEEL_GATHER=12" "DBEEL_RESOLVE_TS16=1" "DBEEL_GATHER=10,DBEEL_RESOLVE_TS16=1" "DBEEL_GATHER=9,DBEEL_RESOLVE_TS16=1" "" 2>&1 | grep -v "^\[" | tee gpurun_out/ab_lean.txt
-for v in 9 11; do
-echo "=== parity suite with DBEEL_GATHER=$v DBEEL_RESOLVE_TS16=1"
-DBEEL_GATHER=$v DBEEL_RESOLVE_TS16=1 timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_reference_reader.py tests/test_host_tree.py tests/test_gpu_cfg5.py -m gpu -x -q 2>&1 | tail -3 | tee gpurun_out/pytest_lean_$v.txt
+timeout 600 python tools/tune.py "" "DBEEL_GATHER=13" "DBEEL_GATHER=14" "DBEEL_GATHER=15" "DBEEL_GATHER=1" "" 2>&1 | grep -v "^\[" | tee gpurun_out/ab_lean.txt
+for v in 15; do
+echo "=== parity suite with DBEEL_GATHER=$v"
+DBEEL_GATHER=$v timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_reference_reader.py tests/test_host_tree.py tests/test_gpu_cfg5.py -m gpu -x -q 2>&1 | tail -3 | tee gpurun_out/pytest_lean_$v.txt
 done
 echo "=== memcheck"
-for v in 9 11; do
-DBEEL_GATHER=$v DBEEL_RESOLVE_TS16=1 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -c "
+for v in 15; do
+DBEEL_GATHER=$v timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -c "
 import numpy as np
 from dbeel_b200 import capi, workloads as W
 import oracle
