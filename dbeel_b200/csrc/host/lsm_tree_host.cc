@@ -5,6 +5,7 @@
 #include <string.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/statvfs.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -472,7 +473,13 @@ static int tree_compact_streamed(dbeel_tree *t, const uint64_t *indices_to_compa
     opts.bloom_seed = bloom_seed;
     if (stream_maps()) { // size every output to its bound and map it (see StreamFiles)
         uint64_t cap[4] = {0, 0, 0, 0};
-        if (dbeel_compact_bound(runs.data(), n, &opts, &cap[1], &cap[2], &cap[3]) == DBEEL_OK) {
+        // A store into a mapped page the file system cannot back raises SIGBUS where pwrite would return ENOSPC: only map when
+        // the volume has room for the bounds (plus slack); otherwise the writers go through pwrite and a full disk is an error code.
+        struct statvfs vfs;
+        bool room = false;
+        if (dbeel_compact_bound(runs.data(), n, &opts, &cap[1], &cap[2], &cap[3]) == DBEEL_OK && fstatvfs(f.out_fd[1], &vfs) == 0)
+            room = (uint64_t)vfs.f_bavail * (uint64_t)vfs.f_frsize >= cap[1] + cap[2] + cap[3] + (64ull << 20);
+        if (room) {
             for (int k = 1; k <= 3; k++) {
                 if (!cap[k] || ftruncate(f.out_fd[k], (off_t)cap[k]) != 0) continue;
                 void *m = mmap(nullptr, cap[k], PROT_READ | PROT_WRITE, MAP_SHARED, f.out_fd[k], 0);
@@ -494,9 +501,11 @@ static int tree_compact_streamed(dbeel_tree *t, const uint64_t *indices_to_compa
     }
     f.unmap();
     const uint64_t lens[4] = {0, out.data_len, out.index_len, out.bloom_len};
-    for (int k = 1; k <= 3; k++) { // a redone job may have written past the final length
-        if (ftruncate(f.out_fd[k], (off_t)lens[k]) != 0 || close(f.out_fd[k]) != 0) { f.out_fd[k] = -1; rc = io_fail(t, "close " + cpath[k]); drop_outputs(); return rc; }
+    for (int k = 1; k <= 3; k++) { // cut to the final length (the files were sized to their bounds; a redone job may have written past it)
+        const bool cut = ftruncate(f.out_fd[k], (off_t)lens[k]) == 0;
+        const bool closed = close(f.out_fd[k]) == 0;
         f.out_fd[k] = -1;
+        if (!cut || !closed) { rc = io_fail(t, "close " + cpath[k]); drop_outputs(); return rc; }
     }
     if (!out.bloom_len) unlink(cpath[3].c_str()); // no filter: no .bloom file (lsm_tree.rs:1068-1076)
     return commit_written(t, indices_to_compact, n, output_index, out.items_written);
