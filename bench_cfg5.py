@@ -9,7 +9,7 @@ import numpy as np
 
 from dbeel_b200 import capi
 from dbeel_b200 import storage_engine as se
-from dbeel_b200.cfg5 import (CAPACITY, CFG5_IDS, CFG5_WRITES, DOC_BYTES, FACTOR, N_SHARDS, ZIPF_S, build_stream_device, own_positions,
+from dbeel_b200.cfg5 import (CAPACITY, CFG5_IDS, CFG5_WRITES, DOC_BYTES, FACTOR, N_SHARDS, ZIPF_S, build_stream_device, own_positions, ring_arcs,
                              pipeline, stream_ids)
 
 # ------------------------------------------------------------------------------------ the checker
@@ -94,7 +94,7 @@ def bench(args, torch, dist, dev, rank, world, local, ClockSampler, hbm_peak, ME
     log(f"[cfg5 r{rank}] {n_writes} arrivals, {total / 1e9:.2f} GB of .data resident in HBM ({time.time() - t:.0f}s)")
     eng = capi.Engine(local)
     ring, ring_ids = capi.shard_ring(N_SHARDS)
-    mine = own_positions(rank, world)
+    mine = own_positions(rank, world, ring)
     steps = max(1, min(args.steps, 5))
     warm = max(1, min(args.warmup, 2))
 
@@ -153,7 +153,9 @@ def bench(args, torch, dist, dev, rank, world, local, ClockSampler, hbm_peak, ME
                 "config": {"workload": f"cfg5: {n_writes} Zipf({ZIPF_S}) writes over {n_ids} keys x {DOC_BYTES} B docs, {N_SHARDS} shards by "
                                        f"murmur3_32 ring of dbeel-0..7, memtables of {CAPACITY} keys, size-tiered picker factor {FACTOR}",
                            "arrival_bytes": int(total_bytes), "memtables": int(sm[2]), "compactions": int(sm[3]),
-                           "shards_per_gpu": len(mine), "ring_ids": [int(x) for x in ring_ids],
+                           "ring_positions_rank0": [int(x) for x in mine], "ring_ids": [int(x) for x in ring_ids],
+                           "ring_arcs": [round(float(x), 4) for x in ring_arcs(ring)],
+                           "placement": "ring positions dealt out by arc length, longest first, each to the least loaded rank",
                            "timing": "wall clock of route + cut + flush waves + picker rounds per rank (device synchronised), max over ranks"},
                 "kernel_ms_per_step": round(float(tm[1]) / steps, 3),
                 "kernel_value": round(total_bytes * steps / 1e6 / (float(tm[1]) / 1e3), 1),

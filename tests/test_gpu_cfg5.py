@@ -21,7 +21,7 @@ def test_cfg5_pipeline_matches_the_oracle(engine, n_writes, capacity, factor, wa
     data_host = data.cpu().numpy()
     seen = 0
     for rank in range(world):  # the ranks of an N-GPU run, one after the other on this GPU
-        res = cfg5.pipeline(engine, torch, dev, data, index, ring, cfg5.own_positions(rank, world), wave=wave, capacity=capacity, factor=factor)
+        res = cfg5.pipeline(engine, torch, dev, data, index, ring, cfg5.own_positions(rank, world, ring), wave=wave, capacity=capacity, factor=factor)
         assert not res["short"], res["short"]
         ok, _, _, why = bench_cfg5.check_against_oracle(res, data_host, res["routed"][:index.numel()].cpu().numpy(), capacity=capacity)
         assert ok, why

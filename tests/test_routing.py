@@ -75,6 +75,27 @@ def _arrivals(n, seed=5, nasty=False):
     return sstable.build_run(ents)
 
 
+def test_cfg5_shard_placement_balances_the_ring():
+    """dbeel_b200/cfg5.own_positions: every ring position goes to exactly one rank, the same table on every rank, and the ranks'
+    shares of the hash space are as even as the (very uneven, no virtual nodes) arcs of dbeel-0..7 allow."""
+    from dbeel_b200 import cfg5
+    ring, _ = capi.shard_ring(8)
+    arcs = cfg5.ring_arcs(ring)
+    assert abs(float(arcs.sum()) - 1.0) < 1e-12 and (arcs > 0).all()
+    # the arc of a position is the share of uniformly drawn hashes the ring routes to it
+    rng = np.random.default_rng(5)
+    hs = rng.integers(0, 2**32, 200_000, dtype=np.uint64)
+    owners = np.array([capi.ring_owner(ring, int(h)) for h in hs[:20_000]])
+    got = np.bincount(owners, minlength=8) / 20_000
+    assert np.abs(got - arcs).max() < 0.01
+    for world in (1, 2, 4, 8):
+        parts = [cfg5.own_positions(r, world, ring) for r in range(world)]
+        assert sorted(sum(parts, [])) == list(range(8))
+        loads = [float(sum(arcs[p] for p in ps)) for ps in parts]
+        assert max(loads) <= max(float(arcs.max()), 1.0 / world + 0.02), (world, loads)
+    assert cfg5.own_positions(1, 2) == [4, 5, 6, 7]  # without a ring: contiguous blocks
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("n,n_shards,nasty", [(1, 8, False), (255, 8, False), (257, 3, True), (5000, 8, True), (70_000, 8, False),
                                                (33_333, 1, False), (20_000, 64, True), (9_000, 256, False)])
