@@ -181,21 +181,16 @@ def pipeline(eng, torch, dev, data, index, ring: np.ndarray, positions, wave: in
     calls += 1
     starts = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint64)
     positions = sorted(int(x) for x in positions)
-    cuts_of: Dict[int, list] = {}
-    k0 = 0
-    while k0 < len(positions):  # one call per block of neighbouring ring positions (their streams lie back to back)
-        k1 = k0
-        while k1 + 1 < len(positions) and positions[k1 + 1] == positions[k1] + 1:
-            k1 += 1
-        p0, p1 = positions[k0], positions[k1] + 1
-        cuts = eng.memtable_cuts_device(h64.data_ptr(), starts[p0:p1 + 1], capacity)
-        st = eng.stats()
-        ms["cut"] += st["ms_total"]
-        launches += st["kernel_launches"]
-        calls += 1
-        for k, pos in enumerate(range(p0, p1)):
-            cuts_of[pos] = cuts[k]
-        k0 = k1 + 1
+    # ONE call over the block of ring positions that covers the own ones: the kernel walks every stream with a CTA of its own, so
+    # the call takes as long as its longest stream whatever else runs next to it -- foreign streams in between cost nothing,
+    # while one call per run of neighbouring positions would walk those runs one after the other (measured: 51 ms instead of 22).
+    p0, p1 = positions[0], positions[-1] + 1
+    cuts = eng.memtable_cuts_device(h64.data_ptr(), starts[p0:p1 + 1], capacity)
+    st = eng.stats()
+    ms["cut"] += st["ms_total"]
+    launches += st["kernel_launches"]
+    calls += 1
+    cuts_of = {pos: cuts[k] for k, pos in enumerate(range(p0, p1))}
     # memtables of every own shard: (first arrival, arrivals) inside the shard's stream; the tail that never filled is
     # flushed too (what a shutdown / the recovery flush of open_or_create_ex does, lsm_tree.rs:478-513)
     mem: Dict[int, List] = {}
