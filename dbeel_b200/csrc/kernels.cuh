@@ -1173,7 +1173,7 @@ __global__ void __launch_bounds__(kResolveThreads, kFused ? DBEEL_RESOLVE_FUSED_
         // Arrival batches: the winner of a group of equal keys is simply its LAST member (RedBlackTree::set replaces in place,
         // lib.rs:509-511), and every member knows locally whether it is the last one.  No walk over the group: a hot key of a
         // Zipf stream fills hundreds of consecutive positions of a memtable, and a head thread stepping through them one
-        // dependent load at a time was 93 % of the flush (10.6 of 11.4 ms for 60 memtables, profiles/r02_cfg5.md).
+        // dependent load at a time was 93 % of the flush (10.6 of 11.4 ms for 60 memtables).
         if (active && !eq_next) {
             keep = 1; // tombstones are ordinary entries of a flush (lsm_tree.rs:790-795)
             ks = s_ks[tid]; fs = s_fs[tid]; src = s_entry[tid];
