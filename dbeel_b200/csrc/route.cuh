@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(kRouteThreads) k_route_scatter(RouteParams p) 
 // ------------------------------------------------------------------------------------
 // Memtable-full trigger on the device (a11: lsm_tree.rs:747-765, the flush starts right after the insert that makes the
 // tree hold `capacity` keys).  Input: one shard's stream of 64-bit key identities in arrival order; output: where every
-// memtable ends.  One CTA per stream walks it 2048 arrivals at a time with a hash SET of the current memtable's keys in
+// memtable ends.  One CTA per stream walks it 1024 arrivals at a time with a hash SET of the current memtable's keys in
 // shared memory: insert (CAS), decide which thread of the chunk saw each new key FIRST (atomicMin of the thread index),
 // prefix-sum those flags, and cut at the arrival that brings the count to `capacity`.
 //
@@ -151,8 +151,12 @@ __global__ void __launch_bounds__(kRouteThreads) k_route_scatter(RouteParams p) 
 // memtable one key too large.  The flush reports every memtable's exact distinct count, so callers verify
 // items == capacity for every memtable but the last of a stream and fall back to dbeel_memtable_cut (exact, host) if not.
 
+// Round 2 also tried 2048 arrivals per step with the next step prefetched (16.8 ms for the cfg5 stream instead of 22.3) and, on
+// top of that, one table access per warp and key (__match_any_sync + a shuffle): the latter measured 33.0 ms on the same stream
+// (profiles/r02_v5_bench_cfg5_n2.json, r02_v6_bench_cfg5.json) -- match.any costs more than the contention it removes.  This is
+// the version of profiles/r02_v2_bench_cfg5.json (22.3 ms), restored as it was measured and tested.
 constexpr uint32_t kCutSlots = 16384; // shared memory: 128 KB of identities + 64 KB of first-seen thread ids
-constexpr uint32_t kCutMaxCapacity = 9216; // load factor <= (capacity + 2048) / slots = 0.69
+constexpr uint32_t kCutMaxCapacity = 9216; // load factor <= (capacity + 1024) / slots = 0.625
 
 struct CutParams {
     const unsigned long long *hash64; // shard-major
@@ -179,63 +183,33 @@ __global__ void __launch_bounds__(1024) k_memtable_cuts(CutParams p) {
     uint32_t *cuts = p.cuts + p.cut_base[stream];
     for (uint32_t k = tid; k < kCutSlots; k += 1024) { tab[k] = 0; first[k] = 0; }
     __syncthreads();
-    // Two arrivals per thread (a step covers 2048), the next step's identities fetched while this one is worked on: the
-    // walk is sequential by nature (a cut decides where the next memtable starts), so what counts is the time per step.
-    constexpr uint32_t kStep = 2048;
     uint32_t pos = 0, count = 0, ncut = 0;
-    auto ld2 = [&](uint32_t at, unsigned long long *a, unsigned long long *b) {
-        const uint64_t i0 = (uint64_t)at + 2u * tid;
-        *a = i0 < n ? h64[i0] : 0ull;
-        *b = i0 + 1 < n ? h64[i0 + 1] : 0ull;
-    };
-    unsigned long long n0, n1;
-    ld2(0, &n0, &n1);
     while (pos < n) {
-        const uint32_t k0 = 2u * tid, k1 = k0 + 1; // positions inside the step, in arrival order
-        const bool act0 = (uint64_t)pos + k0 < n, act1 = (uint64_t)pos + k1 < n;
-        unsigned long long h[2] = {n0, n1};
-        if ((uint64_t)pos + kStep < n) ld2(pos + kStep, &n0, &n1); // right unless this step ends in a cut (one step in ~8)
-        const bool act[2] = {act0, act1};
-        uint32_t slot[2] = {0, 0};
-        bool won[2] = {false, false};
-        // A Zipf stream puts its hottest key into ~6 % of the arrivals: one lane per warp and key goes to the table (the lowest,
-        // i.e. the earliest arrival), its peers take the slot from it -- 32 contenders per hot slot instead of ~120.
-        bool lead[2] = {false, false};
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-            if (act[q] && h[q] == 0) h[q] = 1; // 0 marks an empty slot (and the lanes past the end of the stream)
-            const unsigned long long hv = act[q] ? h[q] : 0ull;
-            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, hv);
-            const uint32_t leader = (uint32_t)__ffs((int)peers) - 1u;
-            lead[q] = act[q] && (tid & 31u) == leader;
-            uint32_t sl = 0;
-            if (lead[q]) {
-                sl = (uint32_t)(hv ^ (hv >> 29)) & (kCutSlots - 1);
-                while (true) {
-                    const unsigned long long cur = atomicCAS(&tab[sl], 0ull, hv);
-                    if (cur == 0) { won[q] = true; break; }
-                    if (cur == hv) break;
-                    sl = (sl + 1) & (kCutSlots - 1);
-                }
+        const uint32_t i = pos + tid;
+        const bool act = i < n;
+        unsigned long long h = act ? h64[i] : 0;
+        if (act && h == 0) h = 1; // 0 marks an empty slot
+        uint32_t slot = 0;
+        bool won = false;
+        if (act) {
+            slot = (uint32_t)(h ^ (h >> 29)) & (kCutSlots - 1);
+            while (true) {
+                const unsigned long long cur = atomicCAS(&tab[slot], 0ull, h);
+                if (cur == 0) { won = true; break; }
+                if (cur == h) break;
+                slot = (slot + 1) & (kCutSlots - 1);
             }
-            slot[q] = __shfl_sync(0xFFFFFFFFu, sl, leader);
         }
         if (tid == 0) s_cut = 0xFFFFFFFFu;
-#pragma unroll
-        for (int q = 0; q < 2; q++)
-            if (won[q]) first[slot[q]] = 0xFFFFFFFFu; // new in this step: the position of its first arrival goes here
+        if (won) first[slot] = 0xFFFFFFFFu; // new in this chunk: someone's thread id goes here
         __syncthreads();
-#pragma unroll
-        for (int q = 0; q < 2; q++)
-            if (lead[q] && first[slot[q]] != 0) atomicMin(&first[slot[q]], (q ? k1 : k0) + 1); // the leader is its group's earliest arrival
+        if (act && first[slot] != 0) atomicMin(&first[slot], tid + 1);
         __syncthreads();
-        const uint32_t f0 = (act0 && first[slot[0]] == k0 + 1) ? 1u : 0u;
-        const uint32_t f1 = (act1 && first[slot[1]] == k1 + 1) ? 1u : 0u;
+        const uint32_t flag = (act && first[slot] == tid + 1) ? 1u : 0u;
         unsigned long long vb = 0, tb;
-        uint32_t vc = f0 + f1, tc;
+        uint32_t vc = flag, tc;
         block_excl_scan_1024(vb, vc, s_b, s_c, &tb, &tc);
-        if (f0 && count + vc + 1 == p.capacity) s_cut = k0; // the insert that fills the tree
-        if (f1 && count + vc + f0 + 1 == p.capacity) s_cut = k1;
+        if (flag && count + vc + 1 == p.capacity) s_cut = tid; // the insert that fills the tree
         __syncthreads();
         const uint32_t cut = s_cut;
         if (cut != 0xFFFFFFFFu) {
@@ -244,13 +218,10 @@ __global__ void __launch_bounds__(1024) k_memtable_cuts(CutParams p) {
             ncut++;
             count = 0;
             for (uint32_t k = tid; k < kCutSlots; k += 1024) { tab[k] = 0; first[k] = 0; }
-            ld2(pos, &n0, &n1); // the step after a cut starts right behind it
         } else {
-#pragma unroll
-            for (int q = 0; q < 2; q++)
-                if (won[q]) first[slot[q]] = 0; // the key is old news for the steps that follow
+            if (won) first[slot] = 0; // the key is old news for the chunks that follow
             count += tc;
-            pos += kStep;
+            pos += 1024;
         }
         __syncthreads();
     }
