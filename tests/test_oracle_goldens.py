@@ -426,3 +426,71 @@ def test_timestamp_range_check_restated():
     assert oracle.timestamp_decodes(lo) and not oracle.timestamp_decodes(lo - 1)
     assert oracle.timestamp_decodes(hi) and not oracle.timestamp_decodes(hi + 1)
     assert oracle.timestamp_decodes(10**9 << 64)  # 2^64 seconds wrap to 0: the cast, not the value, is range-checked
+
+
+# ----------------------------------------------------------------------------- bloom, second restatement
+
+def _py_siphash13(k0: int, k1: int, msg: bytes) -> int:
+    """SipHash-1-3 written out in Python from the algorithm's definition (c = 1 compression round, d = 3 finalisation rounds),
+    independent of the C oracle; pinned below on the same CPython vectors as the oracle's."""
+    M = (1 << 64) - 1
+    rotl = lambda v, b: ((v << b) | (v >> (64 - b))) & M
+    v0, v1, v2, v3 = k0 ^ 0x736F6D6570736575, k1 ^ 0x646F72616E646F6D, k0 ^ 0x6C7967656E657261, k1 ^ 0x7465646279746573
+
+    def rnd():
+        nonlocal v0, v1, v2, v3
+        v0 = (v0 + v1) & M; v1 = rotl(v1, 13); v1 ^= v0; v0 = rotl(v0, 32)
+        v2 = (v2 + v3) & M; v3 = rotl(v3, 16); v3 ^= v2
+        v0 = (v0 + v3) & M; v3 = rotl(v3, 21); v3 ^= v0
+        v2 = (v2 + v1) & M; v1 = rotl(v1, 17); v1 ^= v2; v2 = rotl(v2, 32)
+
+    n = len(msg)
+    for i in range(0, n - n % 8, 8):
+        m = int.from_bytes(msg[i:i + 8], "little")
+        v3 ^= m; rnd(); v0 ^= m
+    m = int.from_bytes(msg[n - n % 8:] + bytes(8 - n % 8), "little") | ((n & 0xFF) << 56)
+    v3 ^= m; rnd(); v0 ^= m
+    v2 ^= 0xFF
+    rnd(); rnd(); rnd()
+    return v0 ^ v1 ^ v2 ^ v3
+
+
+def test_bloom_file_against_an_independent_python_model():
+    """The whole .bloom file a compaction writes, rebuilt in Python from the crates' definitions as SURVEY A.4 records them --
+    Hash for Vec<u8> = write_usize(len) ++ bytes into two SipHasher13 (keys = seed[0:16], seed[16:32]); bit i of key =
+    g_i % bitmap_bits with g_0 = h0, g_1 = h1, g_i = (h0 + i*h1 mod 2^64) % (2^64 - 59); BitVec<u32> storage, bit b of word
+    w = position 32 w + b; bincode: n_words, words, nbits, bitmap_bits, k_num, 2 x (k0, k1, length, v0, v2, v1, v3, tail, ntail)
+    -- and compared byte for byte with the oracle's.  A second restatement, not a pin on the crate (its source is not in this
+    image): it guards the C oracle against slips of its own."""
+    vec = json.load(open(os.path.join(GOLDEN, "siphash13_cpython.json")))["vectors"]
+    for x in vec:
+        assert _py_siphash13(x["k0"], x["k1"], bytes.fromhex(x["msg"])) == oracle.siphash13(x["k0"], x["k1"], bytes.fromhex(x["msg"]))
+    rng = np.random.default_rng(77)
+    keys = sorted({bytes(rng.integers(0, 256, int(rng.integers(1, 40)), dtype=np.uint8)) for _ in range(700)})
+    ents = [(k, bytes(rng.integers(0, 256, 150, dtype=np.uint8)), BASE_TS + j) for j, k in enumerate(keys)]
+    runs = [sstable.build_run(ents[:400]), sstable.build_run(ents[300:])]
+    seed = bytes(rng.integers(0, 256, 32, dtype=np.uint8))
+    d, i, bloom, n = oracle.compact(runs, False, bloom_min_size=10_000, seed=seed)
+    assert bloom is not None and n == len(keys)
+    items = 400 + (len(keys) - 300)  # sized for the input entries
+    nbytes = oracle.bloom_bitmap_bytes(items)
+    bits, k_num = nbytes * 8, oracle.bloom_k_num(nbytes * 8, items)
+    n_words = (bits + 31) // 32
+    words = np.zeros(n_words, dtype=np.uint32)
+    sk = [int.from_bytes(seed[8 * q:8 * q + 8], "little") for q in range(4)]
+    P = (1 << 64) - 59
+    for k in keys:
+        msg = len(k).to_bytes(8, "little") + k
+        h0, h1 = _py_siphash13(sk[0], sk[1], msg), _py_siphash13(sk[2], sk[3], msg)
+        for t in range(k_num):
+            g = h0 if t == 0 else h1 if t == 1 else ((h0 + t * h1) & ((1 << 64) - 1)) % P
+            b = g % bits
+            words[b >> 5] |= np.uint32(1 << (b & 31))
+    out = bytearray()
+    out += n_words.to_bytes(8, "little") + words.astype("<u4").tobytes()
+    out += bits.to_bytes(8, "little") + bits.to_bytes(8, "little") + k_num.to_bytes(4, "little")
+    for q in (0, 2):
+        k0, k1 = sk[q], sk[q + 1]
+        fresh = [k0, k1, 0, k0 ^ 0x736F6D6570736575, k0 ^ 0x6C7967656E657261, k1 ^ 0x646F72616E646F6D, k1 ^ 0x7465646279746573, 0, 0]
+        out += b"".join(v.to_bytes(8, "little") for v in fresh)
+    assert bytes(bloom) == bytes(out)
