@@ -633,6 +633,14 @@ def mem_available_bytes() -> int:
     return 64 << 30
 
 
+def ref_jobs_per_step(threads: int, floor_threads: int, t_cal: float, steps: int, warm: int, budget_s: float) -> int:
+    """Concurrent full-size jobs per step of the reference arm: `floor_threads` of them took t_cal seconds; at that (memory-
+    bandwidth-bound) rate a step of n jobs takes n * t_cal / floor_threads, and steps + warm of them have to fit budget_s."""
+    per_job_s = max(1e-3, t_cal / floor_threads)
+    fit = int(budget_s / max(1, steps + warm) / per_job_s)
+    return max(floor_threads, min(threads, fit))
+
+
 def run_reference(args):
     """The reference's CPU implementation of the path on this box's host cores: the C oracle port of LSMTree::compact
     (the Rust reference cannot be built here: no cargo/rustc), one single-threaded FULL-SIZE shard compaction per core,
@@ -672,6 +680,23 @@ def run_reference(args):
         for th in ts:
             th.join()
 
+    # The whole --steps K --warmup W run has to end within a few minutes (DBEEL_REF_BUDGET_S, default 210 s of stepping): a step
+    # is `threads` concurrent FULL jobs, and 64 of them take ~38 s on this host (the path is memory-bandwidth-bound: 64 threads
+    # deliver what ~8 do), so the number of concurrent jobs per step is cut to what fits -- never below the 8 jobs of one GPU
+    # step.  Calibration: the step's own 8 jobs on 8 threads, untimed.
+    budget_s = float(os.environ.get("DBEEL_REF_BUDGET_S", "210"))
+    floor_threads = min(threads, N_JOBS)
+    if threads > floor_threads:
+        full = shards
+        shards = full[:floor_threads]
+        t_cal = time.perf_counter()
+        step()
+        t_cal = time.perf_counter() - t_cal
+        threads = ref_jobs_per_step(threads, floor_threads, t_cal, steps, warm, budget_s)
+        shards = full[:threads]
+        in_bytes = sum(sstable.input_bytes(s) for s in shards)
+        log(f"[bench ref] calibration: {floor_threads} concurrent jobs in {t_cal:.1f}s -> {threads} concurrent jobs per step "
+            f"for {steps}+{warm} steps in ~{budget_s:.0f}s")
     for _ in range(warm):
         step()
     t0 = time.perf_counter()
@@ -683,7 +708,8 @@ def run_reference(args):
     t1 = time.perf_counter()
     one(shards[0])
     alone = sstable.input_bytes(shards[0]) / 1e6 / (time.perf_counter() - t1)
-    sample = (f"{threads} concurrent single-threaded shard compactions per step, each the FULL job of the GPU arm's config "
+    sample = (f"{threads} concurrent single-threaded shard compactions per step (as many as fit {steps}+{warm} steps into ~{budget_s:.0f} s, at least "
+              f"the {N_JOBS} jobs of one GPU step; the path is memory-bandwidth-bound beyond ~8 threads), each the FULL job of the GPU arm's config "
               f"(8 runs x 1,000,000 keys x 256 B docs, seeds 40+i; {in_bytes / 1e6:.0f} MB in per step), RAM-resident files, "
               "page-cache write-through copies emulated")
     cfg_line = common_config()

@@ -55,3 +55,16 @@ def test_single_process_is_a_no_op():
     assert sj.world() == 1 and sj.rank() == 0 and sj.owner_of(5, 4) == 1
     assert sj.reduce_report({"ms": 1.0}, torch.device("cpu"), ["ms"], []) == {"ms": 1.0}
     assert sj.ShardJob.from_row(jobs[1].as_row()) == jobs[1]
+
+
+def test_reference_arm_fits_its_steps_into_the_budget():
+    """bench.py --impl reference: the number of concurrent full-size jobs per step is cut so that K + W steps end within the
+    budget, never below the 8 jobs of one GPU step, never above the host's threads."""
+    import bench
+    # 8 concurrent jobs took 5 s: 0.625 s per job; 20 + 5 steps in 210 s -> 8.4 s per step -> 13 jobs
+    assert bench.ref_jobs_per_step(64, 8, 5.0, 20, 5, 210.0) == 13
+    # a short run has room for every thread
+    assert bench.ref_jobs_per_step(64, 8, 5.0, 3, 1, 210.0) == 64
+    # a slow host never drops below one GPU step's jobs
+    assert bench.ref_jobs_per_step(64, 8, 60.0, 20, 5, 210.0) == 8
+    assert bench.ref_jobs_per_step(4, 4, 60.0, 20, 5, 210.0) == 4
