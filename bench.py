@@ -275,7 +275,7 @@ def file_fed_job(eng, expected):
         shutil.rmtree(root, ignore_errors=True)
 
 
-def other_configs(eng, torch, dev, peak, job0_expected=None):
+def other_configs(eng, torch, dev, peak):
     """Evidence for the configs that are not the headline, outside every timed headline region (rank 0, N = 1)."""
     import oracle
     from dbeel_b200 import capi, sstable
@@ -303,9 +303,13 @@ def other_configs(eng, torch, dev, peak, job0_expected=None):
     log(f"[bench] other configs: cfg1 parity {out['cfg1']['parity_vs_oracle']}, cfg3 {out['cfg3']['ms_per_step']} ms/step "
         f"parity {out['cfg3']['parity_vs_oracle']} ({time.time() - t:.0f}s)")
     del runs, got, exp
-    try:  # row N3: the headline job file to file
+    try:  # row N3: the headline job file to file -- in a child process with a deadline, so that nothing on that path (threads,
+        # files, a full tmpfs) can take the headline line down with it
+        import subprocess
         t = time.time()
-        out["file_fed"] = file_fed_job(eng, job0_expected)
+        cp = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "file_fed.py"), "--parity"], capture_output=True, text=True, timeout=240)
+        lines = [ln for ln in cp.stdout.splitlines() if ln.startswith("{")]
+        out["file_fed"] = json.loads(lines[-1]) if cp.returncode == 0 and lines else {"error": f"rc {cp.returncode}: {cp.stderr[-300:]}"}
         log(f"[bench] file-fed job: {out['file_fed']} ({time.time() - t:.0f}s)")
     except Exception as ex:  # pragma: no cover
         out["file_fed"] = {"error": repr(ex)}
@@ -555,7 +559,7 @@ def run_gpu(args):
     others = None
     if rank == 0 and world == 1 and not args.no_cpu and args.workload == "cfg2" and not args.no_others:
         del pins, h_jobs, jobs_runs
-        others = other_configs(eng, torch, dev, peak, job0_expected=first)
+        others = other_configs(eng, torch, dev, peak)
 
     if rank != 0:
         if world > 1:
